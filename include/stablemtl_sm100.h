@@ -1,0 +1,315 @@
+/*
+ * stablemtl_sm100.h -- C ABI of libstablemtl_sm100.so: the B200 (sm_100a) kernels behind the
+ * single-step latent pass of StableMTLPipeline (VAE encode -> SD-2 UNet [+ task attention] -> VAE decode).
+ *
+ * The reference has no FFI of its own (it is pure Python on top of torch/cuDNN/cuBLAS/xformers), so every
+ * entry point below names the reference call site (file:line under /root/reference) whose library kernel it
+ * replaces.  Conventions:
+ *   - plain pointers + sizes only; all pointers are DEVICE pointers unless a name ends in _host;
+ *   - every function returns 0 on success and a negative SMTL_E* code on failure (no exceptions cross the
+ *     ABI); smtl_last_error() returns a thread-local message for the last failure;
+ *   - no allocation inside: the caller owns every buffer, scratch included;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous and thread-safe w.r.t. distinct
+ *     streams; there is no global mutable state;
+ *   - activations are pixel-major ("NHWC"): a feature map is a row-major matrix [B*H*W, C]
+ *       compact layout : row = (b*H + y)*W + x                  fp32 residual stream / bf16 tokens
+ *       padded  layout : row = (b*(H+2) + y+1)*(W+2) + x+1      bf16, 1-pixel zero halo (conv operand)
+ *   - weights are bf16 [N, K] K-major; conv filters are [Cout, tap*Cin + c], tap = ky*3 + kx.
+ */
+#ifndef STABLEMTL_SM100_H
+#define STABLEMTL_SM100_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMTL_ABI_VERSION 1
+
+enum {
+    SMTL_OK = 0,
+    SMTL_EINVAL = -1,   /* bad argument (shape/alignment/NULL) */
+    SMTL_ECUDA = -2,    /* CUDA runtime / driver error */
+    SMTL_ENODEV = -3,   /* no sm_100 device / driver entry point missing */
+    SMTL_EKIND = -4     /* unknown op kind in a plan */
+};
+
+enum { SMTL_ACT_NONE = 0, SMTL_ACT_GELU = 1, SMTL_ACT_GEGLU = 2, SMTL_ACT_SILU = 3 };
+enum { SMTL_ROWMAP_IDENTITY = 0, SMTL_ROWMAP_CONV_PAD = 1 };
+
+#define SMTL_MAX_SEG 12
+#define SMTL_MAX_TASKS 8
+
+/* ------------------------------------------------------------------------------------------------ GEMM / conv
+ * D[m, n] = sum over K segments of A_src[m + row_shift, a_col0 + kk] * B[n, kbase + kk]
+ * One tcgen05 kernel (TMA-fed, TMEM accumulators) serves
+ *   - token linears                    nn.Linear                 src/model/attention.py:185,191,210,212,442-451,460
+ *                                      diffusers FeedForward     src/model/attention.py:285,372
+ *                                      task MLP / MLPv2          src/model/attention.py:494-495,512,598
+ *   - 3x3 stride-1 convs as implicit GEMM over the padded layout (9 row-shifted K segments)
+ *                                      InflatedConv3d            src/model/resnet.py:14-16,143,159
+ *   - 1x1 shortcut fused as a 10th K segment read from a second source   src/model/resnet.py:172,200
+ *   - the VAE convs / attention projections (diffusers AutoencoderKL)    src/stablemtl_pipeline.py:619-620,642-643
+ * Epilogue (fused): v = act(acc + bias); aux_bf16 = v; v += res1 + res2; out_f32 = v; out_bf16 = v.
+ */
+typedef struct smtl_gemm_seg {
+    int32_t row_shift;  /* added to the GEMM row to get the A row (may be negative; OOB rows read as 0) */
+    int32_t kblocks;    /* number of 64-wide K blocks in this segment */
+    int32_t src;        /* 0: a0, 1: a1 */
+    int32_t a_col0;     /* first A column of the segment */
+} smtl_gemm_seg;
+
+typedef struct smtl_gemm_args {
+    const void* a0;     /* bf16 [a0_rows, a0_cols], leading dim a0_ld (elements) */
+    const void* a1;     /* optional second A source */
+    const void* b;      /* bf16 [n, k], leading dim ldb */
+    int64_t a0_rows, a1_rows;
+    int32_t a0_cols, a1_cols;
+    int32_t a0_ld, a1_ld;
+    int64_t m;          /* GEMM rows */
+    int32_t n, k, ldb;
+    int32_t nseg;       /* 0 => one segment covering k from a0 */
+    smtl_gemm_seg seg[SMTL_MAX_SEG];
+    const float* bias;  /* fp32 [n] (or [m] if bias_per_row) or NULL */
+    int32_t bias_per_row;
+    int32_t act;        /* SMTL_ACT_*; GEGLU: B rows are tile-interleaved value|gate, output has n/2 columns */
+    const float* res1;  /* fp32 [out_rows, n_out] residuals, leading dim ldres, or NULL */
+    const float* res2;
+    int32_t ldres;
+    float* out_f32;     /* any subset of the three outputs may be NULL */
+    void* out_bf16;
+    void* aux_bf16;     /* value before the residual add (child-UNet feature tap, attention.py:348-349) */
+    int32_t ldc;        /* leading dim of out_f32 / out_bf16 */
+    int32_t ld_aux;
+    int32_t rowmap;     /* SMTL_ROWMAP_CONV_PAD: GEMM row = padded pixel, output row = compact pixel; halo rows dropped */
+    int32_t img_h, img_w; /* interior size for the conv row map (padded size is +2) */
+    int32_t block_n;    /* 0 = auto; else 32/64/128/256 */
+} smtl_gemm_args;
+
+typedef struct smtl_gemm_op {
+    smtl_gemm_args args;
+    uint64_t tmap_a0[16];   /* CUtensorMap images (128 B each) */
+    uint64_t tmap_a1[16];
+    uint64_t tmap_b[16];
+    int32_t block_n;
+    int32_t grid;
+    int32_t tiles_m, tiles_n;
+    int32_t total_kblocks;
+    int32_t smem_bytes;
+} smtl_gemm_op;
+
+int smtl_gemm_plan(const smtl_gemm_args* args, smtl_gemm_op* op);
+int smtl_gemm_run(const smtl_gemm_op* op, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ attention
+ * Flash-style self-attention, head dim 64, softmax in fp32, tcgen05 for QK^T and PV.
+ * Replaces xformers.ops.memory_efficient_attention at src/model/attention.py:391-397,417.
+ * q/k/v live in one bf16 matrix [batch*ntok, ld] (the fused QKV projection) at column offsets *_col0 + head*64.
+ */
+typedef struct smtl_fattn_args {
+    const void* qkv;
+    int32_t ld;
+    int32_t q_col0, k_col0, v_col0;
+    int32_t batch, ntok, heads;
+    void* out_bf16;     /* [batch*ntok, ldo], head h at columns h*64 */
+    int32_t ldo;
+    float scale;        /* 1/sqrt(64) */
+} smtl_fattn_args;
+
+typedef struct smtl_fattn_op {
+    smtl_fattn_args args;
+    uint64_t tmap_qkv[16];
+    int32_t grid_x, grid_y;
+    int32_t smem_bytes;
+    int32_t pad_;
+} smtl_fattn_op;
+
+int smtl_fattn_plan(const smtl_fattn_args* args, smtl_fattn_op* op);
+int smtl_fattn_run(const smtl_fattn_op* op, void* stream);
+
+/* Row softmax fp32 -> bf16 probabilities (VAE mid-block single-head attention, d = 512;
+ * diffusers Attention inside AutoencoderKL, reached from src/stablemtl_pipeline.py:619,643). */
+typedef struct smtl_softmax_args {
+    const float* s;
+    int64_t rows;
+    int32_t n, lds;
+    float scale;
+    void* p_bf16;
+    int32_t ldp;
+} smtl_softmax_args;
+int smtl_softmax_run(const smtl_softmax_args* a, void* stream);
+
+/* Cross-attention on <= 4 constant text tokens (diffusers Attention as attn2, src/model/attention.py:267-275,360-362).
+ * kc/vc are the pre-projected keys/values to_k(text), to_v(text): fp32 [ntask, 4, heads*64]. */
+typedef struct smtl_xattn_args {
+    const void* q_bf16;
+    int32_t ldq;
+    int64_t rows;
+    int32_t heads;
+    const float* kc;
+    const float* vc;
+    int32_t ntok[SMTL_MAX_TASKS];
+    int32_t task_of_group[SMTL_MAX_TASKS]; /* row group g = row / rows_per_group uses text of task_of_group[g] */
+    int64_t rows_per_group;
+    void* out_bf16;
+    int32_t ldo;
+    float scale;
+} smtl_xattn_args;
+int smtl_xattn_run(const smtl_xattn_args* a, void* stream);
+
+/* Per-pixel cross-task attention (src/model/attention.py:500-519,553-597): Nq = 1, Nk = number of other task
+ * streams, nheads heads of c/nheads channels. q rows are (main task group, image, pixel); k/v rows are
+ * (source task group, image, pixel). */
+typedef struct smtl_taskattn_args {
+    const void* q_bf16;
+    const void* k_bf16;
+    const void* v_bf16;
+    void* out_bf16;
+    int32_t c, nheads;
+    int32_t n_main, n_src;
+    int64_t rows_per_group;                 /* images * tokens */
+    int32_t main_task[SMTL_MAX_TASKS];      /* task id of each q row group */
+    int32_t src_task[SMTL_MAX_TASKS];       /* task id of each k/v row group */
+    int32_t exclude_self;                   /* skip src whose task id equals the row's main task (stablemtl_pipeline.py:483-484) */
+    float scale;                            /* 1/sqrt(c/nheads) */
+} smtl_taskattn_args;
+int smtl_taskattn_run(const smtl_taskattn_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ normalisation
+ * GroupNorm statistics + apply (+SiLU) over a (virtually concatenated) fp32 compact map, emitting the bf16
+ * operand of the next GEMM/conv.  Replaces torch GroupNorm + F.silu + torch.cat at
+ * src/model/resnet.py:177-178,188,194, src/model/attention.py:183, src/model/unet.py:438-439,
+ * src/model/unet_blocks.py:509,597 and the GroupNorms of diffusers' VAE blocks.
+ */
+typedef struct smtl_gn_args {
+    const float* x0;
+    const float* x1;        /* second source of a channel concat, or NULL */
+    int32_t c0, c1;
+    int32_t batch, h, w;
+    int32_t groups;
+    float eps;
+    float* partial;         /* scratch fp32 [batch, nchunk, groups, 2] */
+    int32_t nchunk;
+    const float* gamma;
+    const float* beta;
+    int32_t silu;
+    int32_t pad_out;        /* 1: padded layout with zero halo, 0: compact */
+    void* out_bf16;
+    void* raw_bf16;         /* optional un-normalised bf16 copy, same layout (1x1 shortcut operand) */
+} smtl_gn_args;
+int smtl_gn_run(const smtl_gn_args* a, void* stream);
+
+/* LayerNorm over the channel dim, fp32 or bf16 in, bf16 out; up to two affine outputs from one pass and
+ * per-row-group affine parameters (task_norm_{q,k,v}[task], src/util/model.py:133-138).
+ * Replaces nn.LayerNorm at src/model/attention.py:338,358,372,494-495,512. */
+typedef struct smtl_ln_args {
+    const void* x;
+    int32_t x_is_bf16;
+    int32_t c, ldx;
+    int64_t rows;
+    float eps;
+    int64_t rows_per_group; /* affine set index = row / rows_per_group (use rows for a single set) */
+    const float* gamma0;    /* [ngroup, c] */
+    const float* beta0;
+    void* out0;
+    const float* gamma1;    /* optional second affine/output */
+    const float* beta1;
+    void* out1;
+    int32_t ldo;
+    int32_t pad_;
+} smtl_ln_args;
+int smtl_ln_run(const smtl_ln_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ data movement
+ * Nearest upsample (x2 or explicit size: src = floor(dst * in/out)) fused with the bf16 cast and the zero halo
+ * of the following 3x3 conv.  Replaces F.interpolate at src/model/resnet.py:58-61. */
+typedef struct smtl_upsample_args {
+    const float* x;
+    int32_t batch, h, w, c;
+    int32_t oh, ow;
+    void* out_bf16;         /* padded layout [batch, oh+2, ow+2, c] */
+} smtl_upsample_args;
+int smtl_upsample_run(const smtl_upsample_args* a, void* stream);
+
+/* Explicit im2col (bf16) for the few convs the shifted-GEMM form does not cover: stride-2 downsamplers
+ * (src/model/resnet.py:87,105; diffusers Downsample2D with (0,1,0,1) padding) and tiny-Cin stems (conv_in). */
+typedef struct smtl_im2col_args {
+    const float* x;         /* compact fp32 [batch, h, w, c] */
+    int32_t batch, h, w, c;
+    int32_t stride, pad_t, pad_l;
+    int32_t oh, ow;
+    int32_t kpad;           /* row length of the output (>= 9*c, multiple of 64, zero filled) */
+    void* out_bf16;         /* [batch*oh*ow, kpad] */
+} smtl_im2col_args;
+int smtl_im2col_run(const smtl_im2col_args* a, void* stream);
+
+/* [0,255] NCHW rgb -> [-1,1] NHWC fp32 (src/stablemtl_pipeline.py:263). */
+typedef struct smtl_rgbprep_args {
+    const float* rgb_nchw;
+    int32_t batch, h, w;
+    float* out_nhwc;
+} smtl_rgbprep_args;
+int smtl_rgbprep_run(const smtl_rgbprep_args* a, void* stream);
+
+/* UNet input assembly (src/stablemtl_pipeline.py:431-450,557-558,582-584): row group g of the output takes its
+ * first 4 channels from latent image first_img[g*images + i], the next 4 from second_img[...], last 4 = 0. */
+typedef struct smtl_unetin_args {
+    const float* latents;   /* fp32 [n_lat_images, hw, 4] */
+    const int32_t* first_img;   /* device int32 [out_images] */
+    const int32_t* second_img;  /* device int32 [out_images] */
+    int32_t out_images, hw;
+    float* out;             /* fp32 [out_images, hw, 12] */
+} smtl_unetin_args;
+int smtl_unetin_run(const smtl_unetin_args* a, void* stream);
+
+/* Task-map epilogue (src/stablemtl_pipeline.py:601,645-654 and the post-processing at :297-366):
+ * x is the VAE decoder output fp32 [batch, hw, 3]. */
+enum {
+    SMTL_MAP_MEAN1 = 0,     /* depth / shading: mean over 3 channels, clip; post = (x+1)/2 */
+    SMTL_MAP_RGB3 = 1,      /* albedo: clip; post = (x+1)/2 */
+    SMTL_MAP_NORMAL = 2,    /* normal: clip; post = x / max(|x|,0->1) */
+    SMTL_MAP_FLOW2 = 3,     /* optical flow: first 2 channels, clip */
+    SMTL_MAP_FLOW3 = 4,     /* scene flow: 3 channels, clip */
+    SMTL_MAP_SEMANTIC = 5   /* semantic: clip; post = argmin_k |x - palette_k| (first index wins ties) */
+};
+typedef struct smtl_taskmap_args {
+    const float* x;
+    int32_t batch, hw, mode;
+    float* out_clipped;     /* optional: [batch, cout, hw] planar = single_infer() result */
+    float* out_post;        /* optional: [batch, cout, hw] planar post-processed map */
+    int64_t* out_ids;       /* semantic only: [batch, hw] */
+    const float* palette;   /* semantic only: fp32 [npalette, 3] already mapped to [-1,1] */
+    int32_t npalette;
+    int32_t pad_;
+} smtl_taskmap_args;
+int smtl_taskmap_run(const smtl_taskmap_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ plans
+ * A plan is an array of (kind, pointer-to-op-struct); smtl_run_plan launches them in order on one stream
+ * from native code, so a whole UNet/VAE pass costs one call across the ABI (and can be stream-captured
+ * into a CUDA graph by the caller). */
+enum {
+    SMTL_OP_GEMM = 1, SMTL_OP_FATTN = 2, SMTL_OP_SOFTMAX = 3, SMTL_OP_XATTN = 4, SMTL_OP_TASKATTN = 5,
+    SMTL_OP_GN = 6, SMTL_OP_LN = 7, SMTL_OP_UPSAMPLE = 8, SMTL_OP_IM2COL = 9, SMTL_OP_RGBPREP = 10,
+    SMTL_OP_UNETIN = 11, SMTL_OP_TASKMAP = 12
+};
+typedef struct smtl_op_ref {
+    int32_t kind;
+    int32_t pad_;
+    const void* op;
+} smtl_op_ref;
+int smtl_run_plan(const smtl_op_ref* ops, int32_t n_ops, void* stream);
+/* number of kernel launches smtl_run_plan(ops) performs (a GN op is two kernels) */
+int smtl_plan_launches(const smtl_op_ref* ops, int32_t n_ops);
+
+/* ------------------------------------------------------------------------------------------------ misc */
+int smtl_abi_version(void);
+const char* smtl_last_error(void);
+/* sizeof() of every struct above, in declaration order, for binding self-checks; returns the count written */
+int smtl_struct_sizes(int32_t* out, int32_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STABLEMTL_SM100_H */

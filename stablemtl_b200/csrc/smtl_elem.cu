@@ -1,0 +1,678 @@
+// smtl_elem.cu -- the HBM-bound kernels of the StableMTL hot path: GroupNorm / LayerNorm, layout producers
+// (zero-halo padding, nearest upsample, im2col, UNet-input assembly), small-key attentions and the task-map
+// epilogue.  All are coalesced 16-byte-per-thread streaming kernels with warp-shuffle reductions.
+#include "smtl_common.cuh"
+#include "smtl_host.h"
+
+namespace {
+using namespace smtl;
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// ============================================================================================= GroupNorm
+// stats: grid (nchunk, batch); block = (C/4) * rows_par threads; thread owns 4 fixed channels.
+__global__ void gn_stats_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int c0, int c1, int hw,
+                                int groups, int nchunk, float* __restrict__ partial) {
+    extern __shared__ float sm[];   // [2*groups]
+    const int C = c0 + c1;
+    const int cv = C >> 2;
+    const int rows_par = blockDim.x / cv;
+    const int cvec = threadIdx.x % cv;
+    const int rlane = threadIdx.x / cv;
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int per = (hw + nchunk - 1) / nchunk;
+    const int p_begin = chunk * per;
+    const int p_end = min(hw, p_begin + per);
+    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    const int c = cvec * 4;
+    const float* src;
+    int ld, cc;
+    if (c < c0) { src = x0; ld = c0; cc = c; } else { src = x1; ld = c1; cc = c - c0; }
+    float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+    if (rlane < rows_par) {
+        const float* base = src + ((int64_t)b * hw) * ld + cc;
+        for (int p = p_begin + rlane; p < p_end; p += rows_par) {
+            const float4 v = ldg4(base + (int64_t)p * ld);
+            s[0] += v.x; q[0] += v.x * v.x;
+            s[1] += v.y; q[1] += v.y * v.y;
+            s[2] += v.z; q[2] += v.z * v.z;
+            s[3] += v.w; q[3] += v.w * v.w;
+        }
+        const int cpg = C / groups;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int g = (c + i) / cpg;
+            atomicAdd(&sm[2 * g], s[i]);
+            atomicAdd(&sm[2 * g + 1], q[i]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x)
+        partial[((int64_t)(b * nchunk + chunk) * groups) * 2 + i] = sm[i];
+}
+
+// apply: grid (blocks_per_image, batch), 256 threads, thread handles 8 channels of one (padded) pixel per step.
+__global__ void gn_apply_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int c0, int c1, int h, int w,
+                                int groups, float eps, const float* __restrict__ partial, int nchunk,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu, int pad_out,
+                                __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ raw) {
+    extern __shared__ float sm[];   // scale[C], shift[C], mean[groups], rstd[groups]
+    const int C = c0 + c1;
+    float* scale = sm;
+    float* shift = sm + C;
+    float* gmean = sm + 2 * C;
+    float* grstd = gmean + groups;
+    const int b = blockIdx.y;
+    const int hw = h * w;
+    const int cpg = C / groups;
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        double s = 0.0, q = 0.0;
+        for (int k = 0; k < nchunk; ++k) {
+            const float* pp = partial + ((int64_t)(b * nchunk + k) * groups + g) * 2;
+            s += (double)pp[0];
+            q += (double)pp[1];
+        }
+        const double n = (double)hw * cpg;
+        const double mean = s / n;
+        double var = q / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        gmean[g] = (float)mean;
+        grstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const float sc = grstd[g] * gamma[c];
+        scale[c] = sc;
+        shift[c] = beta[c] - gmean[g] * sc;
+    }
+    __syncthreads();
+    const int cv8 = C >> 3;
+    const int hp = pad_out ? h + 2 : h, wp = pad_out ? w + 2 : w;
+    const int64_t total = (int64_t)hp * wp * cv8;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int pix = (int)(idx / cv8);
+        const int c = (int)(idx - (int64_t)pix * cv8) * 8;
+        int y = pix / wp, x = pix - y * wp;
+        uint4 o = make_uint4(0, 0, 0, 0), r = make_uint4(0, 0, 0, 0);
+        bool interior = true;
+        if (pad_out) {
+            interior = (y >= 1 && y <= h && x >= 1 && x <= w);
+            y -= 1; x -= 1;
+        }
+        if (interior) {
+            const float* src;
+            int ld, cc;
+            if (c < c0) { src = x0; ld = c0; cc = c; } else { src = x1; ld = c1; cc = c - c0; }
+            const float* ptr = src + ((int64_t)b * hw + (int64_t)y * w + x) * ld + cc;
+            const float4 a = ldg4(ptr), bb = ldg4(ptr + 4);
+            float v[8] = {a.x, a.y, a.z, a.w, bb.x, bb.y, bb.z, bb.w};
+            if (raw) {
+                r.x = pack_bf16x2(v[0], v[1]); r.y = pack_bf16x2(v[2], v[3]);
+                r.z = pack_bf16x2(v[4], v[5]); r.w = pack_bf16x2(v[6], v[7]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float t = v[i] * scale[c + i] + shift[c + i];
+                if (do_silu) t = silu(t);
+                v[i] = t;
+            }
+            o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+            o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+        }
+        const int64_t orow = (int64_t)b * hp * wp + pix;
+        *reinterpret_cast<uint4*>(out + orow * C + c) = o;
+        if (raw) *reinterpret_cast<uint4*>(raw + orow * C + c) = r;
+    }
+}
+
+// ============================================================================================= LayerNorm
+// one warp per row; lane holds up to 10 float4 (C <= 1280).
+template <bool IN_BF16>
+__global__ void ln_kernel(const void* __restrict__ xv, int c, int ldx, int64_t rows, float eps, int64_t rows_per_group,
+                          const float* __restrict__ gamma0, const float* __restrict__ beta0,
+                          __nv_bfloat16* __restrict__ out0, const float* __restrict__ gamma1,
+                          const float* __restrict__ beta1, __nv_bfloat16* __restrict__ out1, int ldo) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const int nv = c >> 2;
+    float4 v[10];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const int j = lane + 32 * i;
+        if (j < nv) {
+            if (IN_BF16) {
+                const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(xv) +
+                                                                     row * ldx + 4 * j));
+                const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+                v[i] = make_float4(a.x, a.y, b.x, b.y);
+            } else {
+                v[i] = ldg4(reinterpret_cast<const float*>(xv) + row * ldx + 4 * j);
+            }
+            s += v[i].x + v[i].y + v[i].z + v[i].w;
+        }
+    }
+    const float mean = warp_sum(s) / (float)c;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const int j = lane + 32 * i;
+        if (j < nv) {
+            const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+            q += a * a + b * b + cc * cc + d * d;
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)c + eps);
+    const int64_t grp = row / rows_per_group;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const int j = lane + 32 * i;
+        if (j < nv) {
+            const float n0 = (v[i].x - mean) * rstd, n1 = (v[i].y - mean) * rstd, n2 = (v[i].z - mean) * rstd,
+                        n3 = (v[i].w - mean) * rstd;
+            {
+                const float4 g = ldg4(gamma0 + grp * c + 4 * j), b = ldg4(beta0 + grp * c + 4 * j);
+                uint2 o;
+                o.x = pack_bf16x2(n0 * g.x + b.x, n1 * g.y + b.y);
+                o.y = pack_bf16x2(n2 * g.z + b.z, n3 * g.w + b.w);
+                *reinterpret_cast<uint2*>(out0 + row * ldo + 4 * j) = o;
+            }
+            if (out1) {
+                const float4 g = ldg4(gamma1 + grp * c + 4 * j), b = ldg4(beta1 + grp * c + 4 * j);
+                uint2 o;
+                o.x = pack_bf16x2(n0 * g.x + b.x, n1 * g.y + b.y);
+                o.y = pack_bf16x2(n2 * g.z + b.z, n3 * g.w + b.w);
+                *reinterpret_cast<uint2*>(out1 + row * ldo + 4 * j) = o;
+            }
+        }
+    }
+}
+
+// ============================================================================================= layout producers
+__global__ void upsample_pad_kernel(const float* __restrict__ x, int batch, int h, int w, int c, int oh, int ow,
+                                    __nv_bfloat16* __restrict__ out) {
+    const int cv8 = c >> 3;
+    const int hp = oh + 2, wp = ow + 2;
+    const int64_t total = (int64_t)batch * hp * wp * cv8;
+    const float sy = (float)h / (float)oh, sx = (float)w / (float)ow;   // ATen nearest: src = min(floor(dst*scale), in-1)
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pix = idx / cv8;
+        const int cc = (int)(idx - pix * cv8) * 8;
+        const int b = (int)(pix / (hp * wp));
+        const int rem = (int)(pix - (int64_t)b * hp * wp);
+        const int yp = rem / wp, xp = rem - yp * wp;
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (yp >= 1 && yp <= oh && xp >= 1 && xp <= ow) {
+            const int ysrc = min((int)floorf((float)(yp - 1) * sy), h - 1);
+            const int xsrc = min((int)floorf((float)(xp - 1) * sx), w - 1);
+            const float* ptr = x + (((int64_t)b * h + ysrc) * w + xsrc) * c + cc;
+            const float4 a = ldg4(ptr), bb = ldg4(ptr + 4);
+            o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
+            o.z = pack_bf16x2(bb.x, bb.y); o.w = pack_bf16x2(bb.z, bb.w);
+        }
+        *reinterpret_cast<uint4*>(out + pix * c + cc) = o;
+    }
+}
+
+// im2col, 8 channels per thread (c % 8 == 0, kpad == 9*c)
+__global__ void im2col_vec8_kernel(const float* __restrict__ x, int batch, int h, int w, int c, int stride, int pad_t,
+                                   int pad_l, int oh, int ow, __nv_bfloat16* __restrict__ out) {
+    const int cv8 = c >> 3;
+    const int64_t total = (int64_t)batch * oh * ow * 9 * cv8;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int cc = (int)(idx % cv8) * 8;
+        int64_t t = idx / cv8;
+        const int tap = (int)(t % 9);
+        const int64_t opix = t / 9;
+        const int b = (int)(opix / (oh * ow));
+        const int rem = (int)(opix - (int64_t)b * oh * ow);
+        const int oy = rem / ow, ox = rem - oy * ow;
+        const int iy = oy * stride - pad_t + tap / 3, ix = ox * stride - pad_l + tap % 3;
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (iy >= 0 && iy < h && ix >= 0 && ix < w) {
+            const float* ptr = x + (((int64_t)b * h + iy) * w + ix) * c + cc;
+            const float4 a = ldg4(ptr), bb = ldg4(ptr + 4);
+            o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
+            o.z = pack_bf16x2(bb.x, bb.y); o.w = pack_bf16x2(bb.z, bb.w);
+        }
+        *reinterpret_cast<uint4*>(out + opix * (int64_t)(9 * c) + tap * c + cc) = o;
+    }
+}
+// im2col, scalar (tiny Cin stems: 3 or 12 channels), zero-fills k in [9c, kpad)
+__global__ void im2col_scalar_kernel(const float* __restrict__ x, int batch, int h, int w, int c, int stride, int pad_t,
+                                     int pad_l, int oh, int ow, int kpad, __nv_bfloat16* __restrict__ out) {
+    const int64_t total = (int64_t)batch * oh * ow * kpad;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(idx % kpad);
+        const int64_t opix = idx / kpad;
+        float v = 0.f;
+        if (k < 9 * c) {
+            const int tap = k / c, cc = k - tap * c;
+            const int b = (int)(opix / (oh * ow));
+            const int rem = (int)(opix - (int64_t)b * oh * ow);
+            const int oy = rem / ow, ox = rem - oy * ow;
+            const int iy = oy * stride - pad_t + tap / 3, ix = ox * stride - pad_l + tap % 3;
+            if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = __ldg(x + (((int64_t)b * h + iy) * w + ix) * c + cc);
+        }
+        out[idx] = __float2bfloat16(v);
+    }
+}
+
+__global__ void rgbprep_kernel(const float* __restrict__ rgb, int batch, int hw, float* __restrict__ out) {
+    const int64_t total = (int64_t)batch * hw;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = idx / hw, p = idx - b * hw;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const float v = __ldg(rgb + (b * 3 + ch) * hw + p);
+            out[idx * 3 + ch] = v / 255.0f * 2.0f - 1.0f;   // same op order as stablemtl_pipeline.py:263
+        }
+    }
+}
+
+__global__ void unetin_kernel(const float* __restrict__ lat, const int* __restrict__ first_img,
+                              const int* __restrict__ second_img, int out_images, int hw, float* __restrict__ out) {
+    const int64_t total = (int64_t)out_images * hw;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int img = (int)(idx / hw);
+        const int p = (int)(idx - (int64_t)img * hw);
+        const float4 a = ldg4(lat + ((int64_t)first_img[img] * hw + p) * 4);
+        const float4 b = ldg4(lat + ((int64_t)second_img[img] * hw + p) * 4);
+        float4* o = reinterpret_cast<float4*>(out + idx * 12);
+        o[0] = a;
+        o[1] = b;
+        o[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// ============================================================================================= small attentions
+// row softmax fp32 -> bf16 (n <= 8192), one CTA of 256 threads per row
+__global__ void softmax_rows_kernel(const float* __restrict__ s, int n, int lds, float scale,
+                                    __nv_bfloat16* __restrict__ p, int ldp) {
+    __shared__ float red[8];
+    const int64_t row = blockIdx.x;
+    const float* src = s + row * lds;
+    float v[32];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const int j = threadIdx.x + i * 256;
+        v[i] = (j < n) ? src[j] * scale : -INFINITY;
+        mx = fmaxf(mx, v[i]);
+    }
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+    __syncthreads();
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const int j = threadIdx.x + i * 256;
+        if (j < n) { v[i] = __expf(v[i] - mx); sum += v[i]; }
+    }
+    sum = warp_sum(sum);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += red[i];
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const int j = threadIdx.x + i * 256;
+        if (j < n) p[row * ldp + j] = __float2bfloat16(v[i] * inv);
+    }
+}
+
+struct XattnK {
+    int ntok[SMTL_MAX_TASKS];
+    int task_of_group[SMTL_MAX_TASKS];
+};
+// cross-attention on <= 4 constant keys: one warp per token row, lane owns 2 of the 64 head dims
+__global__ void xattn_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int64_t rows, int heads,
+                             const float* __restrict__ kc, const float* __restrict__ vc, XattnK tk,
+                             int64_t rows_per_group, __nv_bfloat16* __restrict__ out, int ldo, float scale) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const int grp = (int)(row / rows_per_group);
+    const int task = tk.task_of_group[grp];
+    const int nt = tk.ntok[task];
+    const int C = heads * 64;
+    const float* kbase = kc + (int64_t)task * 4 * C;
+    const float* vbase = vc + (int64_t)task * 4 * C;
+    for (int hd = 0; hd < heads; ++hd) {
+        const int col = hd * 64 + 2 * lane;
+        const float2 qv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(q + row * ldq + col));
+        float sc[4];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float d = 0.f;
+            if (j < nt) {
+                const float2 kv = __ldg(reinterpret_cast<const float2*>(kbase + j * C + col));
+                d = qv.x * kv.x + qv.y * kv.y;
+            }
+            d = warp_sum(d) * scale;
+            sc[j] = (j < nt) ? d : -INFINITY;
+            mx = fmaxf(mx, sc[j]);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { sc[j] = (j < nt) ? __expf(sc[j] - mx) : 0.f; sum += sc[j]; }
+        const float inv = 1.0f / sum;
+        float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < nt) {
+                const float2 vv = __ldg(reinterpret_cast<const float2*>(vbase + j * C + col));
+                o0 += sc[j] * vv.x;
+                o1 += sc[j] * vv.y;
+            }
+        }
+        *reinterpret_cast<uint32_t*>(out + row * ldo + col) = pack_bf16x2(o0 * inv, o1 * inv);
+    }
+}
+
+struct TaskIds {
+    int main_task[SMTL_MAX_TASKS];
+    int src_task[SMTL_MAX_TASKS];
+};
+// per-pixel cross-task attention: one thread per (q row, head); Nk <= 8 source streams
+__global__ void taskattn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                                const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out, int c, int nheads,
+                                int n_main, int n_src, int64_t rows_per_group, TaskIds ids, int exclude_self,
+                                float scale) {
+    const int64_t total = (int64_t)n_main * rows_per_group * nheads;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int hd = (int)(idx % nheads);
+    const int64_t row = idx / nheads;
+    const int grp = (int)(row / rows_per_group);
+    const int64_t pix = row - (int64_t)grp * rows_per_group;
+    const int dh = c / nheads;
+    const int nch = dh >> 3;
+    const int my_task = ids.main_task[grp];
+    const uint4* qp = reinterpret_cast<const uint4*>(q + row * c + hd * dh);
+    float sc[SMTL_MAX_TASKS];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int s = 0; s < SMTL_MAX_TASKS; ++s) {
+        sc[s] = -INFINITY;
+        if (s < n_src && !(exclude_self && ids.src_task[s] == my_task)) {
+            const uint4* kp = reinterpret_cast<const uint4*>(k + ((int64_t)s * rows_per_group + pix) * c + hd * dh);
+            float d = 0.f;
+            for (int i = 0; i < nch; ++i) {
+                const uint4 a = __ldg(qp + i), b = __ldg(kp + i);
+                float2 x, y;
+                x = unpack_bf16x2(a.x); y = unpack_bf16x2(b.x); d += x.x * y.x + x.y * y.y;
+                x = unpack_bf16x2(a.y); y = unpack_bf16x2(b.y); d += x.x * y.x + x.y * y.y;
+                x = unpack_bf16x2(a.z); y = unpack_bf16x2(b.z); d += x.x * y.x + x.y * y.y;
+                x = unpack_bf16x2(a.w); y = unpack_bf16x2(b.w); d += x.x * y.x + x.y * y.y;
+            }
+            sc[s] = d * scale;
+            mx = fmaxf(mx, sc[s]);
+        }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int s = 0; s < SMTL_MAX_TASKS; ++s) {
+        sc[s] = (sc[s] == -INFINITY) ? 0.f : __expf(sc[s] - mx);
+        sum += sc[s];
+    }
+    const float inv = (sum > 0.f) ? 1.0f / sum : 0.f;
+    uint4* op = reinterpret_cast<uint4*>(out + row * c + hd * dh);
+    for (int i = 0; i < nch; ++i) {
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int s = 0; s < SMTL_MAX_TASKS; ++s) {
+            if (s < n_src && sc[s] != 0.f) {
+                const uint4 b =
+                    __ldg(reinterpret_cast<const uint4*>(v + ((int64_t)s * rows_per_group + pix) * c + hd * dh) + i);
+                float2 y;
+                y = unpack_bf16x2(b.x); acc[0] += sc[s] * y.x; acc[1] += sc[s] * y.y;
+                y = unpack_bf16x2(b.y); acc[2] += sc[s] * y.x; acc[3] += sc[s] * y.y;
+                y = unpack_bf16x2(b.z); acc[4] += sc[s] * y.x; acc[5] += sc[s] * y.y;
+                y = unpack_bf16x2(b.w); acc[6] += sc[s] * y.x; acc[7] += sc[s] * y.y;
+            }
+        }
+        uint4 o;
+        o.x = pack_bf16x2(acc[0] * inv, acc[1] * inv); o.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
+        o.z = pack_bf16x2(acc[4] * inv, acc[5] * inv); o.w = pack_bf16x2(acc[6] * inv, acc[7] * inv);
+        op[i] = o;
+    }
+}
+
+// ============================================================================================= task-map epilogue
+__device__ __forceinline__ float clip1(float v) { return fminf(fmaxf(v, -1.0f), 1.0f); }
+
+__global__ void taskmap_kernel(const float* __restrict__ x, int batch, int hw, int mode, float* __restrict__ out_clip,
+                               float* __restrict__ out_post, long long* __restrict__ out_ids,
+                               const float* __restrict__ palette, int npal) {
+    const int64_t total = (int64_t)batch * hw;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = idx / hw, p = idx - b * hw;
+        const float c0 = x[idx * 3], c1 = x[idx * 3 + 1], c2 = x[idx * 3 + 2];
+        if (mode == SMTL_MAP_MEAN1) {
+            // torch mean over 3 channels = (c0 + c1 + c2) / 3 (stablemtl_pipeline.py:647), then clip (:601)
+            const float m = clip1((c0 + c1 + c2) / 3.0f);
+            if (out_clip) out_clip[idx] = m;
+            if (out_post) out_post[idx] = (m + 1.0f) / 2.0f;
+        } else if (mode == SMTL_MAP_FLOW2) {
+            const float a = clip1(c0), bb = clip1(c1);
+            if (out_clip) { out_clip[(b * 2) * hw + p] = a; out_clip[(b * 2 + 1) * hw + p] = bb; }
+            if (out_post) { out_post[(b * 2) * hw + p] = a; out_post[(b * 2 + 1) * hw + p] = bb; }
+        } else {
+            const float a = clip1(c0), bb = clip1(c1), cc = clip1(c2);
+            if (out_clip) {
+                out_clip[(b * 3) * hw + p] = a; out_clip[(b * 3 + 1) * hw + p] = bb; out_clip[(b * 3 + 2) * hw + p] = cc;
+            }
+            if (mode == SMTL_MAP_SEMANTIC) {
+                if (out_ids) {
+                    int best = 0;
+                    float bd = INFINITY;
+                    for (int k = 0; k < npal; ++k) {
+                        const float d0 = a - palette[3 * k], d1 = bb - palette[3 * k + 1], d2 = cc - palette[3 * k + 2];
+                        const float d = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);   // torch.cdist p=2, argmin first index
+                        if (d < bd) { bd = d; best = k; }
+                    }
+                    out_ids[idx] = best;
+                }
+            } else if (out_post) {
+                float r0 = a, r1 = bb, r2 = cc;
+                if (mode == SMTL_MAP_RGB3) {
+                    r0 = (a + 1.0f) / 2.0f; r1 = (bb + 1.0f) / 2.0f; r2 = (cc + 1.0f) / 2.0f;
+                } else if (mode == SMTL_MAP_NORMAL) {
+                    float nrm = sqrtf(a * a + bb * bb + cc * cc);
+                    if (nrm == 0.f) nrm = 1.0f;
+                    r0 = a / nrm; r1 = bb / nrm; r2 = cc / nrm;
+                }
+                out_post[(b * 3) * hw + p] = r0; out_post[(b * 3 + 1) * hw + p] = r1; out_post[(b * 3 + 2) * hw + p] = r2;
+            }
+        }
+    }
+}
+
+inline int grid_for(int64_t total, int block, int max_blocks = 148 * 16) {
+    int64_t g = (total + block - 1) / block;
+    if (g > max_blocks) g = max_blocks;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" int smtl_gn_run(const smtl_gn_args* a, void* stream) {
+    SMTL_CHECK_ARG(a && a->x0 && a->partial && a->gamma && a->beta && a->out_bf16, "gn: NULL argument");
+    const int C = a->c0 + a->c1;
+    SMTL_CHECK_ARG(a->c1 == 0 || a->x1, "gn: c1 > 0 without x1");
+    SMTL_CHECK_ARG(C % a->groups == 0 && a->c0 % 8 == 0 && a->c1 % 8 == 0, "gn: C=%d+%d groups=%d unsupported", a->c0,
+                   a->c1, a->groups);
+    SMTL_CHECK_ARG(C / 4 <= 1024 && a->groups <= 64, "gn: C=%d too wide", C);
+    SMTL_CHECK_ARG(a->nchunk >= 1 && a->batch >= 1 && a->h >= 1 && a->w >= 1, "gn: bad extent");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int cv = C / 4;
+    int rows_par = 256 / cv;
+    if (rows_par < 1) rows_par = 1;
+    const int hw = a->h * a->w;
+    gn_stats_kernel<<<dim3(a->nchunk, a->batch), cv * rows_par, 2 * a->groups * sizeof(float), st>>>(
+        a->x0, a->x1, a->c0, a->c1, hw, a->groups, a->nchunk, a->partial);
+    SMTL_CHECK_CUDA(cudaGetLastError());
+    const int hp = a->pad_out ? a->h + 2 : a->h, wp = a->pad_out ? a->w + 2 : a->w;
+    const int64_t per_img = (int64_t)hp * wp * (C / 8);
+    int bpi = (int)((per_img + 256 * 4 - 1) / (256 * 4));
+    const int cap = (148 * 8 + a->batch - 1) / a->batch;
+    if (bpi > cap) bpi = cap;
+    if (bpi < 1) bpi = 1;
+    const size_t smem = (2 * C + 2 * a->groups) * sizeof(float);
+    gn_apply_kernel<<<dim3(bpi, a->batch), 256, smem, st>>>(
+        a->x0, a->x1, a->c0, a->c1, a->h, a->w, a->groups, a->eps, a->partial, a->nchunk, a->gamma, a->beta, a->silu,
+        a->pad_out, reinterpret_cast<__nv_bfloat16*>(a->out_bf16), reinterpret_cast<__nv_bfloat16*>(a->raw_bf16));
+    SMTL_CHECK_CUDA(cudaGetLastError());
+    return SMTL_OK;
+}
+
+extern "C" int smtl_ln_run(const smtl_ln_args* a, void* stream) {
+    SMTL_CHECK_ARG(a && a->x && a->gamma0 && a->beta0 && a->out0, "ln: NULL argument");
+    SMTL_CHECK_ARG(a->c % 4 == 0 && a->c <= 1280 && a->ldx % 4 == 0 && a->ldo % 4 == 0, "ln: c=%d ldx=%d unsupported",
+                   a->c, a->ldx);
+    SMTL_CHECK_ARG(a->rows > 0 && a->rows_per_group > 0, "ln: bad rows");
+    SMTL_CHECK_ARG(!a->out1 || (a->gamma1 && a->beta1), "ln: out1 without affine");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int wpb = 8;
+    const int64_t grid = (a->rows + wpb - 1) / wpb;
+    if (a->x_is_bf16)
+        ln_kernel<true><<<(unsigned)grid, wpb * 32, 0, st>>>(a->x, a->c, a->ldx, a->rows, a->eps, a->rows_per_group,
+                                                             a->gamma0, a->beta0, (__nv_bfloat16*)a->out0, a->gamma1,
+                                                             a->beta1, (__nv_bfloat16*)a->out1, a->ldo);
+    else
+        ln_kernel<false><<<(unsigned)grid, wpb * 32, 0, st>>>(a->x, a->c, a->ldx, a->rows, a->eps, a->rows_per_group,
+                                                              a->gamma0, a->beta0, (__nv_bfloat16*)a->out0, a->gamma1,
+                                                              a->beta1, (__nv_bfloat16*)a->out1, a->ldo);
+    SMTL_CHECK_CUDA(cudaGetLastError());
+    return SMTL_OK;
+}
+
+extern "C" int smtl_upsample_run(const smtl_upsample_args* a, void* stream) {
+    SMTL_CHECK_ARG(a && a->x && a->out_bf16, "upsample: NULL argument");
+    SMTL_CHECK_ARG(a->c % 8 == 0 && a->oh >= a->h && a->ow >= a->w, "upsample: bad shape");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int64_t total = (int64_t)a->batch * (a->oh + 2) * (a->ow + 2) * (a->c / 8);
+    upsample_pad_kernel<<<grid_for(total, 256), 256, 0, st>>>(a->x, a->batch, a->h, a->w, a->c, a->oh, a->ow,
+                                                              (__nv_bfloat16*)a->out_bf16);
+    SMTL_CHECK_CUDA(cudaGetLastError());
+    return SMTL_OK;
+}
+
+extern "C" int smtl_im2col_run(const smtl_im2col_args* a, void* stream) {
+    SMTL_CHECK_ARG(a && a->x && a->out_bf16, "im2col: NULL argument");
+    SMTL_CHECK_ARG(a->kpad >= 9 * a->c && a->kpad % 8 == 0, "im2col: kpad %d < 9*c or unaligned", a->kpad);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (a->c % 8 == 0 && a->kpad == 9 * a->c) {
+        const int64_t total = (int64_t)a->batch * a->oh * a->ow * 9 * (a->c / 8);
+        im2col_vec8_kernel<<<grid_for(total, 256), 256, 0, st>>>(a->x, a->batch, a->h, a->w, a->c, a->stride, a->pad_t,
+                                                                 a->pad_l, a->oh, a->ow, (__nv_bfloat16*)a->out_bf16);
+    } else {
+        const int64_t total = (int64_t)a->batch * a->oh * a->ow * a->kpad;
+        im2col_scalar_kernel<<<grid_for(total, 256), 256, 0, st>>>(a->x, a->batch, a->h, a->w, a->c, a->stride,
+                                                                   a->pad_t, a->pad_l, a->oh, a->ow, a->kpad,
+                                                                   (__nv_bfloat16*)a->out_bf16);
+    }
+    SMTL_CHECK_CUDA(cudaGetLastError());
+    return SMTL_OK;
+}
+
+extern "C" int smtl_rgbprep_run(const smtl_rgbprep_args* a, void* stream) {
+    SMTL_CHECK_ARG(a && a->rgb_nchw && a->out_nhwc, "rgbprep: NULL argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int64_t total = (int64_t)a->batch * a->h * a->w;
+    rgbprep_kernel<<<grid_for(total, 256), 256, 0, st>>>(a->rgb_nchw, a->batch, a->h * a->w, a->out_nhwc);
+    SMTL_CHECK_CUDA(cudaGetLastError());
+    return SMTL_OK;
+}
+
+extern "C" int smtl_unetin_run(const smtl_unetin_args* a, void* stream) {
+    SMTL_CHECK_ARG(a && a->latents && a->first_img && a->second_img && a->out, "unetin: NULL argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int64_t total = (int64_t)a->out_images * a->hw;
+    unetin_kernel<<<grid_for(total, 256), 256, 0, st>>>(a->latents, a->first_img, a->second_img, a->out_images, a->hw,
+                                                        a->out);
+    SMTL_CHECK_CUDA(cudaGetLastError());
+    return SMTL_OK;
+}
+
+extern "C" int smtl_softmax_run(const smtl_softmax_args* a, void* stream) {
+    SMTL_CHECK_ARG(a && a->s && a->p_bf16, "softmax: NULL argument");
+    SMTL_CHECK_ARG(a->n > 0 && a->n <= 8192 && a->rows > 0, "softmax: n=%d out of range", a->n);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    softmax_rows_kernel<<<(unsigned)a->rows, 256, 0, st>>>(a->s, a->n, a->lds, a->scale, (__nv_bfloat16*)a->p_bf16,
+                                                           a->ldp);
+    SMTL_CHECK_CUDA(cudaGetLastError());
+    return SMTL_OK;
+}
+
+extern "C" int smtl_xattn_run(const smtl_xattn_args* a, void* stream) {
+    SMTL_CHECK_ARG(a && a->q_bf16 && a->kc && a->vc && a->out_bf16, "xattn: NULL argument");
+    SMTL_CHECK_ARG(a->rows > 0 && a->rows_per_group > 0 && a->heads > 0, "xattn: bad extent");
+    SMTL_CHECK_ARG((a->rows + a->rows_per_group - 1) / a->rows_per_group <= SMTL_MAX_TASKS, "xattn: too many groups");
+    XattnK tk;
+    for (int i = 0; i < SMTL_MAX_TASKS; ++i) {
+        tk.ntok[i] = a->ntok[i];
+        tk.task_of_group[i] = a->task_of_group[i];
+        SMTL_CHECK_ARG(a->ntok[i] >= 0 && a->ntok[i] <= 4, "xattn: ntok[%d]=%d", i, a->ntok[i]);
+        SMTL_CHECK_ARG(a->task_of_group[i] >= 0 && a->task_of_group[i] < SMTL_MAX_TASKS, "xattn: bad task id");
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int wpb = 8;
+    const int64_t grid = (a->rows + wpb - 1) / wpb;
+    xattn_kernel<<<(unsigned)grid, wpb * 32, 0, st>>>((const __nv_bfloat16*)a->q_bf16, a->ldq, a->rows, a->heads, a->kc,
+                                                      a->vc, tk, a->rows_per_group, (__nv_bfloat16*)a->out_bf16, a->ldo,
+                                                      a->scale);
+    SMTL_CHECK_CUDA(cudaGetLastError());
+    return SMTL_OK;
+}
+
+extern "C" int smtl_taskattn_run(const smtl_taskattn_args* a, void* stream) {
+    SMTL_CHECK_ARG(a && a->q_bf16 && a->k_bf16 && a->v_bf16 && a->out_bf16, "taskattn: NULL argument");
+    SMTL_CHECK_ARG(a->n_main >= 1 && a->n_main <= SMTL_MAX_TASKS && a->n_src >= 1 && a->n_src <= SMTL_MAX_TASKS,
+                   "taskattn: n_main=%d n_src=%d", a->n_main, a->n_src);
+    SMTL_CHECK_ARG(a->c % (a->nheads * 8) == 0, "taskattn: c=%d nheads=%d", a->c, a->nheads);
+    TaskIds ids;
+    for (int i = 0; i < SMTL_MAX_TASKS; ++i) { ids.main_task[i] = a->main_task[i]; ids.src_task[i] = a->src_task[i]; }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int64_t total = (int64_t)a->n_main * a->rows_per_group * a->nheads;
+    const int64_t grid = (total + 127) / 128;
+    taskattn_kernel<<<(unsigned)grid, 128, 0, st>>>((const __nv_bfloat16*)a->q_bf16, (const __nv_bfloat16*)a->k_bf16,
+                                                    (const __nv_bfloat16*)a->v_bf16, (__nv_bfloat16*)a->out_bf16, a->c,
+                                                    a->nheads, a->n_main, a->n_src, a->rows_per_group, ids,
+                                                    a->exclude_self, a->scale);
+    SMTL_CHECK_CUDA(cudaGetLastError());
+    return SMTL_OK;
+}
+
+extern "C" int smtl_taskmap_run(const smtl_taskmap_args* a, void* stream) {
+    SMTL_CHECK_ARG(a && a->x, "taskmap: NULL argument");
+    SMTL_CHECK_ARG(a->mode >= SMTL_MAP_MEAN1 && a->mode <= SMTL_MAP_SEMANTIC, "taskmap: mode %d", a->mode);
+    SMTL_CHECK_ARG(a->mode != SMTL_MAP_SEMANTIC || !a->out_ids || (a->palette && a->npalette > 0),
+                   "taskmap: semantic needs a palette");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int64_t total = (int64_t)a->batch * a->hw;
+    taskmap_kernel<<<grid_for(total, 256), 256, 0, st>>>(a->x, a->batch, a->hw, a->mode, a->out_clipped, a->out_post,
+                                                         (long long*)a->out_ids, a->palette, a->npalette);
+    SMTL_CHECK_CUDA(cudaGetLastError());
+    return SMTL_OK;
+}

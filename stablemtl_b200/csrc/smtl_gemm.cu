@@ -1,0 +1,446 @@
+// smtl_gemm.cu -- the tensor-core workhorse of the StableMTL hot path.
+//
+// One persistent, warp-specialised tcgen05 kernel:
+//   warp 0      : TMA producer  (cp.async.bulk.tensor 2-D, 128-byte swizzle, mbarrier complete_tx)
+//   warp 1      : MMA issuer    (one elected lane issues tcgen05.mma, fp32 accumulators in TMEM, 2 stages)
+//   warps 2..5  : epilogue      (tcgen05.ld -> bias / GELU / GEGLU / residual -> fp32 and/or bf16 stores)
+//
+// D[m, n] = sum over K segments of A_src[m + row_shift, a_col0 + k] * B[n, kbase + k].
+// With one segment this is a plain token GEMM (nn.Linear, reference src/model/attention.py:185-212,442-460);
+// with nine row-shifted segments over the zero-halo padded layout it is a 3x3 stride-1 convolution as an
+// implicit GEMM (InflatedConv3d, src/model/resnet.py:14-16); a tenth segment from a second tensor fuses the
+// 1x1 shortcut conv (src/model/resnet.py:172,200).
+#include "smtl_common.cuh"
+#include "smtl_host.h"
+
+namespace {
+
+using namespace smtl;
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;                       // one 128-byte swizzle atom of bf16
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int NUM_THREADS = 192;
+constexpr int SMEM_BUDGET = 227 * 1024;
+
+struct alignas(64) GemmKParams {
+    CUtensorMap tm_a0;
+    CUtensorMap tm_a1;
+    CUtensorMap tm_b;
+    int64_t m;
+    int32_t n;            // B rows (pre-activation columns)
+    int32_t n_out;        // output columns (n, or n/2 for GEGLU)
+    int32_t tiles_m, tiles_n;
+    int32_t total_kb;
+    int32_t stages;
+    int32_t nseg;
+    smtl_gemm_seg seg[SMTL_MAX_SEG];
+    const float* bias;
+    int32_t bias_per_row;
+    int32_t act;
+    const float* res1;
+    const float* res2;
+    int32_t ldres;
+    float* out_f32;
+    __nv_bfloat16* out_bf16;
+    __nv_bfloat16* aux_bf16;
+    int32_t ldc;
+    int32_t ld_aux;
+    int32_t rowmap;
+    int32_t img_h, img_w;
+};
+
+__device__ __forceinline__ void st_global_v4_f32(float* p, float a, float b, float c, float d) {
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void st_global_v4_b32(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_constant__ GemmKParams p) {
+    constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
+    constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    constexpr int TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    constexpr int ACC_STRIDE = TMEM_COLS / 2;
+    constexpr uint32_t IDESC = make_idesc_bf16(BLOCK_M, BN);
+    constexpr int MAX_STAGES = 12;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stages = p.stages;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * STAGE_BYTES);
+    uint64_t* full_bar = bars;                       // [stages]   TMA -> MMA
+    uint64_t* empty_bar = bars + MAX_STAGES;         // [stages]   MMA -> TMA
+    uint64_t* acc_full = bars + 2 * MAX_STAGES;      // [2]        MMA -> epilogue
+    uint64_t* acc_empty = bars + 2 * MAX_STAGES + 2; // [2]        epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tm_a0);
+        tma_prefetch_desc(&p.tm_a1);
+        tma_prefetch_desc(&p.tm_b);
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&acc_empty[s], 4);   // one arrive per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_tiles = p.tiles_m * p.tiles_n;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+                const int64_t m0 = (int64_t)tm * BLOCK_M;
+                const int n0 = tn * BN;
+                int kb_global = 0;
+                for (int s = 0; s < p.nseg; ++s) {
+                    const smtl_gemm_seg sg = p.seg[s];
+                    const CUtensorMap* tma = sg.src ? &p.tm_a1 : &p.tm_a0;
+                    const int32_t arow = (int32_t)(m0 + sg.row_shift);
+                    for (int kb = 0; kb < sg.kblocks; ++kb, ++kb_global) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1u);
+                        uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
+                        uint8_t* sb = sa + A_STAGE_BYTES;
+                        mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                        tma_load_2d(sa, tma, &full_bar[stage], sg.a_col0 + kb * BLOCK_K, arow);
+                        tma_load_2d(sb, &p.tm_b, &full_bar[stage], kb_global * BLOCK_K, n0);
+                        if (++stage == stages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&acc_empty[acc], acc_phase ^ 1u);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * ACC_STRIDE;
+            for (int kb = 0; kb < p.total_kb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+                    const uint64_t da = make_smem_desc_sw128(sa);
+                    const uint64_t db = make_smem_desc_sw128(sa + A_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 16; ++k) {
+                        // +32 B per 16-element K step inside the swizzle atom: start-address field += 2
+                        tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
+                    }
+                    tc_commit(&empty_bar[stage]);                       // smem slot free once these MMAs retire
+                    if (kb == p.total_kb - 1) tc_commit(&acc_full[acc]); // accumulator ready
+                }
+                __syncwarp();
+                if (++stage == stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+        const int row_in_tile = quarter * 32 + lane;
+        const bool geglu = (p.act == SMTL_ACT_GEGLU);
+        const int out_bn = geglu ? BN / 2 : BN;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+            const int64_t grow = (int64_t)tm * BLOCK_M + row_in_tile;
+            const int n0 = tn * BN;
+            bool row_ok = grow < p.m;
+            int64_t orow = grow;
+            if (p.rowmap == SMTL_ROWMAP_CONV_PAD) {
+                const int wp = p.img_w + 2;
+                const int plane = (p.img_h + 2) * wp;
+                const int64_t img = grow / plane;
+                const int rem = (int)(grow - img * plane);
+                const int yp = rem / wp, xp = rem - yp * wp;
+                row_ok = row_ok && yp >= 1 && yp <= p.img_h && xp >= 1 && xp <= p.img_w;
+                orow = (img * p.img_h + (yp - 1)) * p.img_w + (xp - 1);
+            }
+            const float row_bias = (p.bias && p.bias_per_row && grow < p.m) ? __ldg(p.bias + grow) : 0.0f;
+
+            mbar_wait(&acc_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
+
+            for (int c0 = 0; c0 < out_bn; c0 += 32) {
+                const int ncol_in = n0 + c0;                       // B-row index of the chunk's first column
+                if (ncol_in >= p.n) break;                         // warp-uniform
+                uint32_t r[32];
+                float v[32];
+                tmem_ld_32x32(taddr + c0, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                if (p.bias) {
+                    if (p.bias_per_row) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] += row_bias;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (ncol_in + j < p.n) v[j] += __ldg(p.bias + ncol_in + j);
+                    }
+                }
+                int ocol = ncol_in;                                // output column of v[0]
+                if (geglu) {
+                    tmem_ld_32x32(taddr + BN / 2 + c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float g = __uint_as_float(r[j]);
+                        if (p.bias) g += __ldg(p.bias + n0 + BN / 2 + c0 + j);
+                        v[j] *= gelu_erf(g);
+                    }
+                    ocol = tn * (BN / 2) + c0;
+                } else if (p.act == SMTL_ACT_GELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                } else if (p.act == SMTL_ACT_SILU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
+                }
+                if (row_ok) {
+                const bool full = (ocol + 32 <= p.n_out);
+                if (p.aux_bf16) {
+                    __nv_bfloat16* dst = p.aux_bf16 + orow * (int64_t)p.ld_aux + ocol;
+                    if (full && (p.ld_aux & 7) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8)
+                            st_global_v4_b32(dst + j, pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
+                                             pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
+                    } else {
+                        for (int j = 0; j < 32; ++j)
+                            if (ocol + j < p.n_out) dst[j] = __float2bfloat16(v[j]);
+                    }
+                }
+                if (p.res1) {
+                    const float* src = p.res1 + orow * (int64_t)p.ldres + ocol;
+                    if (full && (p.ldres & 3) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 t = __ldg(reinterpret_cast<const float4*>(src + j));
+                            v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+                        }
+                    } else {
+                        for (int j = 0; j < 32; ++j)
+                            if (ocol + j < p.n_out) v[j] += __ldg(src + j);
+                    }
+                }
+                if (p.res2) {
+                    const float* src = p.res2 + orow * (int64_t)p.ldres + ocol;
+                    if (full && (p.ldres & 3) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 t = __ldg(reinterpret_cast<const float4*>(src + j));
+                            v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+                        }
+                    } else {
+                        for (int j = 0; j < 32; ++j)
+                            if (ocol + j < p.n_out) v[j] += __ldg(src + j);
+                    }
+                }
+                if (p.out_f32) {
+                    float* dst = p.out_f32 + orow * (int64_t)p.ldc + ocol;
+                    if (full && (p.ldc & 3) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) st_global_v4_f32(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+                        for (int j = 0; j < 32; ++j)
+                            if (ocol + j < p.n_out) dst[j] = v[j];
+                    }
+                }
+                if (p.out_bf16) {
+                    __nv_bfloat16* dst = p.out_bf16 + orow * (int64_t)p.ldc + ocol;
+                    if (full && (p.ldc & 7) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8)
+                            st_global_v4_b32(dst + j, pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
+                                             pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
+                    } else {
+                        for (int j = 0; j < 32; ++j)
+                            if (ocol + j < p.n_out) dst[j] = __float2bfloat16(v[j]);
+                    }
+                }
+                }  // row_ok
+                __syncwarp();   // reconverge before the next warp-collective tcgen05.ld
+            }
+            // release this accumulator stage back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int BN>
+int launch_gemm(const GemmKParams& kp, int grid, int smem_bytes, cudaStream_t stream) {
+    static bool attr_set = false;   // per-instantiation; benign race (idempotent)
+    if (!attr_set) {
+        SMTL_CHECK_CUDA(cudaFuncSetAttribute(smtl_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             SMEM_BUDGET));
+        attr_set = true;
+    }
+    smtl_gemm_kernel<BN><<<grid, NUM_THREADS, smem_bytes, stream>>>(kp);
+    SMTL_CHECK_CUDA(cudaGetLastError());
+    return SMTL_OK;
+}
+
+int pick_block_n(int n, int act) {
+    if (act == SMTL_ACT_GEGLU) return 256;
+    if (n <= 32) return 32;
+    if (n <= 64) return 64;
+    if (n <= 128) return 128;
+    const int cands[] = {128, 160, 192, 224, 256};
+    int best = 256;
+    double best_cost = 1e30;
+    for (int bn : cands) {
+        const int tiles = (n + bn - 1) / bn;
+        // MMA time ~ tiles * max(bn, 160) (narrow tiles are smem-bandwidth bound); small bonus for wide tiles
+        const double cost = (double)tiles * (bn > 160 ? bn : 160) * (1.0 + 16.0 / bn);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+    }
+    return best;
+}
+
+}  // namespace
+
+extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
+    SMTL_CHECK_ARG(a && op, "gemm_plan: NULL argument");
+    SMTL_CHECK_ARG(a->a0 && a->b, "gemm_plan: NULL operand");
+    SMTL_CHECK_ARG(a->m > 0 && a->n > 0 && a->k > 0, "gemm_plan: empty problem m=%lld n=%d k=%d", (long long)a->m,
+                   a->n, a->k);
+    SMTL_CHECK_ARG(a->out_f32 || a->out_bf16 || a->aux_bf16, "gemm_plan: no output");
+    SMTL_CHECK_ARG(a->nseg >= 0 && a->nseg <= SMTL_MAX_SEG, "gemm_plan: nseg %d out of range", a->nseg);
+    memset(op, 0, sizeof(*op));
+    op->args = *a;
+    smtl_gemm_args& g = op->args;
+    if (g.nseg == 0) {
+        g.nseg = 1;
+        g.seg[0].row_shift = 0;
+        g.seg[0].kblocks = (g.k + BLOCK_K - 1) / BLOCK_K;
+        g.seg[0].src = 0;
+        g.seg[0].a_col0 = 0;
+    }
+    int total_kb = 0;
+    for (int s = 0; s < g.nseg; ++s) {
+        SMTL_CHECK_ARG(g.seg[s].kblocks > 0, "gemm_plan: segment %d has no K blocks", s);
+        SMTL_CHECK_ARG(g.seg[s].src == 0 || (g.seg[s].src == 1 && g.a1), "gemm_plan: segment %d bad source", s);
+        total_kb += g.seg[s].kblocks;
+    }
+    SMTL_CHECK_ARG(total_kb * BLOCK_K >= g.k && (total_kb - 1) * BLOCK_K < g.k,
+                   "gemm_plan: segments cover %d K blocks but k=%d", total_kb, g.k);
+    int bn = g.block_n ? g.block_n : pick_block_n(g.n, g.act);
+    SMTL_CHECK_ARG(bn == 32 || bn == 64 || bn == 128 || bn == 160 || bn == 192 || bn == 224 || bn == 256,
+                   "gemm_plan: unsupported block_n %d", bn);
+    if (g.act == SMTL_ACT_GEGLU) {
+        SMTL_CHECK_ARG(bn == 256 && g.n % 256 == 0, "gemm_plan: GEGLU needs n %% 256 == 0 (n=%d)", g.n);
+        SMTL_CHECK_ARG(!g.bias_per_row, "gemm_plan: GEGLU with per-row bias");
+    }
+    if (g.rowmap == SMTL_ROWMAP_CONV_PAD)
+        SMTL_CHECK_ARG(g.img_h > 0 && g.img_w > 0, "gemm_plan: conv row map needs img_h/img_w");
+    SMTL_CHECK_ARG(g.m + 4096 < (int64_t)1 << 31, "gemm_plan: m too large for 32-bit TMA coordinates");
+
+    op->block_n = bn;
+    op->tiles_m = (int)((g.m + BLOCK_M - 1) / BLOCK_M);
+    op->tiles_n = (g.n + bn - 1) / bn;
+    op->total_kblocks = total_kb;
+    const int stage_bytes = A_STAGE_BYTES + bn * BLOCK_K * 2;
+    int stages = (SMEM_BUDGET - 1024 - 512) / stage_bytes;
+    if (stages > 8) stages = 8;
+    op->smem_bytes = 1024 + stages * stage_bytes + 512;
+    const long long tiles = (long long)op->tiles_m * op->tiles_n;
+    const int sms = smtl_host::num_sms();
+    op->grid = (int)(tiles < sms ? tiles : sms);
+
+    int rc = smtl_host::encode_tmap_bf16_2d(op->tmap_a0, g.a0, (uint64_t)g.a0_rows, (uint64_t)g.a0_cols,
+                                            (uint64_t)g.a0_ld, BLOCK_M);
+    if (rc) return rc;
+    if (g.a1) {
+        rc = smtl_host::encode_tmap_bf16_2d(op->tmap_a1, g.a1, (uint64_t)g.a1_rows, (uint64_t)g.a1_cols,
+                                            (uint64_t)g.a1_ld, BLOCK_M);
+        if (rc) return rc;
+    } else {
+        memcpy(op->tmap_a1, op->tmap_a0, sizeof(op->tmap_a0));
+    }
+    rc = smtl_host::encode_tmap_bf16_2d(op->tmap_b, g.b, (uint64_t)g.n, (uint64_t)g.k, (uint64_t)g.ldb, (uint32_t)bn);
+    return rc;
+}
+
+extern "C" int smtl_gemm_run(const smtl_gemm_op* op, void* stream) {
+    SMTL_CHECK_ARG(op, "gemm_run: NULL op");
+    const smtl_gemm_args& g = op->args;
+    GemmKParams kp;
+    memcpy(&kp.tm_a0, op->tmap_a0, 128);
+    memcpy(&kp.tm_a1, op->tmap_a1, 128);
+    memcpy(&kp.tm_b, op->tmap_b, 128);
+    kp.m = g.m;
+    kp.n = g.n;
+    kp.n_out = (g.act == SMTL_ACT_GEGLU) ? g.n / 2 : g.n;
+    kp.tiles_m = op->tiles_m;
+    kp.tiles_n = op->tiles_n;
+    kp.total_kb = op->total_kblocks;
+    const int stage_bytes = A_STAGE_BYTES + op->block_n * BLOCK_K * 2;
+    kp.stages = (op->smem_bytes - 1024 - 512) / stage_bytes;
+    kp.nseg = g.nseg;
+    for (int s = 0; s < SMTL_MAX_SEG; ++s) kp.seg[s] = g.seg[s];
+    kp.bias = g.bias;
+    kp.bias_per_row = g.bias_per_row;
+    kp.act = g.act;
+    kp.res1 = g.res1;
+    kp.res2 = g.res2;
+    kp.ldres = g.ldres;
+    kp.out_f32 = g.out_f32;
+    kp.out_bf16 = reinterpret_cast<__nv_bfloat16*>(g.out_bf16);
+    kp.aux_bf16 = reinterpret_cast<__nv_bfloat16*>(g.aux_bf16);
+    kp.ldc = g.ldc;
+    kp.ld_aux = g.ld_aux;
+    kp.rowmap = g.rowmap;
+    kp.img_h = g.img_h;
+    kp.img_w = g.img_w;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (op->block_n) {
+        case 32: return launch_gemm<32>(kp, op->grid, op->smem_bytes, st);
+        case 64: return launch_gemm<64>(kp, op->grid, op->smem_bytes, st);
+        case 128: return launch_gemm<128>(kp, op->grid, op->smem_bytes, st);
+        case 160: return launch_gemm<160>(kp, op->grid, op->smem_bytes, st);
+        case 192: return launch_gemm<192>(kp, op->grid, op->smem_bytes, st);
+        case 224: return launch_gemm<224>(kp, op->grid, op->smem_bytes, st);
+        case 256: return launch_gemm<256>(kp, op->grid, op->smem_bytes, st);
+        default: smtl_host::set_error("gemm_run: bad block_n %d", op->block_n); return SMTL_EINVAL;
+    }
+}

@@ -1,0 +1,284 @@
+"""Thin host-side wrappers: torch tensors in, C-ABI op structs out.
+
+Every function returns an `Op` (kind, struct) that can be executed immediately with `.run()` or collected
+into a `Plan`, which hands the whole launch list to native code in one call (`smtl_run_plan`).
+torch is used only for device memory and the current stream.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_RUNNERS = {
+    L.OP_GEMM: "smtl_gemm_run", L.OP_FATTN: "smtl_fattn_run", L.OP_SOFTMAX: "smtl_softmax_run",
+    L.OP_XATTN: "smtl_xattn_run", L.OP_TASKATTN: "smtl_taskattn_run", L.OP_GN: "smtl_gn_run",
+    L.OP_LN: "smtl_ln_run", L.OP_UPSAMPLE: "smtl_upsample_run", L.OP_IM2COL: "smtl_im2col_run",
+    L.OP_RGBPREP: "smtl_rgbprep_run", L.OP_UNETIN: "smtl_unetin_run", L.OP_TASKMAP: "smtl_taskmap_run",
+}
+
+
+class Op:
+    __slots__ = ("kind", "struct", "keep", "flops", "name")
+
+    def __init__(self, kind, struct, keep=(), flops=0, name=""):
+        self.kind, self.struct, self.keep, self.flops, self.name = kind, struct, keep, flops, name
+
+    def run(self):
+        fn = getattr(L.lib, _RUNNERS[self.kind])
+        L.check(fn(C.byref(self.struct), _stream()), _RUNNERS[self.kind])
+        return self
+
+
+class Plan:
+    """An ordered launch list executed natively (one ABI crossing per pass)."""
+
+    def __init__(self):
+        self.ops = []
+        self._arr = None
+
+    def add(self, op):
+        self.ops.append(op)
+        self._arr = None
+        return op
+
+    def extend(self, ops):
+        for o in ops:
+            self.add(o)
+
+    def finalize(self):
+        arr = (L.OpRef * len(self.ops))()
+        for i, o in enumerate(self.ops):
+            arr[i].kind = o.kind
+            arr[i].op = C.cast(C.pointer(o.struct), C.c_void_p)
+        self._arr = arr
+        return self
+
+    @property
+    def launches(self):
+        if self._arr is None:
+            self.finalize()
+        return L.lib.smtl_plan_launches(self._arr, len(self.ops))
+
+    @property
+    def flops(self):
+        return sum(o.flops for o in self.ops)
+
+    def run(self):
+        if self._arr is None:
+            self.finalize()
+        L.check(L.lib.smtl_run_plan(self._arr, len(self.ops), _stream()), "smtl_run_plan")
+
+
+# ------------------------------------------------------------------------------------------------- GEMM / conv
+def gemm(a0, b, *, m=None, k=None, n=None, a1=None, segs=None, bias=None, bias_per_row=False, act=L.ACT_NONE,
+         res1=None, res2=None, out_f32=None, out_bf16=None, aux_bf16=None, rowmap=L.ROWMAP_IDENTITY, img_hw=None,
+         block_n=0, name="gemm"):
+    """D = A @ B^T (+ fused epilogue).  a0/a1: bf16 [rows, cols] (row stride = stride(0)); b: bf16 [n, k].
+    segs: list of (row_shift, kblocks, src, a_col0)."""
+    assert a0.dtype == BF16 and b.dtype == BF16 and a0.stride(-1) == 1 and b.stride(-1) == 1
+    g = L.GemmArgs()
+    g.a0, g.a0_rows, g.a0_cols, g.a0_ld = a0.data_ptr(), a0.shape[0], a0.shape[1], a0.stride(0)
+    if a1 is not None:
+        assert a1.dtype == BF16 and a1.stride(-1) == 1
+        g.a1, g.a1_rows, g.a1_cols, g.a1_ld = a1.data_ptr(), a1.shape[0], a1.shape[1], a1.stride(0)
+    g.b, g.ldb = b.data_ptr(), b.stride(0)
+    g.n = b.shape[0] if n is None else n
+    g.k = b.shape[1] if k is None else k
+    g.m = a0.shape[0] if m is None else m
+    if segs:
+        g.nseg = len(segs)
+        for i, (shift, kb, src, col0) in enumerate(segs):
+            g.seg[i].row_shift, g.seg[i].kblocks, g.seg[i].src, g.seg[i].a_col0 = shift, kb, src, col0
+    if bias is not None:
+        assert bias.dtype == F32
+        g.bias = bias.data_ptr()
+    g.bias_per_row = int(bias_per_row)
+    g.act = act
+    n_out = g.n // 2 if act == L.ACT_GEGLU else g.n
+    for r in (res1, res2):
+        if r is not None:
+            assert r.dtype == F32 and r.stride(-1) == 1
+            g.ldres = r.stride(0)
+    g.res1, g.res2 = _ptr(res1), _ptr(res2)
+    outs = [t for t in (out_f32, out_bf16) if t is not None]
+    if out_f32 is not None:
+        assert out_f32.dtype == F32 and out_f32.stride(-1) == 1
+    if out_bf16 is not None:
+        assert out_bf16.dtype == BF16 and out_bf16.stride(-1) == 1
+    if len(outs) == 2:
+        assert out_f32.stride(0) == out_bf16.stride(0)
+    if outs:
+        g.ldc = outs[0].stride(0)
+        assert outs[0].shape[-1] >= n_out or outs[0].stride(0) >= n_out
+    g.out_f32, g.out_bf16 = _ptr(out_f32), _ptr(out_bf16)
+    if aux_bf16 is not None:
+        assert aux_bf16.dtype == BF16
+        g.aux_bf16, g.ld_aux = aux_bf16.data_ptr(), aux_bf16.stride(0)
+    g.rowmap = rowmap
+    if img_hw is not None:
+        g.img_h, g.img_w = img_hw
+    g.block_n = block_n
+    op = L.GemmOp()
+    L.check(L.lib.smtl_gemm_plan(C.byref(g), C.byref(op)), "smtl_gemm_plan")
+    flops = 2 * int(g.m) * int(g.n) * int(g.k)
+    return Op(L.OP_GEMM, op, (a0, a1, b, bias, res1, res2, out_f32, out_bf16, aux_bf16), flops, name)
+
+
+def conv3x3_segs(cin, w, shortcut_cin=0):
+    """K segments of a 3x3/s1/p1 conv over the padded layout (+ optional fused 1x1 shortcut from source 1)."""
+    assert cin % 64 == 0
+    wp = w + 2
+    segs = [((ky - 1) * wp + (kx - 1), cin // 64, 0, 0) for ky in range(3) for kx in range(3)]
+    if shortcut_cin:
+        assert shortcut_cin % 64 == 0
+        segs.append((0, shortcut_cin // 64, 1, 0))
+    return segs
+
+
+def conv3x3(a_pad, wmat, batch, h, w, *, a_short=None, name="conv3x3", **epi):
+    """a_pad: bf16 [batch*(h+2)*(w+2), cin] zero-halo layout; wmat: bf16 [cout, 9*cin (+ c_short)]."""
+    cin = a_pad.shape[1]
+    cs = 0 if a_short is None else a_short.shape[1]
+    op = gemm(a_pad, wmat, m=batch * (h + 2) * (w + 2), a1=a_short, segs=conv3x3_segs(cin, w, cs),
+              rowmap=L.ROWMAP_CONV_PAD, img_hw=(h, w), name=name, **epi)
+    op.flops = 2 * batch * h * w * wmat.shape[0] * wmat.shape[1]   # algorithmic (halo rows excluded)
+    return op
+
+
+# ------------------------------------------------------------------------------------------------- attention
+def flash_attn(qkv, batch, ntok, heads, out, q_col0, k_col0, v_col0, scale=0.125):
+    a = L.FattnArgs()
+    a.qkv, a.ld = qkv.data_ptr(), qkv.stride(0)
+    a.q_col0, a.k_col0, a.v_col0 = q_col0, k_col0, v_col0
+    a.batch, a.ntok, a.heads = batch, ntok, heads
+    a.out_bf16, a.ldo, a.scale = out.data_ptr(), out.stride(0), scale
+    assert qkv.dtype == BF16 and out.dtype == BF16 and qkv.shape[0] == batch * ntok
+    op = L.FattnOp()
+    L.check(L.lib.smtl_fattn_plan(C.byref(a), C.byref(op)), "smtl_fattn_plan")
+    return Op(L.OP_FATTN, op, (qkv, out), 4 * batch * heads * ntok * ntok * 64, "flash_attn")
+
+
+def softmax_rows(s, p, scale):
+    a = L.SoftmaxArgs()
+    a.s, a.rows, a.n, a.lds, a.scale = s.data_ptr(), s.shape[0], s.shape[1], s.stride(0), scale
+    a.p_bf16, a.ldp = p.data_ptr(), p.stride(0)
+    assert s.dtype == F32 and p.dtype == BF16
+    return Op(L.OP_SOFTMAX, a, (s, p), 0, "softmax")
+
+
+def xattn(q, kc, vc, ntok, task_of_group, rows_per_group, heads, out, scale=0.125):
+    a = L.XattnArgs()
+    a.q_bf16, a.ldq, a.rows, a.heads = q.data_ptr(), q.stride(0), q.shape[0], heads
+    a.kc, a.vc = kc.data_ptr(), vc.data_ptr()
+    assert kc.dtype == F32 and vc.dtype == F32 and kc.shape[1] == 4 and kc.shape[2] == heads * 64
+    for i in range(L.MAX_TASKS):
+        a.ntok[i] = ntok[i] if i < len(ntok) else 0
+        a.task_of_group[i] = task_of_group[i] if i < len(task_of_group) else 0
+    a.rows_per_group = rows_per_group
+    a.out_bf16, a.ldo, a.scale = out.data_ptr(), out.stride(0), scale
+    return Op(L.OP_XATTN, a, (q, kc, vc, out), 0, "xattn")
+
+
+def task_attn(q, k, v, out, c, nheads, main_tasks, src_tasks, rows_per_group, exclude_self=True):
+    a = L.TaskAttnArgs()
+    a.q_bf16, a.k_bf16, a.v_bf16, a.out_bf16 = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    a.c, a.nheads, a.n_main, a.n_src = c, nheads, len(main_tasks), len(src_tasks)
+    a.rows_per_group = rows_per_group
+    for i, t in enumerate(main_tasks):
+        a.main_task[i] = t
+    for i, t in enumerate(src_tasks):
+        a.src_task[i] = t
+    a.exclude_self = int(exclude_self)
+    a.scale = float((c // nheads) ** -0.5)
+    assert q.dtype == BF16 and k.dtype == BF16 and v.dtype == BF16 and out.dtype == BF16
+    assert q.shape == (len(main_tasks) * rows_per_group, c) and k.shape == (len(src_tasks) * rows_per_group, c)
+    return Op(L.OP_TASKATTN, a, (q, k, v, out), 0, "task_attn")
+
+
+# ------------------------------------------------------------------------------------------------- norms
+def gn_nchunk(hw):
+    return max(1, min(64, hw // 512))
+
+
+def group_norm(x0, batch, h, w, gamma, beta, out, *, x1=None, eps, silu, pad_out, partial, raw=None, groups=32):
+    a = L.GnArgs()
+    a.x0, a.c0 = x0.data_ptr(), x0.shape[-1]
+    if x1 is not None:
+        a.x1, a.c1 = x1.data_ptr(), x1.shape[-1]
+    a.batch, a.h, a.w, a.groups, a.eps = batch, h, w, groups, eps
+    a.nchunk = gn_nchunk(h * w)
+    assert partial.dtype == F32 and partial.numel() >= batch * a.nchunk * groups * 2
+    a.partial = partial.data_ptr()
+    a.gamma, a.beta = gamma.data_ptr(), beta.data_ptr()
+    a.silu, a.pad_out = int(silu), int(pad_out)
+    a.out_bf16, a.raw_bf16 = out.data_ptr(), _ptr(raw)
+    assert x0.dtype == F32 and out.dtype == BF16 and x0.is_contiguous()
+    return Op(L.OP_GN, a, (x0, x1, gamma, beta, out, raw, partial), 0, "group_norm")
+
+
+def layer_norm(x, gamma0, beta0, out0, *, gamma1=None, beta1=None, out1=None, rows_per_group=None, eps=1e-5):
+    a = L.LnArgs()
+    a.x, a.x_is_bf16, a.c, a.ldx = x.data_ptr(), int(x.dtype == BF16), x.shape[1], x.stride(0)
+    a.rows, a.eps = x.shape[0], eps
+    a.rows_per_group = x.shape[0] if rows_per_group is None else rows_per_group
+    a.gamma0, a.beta0, a.out0 = gamma0.data_ptr(), beta0.data_ptr(), out0.data_ptr()
+    a.gamma1, a.beta1, a.out1 = _ptr(gamma1), _ptr(beta1), _ptr(out1)
+    a.ldo = out0.stride(0)
+    assert out0.dtype == BF16 and gamma0.dtype == F32
+    return Op(L.OP_LN, a, (x, gamma0, beta0, out0, gamma1, beta1, out1), 0, "layer_norm")
+
+
+# ------------------------------------------------------------------------------------------------- data movement
+def upsample_pad(x, batch, h, w, oh, ow, out):
+    a = L.UpsampleArgs()
+    a.x, a.batch, a.h, a.w, a.c, a.oh, a.ow, a.out_bf16 = x.data_ptr(), batch, h, w, x.shape[-1], oh, ow, out.data_ptr()
+    assert x.dtype == F32 and out.dtype == BF16
+    return Op(L.OP_UPSAMPLE, a, (x, out), 0, "upsample")
+
+
+def im2col(x, batch, h, w, out, *, stride, pad_t, pad_l, oh, ow):
+    a = L.Im2colArgs()
+    a.x, a.batch, a.h, a.w, a.c = x.data_ptr(), batch, h, w, x.shape[-1]
+    a.stride, a.pad_t, a.pad_l, a.oh, a.ow, a.kpad = stride, pad_t, pad_l, oh, ow, out.shape[-1]
+    a.out_bf16 = out.data_ptr()
+    assert x.dtype == F32 and out.dtype == BF16 and out.is_contiguous()
+    return Op(L.OP_IM2COL, a, (x, out), 0, "im2col")
+
+
+def rgb_prep(rgb_nchw, out_nhwc):
+    a = L.RgbprepArgs()
+    b, _, h, w = rgb_nchw.shape
+    a.rgb_nchw, a.batch, a.h, a.w, a.out_nhwc = rgb_nchw.data_ptr(), b, h, w, out_nhwc.data_ptr()
+    assert rgb_nchw.dtype == F32 and rgb_nchw.is_contiguous() and out_nhwc.dtype == F32
+    return Op(L.OP_RGBPREP, a, (rgb_nchw, out_nhwc), 0, "rgb_prep")
+
+
+def unet_input(latents, first_img, second_img, hw, out):
+    a = L.UnetinArgs()
+    a.latents, a.first_img, a.second_img = latents.data_ptr(), first_img.data_ptr(), second_img.data_ptr()
+    a.out_images, a.hw, a.out = first_img.numel(), hw, out.data_ptr()
+    assert first_img.dtype == torch.int32 and second_img.dtype == torch.int32 and latents.dtype == F32
+    return Op(L.OP_UNETIN, a, (latents, first_img, second_img, out), 0, "unet_input")
+
+
+def task_map(x, batch, hw, mode, *, out_clipped=None, out_post=None, out_ids=None, palette=None):
+    a = L.TaskmapArgs()
+    a.x, a.batch, a.hw, a.mode = x.data_ptr(), batch, hw, mode
+    a.out_clipped, a.out_post, a.out_ids = _ptr(out_clipped), _ptr(out_post), _ptr(out_ids)
+    if palette is not None:
+        a.palette, a.npalette = palette.data_ptr(), palette.shape[0]
+    assert x.dtype == F32
+    return Op(L.OP_TASKMAP, a, (x, out_clipped, out_post, out_ids, palette), 0, "task_map")

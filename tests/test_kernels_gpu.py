@@ -1,0 +1,307 @@
+"""Per-kernel numerics on the B200: each CUDA kernel against a plain PyTorch fp32 restatement of the same op
+(the op-level oracle), called through the C ABI.  bf16 operands are rounded first so the comparison isolates
+the kernel's arithmetic; tolerances are stated per test."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _ops():
+    from stablemtl_b200 import ops, _lib
+    return ops, _lib
+
+
+def rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+@pytest.mark.parametrize("m,n,k,bn", [
+    (128, 256, 64, 0), (256, 256, 320, 0), (300, 320, 320, 0), (1000, 640, 1280, 0), (4800, 1280, 320, 0),
+    (130, 4, 576, 0), (777, 96, 200, 0), (512, 960, 320, 0), (512, 1920, 640, 0), (20000, 320, 2880, 0),
+    (512, 320, 128, 64), (512, 320, 128, 128), (512, 320, 128, 224),
+])
+def test_gemm_plain(m, n, k, bn):
+    ops, L = _ops()
+    kp = (k + 7) // 8 * 8
+    a = rnd(m, kp, seed=1).bfloat16()[:, :k] if kp != k else rnd(m, k, seed=1).bfloat16()
+    b = rnd(n, kp, scale=k ** -0.5, seed=2).bfloat16()
+    if kp != k:
+        b = b[:, :k]
+    bias = rnd(n, seed=3)
+    res = rnd(m, n, seed=4)
+    out = torch.full((m, n), float("nan"), device=DEV)
+    outb = torch.empty(m, n, device=DEV, dtype=torch.bfloat16) if n % 8 == 0 else None
+    ops.gemm(a, b, bias=bias, res1=res, out_f32=out, out_bf16=outb, block_n=bn).run()
+    torch.cuda.synchronize()
+    ref = a.float() @ b.float().t() + bias + res
+    err = rel_l2(out, ref)
+    assert err < 2e-5, f"gemm {m}x{n}x{k}: rel-L2 {err}"   # fp32 accumulate of exact bf16 products
+    if outb is not None:
+        assert rel_l2(outb.float(), ref) < 4e-3
+
+
+def test_gemm_gelu_aux_two_res():
+    ops, L = _ops()
+    m, n, k = 700, 640, 640
+    a, b = rnd(m, k, seed=1).bfloat16(), rnd(n, k, scale=k ** -0.5, seed=2).bfloat16()
+    bias, r1, r2 = rnd(n, seed=3), rnd(m, n, seed=4), rnd(m, n, seed=5)
+    out = torch.empty(m, n, device=DEV)
+    aux = torch.empty(m, n, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(a, b, bias=bias, act=L.ACT_GELU, res1=r1, res2=r2, out_f32=out, aux_bf16=aux).run()
+    torch.cuda.synchronize()
+    pre = F.gelu(a.float() @ b.float().t() + bias)
+    assert rel_l2(out, pre + r1 + r2) < 2e-5
+    assert rel_l2(aux.float(), pre) < 4e-3
+
+
+def test_gemm_geglu():
+    ops, L = _ops()
+    from stablemtl_b200.weights import interleave_geglu
+    m, c = 600, 320
+    a = rnd(m, c, seed=1).bfloat16()
+    w = rnd(8 * c, c, scale=c ** -0.5, seed=2).bfloat16()
+    bias = rnd(8 * c, seed=3)
+    wi, bi = interleave_geglu(w, bias)
+    out = torch.empty(m, 4 * c, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(a, wi, bias=bi, act=L.ACT_GEGLU, out_bf16=out).run()
+    torch.cuda.synchronize()
+    h = a.float() @ w.float().t() + bias
+    ref = h[:, :4 * c] * F.gelu(h[:, 4 * c:])
+    assert rel_l2(out.float(), ref) < 4e-3
+
+
+def test_gemm_bias_per_row_swapped():
+    ops, L = _ops()
+    m, n, k = 512, 300, 512      # D^T = W X^T : rows are output channels
+    w, x = rnd(m, k, scale=k ** -0.5, seed=1).bfloat16(), rnd(n, k, seed=2).bfloat16()
+    bias = rnd(m, seed=3)
+    out = torch.empty(m, 304, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(w, x, bias=bias, bias_per_row=True, out_bf16=out[:, :300]).run()
+    torch.cuda.synchronize()
+    ref = w.float() @ x.float().t() + bias[:, None]
+    assert rel_l2(out[:, :300].float(), ref) < 4e-3
+
+
+def _pad_layout(x_nhwc):
+    b, h, w, c = x_nhwc.shape
+    p = torch.zeros(b, h + 2, w + 2, c, device=x_nhwc.device, dtype=x_nhwc.dtype)
+    p[:, 1:-1, 1:-1] = x_nhwc
+    return p.reshape(-1, c)
+
+
+@pytest.mark.parametrize("b,h,w,cin,cout,cs", [(2, 8, 10, 64, 64, 0), (3, 15, 20, 320, 640, 0), (2, 30, 40, 640, 320, 960),
+                                               (1, 60, 80, 128, 4, 0), (2, 6, 20, 1280, 1280, 0)])
+def test_conv3x3_implicit_gemm(b, h, w, cin, cout, cs):
+    ops, L = _ops()
+    x = rnd(b, h, w, cin, seed=1).bfloat16()
+    wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=2).bfloat16()
+    bias = rnd(cout, seed=3)
+    res = rnd(b * h * w, cout, seed=4)
+    wmat = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1)
+    xs = None
+    if cs:
+        xs_nhwc = rnd(b, h, w, cs, seed=5).bfloat16()
+        ws = rnd(cout, cs, scale=cs ** -0.5, seed=6).bfloat16()
+        wmat = torch.cat([wmat, ws], dim=1)
+        ref = ref + F.conv2d(xs_nhwc.float().permute(0, 3, 1, 2), ws.float()[:, :, None, None])
+        xs = _pad_layout(xs_nhwc)
+    wmat = wmat.contiguous()
+    ref = ref.permute(0, 2, 3, 1).reshape(b * h * w, cout) + res
+    out = torch.full((b * h * w, cout), float("nan"), device=DEV)
+    ops.conv3x3(_pad_layout(x), wmat, b, h, w, a_short=xs, bias=bias, res1=res, out_f32=out).run()
+    torch.cuda.synchronize()
+    err = rel_l2(out, ref)
+    assert err < 2e-5, f"conv rel-L2 {err}"
+
+
+@pytest.mark.parametrize("batch,ntok,heads", [(1, 128, 1), (2, 300, 5), (1, 80, 20), (2, 1200, 10), (1, 4800, 5), (3, 468, 2)])
+def test_flash_attention(batch, ntok, heads):
+    ops, L = _ops()
+    c = heads * 64
+    qkv = rnd(batch * ntok, 3 * c, seed=1).bfloat16()
+    out = torch.zeros(batch * ntok, c, device=DEV, dtype=torch.bfloat16)
+    ops.flash_attn(qkv, batch, ntok, heads, out, 0, c, 2 * c).run()
+    torch.cuda.synchronize()
+    q, k, v = [t.float().reshape(batch, ntok, heads, 64).permute(0, 2, 1, 3) for t in qkv.split(c, dim=1)]
+    ref = torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1) @ v
+    ref = ref.permute(0, 2, 1, 3).reshape(batch * ntok, c)
+    err = rel_l2(out.float(), ref)
+    assert err < 1e-2, f"flash attention rel-L2 {err}"   # P and O are rounded to bf16
+
+
+@pytest.mark.parametrize("b,h,w,c0,c1,silu,pad", [(2, 8, 10, 320, 0, True, True), (1, 15, 20, 1280, 640, True, True),
+                                                  (2, 30, 40, 640, 320, True, True), (2, 6, 20, 320, 0, False, False),
+                                                  (1, 64, 96, 128, 0, True, True)])
+def test_group_norm(b, h, w, c0, c1, silu, pad):
+    ops, L = _ops()
+    x0 = rnd(b, h * w, c0, seed=1) * 2 + 0.5
+    x1 = rnd(b, h * w, c1, seed=2) - 0.3 if c1 else None
+    C = c0 + c1
+    gamma, beta = rnd(C, seed=3) + 1, rnd(C, seed=4)
+    hp, wp = (h + 2, w + 2) if pad else (h, w)
+    out = torch.full((b * hp * wp, C), float("nan"), device=DEV, dtype=torch.bfloat16)
+    raw = torch.full((b * hp * wp, C), float("nan"), device=DEV, dtype=torch.bfloat16)
+    partial = torch.empty(b * 64 * 32 * 2, device=DEV)
+    ops.group_norm(x0, b, h, w, gamma, beta, out, x1=x1, eps=1e-5, silu=silu, pad_out=pad, partial=partial, raw=raw).run()
+    torch.cuda.synchronize()
+    xc = torch.cat([x0, x1], dim=-1) if c1 else x0
+    xn = xc.reshape(b, h, w, C).permute(0, 3, 1, 2)
+    ref = F.group_norm(xn, 32, gamma, beta, eps=1e-5)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 3, 1)
+    rawref = xc.reshape(b, h, w, C)
+    if pad:
+        ref = _pad_layout(ref)
+        rawref = _pad_layout(rawref)
+    assert rel_l2(out.float(), ref.reshape(-1, C)) < 4e-3
+    assert rel_l2(raw.float(), rawref.reshape(-1, C)) < 4e-3
+    if pad:
+        halo = out.reshape(b, hp, wp, C)
+        assert halo[:, 0].abs().max() == 0 and halo[:, :, 0].abs().max() == 0 and halo[:, -1].abs().max() == 0
+
+
+@pytest.mark.parametrize("rows,c,bf16_in", [(1000, 320, False), (77, 640, False), (300, 1280, True)])
+def test_layer_norm(rows, c, bf16_in):
+    ops, L = _ops()
+    x = rnd(rows, c, seed=1) * 3 + 1
+    if bf16_in:
+        x = x.bfloat16()
+    ng = 2
+    rpg = (rows + 1) // 2
+    g0, b0, g1, b1 = rnd(ng, c, seed=2) + 1, rnd(ng, c, seed=3), rnd(ng, c, seed=4) + 1, rnd(ng, c, seed=5)
+    o0 = torch.empty(rows, c, device=DEV, dtype=torch.bfloat16)
+    o1 = torch.empty(rows, c, device=DEV, dtype=torch.bfloat16)
+    ops.layer_norm(x, g0, b0, o0, gamma1=g1, beta1=b1, out1=o1, rows_per_group=rpg).run()
+    torch.cuda.synchronize()
+    xn = F.layer_norm(x.float(), (c,), eps=1e-5)
+    grp = (torch.arange(rows, device=DEV) // rpg)
+    assert rel_l2(o0.float(), xn * g0[grp] + b0[grp]) < 4e-3
+    assert rel_l2(o1.float(), xn * g1[grp] + b1[grp]) < 4e-3
+
+
+@pytest.mark.parametrize("h,w,oh,ow", [(8, 10, 15, 20), (15, 20, 30, 40), (6, 20, 12, 39), (4, 4, 8, 8)])
+def test_upsample_pad(h, w, oh, ow):
+    ops, L = _ops()
+    b, c = 2, 64
+    x = rnd(b, h, w, c, seed=1)
+    out = torch.full((b * (oh + 2) * (ow + 2), c), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.upsample_pad(x, b, h, w, oh, ow, out).run()
+    torch.cuda.synchronize()
+    ref = F.interpolate(x.permute(0, 3, 1, 2), size=(oh, ow), mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(out.float(), _pad_layout(ref.bfloat16()).float())
+
+
+@pytest.mark.parametrize("c,stride,pt,pl,kpad", [(64, 2, 1, 1, 576), (128, 2, 0, 0, 1152), (3, 1, 1, 1, 64), (12, 1, 1, 1, 128)])
+def test_im2col(c, stride, pt, pl, kpad):
+    ops, L = _ops()
+    b, h, w = 2, 12, 14
+    x = rnd(b, h, w, c, seed=1)
+    if stride == 2 and pt == 0:
+        oh, ow = (h + 1 - 3) // 2 + 1, (w + 1 - 3) // 2 + 1     # diffusers Downsample2D: pad (0,1,0,1), stride 2
+    else:
+        oh, ow = (h + 2 * pt - 3) // stride + 1, (w + 2 * pl - 3) // stride + 1
+    out = torch.full((b * oh * ow, kpad), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.im2col(x, b, h, w, out, stride=stride, pad_t=pt, pad_l=pl, oh=oh, ow=ow).run()
+    torch.cuda.synchronize()
+    xn = x.permute(0, 3, 1, 2)
+    if stride == 2 and pt == 0:
+        xn = F.pad(xn, (0, 1, 0, 1))
+        cols = F.unfold(xn, 3, stride=2)
+    else:
+        cols = F.unfold(xn, 3, padding=pt, stride=stride)
+    cols = cols.reshape(b, c, 9, oh * ow).permute(0, 3, 2, 1).reshape(b * oh * ow, 9 * c)   # [pix, tap*c + ch]
+    assert torch.equal(out[:, :9 * c].float(), cols.bfloat16().float())
+    assert out[:, 9 * c:].abs().sum() == 0
+
+
+def test_xattn_small_keys():
+    ops, L = _ops()
+    heads, rows_per_group, groups = 5, 100, 3
+    c = heads * 64
+    q = rnd(groups * rows_per_group, c, seed=1).bfloat16()
+    kc, vc = rnd(7, 4, c, seed=2), rnd(7, 4, c, seed=3)
+    ntok = [3, 3, 3, 4, 4, 3, 3]
+    tog = [3, 0, 6]
+    out = torch.empty_like(q)
+    ops.xattn(q, kc, vc, ntok, tog, rows_per_group, heads, out).run()
+    torch.cuda.synchronize()
+    ref = torch.empty(groups * rows_per_group, c, device=DEV)
+    for g, t in enumerate(tog):
+        qq = q[g * rows_per_group:(g + 1) * rows_per_group].float().reshape(-1, heads, 64)
+        k = kc[t, :ntok[t]].reshape(ntok[t], heads, 64)
+        v = vc[t, :ntok[t]].reshape(ntok[t], heads, 64)
+        s = torch.einsum("nhd,jhd->nhj", qq, k) / 8.0
+        ref[g * rows_per_group:(g + 1) * rows_per_group] = torch.einsum("nhj,jhd->nhd", s.softmax(-1), v).reshape(-1, c)
+    assert rel_l2(out.float(), ref) < 4e-3
+
+
+@pytest.mark.parametrize("c", [320, 640, 1280])
+def test_task_attention(c):
+    ops, L = _ops()
+    rpg, nheads = 150, 4
+    main, src = [2, 0, 5], [0, 1, 2, 3, 4, 5, 6]
+    q = rnd(len(main) * rpg, c, seed=1).bfloat16()
+    k = rnd(len(src) * rpg, c, seed=2).bfloat16()
+    v = rnd(len(src) * rpg, c, seed=3).bfloat16()
+    out = torch.empty_like(q)
+    ops.task_attn(q, k, v, out, c, nheads, main, src, rpg).run()
+    torch.cuda.synchronize()
+    dh = c // nheads
+    ref = torch.empty(len(main) * rpg, c, device=DEV)
+    for g, t in enumerate(main):
+        sel = [i for i, s in enumerate(src) if s != t]
+        qq = q[g * rpg:(g + 1) * rpg].float().reshape(rpg, nheads, dh)
+        kk = torch.stack([k[i * rpg:(i + 1) * rpg].float() for i in sel], 1).reshape(rpg, len(sel), nheads, dh)
+        vv = torch.stack([v[i * rpg:(i + 1) * rpg].float() for i in sel], 1).reshape(rpg, len(sel), nheads, dh)
+        s = torch.einsum("nhd,nthd->nht", qq, kk) / math.sqrt(dh)
+        ref[g * rpg:(g + 1) * rpg] = torch.einsum("nht,nthd->nhd", s.softmax(-1), vv).reshape(rpg, c)
+    assert rel_l2(out.float(), ref) < 4e-3
+
+
+def test_softmax_rows():
+    ops, L = _ops()
+    s = rnd(300, 4800, seed=1) * 5
+    p = torch.empty(300, 4800, device=DEV, dtype=torch.bfloat16)
+    ops.softmax_rows(s, p, 0.25).run()
+    torch.cuda.synchronize()
+    assert rel_l2(p.float(), torch.softmax(s * 0.25, -1)) < 4e-3
+
+
+def test_task_map_modes():
+    ops, L = _ops()
+    b, hw = 2, 500
+    x = rnd(b, hw, 3, seed=1) * 1.2
+    pal = (torch.tensor([[128, 64, 128], [70, 70, 70], [153, 153, 153], [250, 170, 30], [220, 220, 0], [107, 142, 35],
+                         [70, 130, 180], [0, 0, 142]], dtype=torch.float32, device=DEV) / 255.0 * 2.0 - 1.0)
+    xc = x.clamp(-1, 1).permute(0, 2, 1)          # [b,3,hw]
+    clip = torch.empty(b, 1, hw, device=DEV); post = torch.empty(b, 1, hw, device=DEV)
+    ops.task_map(x, b, hw, L.MAP_MEAN1, out_clipped=clip, out_post=post).run()
+    m = x.mean(-1).clamp(-1, 1)[:, None]
+    assert torch.allclose(clip, m, atol=1e-6) and torch.allclose(post, (m + 1) / 2, atol=1e-6)
+    post3 = torch.empty(b, 3, hw, device=DEV)
+    ops.task_map(x, b, hw, L.MAP_NORMAL, out_post=post3).run()
+    assert torch.allclose(post3, xc / xc.norm(dim=1, keepdim=True).clamp_min(1e-30), atol=1e-6)
+    ops.task_map(x, b, hw, L.MAP_RGB3, out_post=post3).run()
+    assert torch.allclose(post3, (xc + 1) / 2, atol=1e-6)
+    f2 = torch.empty(b, 2, hw, device=DEV)
+    ops.task_map(x, b, hw, L.MAP_FLOW2, out_clipped=f2).run()
+    assert torch.equal(f2, xc[:, :2])
+    ids = torch.empty(b, hw, device=DEV, dtype=torch.int64)
+    ops.task_map(x, b, hw, L.MAP_SEMANTIC, out_ids=ids, palette=pal).run()
+    torch.cuda.synchronize()
+    ref = torch.cdist(xc.permute(0, 2, 1).reshape(-1, 3), pal).argmin(1).reshape(b, hw)
+    assert (ids == ref).float().mean() > 0.999
