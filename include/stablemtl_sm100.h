@@ -263,6 +263,19 @@ typedef struct smtl_unetin_args {
 } smtl_unetin_args;
 int smtl_unetin_run(const smtl_unetin_args* a, void* stream);
 
+/* Tiny per-pixel channel mix, fp32: y[m, j] = sum_i x[m, i] * w[j, i] + b[j]  (cin, cout <= 16).
+ * The 1x1 post_quant_conv of the VAE (diffusers AutoencoderKL, src/stablemtl_pipeline.py:640-642) with the
+ * 1/0.18215 latent scaling folded into w. */
+typedef struct smtl_chanmix_args {
+    const float* x;
+    int64_t rows;
+    int32_t cin, cout;
+    const float* w;         /* [cout, cin] */
+    const float* b;         /* [cout] or NULL */
+    float* y;
+} smtl_chanmix_args;
+int smtl_chanmix_run(const smtl_chanmix_args* a, void* stream);
+
 /* Task-map epilogue (src/stablemtl_pipeline.py:601,645-654 and the post-processing at :297-366):
  * x is the VAE decoder output fp32 [batch, hw, 3]. */
 enum {
@@ -292,7 +305,7 @@ int smtl_taskmap_run(const smtl_taskmap_args* a, void* stream);
 enum {
     SMTL_OP_GEMM = 1, SMTL_OP_FATTN = 2, SMTL_OP_SOFTMAX = 3, SMTL_OP_XATTN = 4, SMTL_OP_TASKATTN = 5,
     SMTL_OP_GN = 6, SMTL_OP_LN = 7, SMTL_OP_UPSAMPLE = 8, SMTL_OP_IM2COL = 9, SMTL_OP_RGBPREP = 10,
-    SMTL_OP_UNETIN = 11, SMTL_OP_TASKMAP = 12
+    SMTL_OP_UNETIN = 11, SMTL_OP_TASKMAP = 12, SMTL_OP_CHANMIX = 13
 };
 typedef struct smtl_op_ref {
     int32_t kind;

@@ -61,8 +61,8 @@ class Attention(nn.Module):
         scores = self.scale * torch.bmm(query, key.transpose(-1, -2))
         if attention_mask is not None:
             scores = scores + attention_mask
-        if self.upcast_softmax:
-            scores = scores.float()
+        if self.upcast_softmax and scores.dtype in (torch.float16, torch.bfloat16):
+            scores = scores.float()     # (diffusers upcasts unconditionally; a float64 pinning run must not be downcast)
         return scores.softmax(dim=-1).to(dtype)
 
     def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, **kwargs):

@@ -1,0 +1,91 @@
+"""Micro-benchmarks of the hot kernels on representative StableMTL shapes (CUDA events, L2 flushed between
+iterations).  Prints one line per case: time, TFLOP/s, fraction of the measured bf16 peak."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from stablemtl_b200 import ops, _lib as L  # noqa: E402
+
+DEV = "cuda"
+PEAK = 1630.0
+try:
+    PEAK = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["bf16_tflops"]
+except Exception:
+    pass
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+
+
+def timeit(op, iters=5):
+    for _ in range(2):
+        op.run()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        op.run()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def report(name, op, flops=None):
+    ms = timeit(op)
+    fl = op.flops if flops is None else flops
+    tf = fl / ms / 1e9
+    print(f"{name:56s} {ms:9.3f} ms {tf:8.1f} TFLOP/s  {tf / PEAK * 100:5.1f}% of measured burst peak", flush=True)
+
+
+def rb(*shape):
+    return (torch.randn(*shape, device=DEV) * 0.5).bfloat16()
+
+
+def gemm_case(name, m, n, k, **kw):
+    a, b = rb(m, k), rb(n, k)
+    out = torch.empty(m, n, device=DEV)
+    report(f"gemm {name} m={m} n={n} k={k}", ops.gemm(a, b, out_f32=out, **kw))
+
+
+def conv_case(name, batch, h, w, cin, cout):
+    a = rb(batch * (h + 2) * (w + 2), cin)
+    wm = rb(cout, 9 * cin)
+    out = torch.empty(batch * h * w, cout, device=DEV)
+    bias = torch.zeros(cout, device=DEV)
+    report(f"conv3x3 {name} b={batch} {h}x{w} {cin}->{cout}", ops.conv3x3(a, wm, batch, h, w, bias=bias, out_f32=out))
+
+
+def attn_case(batch, ntok, heads):
+    c = heads * 64
+    qkv = rb(batch * ntok, 3 * c)
+    out = torch.empty(batch * ntok, c, device=DEV, dtype=torch.bfloat16)
+    report(f"flash_attn b={batch} ntok={ntok} heads={heads}", ops.flash_attn(qkv, batch, ntok, heads, out, 0, c, 2 * c))
+
+
+if __name__ == "__main__":
+    gemm_case("square", 8192, 8192, 8192)
+    gemm_case("square bn128", 8192, 8192, 8192, block_n=128)
+    gemm_case("ff1 L0", 16 * 4800, 2560, 320)
+    gemm_case("ff2 L0", 16 * 4800, 320, 1280)
+    gemm_case("qkv L0", 16 * 4800, 960, 320)
+    gemm_case("lin L0", 16 * 4800, 320, 320)
+    gemm_case("ff1 L1", 16 * 1200, 5120, 640)
+    gemm_case("lin L2", 16 * 300, 1280, 1280)
+    gemm_case("ff1 L2", 112 * 300, 10240, 1280)
+    conv_case("unet L0", 16, 60, 80, 320, 320)
+    conv_case("unet L0 cat", 16, 60, 80, 960, 320)
+    conv_case("unet L1", 16, 30, 40, 640, 640)
+    conv_case("unet L2", 16, 15, 20, 1280, 1280)
+    conv_case("unet L2 cat", 16, 15, 20, 2560, 1280)
+    conv_case("unet L3", 112, 8, 10, 1280, 1280)
+    conv_case("vae 1/1", 2, 480, 640, 128, 128)
+    conv_case("vae 1/2", 2, 240, 320, 256, 256)
+    conv_case("vae 1/4", 4, 120, 160, 512, 512)
+    conv_case("vae 1/8", 8, 60, 80, 512, 512)
+    attn_case(16, 4800, 5)
+    attn_case(16, 1200, 10)
+    attn_case(16, 300, 20)

@@ -17,7 +17,7 @@ ACT_NONE, ACT_GELU, ACT_GEGLU, ACT_SILU = 0, 1, 2, 3
 ROWMAP_IDENTITY, ROWMAP_CONV_PAD = 0, 1
 MAP_MEAN1, MAP_RGB3, MAP_NORMAL, MAP_FLOW2, MAP_FLOW3, MAP_SEMANTIC = range(6)
 (OP_GEMM, OP_FATTN, OP_SOFTMAX, OP_XATTN, OP_TASKATTN, OP_GN, OP_LN, OP_UPSAMPLE, OP_IM2COL, OP_RGBPREP,
- OP_UNETIN, OP_TASKMAP) = range(1, 13)
+ OP_UNETIN, OP_TASKMAP, OP_CHANMIX) = range(1, 14)
 
 vp = C.c_void_p
 i32 = C.c_int32
@@ -137,6 +137,10 @@ class UnetinArgs(C.Structure):
                 ("out", vp)]
 
 
+class ChanmixArgs(C.Structure):
+    _fields_ = [("x", vp), ("rows", i64), ("cin", i32), ("cout", i32), ("w", vp), ("b", vp), ("y", vp)]
+
+
 class TaskmapArgs(C.Structure):
     _fields_ = [("x", vp), ("batch", i32), ("hw", i32), ("mode", i32), ("out_clipped", vp), ("out_post", vp),
                 ("out_ids", vp), ("palette", vp), ("npalette", i32), ("pad_", i32)]
@@ -147,12 +151,12 @@ class OpRef(C.Structure):
 
 
 STRUCTS_IN_HEADER_ORDER = [GemmSeg, GemmArgs, GemmOp, FattnArgs, FattnOp, SoftmaxArgs, XattnArgs, TaskAttnArgs,
-                           GnArgs, LnArgs, UpsampleArgs, Im2colArgs, RgbprepArgs, UnetinArgs, TaskmapArgs, OpRef]
+                           GnArgs, LnArgs, UpsampleArgs, Im2colArgs, RgbprepArgs, UnetinArgs, ChanmixArgs, TaskmapArgs, OpRef]
 
 EXPORTS = [
     "smtl_gemm_plan", "smtl_gemm_run", "smtl_fattn_plan", "smtl_fattn_run", "smtl_softmax_run", "smtl_xattn_run",
     "smtl_taskattn_run", "smtl_gn_run", "smtl_ln_run", "smtl_upsample_run", "smtl_im2col_run", "smtl_rgbprep_run",
-    "smtl_unetin_run", "smtl_taskmap_run", "smtl_run_plan", "smtl_plan_launches", "smtl_abi_version",
+    "smtl_unetin_run", "smtl_chanmix_run", "smtl_taskmap_run", "smtl_run_plan", "smtl_plan_launches", "smtl_abi_version",
     "smtl_last_error", "smtl_struct_sizes",
 ]
 

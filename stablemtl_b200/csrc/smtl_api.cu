@@ -85,7 +85,8 @@ int smtl_struct_sizes(int32_t* out, int32_t cap) {
         (int32_t)sizeof(smtl_fattn_args),   (int32_t)sizeof(smtl_fattn_op),     (int32_t)sizeof(smtl_softmax_args),
         (int32_t)sizeof(smtl_xattn_args),   (int32_t)sizeof(smtl_taskattn_args), (int32_t)sizeof(smtl_gn_args),
         (int32_t)sizeof(smtl_ln_args),      (int32_t)sizeof(smtl_upsample_args), (int32_t)sizeof(smtl_im2col_args),
-        (int32_t)sizeof(smtl_rgbprep_args), (int32_t)sizeof(smtl_unetin_args),  (int32_t)sizeof(smtl_taskmap_args),
+        (int32_t)sizeof(smtl_rgbprep_args), (int32_t)sizeof(smtl_unetin_args),  (int32_t)sizeof(smtl_chanmix_args),
+        (int32_t)sizeof(smtl_taskmap_args),
         (int32_t)sizeof(smtl_op_ref)};
     const int n = (int)(sizeof(sizes) / sizeof(sizes[0]));
     for (int i = 0; i < n && i < cap; ++i) out[i] = sizes[i];
@@ -115,6 +116,7 @@ int smtl_run_plan(const smtl_op_ref* ops, int32_t n_ops, void* stream) {
             case SMTL_OP_RGBPREP: rc = smtl_rgbprep_run((const smtl_rgbprep_args*)p, stream); break;
             case SMTL_OP_UNETIN: rc = smtl_unetin_run((const smtl_unetin_args*)p, stream); break;
             case SMTL_OP_TASKMAP: rc = smtl_taskmap_run((const smtl_taskmap_args*)p, stream); break;
+            case SMTL_OP_CHANMIX: rc = smtl_chanmix_run((const smtl_chanmix_args*)p, stream); break;
             default:
                 smtl_host::set_error("plan op %d: unknown kind %d", i, ops[i].kind);
                 return SMTL_EKIND;

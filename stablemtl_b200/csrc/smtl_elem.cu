@@ -455,6 +455,19 @@ __global__ void taskattn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_
     }
 }
 
+__global__ void chanmix_kernel(const float* __restrict__ x, int64_t rows, int cin, int cout, const float* __restrict__ w,
+                               const float* __restrict__ b, float* __restrict__ y) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+        float in[16];
+        for (int i = 0; i < cin; ++i) in[i] = x[r * cin + i];
+        for (int j = 0; j < cout; ++j) {
+            float acc = b ? b[j] : 0.f;
+            for (int i = 0; i < cin; ++i) acc += in[i] * w[j * cin + i];
+            y[r * cout + j] = acc;
+        }
+    }
+}
+
 // ============================================================================================= task-map epilogue
 __device__ __forceinline__ float clip1(float v) { return fminf(fmaxf(v, -1.0f), 1.0f); }
 
@@ -660,6 +673,15 @@ extern "C" int smtl_taskattn_run(const smtl_taskattn_args* a, void* stream) {
                                                     (const __nv_bfloat16*)a->v_bf16, (__nv_bfloat16*)a->out_bf16, a->c,
                                                     a->nheads, a->n_main, a->n_src, a->rows_per_group, ids,
                                                     a->exclude_self, a->scale);
+    SMTL_CHECK_CUDA(cudaGetLastError());
+    return SMTL_OK;
+}
+
+extern "C" int smtl_chanmix_run(const smtl_chanmix_args* a, void* stream) {
+    SMTL_CHECK_ARG(a && a->x && a->w && a->y, "chanmix: NULL argument");
+    SMTL_CHECK_ARG(a->cin >= 1 && a->cin <= 16 && a->cout >= 1 && a->cout <= 16 && a->rows > 0, "chanmix: bad shape");
+    chanmix_kernel<<<grid_for(a->rows, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a->x, a->rows, a->cin,
+                                                                                              a->cout, a->w, a->b, a->y);
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;
 }

@@ -1,0 +1,628 @@
+"""Plan builders: the SD-2 UNet (single-stream / child / multi-stream main) and the SD-2 VAE expressed as
+launch lists over the C-ABI kernels (ops.py).  A plan is built once per (batch, resolution) with statically
+assigned buffers and replayed natively (`Plan.run()` -> smtl_run_plan).
+
+Layouts: feature maps are pixel-major matrices; the residual stream is fp32 "compact" [B*H*W, C]; conv/GEMM
+operands are bf16 (padded zero-halo layout for 3x3 convs).  See include/stablemtl_sm100.h.
+
+Reference structure followed (paths under /root/reference):
+  UNet   src/model/unet.py:284-445, src/model/unet_blocks.py, src/model/resnet.py, src/model/attention.py
+  VAE    diffusers AutoencoderKL as used by src/stablemtl_pipeline.py:607-656
+"""
+import math
+
+import torch
+
+from . import _lib as L
+from . import ops
+from .synth import UNetConfig, VAEConfig
+from .weights import conv_weight_matrix, interleave_geglu
+
+BF16, F32 = torch.bfloat16, torch.float32
+LATENT_SCALE = 0.18215          # stablemtl_pipeline.py:134-135
+
+
+def down_size(n):               # conv 3x3 stride 2 pad 1 (resnet.py:87)
+    return (n - 1) // 2 + 1
+
+
+class Pool:
+    """Plan-time buffer pool: intermediates are carved out of reusable device blocks; a block returns to the free
+    list when the builder releases it (stream order makes reuse after the last consumer safe)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.free = []          # list of uint8 tensors
+        self.owner = {}         # data_ptr -> block
+        self.total = 0
+
+    def alloc(self, shape, dtype):
+        n = 1
+        for s in shape:
+            n *= int(s)
+        nbytes = max(256, (n * torch.empty((), dtype=dtype).element_size() + 255) // 256 * 256)
+        best = None
+        for i, blk in enumerate(self.free):
+            if blk.numel() >= nbytes and (best is None or blk.numel() < self.free[best].numel()):
+                best = i
+        if best is not None and self.free[best].numel() <= max(2 * nbytes, nbytes + (64 << 20)):
+            blk = self.free.pop(best)
+        else:
+            blk = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.total += nbytes
+        t = blk[: n * torch.empty((), dtype=dtype).element_size()].view(dtype).reshape(shape)
+        self.owner[t.data_ptr()] = blk
+        return t
+
+    def release(self, *tensors):
+        for t in tensors:
+            if t is None:
+                continue
+            blk = self.owner.pop(t.data_ptr(), None)
+            if blk is not None:
+                self.free.append(blk)
+
+
+def _dev(t, device, dtype=F32):
+    return t.to(device=device, dtype=dtype).contiguous()
+
+
+# ================================================================================================== UNet weights
+class UNetWeights:
+    """Reference state dict (Appendix B key layout) -> kernel layouts, with load-time constant folding:
+    time embedding -> conv1 bias (t = 999, stablemtl_pipeline.py:552), text -> per-layer cross-attention K/V
+    (stablemtl_pipeline.py:464-472), shortcut weights/bias appended to conv2."""
+
+    def __init__(self, sd, cfg: UNetConfig, text, tasks, device, timestep=999):
+        self.cfg, self.device, self.tasks = cfg, device, list(tasks)
+        self.w = {}
+        d = device
+        g = lambda k: sd[k].to(d, F32)
+        c = cfg.block_out_channels
+        # --- time embedding (unet.py:347-353; diffusers Timesteps flip_sin_to_cos=True, shift 0)
+        half = c[0] // 2
+        freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=F32) / half)
+        e = torch.tensor([float(timestep)])[:, None] * freqs[None, :]
+        emb = torch.cat([torch.cos(e), torch.sin(e)], dim=-1).to(d)
+        emb = torch.nn.functional.linear(emb, g("time_embedding.linear_1.weight"), g("time_embedding.linear_1.bias"))
+        temb = torch.nn.functional.linear(torch.nn.functional.silu(emb), g("time_embedding.linear_2.weight"),
+                                          g("time_embedding.linear_2.bias"))
+        self.silu_temb = torch.nn.functional.silu(temb)[0]
+        # --- text tokens, padded to 4 per task
+        self.ntok = [text[t].shape[0] for t in self.tasks]
+        txt = torch.zeros(len(self.tasks), 4, cfg.cross_attention_dim, device=d)
+        for i, t in enumerate(self.tasks):
+            txt[i, : self.ntok[i]] = text[t].to(d, F32)
+        self.text = txt
+        # --- stem / head
+        w_in = g("conv_in.weight")                                   # [c0, 12, 3, 3]
+        kin = 9 * cfg.in_channels
+        self.kin_pad = (kin + 63) // 64 * 64
+        wm = torch.zeros(c[0], self.kin_pad, device=d)
+        wm[:, :kin] = conv_weight_matrix(w_in)
+        self.w["conv_in.w"] = wm.to(BF16)
+        self.w["conv_in.b"] = g("conv_in.bias")
+        self.w["conv_out.w"] = conv_weight_matrix(g("conv_out.weight")).to(BF16)
+        self.w["conv_out.b"] = g("conv_out.bias")
+        self.w["conv_norm_out.g"], self.w["conv_norm_out.b"] = g("conv_norm_out.weight"), g("conv_norm_out.bias")
+        self._sd, self._g = sd, g
+
+    # lazily converted per-module weights (cached)
+    def resnet(self, p):
+        if p + ".w1" not in self.w:
+            g, w = self._g, self.w
+            w[p + ".n1g"], w[p + ".n1b"] = g(p + ".norm1.weight"), g(p + ".norm1.bias")
+            w[p + ".n2g"], w[p + ".n2b"] = g(p + ".norm2.weight"), g(p + ".norm2.bias")
+            w[p + ".w1"] = conv_weight_matrix(g(p + ".conv1.weight")).to(BF16)
+            b1 = g(p + ".conv1.bias")
+            if (p + ".time_emb_proj.weight") in self._sd:            # resnet.py:183-186, constant at inference
+                b1 = b1 + torch.nn.functional.linear(self.silu_temb, g(p + ".time_emb_proj.weight"),
+                                                     g(p + ".time_emb_proj.bias"))
+            w[p + ".b1"] = b1.contiguous()
+            w2 = conv_weight_matrix(g(p + ".conv2.weight"))
+            b2 = g(p + ".conv2.bias")
+            if (p + ".conv_shortcut.weight") in self._sd:
+                ws = g(p + ".conv_shortcut.weight")
+                w2 = torch.cat([w2, ws.reshape(ws.shape[0], ws.shape[1])], dim=1)
+                b2 = b2 + g(p + ".conv_shortcut.bias")
+                w[p + ".short"] = True
+            w[p + ".w2"] = w2.to(BF16).contiguous()
+            w[p + ".b2"] = b2.contiguous()
+        return self.w
+
+    def conv(self, p):
+        if p + ".w" not in self.w:
+            self.w[p + ".w"] = conv_weight_matrix(self._g(p + ".weight")).to(BF16)
+            self.w[p + ".b"] = self._g(p + ".bias")
+        return self.w[p + ".w"], self.w[p + ".b"]
+
+    def transformer(self, p):
+        if p + ".qkv" not in self.w:
+            g, w = self._g, self.w
+            t = p + ".transformer_blocks.0"
+            w[p + ".ng"], w[p + ".nb"] = g(p + ".norm.weight"), g(p + ".norm.bias")
+            for n in ("proj_in", "proj_out"):
+                w[f"{p}.{n}.w"], w[f"{p}.{n}.b"] = g(f"{p}.{n}.weight").to(BF16), g(f"{p}.{n}.bias")
+            for i in (1, 2, 3):
+                w[f"{p}.ln{i}g"], w[f"{p}.ln{i}b"] = g(f"{t}.norm{i}.weight"), g(f"{t}.norm{i}.bias")
+            w[p + ".qkv"] = torch.cat([g(f"{t}.attn1.to_q.weight"), g(f"{t}.attn1.to_k.weight"),
+                                       g(f"{t}.attn1.to_v.weight")], dim=0).to(BF16).contiguous()
+            w[p + ".o.w"], w[p + ".o.b"] = g(f"{t}.attn1.to_out.0.weight").to(BF16), g(f"{t}.attn1.to_out.0.bias")
+            w[p + ".q2"] = g(f"{t}.attn2.to_q.weight").to(BF16)
+            # cross-attention keys/values of the constant task-name tokens: [ntask, 4, C] fp32
+            w[p + ".kc"] = torch.nn.functional.linear(self.text, g(f"{t}.attn2.to_k.weight")).contiguous()
+            w[p + ".vc"] = torch.nn.functional.linear(self.text, g(f"{t}.attn2.to_v.weight")).contiguous()
+            w[p + ".o2.w"], w[p + ".o2.b"] = g(f"{t}.attn2.to_out.0.weight").to(BF16), g(f"{t}.attn2.to_out.0.bias")
+            wi, bi = interleave_geglu(g(f"{t}.ff.net.0.proj.weight"), g(f"{t}.ff.net.0.proj.bias"))
+            w[p + ".ff1.w"], w[p + ".ff1.b"] = wi.to(BF16), bi
+            w[p + ".ff2.w"], w[p + ".ff2.b"] = g(f"{t}.ff.net.2.weight").to(BF16), g(f"{t}.ff.net.2.bias")
+        return self.w
+
+    def task_modules(self, p):
+        """per-task MLPs / norms stacked over tasks (util/model.py:102-146)."""
+        if p + ".tq0.w" not in self.w:
+            g, w = self._g, self.w
+            a = p + ".transformer_blocks.0.attn1"
+            T = self.tasks
+            st = lambda fmt, dt=F32: torch.stack([g(fmt.format(t=t)) for t in T]).to(dt).contiguous()
+            for kv in ("k", "v"):
+                w[f"{p}.t{kv}1.w"], w[f"{p}.t{kv}1.b"] = st(a + ".task_to_" + kv + ".{t}.fc1.weight", BF16), st(a + ".task_to_" + kv + ".{t}.fc1.bias")
+                w[f"{p}.t{kv}2.w"], w[f"{p}.t{kv}2.b"] = st(a + ".task_to_" + kv + ".{t}.fc2.weight", BF16), st(a + ".task_to_" + kv + ".{t}.fc2.bias")
+                w[f"{p}.tn{kv}.g"], w[f"{p}.tn{kv}.b"] = st(a + ".task_norm_" + kv + ".{t}.weight"), st(a + ".task_norm_" + kv + ".{t}.bias")
+            for i, n in enumerate((0, 2, 4, 6)):
+                w[f"{p}.tq{i}.w"], w[f"{p}.tq{i}.b"] = st(a + ".task_to_q.{t}.net." + str(n) + ".weight", BF16), st(a + ".task_to_q.{t}.net." + str(n) + ".bias")
+            w[f"{p}.tnq.g"], w[f"{p}.tnq.b"] = st(a + ".task_norm_q.{t}.weight"), st(a + ".task_norm_q.{t}.bias")
+            w[p + ".tout.w"], w[p + ".tout.b"] = g(a + ".to_out_task.weight").to(BF16), g(a + ".to_out_task.bias")
+        return self.w
+
+
+# ================================================================================================== UNet plan
+class UNetPlan:
+    """One batched UNet pass over `groups` row groups of `images` images each (group g runs task group_tasks[g]).
+
+    mode "single": plain UNet (StableMTL-S / child without taps)
+    mode "child" : also writes the 16 attn1 outputs (bf16) for the task attention of the main pass
+    mode "main"  : consumes `feats` (list of 16 bf16 [n_src*images*N_l, C_l], rows grouped by source task)
+    """
+
+    def __init__(self, W: UNetWeights, images, h, w, group_tasks, mode="single", feats=None, src_tasks=None,
+                 pool=None, x_in=None):
+        cfg = W.cfg
+        self.W, self.cfg, self.mode = W, cfg, mode
+        dev = W.device
+        self.pool = pool or Pool(dev)
+        P = self.pool
+        self.plan = ops.Plan()
+        add = self.plan.add
+        G = len(group_tasks)
+        Be = G * images
+        self.Be, self.h, self.w = Be, h, w
+        c = cfg.block_out_channels
+        nlev = len(c)
+        sizes = [(h, w)]
+        for _ in range(nlev - 1):
+            sizes.append((down_size(sizes[-1][0]), down_size(sizes[-1][1])))
+        self.gn_partial = torch.empty(Be * 64 * 32 * 2, device=dev, dtype=F32)
+        self.group_tasks = list(group_tasks)
+        self.images = images
+        self.feats_out = [] if mode == "child" else None
+        self.feats_in, self.src_tasks = feats, src_tasks
+        self.layer = 0
+
+        # ---- stem: [Be, hw, 12] fp32 -> im2col -> GEMM
+        self.x_in = x_in if x_in is not None else torch.zeros(Be * h * w, cfg.in_channels, device=dev, dtype=F32)
+        col = P.alloc((Be * h * w, W.kin_pad), BF16)
+        add(ops.im2col(self.x_in.view(Be, h, w, cfg.in_channels), Be, h, w, col, stride=1, pad_t=1, pad_l=1, oh=h, ow=w))
+        x = P.alloc((Be * h * w, c[0]), F32)
+        add(ops.gemm(col, W.w["conv_in.w"], bias=W.w["conv_in.b"], out_f32=x, name="conv_in"))
+        P.release(col)
+
+        skips = [x]
+        ch = c[0]
+        for i in range(nlev):
+            hh, ww = sizes[i]
+            for j in range(cfg.layers_per_block):
+                x_new = self.resnet(f"down_blocks.{i}.resnets.{j}", x, None, hh, ww, c[i])
+                if x is not skips[-1]:
+                    P.release(x)
+                x = x_new
+                if i < nlev - 1:
+                    x_new = self.transformer(f"down_blocks.{i}.attentions.{j}", x, hh, ww, c[i], cfg.heads[i])
+                    P.release(x)
+                    x = x_new
+                skips.append(x)
+            if i < nlev - 1:
+                h2, w2 = sizes[i + 1]
+                wt, bs = W.conv(f"down_blocks.{i}.downsamplers.0.conv")
+                col = P.alloc((Be * h2 * w2, 9 * c[i]), BF16)
+                add(ops.im2col(x.view(Be, hh, ww, c[i]), Be, hh, ww, col, stride=2, pad_t=1, pad_l=1, oh=h2, ow=w2))
+                x = P.alloc((Be * h2 * w2, c[i]), F32)
+                add(ops.gemm(col, wt, bias=bs, out_f32=x, name="downsample"))
+                P.release(col)
+                skips.append(x)
+        hh, ww = sizes[-1]
+        x_new = self.resnet("mid_block.resnets.0", x, None, hh, ww, c[-1])
+        x = x_new                                   # previous x is still referenced as a skip
+        x_new = self.transformer("mid_block.attentions.0", x, hh, ww, c[-1], cfg.heads[-1])
+        P.release(x)
+        x = x_new
+        x_new = self.resnet("mid_block.resnets.1", x, None, hh, ww, c[-1])
+        P.release(x)
+        x = x_new
+        for i in range(nlev):
+            lev = nlev - 1 - i
+            hh, ww = sizes[lev]
+            cout = c[lev]
+            for j in range(cfg.layers_per_block + 1):
+                skip = skips.pop()
+                x_new = self.resnet(f"up_blocks.{i}.resnets.{j}", x, skip, hh, ww, cout)
+                P.release(x, skip)
+                x = x_new
+                if i > 0:
+                    x_new = self.transformer(f"up_blocks.{i}.attentions.{j}", x, hh, ww, cout, cfg.heads[lev])
+                    P.release(x)
+                    x = x_new
+            if i < nlev - 1:
+                oh, ow = sizes[lev - 1]                       # explicit size of the next skip (unet.py:415-416)
+                wt, bs = W.conv(f"up_blocks.{i}.upsamplers.0.conv")
+                up = P.alloc((Be * (oh + 2) * (ow + 2), cout), BF16)
+                add(ops.upsample_pad(x.view(Be, hh, ww, cout), Be, hh, ww, oh, ow, up))
+                x_new = P.alloc((Be * oh * ow, cout), F32)
+                add(ops.conv3x3(up, wt, Be, oh, ow, bias=bs, out_f32=x_new, name="upsample_conv"))
+                P.release(up, x)
+                x = x_new
+        # ---- head
+        a = P.alloc((Be * (h + 2) * (w + 2), c[0]), BF16)
+        add(ops.group_norm(x, Be, h, w, W.w["conv_norm_out.g"], W.w["conv_norm_out.b"], a, eps=cfg.norm_eps, silu=True,
+                           pad_out=True, partial=self.gn_partial, groups=cfg.norm_num_groups))
+        self.out = torch.empty(Be * h * w, cfg.out_channels, device=dev, dtype=F32)
+        add(ops.conv3x3(a, W.w["conv_out.w"], Be, h, w, bias=W.w["conv_out.b"], out_f32=self.out, name="conv_out"))
+        P.release(a, x)
+        self.plan.finalize()
+
+    # ---------------------------------------------------------------------------------------------- resnet
+    def resnet(self, p, x, skip, h, w, cout):
+        """ResnetBlock3D (resnet.py:174-204) on the virtual concat [x, skip] (unet_blocks.py:509,597)."""
+        W, P, add, cfg, Be = self.W, self.pool, self.plan.add, self.cfg, self.Be
+        wt = W.resnet(p)
+        cin = x.shape[1] + (skip.shape[1] if skip is not None else 0)
+        short = wt.get(p + ".short", False)
+        a1 = P.alloc((Be * (h + 2) * (w + 2), cin), BF16)
+        raw = P.alloc((Be * (h + 2) * (w + 2), cin), BF16) if short else None
+        add(ops.group_norm(x, Be, h, w, wt[p + ".n1g"], wt[p + ".n1b"], a1, x1=skip, eps=cfg.norm_eps, silu=True,
+                           pad_out=True, partial=self.gn_partial, raw=raw, groups=cfg.norm_num_groups))
+        h1 = P.alloc((Be * h * w, cout), F32)
+        add(ops.conv3x3(a1, wt[p + ".w1"], Be, h, w, bias=wt[p + ".b1"], out_f32=h1, name="res.conv1"))
+        P.release(a1)
+        a2 = P.alloc((Be * (h + 2) * (w + 2), cout), BF16)
+        add(ops.group_norm(h1, Be, h, w, wt[p + ".n2g"], wt[p + ".n2b"], a2, eps=cfg.norm_eps, silu=True, pad_out=True,
+                           partial=self.gn_partial, groups=cfg.norm_num_groups))
+        P.release(h1)
+        out = P.alloc((Be * h * w, cout), F32)
+        add(ops.conv3x3(a2, wt[p + ".w2"], Be, h, w, a_short=raw, bias=wt[p + ".b2"], res1=None if short else x,
+                        out_f32=out, name="res.conv2"))
+        P.release(a2, raw)
+        return out
+
+    # ---------------------------------------------------------------------------------------------- transformer
+    def transformer(self, p, x, h, w, C, heads):
+        """Transformer3DModel + BasicTransformerBlock (attention.py:174-223, 323-380) on tokens [Be*N, C]."""
+        W, P, add, cfg, Be = self.W, self.pool, self.plan.add, self.cfg, self.Be
+        wt = W.transformer(p)
+        N = h * w
+        M = Be * N
+        rpg = self.images * N                      # rows per task group
+        xn = P.alloc((M, C), BF16)
+        add(ops.group_norm(x, Be, h, w, wt[p + ".ng"], wt[p + ".nb"], xn, eps=1e-6, silu=False, pad_out=False,
+                           partial=self.gn_partial, groups=cfg.norm_num_groups))
+        hs = P.alloc((M, C), F32)
+        add(ops.gemm(xn, wt[p + ".proj_in.w"], bias=wt[p + ".proj_in.b"], out_f32=hs, name="proj_in"))
+        n1 = xn                                    # reuse as LN output
+        add(ops.layer_norm(hs, wt[p + ".ln1g"], wt[p + ".ln1b"], n1))
+        qkv = P.alloc((M, 3 * C), BF16)
+        add(ops.gemm(n1, wt[p + ".qkv"], out_bf16=qkv, name="qkv"))
+        att = n1
+        add(ops.flash_attn(qkv, Be, N, heads, att, 0, C, 2 * C))
+        P.release(qkv)
+        if self.mode != "main":
+            feat = None
+            if self.mode == "child":
+                feat = torch.empty(M, C, device=W.device, dtype=BF16)      # owned by the plan, read by the main pass
+                self.feats_out.append(feat)
+            # h += to_out(attn); the pre-residual value is the "afterSelfAttn_residual" tap (attention.py:348-349)
+            add(ops.gemm(att, wt[p + ".o.w"], bias=wt[p + ".o.b"], res1=hs, out_f32=hs, aux_bf16=feat, name="attn_out"))
+        else:
+            tw = W.task_modules(p)
+            nT = len(W.tasks)
+            attn_out = P.alloc((M, C), F32)
+            add(ops.gemm(att, wt[p + ".o.w"], bias=wt[p + ".o.b"], out_f32=attn_out, name="attn_out"))
+            # q = MLPv2_q[main task](LN_q[main task](attn_out))         attention.py:512
+            qn = att
+            gq = torch.stack([tw[p + ".tnq.g"][t] for t in self.group_tasks]).contiguous()
+            bq = torch.stack([tw[p + ".tnq.b"][t] for t in self.group_tasks]).contiguous()
+            add(ops.layer_norm(attn_out, gq, bq, qn, rows_per_group=rpg))
+            hq = cfg.task_q_hidden
+            q1, q2 = P.alloc((M, hq), BF16), P.alloc((M, hq), BF16)
+            tq = P.alloc((M, C), BF16)
+            for gi, t in enumerate(self.group_tasks):
+                r = slice(gi * rpg, (gi + 1) * rpg)
+                add(ops.gemm(qn[r], tw[p + ".tq0.w"][t], bias=tw[p + ".tq0.b"][t], act=L.ACT_GELU, out_bf16=q1[r], name="task_q0"))
+                add(ops.gemm(q1[r], tw[p + ".tq1.w"][t], bias=tw[p + ".tq1.b"][t], act=L.ACT_GELU, out_bf16=q2[r], name="task_q1"))
+                add(ops.gemm(q2[r], tw[p + ".tq2.w"][t], bias=tw[p + ".tq2.b"][t], act=L.ACT_GELU, out_bf16=q1[r], name="task_q2"))
+                add(ops.gemm(q1[r], tw[p + ".tq3.w"][t], bias=tw[p + ".tq3.b"][t], out_bf16=tq[r], name="task_q3"))
+            P.release(q1, q2)
+            # k_t, v_t = MLP_{k,v}[t](LN_{k,v}[t](feat_t)) once per source stream           attention.py:494-495
+            F_l = self.feats_in[self.layer]
+            S = len(self.src_tasks)
+            Ms = S * rpg
+            assert F_l.shape == (Ms, C), (F_l.shape, Ms, C)
+            kn, vn = P.alloc((Ms, C), BF16), P.alloc((Ms, C), BF16)
+            gk = torch.stack([tw[p + ".tnk.g"][t] for t in self.src_tasks]).contiguous()
+            bk = torch.stack([tw[p + ".tnk.b"][t] for t in self.src_tasks]).contiguous()
+            gv = torch.stack([tw[p + ".tnv.g"][t] for t in self.src_tasks]).contiguous()
+            bv = torch.stack([tw[p + ".tnv.b"][t] for t in self.src_tasks]).contiguous()
+            add(ops.layer_norm(F_l, gk, bk, kn, gamma1=gv, beta1=bv, out1=vn, rows_per_group=rpg))
+            hk, hv = P.alloc((Ms, C // 2), BF16), P.alloc((Ms, C // 2), BF16)
+            K, V = P.alloc((Ms, C), BF16), P.alloc((Ms, C), BF16)
+            for si, t in enumerate(self.src_tasks):
+                r = slice(si * rpg, (si + 1) * rpg)
+                add(ops.gemm(kn[r], tw[p + ".tk1.w"][t], bias=tw[p + ".tk1.b"][t], act=L.ACT_GELU, out_bf16=hk[r], name="task_k1"))
+                add(ops.gemm(vn[r], tw[p + ".tv1.w"][t], bias=tw[p + ".tv1.b"][t], act=L.ACT_GELU, out_bf16=hv[r], name="task_v1"))
+                add(ops.gemm(hk[r], tw[p + ".tk2.w"][t], bias=tw[p + ".tk2.b"][t], out_bf16=K[r], name="task_k2"))
+                add(ops.gemm(hv[r], tw[p + ".tv2.w"][t], bias=tw[p + ".tv2.b"][t], out_bf16=V[r], name="task_v2"))
+            P.release(kn, vn, hk, hv)
+            ta = qn
+            add(ops.task_attn(tq, K, V, ta, C, cfg.n_attns, self.group_tasks, self.src_tasks, rpg, exclude_self=True))
+            P.release(tq, K, V)
+            # h += attn_out + to_out_task(task attention)                                   attention.py:598-600, :347
+            add(ops.gemm(ta, tw[p + ".tout.w"], bias=tw[p + ".tout.b"], res1=attn_out, res2=hs, out_f32=hs, name="to_out_task"))
+            P.release(attn_out)
+        self.layer += 1
+        # ---- cross-attention on the task-name tokens (attention.py:355-364)
+        n2 = att
+        add(ops.layer_norm(hs, wt[p + ".ln2g"], wt[p + ".ln2b"], n2))
+        q2b = P.alloc((M, C), BF16)
+        add(ops.gemm(n2, wt[p + ".q2"], out_bf16=q2b, name="xattn_q"))
+        xa = n2
+        add(ops.xattn(q2b, wt[p + ".kc"], wt[p + ".vc"], W.ntok, self.group_tasks, rpg, heads, xa))
+        P.release(q2b)
+        add(ops.gemm(xa, wt[p + ".o2.w"], bias=wt[p + ".o2.b"], res1=hs, out_f32=hs, name="xattn_out"))
+        # ---- GEGLU feed-forward (attention.py:372-373)
+        n3 = xa
+        add(ops.layer_norm(hs, wt[p + ".ln3g"], wt[p + ".ln3b"], n3))
+        gg = P.alloc((M, 4 * C), BF16)
+        add(ops.gemm(n3, wt[p + ".ff1.w"], bias=wt[p + ".ff1.b"], act=L.ACT_GEGLU, out_bf16=gg, name="ff1_geglu"))
+        hb = n3
+        add(ops.gemm(gg, wt[p + ".ff2.w"], bias=wt[p + ".ff2.b"], res1=hs, out_bf16=hb, name="ff2"))
+        P.release(gg, hs)
+        out = P.alloc((M, C), F32)
+        add(ops.gemm(hb, wt[p + ".proj_out.w"], bias=wt[p + ".proj_out.b"], res1=x, out_f32=out, name="proj_out"))
+        P.release(hb)
+        return out
+
+    def run(self):
+        self.plan.run()
+
+
+# ================================================================================================== VAE
+class VAEWeights:
+    def __init__(self, sd, cfg: VAEConfig, device):
+        self.cfg, self.device, self._sd = cfg, device, sd
+        self.w = {}
+        self._g = lambda k: sd[k].to(device, F32)
+        g, w = self._g, self.w
+        # encoder stem (3 -> c0), K = 27 padded to 64
+        wm = torch.zeros(cfg.block_out_channels[0], 64, device=device)
+        wm[:, :27] = conv_weight_matrix(g("encoder.conv_in.weight"))
+        w["enc.conv_in.w"], w["enc.conv_in.b"] = wm.to(BF16), g("encoder.conv_in.bias")
+        # encoder head: conv_out (3x3, C -> 2L) then quant_conv (1x1) then mean half * 0.18215, folded into one conv C -> L
+        lat = cfg.latent_channels
+        wq = g("quant_conv.weight").reshape(2 * lat, 2 * lat)[:lat]                # [L, 2L]
+        wco = conv_weight_matrix(g("encoder.conv_out.weight"))                     # [2L, 9C]
+        w["enc.head.w"] = (LATENT_SCALE * (wq @ wco)).to(BF16).contiguous()
+        w["enc.head.b"] = (LATENT_SCALE * (wq @ g("encoder.conv_out.bias") + g("quant_conv.bias")[:lat])).contiguous()
+        # decoder stem: latent / 0.18215 -> post_quant_conv (1x1) as a channel mix, then conv_in (L -> C), K = 36 -> 64
+        w["dec.pq.w"] = (g("post_quant_conv.weight").reshape(lat, lat) / LATENT_SCALE).contiguous()
+        w["dec.pq.b"] = g("post_quant_conv.bias")
+        cd = cfg.block_out_channels[-1]
+        wm = torch.zeros(cd, 64, device=device)
+        wm[:, : 9 * lat] = conv_weight_matrix(g("decoder.conv_in.weight"))
+        w["dec.conv_in.w"], w["dec.conv_in.b"] = wm.to(BF16), g("decoder.conv_in.bias")
+        w["dec.head.w"] = conv_weight_matrix(g("decoder.conv_out.weight")).to(BF16)
+        w["dec.head.b"] = g("decoder.conv_out.bias")
+        for s in ("encoder", "decoder"):
+            w[f"{s}.ng"], w[f"{s}.nb"] = g(f"{s}.conv_norm_out.weight"), g(f"{s}.conv_norm_out.bias")
+
+    def resnet(self, p):
+        if p + ".w1" not in self.w:
+            g, w = self._g, self.w
+            w[p + ".n1g"], w[p + ".n1b"] = g(p + ".norm1.weight"), g(p + ".norm1.bias")
+            w[p + ".n2g"], w[p + ".n2b"] = g(p + ".norm2.weight"), g(p + ".norm2.bias")
+            w[p + ".w1"], w[p + ".b1"] = conv_weight_matrix(g(p + ".conv1.weight")).to(BF16), g(p + ".conv1.bias")
+            w2, b2 = conv_weight_matrix(g(p + ".conv2.weight")), g(p + ".conv2.bias")
+            if (p + ".conv_shortcut.weight") in self._sd:
+                ws = g(p + ".conv_shortcut.weight")
+                w2 = torch.cat([w2, ws.reshape(ws.shape[0], ws.shape[1])], dim=1)
+                b2 = b2 + g(p + ".conv_shortcut.bias")
+                w[p + ".short"] = True
+            w[p + ".w2"], w[p + ".b2"] = w2.to(BF16).contiguous(), b2.contiguous()
+        return self.w
+
+    def conv(self, p):
+        if p + ".w" not in self.w:
+            self.w[p + ".w"] = conv_weight_matrix(self._g(p + ".weight")).to(BF16)
+            self.w[p + ".b"] = self._g(p + ".bias")
+        return self.w[p + ".w"], self.w[p + ".b"]
+
+    def attn(self, p):
+        if p + ".qk.w" not in self.w:
+            g, w = self._g, self.w
+            w[p + ".ng"], w[p + ".nb"] = g(p + ".group_norm.weight"), g(p + ".group_norm.bias")
+            w[p + ".qk.w"] = torch.cat([g(p + ".to_q.weight"), g(p + ".to_k.weight")]).to(BF16).contiguous()
+            w[p + ".qk.b"] = torch.cat([g(p + ".to_q.bias"), g(p + ".to_k.bias")]).contiguous()
+            w[p + ".v.w"], w[p + ".v.b"] = g(p + ".to_v.weight").to(BF16), g(p + ".to_v.bias")
+            w[p + ".o.w"], w[p + ".o.b"] = g(p + ".to_out.0.weight").to(BF16), g(p + ".to_out.0.bias")
+        return self.w
+
+
+class _VAEBase:
+    def _resnet(self, p, x, h, w, cout):
+        W, P, add, B, G = self.W, self.pool, self.plan.add, self.B, self.W.cfg.norm_num_groups
+        wt = W.resnet(p)
+        cin = x.shape[1]
+        short = wt.get(p + ".short", False)
+        a1 = P.alloc((B * (h + 2) * (w + 2), cin), BF16)
+        raw = P.alloc((B * (h + 2) * (w + 2), cin), BF16) if short else None
+        add(ops.group_norm(x, B, h, w, wt[p + ".n1g"], wt[p + ".n1b"], a1, eps=1e-6, silu=True, pad_out=True,
+                           partial=self.gn_partial, raw=raw, groups=G))
+        h1 = P.alloc((B * h * w, cout), F32)
+        add(ops.conv3x3(a1, wt[p + ".w1"], B, h, w, bias=wt[p + ".b1"], out_f32=h1, name="vae.conv1"))
+        P.release(a1)
+        a2 = P.alloc((B * (h + 2) * (w + 2), cout), BF16)
+        add(ops.group_norm(h1, B, h, w, wt[p + ".n2g"], wt[p + ".n2b"], a2, eps=1e-6, silu=True, pad_out=True,
+                           partial=self.gn_partial, groups=G))
+        P.release(h1)
+        out = P.alloc((B * h * w, cout), F32)
+        add(ops.conv3x3(a2, wt[p + ".w2"], B, h, w, a_short=raw, bias=wt[p + ".b2"], res1=None if short else x,
+                        out_f32=out, name="vae.conv2"))
+        P.release(a2, raw)
+        return out
+
+    def _mid_attn(self, p, x, h, w, C):
+        """diffusers Attention(heads=1, dim_head=C, residual_connection=True) inside UNetMidBlock2D (Appendix A):
+        unfused QK^T -> softmax -> PV through the GEMM kernel (single head, d = C = 512)."""
+        W, P, add, B, G = self.W, self.pool, self.plan.add, self.B, self.W.cfg.norm_num_groups
+        wt = W.attn(p)
+        N = h * w
+        M = B * N
+        Np = (N + 7) // 8 * 8
+        xn = P.alloc((M, C), BF16)
+        add(ops.group_norm(x, B, h, w, wt[p + ".ng"], wt[p + ".nb"], xn, eps=1e-6, silu=False, pad_out=False,
+                           partial=self.gn_partial, groups=G))
+        qk = P.alloc((M, 2 * C), BF16)
+        add(ops.gemm(xn, wt[p + ".qk.w"], bias=wt[p + ".qk.b"], out_bf16=qk, name="vae.qk"))
+        o = P.alloc((M, C), BF16)
+        vT = P.alloc((C, Np), BF16)
+        S = P.alloc((N, Np), F32)
+        Pm = P.alloc((N, Np), BF16)
+        for b in range(B):
+            r = slice(b * N, (b + 1) * N)
+            add(ops.gemm(wt[p + ".v.w"], xn[r], bias=wt[p + ".v.b"], bias_per_row=True, out_bf16=vT[:, :N], name="vae.vT"))
+            add(ops.gemm(qk[r, :C], qk[r, C:], out_f32=S[:, :N], name="vae.qkT"))
+            add(ops.softmax_rows(S[:, :N], Pm[:, :N], float(C) ** -0.5))
+            add(ops.gemm(Pm[:, :N], vT[:, :N], out_bf16=o[r], name="vae.pv"))
+        P.release(vT, S, Pm, qk, xn)
+        out = P.alloc((M, C), F32)
+        add(ops.gemm(o, wt[p + ".o.w"], bias=wt[p + ".o.b"], res1=x, out_f32=out, name="vae.attn_out"))
+        P.release(o)
+        return out
+
+    def _mid(self, p, x, h, w, C):
+        P = self.pool
+        y = self._resnet(p + ".resnets.0", x, h, w, C)
+        P.release(x)
+        z = self._mid_attn(p + ".attentions.0", y, h, w, C)
+        P.release(y)
+        y = self._resnet(p + ".resnets.1", z, h, w, C)
+        P.release(z)
+        return y
+
+    def run(self):
+        self.plan.run()
+
+
+class VAEEncodePlan(_VAEBase):
+    """encode_rgb (stablemtl_pipeline.py:607-624): rgb [B,3,H,W] in [0,255] -> latent mean * 0.18215, fp32 [B*h*w, 4]."""
+
+    def __init__(self, W: VAEWeights, B, H, Wd, pool=None, rgb=None):
+        self.W, self.B = W, B
+        dev = W.device
+        self.pool = P = pool or Pool(dev)
+        self.plan = ops.Plan()
+        add = self.plan.add
+        cfg = W.cfg
+        c = cfg.block_out_channels
+        self.gn_partial = torch.empty(B * 64 * 32 * 2, device=dev, dtype=F32)
+        self.rgb = rgb if rgb is not None else torch.zeros(B, 3, H, Wd, device=dev, dtype=F32)
+        xin = P.alloc((B * H * Wd, 3), F32)
+        add(ops.rgb_prep(self.rgb, xin))
+        col = P.alloc((B * H * Wd, 64), BF16)
+        add(ops.im2col(xin.view(B, H, Wd, 3), B, H, Wd, col, stride=1, pad_t=1, pad_l=1, oh=H, ow=Wd))
+        P.release(xin)
+        x = P.alloc((B * H * Wd, c[0]), F32)
+        add(ops.gemm(col, W.w["enc.conv_in.w"], bias=W.w["enc.conv_in.b"], out_f32=x, name="vae.enc.conv_in"))
+        P.release(col)
+        h, w = H, Wd
+        for i in range(len(c)):
+            for j in range(cfg.layers_per_block):
+                y = self._resnet(f"encoder.down_blocks.{i}.resnets.{j}", x, h, w, c[i])
+                P.release(x)
+                x = y
+            if i < len(c) - 1:
+                # diffusers Downsample2D: F.pad(x, (0,1,0,1)) then 3x3 stride 2 pad 0
+                h2, w2 = (h + 1 - 3) // 2 + 1, (w + 1 - 3) // 2 + 1
+                wt, bs = W.conv(f"encoder.down_blocks.{i}.downsamplers.0.conv")
+                col = P.alloc((B * h2 * w2, 9 * c[i]), BF16)
+                add(ops.im2col(x.view(B, h, w, c[i]), B, h, w, col, stride=2, pad_t=0, pad_l=0, oh=h2, ow=w2))
+                y = P.alloc((B * h2 * w2, c[i]), F32)
+                add(ops.gemm(col, wt, bias=bs, out_f32=y, name="vae.enc.down"))
+                P.release(col, x)
+                x, h, w = y, h2, w2
+        x = self._mid("encoder.mid_block", x, h, w, c[-1])
+        a = P.alloc((B * (h + 2) * (w + 2), c[-1]), BF16)
+        add(ops.group_norm(x, B, h, w, W.w["encoder.ng"], W.w["encoder.nb"], a, eps=1e-6, silu=True, pad_out=True,
+                           partial=self.gn_partial, groups=cfg.norm_num_groups))
+        self.out = torch.empty(B * h * w, cfg.latent_channels, device=dev, dtype=F32)
+        add(ops.conv3x3(a, W.w["enc.head.w"], B, h, w, bias=W.w["enc.head.b"], out_f32=self.out, name="vae.enc.head"))
+        P.release(a, x)
+        self.h, self.w = h, w
+        self.plan.finalize()
+
+
+class VAEDecodePlan(_VAEBase):
+    """decode_output (stablemtl_pipeline.py:626-643): latent fp32 [B*h*w, 4] -> decoder output fp32 [B*H*W, 3]."""
+
+    def __init__(self, W: VAEWeights, B, h, w, pool=None, latent=None):
+        self.W, self.B = W, B
+        dev = W.device
+        self.pool = P = pool or Pool(dev)
+        self.plan = ops.Plan()
+        add = self.plan.add
+        cfg = W.cfg
+        c = list(reversed(cfg.block_out_channels))
+        lat = cfg.latent_channels
+        self.latent = latent if latent is not None else torch.zeros(B * h * w, lat, device=dev, dtype=F32)
+        H, Wd = h * 2 ** (len(c) - 1), w * 2 ** (len(c) - 1)
+        self.gn_partial = torch.empty(B * 64 * 32 * 2, device=dev, dtype=F32)
+        z = P.alloc((B * h * w, lat), F32)
+        add(ops.chan_mix(self.latent, W.w["dec.pq.w"], W.w["dec.pq.b"], z))
+        col = P.alloc((B * h * w, 64), BF16)
+        add(ops.im2col(z.view(B, h, w, lat), B, h, w, col, stride=1, pad_t=1, pad_l=1, oh=h, ow=w))
+        P.release(z)
+        x = P.alloc((B * h * w, c[0]), F32)
+        add(ops.gemm(col, W.w["dec.conv_in.w"], bias=W.w["dec.conv_in.b"], out_f32=x, name="vae.dec.conv_in"))
+        P.release(col)
+        x = self._mid("decoder.mid_block", x, h, w, c[0])
+        for i in range(len(c)):
+            for j in range(cfg.layers_per_block + 1):
+                y = self._resnet(f"decoder.up_blocks.{i}.resnets.{j}", x, h, w, c[i])
+                P.release(x)
+                x = y
+            if i < len(c) - 1:
+                wt, bs = W.conv(f"decoder.up_blocks.{i}.upsamplers.0.conv")
+                up = P.alloc((B * (2 * h + 2) * (2 * w + 2), c[i]), BF16)
+                add(ops.upsample_pad(x.view(B, h, w, c[i]), B, h, w, 2 * h, 2 * w, up))
+                P.release(x)
+                h, w = 2 * h, 2 * w
+                x = P.alloc((B * h * w, c[i]), F32)
+                add(ops.conv3x3(up, wt, B, h, w, bias=bs, out_f32=x, name="vae.dec.up"))
+                P.release(up)
+        a = P.alloc((B * (h + 2) * (w + 2), c[-1]), BF16)
+        add(ops.group_norm(x, B, h, w, W.w["decoder.ng"], W.w["decoder.nb"], a, eps=1e-6, silu=True, pad_out=True,
+                           partial=self.gn_partial, groups=cfg.norm_num_groups))
+        P.release(x)
+        self.out = torch.empty(B * h * w, 3, device=dev, dtype=F32)
+        add(ops.conv3x3(a, W.w["dec.head.w"], B, h, w, bias=W.w["dec.head.b"], out_f32=self.out, name="vae.dec.head"))
+        P.release(a)
+        self.H, self.Wd = h, w
+        self.plan.finalize()

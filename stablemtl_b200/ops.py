@@ -27,6 +27,7 @@ _RUNNERS = {
     L.OP_XATTN: "smtl_xattn_run", L.OP_TASKATTN: "smtl_taskattn_run", L.OP_GN: "smtl_gn_run",
     L.OP_LN: "smtl_ln_run", L.OP_UPSAMPLE: "smtl_upsample_run", L.OP_IM2COL: "smtl_im2col_run",
     L.OP_RGBPREP: "smtl_rgbprep_run", L.OP_UNETIN: "smtl_unetin_run", L.OP_TASKMAP: "smtl_taskmap_run",
+    L.OP_CHANMIX: "smtl_chanmix_run",
 }
 
 
@@ -272,6 +273,14 @@ def unet_input(latents, first_img, second_img, hw, out):
     a.out_images, a.hw, a.out = first_img.numel(), hw, out.data_ptr()
     assert first_img.dtype == torch.int32 and second_img.dtype == torch.int32 and latents.dtype == F32
     return Op(L.OP_UNETIN, a, (latents, first_img, second_img, out), 0, "unet_input")
+
+
+def chan_mix(x, w, b, y):
+    a = L.ChanmixArgs()
+    a.x, a.rows, a.cin, a.cout = x.data_ptr(), x.numel() // w.shape[1], w.shape[1], w.shape[0]
+    a.w, a.b, a.y = w.data_ptr(), _ptr(b), y.data_ptr()
+    assert x.dtype == F32 and w.dtype == F32 and y.dtype == F32
+    return Op(L.OP_CHANMIX, a, (x, w, b, y), 0, "chan_mix")
 
 
 def task_map(x, batch, hw, mode, *, out_clipped=None, out_post=None, out_ids=None, palette=None):

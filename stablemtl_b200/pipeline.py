@@ -1,0 +1,237 @@
+"""Host-side mirror of the reference pipeline for the accelerated path.
+
+`StableMTLEngine` is the batched all-task fast path (deduplicated schedule of SURVEY.md §3.1: 1-2 VAE encodes,
+one batched child pass over the 7 task streams, one batched main pass, 7 decodes).
+`StableMTLPipeline` keeps the reference's call surface (`src/stablemtl_pipeline.py:177-194`, `:519-529`) on top of
+it so `eval_mtl.py` / `StableMTLTrainer.validate_single_dataset` (`src/trainer/stablemtl_trainer.py:697-712`)
+can call it unchanged.  All numerics run in the sm_100a kernels; torch is used for device memory, H2D/D2H copies
+and the current stream only.  There is no CPU / PyTorch fallback: constructing either class without a CUDA
+device raises.
+"""
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import ops
+from .engine import BF16, F32, Pool, UNetPlan, UNetWeights, VAEDecodePlan, VAEEncodePlan, VAEWeights
+from .synth import FLOW_TASKS, TASKS, UNetConfig, VAEConfig
+
+# VKitti2Encoder(n_classes=8).class_color_embeddings (src/dataset/semantic/encoding.py:10-35,92-96; labels.py:42-55)
+PALETTE = [[128, 64, 128], [70, 70, 70], [153, 153, 153], [250, 170, 30], [220, 220, 0], [107, 142, 35],
+           [70, 130, 180], [0, 0, 142]]
+TASK_MODE = {"depth": L.MAP_MEAN1, "shading": L.MAP_MEAN1, "albedo": L.MAP_RGB3, "normal": L.MAP_NORMAL,
+             "optical_flow": L.MAP_FLOW2, "scene_flow": L.MAP_FLOW3, "semantic": L.MAP_SEMANTIC}
+TASK_CH = {"depth": 1, "shading": 1, "albedo": 3, "normal": 3, "optical_flow": 2, "scene_flow": 3, "semantic": 3}
+
+
+def _require_cuda(device):
+    if not torch.cuda.is_available():
+        raise RuntimeError("stablemtl_b200 needs a CUDA (sm_100a) device: there is no CPU fallback")
+    return torch.device(device)
+
+
+class StableMTLEngine:
+    def __init__(self, ucfg: UNetConfig, vcfg: VAEConfig, child_sd, vae_sd, text: Dict[str, torch.Tensor],
+                 main_sd=None, tasks: List[str] = TASKS, device="cuda", max_decode_batch=8):
+        self.device = _require_cuda(device)
+        self.ucfg, self.vcfg, self.tasks = ucfg, vcfg, list(tasks)
+        self.multi = main_sd is not None
+        self.child_w = UNetWeights(child_sd, ucfg, text, self.tasks, self.device)
+        self.main_w = UNetWeights(main_sd, ucfg, text, self.tasks, self.device) if self.multi else None
+        self.vae_w = VAEWeights(vae_sd, vcfg, self.device)
+        self.palette = (torch.tensor(PALETTE, dtype=F32, device=self.device) / 255.0 * 2.0 - 1.0).contiguous()
+        self.max_decode_batch = max_decode_batch
+        self._plans = {}
+
+    # ------------------------------------------------------------------------------------------ plan construction
+    def _build(self, B, H, W, with_next):
+        dev = self.device
+        pool = Pool(dev)
+        T = len(self.tasks)
+        n_enc = 2 * B if with_next else B
+        enc = VAEEncodePlan(self.vae_w, n_enc, H, W, pool=pool)
+        h, w = enc.h, enc.w
+        hw = h * w
+        first = torch.arange(B, dtype=torch.int32).repeat(T)
+        second = first.clone()
+        if with_next:
+            for gi, t in enumerate(self.tasks):
+                if t in FLOW_TASKS:                                  # stablemtl_pipeline.py:433-434
+                    second[gi * B:(gi + 1) * B] += B
+        first, second = first.to(dev), second.to(dev)
+        x_in = torch.empty(T * B * hw, self.ucfg.in_channels, device=dev, dtype=F32)
+        assemble = ops.unet_input(enc.out, first, second, hw, x_in)
+        groups = list(range(T))
+        if self.multi:
+            child = UNetPlan(self.child_w, B, h, w, groups, mode="child", pool=pool, x_in=x_in)
+            main = UNetPlan(self.main_w, B, h, w, groups, mode="main", feats=child.feats_out, src_tasks=groups,
+                            pool=pool, x_in=x_in)
+            unets = [child, main]
+            lat = main.out
+        else:
+            single = UNetPlan(self.child_w, B, h, w, groups, mode="single", pool=pool, x_in=x_in)
+            unets = [single]
+            lat = single.out
+        n_lat = T * B
+        bd = max(d for d in range(1, min(self.max_decode_batch, n_lat) + 1) if n_lat % d == 0)
+        dec = VAEDecodePlan(self.vae_w, bd, h, w, pool=pool)
+        HW = H * W
+        out = {}
+        for t in self.tasks:
+            ch = TASK_CH[t]
+            out[t] = {"clipped": torch.empty(B, ch, H, W, device=dev, dtype=F32)}
+            if t == "semantic":
+                out[t]["post"] = torch.empty(B, H, W, device=dev, dtype=torch.int64)
+            else:
+                out[t]["post"] = torch.empty(B, ch, H, W, device=dev, dtype=F32)
+        chunks = []
+        for c0 in range(0, n_lat, bd):
+            maps = []
+            i = c0
+            while i < c0 + bd:                                       # split the chunk at task boundaries
+                gi, img = divmod(i, B)
+                n = min(B - img, c0 + bd - i)
+                t = self.tasks[gi]
+                x = dec.out[(i - c0) * HW:(i - c0 + n) * HW]
+                o = out[t]
+                if t == "semantic":
+                    maps.append(ops.task_map(x, n, HW, TASK_MODE[t], out_clipped=o["clipped"][img:img + n],
+                                             out_ids=o["post"][img:img + n], palette=self.palette))
+                else:
+                    maps.append(ops.task_map(x, n, HW, TASK_MODE[t], out_clipped=o["clipped"][img:img + n],
+                                             out_post=o["post"][img:img + n]))
+                i += n
+            chunks.append((c0, maps))
+        launches = enc.plan.launches + 1 + sum(u.plan.launches for u in unets) + \
+            len(chunks) * dec.plan.launches + sum(len(m) for _, m in chunks)
+        flops = enc.plan.flops + sum(u.plan.flops for u in unets) + len(chunks) * dec.plan.flops
+        return dict(enc=enc, assemble=assemble, unets=unets, lat=lat, dec=dec, bd=bd, chunks=chunks, out=out, hw=hw,
+                    pool=pool, launches=launches, flops=flops, h=h, w=w)
+
+    def plan_for(self, B, H, W, with_next=True):
+        key = (B, H, W, with_next)
+        if key not in self._plans:
+            self._plans[key] = self._build(B, H, W, with_next)
+        return self._plans[key]
+
+    # ------------------------------------------------------------------------------------------ execution
+    @torch.no_grad()
+    def predict(self, rgb: torch.Tensor, rgb_next: Optional[torch.Tensor] = None, return_latents=False):
+        """rgb / rgb_next: float [B,3,H,W] in [0,255] (host or device).  Returns {task: map} with the reference's
+        post-processing (stablemtl_pipeline.py:297-366): depth/shading/albedo in [0,1], unit normals, flows in
+        [-1,1], semantic class ids (int64 [B,H,W]).  `.last` keeps the clipped single_infer() tensors."""
+        B, _, H, W = rgb.shape
+        p = self.plan_for(B, H, W, rgb_next is not None)
+        enc = p["enc"]
+        enc.rgb[:B].copy_(rgb.to(F32), non_blocking=True)
+        if rgb_next is not None:
+            enc.rgb[B:].copy_(rgb_next.to(F32), non_blocking=True)
+        enc.run()
+        p["assemble"].run()
+        for u in p["unets"]:
+            u.run()
+        dec, bd, hw = p["dec"], p["bd"], p["hw"]
+        lat = p["lat"]
+        for c0, maps in p["chunks"]:
+            dec.latent.copy_(lat[c0 * hw:(c0 + bd) * hw])
+            dec.run()
+            for m in maps:
+                m.run()
+        self.last = {t: p["out"][t]["clipped"] for t in self.tasks}
+        res = {t: p["out"][t]["post"] for t in self.tasks}
+        if return_latents:
+            T = len(self.tasks)
+            lats = lat.view(T, B, p["h"], p["w"], -1).permute(0, 1, 4, 2, 3)
+            return res, {t: lats[i] for i, t in enumerate(self.tasks)}
+        return res
+
+    def launches_per_step(self, B, H, W, with_next=True):
+        return self.plan_for(B, H, W, with_next)["launches"]
+
+    def flops_per_step(self, B, H, W, with_next=True):
+        return self.plan_for(B, H, W, with_next)["flops"]
+
+
+# ====================================================================================================== drop-in facade
+class _Out(dict):
+    """Attribute/dict output object standing in for diffusers.utils.BaseOutput (stablemtl_pipeline.py:32-109)."""
+    __getattr__ = dict.__getitem__
+
+
+class StableMTLPipeline:
+    """Call-compatible with the reference `StableMTLPipeline.__call__` / `.single_infer`.
+
+    The first call for an image (pair) computes all task maps with the batched engine and caches them; the
+    following calls of the evaluation loop (one per `output_type`, stablemtl_trainer.py:697-712) are served from
+    the cache, which is exactly the deduplication the reference leaves on the table."""
+
+    rgb_latent_scale_factor = 0.18215
+    latent_scale_factor = 0.18215
+
+    def __init__(self, engine: StableMTLEngine, input_noise="deterministic", encode_rgb_model="duplicate"):
+        if input_noise != "deterministic" or encode_rgb_model != "duplicate":
+            raise ValueError("the accelerated path implements input_noise='deterministic', encode_rgb_model='duplicate' "
+                             "(config/train_base_config.yaml:18-24)")
+        self.engine = engine
+        self.device = engine.device
+        self._key = None
+
+    def _all_tasks(self, rgb_norm, rgb_next_norm):
+        key = (rgb_norm.data_ptr(), tuple(rgb_norm.shape), None if rgb_next_norm is None else rgb_next_norm.data_ptr())
+        fresh = self._key is None or self._key[0] != key or not torch.equal(self._key[1], rgb_norm.to(self.device))
+        if fresh:
+            # the engine takes [0,255]; undo (x/255*2-1) of stablemtl_pipeline.py:263 exactly where representable
+            rgb = (rgb_norm.to(self.device, F32) + 1.0) / 2.0 * 255.0
+            nxt = None if rgb_next_norm is None else (rgb_next_norm.to(self.device, F32) + 1.0) / 2.0 * 255.0
+            self.engine.predict(rgb, nxt)
+            self._key = (key, rgb_norm.to(self.device).clone())
+        return self.engine.last
+
+    @torch.no_grad()
+    def single_infer(self, rgb_norm, num_inference_steps, generator, show_pbar, output_type,
+                     exclude_mainstream_output_type, rgb_next_norm=None, task_output_types=[]):
+        if output_type not in self.engine.tasks:
+            raise ValueError(f"Unknown output type: {output_type}")
+        if self.engine.multi and not exclude_mainstream_output_type:
+            raise ValueError("the multi-stream engine is built for exclude_mainstream_output_type=True "
+                             "(config/train_stablemtl.yaml:22)")
+        return self._all_tasks(rgb_norm, rgb_next_norm)[output_type]
+
+    @torch.no_grad()
+    def __call__(self, input_image, exclude_mainstream_output_type, next_input_image=None, denoising_steps=None,
+                 ensemble_size=5, processing_res=None, match_input_res=True, resample_method="bilinear", batch_size=0,
+                 generator=None, color_map="Spectral", show_progress_bar=True, ensemble_kwargs=None,
+                 output_type="depth", task_output_types=[]):
+        if processing_res:
+            raise ValueError("processing_res > 0 (resize) is outside the accelerated path; eval uses processing_res=0 "
+                             "(config/train_base_config.yaml:179-180)")
+        rgb, nxt = input_image, next_input_image
+        assert rgb.min() >= 0 and rgb.max() <= 255, "Input images should be in [0,255] range"
+        rgb_norm = rgb / 255.0 * 2.0 - 1.0
+        nxt_norm = None if nxt is None else nxt / 255.0 * 2.0 - 1.0
+        out = self.single_infer(rgb_norm, denoising_steps, generator, show_progress_bar, output_type,
+                                exclude_mainstream_output_type, nxt_norm, task_output_types)
+        pred = out.squeeze().cpu().numpy()                                       # stablemtl_pipeline.py:294-295
+        if output_type == "albedo":
+            return _Out(albedo_np=(pred + 1.0) / 2.0)
+        if output_type == "shading":
+            return _Out(shading_np=(pred + 1.0) / 2.0)
+        if output_type == "depth":
+            return _Out(depth_np=(pred + 1.0) / 2.0, depth_colored=None)
+        if output_type == "normal":
+            n = np.linalg.norm(pred, axis=0, keepdims=True)
+            n[n == 0] = 1.0
+            return _Out(normal_np=pred / n, normal_colored=None)
+        if output_type == "optical_flow":
+            return _Out(optical_flow_np=pred)
+        if output_type == "scene_flow":
+            return _Out(scene_flow_np=pred)
+        if output_type == "semantic":
+            pal = np.asarray(PALETTE, dtype=np.float32)
+            emb = pal / 255.0 * 2.0 - 1.0
+            flat = pred.transpose(1, 2, 0).reshape(-1, 3)
+            d = np.sqrt(((flat[:, None, :] - emb[None]) ** 2).sum(-1))
+            return _Out(semantic_class_id=d.argmin(1).reshape(pred.shape[1:]), class_color_visualizes=pal)
+        raise ValueError(f"Unknown output type: {output_type}")
