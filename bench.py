@@ -1,0 +1,434 @@
+"""bench.py -- images/sec of the StableMTL all-task latent pass on B200 (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload single|multi]
+
+One "step" = one pass of the hot path (VAE encode -> UNet(s) -> 7 VAE decodes + task-map epilogue) over one batch
+of synthetic 480x640 image pairs; every image yields all 7 task maps.  Default workload = BASELINE.json configs[1]
+(single-stream, batch 16 per GPU); `--workload multi` = configs[2]'s per-GPU slice (multi-stream, batch 8 per GPU).
+Weak scaling: each rank (one process per GPU under torchrun) runs its own batch; no data-path collective.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="single", choices=["single", "multi"])
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default 16 single / 8 multi)")
+    ap.add_argument("--height", type=int, default=480)
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--breakdown", default="", help="write a per-kernel-kind time breakdown JSON here")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------------ algorithmic FLOPs
+def algorithmic_flops(h, w, multi):
+    """2*MAC of the deduplicated schedule for ONE image (SURVEY.md §8d / Appendix C formulas), latent h x w."""
+    from stablemtl_b200.synth import SD2_UNET as U, SD2_VAE as V
+
+    def conv(cin, cout, hh, ww, k=3):
+        return 2 * cin * cout * k * k * hh * ww
+
+    def down(n):
+        return (n - 1) // 2 + 1
+    c = U.block_out_channels
+    sizes = [(h, w)]
+    for _ in range(3):
+        sizes.append((down(sizes[-1][0]), down(sizes[-1][1])))
+
+    def resnet(cin, cout, hw):
+        f = conv(cin, cout, *hw) + conv(cout, cout, *hw)
+        if cin != cout:
+            f += conv(cin, cout, *hw, k=1)
+        return f
+
+    def transformer(C, hw, tasks=0):
+        n = hw[0] * hw[1]
+        f = 40 * C * C * n + 4 * n * n * C + 16 * n * C
+        if tasks:
+            hq = U.task_q_hidden
+            f += 2 * n * (2 * hq * C + 2 * hq * hq) + 2 * C * C * n + 4 * n * (tasks - 1) * C
+        return f
+
+    def unet(tasks=0):
+        f = conv(12, c[0], h, w)
+        ch = c[0]
+        for i in range(4):
+            for j in range(2):
+                f += resnet(ch if j == 0 else c[i], c[i], sizes[i])
+                if i < 3:
+                    f += transformer(c[i], sizes[i], tasks)
+            ch = c[i]
+            if i < 3:
+                f += conv(c[i], c[i], *sizes[i + 1])
+        f += 2 * resnet(c[3], c[3], sizes[3]) + transformer(c[3], sizes[3], tasks)
+        skip = [c[0], c[0], c[0], c[0], c[1], c[1], c[1], c[2], c[2], c[2], c[3], c[3]]
+        x = c[3]
+        for i in range(4):
+            lev = 3 - i
+            for j in range(3):
+                f += resnet(x + skip.pop(), c[lev], sizes[lev])
+                x = c[lev]
+                if i > 0:
+                    f += transformer(c[lev], sizes[lev], tasks)
+            if i < 3:
+                f += conv(c[lev], c[lev], *sizes[lev - 1])
+        return f + conv(c[0], 4, h, w)
+
+    kv_mlps = sum(4 * C * C * (s[0] * s[1]) for C, s in
+                  [(c[0], sizes[0])] * 5 + [(c[1], sizes[1])] * 5 + [(c[2], sizes[2])] * 5 + [(c[3], sizes[3])])
+    v = V.block_out_channels
+    H, W = 8 * h, 8 * w
+
+    def vres(cin, cout, hh, ww):
+        return resnet(cin, cout, (hh, ww))
+
+    def vmid(C, hh, ww):
+        n = hh * ww
+        return 2 * vres(C, C, hh, ww) + 8 * C * C * n + 4 * n * n * C
+    enc = conv(3, v[0], H, W)
+    hh, ww, ch = H, W, v[0]
+    for i in range(4):
+        enc += vres(ch, v[i], hh, ww) + vres(v[i], v[i], hh, ww)
+        ch = v[i]
+        if i < 3:
+            hh, ww = hh // 2, ww // 2
+            enc += conv(ch, ch, hh, ww)
+    enc += vmid(v[3], hh, ww) + conv(v[3], 8, hh, ww) + conv(8, 8, hh, ww, k=1)
+    dec = conv(4, 4, h, w, k=1) + conv(4, v[3], h, w) + vmid(v[3], h, w)
+    hh, ww, ch = h, w, v[3]
+    rev = list(reversed(v))
+    for i, co in enumerate(rev):
+        dec += vres(ch, co, hh, ww) + 2 * vres(co, co, hh, ww)
+        ch = co
+        if i < 3:
+            hh, ww = hh * 2, ww * 2
+            dec += conv(ch, ch, hh, ww)
+    dec += conv(v[0], 3, hh, ww)
+    if multi:
+        # 7 child + 7 main passes; the per-source-task K/V MLPs run once per stream (7x), not once per main task
+        unets = 7 * unet() + 7 * unet(tasks=7) + 7 * kv_mlps
+    else:
+        unets = 7 * unet()
+    return dict(total=2 * enc + unets + 7 * dec, unet=unets, enc=enc, dec=dec)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().strip().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            sm.sort()
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline (oracle)
+def cpu_sample(H, W, threads, sds=None):
+    """Times the fp32 oracle (reference algorithm restated, oracle/) on the host cores on a bounded sample of the
+    workload: ONE 480x640 image, ONE task: 1 VAE encode + 1 single-stream UNet pass + 1 VAE decode.  The all-7-task
+    image time is 2*enc + 7*unet + 7*dec (the same deduplicated schedule the GPU arm runs)."""
+    from oracle import stablemtl_oracle as O
+    from stablemtl_b200 import synth
+    torch.set_num_threads(threads)
+    if sds is None:
+        sds = (synth.make_unet_state_dict(synth.SD2_UNET, 0), synth.make_vae_state_dict(synth.SD2_VAE, 2),
+               synth.make_text_embeddings(1024))
+    child, vae, text = sds
+    rgb, _ = synth.make_images(1, H, W, 0)
+    rn = rgb / 255.0 * 2.0 - 1.0
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        lat = O.vae_encode(vae, synth.SD2_VAE, rn)
+        t1 = time.perf_counter()
+        x = torch.cat([lat, lat, torch.zeros_like(lat)], 1)
+        out, _ = O.unet_forward(child, synth.SD2_UNET, x, text["depth"][None])
+        t2 = time.perf_counter()
+        O.vae_decode(vae, synth.SD2_VAE, out)
+        t3 = time.perf_counter()
+    return dict(enc=t1 - t0, unet=t2 - t1, dec=t3 - t2)
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host CPU (oracle port; the reference itself cannot be
+    imported on the GPU box: /root/reference and its diffusers/xformers dependencies do not exist there)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from stablemtl_b200 import synth
+    threads = os.cpu_count() or 1
+    H, W = args.height, args.width
+    sds = (synth.make_unet_state_dict(synth.SD2_UNET, 0), synth.make_vae_state_dict(synth.SD2_VAE, 2),
+           synth.make_text_embeddings(1024))
+    warm = min(args.warmup, 1)
+    for _ in range(warm):
+        cpu_sample(H, W, threads, sds)
+    acc = dict(enc=0.0, unet=0.0, dec=0.0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        s = cpu_sample(H, W, threads, sds)
+        for k in acc:
+            acc[k] += s[k]
+    wall = time.perf_counter() - t0
+    for k in acc:
+        acc[k] /= args.steps
+    per_image = 2 * acc["enc"] + 7 * acc["unet"] + 7 * acc["dec"]
+    value = 1.0 / per_image
+    sample = (f"per step: 1 image x 1 task at {H}x{W} (1 VAE encode + 1 single-stream UNet pass + 1 VAE decode, fp32); "
+              f"image time = 2*enc + 7*unet + 7*dec = {per_image:.1f} s (enc {acc['enc']:.2f} s, unet {acc['unet']:.2f} s, "
+              f"dec {acc['dec']:.2f} s)")
+    line = {
+        "impl": "reference", "metric": "images/sec (all-task dense maps) at 480x640", "value": value, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": warm, "ms_per_step": wall / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "StableMTL-S single-stream, all 7 task maps per image, 480x640, random-init SD-2 UNet+VAE, "
+                               "CPU fp32 (oracle port of the reference algorithm)"},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the CUDA path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from stablemtl_b200 import ops, synth
+    from stablemtl_b200 import _lib as L
+    from stablemtl_b200.pipeline import StableMTLEngine
+    ops.set_precision(args.precision)
+    multi = args.workload == "multi"
+    B = args.batch or (8 if multi else 16)
+    H, W = args.height, args.width
+
+    child = synth.make_unet_state_dict(synth.SD2_UNET, 0)
+    vae = synth.make_vae_state_dict(synth.SD2_VAE, 2)
+    text = synth.make_text_embeddings(1024)
+    main_sd = None
+    if multi:
+        main_sd = dict(synth.make_unet_state_dict(synth.SD2_UNET, 10))
+        main_sd.update(synth.make_task_modules_state_dict(synth.SD2_UNET, seed=11))
+    eng = StableMTLEngine(synth.SD2_UNET, synth.SD2_VAE, child, vae, text, main_sd, device=dev)
+    del main_sd
+
+    g = torch.Generator().manual_seed(100 + rank)
+    rgb_h = torch.randint(0, 256, (B, 3, H, W), generator=g, dtype=torch.uint8).pin_memory()
+    nxt_h = torch.randint(0, 256, (B, 3, H, W), generator=g, dtype=torch.uint8).pin_memory()
+    rgb_d, nxt_d = rgb_h.to(dev), nxt_h.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(x):
+        if world > 1:
+            t = torch.tensor([x], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+        return x
+
+    for _ in range(max(args.warmup, 1)):
+        res = eng.predict(rgb_d, nxt_d)
+    barrier()
+
+    # ---- value: device-resident inputs, CUDA events on the launching stream, max over ranks
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        res = eng.predict(rgb_d, nxt_d)
+    e1.record()
+    barrier()
+    ms = reduce_max(e0.elapsed_time(e1))
+    clocks = sampler.stop() if sampler else {}
+    ms_per_step = ms / args.steps
+    value = world * B / (ms_per_step / 1e3)
+
+    # ---- e2e: pinned host images in, all task maps back to pinned host memory, inside the timed region
+    out_h = {t: torch.empty(v.shape, dtype=v.dtype).pin_memory() for t, v in res.items()}
+    h2d = rgb_h.numel() + nxt_h.numel()
+    d2h = sum(v.numel() * v.element_size() for v in out_h.values())
+
+    def e2e_step():
+        r = eng.predict(rgb_h, nxt_h)                       # H2D copies of the pinned uint8 images happen inside
+        for t, v in r.items():
+            out_h[t].copy_(v, non_blocking=True)
+
+    e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = reduce_max(e0.elapsed_time(e1)) / args.steps
+    e2e_value = world * B / (e2e_ms / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (smtl_gemm_kernel: every conv and linear): per-launch CUDA events
+    p = eng.plan_for(B, H, W, True, torch.uint8)
+    plans = [("vae_encode", p["enc"].plan, 1)] + [(f"unet{i}", u.plan, 1) for i, u in enumerate(p["unets"])] + \
+        [("vae_decode", p["dec"].plan, len(p["chunks"]))]
+    by_name = {}
+    gemm_ms = gemm_flops = 0.0
+    fattn_ms = fattn_flops = 0.0
+    total_ms = 0.0
+    for pname, plan, reps in plans:
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(plan.ops) + 1)]
+        torch.cuda.synchronize()
+        evs[0].record()
+        for i, op in enumerate(plan.ops):
+            op.run()
+            evs[i + 1].record()
+        torch.cuda.synchronize()
+        for i, op in enumerate(plan.ops):
+            t = evs[i].elapsed_time(evs[i + 1]) * reps
+            d = by_name.setdefault(f"{pname}:{op.name}", [0.0, 0.0, 0])
+            d[0] += t
+            d[1] += op.flops * reps
+            d[2] += reps
+            total_ms += t
+            if op.kind == L.OP_GEMM:
+                gemm_ms += t
+                gemm_flops += op.flops * reps
+            elif op.kind == L.OP_FATTN:
+                fattn_ms += t
+                fattn_flops += op.flops * reps
+    pk = peaks()
+    peak = pk["bf16_tflops_sustained"] if pk else 1400.0
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
+    alg = algorithmic_flops(H // 8, W // 8, multi)
+    if args.breakdown:
+        with open(args.breakdown, "w") as f:
+            json.dump({"ms_per_step": ms_per_step, "instrumented_ms": total_ms,
+                       "ops": {k: {"ms": v[0], "tflops": (v[1] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else 0), "launches": v[2]}
+                               for k, v in sorted(by_name.items(), key=lambda kv: -kv[1][0])}}, f, indent=1)
+
+    line = {
+        "metric": "images/sec (all-task dense maps) at 480x640", "value": value, "unit": "images/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": f"{args.precision} operands, fp32 accumulate (tcgen05 kind::f16)", "data": "synthetic",
+        "config": {
+            "workload": (f"StableMTL {'multi-stream (7 child streams + main UNet with task attention)' if multi else 'single-stream'}"
+                         f", all 7 task maps per image, batch {B} per GPU at {H}x{W}, random-init SD-2 UNet+VAE"),
+            "global_batch": world * B, "parallelism": f"dp{world} (images sharded, no data-path collective)",
+            "l2": f"per-step working set ({eng.plan_for(B, H, W, True, torch.uint8)['pool'].total / 2**30:.1f} GiB of activations) >> 126 MB L2; no flush needed",
+        },
+        "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": p["launches"],
+        "clocks": clocks,
+        "roofline": {
+            "kernel": "smtl_gemm_kernel (tcgen05 implicit-GEMM convs + token linears)", "bound": "tensor",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if pk else "fallback",
+            "traffic": None, "share_of_step": gemm_ms / total_ms,
+            "whole_step_tflops": alg["total"] * B / (ms_per_step * 1e-3) / 1e12,
+            "whole_step_frac": alg["total"] * B / (ms_per_step * 1e-3) / 1e12 / peak,
+            "unet_contractions_frac_of_peak": None,
+            "flash_attn_tflops": (fattn_flops / (fattn_ms * 1e-3) / 1e12) if fattn_ms > 0 else None,
+            "flash_attn_share_of_step": fattn_ms / total_ms,
+            "algorithmic_tflop_per_image": alg["total"] / 1e12,
+        },
+    }
+    # UNet-only fraction of peak (north_star "UNet % TC peak"): algorithmic UNet flops / instrumented UNet time
+    unet_ms = sum(v[0] for k, v in by_name.items() if k.startswith("unet"))
+    if unet_ms > 0:
+        line["roofline"]["unet_contractions_frac_of_peak"] = alg["unet"] * B / (unet_ms * 1e-3) / 1e12 / peak
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        s = cpu_sample(H, W, threads, (child, vae, text))
+        per_image = 2 * s["enc"] + 7 * s["unet"] + 7 * s["dec"]
+        line["cpu_baseline"] = {
+            "value": 1.0 / per_image, "unit": "images/s", "cores": threads, "kind": "port",
+            "sample": (f"fp32 oracle (reference algorithm), 1 image x 1 task at {H}x{W}: enc {s['enc']:.2f} s + unet "
+                       f"{s['unet']:.2f} s + dec {s['dec']:.2f} s; all-7-task image = 2*enc + 7*unet + 7*dec = {per_image:.1f} s"),
+        }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -37,6 +37,9 @@ enum {
 
 enum { SMTL_ACT_NONE = 0, SMTL_ACT_GELU = 1, SMTL_ACT_GEGLU = 2, SMTL_ACT_SILU = 3 };
 enum { SMTL_ROWMAP_IDENTITY = 0, SMTL_ROWMAP_CONV_PAD = 1 };
+/* 16-bit operand format of a call (field `fmt16`): the buffers named *_bf16 hold bf16 (0) or IEEE fp16 (1).
+ * Both run at the same tcgen05 kind::f16 rate with fp32 accumulation; fp16 conversions saturate at +-65504. */
+enum { SMTL_FMT_BF16 = 0, SMTL_FMT_F16 = 1 };
 
 #define SMTL_MAX_SEG 12
 #define SMTL_MAX_TASKS 8
@@ -84,7 +87,8 @@ typedef struct smtl_gemm_args {
     int32_t ld_aux;
     int32_t rowmap;     /* SMTL_ROWMAP_CONV_PAD: GEMM row = padded pixel, output row = compact pixel; halo rows dropped */
     int32_t img_h, img_w; /* interior size for the conv row map (padded size is +2) */
-    int32_t block_n;    /* 0 = auto; else 32/64/128/256 */
+    int32_t block_n;    /* 0 = auto; else 32/64/128/160/192/224/256 */
+    int32_t fmt16;      /* SMTL_FMT_* of a0/a1/b/out_bf16/aux_bf16 */
 } smtl_gemm_args;
 
 typedef struct smtl_gemm_op {
@@ -115,6 +119,8 @@ typedef struct smtl_fattn_args {
     void* out_bf16;     /* [batch*ntok, ldo], head h at columns h*64 */
     int32_t ldo;
     float scale;        /* 1/sqrt(64) */
+    int32_t fmt16;
+    int32_t pad_;
 } smtl_fattn_args;
 
 typedef struct smtl_fattn_op {
@@ -137,6 +143,7 @@ typedef struct smtl_softmax_args {
     float scale;
     void* p_bf16;
     int32_t ldp;
+    int32_t fmt16;
 } smtl_softmax_args;
 int smtl_softmax_run(const smtl_softmax_args* a, void* stream);
 
@@ -155,6 +162,8 @@ typedef struct smtl_xattn_args {
     void* out_bf16;
     int32_t ldo;
     float scale;
+    int32_t fmt16;
+    int32_t pad_;
 } smtl_xattn_args;
 int smtl_xattn_run(const smtl_xattn_args* a, void* stream);
 
@@ -173,6 +182,8 @@ typedef struct smtl_taskattn_args {
     int32_t src_task[SMTL_MAX_TASKS];       /* task id of each k/v row group */
     int32_t exclude_self;                   /* skip src whose task id equals the row's main task (stablemtl_pipeline.py:483-484) */
     float scale;                            /* 1/sqrt(c/nheads) */
+    int32_t fmt16;
+    int32_t pad_;
 } smtl_taskattn_args;
 int smtl_taskattn_run(const smtl_taskattn_args* a, void* stream);
 
@@ -197,6 +208,8 @@ typedef struct smtl_gn_args {
     int32_t pad_out;        /* 1: padded layout with zero halo, 0: compact */
     void* out_bf16;
     void* raw_bf16;         /* optional un-normalised bf16 copy, same layout (1x1 shortcut operand) */
+    int32_t fmt16;
+    int32_t pad_;
 } smtl_gn_args;
 int smtl_gn_run(const smtl_gn_args* a, void* stream);
 
@@ -217,7 +230,7 @@ typedef struct smtl_ln_args {
     const float* beta1;
     void* out1;
     int32_t ldo;
-    int32_t pad_;
+    int32_t fmt16;          /* format of out0/out1 and of x when x_is_bf16 */
 } smtl_ln_args;
 int smtl_ln_run(const smtl_ln_args* a, void* stream);
 
@@ -229,6 +242,8 @@ typedef struct smtl_upsample_args {
     int32_t batch, h, w, c;
     int32_t oh, ow;
     void* out_bf16;         /* padded layout [batch, oh+2, ow+2, c] */
+    int32_t fmt16;
+    int32_t pad_;
 } smtl_upsample_args;
 int smtl_upsample_run(const smtl_upsample_args* a, void* stream);
 
@@ -241,13 +256,16 @@ typedef struct smtl_im2col_args {
     int32_t oh, ow;
     int32_t kpad;           /* row length of the output (>= 9*c, multiple of 64, zero filled) */
     void* out_bf16;         /* [batch*oh*ow, kpad] */
+    int32_t fmt16;
+    int32_t pad_;
 } smtl_im2col_args;
 int smtl_im2col_run(const smtl_im2col_args* a, void* stream);
 
 /* [0,255] NCHW rgb -> [-1,1] NHWC fp32 (src/stablemtl_pipeline.py:263). */
 typedef struct smtl_rgbprep_args {
-    const float* rgb_nchw;
+    const void* rgb_nchw;   /* float32 or uint8 [batch, 3, h, w] in [0,255] */
     int32_t batch, h, w;
+    int32_t src_u8;         /* 1: rgb_nchw is uint8 */
     float* out_nhwc;
 } smtl_rgbprep_args;
 int smtl_rgbprep_run(const smtl_rgbprep_args* a, void* stream);

@@ -15,6 +15,7 @@ MAX_TASKS = 8
 
 ACT_NONE, ACT_GELU, ACT_GEGLU, ACT_SILU = 0, 1, 2, 3
 ROWMAP_IDENTITY, ROWMAP_CONV_PAD = 0, 1
+FMT_BF16, FMT_F16 = 0, 1
 MAP_MEAN1, MAP_RGB3, MAP_NORMAL, MAP_FLOW2, MAP_FLOW3, MAP_SEMANTIC = range(6)
 (OP_GEMM, OP_FATTN, OP_SOFTMAX, OP_XATTN, OP_TASKATTN, OP_GN, OP_LN, OP_UPSAMPLE, OP_IM2COL, OP_RGBPREP,
  OP_UNETIN, OP_TASKMAP, OP_CHANMIX) = range(1, 14)
@@ -47,7 +48,7 @@ class GemmArgs(C.Structure):
         ("ldc", i32), ("ld_aux", i32),
         ("rowmap", i32),
         ("img_h", i32), ("img_w", i32),
-        ("block_n", i32),
+        ("block_n", i32), ("fmt16", i32),
     ]
 
 
@@ -64,7 +65,7 @@ class FattnArgs(C.Structure):
     _fields_ = [
         ("qkv", vp), ("ld", i32), ("q_col0", i32), ("k_col0", i32), ("v_col0", i32),
         ("batch", i32), ("ntok", i32), ("heads", i32),
-        ("out_bf16", vp), ("ldo", i32), ("scale", f32),
+        ("out_bf16", vp), ("ldo", i32), ("scale", f32), ("fmt16", i32), ("pad_", i32),
     ]
 
 
@@ -74,7 +75,7 @@ class FattnOp(C.Structure):
 
 
 class SoftmaxArgs(C.Structure):
-    _fields_ = [("s", vp), ("rows", i64), ("n", i32), ("lds", i32), ("scale", f32), ("p_bf16", vp), ("ldp", i32)]
+    _fields_ = [("s", vp), ("rows", i64), ("n", i32), ("lds", i32), ("scale", f32), ("p_bf16", vp), ("ldp", i32), ("fmt16", i32)]
 
 
 class XattnArgs(C.Structure):
@@ -83,7 +84,7 @@ class XattnArgs(C.Structure):
         ("kc", vp), ("vc", vp),
         ("ntok", i32 * MAX_TASKS), ("task_of_group", i32 * MAX_TASKS),
         ("rows_per_group", i64),
-        ("out_bf16", vp), ("ldo", i32), ("scale", f32),
+        ("out_bf16", vp), ("ldo", i32), ("scale", f32), ("fmt16", i32), ("pad_", i32),
     ]
 
 
@@ -93,7 +94,7 @@ class TaskAttnArgs(C.Structure):
         ("c", i32), ("nheads", i32), ("n_main", i32), ("n_src", i32),
         ("rows_per_group", i64),
         ("main_task", i32 * MAX_TASKS), ("src_task", i32 * MAX_TASKS),
-        ("exclude_self", i32), ("scale", f32),
+        ("exclude_self", i32), ("scale", f32), ("fmt16", i32), ("pad_", i32),
     ]
 
 
@@ -104,7 +105,7 @@ class GnArgs(C.Structure):
         ("partial", vp), ("nchunk", i32),
         ("gamma", vp), ("beta", vp),
         ("silu", i32), ("pad_out", i32),
-        ("out_bf16", vp), ("raw_bf16", vp),
+        ("out_bf16", vp), ("raw_bf16", vp), ("fmt16", i32), ("pad_", i32),
     ]
 
 
@@ -114,22 +115,22 @@ class LnArgs(C.Structure):
         ("rows", i64), ("eps", f32), ("rows_per_group", i64),
         ("gamma0", vp), ("beta0", vp), ("out0", vp),
         ("gamma1", vp), ("beta1", vp), ("out1", vp),
-        ("ldo", i32), ("pad_", i32),
+        ("ldo", i32), ("fmt16", i32),
     ]
 
 
 class UpsampleArgs(C.Structure):
     _fields_ = [("x", vp), ("batch", i32), ("h", i32), ("w", i32), ("c", i32), ("oh", i32), ("ow", i32),
-                ("out_bf16", vp)]
+                ("out_bf16", vp), ("fmt16", i32), ("pad_", i32)]
 
 
 class Im2colArgs(C.Structure):
     _fields_ = [("x", vp), ("batch", i32), ("h", i32), ("w", i32), ("c", i32), ("stride", i32), ("pad_t", i32),
-                ("pad_l", i32), ("oh", i32), ("ow", i32), ("kpad", i32), ("out_bf16", vp)]
+                ("pad_l", i32), ("oh", i32), ("ow", i32), ("kpad", i32), ("out_bf16", vp), ("fmt16", i32), ("pad_", i32)]
 
 
 class RgbprepArgs(C.Structure):
-    _fields_ = [("rgb_nchw", vp), ("batch", i32), ("h", i32), ("w", i32), ("out_nhwc", vp)]
+    _fields_ = [("rgb_nchw", vp), ("batch", i32), ("h", i32), ("w", i32), ("src_u8", i32), ("out_nhwc", vp)]
 
 
 class UnetinArgs(C.Structure):

@@ -23,9 +23,10 @@ struct alignas(64) FattnKParams {
     CUtensorMap tm;
     int32_t q_col0, k_col0, v_col0;
     int32_t ntok, heads;
-    __nv_bfloat16* out;
+    uint16_t* out;
     int32_t ldo;
     float scale_log2;
+    int32_t fmt;
 };
 
 __global__ void __launch_bounds__(FA_THREADS, 2) smtl_fattn_kernel(const __grid_constant__ FattnKParams p) {
@@ -87,8 +88,8 @@ __global__ void __launch_bounds__(FA_THREADS, 2) smtl_fattn_kernel(const __grid_
             }
         }
     } else if (warp == 1) {
-        constexpr uint32_t IDESC_S = make_idesc_bf16(BQ, BKV, 0, 0);   // S[128,128] = Q[128,64] K[128,64]^T
-        constexpr uint32_t IDESC_O = make_idesc_bf16(BQ, HD, 0, 1);    // O[128,64] += P[128,128] V[128,64] (V MN-major)
+        const uint32_t IDESC_S = make_idesc_16(BQ, BKV, 0, 0, p.fmt);   // S[128,128] = Q[128,64] K[128,64]^T
+        const uint32_t IDESC_O = make_idesc_16(BQ, HD, 0, 1, p.fmt);    // O[128,64] += P[128,128] V[128,64] (V MN-major)
         mbar_wait(q_full, 0);
         for (int j = 0; j < ntiles; ++j) {
             const int s = j & 1;
@@ -159,8 +160,8 @@ __global__ void __launch_bounds__(FA_THREADS, 2) smtl_fattn_kernel(const __grid_
                 for (int i = 0; i < 32; i += 2) {
                     float p0 = (c * 32 + i < kv_valid) ? exp2f(__uint_as_float(rr[i]) * p.scale_log2 - m_new) : 0.f;
                     float p1 = (c * 32 + i + 1 < kv_valid) ? exp2f(__uint_as_float(rr[i + 1]) * p.scale_log2 - m_new) : 0.f;
-                    const uint32_t u = pack_bf16x2(p0, p1);
-                    const float2 back = unpack_bf16x2(u);   // sum what the tensor core will actually see
+                    const uint32_t u = pack16x2(p0, p1, p.fmt);
+                    const float2 back = unpack16x2(u, p.fmt);   // sum what the tensor core will actually see
                     psum += back.x + back.y;
                     pk[i >> 1] = u;
                 }
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2) smtl_fattn_kernel(const __grid_
         tc_fence_after();
         const float inv = 1.0f / l_run;
         const bool row_ok = (q0 + r) < p.ntok;
-        __nv_bfloat16* dst = p.out + (int64_t)(row_base + q0 + r) * p.ldo + hd * HD;
+        uint16_t* dst = p.out + (int64_t)(row_base + q0 + r) * p.ldo + hd * HD;
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
             uint32_t rr[32];
@@ -211,10 +212,10 @@ __global__ void __launch_bounds__(FA_THREADS, 2) smtl_fattn_kernel(const __grid_
 #pragma unroll
                 for (int i = 0; i < 32; i += 8) {
                     uint4 o;
-                    o.x = pack_bf16x2(__uint_as_float(rr[i]) * inv, __uint_as_float(rr[i + 1]) * inv);
-                    o.y = pack_bf16x2(__uint_as_float(rr[i + 2]) * inv, __uint_as_float(rr[i + 3]) * inv);
-                    o.z = pack_bf16x2(__uint_as_float(rr[i + 4]) * inv, __uint_as_float(rr[i + 5]) * inv);
-                    o.w = pack_bf16x2(__uint_as_float(rr[i + 6]) * inv, __uint_as_float(rr[i + 7]) * inv);
+                    o.x = pack16x2(__uint_as_float(rr[i]) * inv, __uint_as_float(rr[i + 1]) * inv, p.fmt);
+                    o.y = pack16x2(__uint_as_float(rr[i + 2]) * inv, __uint_as_float(rr[i + 3]) * inv, p.fmt);
+                    o.z = pack16x2(__uint_as_float(rr[i + 4]) * inv, __uint_as_float(rr[i + 5]) * inv, p.fmt);
+                    o.w = pack16x2(__uint_as_float(rr[i + 6]) * inv, __uint_as_float(rr[i + 7]) * inv, p.fmt);
                     *reinterpret_cast<uint4*>(dst + c * 32 + i) = o;
                 }
             }
@@ -263,7 +264,8 @@ extern "C" int smtl_fattn_run(const smtl_fattn_op* op, void* stream) {
     kp.v_col0 = a.v_col0;
     kp.ntok = a.ntok;
     kp.heads = a.heads;
-    kp.out = reinterpret_cast<__nv_bfloat16*>(a.out_bf16);
+    kp.out = reinterpret_cast<uint16_t*>(a.out_bf16);
+    kp.fmt = a.fmt16;
     kp.ldo = a.ldo;
     kp.scale_log2 = a.scale * 1.4426950408889634f;
     smtl_fattn_kernel<<<dim3(op->grid_x, op->grid_y), FA_THREADS, op->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(kp);

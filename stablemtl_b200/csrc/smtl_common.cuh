@@ -7,6 +7,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -141,11 +142,15 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128_lbo(uint32_t smem_addr,
     return d;
 }
 
-// Instruction descriptor, kind::f16, bf16 x bf16 -> fp32. a_mn / b_mn = 1 selects an MN-major operand.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn = 0, int b_mn = 0) {
+// 16-bit operand formats of the path (SMTL_FMT_* in the C header): both run at the same kind::f16 tensor rate.
+constexpr int FMT_BF16 = 0;
+constexpr int FMT_F16 = 1;
+
+// Instruction descriptor, kind::f16, 16-bit x 16-bit -> fp32. a_mn / b_mn = 1 selects an MN-major operand.
+__host__ __device__ constexpr uint32_t make_idesc_16(int M, int N, int a_mn, int b_mn, int fmt) {
     return (1u << 4)                                  // D format: F32
-           | (1u << 7)                                // A format: BF16
-           | (1u << 10)                               // B format: BF16
+           | ((fmt == FMT_F16 ? 0u : 1u) << 7)        // A format: F16 = 0, BF16 = 1
+           | ((fmt == FMT_F16 ? 0u : 1u) << 10)       // B format
            | (static_cast<uint32_t>(a_mn) << 15)      // A major
            | (static_cast<uint32_t>(b_mn) << 16)      // B major
            | (static_cast<uint32_t>(N >> 3) << 17)    // N / 8
@@ -186,13 +191,27 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+// fp32 -> 16-bit pair.  fp16 conversions saturate at +-65504 instead of overflowing to inf.
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi, int fmt) {
+    if (fmt == FMT_F16) {
+        lo = fminf(fmaxf(lo, -65504.f), 65504.f);
+        hi = fminf(fmaxf(hi, -65504.f), 65504.f);
+        __half2 v = __floats2half2_rn(lo, hi);
+        return *reinterpret_cast<uint32_t*>(&v);
+    }
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+__device__ __forceinline__ float2 unpack16x2(uint32_t u, int fmt) {
+    if (fmt == FMT_F16) {
+        __half2 v = *reinterpret_cast<__half2*>(&u);
+        return __half22float2(v);
+    }
     __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
     return __bfloat1622float2(v);
+}
+__device__ __forceinline__ uint16_t to16(float x, int fmt) {
+    return static_cast<uint16_t>(pack16x2(x, 0.f, fmt) & 0xFFFFu);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

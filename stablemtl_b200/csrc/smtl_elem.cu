@@ -56,7 +56,7 @@ __global__ void gn_stats_kernel(const float* __restrict__ x0, const float* __res
 __global__ void gn_apply_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int c0, int c1, int h, int w,
                                 int groups, float eps, const float* __restrict__ partial, int nchunk,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu, int pad_out,
-                                __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ raw) {
+                                uint16_t* __restrict__ out, uint16_t* __restrict__ raw, int fmt) {
     extern __shared__ float sm[];   // scale[C], shift[C], mean[groups], rstd[groups]
     const int C = c0 + c1;
     float* scale = sm;
@@ -110,8 +110,8 @@ __global__ void gn_apply_kernel(const float* __restrict__ x0, const float* __res
             const float4 a = ldg4(ptr), bb = ldg4(ptr + 4);
             float v[8] = {a.x, a.y, a.z, a.w, bb.x, bb.y, bb.z, bb.w};
             if (raw) {
-                r.x = pack_bf16x2(v[0], v[1]); r.y = pack_bf16x2(v[2], v[3]);
-                r.z = pack_bf16x2(v[4], v[5]); r.w = pack_bf16x2(v[6], v[7]);
+                r.x = pack16x2(v[0], v[1], fmt); r.y = pack16x2(v[2], v[3], fmt);
+                r.z = pack16x2(v[4], v[5], fmt); r.w = pack16x2(v[6], v[7], fmt);
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -119,8 +119,8 @@ __global__ void gn_apply_kernel(const float* __restrict__ x0, const float* __res
                 if (do_silu) t = silu(t);
                 v[i] = t;
             }
-            o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-            o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+            o.x = pack16x2(v[0], v[1], fmt); o.y = pack16x2(v[2], v[3], fmt);
+            o.z = pack16x2(v[4], v[5], fmt); o.w = pack16x2(v[6], v[7], fmt);
         }
         const int64_t orow = (int64_t)b * hp * wp + pix;
         *reinterpret_cast<uint4*>(out + orow * C + c) = o;
@@ -133,8 +133,8 @@ __global__ void gn_apply_kernel(const float* __restrict__ x0, const float* __res
 template <bool IN_BF16>
 __global__ void ln_kernel(const void* __restrict__ xv, int c, int ldx, int64_t rows, float eps, int64_t rows_per_group,
                           const float* __restrict__ gamma0, const float* __restrict__ beta0,
-                          __nv_bfloat16* __restrict__ out0, const float* __restrict__ gamma1,
-                          const float* __restrict__ beta1, __nv_bfloat16* __restrict__ out1, int ldo) {
+                          uint16_t* __restrict__ out0, const float* __restrict__ gamma1,
+                          const float* __restrict__ beta1, uint16_t* __restrict__ out1, int ldo, int fmt) {
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -146,9 +146,9 @@ __global__ void ln_kernel(const void* __restrict__ xv, int c, int ldx, int64_t r
         const int j = lane + 32 * i;
         if (j < nv) {
             if (IN_BF16) {
-                const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(xv) +
+                const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(xv) +
                                                                      row * ldx + 4 * j));
-                const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+                const float2 a = unpack16x2(u.x, fmt), b = unpack16x2(u.y, fmt);
                 v[i] = make_float4(a.x, a.y, b.x, b.y);
             } else {
                 v[i] = ldg4(reinterpret_cast<const float*>(xv) + row * ldx + 4 * j);
@@ -177,15 +177,15 @@ __global__ void ln_kernel(const void* __restrict__ xv, int c, int ldx, int64_t r
             {
                 const float4 g = ldg4(gamma0 + grp * c + 4 * j), b = ldg4(beta0 + grp * c + 4 * j);
                 uint2 o;
-                o.x = pack_bf16x2(n0 * g.x + b.x, n1 * g.y + b.y);
-                o.y = pack_bf16x2(n2 * g.z + b.z, n3 * g.w + b.w);
+                o.x = pack16x2(n0 * g.x + b.x, n1 * g.y + b.y, fmt);
+                o.y = pack16x2(n2 * g.z + b.z, n3 * g.w + b.w, fmt);
                 *reinterpret_cast<uint2*>(out0 + row * ldo + 4 * j) = o;
             }
             if (out1) {
                 const float4 g = ldg4(gamma1 + grp * c + 4 * j), b = ldg4(beta1 + grp * c + 4 * j);
                 uint2 o;
-                o.x = pack_bf16x2(n0 * g.x + b.x, n1 * g.y + b.y);
-                o.y = pack_bf16x2(n2 * g.z + b.z, n3 * g.w + b.w);
+                o.x = pack16x2(n0 * g.x + b.x, n1 * g.y + b.y, fmt);
+                o.y = pack16x2(n2 * g.z + b.z, n3 * g.w + b.w, fmt);
                 *reinterpret_cast<uint2*>(out1 + row * ldo + 4 * j) = o;
             }
         }
@@ -194,7 +194,7 @@ __global__ void ln_kernel(const void* __restrict__ xv, int c, int ldx, int64_t r
 
 // ============================================================================================= layout producers
 __global__ void upsample_pad_kernel(const float* __restrict__ x, int batch, int h, int w, int c, int oh, int ow,
-                                    __nv_bfloat16* __restrict__ out) {
+                                    uint16_t* __restrict__ out, int fmt) {
     const int cv8 = c >> 3;
     const int hp = oh + 2, wp = ow + 2;
     const int64_t total = (int64_t)batch * hp * wp * cv8;
@@ -212,8 +212,8 @@ __global__ void upsample_pad_kernel(const float* __restrict__ x, int batch, int 
             const int xsrc = min((int)floorf((float)(xp - 1) * sx), w - 1);
             const float* ptr = x + (((int64_t)b * h + ysrc) * w + xsrc) * c + cc;
             const float4 a = ldg4(ptr), bb = ldg4(ptr + 4);
-            o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
-            o.z = pack_bf16x2(bb.x, bb.y); o.w = pack_bf16x2(bb.z, bb.w);
+            o.x = pack16x2(a.x, a.y, fmt); o.y = pack16x2(a.z, a.w, fmt);
+            o.z = pack16x2(bb.x, bb.y, fmt); o.w = pack16x2(bb.z, bb.w, fmt);
         }
         *reinterpret_cast<uint4*>(out + pix * c + cc) = o;
     }
@@ -221,7 +221,7 @@ __global__ void upsample_pad_kernel(const float* __restrict__ x, int batch, int 
 
 // im2col, 8 channels per thread (c % 8 == 0, kpad == 9*c)
 __global__ void im2col_vec8_kernel(const float* __restrict__ x, int batch, int h, int w, int c, int stride, int pad_t,
-                                   int pad_l, int oh, int ow, __nv_bfloat16* __restrict__ out) {
+                                   int pad_l, int oh, int ow, uint16_t* __restrict__ out, int fmt) {
     const int cv8 = c >> 3;
     const int64_t total = (int64_t)batch * oh * ow * 9 * cv8;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -238,15 +238,15 @@ __global__ void im2col_vec8_kernel(const float* __restrict__ x, int batch, int h
         if (iy >= 0 && iy < h && ix >= 0 && ix < w) {
             const float* ptr = x + (((int64_t)b * h + iy) * w + ix) * c + cc;
             const float4 a = ldg4(ptr), bb = ldg4(ptr + 4);
-            o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
-            o.z = pack_bf16x2(bb.x, bb.y); o.w = pack_bf16x2(bb.z, bb.w);
+            o.x = pack16x2(a.x, a.y, fmt); o.y = pack16x2(a.z, a.w, fmt);
+            o.z = pack16x2(bb.x, bb.y, fmt); o.w = pack16x2(bb.z, bb.w, fmt);
         }
         *reinterpret_cast<uint4*>(out + opix * (int64_t)(9 * c) + tap * c + cc) = o;
     }
 }
 // im2col, scalar (tiny Cin stems: 3 or 12 channels), zero-fills k in [9c, kpad)
 __global__ void im2col_scalar_kernel(const float* __restrict__ x, int batch, int h, int w, int c, int stride, int pad_t,
-                                     int pad_l, int oh, int ow, int kpad, __nv_bfloat16* __restrict__ out) {
+                                     int pad_l, int oh, int ow, int kpad, uint16_t* __restrict__ out, int fmt) {
     const int64_t total = (int64_t)batch * oh * ow * kpad;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
@@ -261,18 +261,20 @@ __global__ void im2col_scalar_kernel(const float* __restrict__ x, int batch, int
             const int iy = oy * stride - pad_t + tap / 3, ix = ox * stride - pad_l + tap % 3;
             if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = __ldg(x + (((int64_t)b * h + iy) * w + ix) * c + cc);
         }
-        out[idx] = __float2bfloat16(v);
+        out[idx] = to16(v, fmt);
     }
 }
 
-__global__ void rgbprep_kernel(const float* __restrict__ rgb, int batch, int hw, float* __restrict__ out) {
+__global__ void rgbprep_kernel(const void* __restrict__ rgbv, int src_u8, int batch, int hw, float* __restrict__ out) {
+    const float* rgb = reinterpret_cast<const float*>(rgbv);
+    const uint8_t* rgb8 = reinterpret_cast<const uint8_t*>(rgbv);
     const int64_t total = (int64_t)batch * hw;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t b = idx / hw, p = idx - b * hw;
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
-            const float v = __ldg(rgb + (b * 3 + ch) * hw + p);
+            const float v = src_u8 ? (float)__ldg(rgb8 + (b * 3 + ch) * hw + p) : __ldg(rgb + (b * 3 + ch) * hw + p);
             out[idx * 3 + ch] = v / 255.0f * 2.0f - 1.0f;   // same op order as stablemtl_pipeline.py:263
         }
     }
@@ -297,7 +299,7 @@ __global__ void unetin_kernel(const float* __restrict__ lat, const int* __restri
 // ============================================================================================= small attentions
 // row softmax fp32 -> bf16 (n <= 8192), one CTA of 256 threads per row
 __global__ void softmax_rows_kernel(const float* __restrict__ s, int n, int lds, float scale,
-                                    __nv_bfloat16* __restrict__ p, int ldp) {
+                                    uint16_t* __restrict__ p, int ldp, int fmt) {
     __shared__ float red[8];
     const int64_t row = blockIdx.x;
     const float* src = s + row * lds;
@@ -332,7 +334,7 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, int n, int lds,
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
         const int j = threadIdx.x + i * 256;
-        if (j < n) p[row * ldp + j] = __float2bfloat16(v[i] * inv);
+        if (j < n) p[row * ldp + j] = to16(v[i] * inv, fmt);
     }
 }
 
@@ -341,9 +343,9 @@ struct XattnK {
     int task_of_group[SMTL_MAX_TASKS];
 };
 // cross-attention on <= 4 constant keys: one warp per token row, lane owns 2 of the 64 head dims
-__global__ void xattn_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int64_t rows, int heads,
+__global__ void xattn_kernel(const uint16_t* __restrict__ q, int ldq, int64_t rows, int heads,
                              const float* __restrict__ kc, const float* __restrict__ vc, XattnK tk,
-                             int64_t rows_per_group, __nv_bfloat16* __restrict__ out, int ldo, float scale) {
+                             int64_t rows_per_group, uint16_t* __restrict__ out, int ldo, float scale, int fmt) {
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -355,7 +357,7 @@ __global__ void xattn_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int64
     const float* vbase = vc + (int64_t)task * 4 * C;
     for (int hd = 0; hd < heads; ++hd) {
         const int col = hd * 64 + 2 * lane;
-        const float2 qv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(q + row * ldq + col));
+        const float2 qv = unpack16x2(*reinterpret_cast<const uint32_t*>(q + row * ldq + col), fmt);
         float sc[4];
         float mx = -INFINITY;
 #pragma unroll
@@ -382,7 +384,7 @@ __global__ void xattn_kernel(const __nv_bfloat16* __restrict__ q, int ldq, int64
                 o1 += sc[j] * vv.y;
             }
         }
-        *reinterpret_cast<uint32_t*>(out + row * ldo + col) = pack_bf16x2(o0 * inv, o1 * inv);
+        *reinterpret_cast<uint32_t*>(out + row * ldo + col) = pack16x2(o0 * inv, o1 * inv, fmt);
     }
 }
 
@@ -391,10 +393,10 @@ struct TaskIds {
     int src_task[SMTL_MAX_TASKS];
 };
 // per-pixel cross-task attention: one thread per (q row, head); Nk <= 8 source streams
-__global__ void taskattn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
-                                const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out, int c, int nheads,
+__global__ void taskattn_kernel(const uint16_t* __restrict__ q, const uint16_t* __restrict__ k,
+                                const uint16_t* __restrict__ v, uint16_t* __restrict__ out, int c, int nheads,
                                 int n_main, int n_src, int64_t rows_per_group, TaskIds ids, int exclude_self,
-                                float scale) {
+                                float scale, int fmt) {
     const int64_t total = (int64_t)n_main * rows_per_group * nheads;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -417,10 +419,10 @@ __global__ void taskattn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_
             for (int i = 0; i < nch; ++i) {
                 const uint4 a = __ldg(qp + i), b = __ldg(kp + i);
                 float2 x, y;
-                x = unpack_bf16x2(a.x); y = unpack_bf16x2(b.x); d += x.x * y.x + x.y * y.y;
-                x = unpack_bf16x2(a.y); y = unpack_bf16x2(b.y); d += x.x * y.x + x.y * y.y;
-                x = unpack_bf16x2(a.z); y = unpack_bf16x2(b.z); d += x.x * y.x + x.y * y.y;
-                x = unpack_bf16x2(a.w); y = unpack_bf16x2(b.w); d += x.x * y.x + x.y * y.y;
+                x = unpack16x2(a.x, fmt); y = unpack16x2(b.x, fmt); d += x.x * y.x + x.y * y.y;
+                x = unpack16x2(a.y, fmt); y = unpack16x2(b.y, fmt); d += x.x * y.x + x.y * y.y;
+                x = unpack16x2(a.z, fmt); y = unpack16x2(b.z, fmt); d += x.x * y.x + x.y * y.y;
+                x = unpack16x2(a.w, fmt); y = unpack16x2(b.w, fmt); d += x.x * y.x + x.y * y.y;
             }
             sc[s] = d * scale;
             mx = fmaxf(mx, sc[s]);
@@ -442,15 +444,15 @@ __global__ void taskattn_kernel(const __nv_bfloat16* __restrict__ q, const __nv_
                 const uint4 b =
                     __ldg(reinterpret_cast<const uint4*>(v + ((int64_t)s * rows_per_group + pix) * c + hd * dh) + i);
                 float2 y;
-                y = unpack_bf16x2(b.x); acc[0] += sc[s] * y.x; acc[1] += sc[s] * y.y;
-                y = unpack_bf16x2(b.y); acc[2] += sc[s] * y.x; acc[3] += sc[s] * y.y;
-                y = unpack_bf16x2(b.z); acc[4] += sc[s] * y.x; acc[5] += sc[s] * y.y;
-                y = unpack_bf16x2(b.w); acc[6] += sc[s] * y.x; acc[7] += sc[s] * y.y;
+                y = unpack16x2(b.x, fmt); acc[0] += sc[s] * y.x; acc[1] += sc[s] * y.y;
+                y = unpack16x2(b.y, fmt); acc[2] += sc[s] * y.x; acc[3] += sc[s] * y.y;
+                y = unpack16x2(b.z, fmt); acc[4] += sc[s] * y.x; acc[5] += sc[s] * y.y;
+                y = unpack16x2(b.w, fmt); acc[6] += sc[s] * y.x; acc[7] += sc[s] * y.y;
             }
         }
         uint4 o;
-        o.x = pack_bf16x2(acc[0] * inv, acc[1] * inv); o.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
-        o.z = pack_bf16x2(acc[4] * inv, acc[5] * inv); o.w = pack_bf16x2(acc[6] * inv, acc[7] * inv);
+        o.x = pack16x2(acc[0] * inv, acc[1] * inv, fmt); o.y = pack16x2(acc[2] * inv, acc[3] * inv, fmt);
+        o.z = pack16x2(acc[4] * inv, acc[5] * inv, fmt); o.w = pack16x2(acc[6] * inv, acc[7] * inv, fmt);
         op[i] = o;
     }
 }
@@ -554,7 +556,7 @@ extern "C" int smtl_gn_run(const smtl_gn_args* a, void* stream) {
     const size_t smem = (2 * C + 2 * a->groups) * sizeof(float);
     gn_apply_kernel<<<dim3(bpi, a->batch), 256, smem, st>>>(
         a->x0, a->x1, a->c0, a->c1, a->h, a->w, a->groups, a->eps, a->partial, a->nchunk, a->gamma, a->beta, a->silu,
-        a->pad_out, reinterpret_cast<__nv_bfloat16*>(a->out_bf16), reinterpret_cast<__nv_bfloat16*>(a->raw_bf16));
+        a->pad_out, reinterpret_cast<uint16_t*>(a->out_bf16), reinterpret_cast<uint16_t*>(a->raw_bf16), a->fmt16);
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;
 }
@@ -570,12 +572,12 @@ extern "C" int smtl_ln_run(const smtl_ln_args* a, void* stream) {
     const int64_t grid = (a->rows + wpb - 1) / wpb;
     if (a->x_is_bf16)
         ln_kernel<true><<<(unsigned)grid, wpb * 32, 0, st>>>(a->x, a->c, a->ldx, a->rows, a->eps, a->rows_per_group,
-                                                             a->gamma0, a->beta0, (__nv_bfloat16*)a->out0, a->gamma1,
-                                                             a->beta1, (__nv_bfloat16*)a->out1, a->ldo);
+                                                             a->gamma0, a->beta0, (uint16_t*)a->out0, a->gamma1,
+                                                             a->beta1, (uint16_t*)a->out1, a->ldo, a->fmt16);
     else
         ln_kernel<false><<<(unsigned)grid, wpb * 32, 0, st>>>(a->x, a->c, a->ldx, a->rows, a->eps, a->rows_per_group,
-                                                              a->gamma0, a->beta0, (__nv_bfloat16*)a->out0, a->gamma1,
-                                                              a->beta1, (__nv_bfloat16*)a->out1, a->ldo);
+                                                              a->gamma0, a->beta0, (uint16_t*)a->out0, a->gamma1,
+                                                              a->beta1, (uint16_t*)a->out1, a->ldo, a->fmt16);
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;
 }
@@ -586,7 +588,7 @@ extern "C" int smtl_upsample_run(const smtl_upsample_args* a, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int64_t total = (int64_t)a->batch * (a->oh + 2) * (a->ow + 2) * (a->c / 8);
     upsample_pad_kernel<<<grid_for(total, 256), 256, 0, st>>>(a->x, a->batch, a->h, a->w, a->c, a->oh, a->ow,
-                                                              (__nv_bfloat16*)a->out_bf16);
+                                                              (uint16_t*)a->out_bf16, a->fmt16);
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;
 }
@@ -598,12 +600,12 @@ extern "C" int smtl_im2col_run(const smtl_im2col_args* a, void* stream) {
     if (a->c % 8 == 0 && a->kpad == 9 * a->c) {
         const int64_t total = (int64_t)a->batch * a->oh * a->ow * 9 * (a->c / 8);
         im2col_vec8_kernel<<<grid_for(total, 256), 256, 0, st>>>(a->x, a->batch, a->h, a->w, a->c, a->stride, a->pad_t,
-                                                                 a->pad_l, a->oh, a->ow, (__nv_bfloat16*)a->out_bf16);
+                                                                 a->pad_l, a->oh, a->ow, (uint16_t*)a->out_bf16, a->fmt16);
     } else {
         const int64_t total = (int64_t)a->batch * a->oh * a->ow * a->kpad;
         im2col_scalar_kernel<<<grid_for(total, 256), 256, 0, st>>>(a->x, a->batch, a->h, a->w, a->c, a->stride,
                                                                    a->pad_t, a->pad_l, a->oh, a->ow, a->kpad,
-                                                                   (__nv_bfloat16*)a->out_bf16);
+                                                                   (uint16_t*)a->out_bf16, a->fmt16);
     }
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;
@@ -613,7 +615,7 @@ extern "C" int smtl_rgbprep_run(const smtl_rgbprep_args* a, void* stream) {
     SMTL_CHECK_ARG(a && a->rgb_nchw && a->out_nhwc, "rgbprep: NULL argument");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int64_t total = (int64_t)a->batch * a->h * a->w;
-    rgbprep_kernel<<<grid_for(total, 256), 256, 0, st>>>(a->rgb_nchw, a->batch, a->h * a->w, a->out_nhwc);
+    rgbprep_kernel<<<grid_for(total, 256), 256, 0, st>>>(a->rgb_nchw, a->src_u8, a->batch, a->h * a->w, a->out_nhwc);
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;
 }
@@ -632,8 +634,8 @@ extern "C" int smtl_softmax_run(const smtl_softmax_args* a, void* stream) {
     SMTL_CHECK_ARG(a && a->s && a->p_bf16, "softmax: NULL argument");
     SMTL_CHECK_ARG(a->n > 0 && a->n <= 8192 && a->rows > 0, "softmax: n=%d out of range", a->n);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    softmax_rows_kernel<<<(unsigned)a->rows, 256, 0, st>>>(a->s, a->n, a->lds, a->scale, (__nv_bfloat16*)a->p_bf16,
-                                                           a->ldp);
+    softmax_rows_kernel<<<(unsigned)a->rows, 256, 0, st>>>(a->s, a->n, a->lds, a->scale, (uint16_t*)a->p_bf16,
+                                                           a->ldp, a->fmt16);
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;
 }
@@ -652,9 +654,9 @@ extern "C" int smtl_xattn_run(const smtl_xattn_args* a, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int wpb = 8;
     const int64_t grid = (a->rows + wpb - 1) / wpb;
-    xattn_kernel<<<(unsigned)grid, wpb * 32, 0, st>>>((const __nv_bfloat16*)a->q_bf16, a->ldq, a->rows, a->heads, a->kc,
-                                                      a->vc, tk, a->rows_per_group, (__nv_bfloat16*)a->out_bf16, a->ldo,
-                                                      a->scale);
+    xattn_kernel<<<(unsigned)grid, wpb * 32, 0, st>>>((const uint16_t*)a->q_bf16, a->ldq, a->rows, a->heads, a->kc,
+                                                      a->vc, tk, a->rows_per_group, (uint16_t*)a->out_bf16, a->ldo,
+                                                      a->scale, a->fmt16);
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;
 }
@@ -669,10 +671,10 @@ extern "C" int smtl_taskattn_run(const smtl_taskattn_args* a, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int64_t total = (int64_t)a->n_main * a->rows_per_group * a->nheads;
     const int64_t grid = (total + 127) / 128;
-    taskattn_kernel<<<(unsigned)grid, 128, 0, st>>>((const __nv_bfloat16*)a->q_bf16, (const __nv_bfloat16*)a->k_bf16,
-                                                    (const __nv_bfloat16*)a->v_bf16, (__nv_bfloat16*)a->out_bf16, a->c,
+    taskattn_kernel<<<(unsigned)grid, 128, 0, st>>>((const uint16_t*)a->q_bf16, (const uint16_t*)a->k_bf16,
+                                                    (const uint16_t*)a->v_bf16, (uint16_t*)a->out_bf16, a->c,
                                                     a->nheads, a->n_main, a->n_src, a->rows_per_group, ids,
-                                                    a->exclude_self, a->scale);
+                                                    a->exclude_self, a->scale, a->fmt16);
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;
 }

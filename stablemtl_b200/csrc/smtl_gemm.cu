@@ -42,12 +42,13 @@ struct alignas(64) GemmKParams {
     const float* res2;
     int32_t ldres;
     float* out_f32;
-    __nv_bfloat16* out_bf16;
-    __nv_bfloat16* aux_bf16;
+    uint16_t* out_bf16;
+    uint16_t* aux_bf16;
     int32_t ldc;
     int32_t ld_aux;
     int32_t rowmap;
     int32_t img_h, img_w;
+    int32_t fmt;
 };
 
 __device__ __forceinline__ void st_global_v4_f32(float* p, float a, float b, float c, float d) {
@@ -63,7 +64,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
     constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     constexpr int TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
     constexpr int ACC_STRIDE = TMEM_COLS / 2;
-    constexpr uint32_t IDESC = make_idesc_bf16(BLOCK_M, BN);
     constexpr int MAX_STAGES = 12;
 
     extern __shared__ uint8_t smem_raw[];
@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
+        const uint32_t IDESC = make_idesc_16(BLOCK_M, BN, 0, 0, p.fmt);
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
@@ -230,15 +231,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
                 if (row_ok) {
                 const bool full = (ocol + 32 <= p.n_out);
                 if (p.aux_bf16) {
-                    __nv_bfloat16* dst = p.aux_bf16 + orow * (int64_t)p.ld_aux + ocol;
+                    uint16_t* dst = p.aux_bf16 + orow * (int64_t)p.ld_aux + ocol;
                     if (full && (p.ld_aux & 7) == 0) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 8)
-                            st_global_v4_b32(dst + j, pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
-                                             pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
+                            st_global_v4_b32(dst + j, pack16x2(v[j], v[j + 1], p.fmt), pack16x2(v[j + 2], v[j + 3], p.fmt),
+                                             pack16x2(v[j + 4], v[j + 5], p.fmt), pack16x2(v[j + 6], v[j + 7], p.fmt));
                     } else {
                         for (int j = 0; j < 32; ++j)
-                            if (ocol + j < p.n_out) dst[j] = __float2bfloat16(v[j]);
+                            if (ocol + j < p.n_out) dst[j] = to16(v[j], p.fmt);
                     }
                 }
                 if (p.res1) {
@@ -278,15 +279,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
                     }
                 }
                 if (p.out_bf16) {
-                    __nv_bfloat16* dst = p.out_bf16 + orow * (int64_t)p.ldc + ocol;
+                    uint16_t* dst = p.out_bf16 + orow * (int64_t)p.ldc + ocol;
                     if (full && (p.ldc & 7) == 0) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 8)
-                            st_global_v4_b32(dst + j, pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
-                                             pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
+                            st_global_v4_b32(dst + j, pack16x2(v[j], v[j + 1], p.fmt), pack16x2(v[j + 2], v[j + 3], p.fmt),
+                                             pack16x2(v[j + 4], v[j + 5], p.fmt), pack16x2(v[j + 6], v[j + 7], p.fmt));
                     } else {
                         for (int j = 0; j < 32; ++j)
-                            if (ocol + j < p.n_out) dst[j] = __float2bfloat16(v[j]);
+                            if (ocol + j < p.n_out) dst[j] = to16(v[j], p.fmt);
                     }
                 }
                 }  // row_ok
@@ -371,6 +372,7 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
         SMTL_CHECK_ARG(bn == 256 && g.n % 256 == 0, "gemm_plan: GEGLU needs n %% 256 == 0 (n=%d)", g.n);
         SMTL_CHECK_ARG(!g.bias_per_row, "gemm_plan: GEGLU with per-row bias");
     }
+    SMTL_CHECK_ARG(g.fmt16 == SMTL_FMT_BF16 || g.fmt16 == SMTL_FMT_F16, "gemm_plan: bad fmt16 %d", g.fmt16);
     if (g.rowmap == SMTL_ROWMAP_CONV_PAD)
         SMTL_CHECK_ARG(g.img_h > 0 && g.img_w > 0, "gemm_plan: conv row map needs img_h/img_w");
     SMTL_CHECK_ARG(g.m + 4096 < (int64_t)1 << 31, "gemm_plan: m too large for 32-bit TMA coordinates");
@@ -425,13 +427,14 @@ extern "C" int smtl_gemm_run(const smtl_gemm_op* op, void* stream) {
     kp.res2 = g.res2;
     kp.ldres = g.ldres;
     kp.out_f32 = g.out_f32;
-    kp.out_bf16 = reinterpret_cast<__nv_bfloat16*>(g.out_bf16);
-    kp.aux_bf16 = reinterpret_cast<__nv_bfloat16*>(g.aux_bf16);
+    kp.out_bf16 = reinterpret_cast<uint16_t*>(g.out_bf16);
+    kp.aux_bf16 = reinterpret_cast<uint16_t*>(g.aux_bf16);
     kp.ldc = g.ldc;
     kp.ld_aux = g.ld_aux;
     kp.rowmap = g.rowmap;
     kp.img_h = g.img_h;
     kp.img_w = g.img_w;
+    kp.fmt = g.fmt16;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     switch (op->block_n) {
         case 32: return launch_gemm<32>(kp, op->grid, op->smem_bytes, st);

@@ -18,7 +18,7 @@ from . import ops
 from .synth import UNetConfig, VAEConfig
 from .weights import conv_weight_matrix, interleave_geglu
 
-BF16, F32 = torch.bfloat16, torch.float32
+F32 = torch.float32
 LATENT_SCALE = 0.18215          # stablemtl_pipeline.py:134-135
 
 
@@ -100,9 +100,9 @@ class UNetWeights:
         self.kin_pad = (kin + 63) // 64 * 64
         wm = torch.zeros(c[0], self.kin_pad, device=d)
         wm[:, :kin] = conv_weight_matrix(w_in)
-        self.w["conv_in.w"] = wm.to(BF16)
+        self.w["conv_in.w"] = wm.to(ops.h16())
         self.w["conv_in.b"] = g("conv_in.bias")
-        self.w["conv_out.w"] = conv_weight_matrix(g("conv_out.weight")).to(BF16)
+        self.w["conv_out.w"] = conv_weight_matrix(g("conv_out.weight")).to(ops.h16())
         self.w["conv_out.b"] = g("conv_out.bias")
         self.w["conv_norm_out.g"], self.w["conv_norm_out.b"] = g("conv_norm_out.weight"), g("conv_norm_out.bias")
         self._sd, self._g = sd, g
@@ -113,7 +113,7 @@ class UNetWeights:
             g, w = self._g, self.w
             w[p + ".n1g"], w[p + ".n1b"] = g(p + ".norm1.weight"), g(p + ".norm1.bias")
             w[p + ".n2g"], w[p + ".n2b"] = g(p + ".norm2.weight"), g(p + ".norm2.bias")
-            w[p + ".w1"] = conv_weight_matrix(g(p + ".conv1.weight")).to(BF16)
+            w[p + ".w1"] = conv_weight_matrix(g(p + ".conv1.weight")).to(ops.h16())
             b1 = g(p + ".conv1.bias")
             if (p + ".time_emb_proj.weight") in self._sd:            # resnet.py:183-186, constant at inference
                 b1 = b1 + torch.nn.functional.linear(self.silu_temb, g(p + ".time_emb_proj.weight"),
@@ -126,13 +126,13 @@ class UNetWeights:
                 w2 = torch.cat([w2, ws.reshape(ws.shape[0], ws.shape[1])], dim=1)
                 b2 = b2 + g(p + ".conv_shortcut.bias")
                 w[p + ".short"] = True
-            w[p + ".w2"] = w2.to(BF16).contiguous()
+            w[p + ".w2"] = w2.to(ops.h16()).contiguous()
             w[p + ".b2"] = b2.contiguous()
         return self.w
 
     def conv(self, p):
         if p + ".w" not in self.w:
-            self.w[p + ".w"] = conv_weight_matrix(self._g(p + ".weight")).to(BF16)
+            self.w[p + ".w"] = conv_weight_matrix(self._g(p + ".weight")).to(ops.h16())
             self.w[p + ".b"] = self._g(p + ".bias")
         return self.w[p + ".w"], self.w[p + ".b"]
 
@@ -142,20 +142,20 @@ class UNetWeights:
             t = p + ".transformer_blocks.0"
             w[p + ".ng"], w[p + ".nb"] = g(p + ".norm.weight"), g(p + ".norm.bias")
             for n in ("proj_in", "proj_out"):
-                w[f"{p}.{n}.w"], w[f"{p}.{n}.b"] = g(f"{p}.{n}.weight").to(BF16), g(f"{p}.{n}.bias")
+                w[f"{p}.{n}.w"], w[f"{p}.{n}.b"] = g(f"{p}.{n}.weight").to(ops.h16()), g(f"{p}.{n}.bias")
             for i in (1, 2, 3):
                 w[f"{p}.ln{i}g"], w[f"{p}.ln{i}b"] = g(f"{t}.norm{i}.weight"), g(f"{t}.norm{i}.bias")
             w[p + ".qkv"] = torch.cat([g(f"{t}.attn1.to_q.weight"), g(f"{t}.attn1.to_k.weight"),
-                                       g(f"{t}.attn1.to_v.weight")], dim=0).to(BF16).contiguous()
-            w[p + ".o.w"], w[p + ".o.b"] = g(f"{t}.attn1.to_out.0.weight").to(BF16), g(f"{t}.attn1.to_out.0.bias")
-            w[p + ".q2"] = g(f"{t}.attn2.to_q.weight").to(BF16)
+                                       g(f"{t}.attn1.to_v.weight")], dim=0).to(ops.h16()).contiguous()
+            w[p + ".o.w"], w[p + ".o.b"] = g(f"{t}.attn1.to_out.0.weight").to(ops.h16()), g(f"{t}.attn1.to_out.0.bias")
+            w[p + ".q2"] = g(f"{t}.attn2.to_q.weight").to(ops.h16())
             # cross-attention keys/values of the constant task-name tokens: [ntask, 4, C] fp32
             w[p + ".kc"] = torch.nn.functional.linear(self.text, g(f"{t}.attn2.to_k.weight")).contiguous()
             w[p + ".vc"] = torch.nn.functional.linear(self.text, g(f"{t}.attn2.to_v.weight")).contiguous()
-            w[p + ".o2.w"], w[p + ".o2.b"] = g(f"{t}.attn2.to_out.0.weight").to(BF16), g(f"{t}.attn2.to_out.0.bias")
+            w[p + ".o2.w"], w[p + ".o2.b"] = g(f"{t}.attn2.to_out.0.weight").to(ops.h16()), g(f"{t}.attn2.to_out.0.bias")
             wi, bi = interleave_geglu(g(f"{t}.ff.net.0.proj.weight"), g(f"{t}.ff.net.0.proj.bias"))
-            w[p + ".ff1.w"], w[p + ".ff1.b"] = wi.to(BF16), bi
-            w[p + ".ff2.w"], w[p + ".ff2.b"] = g(f"{t}.ff.net.2.weight").to(BF16), g(f"{t}.ff.net.2.bias")
+            w[p + ".ff1.w"], w[p + ".ff1.b"] = wi.to(ops.h16()), bi
+            w[p + ".ff2.w"], w[p + ".ff2.b"] = g(f"{t}.ff.net.2.weight").to(ops.h16()), g(f"{t}.ff.net.2.bias")
         return self.w
 
     def task_modules(self, p):
@@ -166,13 +166,13 @@ class UNetWeights:
             T = self.tasks
             st = lambda fmt, dt=F32: torch.stack([g(fmt.format(t=t)) for t in T]).to(dt).contiguous()
             for kv in ("k", "v"):
-                w[f"{p}.t{kv}1.w"], w[f"{p}.t{kv}1.b"] = st(a + ".task_to_" + kv + ".{t}.fc1.weight", BF16), st(a + ".task_to_" + kv + ".{t}.fc1.bias")
-                w[f"{p}.t{kv}2.w"], w[f"{p}.t{kv}2.b"] = st(a + ".task_to_" + kv + ".{t}.fc2.weight", BF16), st(a + ".task_to_" + kv + ".{t}.fc2.bias")
+                w[f"{p}.t{kv}1.w"], w[f"{p}.t{kv}1.b"] = st(a + ".task_to_" + kv + ".{t}.fc1.weight", ops.h16()), st(a + ".task_to_" + kv + ".{t}.fc1.bias")
+                w[f"{p}.t{kv}2.w"], w[f"{p}.t{kv}2.b"] = st(a + ".task_to_" + kv + ".{t}.fc2.weight", ops.h16()), st(a + ".task_to_" + kv + ".{t}.fc2.bias")
                 w[f"{p}.tn{kv}.g"], w[f"{p}.tn{kv}.b"] = st(a + ".task_norm_" + kv + ".{t}.weight"), st(a + ".task_norm_" + kv + ".{t}.bias")
             for i, n in enumerate((0, 2, 4, 6)):
-                w[f"{p}.tq{i}.w"], w[f"{p}.tq{i}.b"] = st(a + ".task_to_q.{t}.net." + str(n) + ".weight", BF16), st(a + ".task_to_q.{t}.net." + str(n) + ".bias")
+                w[f"{p}.tq{i}.w"], w[f"{p}.tq{i}.b"] = st(a + ".task_to_q.{t}.net." + str(n) + ".weight", ops.h16()), st(a + ".task_to_q.{t}.net." + str(n) + ".bias")
             w[f"{p}.tnq.g"], w[f"{p}.tnq.b"] = st(a + ".task_norm_q.{t}.weight"), st(a + ".task_norm_q.{t}.bias")
-            w[p + ".tout.w"], w[p + ".tout.b"] = g(a + ".to_out_task.weight").to(BF16), g(a + ".to_out_task.bias")
+            w[p + ".tout.w"], w[p + ".tout.b"] = g(a + ".to_out_task.weight").to(ops.h16()), g(a + ".to_out_task.bias")
         return self.w
 
 
@@ -211,7 +211,7 @@ class UNetPlan:
 
         # ---- stem: [Be, hw, 12] fp32 -> im2col -> GEMM
         self.x_in = x_in if x_in is not None else torch.zeros(Be * h * w, cfg.in_channels, device=dev, dtype=F32)
-        col = P.alloc((Be * h * w, W.kin_pad), BF16)
+        col = P.alloc((Be * h * w, W.kin_pad), ops.h16())
         add(ops.im2col(self.x_in.view(Be, h, w, cfg.in_channels), Be, h, w, col, stride=1, pad_t=1, pad_l=1, oh=h, ow=w))
         x = P.alloc((Be * h * w, c[0]), F32)
         add(ops.gemm(col, W.w["conv_in.w"], bias=W.w["conv_in.b"], out_f32=x, name="conv_in"))
@@ -234,7 +234,7 @@ class UNetPlan:
             if i < nlev - 1:
                 h2, w2 = sizes[i + 1]
                 wt, bs = W.conv(f"down_blocks.{i}.downsamplers.0.conv")
-                col = P.alloc((Be * h2 * w2, 9 * c[i]), BF16)
+                col = P.alloc((Be * h2 * w2, 9 * c[i]), ops.h16())
                 add(ops.im2col(x.view(Be, hh, ww, c[i]), Be, hh, ww, col, stride=2, pad_t=1, pad_l=1, oh=h2, ow=w2))
                 x = P.alloc((Be * h2 * w2, c[i]), F32)
                 add(ops.gemm(col, wt, bias=bs, out_f32=x, name="downsample"))
@@ -265,14 +265,14 @@ class UNetPlan:
             if i < nlev - 1:
                 oh, ow = sizes[lev - 1]                       # explicit size of the next skip (unet.py:415-416)
                 wt, bs = W.conv(f"up_blocks.{i}.upsamplers.0.conv")
-                up = P.alloc((Be * (oh + 2) * (ow + 2), cout), BF16)
+                up = P.alloc((Be * (oh + 2) * (ow + 2), cout), ops.h16())
                 add(ops.upsample_pad(x.view(Be, hh, ww, cout), Be, hh, ww, oh, ow, up))
                 x_new = P.alloc((Be * oh * ow, cout), F32)
                 add(ops.conv3x3(up, wt, Be, oh, ow, bias=bs, out_f32=x_new, name="upsample_conv"))
                 P.release(up, x)
                 x = x_new
         # ---- head
-        a = P.alloc((Be * (h + 2) * (w + 2), c[0]), BF16)
+        a = P.alloc((Be * (h + 2) * (w + 2), c[0]), ops.h16())
         add(ops.group_norm(x, Be, h, w, W.w["conv_norm_out.g"], W.w["conv_norm_out.b"], a, eps=cfg.norm_eps, silu=True,
                            pad_out=True, partial=self.gn_partial, groups=cfg.norm_num_groups))
         self.out = torch.empty(Be * h * w, cfg.out_channels, device=dev, dtype=F32)
@@ -287,14 +287,14 @@ class UNetPlan:
         wt = W.resnet(p)
         cin = x.shape[1] + (skip.shape[1] if skip is not None else 0)
         short = wt.get(p + ".short", False)
-        a1 = P.alloc((Be * (h + 2) * (w + 2), cin), BF16)
-        raw = P.alloc((Be * (h + 2) * (w + 2), cin), BF16) if short else None
+        a1 = P.alloc((Be * (h + 2) * (w + 2), cin), ops.h16())
+        raw = P.alloc((Be * (h + 2) * (w + 2), cin), ops.h16()) if short else None
         add(ops.group_norm(x, Be, h, w, wt[p + ".n1g"], wt[p + ".n1b"], a1, x1=skip, eps=cfg.norm_eps, silu=True,
                            pad_out=True, partial=self.gn_partial, raw=raw, groups=cfg.norm_num_groups))
         h1 = P.alloc((Be * h * w, cout), F32)
         add(ops.conv3x3(a1, wt[p + ".w1"], Be, h, w, bias=wt[p + ".b1"], out_f32=h1, name="res.conv1"))
         P.release(a1)
-        a2 = P.alloc((Be * (h + 2) * (w + 2), cout), BF16)
+        a2 = P.alloc((Be * (h + 2) * (w + 2), cout), ops.h16())
         add(ops.group_norm(h1, Be, h, w, wt[p + ".n2g"], wt[p + ".n2b"], a2, eps=cfg.norm_eps, silu=True, pad_out=True,
                            partial=self.gn_partial, groups=cfg.norm_num_groups))
         P.release(h1)
@@ -312,14 +312,14 @@ class UNetPlan:
         N = h * w
         M = Be * N
         rpg = self.images * N                      # rows per task group
-        xn = P.alloc((M, C), BF16)
+        xn = P.alloc((M, C), ops.h16())
         add(ops.group_norm(x, Be, h, w, wt[p + ".ng"], wt[p + ".nb"], xn, eps=1e-6, silu=False, pad_out=False,
                            partial=self.gn_partial, groups=cfg.norm_num_groups))
         hs = P.alloc((M, C), F32)
         add(ops.gemm(xn, wt[p + ".proj_in.w"], bias=wt[p + ".proj_in.b"], out_f32=hs, name="proj_in"))
         n1 = xn                                    # reuse as LN output
         add(ops.layer_norm(hs, wt[p + ".ln1g"], wt[p + ".ln1b"], n1))
-        qkv = P.alloc((M, 3 * C), BF16)
+        qkv = P.alloc((M, 3 * C), ops.h16())
         add(ops.gemm(n1, wt[p + ".qkv"], out_bf16=qkv, name="qkv"))
         att = n1
         add(ops.flash_attn(qkv, Be, N, heads, att, 0, C, 2 * C))
@@ -327,7 +327,7 @@ class UNetPlan:
         if self.mode != "main":
             feat = None
             if self.mode == "child":
-                feat = torch.empty(M, C, device=W.device, dtype=BF16)      # owned by the plan, read by the main pass
+                feat = torch.empty(M, C, device=W.device, dtype=ops.h16())      # owned by the plan, read by the main pass
                 self.feats_out.append(feat)
             # h += to_out(attn); the pre-residual value is the "afterSelfAttn_residual" tap (attention.py:348-349)
             add(ops.gemm(att, wt[p + ".o.w"], bias=wt[p + ".o.b"], res1=hs, out_f32=hs, aux_bf16=feat, name="attn_out"))
@@ -342,8 +342,8 @@ class UNetPlan:
             bq = torch.stack([tw[p + ".tnq.b"][t] for t in self.group_tasks]).contiguous()
             add(ops.layer_norm(attn_out, gq, bq, qn, rows_per_group=rpg))
             hq = cfg.task_q_hidden
-            q1, q2 = P.alloc((M, hq), BF16), P.alloc((M, hq), BF16)
-            tq = P.alloc((M, C), BF16)
+            q1, q2 = P.alloc((M, hq), ops.h16()), P.alloc((M, hq), ops.h16())
+            tq = P.alloc((M, C), ops.h16())
             for gi, t in enumerate(self.group_tasks):
                 r = slice(gi * rpg, (gi + 1) * rpg)
                 add(ops.gemm(qn[r], tw[p + ".tq0.w"][t], bias=tw[p + ".tq0.b"][t], act=L.ACT_GELU, out_bf16=q1[r], name="task_q0"))
@@ -356,14 +356,14 @@ class UNetPlan:
             S = len(self.src_tasks)
             Ms = S * rpg
             assert F_l.shape == (Ms, C), (F_l.shape, Ms, C)
-            kn, vn = P.alloc((Ms, C), BF16), P.alloc((Ms, C), BF16)
+            kn, vn = P.alloc((Ms, C), ops.h16()), P.alloc((Ms, C), ops.h16())
             gk = torch.stack([tw[p + ".tnk.g"][t] for t in self.src_tasks]).contiguous()
             bk = torch.stack([tw[p + ".tnk.b"][t] for t in self.src_tasks]).contiguous()
             gv = torch.stack([tw[p + ".tnv.g"][t] for t in self.src_tasks]).contiguous()
             bv = torch.stack([tw[p + ".tnv.b"][t] for t in self.src_tasks]).contiguous()
             add(ops.layer_norm(F_l, gk, bk, kn, gamma1=gv, beta1=bv, out1=vn, rows_per_group=rpg))
-            hk, hv = P.alloc((Ms, C // 2), BF16), P.alloc((Ms, C // 2), BF16)
-            K, V = P.alloc((Ms, C), BF16), P.alloc((Ms, C), BF16)
+            hk, hv = P.alloc((Ms, C // 2), ops.h16()), P.alloc((Ms, C // 2), ops.h16())
+            K, V = P.alloc((Ms, C), ops.h16()), P.alloc((Ms, C), ops.h16())
             for si, t in enumerate(self.src_tasks):
                 r = slice(si * rpg, (si + 1) * rpg)
                 add(ops.gemm(kn[r], tw[p + ".tk1.w"][t], bias=tw[p + ".tk1.b"][t], act=L.ACT_GELU, out_bf16=hk[r], name="task_k1"))
@@ -381,7 +381,7 @@ class UNetPlan:
         # ---- cross-attention on the task-name tokens (attention.py:355-364)
         n2 = att
         add(ops.layer_norm(hs, wt[p + ".ln2g"], wt[p + ".ln2b"], n2))
-        q2b = P.alloc((M, C), BF16)
+        q2b = P.alloc((M, C), ops.h16())
         add(ops.gemm(n2, wt[p + ".q2"], out_bf16=q2b, name="xattn_q"))
         xa = n2
         add(ops.xattn(q2b, wt[p + ".kc"], wt[p + ".vc"], W.ntok, self.group_tasks, rpg, heads, xa))
@@ -390,7 +390,7 @@ class UNetPlan:
         # ---- GEGLU feed-forward (attention.py:372-373)
         n3 = xa
         add(ops.layer_norm(hs, wt[p + ".ln3g"], wt[p + ".ln3b"], n3))
-        gg = P.alloc((M, 4 * C), BF16)
+        gg = P.alloc((M, 4 * C), ops.h16())
         add(ops.gemm(n3, wt[p + ".ff1.w"], bias=wt[p + ".ff1.b"], act=L.ACT_GEGLU, out_bf16=gg, name="ff1_geglu"))
         hb = n3
         add(ops.gemm(gg, wt[p + ".ff2.w"], bias=wt[p + ".ff2.b"], res1=hs, out_bf16=hb, name="ff2"))
@@ -414,12 +414,12 @@ class VAEWeights:
         # encoder stem (3 -> c0), K = 27 padded to 64
         wm = torch.zeros(cfg.block_out_channels[0], 64, device=device)
         wm[:, :27] = conv_weight_matrix(g("encoder.conv_in.weight"))
-        w["enc.conv_in.w"], w["enc.conv_in.b"] = wm.to(BF16), g("encoder.conv_in.bias")
+        w["enc.conv_in.w"], w["enc.conv_in.b"] = wm.to(ops.h16()), g("encoder.conv_in.bias")
         # encoder head: conv_out (3x3, C -> 2L) then quant_conv (1x1) then mean half * 0.18215, folded into one conv C -> L
         lat = cfg.latent_channels
         wq = g("quant_conv.weight").reshape(2 * lat, 2 * lat)[:lat]                # [L, 2L]
         wco = conv_weight_matrix(g("encoder.conv_out.weight"))                     # [2L, 9C]
-        w["enc.head.w"] = (LATENT_SCALE * (wq @ wco)).to(BF16).contiguous()
+        w["enc.head.w"] = (LATENT_SCALE * (wq @ wco)).to(ops.h16()).contiguous()
         w["enc.head.b"] = (LATENT_SCALE * (wq @ g("encoder.conv_out.bias") + g("quant_conv.bias")[:lat])).contiguous()
         # decoder stem: latent / 0.18215 -> post_quant_conv (1x1) as a channel mix, then conv_in (L -> C), K = 36 -> 64
         w["dec.pq.w"] = (g("post_quant_conv.weight").reshape(lat, lat) / LATENT_SCALE).contiguous()
@@ -427,8 +427,8 @@ class VAEWeights:
         cd = cfg.block_out_channels[-1]
         wm = torch.zeros(cd, 64, device=device)
         wm[:, : 9 * lat] = conv_weight_matrix(g("decoder.conv_in.weight"))
-        w["dec.conv_in.w"], w["dec.conv_in.b"] = wm.to(BF16), g("decoder.conv_in.bias")
-        w["dec.head.w"] = conv_weight_matrix(g("decoder.conv_out.weight")).to(BF16)
+        w["dec.conv_in.w"], w["dec.conv_in.b"] = wm.to(ops.h16()), g("decoder.conv_in.bias")
+        w["dec.head.w"] = conv_weight_matrix(g("decoder.conv_out.weight")).to(ops.h16())
         w["dec.head.b"] = g("decoder.conv_out.bias")
         for s in ("encoder", "decoder"):
             w[f"{s}.ng"], w[f"{s}.nb"] = g(f"{s}.conv_norm_out.weight"), g(f"{s}.conv_norm_out.bias")
@@ -438,19 +438,19 @@ class VAEWeights:
             g, w = self._g, self.w
             w[p + ".n1g"], w[p + ".n1b"] = g(p + ".norm1.weight"), g(p + ".norm1.bias")
             w[p + ".n2g"], w[p + ".n2b"] = g(p + ".norm2.weight"), g(p + ".norm2.bias")
-            w[p + ".w1"], w[p + ".b1"] = conv_weight_matrix(g(p + ".conv1.weight")).to(BF16), g(p + ".conv1.bias")
+            w[p + ".w1"], w[p + ".b1"] = conv_weight_matrix(g(p + ".conv1.weight")).to(ops.h16()), g(p + ".conv1.bias")
             w2, b2 = conv_weight_matrix(g(p + ".conv2.weight")), g(p + ".conv2.bias")
             if (p + ".conv_shortcut.weight") in self._sd:
                 ws = g(p + ".conv_shortcut.weight")
                 w2 = torch.cat([w2, ws.reshape(ws.shape[0], ws.shape[1])], dim=1)
                 b2 = b2 + g(p + ".conv_shortcut.bias")
                 w[p + ".short"] = True
-            w[p + ".w2"], w[p + ".b2"] = w2.to(BF16).contiguous(), b2.contiguous()
+            w[p + ".w2"], w[p + ".b2"] = w2.to(ops.h16()).contiguous(), b2.contiguous()
         return self.w
 
     def conv(self, p):
         if p + ".w" not in self.w:
-            self.w[p + ".w"] = conv_weight_matrix(self._g(p + ".weight")).to(BF16)
+            self.w[p + ".w"] = conv_weight_matrix(self._g(p + ".weight")).to(ops.h16())
             self.w[p + ".b"] = self._g(p + ".bias")
         return self.w[p + ".w"], self.w[p + ".b"]
 
@@ -458,10 +458,10 @@ class VAEWeights:
         if p + ".qk.w" not in self.w:
             g, w = self._g, self.w
             w[p + ".ng"], w[p + ".nb"] = g(p + ".group_norm.weight"), g(p + ".group_norm.bias")
-            w[p + ".qk.w"] = torch.cat([g(p + ".to_q.weight"), g(p + ".to_k.weight")]).to(BF16).contiguous()
+            w[p + ".qk.w"] = torch.cat([g(p + ".to_q.weight"), g(p + ".to_k.weight")]).to(ops.h16()).contiguous()
             w[p + ".qk.b"] = torch.cat([g(p + ".to_q.bias"), g(p + ".to_k.bias")]).contiguous()
-            w[p + ".v.w"], w[p + ".v.b"] = g(p + ".to_v.weight").to(BF16), g(p + ".to_v.bias")
-            w[p + ".o.w"], w[p + ".o.b"] = g(p + ".to_out.0.weight").to(BF16), g(p + ".to_out.0.bias")
+            w[p + ".v.w"], w[p + ".v.b"] = g(p + ".to_v.weight").to(ops.h16()), g(p + ".to_v.bias")
+            w[p + ".o.w"], w[p + ".o.b"] = g(p + ".to_out.0.weight").to(ops.h16()), g(p + ".to_out.0.bias")
         return self.w
 
 
@@ -471,14 +471,14 @@ class _VAEBase:
         wt = W.resnet(p)
         cin = x.shape[1]
         short = wt.get(p + ".short", False)
-        a1 = P.alloc((B * (h + 2) * (w + 2), cin), BF16)
-        raw = P.alloc((B * (h + 2) * (w + 2), cin), BF16) if short else None
+        a1 = P.alloc((B * (h + 2) * (w + 2), cin), ops.h16())
+        raw = P.alloc((B * (h + 2) * (w + 2), cin), ops.h16()) if short else None
         add(ops.group_norm(x, B, h, w, wt[p + ".n1g"], wt[p + ".n1b"], a1, eps=1e-6, silu=True, pad_out=True,
                            partial=self.gn_partial, raw=raw, groups=G))
         h1 = P.alloc((B * h * w, cout), F32)
         add(ops.conv3x3(a1, wt[p + ".w1"], B, h, w, bias=wt[p + ".b1"], out_f32=h1, name="vae.conv1"))
         P.release(a1)
-        a2 = P.alloc((B * (h + 2) * (w + 2), cout), BF16)
+        a2 = P.alloc((B * (h + 2) * (w + 2), cout), ops.h16())
         add(ops.group_norm(h1, B, h, w, wt[p + ".n2g"], wt[p + ".n2b"], a2, eps=1e-6, silu=True, pad_out=True,
                            partial=self.gn_partial, groups=G))
         P.release(h1)
@@ -496,15 +496,15 @@ class _VAEBase:
         N = h * w
         M = B * N
         Np = (N + 7) // 8 * 8
-        xn = P.alloc((M, C), BF16)
+        xn = P.alloc((M, C), ops.h16())
         add(ops.group_norm(x, B, h, w, wt[p + ".ng"], wt[p + ".nb"], xn, eps=1e-6, silu=False, pad_out=False,
                            partial=self.gn_partial, groups=G))
-        qk = P.alloc((M, 2 * C), BF16)
+        qk = P.alloc((M, 2 * C), ops.h16())
         add(ops.gemm(xn, wt[p + ".qk.w"], bias=wt[p + ".qk.b"], out_bf16=qk, name="vae.qk"))
-        o = P.alloc((M, C), BF16)
-        vT = P.alloc((C, Np), BF16)
+        o = P.alloc((M, C), ops.h16())
+        vT = P.alloc((C, Np), ops.h16())
         S = P.alloc((N, Np), F32)
-        Pm = P.alloc((N, Np), BF16)
+        Pm = P.alloc((N, Np), ops.h16())
         for b in range(B):
             r = slice(b * N, (b + 1) * N)
             add(ops.gemm(wt[p + ".v.w"], xn[r], bias=wt[p + ".v.b"], bias_per_row=True, out_bf16=vT[:, :N], name="vae.vT"))
@@ -534,7 +534,7 @@ class _VAEBase:
 class VAEEncodePlan(_VAEBase):
     """encode_rgb (stablemtl_pipeline.py:607-624): rgb [B,3,H,W] in [0,255] -> latent mean * 0.18215, fp32 [B*h*w, 4]."""
 
-    def __init__(self, W: VAEWeights, B, H, Wd, pool=None, rgb=None):
+    def __init__(self, W: VAEWeights, B, H, Wd, pool=None, rgb=None, rgb_dtype=F32):
         self.W, self.B = W, B
         dev = W.device
         self.pool = P = pool or Pool(dev)
@@ -543,10 +543,10 @@ class VAEEncodePlan(_VAEBase):
         cfg = W.cfg
         c = cfg.block_out_channels
         self.gn_partial = torch.empty(B * 64 * 32 * 2, device=dev, dtype=F32)
-        self.rgb = rgb if rgb is not None else torch.zeros(B, 3, H, Wd, device=dev, dtype=F32)
+        self.rgb = rgb if rgb is not None else torch.zeros(B, 3, H, Wd, device=dev, dtype=rgb_dtype)
         xin = P.alloc((B * H * Wd, 3), F32)
         add(ops.rgb_prep(self.rgb, xin))
-        col = P.alloc((B * H * Wd, 64), BF16)
+        col = P.alloc((B * H * Wd, 64), ops.h16())
         add(ops.im2col(xin.view(B, H, Wd, 3), B, H, Wd, col, stride=1, pad_t=1, pad_l=1, oh=H, ow=Wd))
         P.release(xin)
         x = P.alloc((B * H * Wd, c[0]), F32)
@@ -562,14 +562,14 @@ class VAEEncodePlan(_VAEBase):
                 # diffusers Downsample2D: F.pad(x, (0,1,0,1)) then 3x3 stride 2 pad 0
                 h2, w2 = (h + 1 - 3) // 2 + 1, (w + 1 - 3) // 2 + 1
                 wt, bs = W.conv(f"encoder.down_blocks.{i}.downsamplers.0.conv")
-                col = P.alloc((B * h2 * w2, 9 * c[i]), BF16)
+                col = P.alloc((B * h2 * w2, 9 * c[i]), ops.h16())
                 add(ops.im2col(x.view(B, h, w, c[i]), B, h, w, col, stride=2, pad_t=0, pad_l=0, oh=h2, ow=w2))
                 y = P.alloc((B * h2 * w2, c[i]), F32)
                 add(ops.gemm(col, wt, bias=bs, out_f32=y, name="vae.enc.down"))
                 P.release(col, x)
                 x, h, w = y, h2, w2
         x = self._mid("encoder.mid_block", x, h, w, c[-1])
-        a = P.alloc((B * (h + 2) * (w + 2), c[-1]), BF16)
+        a = P.alloc((B * (h + 2) * (w + 2), c[-1]), ops.h16())
         add(ops.group_norm(x, B, h, w, W.w["encoder.ng"], W.w["encoder.nb"], a, eps=1e-6, silu=True, pad_out=True,
                            partial=self.gn_partial, groups=cfg.norm_num_groups))
         self.out = torch.empty(B * h * w, cfg.latent_channels, device=dev, dtype=F32)
@@ -596,7 +596,7 @@ class VAEDecodePlan(_VAEBase):
         self.gn_partial = torch.empty(B * 64 * 32 * 2, device=dev, dtype=F32)
         z = P.alloc((B * h * w, lat), F32)
         add(ops.chan_mix(self.latent, W.w["dec.pq.w"], W.w["dec.pq.b"], z))
-        col = P.alloc((B * h * w, 64), BF16)
+        col = P.alloc((B * h * w, 64), ops.h16())
         add(ops.im2col(z.view(B, h, w, lat), B, h, w, col, stride=1, pad_t=1, pad_l=1, oh=h, ow=w))
         P.release(z)
         x = P.alloc((B * h * w, c[0]), F32)
@@ -610,14 +610,14 @@ class VAEDecodePlan(_VAEBase):
                 x = y
             if i < len(c) - 1:
                 wt, bs = W.conv(f"decoder.up_blocks.{i}.upsamplers.0.conv")
-                up = P.alloc((B * (2 * h + 2) * (2 * w + 2), c[i]), BF16)
+                up = P.alloc((B * (2 * h + 2) * (2 * w + 2), c[i]), ops.h16())
                 add(ops.upsample_pad(x.view(B, h, w, c[i]), B, h, w, 2 * h, 2 * w, up))
                 P.release(x)
                 h, w = 2 * h, 2 * w
                 x = P.alloc((B * h * w, c[i]), F32)
                 add(ops.conv3x3(up, wt, B, h, w, bias=bs, out_f32=x, name="vae.dec.up"))
                 P.release(up)
-        a = P.alloc((B * (h + 2) * (w + 2), c[-1]), BF16)
+        a = P.alloc((B * (h + 2) * (w + 2), c[-1]), ops.h16())
         add(ops.group_norm(x, B, h, w, W.w["decoder.ng"], W.w["decoder.nb"], a, eps=1e-6, silu=True, pad_out=True,
                            partial=self.gn_partial, groups=cfg.norm_num_groups))
         P.release(x)

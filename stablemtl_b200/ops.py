@@ -10,8 +10,40 @@ import torch
 
 from . import _lib as L
 
-BF16 = torch.bfloat16
 F32 = torch.float32
+
+# 16-bit operand format of every op built from here on.  fp16 (saturating, fp32 accumulate) is the default: it is what
+# keeps the end-to-end maps within 1e-2 relative L2 of the fp32 oracle; bf16 runs at the same tensor rate with
+# ~8x the rounding error (see DESIGN.md "Numerics").
+PREC = {"fmt": L.FMT_F16, "dtype": torch.float16, "name": "fp16"}
+
+
+def set_precision(name):
+    if name == "fp16":
+        PREC.update(fmt=L.FMT_F16, dtype=torch.float16, name="fp16")
+    elif name == "bf16":
+        PREC.update(fmt=L.FMT_BF16, dtype=torch.bfloat16, name="bf16")
+    else:
+        raise ValueError(f"unknown precision {name!r}")
+
+
+def h16():
+    return PREC["dtype"]
+
+
+class _H16:
+    """compares equal to the active 16-bit dtype (so `t.dtype == BF16` follows set_precision)."""
+
+    def __eq__(self, other):
+        return other == PREC["dtype"]
+
+    def __ne__(self, other):
+        return other != PREC["dtype"]
+
+    __hash__ = None
+
+
+BF16 = _H16()
 
 
 def _ptr(t):
@@ -91,6 +123,7 @@ def gemm(a0, b, *, m=None, k=None, n=None, a1=None, segs=None, bias=None, bias_p
     segs: list of (row_shift, kblocks, src, a_col0)."""
     assert a0.dtype == BF16 and b.dtype == BF16 and a0.stride(-1) == 1 and b.stride(-1) == 1
     g = L.GemmArgs()
+    g.fmt16 = PREC["fmt"]
     g.a0, g.a0_rows, g.a0_cols, g.a0_ld = a0.data_ptr(), a0.shape[0], a0.shape[1], a0.stride(0)
     if a1 is not None:
         assert a1.dtype == BF16 and a1.stride(-1) == 1
@@ -162,6 +195,7 @@ def conv3x3(a_pad, wmat, batch, h, w, *, a_short=None, name="conv3x3", **epi):
 # ------------------------------------------------------------------------------------------------- attention
 def flash_attn(qkv, batch, ntok, heads, out, q_col0, k_col0, v_col0, scale=0.125):
     a = L.FattnArgs()
+    a.fmt16 = PREC["fmt"]
     a.qkv, a.ld = qkv.data_ptr(), qkv.stride(0)
     a.q_col0, a.k_col0, a.v_col0 = q_col0, k_col0, v_col0
     a.batch, a.ntok, a.heads = batch, ntok, heads
@@ -174,6 +208,7 @@ def flash_attn(qkv, batch, ntok, heads, out, q_col0, k_col0, v_col0, scale=0.125
 
 def softmax_rows(s, p, scale):
     a = L.SoftmaxArgs()
+    a.fmt16 = PREC["fmt"]
     a.s, a.rows, a.n, a.lds, a.scale = s.data_ptr(), s.shape[0], s.shape[1], s.stride(0), scale
     a.p_bf16, a.ldp = p.data_ptr(), p.stride(0)
     assert s.dtype == F32 and p.dtype == BF16
@@ -182,6 +217,7 @@ def softmax_rows(s, p, scale):
 
 def xattn(q, kc, vc, ntok, task_of_group, rows_per_group, heads, out, scale=0.125):
     a = L.XattnArgs()
+    a.fmt16 = PREC["fmt"]
     a.q_bf16, a.ldq, a.rows, a.heads = q.data_ptr(), q.stride(0), q.shape[0], heads
     a.kc, a.vc = kc.data_ptr(), vc.data_ptr()
     assert kc.dtype == F32 and vc.dtype == F32 and kc.shape[1] == 4 and kc.shape[2] == heads * 64
@@ -195,6 +231,7 @@ def xattn(q, kc, vc, ntok, task_of_group, rows_per_group, heads, out, scale=0.12
 
 def task_attn(q, k, v, out, c, nheads, main_tasks, src_tasks, rows_per_group, exclude_self=True):
     a = L.TaskAttnArgs()
+    a.fmt16 = PREC["fmt"]
     a.q_bf16, a.k_bf16, a.v_bf16, a.out_bf16 = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
     a.c, a.nheads, a.n_main, a.n_src = c, nheads, len(main_tasks), len(src_tasks)
     a.rows_per_group = rows_per_group
@@ -216,6 +253,7 @@ def gn_nchunk(hw):
 
 def group_norm(x0, batch, h, w, gamma, beta, out, *, x1=None, eps, silu, pad_out, partial, raw=None, groups=32):
     a = L.GnArgs()
+    a.fmt16 = PREC["fmt"]
     a.x0, a.c0 = x0.data_ptr(), x0.shape[-1]
     if x1 is not None:
         a.x1, a.c1 = x1.data_ptr(), x1.shape[-1]
@@ -232,7 +270,8 @@ def group_norm(x0, batch, h, w, gamma, beta, out, *, x1=None, eps, silu, pad_out
 
 def layer_norm(x, gamma0, beta0, out0, *, gamma1=None, beta1=None, out1=None, rows_per_group=None, eps=1e-5):
     a = L.LnArgs()
-    a.x, a.x_is_bf16, a.c, a.ldx = x.data_ptr(), int(x.dtype == BF16), x.shape[1], x.stride(0)
+    a.fmt16 = PREC["fmt"]
+    a.x, a.x_is_bf16, a.c, a.ldx = x.data_ptr(), int(x.dtype != F32), x.shape[1], x.stride(0)
     a.rows, a.eps = x.shape[0], eps
     a.rows_per_group = x.shape[0] if rows_per_group is None else rows_per_group
     a.gamma0, a.beta0, a.out0 = gamma0.data_ptr(), beta0.data_ptr(), out0.data_ptr()
@@ -245,6 +284,7 @@ def layer_norm(x, gamma0, beta0, out0, *, gamma1=None, beta1=None, out1=None, ro
 # ------------------------------------------------------------------------------------------------- data movement
 def upsample_pad(x, batch, h, w, oh, ow, out):
     a = L.UpsampleArgs()
+    a.fmt16 = PREC["fmt"]
     a.x, a.batch, a.h, a.w, a.c, a.oh, a.ow, a.out_bf16 = x.data_ptr(), batch, h, w, x.shape[-1], oh, ow, out.data_ptr()
     assert x.dtype == F32 and out.dtype == BF16
     return Op(L.OP_UPSAMPLE, a, (x, out), 0, "upsample")
@@ -252,6 +292,7 @@ def upsample_pad(x, batch, h, w, oh, ow, out):
 
 def im2col(x, batch, h, w, out, *, stride, pad_t, pad_l, oh, ow):
     a = L.Im2colArgs()
+    a.fmt16 = PREC["fmt"]
     a.x, a.batch, a.h, a.w, a.c = x.data_ptr(), batch, h, w, x.shape[-1]
     a.stride, a.pad_t, a.pad_l, a.oh, a.ow, a.kpad = stride, pad_t, pad_l, oh, ow, out.shape[-1]
     a.out_bf16 = out.data_ptr()
@@ -263,7 +304,8 @@ def rgb_prep(rgb_nchw, out_nhwc):
     a = L.RgbprepArgs()
     b, _, h, w = rgb_nchw.shape
     a.rgb_nchw, a.batch, a.h, a.w, a.out_nhwc = rgb_nchw.data_ptr(), b, h, w, out_nhwc.data_ptr()
-    assert rgb_nchw.dtype == F32 and rgb_nchw.is_contiguous() and out_nhwc.dtype == F32
+    a.src_u8 = int(rgb_nchw.dtype == torch.uint8)
+    assert rgb_nchw.dtype in (F32, torch.uint8) and rgb_nchw.is_contiguous() and out_nhwc.dtype == F32
     return Op(L.OP_RGBPREP, a, (rgb_nchw, out_nhwc), 0, "rgb_prep")
 
 

@@ -15,7 +15,7 @@ import torch
 
 from . import _lib as L
 from . import ops
-from .engine import BF16, F32, Pool, UNetPlan, UNetWeights, VAEDecodePlan, VAEEncodePlan, VAEWeights
+from .engine import F32, Pool, UNetPlan, UNetWeights, VAEDecodePlan, VAEEncodePlan, VAEWeights
 from .synth import FLOW_TASKS, TASKS, UNetConfig, VAEConfig
 
 # VKitti2Encoder(n_classes=8).class_color_embeddings (src/dataset/semantic/encoding.py:10-35,92-96; labels.py:42-55)
@@ -46,12 +46,12 @@ class StableMTLEngine:
         self._plans = {}
 
     # ------------------------------------------------------------------------------------------ plan construction
-    def _build(self, B, H, W, with_next):
+    def _build(self, B, H, W, with_next, rgb_dtype=F32):
         dev = self.device
         pool = Pool(dev)
         T = len(self.tasks)
         n_enc = 2 * B if with_next else B
-        enc = VAEEncodePlan(self.vae_w, n_enc, H, W, pool=pool)
+        enc = VAEEncodePlan(self.vae_w, n_enc, H, W, pool=pool, rgb_dtype=rgb_dtype)
         h, w = enc.h, enc.w
         hw = h * w
         first = torch.arange(B, dtype=torch.int32).repeat(T)
@@ -110,10 +110,10 @@ class StableMTLEngine:
         return dict(enc=enc, assemble=assemble, unets=unets, lat=lat, dec=dec, bd=bd, chunks=chunks, out=out, hw=hw,
                     pool=pool, launches=launches, flops=flops, h=h, w=w)
 
-    def plan_for(self, B, H, W, with_next=True):
-        key = (B, H, W, with_next)
+    def plan_for(self, B, H, W, with_next=True, rgb_dtype=F32):
+        key = (B, H, W, with_next, rgb_dtype)
         if key not in self._plans:
-            self._plans[key] = self._build(B, H, W, with_next)
+            self._plans[key] = self._build(B, H, W, with_next, rgb_dtype)
         return self._plans[key]
 
     # ------------------------------------------------------------------------------------------ execution
@@ -123,11 +123,12 @@ class StableMTLEngine:
         post-processing (stablemtl_pipeline.py:297-366): depth/shading/albedo in [0,1], unit normals, flows in
         [-1,1], semantic class ids (int64 [B,H,W]).  `.last` keeps the clipped single_infer() tensors."""
         B, _, H, W = rgb.shape
-        p = self.plan_for(B, H, W, rgb_next is not None)
+        dt = torch.uint8 if rgb.dtype == torch.uint8 else F32        # uint8 images are converted inside the kernel
+        p = self.plan_for(B, H, W, rgb_next is not None, dt)
         enc = p["enc"]
-        enc.rgb[:B].copy_(rgb.to(F32), non_blocking=True)
+        enc.rgb[:B].copy_(rgb, non_blocking=True)                     # H2D (or D2D) copy; dtype cast only if needed
         if rgb_next is not None:
-            enc.rgb[B:].copy_(rgb_next.to(F32), non_blocking=True)
+            enc.rgb[B:].copy_(rgb_next, non_blocking=True)
         enc.run()
         p["assemble"].run()
         for u in p["unets"]:

@@ -17,6 +17,20 @@ def _ops():
     return ops, _lib
 
 
+def H16():
+    from stablemtl_b200 import ops
+    return ops.h16()
+
+
+@pytest.fixture(autouse=True, params=["fp16", "bf16"])
+def precision(request):
+    """every kernel test runs in both 16-bit operand formats"""
+    from stablemtl_b200 import ops
+    ops.set_precision(request.param)
+    yield request.param
+    ops.set_precision("fp16")
+
+
 def rel_l2(a, b):
     a, b = a.double(), b.double()
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
@@ -35,14 +49,14 @@ def rnd(*shape, scale=1.0, seed=0):
 def test_gemm_plain(m, n, k, bn):
     ops, L = _ops()
     kp = (k + 7) // 8 * 8
-    a = rnd(m, kp, seed=1).bfloat16()[:, :k] if kp != k else rnd(m, k, seed=1).bfloat16()
-    b = rnd(n, kp, scale=k ** -0.5, seed=2).bfloat16()
+    a = rnd(m, kp, seed=1).to(H16())[:, :k] if kp != k else rnd(m, k, seed=1).to(H16())
+    b = rnd(n, kp, scale=k ** -0.5, seed=2).to(H16())
     if kp != k:
         b = b[:, :k]
     bias = rnd(n, seed=3)
     res = rnd(m, n, seed=4)
     out = torch.full((m, n), float("nan"), device=DEV)
-    outb = torch.empty(m, n, device=DEV, dtype=torch.bfloat16) if n % 8 == 0 else None
+    outb = torch.empty(m, n, device=DEV, dtype=H16()) if n % 8 == 0 else None
     ops.gemm(a, b, bias=bias, res1=res, out_f32=out, out_bf16=outb, block_n=bn).run()
     torch.cuda.synchronize()
     ref = a.float() @ b.float().t() + bias + res
@@ -55,10 +69,10 @@ def test_gemm_plain(m, n, k, bn):
 def test_gemm_gelu_aux_two_res():
     ops, L = _ops()
     m, n, k = 700, 640, 640
-    a, b = rnd(m, k, seed=1).bfloat16(), rnd(n, k, scale=k ** -0.5, seed=2).bfloat16()
+    a, b = rnd(m, k, seed=1).to(H16()), rnd(n, k, scale=k ** -0.5, seed=2).to(H16())
     bias, r1, r2 = rnd(n, seed=3), rnd(m, n, seed=4), rnd(m, n, seed=5)
     out = torch.empty(m, n, device=DEV)
-    aux = torch.empty(m, n, device=DEV, dtype=torch.bfloat16)
+    aux = torch.empty(m, n, device=DEV, dtype=H16())
     ops.gemm(a, b, bias=bias, act=L.ACT_GELU, res1=r1, res2=r2, out_f32=out, aux_bf16=aux).run()
     torch.cuda.synchronize()
     pre = F.gelu(a.float() @ b.float().t() + bias)
@@ -70,11 +84,11 @@ def test_gemm_geglu():
     ops, L = _ops()
     from stablemtl_b200.weights import interleave_geglu
     m, c = 600, 320
-    a = rnd(m, c, seed=1).bfloat16()
-    w = rnd(8 * c, c, scale=c ** -0.5, seed=2).bfloat16()
+    a = rnd(m, c, seed=1).to(H16())
+    w = rnd(8 * c, c, scale=c ** -0.5, seed=2).to(H16())
     bias = rnd(8 * c, seed=3)
     wi, bi = interleave_geglu(w, bias)
-    out = torch.empty(m, 4 * c, device=DEV, dtype=torch.bfloat16)
+    out = torch.empty(m, 4 * c, device=DEV, dtype=H16())
     ops.gemm(a, wi, bias=bi, act=L.ACT_GEGLU, out_bf16=out).run()
     torch.cuda.synchronize()
     h = a.float() @ w.float().t() + bias
@@ -85,9 +99,9 @@ def test_gemm_geglu():
 def test_gemm_bias_per_row_swapped():
     ops, L = _ops()
     m, n, k = 512, 300, 512      # D^T = W X^T : rows are output channels
-    w, x = rnd(m, k, scale=k ** -0.5, seed=1).bfloat16(), rnd(n, k, seed=2).bfloat16()
+    w, x = rnd(m, k, scale=k ** -0.5, seed=1).to(H16()), rnd(n, k, seed=2).to(H16())
     bias = rnd(m, seed=3)
-    out = torch.empty(m, 304, device=DEV, dtype=torch.bfloat16)
+    out = torch.empty(m, 304, device=DEV, dtype=H16())
     ops.gemm(w, x, bias=bias, bias_per_row=True, out_bf16=out[:, :300]).run()
     torch.cuda.synchronize()
     ref = w.float() @ x.float().t() + bias[:, None]
@@ -105,16 +119,16 @@ def _pad_layout(x_nhwc):
                                                (1, 60, 80, 128, 4, 0), (2, 6, 20, 1280, 1280, 0)])
 def test_conv3x3_implicit_gemm(b, h, w, cin, cout, cs):
     ops, L = _ops()
-    x = rnd(b, h, w, cin, seed=1).bfloat16()
-    wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=2).bfloat16()
+    x = rnd(b, h, w, cin, seed=1).to(H16())
+    wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=2).to(H16())
     bias = rnd(cout, seed=3)
     res = rnd(b * h * w, cout, seed=4)
     wmat = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1)
     xs = None
     if cs:
-        xs_nhwc = rnd(b, h, w, cs, seed=5).bfloat16()
-        ws = rnd(cout, cs, scale=cs ** -0.5, seed=6).bfloat16()
+        xs_nhwc = rnd(b, h, w, cs, seed=5).to(H16())
+        ws = rnd(cout, cs, scale=cs ** -0.5, seed=6).to(H16())
         wmat = torch.cat([wmat, ws], dim=1)
         ref = ref + F.conv2d(xs_nhwc.float().permute(0, 3, 1, 2), ws.float()[:, :, None, None])
         xs = _pad_layout(xs_nhwc)
@@ -131,8 +145,8 @@ def test_conv3x3_implicit_gemm(b, h, w, cin, cout, cs):
 def test_flash_attention(batch, ntok, heads):
     ops, L = _ops()
     c = heads * 64
-    qkv = rnd(batch * ntok, 3 * c, seed=1).bfloat16()
-    out = torch.zeros(batch * ntok, c, device=DEV, dtype=torch.bfloat16)
+    qkv = rnd(batch * ntok, 3 * c, seed=1).to(H16())
+    out = torch.zeros(batch * ntok, c, device=DEV, dtype=H16())
     ops.flash_attn(qkv, batch, ntok, heads, out, 0, c, 2 * c).run()
     torch.cuda.synchronize()
     q, k, v = [t.float().reshape(batch, ntok, heads, 64).permute(0, 2, 1, 3) for t in qkv.split(c, dim=1)]
@@ -152,8 +166,8 @@ def test_group_norm(b, h, w, c0, c1, silu, pad):
     C = c0 + c1
     gamma, beta = rnd(C, seed=3) + 1, rnd(C, seed=4)
     hp, wp = (h + 2, w + 2) if pad else (h, w)
-    out = torch.full((b * hp * wp, C), float("nan"), device=DEV, dtype=torch.bfloat16)
-    raw = torch.full((b * hp * wp, C), float("nan"), device=DEV, dtype=torch.bfloat16)
+    out = torch.full((b * hp * wp, C), float("nan"), device=DEV, dtype=H16())
+    raw = torch.full((b * hp * wp, C), float("nan"), device=DEV, dtype=H16())
     partial = torch.empty(b * 64 * 32 * 2, device=DEV)
     ops.group_norm(x0, b, h, w, gamma, beta, out, x1=x1, eps=1e-5, silu=silu, pad_out=pad, partial=partial, raw=raw).run()
     torch.cuda.synchronize()
@@ -179,12 +193,12 @@ def test_layer_norm(rows, c, bf16_in):
     ops, L = _ops()
     x = rnd(rows, c, seed=1) * 3 + 1
     if bf16_in:
-        x = x.bfloat16()
+        x = x.to(H16())
     ng = 2
     rpg = (rows + 1) // 2
     g0, b0, g1, b1 = rnd(ng, c, seed=2) + 1, rnd(ng, c, seed=3), rnd(ng, c, seed=4) + 1, rnd(ng, c, seed=5)
-    o0 = torch.empty(rows, c, device=DEV, dtype=torch.bfloat16)
-    o1 = torch.empty(rows, c, device=DEV, dtype=torch.bfloat16)
+    o0 = torch.empty(rows, c, device=DEV, dtype=H16())
+    o1 = torch.empty(rows, c, device=DEV, dtype=H16())
     ops.layer_norm(x, g0, b0, o0, gamma1=g1, beta1=b1, out1=o1, rows_per_group=rpg).run()
     torch.cuda.synchronize()
     xn = F.layer_norm(x.float(), (c,), eps=1e-5)
@@ -198,11 +212,11 @@ def test_upsample_pad(h, w, oh, ow):
     ops, L = _ops()
     b, c = 2, 64
     x = rnd(b, h, w, c, seed=1)
-    out = torch.full((b * (oh + 2) * (ow + 2), c), float("nan"), device=DEV, dtype=torch.bfloat16)
+    out = torch.full((b * (oh + 2) * (ow + 2), c), float("nan"), device=DEV, dtype=H16())
     ops.upsample_pad(x, b, h, w, oh, ow, out).run()
     torch.cuda.synchronize()
     ref = F.interpolate(x.permute(0, 3, 1, 2), size=(oh, ow), mode="nearest").permute(0, 2, 3, 1)
-    assert torch.equal(out.float(), _pad_layout(ref.bfloat16()).float())
+    assert torch.equal(out.float(), _pad_layout(ref.to(H16())).float())
 
 
 @pytest.mark.parametrize("c,stride,pt,pl,kpad", [(64, 2, 1, 1, 576), (128, 2, 0, 0, 1152), (3, 1, 1, 1, 64), (12, 1, 1, 1, 128)])
@@ -214,7 +228,7 @@ def test_im2col(c, stride, pt, pl, kpad):
         oh, ow = (h + 1 - 3) // 2 + 1, (w + 1 - 3) // 2 + 1     # diffusers Downsample2D: pad (0,1,0,1), stride 2
     else:
         oh, ow = (h + 2 * pt - 3) // stride + 1, (w + 2 * pl - 3) // stride + 1
-    out = torch.full((b * oh * ow, kpad), float("nan"), device=DEV, dtype=torch.bfloat16)
+    out = torch.full((b * oh * ow, kpad), float("nan"), device=DEV, dtype=H16())
     ops.im2col(x, b, h, w, out, stride=stride, pad_t=pt, pad_l=pl, oh=oh, ow=ow).run()
     torch.cuda.synchronize()
     xn = x.permute(0, 3, 1, 2)
@@ -224,7 +238,7 @@ def test_im2col(c, stride, pt, pl, kpad):
     else:
         cols = F.unfold(xn, 3, padding=pt, stride=stride)
     cols = cols.reshape(b, c, 9, oh * ow).permute(0, 3, 2, 1).reshape(b * oh * ow, 9 * c)   # [pix, tap*c + ch]
-    assert torch.equal(out[:, :9 * c].float(), cols.bfloat16().float())
+    assert torch.equal(out[:, :9 * c].float(), cols.to(H16()).float())
     assert out[:, 9 * c:].abs().sum() == 0
 
 
@@ -232,7 +246,7 @@ def test_xattn_small_keys():
     ops, L = _ops()
     heads, rows_per_group, groups = 5, 100, 3
     c = heads * 64
-    q = rnd(groups * rows_per_group, c, seed=1).bfloat16()
+    q = rnd(groups * rows_per_group, c, seed=1).to(H16())
     kc, vc = rnd(7, 4, c, seed=2), rnd(7, 4, c, seed=3)
     ntok = [3, 3, 3, 4, 4, 3, 3]
     tog = [3, 0, 6]
@@ -254,9 +268,9 @@ def test_task_attention(c):
     ops, L = _ops()
     rpg, nheads = 150, 4
     main, src = [2, 0, 5], [0, 1, 2, 3, 4, 5, 6]
-    q = rnd(len(main) * rpg, c, seed=1).bfloat16()
-    k = rnd(len(src) * rpg, c, seed=2).bfloat16()
-    v = rnd(len(src) * rpg, c, seed=3).bfloat16()
+    q = rnd(len(main) * rpg, c, seed=1).to(H16())
+    k = rnd(len(src) * rpg, c, seed=2).to(H16())
+    v = rnd(len(src) * rpg, c, seed=3).to(H16())
     out = torch.empty_like(q)
     ops.task_attn(q, k, v, out, c, nheads, main, src, rpg).run()
     torch.cuda.synchronize()
@@ -275,7 +289,7 @@ def test_task_attention(c):
 def test_softmax_rows():
     ops, L = _ops()
     s = rnd(300, 4800, seed=1) * 5
-    p = torch.empty(300, 4800, device=DEV, dtype=torch.bfloat16)
+    p = torch.empty(300, 4800, device=DEV, dtype=H16())
     ops.softmax_rows(s, p, 0.25).run()
     torch.cuda.synchronize()
     assert rel_l2(p.float(), torch.softmax(s * 0.25, -1)) < 4e-3
