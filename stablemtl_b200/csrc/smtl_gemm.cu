@@ -58,6 +58,130 @@ __device__ __forceinline__ void st_global_v4_b32(void* p, uint32_t a, uint32_t b
     asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// Epilogue for one accumulator row per thread: `taddr` = TMEM address of this warp's lane quarter, column 0 of the
+// tile; `grow` = GEMM-space row of this thread; `tn` = N-tile index.  All tcgen05.ld are warp-collective.
+template <int BN>
+__device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t taddr, int64_t grow, int tn) {
+    const bool geglu = (p.act == SMTL_ACT_GEGLU);
+    const int out_bn = geglu ? BN / 2 : BN;
+    const int n0 = tn * BN;
+    bool row_ok = grow < p.m;
+    int64_t orow = grow;
+    if (p.rowmap == SMTL_ROWMAP_CONV_PAD) {
+        const int wp = p.img_w + 2;
+        const int plane = (p.img_h + 2) * wp;
+        const int64_t img = grow / plane;
+        const int rem = (int)(grow - img * plane);
+        const int yp = rem / wp, xp = rem - yp * wp;
+        row_ok = row_ok && yp >= 1 && yp <= p.img_h && xp >= 1 && xp <= p.img_w;
+        orow = (img * p.img_h + (yp - 1)) * p.img_w + (xp - 1);
+    }
+    const float row_bias = (p.bias && p.bias_per_row && grow < p.m) ? __ldg(p.bias + grow) : 0.0f;
+
+    for (int c0 = 0; c0 < out_bn; c0 += 32) {
+        const int ncol_in = n0 + c0;                       // B-row index of the chunk's first column
+        if (ncol_in >= p.n) break;                         // warp-uniform
+        uint32_t r[32];
+        float v[32];
+        tmem_ld_32x32(taddr + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias) {
+            if (p.bias_per_row) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += row_bias;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (ncol_in + j < p.n) v[j] += __ldg(p.bias + ncol_in + j);
+            }
+        }
+        int ocol = ncol_in;                                // output column of v[0]
+        if (geglu) {
+            tmem_ld_32x32(taddr + BN / 2 + c0, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float g = __uint_as_float(r[j]);
+                if (p.bias) g += __ldg(p.bias + n0 + BN / 2 + c0 + j);
+                v[j] *= gelu_erf(g);
+            }
+            ocol = tn * (BN / 2) + c0;
+        } else if (p.act == SMTL_ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        } else if (p.act == SMTL_ACT_SILU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
+        }
+        if (row_ok) {
+        const bool full = (ocol + 32 <= p.n_out);
+        if (p.aux_bf16) {
+            uint16_t* dst = p.aux_bf16 + orow * (int64_t)p.ld_aux + ocol;
+            if (full && (p.ld_aux & 7) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8)
+                    st_global_v4_b32(dst + j, pack16x2(v[j], v[j + 1], p.fmt), pack16x2(v[j + 2], v[j + 3], p.fmt),
+                                     pack16x2(v[j + 4], v[j + 5], p.fmt), pack16x2(v[j + 6], v[j + 7], p.fmt));
+            } else {
+                for (int j = 0; j < 32; ++j)
+                    if (ocol + j < p.n_out) dst[j] = to16(v[j], p.fmt);
+            }
+        }
+        if (p.res1) {
+            const float* src = p.res1 + orow * (int64_t)p.ldres + ocol;
+            if (full && (p.ldres & 3) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(src + j));
+                    v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+                }
+            } else {
+                for (int j = 0; j < 32; ++j)
+                    if (ocol + j < p.n_out) v[j] += __ldg(src + j);
+            }
+        }
+        if (p.res2) {
+            const float* src = p.res2 + orow * (int64_t)p.ldres + ocol;
+            if (full && (p.ldres & 3) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(src + j));
+                    v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+                }
+            } else {
+                for (int j = 0; j < 32; ++j)
+                    if (ocol + j < p.n_out) v[j] += __ldg(src + j);
+            }
+        }
+        if (p.out_f32) {
+            float* dst = p.out_f32 + orow * (int64_t)p.ldc + ocol;
+            if (full && (p.ldc & 3) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) st_global_v4_f32(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+                for (int j = 0; j < 32; ++j)
+                    if (ocol + j < p.n_out) dst[j] = v[j];
+            }
+        }
+        if (p.out_bf16) {
+            uint16_t* dst = p.out_bf16 + orow * (int64_t)p.ldc + ocol;
+            if (full && (p.ldc & 7) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8)
+                    st_global_v4_b32(dst + j, pack16x2(v[j], v[j + 1], p.fmt), pack16x2(v[j + 2], v[j + 3], p.fmt),
+                                     pack16x2(v[j + 4], v[j + 5], p.fmt), pack16x2(v[j + 6], v[j + 7], p.fmt));
+            } else {
+                for (int j = 0; j < 32; ++j)
+                    if (ocol + j < p.n_out) dst[j] = to16(v[j], p.fmt);
+            }
+        }
+        }  // row_ok
+        __syncwarp();   // reconverge before the next warp-collective tcgen05.ld
+    }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_constant__ GemmKParams p) {
     constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
@@ -165,134 +289,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
         // ------------------------------------------------------------------ epilogue (warps 2..5)
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
         const int row_in_tile = quarter * 32 + lane;
-        const bool geglu = (p.act == SMTL_ACT_GEGLU);
-        const int out_bn = geglu ? BN / 2 : BN;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
-            const int64_t grow = (int64_t)tm * BLOCK_M + row_in_tile;
-            const int n0 = tn * BN;
-            bool row_ok = grow < p.m;
-            int64_t orow = grow;
-            if (p.rowmap == SMTL_ROWMAP_CONV_PAD) {
-                const int wp = p.img_w + 2;
-                const int plane = (p.img_h + 2) * wp;
-                const int64_t img = grow / plane;
-                const int rem = (int)(grow - img * plane);
-                const int yp = rem / wp, xp = rem - yp * wp;
-                row_ok = row_ok && yp >= 1 && yp <= p.img_h && xp >= 1 && xp <= p.img_w;
-                orow = (img * p.img_h + (yp - 1)) * p.img_w + (xp - 1);
-            }
-            const float row_bias = (p.bias && p.bias_per_row && grow < p.m) ? __ldg(p.bias + grow) : 0.0f;
-
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
-
-            for (int c0 = 0; c0 < out_bn; c0 += 32) {
-                const int ncol_in = n0 + c0;                       // B-row index of the chunk's first column
-                if (ncol_in >= p.n) break;                         // warp-uniform
-                uint32_t r[32];
-                float v[32];
-                tmem_ld_32x32(taddr + c0, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                if (p.bias) {
-                    if (p.bias_per_row) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] += row_bias;
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (ncol_in + j < p.n) v[j] += __ldg(p.bias + ncol_in + j);
-                    }
-                }
-                int ocol = ncol_in;                                // output column of v[0]
-                if (geglu) {
-                    tmem_ld_32x32(taddr + BN / 2 + c0, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float g = __uint_as_float(r[j]);
-                        if (p.bias) g += __ldg(p.bias + n0 + BN / 2 + c0 + j);
-                        v[j] *= gelu_erf(g);
-                    }
-                    ocol = tn * (BN / 2) + c0;
-                } else if (p.act == SMTL_ACT_GELU) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-                } else if (p.act == SMTL_ACT_SILU) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
-                }
-                if (row_ok) {
-                const bool full = (ocol + 32 <= p.n_out);
-                if (p.aux_bf16) {
-                    uint16_t* dst = p.aux_bf16 + orow * (int64_t)p.ld_aux + ocol;
-                    if (full && (p.ld_aux & 7) == 0) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8)
-                            st_global_v4_b32(dst + j, pack16x2(v[j], v[j + 1], p.fmt), pack16x2(v[j + 2], v[j + 3], p.fmt),
-                                             pack16x2(v[j + 4], v[j + 5], p.fmt), pack16x2(v[j + 6], v[j + 7], p.fmt));
-                    } else {
-                        for (int j = 0; j < 32; ++j)
-                            if (ocol + j < p.n_out) dst[j] = to16(v[j], p.fmt);
-                    }
-                }
-                if (p.res1) {
-                    const float* src = p.res1 + orow * (int64_t)p.ldres + ocol;
-                    if (full && (p.ldres & 3) == 0) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 t = __ldg(reinterpret_cast<const float4*>(src + j));
-                            v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-                        }
-                    } else {
-                        for (int j = 0; j < 32; ++j)
-                            if (ocol + j < p.n_out) v[j] += __ldg(src + j);
-                    }
-                }
-                if (p.res2) {
-                    const float* src = p.res2 + orow * (int64_t)p.ldres + ocol;
-                    if (full && (p.ldres & 3) == 0) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 t = __ldg(reinterpret_cast<const float4*>(src + j));
-                            v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-                        }
-                    } else {
-                        for (int j = 0; j < 32; ++j)
-                            if (ocol + j < p.n_out) v[j] += __ldg(src + j);
-                    }
-                }
-                if (p.out_f32) {
-                    float* dst = p.out_f32 + orow * (int64_t)p.ldc + ocol;
-                    if (full && (p.ldc & 3) == 0) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) st_global_v4_f32(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    } else {
-                        for (int j = 0; j < 32; ++j)
-                            if (ocol + j < p.n_out) dst[j] = v[j];
-                    }
-                }
-                if (p.out_bf16) {
-                    uint16_t* dst = p.out_bf16 + orow * (int64_t)p.ldc + ocol;
-                    if (full && (p.ldc & 7) == 0) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8)
-                            st_global_v4_b32(dst + j, pack16x2(v[j], v[j + 1], p.fmt), pack16x2(v[j + 2], v[j + 3], p.fmt),
-                                             pack16x2(v[j + 4], v[j + 5], p.fmt), pack16x2(v[j + 6], v[j + 7], p.fmt));
-                    } else {
-                        for (int j = 0; j < 32; ++j)
-                            if (ocol + j < p.n_out) dst[j] = to16(v[j], p.fmt);
-                    }
-                }
-                }  // row_ok
-                __syncwarp();   // reconverge before the next warp-collective tcgen05.ld
-            }
+            epilogue_rows<BN>(p, taddr, (int64_t)tm * BLOCK_M + row_in_tile, tn);
             // release this accumulator stage back to the MMA warp
             tc_fence_before();
             __syncwarp();

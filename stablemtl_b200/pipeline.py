@@ -148,6 +148,16 @@ class StableMTLEngine:
             return res, {t: lats[i] for i, t in enumerate(self.tasks)}
         return res
 
+    def empty_result(self, H, W):
+        """Zero-image result with the shapes/dtypes `predict` returns (a rank whose shard is empty, shard.py)."""
+        out = {}
+        for t in self.tasks:
+            if t == "semantic":
+                out[t] = torch.empty(0, H, W, device=self.device, dtype=torch.int64)
+            else:
+                out[t] = torch.empty(0, TASK_CH[t], H, W, device=self.device, dtype=F32)
+        return out
+
     def launches_per_step(self, B, H, W, with_next=True):
         return self.plan_for(B, H, W, with_next)["launches"]
 

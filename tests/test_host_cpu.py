@@ -1,0 +1,89 @@
+"""Host-side logic that needs no GPU: weight-layout transforms, FLOP accounting, image sharding."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from stablemtl_b200 import shard, synth  # noqa: E402
+from stablemtl_b200.weights import conv_weight_matrix, interleave_geglu  # noqa: E402
+
+
+def test_conv_weight_matrix_is_krsc():
+    """[Cout, tap*Cin + c] with tap = ky*3+kx reproduces F.conv2d through an explicit im2col."""
+    torch.manual_seed(0)
+    w = torch.randn(5, 4, 3, 3)
+    x = torch.randn(2, 4, 6, 7)
+    ref = F.conv2d(x, w, padding=1)
+    xp = F.pad(x, (1, 1, 1, 1)).permute(0, 2, 3, 1)                        # NHWC padded
+    cols = torch.cat([xp[:, ky:ky + 6, kx:kx + 7, :] for ky in range(3) for kx in range(3)], dim=-1)
+    out = (cols.reshape(-1, 36) @ conv_weight_matrix(w).t()).reshape(2, 6, 7, 5).permute(0, 3, 1, 2)
+    assert torch.allclose(out, ref, atol=1e-5)
+
+
+def test_geglu_interleave_matches_chunk_semantics():
+    """diffusers GEGLU: value = rows [0,4C), gate = rows [4C,8C); the kernel wants [value 128 | gate 128] per tile."""
+    torch.manual_seed(1)
+    C = 64
+    w, b = torch.randn(8 * C, C), torch.randn(8 * C)
+    x = torch.randn(3, C)
+    val, gate = F.linear(x, w, b).chunk(2, dim=-1)
+    ref = val * F.gelu(gate)
+    wi, bi = interleave_geglu(w, b)
+    y = F.linear(x, wi, bi).reshape(3, -1, 2, 128)
+    out = (y[:, :, 0] * F.gelu(y[:, :, 1])).reshape(3, -1)
+    assert torch.allclose(out, ref, atol=1e-5)
+
+
+def test_algorithmic_flops_match_survey():
+    """per-image GFLOP at 480x640."""
+    import bench
+    a = bench.algorithmic_flops(60, 80, multi=False)
+    assert a["enc"] / 1e9 == pytest.approx(1315.5, rel=2e-3)
+    assert a["dec"] / 1e9 == pytest.approx(2953.6, rel=2e-3)
+    assert a["unet"] / 7 / 1e9 == pytest.approx(962.1, rel=2e-3)
+    assert a["total"] / 1e12 == pytest.approx(30.04, rel=2e-3)
+    m = bench.algorithmic_flops(60, 80, multi=True)
+    # SURVEY's 38.75 TFLOP counts the per-source-task K/V MLPs once per MAIN task (6 x 7 = 42 evaluations); they do
+    # not depend on the main task, so the deduplicated schedule evaluates them once per stream (7): 37.69 TFLOP.
+    # bench.py reports against the smaller, honest figure.
+    assert m["total"] / 1e12 == pytest.approx(37.69, rel=2e-3)
+    assert m["total"] < 38.75e12
+    extra_kv = (38.75e12 - m["total"]) / 35             # 35 redundant K/V-MLP evaluations
+    assert extra_kv / 1e9 == pytest.approx(281.2 / 6 * (6 / 6), rel=0.4)
+
+
+def test_synthetic_checkpoint_layout():
+    """Appendix B key layout and determinism of the seeded stand-in checkpoints."""
+    sd = synth.make_unet_state_dict(synth.TINY_UNET, seed=0)
+    assert sd["conv_in.weight"].shape == (64, 12, 3, 3)
+    assert "down_blocks.0.attentions.1.transformer_blocks.0.attn1.to_out.0.bias" in sd
+    assert "up_blocks.3.attentions.2.transformer_blocks.0.ff.net.0.proj.weight" in sd
+    assert "down_blocks.3.attentions.0.norm.weight" not in sd               # DownBlock3D has no attention
+    assert "up_blocks.2.upsamplers.0.conv.weight" in sd and "up_blocks.3.upsamplers.0.conv.weight" not in sd
+    again = synth.make_unet_state_dict(synth.TINY_UNET, seed=0)
+    assert all(torch.equal(sd[k], again[k]) for k in sd)
+    tm = synth.make_task_modules_state_dict(synth.TINY_UNET, seed=11)
+    k = "mid_block.attentions.0.transformer_blocks.0.attn1.task_to_q.depth.net.6.weight"
+    assert tm[k].shape == (256, 64)
+    assert tm["mid_block.attentions.0.transformer_blocks.0.attn1.to_out_task.weight"].abs().max() > 0
+    assert len(synth.TINY_UNET.transformer_dims()) == 16
+    text = synth.make_text_embeddings(128)
+    assert [text[t].shape[0] for t in synth.TASKS] == [3, 3, 3, 4, 4, 3, 3]
+
+
+@pytest.mark.parametrize("n,world", [(64, 8), (16, 1), (7, 4), (3, 8), (0, 2), (128, 8)])
+def test_shard_ranges_partition_the_batch(n, world):
+    sizes = shard.shard_sizes(n, world)
+    assert sum(sizes) == n and max(sizes) - min(sizes) <= 1
+    cover = []
+    for r in range(world):
+        lo, hi = shard.shard_range(n, world, r)
+        cover += list(range(lo, hi))
+    assert cover == list(range(n))
+    with pytest.raises(ValueError):
+        shard.shard_range(n, world, world)

