@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SMTL_ABI_VERSION 1
+#define SMTL_ABI_VERSION 2
 
 enum {
     SMTL_OK = 0,
@@ -89,6 +89,15 @@ typedef struct smtl_gemm_args {
     int32_t img_h, img_w; /* interior size for the conv row map (padded size is +2) */
     int32_t block_n;    /* 0 = auto; else 32/64/128/160/192/224/256 */
     int32_t fmt16;      /* SMTL_FMT_* of a0/a1/b/out_bf16/aux_bf16 */
+    int32_t res_fmt16;  /* 0: res1/res2 are fp32; 1: they are 16-bit (fmt16), same leading dim ldres */
+    /* Fused GroupNorm statistics of the OUTPUT (the input of the next GroupNorm, src/model/resnet.py:177,188):
+     * stats is fp32 [stats_replicas, stats_images, n_out, 2] holding per-(image, channel) sum and sum of squares
+     * of the final value (after residual adds), accumulated with atomic adds -- the caller zeroes it first
+     * (smtl_memset_run).  image = output row / stats_rows_per_image.  NULL = off. */
+    int32_t stats_replicas;         /* >= 1 copies to spread atomic contention; consumers sum them */
+    float* stats;
+    int32_t stats_rows_per_image;
+    int32_t stats_images;
 } smtl_gemm_args;
 
 typedef struct smtl_gemm_op {
@@ -213,6 +222,41 @@ typedef struct smtl_gn_args {
 } smtl_gn_args;
 int smtl_gn_run(const smtl_gn_args* a, void* stream);
 
+/* GroupNorm apply (+SiLU) from PRODUCER-SIDE statistics: the GEMM/conv that wrote x0 (and x1 of a channel
+ * concat, src/model/unet_blocks.py:509,597) also accumulated per-(image, channel) sum / sum of squares
+ * (smtl_gemm_args.stats), so this is a single streaming pass: 16-bit (or fp32) compact map in, 16-bit operand of
+ * the next conv/GEMM out (zero-halo padded or compact).  Group statistics of a virtual concat are assembled from
+ * both sources' channel sums, so a group may straddle the seam. */
+typedef struct smtl_gnapply_args {
+    const void* x0;
+    const void* x1;         /* second source of the concat, or NULL */
+    int32_t c0, c1;
+    int32_t x_fmt16;        /* 0: x0/x1 are fp32; 1: 16-bit (fmt16) */
+    int32_t stats_replicas;
+    const float* stats0;    /* fp32 [stats_replicas, batch, c0, 2] */
+    const float* stats1;    /* fp32 [stats_replicas, batch, c1, 2] or NULL */
+    int32_t batch, h, w;
+    int32_t groups;
+    float eps;
+    int32_t silu;
+    const float* gamma;
+    const float* beta;
+    int32_t pad_out;        /* 1: padded layout with zero halo, 0: compact */
+    int32_t fmt16;
+    void* out_bf16;
+    void* raw_bf16;         /* optional un-normalised 16-bit copy in the output layout (1x1 shortcut operand) */
+} smtl_gnapply_args;
+int smtl_gnapply_run(const smtl_gnapply_args* a, void* stream);
+
+/* cudaMemsetAsync on the plan's stream (zeroing the statistics arena before the producers run). */
+typedef struct smtl_memset_args {
+    void* ptr;
+    int64_t bytes;
+    int32_t value;
+    int32_t pad_;
+} smtl_memset_args;
+int smtl_memset_run(const smtl_memset_args* a, void* stream);
+
 /* LayerNorm over the channel dim, fp32 or bf16 in, bf16 out; up to two affine outputs from one pass and
  * per-row-group affine parameters (task_norm_{q,k,v}[task], src/util/model.py:133-138).
  * Replaces nn.LayerNorm at src/model/attention.py:338,358,372,494-495,512. */
@@ -238,26 +282,26 @@ int smtl_ln_run(const smtl_ln_args* a, void* stream);
  * Nearest upsample (x2 or explicit size: src = floor(dst * in/out)) fused with the bf16 cast and the zero halo
  * of the following 3x3 conv.  Replaces F.interpolate at src/model/resnet.py:58-61. */
 typedef struct smtl_upsample_args {
-    const float* x;
+    const void* x;          /* compact [batch, h, w, c], fp32 or 16-bit (x_fmt16) */
     int32_t batch, h, w, c;
     int32_t oh, ow;
     void* out_bf16;         /* padded layout [batch, oh+2, ow+2, c] */
     int32_t fmt16;
-    int32_t pad_;
+    int32_t x_fmt16;        /* 0: x is fp32; 1: x is 16-bit (fmt16) */
 } smtl_upsample_args;
 int smtl_upsample_run(const smtl_upsample_args* a, void* stream);
 
 /* Explicit im2col (bf16) for the few convs the shifted-GEMM form does not cover: stride-2 downsamplers
  * (src/model/resnet.py:87,105; diffusers Downsample2D with (0,1,0,1) padding) and tiny-Cin stems (conv_in). */
 typedef struct smtl_im2col_args {
-    const float* x;         /* compact fp32 [batch, h, w, c] */
+    const void* x;          /* compact [batch, h, w, c], fp32 or 16-bit (x_fmt16) */
     int32_t batch, h, w, c;
     int32_t stride, pad_t, pad_l;
     int32_t oh, ow;
     int32_t kpad;           /* row length of the output (>= 9*c, multiple of 64, zero filled) */
     void* out_bf16;         /* [batch*oh*ow, kpad] */
     int32_t fmt16;
-    int32_t pad_;
+    int32_t x_fmt16;        /* 0: x is fp32; 1: x is 16-bit (fmt16; vectorised path only) */
 } smtl_im2col_args;
 int smtl_im2col_run(const smtl_im2col_args* a, void* stream);
 
@@ -323,7 +367,7 @@ int smtl_taskmap_run(const smtl_taskmap_args* a, void* stream);
 enum {
     SMTL_OP_GEMM = 1, SMTL_OP_FATTN = 2, SMTL_OP_SOFTMAX = 3, SMTL_OP_XATTN = 4, SMTL_OP_TASKATTN = 5,
     SMTL_OP_GN = 6, SMTL_OP_LN = 7, SMTL_OP_UPSAMPLE = 8, SMTL_OP_IM2COL = 9, SMTL_OP_RGBPREP = 10,
-    SMTL_OP_UNETIN = 11, SMTL_OP_TASKMAP = 12, SMTL_OP_CHANMIX = 13
+    SMTL_OP_UNETIN = 11, SMTL_OP_TASKMAP = 12, SMTL_OP_CHANMIX = 13, SMTL_OP_GNAPPLY = 14, SMTL_OP_MEMSET = 15
 };
 typedef struct smtl_op_ref {
     int32_t kind;

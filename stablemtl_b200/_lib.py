@@ -18,7 +18,7 @@ ROWMAP_IDENTITY, ROWMAP_CONV_PAD = 0, 1
 FMT_BF16, FMT_F16 = 0, 1
 MAP_MEAN1, MAP_RGB3, MAP_NORMAL, MAP_FLOW2, MAP_FLOW3, MAP_SEMANTIC = range(6)
 (OP_GEMM, OP_FATTN, OP_SOFTMAX, OP_XATTN, OP_TASKATTN, OP_GN, OP_LN, OP_UPSAMPLE, OP_IM2COL, OP_RGBPREP,
- OP_UNETIN, OP_TASKMAP, OP_CHANMIX) = range(1, 14)
+ OP_UNETIN, OP_TASKMAP, OP_CHANMIX, OP_GNAPPLY, OP_MEMSET) = range(1, 16)
 
 vp = C.c_void_p
 i32 = C.c_int32
@@ -49,6 +49,9 @@ class GemmArgs(C.Structure):
         ("rowmap", i32),
         ("img_h", i32), ("img_w", i32),
         ("block_n", i32), ("fmt16", i32),
+        ("res_fmt16", i32), ("stats_replicas", i32),
+        ("stats", vp),
+        ("stats_rows_per_image", i32), ("stats_images", i32),
     ]
 
 
@@ -109,6 +112,22 @@ class GnArgs(C.Structure):
     ]
 
 
+class GnApplyArgs(C.Structure):
+    _fields_ = [
+        ("x0", vp), ("x1", vp), ("c0", i32), ("c1", i32),
+        ("x_fmt16", i32), ("stats_replicas", i32),
+        ("stats0", vp), ("stats1", vp),
+        ("batch", i32), ("h", i32), ("w", i32), ("groups", i32), ("eps", f32), ("silu", i32),
+        ("gamma", vp), ("beta", vp),
+        ("pad_out", i32), ("fmt16", i32),
+        ("out_bf16", vp), ("raw_bf16", vp),
+    ]
+
+
+class MemsetArgs(C.Structure):
+    _fields_ = [("ptr", vp), ("bytes", i64), ("value", i32), ("pad_", i32)]
+
+
 class LnArgs(C.Structure):
     _fields_ = [
         ("x", vp), ("x_is_bf16", i32), ("c", i32), ("ldx", i32),
@@ -121,12 +140,12 @@ class LnArgs(C.Structure):
 
 class UpsampleArgs(C.Structure):
     _fields_ = [("x", vp), ("batch", i32), ("h", i32), ("w", i32), ("c", i32), ("oh", i32), ("ow", i32),
-                ("out_bf16", vp), ("fmt16", i32), ("pad_", i32)]
+                ("out_bf16", vp), ("fmt16", i32), ("x_fmt16", i32)]
 
 
 class Im2colArgs(C.Structure):
     _fields_ = [("x", vp), ("batch", i32), ("h", i32), ("w", i32), ("c", i32), ("stride", i32), ("pad_t", i32),
-                ("pad_l", i32), ("oh", i32), ("ow", i32), ("kpad", i32), ("out_bf16", vp), ("fmt16", i32), ("pad_", i32)]
+                ("pad_l", i32), ("oh", i32), ("ow", i32), ("kpad", i32), ("out_bf16", vp), ("fmt16", i32), ("x_fmt16", i32)]
 
 
 class RgbprepArgs(C.Structure):
@@ -152,11 +171,11 @@ class OpRef(C.Structure):
 
 
 STRUCTS_IN_HEADER_ORDER = [GemmSeg, GemmArgs, GemmOp, FattnArgs, FattnOp, SoftmaxArgs, XattnArgs, TaskAttnArgs,
-                           GnArgs, LnArgs, UpsampleArgs, Im2colArgs, RgbprepArgs, UnetinArgs, ChanmixArgs, TaskmapArgs, OpRef]
+                           GnArgs, GnApplyArgs, MemsetArgs, LnArgs, UpsampleArgs, Im2colArgs, RgbprepArgs, UnetinArgs, ChanmixArgs, TaskmapArgs, OpRef]
 
 EXPORTS = [
     "smtl_gemm_plan", "smtl_gemm_run", "smtl_fattn_plan", "smtl_fattn_run", "smtl_softmax_run", "smtl_xattn_run",
-    "smtl_taskattn_run", "smtl_gn_run", "smtl_ln_run", "smtl_upsample_run", "smtl_im2col_run", "smtl_rgbprep_run",
+    "smtl_taskattn_run", "smtl_gn_run", "smtl_gnapply_run", "smtl_memset_run", "smtl_ln_run", "smtl_upsample_run", "smtl_im2col_run", "smtl_rgbprep_run",
     "smtl_unetin_run", "smtl_chanmix_run", "smtl_taskmap_run", "smtl_run_plan", "smtl_plan_launches", "smtl_abi_version",
     "smtl_last_error", "smtl_struct_sizes",
 ]

@@ -9,6 +9,30 @@ using namespace smtl;
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+// 8 consecutive channels starting at element index `idx` of a fp32 or 16-bit tensor -> fp32 registers
+__device__ __forceinline__ void load8(const void* base, int64_t idx, int is16, int fmt, float (&v)[8]) {
+    if (is16) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(base) + idx));
+        float2 f;
+        f = unpack16x2(u.x, fmt); v[0] = f.x; v[1] = f.y;
+        f = unpack16x2(u.y, fmt); v[2] = f.x; v[3] = f.y;
+        f = unpack16x2(u.z, fmt); v[4] = f.x; v[5] = f.y;
+        f = unpack16x2(u.w, fmt); v[6] = f.x; v[7] = f.y;
+    } else {
+        const float* ptr = reinterpret_cast<const float*>(base) + idx;
+        const float4 a = ldg4(ptr), b = ldg4(ptr + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+}
+// the raw 16 bytes when the tensor already is 16-bit (pure copies: upsample / im2col / shortcut operand)
+__device__ __forceinline__ uint4 load8_as16(const void* base, int64_t idx, int is16, int fmt) {
+    if (is16) return __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(base) + idx));
+    float v[8];
+    load8(base, idx, 0, fmt, v);
+    return make_uint4(pack16x2(v[0], v[1], fmt), pack16x2(v[2], v[3], fmt), pack16x2(v[4], v[5], fmt),
+                      pack16x2(v[6], v[7], fmt));
+}
+
 // ============================================================================================= GroupNorm
 // stats: grid (nchunk, batch); block = (C/4) * rows_par threads; thread owns 4 fixed channels.
 __global__ void gn_stats_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int c0, int c1, int hw,
@@ -128,6 +152,109 @@ __global__ void gn_apply_kernel(const float* __restrict__ x0, const float* __res
     }
 }
 
+// GroupNorm apply from producer-side per-(image, channel) statistics (smtl_gemm_args.stats): one streaming pass.
+// grid (blocks_per_image, batch), 256 threads; each thread handles 8 channels of one (padded) pixel per step.
+__global__ void __launch_bounds__(256) gn_apply2_kernel(
+    const void* __restrict__ x0, const void* __restrict__ x1, int c0, int c1, int x16, const float* __restrict__ st0,
+    const float* __restrict__ st1, int replicas, int batch, int h, int w, int groups, float eps,
+    const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu, int pad_out,
+    uint16_t* __restrict__ out, uint16_t* __restrict__ raw, int fmt) {
+    extern __shared__ float sm[];   // scale[C], shift[C], gmean[groups], grstd[groups]
+    const int C = c0 + c1;
+    float* scale = sm;              // first used as per-channel sum
+    float* shift = sm + C;          // first used as per-channel sum of squares
+    float* gmean = sm + 2 * C;
+    float* grstd = gmean + groups;
+    const int b = blockIdx.y;
+    const int hw = h * w;
+    const int cpg = C / groups;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float* st = (c < c0) ? st0 : st1;
+        const int cs = (c < c0) ? c0 : c1;
+        const int cc = (c < c0) ? c : c - c0;
+        float s = 0.f, q = 0.f;
+        for (int r = 0; r < replicas; ++r) {
+            const float2 t = __ldg(reinterpret_cast<const float2*>(st + (((int64_t)r * batch + b) * cs + cc) * 2));
+            s += t.x;
+            q += t.y;
+        }
+        scale[c] = s;
+        shift[c] = q;
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        double s = 0.0, q = 0.0;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            s += (double)scale[c];
+            q += (double)shift[c];
+        }
+        const double n = (double)hw * cpg;
+        const double mean = s / n;
+        double var = q / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        gmean[g] = (float)mean;
+        grstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const float sc = grstd[g] * gamma[c];
+        scale[c] = sc;
+        shift[c] = beta[c] - gmean[g] * sc;
+    }
+    __syncthreads();
+    const int cv8 = C >> 3;
+    const int hp = pad_out ? h + 2 : h, wp = pad_out ? w + 2 : w;
+    const int64_t total = (int64_t)hp * wp * cv8;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const int pix = (int)(idx / cv8);
+        const int c = (int)(idx - (int64_t)pix * cv8) * 8;
+        int y = pix / wp, x = pix - y * wp;
+        uint4 o = make_uint4(0, 0, 0, 0), r = make_uint4(0, 0, 0, 0);
+        bool interior = true;
+        if (pad_out) {
+            interior = (y >= 1 && y <= h && x >= 1 && x <= w);
+            y -= 1; x -= 1;
+        }
+        if (interior) {
+            const void* src;
+            int ld, cc;
+            if (c < c0) { src = x0; ld = c0; cc = c; } else { src = x1; ld = c1; cc = c - c0; }
+            const int64_t eidx = ((int64_t)b * hw + (int64_t)y * w + x) * ld + cc;
+            float v[8];
+            if (x16) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(src) + eidx));
+                r = u;
+                float2 f;
+                f = unpack16x2(u.x, fmt); v[0] = f.x; v[1] = f.y;
+                f = unpack16x2(u.y, fmt); v[2] = f.x; v[3] = f.y;
+                f = unpack16x2(u.z, fmt); v[4] = f.x; v[5] = f.y;
+                f = unpack16x2(u.w, fmt); v[6] = f.x; v[7] = f.y;
+            } else {
+                load8(src, eidx, 0, fmt, v);
+                if (raw) {
+                    r.x = pack16x2(v[0], v[1], fmt); r.y = pack16x2(v[2], v[3], fmt);
+                    r.z = pack16x2(v[4], v[5], fmt); r.w = pack16x2(v[6], v[7], fmt);
+                }
+            }
+            const float4 s0 = *reinterpret_cast<const float4*>(scale + c), s1 = *reinterpret_cast<const float4*>(scale + c + 4);
+            const float4 h0 = *reinterpret_cast<const float4*>(shift + c), h1 = *reinterpret_cast<const float4*>(shift + c + 4);
+            v[0] = v[0] * s0.x + h0.x; v[1] = v[1] * s0.y + h0.y; v[2] = v[2] * s0.z + h0.z; v[3] = v[3] * s0.w + h0.w;
+            v[4] = v[4] * s1.x + h1.x; v[5] = v[5] * s1.y + h1.y; v[6] = v[6] * s1.z + h1.z; v[7] = v[7] * s1.w + h1.w;
+            if (do_silu) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = silu(v[i]);
+            }
+            o.x = pack16x2(v[0], v[1], fmt); o.y = pack16x2(v[2], v[3], fmt);
+            o.z = pack16x2(v[4], v[5], fmt); o.w = pack16x2(v[6], v[7], fmt);
+        }
+        const int64_t orow = (int64_t)b * hp * wp + pix;
+        *reinterpret_cast<uint4*>(out + orow * C + c) = o;
+        if (raw) *reinterpret_cast<uint4*>(raw + orow * C + c) = r;
+    }
+}
+
 // ============================================================================================= LayerNorm
 // one warp per row; lane holds up to 10 float4 (C <= 1280).
 template <bool IN_BF16>
@@ -193,7 +320,7 @@ __global__ void ln_kernel(const void* __restrict__ xv, int c, int ldx, int64_t r
 }
 
 // ============================================================================================= layout producers
-__global__ void upsample_pad_kernel(const float* __restrict__ x, int batch, int h, int w, int c, int oh, int ow,
+__global__ void upsample_pad_kernel(const void* __restrict__ x, int x16, int batch, int h, int w, int c, int oh, int ow,
                                     uint16_t* __restrict__ out, int fmt) {
     const int cv8 = c >> 3;
     const int hp = oh + 2, wp = ow + 2;
@@ -210,18 +337,15 @@ __global__ void upsample_pad_kernel(const float* __restrict__ x, int batch, int 
         if (yp >= 1 && yp <= oh && xp >= 1 && xp <= ow) {
             const int ysrc = min((int)floorf((float)(yp - 1) * sy), h - 1);
             const int xsrc = min((int)floorf((float)(xp - 1) * sx), w - 1);
-            const float* ptr = x + (((int64_t)b * h + ysrc) * w + xsrc) * c + cc;
-            const float4 a = ldg4(ptr), bb = ldg4(ptr + 4);
-            o.x = pack16x2(a.x, a.y, fmt); o.y = pack16x2(a.z, a.w, fmt);
-            o.z = pack16x2(bb.x, bb.y, fmt); o.w = pack16x2(bb.z, bb.w, fmt);
+            o = load8_as16(x, (((int64_t)b * h + ysrc) * w + xsrc) * c + cc, x16, fmt);
         }
         *reinterpret_cast<uint4*>(out + pix * c + cc) = o;
     }
 }
 
 // im2col, 8 channels per thread (c % 8 == 0, kpad == 9*c)
-__global__ void im2col_vec8_kernel(const float* __restrict__ x, int batch, int h, int w, int c, int stride, int pad_t,
-                                   int pad_l, int oh, int ow, uint16_t* __restrict__ out, int fmt) {
+__global__ void im2col_vec8_kernel(const void* __restrict__ x, int x16, int batch, int h, int w, int c, int stride,
+                                   int pad_t, int pad_l, int oh, int ow, uint16_t* __restrict__ out, int fmt) {
     const int cv8 = c >> 3;
     const int64_t total = (int64_t)batch * oh * ow * 9 * cv8;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -236,10 +360,7 @@ __global__ void im2col_vec8_kernel(const float* __restrict__ x, int batch, int h
         const int iy = oy * stride - pad_t + tap / 3, ix = ox * stride - pad_l + tap % 3;
         uint4 o = make_uint4(0, 0, 0, 0);
         if (iy >= 0 && iy < h && ix >= 0 && ix < w) {
-            const float* ptr = x + (((int64_t)b * h + iy) * w + ix) * c + cc;
-            const float4 a = ldg4(ptr), bb = ldg4(ptr + 4);
-            o.x = pack16x2(a.x, a.y, fmt); o.y = pack16x2(a.z, a.w, fmt);
-            o.z = pack16x2(bb.x, bb.y, fmt); o.w = pack16x2(bb.z, bb.w, fmt);
+            o = load8_as16(x, (((int64_t)b * h + iy) * w + ix) * c + cc, x16, fmt);
         }
         *reinterpret_cast<uint4*>(out + opix * (int64_t)(9 * c) + tap * c + cc) = o;
     }
@@ -561,6 +682,36 @@ extern "C" int smtl_gn_run(const smtl_gn_args* a, void* stream) {
     return SMTL_OK;
 }
 
+extern "C" int smtl_gnapply_run(const smtl_gnapply_args* a, void* stream) {
+    SMTL_CHECK_ARG(a && a->x0 && a->stats0 && a->gamma && a->beta && a->out_bf16, "gnapply: NULL argument");
+    const int C = a->c0 + a->c1;
+    SMTL_CHECK_ARG(a->c1 == 0 || (a->x1 && a->stats1), "gnapply: c1 > 0 without x1/stats1");
+    SMTL_CHECK_ARG(a->groups > 0 && C % a->groups == 0 && a->c0 % 8 == 0 && a->c1 % 8 == 0,
+                   "gnapply: C=%d+%d groups=%d unsupported", a->c0, a->c1, a->groups);
+    SMTL_CHECK_ARG(C <= 4096 && a->groups <= 64, "gnapply: C=%d too wide", C);
+    SMTL_CHECK_ARG(a->batch >= 1 && a->h >= 1 && a->w >= 1 && a->stats_replicas >= 1, "gnapply: bad extent");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int hp = a->pad_out ? a->h + 2 : a->h, wp = a->pad_out ? a->w + 2 : a->w;
+    const int64_t per_img = (int64_t)hp * wp * (C / 8);
+    int bpi = (int)((per_img + 256 * 4 - 1) / (256 * 4));
+    const int cap = (148 * 8 + a->batch - 1) / a->batch;
+    if (bpi > cap) bpi = cap;
+    if (bpi < 1) bpi = 1;
+    const size_t smem = (2 * C + 2 * a->groups) * sizeof(float);
+    gn_apply2_kernel<<<dim3(bpi, a->batch), 256, smem, st>>>(
+        a->x0, a->x1, a->c0, a->c1, a->x_fmt16, a->stats0, a->stats1, a->stats_replicas, a->batch, a->h, a->w,
+        a->groups, a->eps, a->gamma, a->beta, a->silu, a->pad_out, reinterpret_cast<uint16_t*>(a->out_bf16),
+        reinterpret_cast<uint16_t*>(a->raw_bf16), a->fmt16);
+    SMTL_CHECK_CUDA(cudaGetLastError());
+    return SMTL_OK;
+}
+
+extern "C" int smtl_memset_run(const smtl_memset_args* a, void* stream) {
+    SMTL_CHECK_ARG(a && a->ptr && a->bytes > 0, "memset: NULL / empty");
+    SMTL_CHECK_CUDA(cudaMemsetAsync(a->ptr, a->value, (size_t)a->bytes, reinterpret_cast<cudaStream_t>(stream)));
+    return SMTL_OK;
+}
+
 extern "C" int smtl_ln_run(const smtl_ln_args* a, void* stream) {
     SMTL_CHECK_ARG(a && a->x && a->gamma0 && a->beta0 && a->out0, "ln: NULL argument");
     SMTL_CHECK_ARG(a->c % 4 == 0 && a->c <= 1280 && a->ldx % 4 == 0 && a->ldo % 4 == 0, "ln: c=%d ldx=%d unsupported",
@@ -587,8 +738,8 @@ extern "C" int smtl_upsample_run(const smtl_upsample_args* a, void* stream) {
     SMTL_CHECK_ARG(a->c % 8 == 0 && a->oh >= a->h && a->ow >= a->w, "upsample: bad shape");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int64_t total = (int64_t)a->batch * (a->oh + 2) * (a->ow + 2) * (a->c / 8);
-    upsample_pad_kernel<<<grid_for(total, 256), 256, 0, st>>>(a->x, a->batch, a->h, a->w, a->c, a->oh, a->ow,
-                                                              (uint16_t*)a->out_bf16, a->fmt16);
+    upsample_pad_kernel<<<grid_for(total, 256), 256, 0, st>>>(a->x, a->x_fmt16, a->batch, a->h, a->w, a->c, a->oh,
+                                                              a->ow, (uint16_t*)a->out_bf16, a->fmt16);
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;
 }
@@ -599,11 +750,13 @@ extern "C" int smtl_im2col_run(const smtl_im2col_args* a, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (a->c % 8 == 0 && a->kpad == 9 * a->c) {
         const int64_t total = (int64_t)a->batch * a->oh * a->ow * 9 * (a->c / 8);
-        im2col_vec8_kernel<<<grid_for(total, 256), 256, 0, st>>>(a->x, a->batch, a->h, a->w, a->c, a->stride, a->pad_t,
-                                                                 a->pad_l, a->oh, a->ow, (uint16_t*)a->out_bf16, a->fmt16);
+        im2col_vec8_kernel<<<grid_for(total, 256), 256, 0, st>>>(a->x, a->x_fmt16, a->batch, a->h, a->w, a->c, a->stride,
+                                                                 a->pad_t, a->pad_l, a->oh, a->ow,
+                                                                 (uint16_t*)a->out_bf16, a->fmt16);
     } else {
+        SMTL_CHECK_ARG(!a->x_fmt16, "im2col: the scalar (tiny Cin) path takes fp32 input");
         const int64_t total = (int64_t)a->batch * a->oh * a->ow * a->kpad;
-        im2col_scalar_kernel<<<grid_for(total, 256), 256, 0, st>>>(a->x, a->batch, a->h, a->w, a->c, a->stride,
+        im2col_scalar_kernel<<<grid_for(total, 256), 256, 0, st>>>((const float*)a->x, a->batch, a->h, a->w, a->c, a->stride,
                                                                    a->pad_t, a->pad_l, a->oh, a->ow, a->kpad,
                                                                    (uint16_t*)a->out_bf16, a->fmt16);
     }

@@ -38,9 +38,12 @@ struct alignas(64) GemmKParams {
     const float* bias;
     int32_t bias_per_row;
     int32_t act;
-    const float* res1;
-    const float* res2;
+    const void* res1;
+    const void* res2;
     int32_t ldres;
+    int32_t res16;
+    float* stats;
+    int32_t stats_rpi, stats_images, stats_rep;
     float* out_f32;
     uint16_t* out_bf16;
     uint16_t* aux_bf16;
@@ -58,26 +61,141 @@ __device__ __forceinline__ void st_global_v4_b32(void* p, uint32_t a, uint32_t b
     asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// Epilogue for one accumulator row per thread: `taddr` = TMEM address of this warp's lane quarter, column 0 of the
-// tile; `grow` = GEMM-space row of this thread; `tn` = N-tile index.  All tcgen05.ld are warp-collective.
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// Lane j <- sum over the 32 lanes of s[j] (recursive halving: 31 shuffles instead of 32 x 5).
+__device__ __forceinline__ float warp_transpose_sum(float (&s)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float mine = upper ? s[i + off] : s[i];
+            const float other = upper ? s[i] : s[i + off];
+            s[i] = mine + __shfl_xor_sync(0xffffffffu, other, off);
+        }
+    }
+    return s[0];
+}
+
+// Per-thread state of one tile's epilogue, computed BEFORE waiting for the accumulator so that the residual
+// prefetches and the bias loads overlap the tile's MMAs.
 template <int BN>
-__device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t taddr, int64_t grow, int tn) {
+struct EpiRow {
+    int64_t orow;          // output row of this thread's accumulator row
+    bool row_ok;           // false: halo / out-of-range row (nothing stored)
+    int img;               // image of the output row (statistics), -1 if !row_ok
+    int img_lo, img_hi;    // warp-wide range of img over valid rows (img_lo > img_hi: no valid row)
+    float row_bias;
+    float bias[BN / 32];   // lane-distributed: bias[k] = bias_vec[n0 + 32 k + lane]
+};
+
+template <int BN>
+__device__ __forceinline__ void epilogue_prepare(const GemmKParams& p, int64_t grow, int tn, int lane, EpiRow<BN>& e) {
     const bool geglu = (p.act == SMTL_ACT_GEGLU);
     const int out_bn = geglu ? BN / 2 : BN;
     const int n0 = tn * BN;
-    bool row_ok = grow < p.m;
-    int64_t orow = grow;
+    e.row_ok = grow < p.m;
+    e.orow = grow;
     if (p.rowmap == SMTL_ROWMAP_CONV_PAD) {
         const int wp = p.img_w + 2;
         const int plane = (p.img_h + 2) * wp;
         const int64_t img = grow / plane;
         const int rem = (int)(grow - img * plane);
         const int yp = rem / wp, xp = rem - yp * wp;
-        row_ok = row_ok && yp >= 1 && yp <= p.img_h && xp >= 1 && xp <= p.img_w;
-        orow = (img * p.img_h + (yp - 1)) * p.img_w + (xp - 1);
+        e.row_ok = e.row_ok && yp >= 1 && yp <= p.img_h && xp >= 1 && xp <= p.img_w;
+        e.orow = (img * p.img_h + (yp - 1)) * p.img_w + (xp - 1);
     }
-    const float row_bias = (p.bias && p.bias_per_row && grow < p.m) ? __ldg(p.bias + grow) : 0.0f;
+    e.row_bias = (p.bias && p.bias_per_row && grow < p.m) ? __ldg(p.bias + grow) : 0.0f;
+#pragma unroll
+    for (int k = 0; k < BN / 32; ++k) {
+        const int c = n0 + 32 * k + lane;
+        e.bias[k] = (p.bias && !p.bias_per_row && c < p.n) ? __ldg(p.bias + c) : 0.0f;
+    }
+    // pull this row's residual lines into L2 while the MMAs of the tile run
+    if (e.row_ok && (p.res1 || p.res2)) {
+        const int ocol0 = geglu ? tn * (BN / 2) : n0;
+        const int esz = p.res16 ? 2 : 4;
+        int ncols = p.n_out - ocol0;
+        if (ncols > out_bn) ncols = out_bn;
+        const int64_t off = (e.orow * (int64_t)p.ldres + ocol0) * esz;
+        for (int b = 0; b < ncols * esz; b += 128) {
+            if (p.res1) prefetch_l2(reinterpret_cast<const char*>(p.res1) + off + b);
+            if (p.res2) prefetch_l2(reinterpret_cast<const char*>(p.res2) + off + b);
+        }
+    }
+    e.img = -1;
+    e.img_lo = 1;
+    e.img_hi = 0;
+    if (p.stats) {
+        e.img = e.row_ok ? (int)(e.orow / p.stats_rpi) : -1;
+        int lo = e.row_ok ? e.img : 0x7fffffff, hi = e.img;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        e.img_lo = lo;
+        e.img_hi = hi;
+    }
+}
 
+// residual add of one 32-column chunk of this thread's row (fp32 or 16-bit source)
+__device__ __forceinline__ void add_residual(const GemmKParams& p, const void* res, int64_t orow, int ocol, bool full,
+                                             float (&v)[32]) {
+    if (p.res16) {
+        const uint16_t* src = reinterpret_cast<const uint16_t*>(res) + orow * (int64_t)p.ldres + ocol;
+        if (full && (p.ldres & 7) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                const uint4 t = ldg_nc_v4(src + j);
+                float2 f;
+                f = unpack16x2(t.x, p.fmt); v[j] += f.x; v[j + 1] += f.y;
+                f = unpack16x2(t.y, p.fmt); v[j + 2] += f.x; v[j + 3] += f.y;
+                f = unpack16x2(t.z, p.fmt); v[j + 4] += f.x; v[j + 5] += f.y;
+                f = unpack16x2(t.w, p.fmt); v[j + 6] += f.x; v[j + 7] += f.y;
+            }
+        } else {
+            for (int j = 0; j < 32; ++j)
+                if (ocol + j < p.n_out) v[j] += unpack16x2((uint32_t)src[j], p.fmt).x;
+        }
+    } else {
+        const float* src = reinterpret_cast<const float*>(res) + orow * (int64_t)p.ldres + ocol;
+        if (full && (p.ldres & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(src + j));
+                v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+            }
+        } else {
+            for (int j = 0; j < 32; ++j)
+                if (ocol + j < p.n_out) v[j] += __ldg(src + j);
+        }
+    }
+}
+
+// Epilogue for one accumulator row per thread: `taddr` = TMEM address of this warp's lane quarter, column 0 of the
+// tile; `tn` = N-tile index.  All tcgen05.ld / shuffles are warp-collective.
+template <int BN>
+__device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t taddr, int tn, int lane,
+                                              const EpiRow<BN>& e) {
+    const bool geglu = (p.act == SMTL_ACT_GEGLU);
+    const int out_bn = geglu ? BN / 2 : BN;
+    const int n0 = tn * BN;
+    const bool row_ok = e.row_ok;
+    const int64_t orow = e.orow;
+    float bq[BN / 32];          // bias queue: bq[0] is always the current chunk's (rotated once per chunk, so the
+#pragma unroll                  // array is only ever indexed with compile-time constants and stays in registers)
+    for (int k = 0; k < BN / 32; ++k) bq[k] = e.bias[k];
+
+#pragma unroll 1
     for (int c0 = 0; c0 < out_bn; c0 += 32) {
         const int ncol_in = n0 + c0;                       // B-row index of the chunk's first column
         if (ncol_in >= p.n) break;                         // warp-uniform
@@ -85,26 +203,22 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t tad
         float v[32];
         tmem_ld_32x32(taddr + c0, r);
         tmem_ld_wait();
+        if (p.bias_per_row) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias) {
-            if (p.bias_per_row) {
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + e.row_bias;
+        } else {
+            const float bl = bq[0];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += row_bias;
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (ncol_in + j < p.n) v[j] += __ldg(p.bias + ncol_in + j);
-            }
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bl, j);
         }
         int ocol = ncol_in;                                // output column of v[0]
         if (geglu) {
             tmem_ld_32x32(taddr + BN / 2 + c0, r);
             tmem_ld_wait();
+            const float gl = bq[BN / 64];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                float g = __uint_as_float(r[j]);
-                if (p.bias) g += __ldg(p.bias + n0 + BN / 2 + c0 + j);
+                const float g = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, gl, j);
                 v[j] *= gelu_erf(g);
             }
             ocol = tn * (BN / 2) + c0;
@@ -115,70 +229,69 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t tad
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
         }
-        if (row_ok) {
         const bool full = (ocol + 32 <= p.n_out);
-        if (p.aux_bf16) {
-            uint16_t* dst = p.aux_bf16 + orow * (int64_t)p.ld_aux + ocol;
-            if (full && (p.ld_aux & 7) == 0) {
+        if (row_ok) {
+            if (p.aux_bf16) {
+                uint16_t* dst = p.aux_bf16 + orow * (int64_t)p.ld_aux + ocol;
+                if (full && (p.ld_aux & 7) == 0) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 8)
-                    st_global_v4_b32(dst + j, pack16x2(v[j], v[j + 1], p.fmt), pack16x2(v[j + 2], v[j + 3], p.fmt),
-                                     pack16x2(v[j + 4], v[j + 5], p.fmt), pack16x2(v[j + 6], v[j + 7], p.fmt));
-            } else {
-                for (int j = 0; j < 32; ++j)
-                    if (ocol + j < p.n_out) dst[j] = to16(v[j], p.fmt);
-            }
-        }
-        if (p.res1) {
-            const float* src = p.res1 + orow * (int64_t)p.ldres + ocol;
-            if (full && (p.ldres & 3) == 0) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 t = __ldg(reinterpret_cast<const float4*>(src + j));
-                    v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+                    for (int j = 0; j < 32; j += 8)
+                        st_global_v4_b32(dst + j, pack16x2(v[j], v[j + 1], p.fmt), pack16x2(v[j + 2], v[j + 3], p.fmt),
+                                         pack16x2(v[j + 4], v[j + 5], p.fmt), pack16x2(v[j + 6], v[j + 7], p.fmt));
+                } else {
+                    for (int j = 0; j < 32; ++j)
+                        if (ocol + j < p.n_out) dst[j] = to16(v[j], p.fmt);
                 }
-            } else {
-                for (int j = 0; j < 32; ++j)
-                    if (ocol + j < p.n_out) v[j] += __ldg(src + j);
             }
-        }
-        if (p.res2) {
-            const float* src = p.res2 + orow * (int64_t)p.ldres + ocol;
-            if (full && (p.ldres & 3) == 0) {
+            if (p.res1) add_residual(p, p.res1, orow, ocol, full, v);
+            if (p.res2) add_residual(p, p.res2, orow, ocol, full, v);
+            if (p.out_f32) {
+                float* dst = p.out_f32 + orow * (int64_t)p.ldc + ocol;
+                if (full && (p.ldc & 3) == 0) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 t = __ldg(reinterpret_cast<const float4*>(src + j));
-                    v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+                    for (int j = 0; j < 32; j += 4) st_global_v4_f32(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+                    for (int j = 0; j < 32; ++j)
+                        if (ocol + j < p.n_out) dst[j] = v[j];
                 }
-            } else {
-                for (int j = 0; j < 32; ++j)
-                    if (ocol + j < p.n_out) v[j] += __ldg(src + j);
             }
-        }
-        if (p.out_f32) {
-            float* dst = p.out_f32 + orow * (int64_t)p.ldc + ocol;
-            if (full && (p.ldc & 3) == 0) {
+            if (p.out_bf16) {
+                uint16_t* dst = p.out_bf16 + orow * (int64_t)p.ldc + ocol;
+                if (full && (p.ldc & 7) == 0) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) st_global_v4_f32(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-                for (int j = 0; j < 32; ++j)
-                    if (ocol + j < p.n_out) dst[j] = v[j];
+                    for (int j = 0; j < 32; j += 8)
+                        st_global_v4_b32(dst + j, pack16x2(v[j], v[j + 1], p.fmt), pack16x2(v[j + 2], v[j + 3], p.fmt),
+                                         pack16x2(v[j + 4], v[j + 5], p.fmt), pack16x2(v[j + 6], v[j + 7], p.fmt));
+                } else {
+                    for (int j = 0; j < 32; ++j)
+                        if (ocol + j < p.n_out) dst[j] = to16(v[j], p.fmt);
+                }
             }
         }
-        if (p.out_bf16) {
-            uint16_t* dst = p.out_bf16 + orow * (int64_t)p.ldc + ocol;
-            if (full && (p.ldc & 7) == 0) {
+        __syncwarp();   // reconverge before the next warp-collective instruction
 #pragma unroll
-                for (int j = 0; j < 32; j += 8)
-                    st_global_v4_b32(dst + j, pack16x2(v[j], v[j + 1], p.fmt), pack16x2(v[j + 2], v[j + 3], p.fmt),
-                                     pack16x2(v[j + 4], v[j + 5], p.fmt), pack16x2(v[j + 6], v[j + 7], p.fmt));
-            } else {
-                for (int j = 0; j < 32; ++j)
-                    if (ocol + j < p.n_out) dst[j] = to16(v[j], p.fmt);
+        for (int k = 0; k + 1 < BN / 32; ++k) bq[k] = bq[k + 1];
+        if (p.stats && e.img_lo <= e.img_hi) {
+            // per-(image, channel) sum / sum of squares of the stored value: lane j ends up owning column ocol + j
+            for (int img = e.img_lo; img <= e.img_hi; ++img) {       // warp-uniform; one iteration unless the
+                float s[32], q[32];                                    // warp's rows straddle an image boundary
+                const bool mine = (e.img == img);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float x = mine ? v[j] : 0.0f;
+                    s[j] = x;
+                    q[j] = x * x;
+                }
+                const float cs = warp_transpose_sum(s, lane);
+                const float cq = warp_transpose_sum(q, lane);
+                if (ocol + lane < p.n_out) {
+                    float* dst = p.stats + (((int64_t)(blockIdx.x % p.stats_rep) * p.stats_images + img) * p.n_out +
+                                            ocol + lane) * 2;
+                    atomicAdd(dst, cs);
+                    atomicAdd(dst + 1, cq);
+                }
             }
         }
-        }  // row_ok
-        __syncwarp();   // reconverge before the next warp-collective tcgen05.ld
     }
 }
 
@@ -294,10 +407,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+            EpiRow<BN> er;
+            epilogue_prepare<BN>(p, (int64_t)tm * BLOCK_M + row_in_tile, tn, lane, er);
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
-            epilogue_rows<BN>(p, taddr, (int64_t)tm * BLOCK_M + row_in_tile, tn);
+            epilogue_rows<BN>(p, taddr, tn, lane, er);
             // release this accumulator stage back to the MMA warp
             tc_fence_before();
             __syncwarp();
@@ -380,6 +495,14 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
     SMTL_CHECK_ARG(g.fmt16 == SMTL_FMT_BF16 || g.fmt16 == SMTL_FMT_F16, "gemm_plan: bad fmt16 %d", g.fmt16);
     if (g.rowmap == SMTL_ROWMAP_CONV_PAD)
         SMTL_CHECK_ARG(g.img_h > 0 && g.img_w > 0, "gemm_plan: conv row map needs img_h/img_w");
+    SMTL_CHECK_ARG(g.res_fmt16 == 0 || g.res_fmt16 == 1, "gemm_plan: bad res_fmt16 %d", g.res_fmt16);
+    if (g.stats) {
+        SMTL_CHECK_ARG(g.stats_rows_per_image > 0 && g.stats_images > 0 && g.stats_replicas >= 1 &&
+                           g.stats_replicas <= 64,
+                       "gemm_plan: stats needs rows_per_image/images/replicas (got %d/%d/%d)", g.stats_rows_per_image,
+                       g.stats_images, g.stats_replicas);
+        SMTL_CHECK_ARG(g.act != SMTL_ACT_GEGLU && !g.bias_per_row, "gemm_plan: stats with GEGLU / per-row bias");
+    }
     SMTL_CHECK_ARG(g.m + 4096 < (int64_t)1 << 31, "gemm_plan: m too large for 32-bit TMA coordinates");
 
     op->block_n = bn;
@@ -431,6 +554,11 @@ extern "C" int smtl_gemm_run(const smtl_gemm_op* op, void* stream) {
     kp.res1 = g.res1;
     kp.res2 = g.res2;
     kp.ldres = g.ldres;
+    kp.res16 = g.res_fmt16;
+    kp.stats = g.stats;
+    kp.stats_rpi = g.stats_rows_per_image;
+    kp.stats_images = g.stats_images;
+    kp.stats_rep = g.stats_replicas > 0 ? g.stats_replicas : 1;
     kp.out_f32 = g.out_f32;
     kp.out_bf16 = reinterpret_cast<uint16_t*>(g.out_bf16);
     kp.aux_bf16 = reinterpret_cast<uint16_t*>(g.aux_bf16);

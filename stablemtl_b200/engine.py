@@ -58,9 +58,63 @@ class Pool:
         for t in tensors:
             if t is None:
                 continue
+            if isinstance(t, Act):
+                t = t.t
             blk = self.owner.pop(t.data_ptr(), None)
             if blk is not None:
                 self.free.append(blk)
+
+
+class Act:
+    """A feature map between layers: 16-bit compact [rows, C] plus the per-(image, channel) sum / sum-of-squares
+    buffer its producing GEMM fills (the statistics of the NEXT GroupNorm, so no separate reduction pass)."""
+    __slots__ = ("t", "stats")
+
+    def __init__(self, t, stats=None):
+        self.t, self.stats = t, stats
+
+    @property
+    def shape(self):
+        return self.t.shape
+
+
+class StatsArena:
+    """All statistics buffers of a plan live in a few contiguous chunks that one memset each zeroes at plan start
+    (every buffer is accumulated into by exactly one GEMM per run)."""
+
+    def __init__(self, device, chunk_bytes=32 << 20):
+        self.device, self.chunk_bytes = device, chunk_bytes
+        self.chunks, self.used = [], []
+
+    def new(self, images, channels):
+        rep = max(1, min(ops.STATS_REPLICAS, 64 // images))
+        n = rep * images * channels * 2
+        n_al = (n + 63) // 64 * 64
+        if not self.chunks or self.used[-1] + n_al > self.chunks[-1].numel():
+            self.chunks.append(torch.zeros(max(self.chunk_bytes // 4, n_al), device=self.device, dtype=F32))
+            self.used.append(0)
+        t = self.chunks[-1][self.used[-1]: self.used[-1] + n].view(rep, images, channels, 2)
+        self.used[-1] += n_al
+        return t
+
+    def memset_ops(self):
+        return [ops.memset_zero(c[:u]) for c, u in zip(self.chunks, self.used) if u > 0]
+
+
+class _PlanBase:
+    """buffer helpers shared by the UNet and VAE plan builders"""
+
+    def _new_act(self, images, hw, C):
+        return Act(self.pool.alloc((images * hw, C), ops.h16()), self.arena.new(images, C))
+
+    @staticmethod
+    def _into(act, hw):
+        """epilogue kwargs of the GEMM that produces `act`"""
+        return dict(out_bf16=act.t, stats=act.stats, stats_rows_per_image=hw)
+
+    def _finish(self):
+        self.plan.ops[0:0] = self.arena.memset_ops()
+        self.plan.finalize()
 
 
 def _dev(t, device, dtype=F32):
@@ -177,7 +231,7 @@ class UNetWeights:
 
 
 # ================================================================================================== UNet plan
-class UNetPlan:
+class UNetPlan(_PlanBase):
     """One batched UNet pass over `groups` row groups of `images` images each (group g runs task group_tasks[g]).
 
     mode "single": plain UNet (StableMTL-S / child without taps)
@@ -192,6 +246,7 @@ class UNetPlan:
         dev = W.device
         self.pool = pool or Pool(dev)
         P = self.pool
+        self.arena = StatsArena(dev)
         self.plan = ops.Plan()
         add = self.plan.add
         G = len(group_tasks)
@@ -202,7 +257,6 @@ class UNetPlan:
         sizes = [(h, w)]
         for _ in range(nlev - 1):
             sizes.append((down_size(sizes[-1][0]), down_size(sizes[-1][1])))
-        self.gn_partial = torch.empty(Be * 64 * 32 * 2, device=dev, dtype=F32)
         self.group_tasks = list(group_tasks)
         self.images = images
         self.feats_out = [] if mode == "child" else None
@@ -213,8 +267,8 @@ class UNetPlan:
         self.x_in = x_in if x_in is not None else torch.zeros(Be * h * w, cfg.in_channels, device=dev, dtype=F32)
         col = P.alloc((Be * h * w, W.kin_pad), ops.h16())
         add(ops.im2col(self.x_in.view(Be, h, w, cfg.in_channels), Be, h, w, col, stride=1, pad_t=1, pad_l=1, oh=h, ow=w))
-        x = P.alloc((Be * h * w, c[0]), F32)
-        add(ops.gemm(col, W.w["conv_in.w"], bias=W.w["conv_in.b"], out_f32=x, name="conv_in"))
+        x = self._new_act(Be, h * w, c[0])
+        add(ops.gemm(col, W.w["conv_in.w"], bias=W.w["conv_in.b"], name="conv_in", **self._into(x, h * w)))
         P.release(col)
 
         skips = [x]
@@ -235,9 +289,9 @@ class UNetPlan:
                 h2, w2 = sizes[i + 1]
                 wt, bs = W.conv(f"down_blocks.{i}.downsamplers.0.conv")
                 col = P.alloc((Be * h2 * w2, 9 * c[i]), ops.h16())
-                add(ops.im2col(x.view(Be, hh, ww, c[i]), Be, hh, ww, col, stride=2, pad_t=1, pad_l=1, oh=h2, ow=w2))
-                x = P.alloc((Be * h2 * w2, c[i]), F32)
-                add(ops.gemm(col, wt, bias=bs, out_f32=x, name="downsample"))
+                add(ops.im2col(x.t.view(Be, hh, ww, c[i]), Be, hh, ww, col, stride=2, pad_t=1, pad_l=1, oh=h2, ow=w2))
+                x = self._new_act(Be, h2 * w2, c[i])
+                add(ops.gemm(col, wt, bias=bs, name="downsample", **self._into(x, h2 * w2)))
                 P.release(col)
                 skips.append(x)
         hh, ww = sizes[-1]
@@ -266,19 +320,19 @@ class UNetPlan:
                 oh, ow = sizes[lev - 1]                       # explicit size of the next skip (unet.py:415-416)
                 wt, bs = W.conv(f"up_blocks.{i}.upsamplers.0.conv")
                 up = P.alloc((Be * (oh + 2) * (ow + 2), cout), ops.h16())
-                add(ops.upsample_pad(x.view(Be, hh, ww, cout), Be, hh, ww, oh, ow, up))
-                x_new = P.alloc((Be * oh * ow, cout), F32)
-                add(ops.conv3x3(up, wt, Be, oh, ow, bias=bs, out_f32=x_new, name="upsample_conv"))
+                add(ops.upsample_pad(x.t.view(Be, hh, ww, cout), Be, hh, ww, oh, ow, up))
+                x_new = self._new_act(Be, oh * ow, cout)
+                add(ops.conv3x3(up, wt, Be, oh, ow, bias=bs, name="upsample_conv", **self._into(x_new, oh * ow)))
                 P.release(up, x)
                 x = x_new
         # ---- head
         a = P.alloc((Be * (h + 2) * (w + 2), c[0]), ops.h16())
-        add(ops.group_norm(x, Be, h, w, W.w["conv_norm_out.g"], W.w["conv_norm_out.b"], a, eps=cfg.norm_eps, silu=True,
-                           pad_out=True, partial=self.gn_partial, groups=cfg.norm_num_groups))
+        add(ops.gn_apply(x.t, x.stats, Be, h, w, W.w["conv_norm_out.g"], W.w["conv_norm_out.b"], a, eps=cfg.norm_eps,
+                         silu=True, pad_out=True, groups=cfg.norm_num_groups))
         self.out = torch.empty(Be * h * w, cfg.out_channels, device=dev, dtype=F32)
         add(ops.conv3x3(a, W.w["conv_out.w"], Be, h, w, bias=W.w["conv_out.b"], out_f32=self.out, name="conv_out"))
         P.release(a, x)
-        self.plan.finalize()
+        self._finish()
 
     # ---------------------------------------------------------------------------------------------- resnet
     def resnet(self, p, x, skip, h, w, cout):
@@ -289,18 +343,19 @@ class UNetPlan:
         short = wt.get(p + ".short", False)
         a1 = P.alloc((Be * (h + 2) * (w + 2), cin), ops.h16())
         raw = P.alloc((Be * (h + 2) * (w + 2), cin), ops.h16()) if short else None
-        add(ops.group_norm(x, Be, h, w, wt[p + ".n1g"], wt[p + ".n1b"], a1, x1=skip, eps=cfg.norm_eps, silu=True,
-                           pad_out=True, partial=self.gn_partial, raw=raw, groups=cfg.norm_num_groups))
-        h1 = P.alloc((Be * h * w, cout), F32)
-        add(ops.conv3x3(a1, wt[p + ".w1"], Be, h, w, bias=wt[p + ".b1"], out_f32=h1, name="res.conv1"))
+        add(ops.gn_apply(x.t, x.stats, Be, h, w, wt[p + ".n1g"], wt[p + ".n1b"], a1,
+                         x1=None if skip is None else skip.t, stats1=None if skip is None else skip.stats,
+                         eps=cfg.norm_eps, silu=True, pad_out=True, raw=raw, groups=cfg.norm_num_groups))
+        h1 = self._new_act(Be, h * w, cout)
+        add(ops.conv3x3(a1, wt[p + ".w1"], Be, h, w, bias=wt[p + ".b1"], name="res.conv1", **self._into(h1, h * w)))
         P.release(a1)
         a2 = P.alloc((Be * (h + 2) * (w + 2), cout), ops.h16())
-        add(ops.group_norm(h1, Be, h, w, wt[p + ".n2g"], wt[p + ".n2b"], a2, eps=cfg.norm_eps, silu=True, pad_out=True,
-                           partial=self.gn_partial, groups=cfg.norm_num_groups))
+        add(ops.gn_apply(h1.t, h1.stats, Be, h, w, wt[p + ".n2g"], wt[p + ".n2b"], a2, eps=cfg.norm_eps, silu=True,
+                         pad_out=True, groups=cfg.norm_num_groups))
         P.release(h1)
-        out = P.alloc((Be * h * w, cout), F32)
-        add(ops.conv3x3(a2, wt[p + ".w2"], Be, h, w, a_short=raw, bias=wt[p + ".b2"], res1=None if short else x,
-                        out_f32=out, name="res.conv2"))
+        out = self._new_act(Be, h * w, cout)
+        add(ops.conv3x3(a2, wt[p + ".w2"], Be, h, w, a_short=raw, bias=wt[p + ".b2"], res1=None if short else x.t,
+                        name="res.conv2", **self._into(out, h * w)))
         P.release(a2, raw)
         return out
 
@@ -313,8 +368,8 @@ class UNetPlan:
         M = Be * N
         rpg = self.images * N                      # rows per task group
         xn = P.alloc((M, C), ops.h16())
-        add(ops.group_norm(x, Be, h, w, wt[p + ".ng"], wt[p + ".nb"], xn, eps=1e-6, silu=False, pad_out=False,
-                           partial=self.gn_partial, groups=cfg.norm_num_groups))
+        add(ops.gn_apply(x.t, x.stats, Be, h, w, wt[p + ".ng"], wt[p + ".nb"], xn, eps=1e-6, silu=False, pad_out=False,
+                         groups=cfg.norm_num_groups))
         hs = P.alloc((M, C), F32)
         add(ops.gemm(xn, wt[p + ".proj_in.w"], bias=wt[p + ".proj_in.b"], out_f32=hs, name="proj_in"))
         n1 = xn                                    # reuse as LN output
@@ -395,8 +450,9 @@ class UNetPlan:
         hb = n3
         add(ops.gemm(gg, wt[p + ".ff2.w"], bias=wt[p + ".ff2.b"], res1=hs, out_bf16=hb, name="ff2"))
         P.release(gg, hs)
-        out = P.alloc((M, C), F32)
-        add(ops.gemm(hb, wt[p + ".proj_out.w"], bias=wt[p + ".proj_out.b"], res1=x, out_f32=out, name="proj_out"))
+        out = self._new_act(Be, N, C)
+        add(ops.gemm(hb, wt[p + ".proj_out.w"], bias=wt[p + ".proj_out.b"], res1=x.t, name="proj_out",
+                     **self._into(out, N)))
         P.release(hb)
         return out
 
@@ -465,7 +521,7 @@ class VAEWeights:
         return self.w
 
 
-class _VAEBase:
+class _VAEBase(_PlanBase):
     def _resnet(self, p, x, h, w, cout):
         W, P, add, B, G = self.W, self.pool, self.plan.add, self.B, self.W.cfg.norm_num_groups
         wt = W.resnet(p)
@@ -473,18 +529,18 @@ class _VAEBase:
         short = wt.get(p + ".short", False)
         a1 = P.alloc((B * (h + 2) * (w + 2), cin), ops.h16())
         raw = P.alloc((B * (h + 2) * (w + 2), cin), ops.h16()) if short else None
-        add(ops.group_norm(x, B, h, w, wt[p + ".n1g"], wt[p + ".n1b"], a1, eps=1e-6, silu=True, pad_out=True,
-                           partial=self.gn_partial, raw=raw, groups=G))
-        h1 = P.alloc((B * h * w, cout), F32)
-        add(ops.conv3x3(a1, wt[p + ".w1"], B, h, w, bias=wt[p + ".b1"], out_f32=h1, name="vae.conv1"))
+        add(ops.gn_apply(x.t, x.stats, B, h, w, wt[p + ".n1g"], wt[p + ".n1b"], a1, eps=1e-6, silu=True, pad_out=True,
+                         raw=raw, groups=G))
+        h1 = self._new_act(B, h * w, cout)
+        add(ops.conv3x3(a1, wt[p + ".w1"], B, h, w, bias=wt[p + ".b1"], name="vae.conv1", **self._into(h1, h * w)))
         P.release(a1)
         a2 = P.alloc((B * (h + 2) * (w + 2), cout), ops.h16())
-        add(ops.group_norm(h1, B, h, w, wt[p + ".n2g"], wt[p + ".n2b"], a2, eps=1e-6, silu=True, pad_out=True,
-                           partial=self.gn_partial, groups=G))
+        add(ops.gn_apply(h1.t, h1.stats, B, h, w, wt[p + ".n2g"], wt[p + ".n2b"], a2, eps=1e-6, silu=True, pad_out=True,
+                         groups=G))
         P.release(h1)
-        out = P.alloc((B * h * w, cout), F32)
-        add(ops.conv3x3(a2, wt[p + ".w2"], B, h, w, a_short=raw, bias=wt[p + ".b2"], res1=None if short else x,
-                        out_f32=out, name="vae.conv2"))
+        out = self._new_act(B, h * w, cout)
+        add(ops.conv3x3(a2, wt[p + ".w2"], B, h, w, a_short=raw, bias=wt[p + ".b2"], res1=None if short else x.t,
+                        name="vae.conv2", **self._into(out, h * w)))
         P.release(a2, raw)
         return out
 
@@ -497,8 +553,8 @@ class _VAEBase:
         M = B * N
         Np = (N + 7) // 8 * 8
         xn = P.alloc((M, C), ops.h16())
-        add(ops.group_norm(x, B, h, w, wt[p + ".ng"], wt[p + ".nb"], xn, eps=1e-6, silu=False, pad_out=False,
-                           partial=self.gn_partial, groups=G))
+        add(ops.gn_apply(x.t, x.stats, B, h, w, wt[p + ".ng"], wt[p + ".nb"], xn, eps=1e-6, silu=False, pad_out=False,
+                         groups=G))
         qk = P.alloc((M, 2 * C), ops.h16())
         add(ops.gemm(xn, wt[p + ".qk.w"], bias=wt[p + ".qk.b"], out_bf16=qk, name="vae.qk"))
         o = P.alloc((M, C), ops.h16())
@@ -512,8 +568,8 @@ class _VAEBase:
             add(ops.softmax_rows(S[:, :N], Pm[:, :N], float(C) ** -0.5))
             add(ops.gemm(Pm[:, :N], vT[:, :N], out_bf16=o[r], name="vae.pv"))
         P.release(vT, S, Pm, qk, xn)
-        out = P.alloc((M, C), F32)
-        add(ops.gemm(o, wt[p + ".o.w"], bias=wt[p + ".o.b"], res1=x, out_f32=out, name="vae.attn_out"))
+        out = self._new_act(B, N, C)
+        add(ops.gemm(o, wt[p + ".o.w"], bias=wt[p + ".o.b"], res1=x.t, name="vae.attn_out", **self._into(out, N)))
         P.release(o)
         return out
 
@@ -538,19 +594,20 @@ class VAEEncodePlan(_VAEBase):
         self.W, self.B = W, B
         dev = W.device
         self.pool = P = pool or Pool(dev)
+        self.arena = StatsArena(dev)
         self.plan = ops.Plan()
         add = self.plan.add
         cfg = W.cfg
         c = cfg.block_out_channels
-        self.gn_partial = torch.empty(B * 64 * 32 * 2, device=dev, dtype=F32)
         self.rgb = rgb if rgb is not None else torch.zeros(B, 3, H, Wd, device=dev, dtype=rgb_dtype)
         xin = P.alloc((B * H * Wd, 3), F32)
         add(ops.rgb_prep(self.rgb, xin))
         col = P.alloc((B * H * Wd, 64), ops.h16())
         add(ops.im2col(xin.view(B, H, Wd, 3), B, H, Wd, col, stride=1, pad_t=1, pad_l=1, oh=H, ow=Wd))
         P.release(xin)
-        x = P.alloc((B * H * Wd, c[0]), F32)
-        add(ops.gemm(col, W.w["enc.conv_in.w"], bias=W.w["enc.conv_in.b"], out_f32=x, name="vae.enc.conv_in"))
+        x = self._new_act(B, H * Wd, c[0])
+        add(ops.gemm(col, W.w["enc.conv_in.w"], bias=W.w["enc.conv_in.b"], name="vae.enc.conv_in",
+                     **self._into(x, H * Wd)))
         P.release(col)
         h, w = H, Wd
         for i in range(len(c)):
@@ -563,20 +620,20 @@ class VAEEncodePlan(_VAEBase):
                 h2, w2 = (h + 1 - 3) // 2 + 1, (w + 1 - 3) // 2 + 1
                 wt, bs = W.conv(f"encoder.down_blocks.{i}.downsamplers.0.conv")
                 col = P.alloc((B * h2 * w2, 9 * c[i]), ops.h16())
-                add(ops.im2col(x.view(B, h, w, c[i]), B, h, w, col, stride=2, pad_t=0, pad_l=0, oh=h2, ow=w2))
-                y = P.alloc((B * h2 * w2, c[i]), F32)
-                add(ops.gemm(col, wt, bias=bs, out_f32=y, name="vae.enc.down"))
+                add(ops.im2col(x.t.view(B, h, w, c[i]), B, h, w, col, stride=2, pad_t=0, pad_l=0, oh=h2, ow=w2))
+                y = self._new_act(B, h2 * w2, c[i])
+                add(ops.gemm(col, wt, bias=bs, name="vae.enc.down", **self._into(y, h2 * w2)))
                 P.release(col, x)
                 x, h, w = y, h2, w2
         x = self._mid("encoder.mid_block", x, h, w, c[-1])
         a = P.alloc((B * (h + 2) * (w + 2), c[-1]), ops.h16())
-        add(ops.group_norm(x, B, h, w, W.w["encoder.ng"], W.w["encoder.nb"], a, eps=1e-6, silu=True, pad_out=True,
-                           partial=self.gn_partial, groups=cfg.norm_num_groups))
+        add(ops.gn_apply(x.t, x.stats, B, h, w, W.w["encoder.ng"], W.w["encoder.nb"], a, eps=1e-6, silu=True,
+                         pad_out=True, groups=cfg.norm_num_groups))
         self.out = torch.empty(B * h * w, cfg.latent_channels, device=dev, dtype=F32)
         add(ops.conv3x3(a, W.w["enc.head.w"], B, h, w, bias=W.w["enc.head.b"], out_f32=self.out, name="vae.enc.head"))
         P.release(a, x)
         self.h, self.w = h, w
-        self.plan.finalize()
+        self._finish()
 
 
 class VAEDecodePlan(_VAEBase):
@@ -586,6 +643,7 @@ class VAEDecodePlan(_VAEBase):
         self.W, self.B = W, B
         dev = W.device
         self.pool = P = pool or Pool(dev)
+        self.arena = StatsArena(dev)
         self.plan = ops.Plan()
         add = self.plan.add
         cfg = W.cfg
@@ -593,14 +651,14 @@ class VAEDecodePlan(_VAEBase):
         lat = cfg.latent_channels
         self.latent = latent if latent is not None else torch.zeros(B * h * w, lat, device=dev, dtype=F32)
         H, Wd = h * 2 ** (len(c) - 1), w * 2 ** (len(c) - 1)
-        self.gn_partial = torch.empty(B * 64 * 32 * 2, device=dev, dtype=F32)
         z = P.alloc((B * h * w, lat), F32)
         add(ops.chan_mix(self.latent, W.w["dec.pq.w"], W.w["dec.pq.b"], z))
         col = P.alloc((B * h * w, 64), ops.h16())
         add(ops.im2col(z.view(B, h, w, lat), B, h, w, col, stride=1, pad_t=1, pad_l=1, oh=h, ow=w))
         P.release(z)
-        x = P.alloc((B * h * w, c[0]), F32)
-        add(ops.gemm(col, W.w["dec.conv_in.w"], bias=W.w["dec.conv_in.b"], out_f32=x, name="vae.dec.conv_in"))
+        x = self._new_act(B, h * w, c[0])
+        add(ops.gemm(col, W.w["dec.conv_in.w"], bias=W.w["dec.conv_in.b"], name="vae.dec.conv_in",
+                     **self._into(x, h * w)))
         P.release(col)
         x = self._mid("decoder.mid_block", x, h, w, c[0])
         for i in range(len(c)):
@@ -611,18 +669,18 @@ class VAEDecodePlan(_VAEBase):
             if i < len(c) - 1:
                 wt, bs = W.conv(f"decoder.up_blocks.{i}.upsamplers.0.conv")
                 up = P.alloc((B * (2 * h + 2) * (2 * w + 2), c[i]), ops.h16())
-                add(ops.upsample_pad(x.view(B, h, w, c[i]), B, h, w, 2 * h, 2 * w, up))
+                add(ops.upsample_pad(x.t.view(B, h, w, c[i]), B, h, w, 2 * h, 2 * w, up))
                 P.release(x)
                 h, w = 2 * h, 2 * w
-                x = P.alloc((B * h * w, c[i]), F32)
-                add(ops.conv3x3(up, wt, B, h, w, bias=bs, out_f32=x, name="vae.dec.up"))
+                x = self._new_act(B, h * w, c[i])
+                add(ops.conv3x3(up, wt, B, h, w, bias=bs, name="vae.dec.up", **self._into(x, h * w)))
                 P.release(up)
         a = P.alloc((B * (h + 2) * (w + 2), c[-1]), ops.h16())
-        add(ops.group_norm(x, B, h, w, W.w["decoder.ng"], W.w["decoder.nb"], a, eps=1e-6, silu=True, pad_out=True,
-                           partial=self.gn_partial, groups=cfg.norm_num_groups))
+        add(ops.gn_apply(x.t, x.stats, B, h, w, W.w["decoder.ng"], W.w["decoder.nb"], a, eps=1e-6, silu=True,
+                         pad_out=True, groups=cfg.norm_num_groups))
         P.release(x)
         self.out = torch.empty(B * h * w, 3, device=dev, dtype=F32)
         add(ops.conv3x3(a, W.w["dec.head.w"], B, h, w, bias=W.w["dec.head.b"], out_f32=self.out, name="vae.dec.head"))
         P.release(a)
         self.H, self.Wd = h, w
-        self.plan.finalize()
+        self._finish()

@@ -59,7 +59,7 @@ _RUNNERS = {
     L.OP_XATTN: "smtl_xattn_run", L.OP_TASKATTN: "smtl_taskattn_run", L.OP_GN: "smtl_gn_run",
     L.OP_LN: "smtl_ln_run", L.OP_UPSAMPLE: "smtl_upsample_run", L.OP_IM2COL: "smtl_im2col_run",
     L.OP_RGBPREP: "smtl_rgbprep_run", L.OP_UNETIN: "smtl_unetin_run", L.OP_TASKMAP: "smtl_taskmap_run",
-    L.OP_CHANMIX: "smtl_chanmix_run",
+    L.OP_CHANMIX: "smtl_chanmix_run", L.OP_GNAPPLY: "smtl_gnapply_run", L.OP_MEMSET: "smtl_memset_run",
 }
 
 
@@ -116,9 +116,17 @@ class Plan:
 
 
 # ------------------------------------------------------------------------------------------------- GEMM / conv
+STATS_REPLICAS = 8      # copies of a statistics buffer the producing GEMM's CTAs spread their atomics over
+
+
+def new_stats(images, channels, device):
+    """fp32 [replicas, images, channels, 2] (sum, sum of squares) filled by a GEMM epilogue; must be zeroed before."""
+    return torch.zeros(STATS_REPLICAS, images, channels, 2, device=device, dtype=F32)
+
+
 def gemm(a0, b, *, m=None, k=None, n=None, a1=None, segs=None, bias=None, bias_per_row=False, act=L.ACT_NONE,
          res1=None, res2=None, out_f32=None, out_bf16=None, aux_bf16=None, rowmap=L.ROWMAP_IDENTITY, img_hw=None,
-         block_n=0, name="gemm"):
+         block_n=0, name="gemm", stats=None, stats_rows_per_image=0):
     """D = A @ B^T (+ fused epilogue).  a0/a1: bf16 [rows, cols] (row stride = stride(0)); b: bf16 [n, k].
     segs: list of (row_shift, kblocks, src, a_col0)."""
     assert a0.dtype == BF16 and b.dtype == BF16 and a0.stride(-1) == 1 and b.stride(-1) == 1
@@ -142,10 +150,19 @@ def gemm(a0, b, *, m=None, k=None, n=None, a1=None, segs=None, bias=None, bias_p
     g.bias_per_row = int(bias_per_row)
     g.act = act
     n_out = g.n // 2 if act == L.ACT_GEGLU else g.n
+    res_dt = None
     for r in (res1, res2):
         if r is not None:
-            assert r.dtype == F32 and r.stride(-1) == 1
+            assert (r.dtype == F32 or r.dtype == BF16) and r.stride(-1) == 1
+            assert res_dt is None or (r.dtype == res_dt and r.stride(0) == g.ldres), "res1/res2 must share dtype and ld"
+            res_dt = r.dtype
             g.ldres = r.stride(0)
+    g.res_fmt16 = int(res_dt is not None and res_dt != F32)
+    if stats is not None:
+        assert stats.dtype == F32 and stats.dim() == 4 and stats.shape[3] == 2 and stats.is_contiguous()
+        assert stats.shape[2] == n_out and stats_rows_per_image > 0
+        g.stats, g.stats_replicas, g.stats_images = stats.data_ptr(), stats.shape[0], stats.shape[1]
+        g.stats_rows_per_image = stats_rows_per_image
     g.res1, g.res2 = _ptr(res1), _ptr(res2)
     outs = [t for t in (out_f32, out_bf16) if t is not None]
     if out_f32 is not None:
@@ -168,7 +185,7 @@ def gemm(a0, b, *, m=None, k=None, n=None, a1=None, segs=None, bias=None, bias_p
     op = L.GemmOp()
     L.check(L.lib.smtl_gemm_plan(C.byref(g), C.byref(op)), "smtl_gemm_plan")
     flops = 2 * int(g.m) * int(g.n) * int(g.k)
-    return Op(L.OP_GEMM, op, (a0, a1, b, bias, res1, res2, out_f32, out_bf16, aux_bf16), flops, name)
+    return Op(L.OP_GEMM, op, (a0, a1, b, bias, res1, res2, out_f32, out_bf16, aux_bf16, stats), flops, name)
 
 
 def conv3x3_segs(cin, w, shortcut_cin=0):
@@ -268,6 +285,35 @@ def group_norm(x0, batch, h, w, gamma, beta, out, *, x1=None, eps, silu, pad_out
     return Op(L.OP_GN, a, (x0, x1, gamma, beta, out, raw, partial), 0, "group_norm")
 
 
+def gn_apply(x0, stats0, batch, h, w, gamma, beta, out, *, x1=None, stats1=None, eps, silu, pad_out, raw=None,
+             groups=32):
+    """GroupNorm(+SiLU) of the (virtually concatenated) compact map [x0 | x1] using the per-(image, channel) sums the
+    producing GEMMs left in stats0 / stats1; writes the 16-bit operand of the next conv (padded) or GEMM (compact)."""
+    a = L.GnApplyArgs()
+    a.fmt16 = PREC["fmt"]
+    a.x0, a.c0 = x0.data_ptr(), x0.shape[-1]
+    a.x_fmt16 = int(x0.dtype != F32)
+    assert x0.is_contiguous() and (x0.dtype == F32 or x0.dtype == BF16)
+    assert stats0.shape[1:] == (batch, x0.shape[-1], 2), (stats0.shape, batch, x0.shape)
+    a.stats0, a.stats_replicas = stats0.data_ptr(), stats0.shape[0]
+    if x1 is not None:
+        assert x1.dtype == x0.dtype and x1.is_contiguous() and stats1.shape == (stats0.shape[0], batch, x1.shape[-1], 2)
+        a.x1, a.c1, a.stats1 = x1.data_ptr(), x1.shape[-1], stats1.data_ptr()
+    a.batch, a.h, a.w, a.groups, a.eps = batch, h, w, groups, eps
+    a.gamma, a.beta = gamma.data_ptr(), beta.data_ptr()
+    a.silu, a.pad_out = int(silu), int(pad_out)
+    a.out_bf16, a.raw_bf16 = out.data_ptr(), _ptr(raw)
+    assert out.dtype == BF16
+    return Op(L.OP_GNAPPLY, a, (x0, x1, stats0, stats1, gamma, beta, out, raw), 0, "gn_apply")
+
+
+def memset_zero(t):
+    a = L.MemsetArgs()
+    a.ptr, a.bytes, a.value = t.data_ptr(), t.numel() * t.element_size(), 0
+    assert t.is_contiguous()
+    return Op(L.OP_MEMSET, a, (t,), 0, "memset")
+
+
 def layer_norm(x, gamma0, beta0, out0, *, gamma1=None, beta1=None, out1=None, rows_per_group=None, eps=1e-5):
     a = L.LnArgs()
     a.fmt16 = PREC["fmt"]
@@ -286,7 +332,8 @@ def upsample_pad(x, batch, h, w, oh, ow, out):
     a = L.UpsampleArgs()
     a.fmt16 = PREC["fmt"]
     a.x, a.batch, a.h, a.w, a.c, a.oh, a.ow, a.out_bf16 = x.data_ptr(), batch, h, w, x.shape[-1], oh, ow, out.data_ptr()
-    assert x.dtype == F32 and out.dtype == BF16
+    a.x_fmt16 = int(x.dtype != F32)
+    assert (x.dtype == F32 or x.dtype == BF16) and out.dtype == BF16
     return Op(L.OP_UPSAMPLE, a, (x, out), 0, "upsample")
 
 
@@ -296,7 +343,8 @@ def im2col(x, batch, h, w, out, *, stride, pad_t, pad_l, oh, ow):
     a.x, a.batch, a.h, a.w, a.c = x.data_ptr(), batch, h, w, x.shape[-1]
     a.stride, a.pad_t, a.pad_l, a.oh, a.ow, a.kpad = stride, pad_t, pad_l, oh, ow, out.shape[-1]
     a.out_bf16 = out.data_ptr()
-    assert x.dtype == F32 and out.dtype == BF16 and out.is_contiguous()
+    a.x_fmt16 = int(x.dtype != F32)
+    assert (x.dtype == F32 or x.dtype == BF16) and out.dtype == BF16 and out.is_contiguous()
     return Op(L.OP_IM2COL, a, (x, out), 0, "im2col")
 
 

@@ -319,3 +319,114 @@ def test_task_map_modes():
     torch.cuda.synchronize()
     ref = torch.cdist(xc.permute(0, 2, 1).reshape(-1, 3), pal).argmin(1).reshape(b, hw)
     assert (ids == ref).float().mean() > 0.999
+
+
+# ------------------------------------------------------------------ 16-bit activations + producer-side GN statistics
+@pytest.mark.parametrize("m,n,k,rpi", [(4800, 320, 320, 1200), (1000, 640, 1280, 250), (600, 128, 576, 600),
+                                       (960, 1280, 320, 80), (777, 96, 200, 777)])
+def test_gemm_16bit_residual_and_channel_stats(m, n, k, rpi):
+    """out16 = A B^T + bias + res16 ; stats[img, col] = (sum, sum of squares) of the fp32 value over the image's rows."""
+    ops, L = _ops()
+    kp = (k + 7) // 8 * 8
+    a = rnd(m, kp, seed=1).to(H16())[:, :k]
+    b = rnd(n, kp, scale=k ** -0.5, seed=2).to(H16())[:, :k]
+    bias = rnd(n, seed=3)
+    res = rnd(m, n, seed=4).to(H16())
+    images = (m + rpi - 1) // rpi
+    stats = ops.new_stats(images, n, DEV)
+    out = torch.empty(m, n, device=DEV, dtype=H16())
+    ops.gemm(a, b, bias=bias, res1=res, out_bf16=out, stats=stats, stats_rows_per_image=rpi).run()
+    torch.cuda.synchronize()
+    ref = a.float() @ b.float().t() + bias + res.float()
+    assert rel_l2(out.float(), ref) < 4e-3
+    st = stats.sum(0)                                            # replicas
+    for img in range(images):
+        blk = ref[img * rpi:(img + 1) * rpi].double()
+        assert rel_l2(st[img, :, 0], blk.sum(0)) < 1e-4, img
+        assert rel_l2(st[img, :, 1], (blk * blk).sum(0)) < 1e-4, img
+
+
+@pytest.mark.parametrize("b,h,w,cin,cout", [(3, 8, 10, 64, 128), (2, 15, 20, 320, 320), (1, 60, 80, 128, 128)])
+def test_conv3x3_16bit_out_with_stats(b, h, w, cin, cout):
+    """the conv row map drops halo rows: they must not leak into the statistics; images straddle tiles (8x10 maps)."""
+    ops, L = _ops()
+    x = rnd(b, h, w, cin, seed=1).to(H16())
+    wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=2).to(H16())
+    bias = rnd(cout, seed=3)
+    res = rnd(b * h * w, cout, seed=4).to(H16())
+    wmat = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(b * h * w, cout)
+    ref = ref + res.float()
+    out = torch.empty(b * h * w, cout, device=DEV, dtype=H16())
+    stats = ops.new_stats(b, cout, DEV)
+    ops.conv3x3(_pad_layout(x), wmat, b, h, w, bias=bias, res1=res, out_bf16=out, stats=stats,
+                stats_rows_per_image=h * w).run()
+    torch.cuda.synchronize()
+    assert rel_l2(out.float(), ref) < 4e-3
+    st = stats.sum(0)
+    blk = ref.reshape(b, h * w, cout).double()
+    assert rel_l2(st[:, :, 0], blk.sum(1)) < 1e-4
+    assert rel_l2(st[:, :, 1], (blk * blk).sum(1)) < 1e-4
+
+
+@pytest.mark.parametrize("b,h,w,c0,c1,silu,pad,x16", [
+    (2, 8, 10, 320, 0, True, True, True), (1, 15, 20, 1280, 640, True, True, True), (2, 30, 40, 640, 320, True, True, True),
+    (2, 6, 20, 320, 0, False, False, True), (1, 64, 96, 128, 0, True, True, True), (2, 8, 10, 320, 0, True, True, False)])
+def test_gn_apply_from_channel_stats(b, h, w, c0, c1, silu, pad, x16):
+    """GroupNorm(+SiLU) over a virtual concat from per-(image, channel) sums; group 21 of 1920 = 1280 + 640 straddles
+    the seam."""
+    ops, L = _ops()
+    dt = H16() if x16 else torch.float32
+    x0 = (rnd(b, h * w, c0, seed=1) * 2 + 0.5).to(dt)
+    x1 = (rnd(b, h * w, c1, seed=2) - 0.3).to(dt) if c1 else None
+
+    def stats_of(x):
+        st = ops.new_stats(b, x.shape[-1], DEV)
+        xd = x.double()
+        full = torch.stack([xd.sum(1), (xd * xd).sum(1)], dim=-1).float()
+        if st.shape[0] > 1:                                    # spread over two replicas: the consumer must sum them
+            st[0], st[1] = full * 0.5, full * 0.5
+        else:
+            st[0] = full
+        return st
+    s0 = stats_of(x0)
+    s1 = stats_of(x1) if c1 else None
+    C = c0 + c1
+    gamma, beta = rnd(C, seed=3) + 1, rnd(C, seed=4)
+    hp, wp = (h + 2, w + 2) if pad else (h, w)
+    out = torch.full((b * hp * wp, C), float("nan"), device=DEV, dtype=H16())
+    raw = torch.full((b * hp * wp, C), float("nan"), device=DEV, dtype=H16())
+    ops.gn_apply(x0.reshape(b * h * w, c0), s0, b, h, w, gamma, beta, out,
+                 x1=None if x1 is None else x1.reshape(b * h * w, c1), stats1=s1, eps=1e-5, silu=silu, pad_out=pad,
+                 raw=raw).run()
+    torch.cuda.synchronize()
+    xc = (torch.cat([x0, x1], dim=-1) if c1 else x0).float()
+    ref = F.group_norm(xc.reshape(b, h, w, C).permute(0, 3, 1, 2), 32, gamma, beta, eps=1e-5)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 3, 1)
+    rawref = xc.reshape(b, h, w, C)
+    if pad:
+        ref, rawref = _pad_layout(ref), _pad_layout(rawref)
+    assert rel_l2(out.float(), ref.reshape(-1, C)) < 4e-3
+    assert rel_l2(raw.float(), rawref.reshape(-1, C)) < 4e-3
+    if pad:
+        halo = out.reshape(b, hp, wp, C)
+        assert halo[:, 0].abs().max() == 0 and halo[:, :, 0].abs().max() == 0 and halo[:, -1].abs().max() == 0
+
+
+def test_upsample_and_im2col_take_16bit_input():
+    ops, L = _ops()
+    b, h, w, c = 2, 8, 10, 64
+    x = rnd(b, h, w, c, seed=1).to(H16())
+    out = torch.full((b * 17 * 22, c), float("nan"), device=DEV, dtype=H16())
+    ops.upsample_pad(x, b, h, w, 15, 20, out).run()
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), size=(15, 20), mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(out.float(), _pad_layout(ref))
+    oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    col = torch.full((b * oh * ow, 9 * c), float("nan"), device=DEV, dtype=H16())
+    ops.im2col(x, b, h, w, col, stride=2, pad_t=1, pad_l=1, oh=oh, ow=ow).run()
+    torch.cuda.synchronize()
+    cols = F.unfold(x.float().permute(0, 3, 1, 2), 3, padding=1, stride=2)
+    cols = cols.reshape(b, c, 9, oh * ow).permute(0, 3, 2, 1).reshape(b * oh * ow, 9 * c)
+    assert torch.equal(col.float(), cols)
