@@ -42,7 +42,7 @@ def report(name, op, flops=None):
 
 
 def rb(*shape):
-    return (torch.randn(*shape, device=DEV) * 0.5).bfloat16()
+    return (torch.randn(*shape, device=DEV) * 0.5).to(ops.h16())
 
 
 def gemm_case(name, m, n, k, **kw):
@@ -62,11 +62,16 @@ def conv_case(name, batch, h, w, cin, cout):
 def attn_case(batch, ntok, heads):
     c = heads * 64
     qkv = rb(batch * ntok, 3 * c)
-    out = torch.empty(batch * ntok, c, device=DEV, dtype=torch.bfloat16)
+    out = torch.empty(batch * ntok, c, device=DEV, dtype=ops.h16())
     report(f"flash_attn b={batch} ntok={ntok} heads={heads}", ops.flash_attn(qkv, batch, ntok, heads, out, 0, c, 2 * c))
 
 
 if __name__ == "__main__":
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
+    if only == "attn":
+        for args in [(16, 4800, 5), (112, 4800, 5), (112, 1200, 10), (112, 300, 20), (112, 80, 20)]:
+            attn_case(*args)
+        sys.exit(0)
     gemm_case("square", 8192, 8192, 8192)
     gemm_case("square bn128", 8192, 8192, 8192, block_n=128)
     gemm_case("ff1 L0", 16 * 4800, 2560, 320)

@@ -9,6 +9,7 @@
 //                             P (bf16) into swizzled smem; rescale of O in TMEM; final O / l epilogue
 #include "smtl_common.cuh"
 #include "smtl_host.h"
+#include <stdlib.h>
 
 namespace {
 using namespace smtl;
@@ -231,6 +232,257 @@ __global__ void __launch_bounds__(FA_THREADS, 2) smtl_fattn_kernel(const __grid_
     }
 }
 
+
+// ================================================================================================ v2 kernel
+// One CTA per SM-resident block of 256 query rows (two 128-row tiles that ping-pong on the tensor core):
+//   warp 0      : TMA producer  (Q0, Q1 once; K/V tiles through an NS-stage ring)
+//   warp 1      : MMA issuer    S_w = Q_w K^T, then O_w += P_w V with P_w read straight from TMEM (tcgen05.mma with
+//                               the A operand in tensor memory), alternating w = 0, 1
+//   warps 2..5  : softmax of tile 0; warps 6..9: softmax of tile 1 -- one query row per thread:
+//                 tcgen05.ld S -> running max (lazy: the reference max only moves when it grows by > 2^8) ->
+//                 p = ex2(s*scale - m) -> 16-bit pairs -> tcgen05.st over the S columns just consumed
+// While one tile's softmax runs on the SFU/ALU pipes the other tile's two MMAs run on the tensor pipe.
+// TMEM columns: S0/P0 [0,128)  S1/P1 [128,256)  O0 [256,320)  O1 [320,384).
+constexpr int F2_THREADS = 320;
+constexpr int F2_NS = 4;                                   // K/V ring stages (32 KB each)
+constexpr int F2_SMEM = 2 * TILE_BYTES + F2_NS * 2 * TILE_BYTES + 256;
+constexpr int F2_TMEM_COLS = 512;
+constexpr float F2_LAZY = 8.0f;                            // log2 units
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+
+template <bool MASKED>
+__device__ __forceinline__ void softmax_tile(const FattnKParams& p, uint32_t t_s, int kv_valid, float& m_run,
+                                             float& l_run, uint32_t t_o, bool have_o) {
+    // the whole S row (128 fp32) is pulled into registers with four back-to-back tcgen05.ld and ONE wait
+    uint32_t rr[128];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&rr[c * 32]));
+    tmem_ld_wait();
+    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 128; i += 4) {
+        float a = __uint_as_float(rr[i]), b = __uint_as_float(rr[i + 1]), c = __uint_as_float(rr[i + 2]),
+              d = __uint_as_float(rr[i + 3]);
+        if (MASKED) {
+            a = (i < kv_valid) ? a : -INFINITY;
+            b = (i + 1 < kv_valid) ? b : -INFINITY;
+            c = (i + 2 < kv_valid) ? c : -INFINITY;
+            d = (i + 3 < kv_valid) ? d : -INFINITY;
+        }
+        mx0 = fmaxf(mx0, a); mx1 = fmaxf(mx1, b); mx2 = fmaxf(mx2, c); mx3 = fmaxf(mx3, d);
+    }
+    const float mx_s = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+    // lazy running max: exact as long as the SAME reference max is used for p, l and O
+    const bool grow = mx_s > m_run + F2_LAZY;
+    if (__any_sync(0xffffffffu, grow)) {
+        const float alpha = grow ? ex2_approx(m_run - mx_s) : 1.0f;     // 0 on the first tile (m_run = -inf)
+        if (grow) { m_run = mx_s; l_run *= alpha; }
+        if (have_o) {
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {                     // rare path: keep its register footprint small
+                uint32_t oo[32];
+                tmem_ld_32x32(t_o + c * 32, oo);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) oo[i] = __float_as_uint(__uint_as_float(oo[i]) * alpha);
+                tmem_st_32x32(t_o + c * 32, oo);
+            }
+        }
+    }
+    const float neg_m = -m_run;
+    float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            float p0 = ex2_approx(fmaf(__uint_as_float(rr[c * 32 + i]), p.scale_log2, neg_m));
+            float p1 = ex2_approx(fmaf(__uint_as_float(rr[c * 32 + i + 1]), p.scale_log2, neg_m));
+            if (MASKED) {
+                p0 = (c * 32 + i < kv_valid) ? p0 : 0.f;
+                p1 = (c * 32 + i + 1 < kv_valid) ? p1 : 0.f;
+            }
+            ps0 += p0;
+            ps1 += p1;
+            pk[i >> 1] = pack16x2(p0, p1, p.fmt);
+        }
+        tmem_st_32x16(t_s + c * 16, pk);          // P aliases the S columns (all of S is in registers by now)
+    }
+    l_run += ps0 + ps1;
+    tmem_st_wait();
+}
+
+__global__ void __launch_bounds__(F2_THREADS, 1) smtl_fattn2_kernel(const __grid_constant__ FattnKParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sQ = smem;                                    // 2 tiles
+    uint8_t* sK = smem + 2 * TILE_BYTES;                   // NS stages
+    uint8_t* sV = sK + F2_NS * TILE_BYTES;                 // NS stages
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + F2_NS * TILE_BYTES);
+    uint64_t* q_full = bars + 0;
+    uint64_t* kv_full = bars + 1;                // [NS]
+    uint64_t* kv_empty = bars + 1 + F2_NS;       // [NS]
+    uint64_t* s_full = bars + 1 + 2 * F2_NS;     // [2]
+    uint64_t* p_full = s_full + 2;               // [2]
+    uint64_t* o_done = p_full + 2;               // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 2 * BQ;
+    const int b = blockIdx.y / p.heads;
+    const int hd = blockIdx.y - b * p.heads;
+    const int row_base = b * p.ntok;
+    const int ntiles = (p.ntok + BKV - 1) / BKV;
+    const bool has1 = (q0 + BQ) < p.ntok;
+
+    if (threadIdx.x == 0) {
+        if ((smem_u32(smem) & 1023u) != 0) { printf("smtl_fattn2: smem base not 1024-aligned\n"); __trap(); }
+        tma_prefetch_desc(&p.tm);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < F2_NS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        for (int w = 0; w < 2; ++w) { mbar_init(&s_full[w], 1); mbar_init(&p_full[w], 4); mbar_init(&o_done[w], 1); }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, F2_TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
+            tma_load_2d(sQ, &p.tm, q_full, p.q_col0 + hd * HD, row_base + q0);
+            tma_load_2d(sQ + TILE_BYTES, &p.tm, q_full, p.q_col0 + hd * HD, row_base + q0 + BQ);
+            for (int j = 0; j < ntiles; ++j) {
+                const int s = j % F2_NS;
+                mbar_wait(&kv_empty[s], ((j / F2_NS) & 1) ^ 1u);
+                mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
+                tma_load_2d(sK + s * TILE_BYTES, &p.tm, &kv_full[s], p.k_col0 + hd * HD, row_base + j * BKV);
+                tma_load_2d(sV + s * TILE_BYTES, &p.tm, &kv_full[s], p.v_col0 + hd * HD, row_base + j * BKV);
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t IDESC_S = make_idesc_16(BQ, BKV, 0, 0, p.fmt);   // S[128,128] = Q[128,64] K[128,64]^T
+        const uint32_t IDESC_O = make_idesc_16(BQ, HD, 0, 1, p.fmt);    // O[128,64] += P[128,128] V[128,64] (V MN-major)
+        const int ntile_q = has1 ? 2 : 1;
+        auto issue_s = [&](int w, int stage) {
+            const uint64_t dq = make_smem_desc_sw128(smem_u32(sQ + w * TILE_BYTES));
+            const uint64_t dk = make_smem_desc_sw128(smem_u32(sK + stage * TILE_BYTES));
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k) tc_mma_f16(tmem_base + w * 128, dq + 2 * k, dk + 2 * k, IDESC_S, k != 0);
+            tc_commit(&s_full[w]);
+        };
+        mbar_wait(q_full, 0);
+        mbar_wait(&kv_full[0], 0);
+        tc_fence_after();
+        if (lane == 0)
+            for (int w = 0; w < ntile_q; ++w) issue_s(w, 0);
+        __syncwarp();
+        for (int j = 0; j < ntiles; ++j) {
+            const int s = j % F2_NS;
+            const int sn = (j + 1) % F2_NS;
+            for (int w = 0; w < ntile_q; ++w) {
+                mbar_wait(&p_full[w], j & 1);                 // softmax wrote P_w(j) and rescaled O_w
+                if (w == 0 && j + 1 < ntiles) mbar_wait(&kv_full[sn], ((j + 1) / F2_NS) & 1);
+                tc_fence_after();
+                if (lane == 0) {
+#pragma unroll
+                    for (int k = 0; k < BKV / 16; ++k) {
+                        // V rows (kv) 16k .. 16k+16: 16 rows * 128 B = 2048 B per K step; P: 8 TMEM columns per step
+                        const uint64_t dv = make_smem_desc_sw128(smem_u32(sV + s * TILE_BYTES) + k * 16 * 128);
+                        tc_mma_f16_ts(tmem_base + 256 + w * 64, tmem_base + w * 128 + 8 * k, dv, IDESC_O, (j | k) != 0);
+                    }
+                    if (j + 1 < ntiles) issue_s(w, sn);       // in-order after PV_w(j): may overwrite P_w(j)
+                    else tc_commit(&o_done[w]);
+                }
+                __syncwarp();
+            }
+            if (lane == 0) tc_commit(&kv_empty[s]);            // K(j), V(j) consumed by every MMA issued so far
+            __syncwarp();
+        }
+    } else {
+        const int w = (warp - 2) >> 2;                         // which query tile
+        if (w == 0 || has1) {
+            const int quarter = warp & 3;                      // TMEM lane quarter this warp may access
+            const int r = quarter * 32 + lane;                 // query row within the tile == TMEM lane
+            const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+            const uint32_t t_s = tmem_base + w * 128 + lane_off;
+            const uint32_t t_o = tmem_base + 256 + w * 64 + lane_off;
+            float m_run = -INFINITY, l_run = 0.f;
+            const int tail = p.ntok - (ntiles - 1) * BKV;      // valid kv columns of the last tile
+            for (int j = 0; j < ntiles; ++j) {
+                mbar_wait(&s_full[w], j & 1);                  // S_w(j) ready; implies PV_w(j-1) retired
+                tc_fence_after();
+                if (j == ntiles - 1 && tail < BKV) softmax_tile<true>(p, t_s, tail, m_run, l_run, t_o, j > 0);
+                else softmax_tile<false>(p, t_s, BKV, m_run, l_run, t_o, j > 0);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[w]);
+            }
+            mbar_wait(&o_done[w], 0);
+            tc_fence_after();
+            const float inv = 1.0f / l_run;
+            const int qrow = q0 + w * BQ + r;
+            const bool row_ok = qrow < p.ntok;
+            uint16_t* dst = p.out + (int64_t)(row_base + qrow) * p.ldo + hd * HD;
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                uint32_t rr[32];
+                tmem_ld_32x32(t_o + c * 32, rr);
+                tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+                        uint4 o;
+                        o.x = pack16x2(__uint_as_float(rr[i]) * inv, __uint_as_float(rr[i + 1]) * inv, p.fmt);
+                        o.y = pack16x2(__uint_as_float(rr[i + 2]) * inv, __uint_as_float(rr[i + 3]) * inv, p.fmt);
+                        o.z = pack16x2(__uint_as_float(rr[i + 4]) * inv, __uint_as_float(rr[i + 5]) * inv, p.fmt);
+                        o.w = pack16x2(__uint_as_float(rr[i + 6]) * inv, __uint_as_float(rr[i + 7]) * inv, p.fmt);
+                        *reinterpret_cast<uint4*>(dst + c * 32 + i) = o;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, F2_TMEM_COLS);
+    }
+}
+
 }  // namespace
 
 extern "C" int smtl_fattn_plan(const smtl_fattn_args* a, smtl_fattn_op* op) {
@@ -240,10 +492,12 @@ extern "C" int smtl_fattn_plan(const smtl_fattn_args* a, smtl_fattn_op* op) {
                    "fattn_plan: unaligned leading dims / column offsets");
     memset(op, 0, sizeof(*op));
     op->args = *a;
-    op->grid_x = (a->ntok + BQ - 1) / BQ;
+    const char* v1 = getenv("SMTL_FATTN_V1");
+    const bool use_v1 = v1 && v1[0] == '1';
+    op->grid_x = use_v1 ? (a->ntok + BQ - 1) / BQ : (a->ntok + 2 * BQ - 1) / (2 * BQ);
     op->grid_y = a->batch * a->heads;
     SMTL_CHECK_ARG(op->grid_y <= 65535, "fattn_plan: batch*heads=%d exceeds grid.y", op->grid_y);
-    op->smem_bytes = FA_SMEM;
+    op->smem_bytes = use_v1 ? FA_SMEM : F2_SMEM;
     return smtl_host::encode_tmap_bf16_2d(op->tmap_qkv, a->qkv, (uint64_t)a->batch * a->ntok, (uint64_t)a->ld,
                                           (uint64_t)a->ld, 128);
 }
@@ -254,6 +508,8 @@ extern "C" int smtl_fattn_run(const smtl_fattn_op* op, void* stream) {
     if (!attr_set) {
         SMTL_CHECK_CUDA(
             cudaFuncSetAttribute(smtl_fattn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+        SMTL_CHECK_CUDA(
+            cudaFuncSetAttribute(smtl_fattn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
         attr_set = true;
     }
     const smtl_fattn_args& a = op->args;
@@ -268,7 +524,10 @@ extern "C" int smtl_fattn_run(const smtl_fattn_op* op, void* stream) {
     kp.fmt = a.fmt16;
     kp.ldo = a.ldo;
     kp.scale_log2 = a.scale * 1.4426950408889634f;
-    smtl_fattn_kernel<<<dim3(op->grid_x, op->grid_y), FA_THREADS, op->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(kp);
+    if (op->smem_bytes == F2_SMEM)
+        smtl_fattn2_kernel<<<dim3(op->grid_x, op->grid_y), F2_THREADS, op->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(kp);
+    else
+        smtl_fattn_kernel<<<dim3(op->grid_x, op->grid_y), FA_THREADS, op->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(kp);
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;
 }

@@ -205,53 +205,83 @@ __global__ void __launch_bounds__(256) gn_apply2_kernel(
     __syncthreads();
     const int cv8 = C >> 3;
     const int hp = pad_out ? h + 2 : h, wp = pad_out ? w + 2 : w;
-    const int64_t total = (int64_t)hp * wp * cv8;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-        const int pix = (int)(idx / cv8);
-        const int c = (int)(idx - (int64_t)pix * cv8) * 8;
-        int y = pix / wp, x = pix - y * wp;
-        uint4 o = make_uint4(0, 0, 0, 0), r = make_uint4(0, 0, 0, 0);
-        bool interior = true;
-        if (pad_out) {
-            interior = (y >= 1 && y <= h && x >= 1 && x <= w);
-            y -= 1; x -= 1;
-        }
-        if (interior) {
-            const void* src;
-            int ld, cc;
-            if (c < c0) { src = x0; ld = c0; cc = c; } else { src = x1; ld = c1; cc = c - c0; }
-            const int64_t eidx = ((int64_t)b * hw + (int64_t)y * w + x) * ld + cc;
-            float v[8];
-            if (x16) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(src) + eidx));
-                r = u;
-                float2 f;
-                f = unpack16x2(u.x, fmt); v[0] = f.x; v[1] = f.y;
-                f = unpack16x2(u.y, fmt); v[2] = f.x; v[3] = f.y;
-                f = unpack16x2(u.z, fmt); v[4] = f.x; v[5] = f.y;
-                f = unpack16x2(u.w, fmt); v[6] = f.x; v[7] = f.y;
-            } else {
-                load8(src, eidx, 0, fmt, v);
-                if (raw) {
-                    r.x = pack16x2(v[0], v[1], fmt); r.y = pack16x2(v[2], v[3], fmt);
-                    r.z = pack16x2(v[4], v[5], fmt); r.w = pack16x2(v[6], v[7], fmt);
+    const uint32_t total = (uint32_t)hp * wp * cv8;            // per image; < 2^31 (checked on the host)
+    constexpr int U = 4;                                       // independent 16-byte loads in flight per thread
+    const uint32_t step = gridDim.x * blockDim.x * U;
+    const int64_t in_base = (int64_t)b * hw;
+    const int64_t out_base = (int64_t)b * hp * wp;
+    for (uint32_t base = blockIdx.x * blockDim.x * U + threadIdx.x; base < total; base += step) {
+        uint4 u[U];
+        float4 f0[U], f1[U];
+        int cch[U];
+        uint32_t opix[U];
+        bool live[U], inter[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const uint32_t idx = base + k * blockDim.x;
+            live[k] = idx < total;
+            const uint32_t pix = idx / cv8;
+            const int c = (int)(idx - pix * cv8) * 8;
+            int y = pix / wp, x = pix - y * wp;
+            bool interior = live[k];
+            if (pad_out) {
+                interior = interior && (y >= 1 && y <= h && x >= 1 && x <= w);
+                y -= 1; x -= 1;
+            }
+            inter[k] = interior;
+            cch[k] = c;
+            opix[k] = pix;
+            u[k] = make_uint4(0, 0, 0, 0);
+            if (interior) {
+                const void* src;
+                int ld, cc;
+                if (c < c0) { src = x0; ld = c0; cc = c; } else { src = x1; ld = c1; cc = c - c0; }
+                const int64_t eidx = (in_base + (int64_t)y * w + x) * ld + cc;
+                if (x16) {
+                    u[k] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(src) + eidx));
+                } else {
+                    f0[k] = ldg4(reinterpret_cast<const float*>(src) + eidx);
+                    f1[k] = ldg4(reinterpret_cast<const float*>(src) + eidx + 4);
                 }
             }
-            const float4 s0 = *reinterpret_cast<const float4*>(scale + c), s1 = *reinterpret_cast<const float4*>(scale + c + 4);
-            const float4 h0 = *reinterpret_cast<const float4*>(shift + c), h1 = *reinterpret_cast<const float4*>(shift + c + 4);
-            v[0] = v[0] * s0.x + h0.x; v[1] = v[1] * s0.y + h0.y; v[2] = v[2] * s0.z + h0.z; v[3] = v[3] * s0.w + h0.w;
-            v[4] = v[4] * s1.x + h1.x; v[5] = v[5] * s1.y + h1.y; v[6] = v[6] * s1.z + h1.z; v[7] = v[7] * s1.w + h1.w;
-            if (do_silu) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = silu(v[i]);
-            }
-            o.x = pack16x2(v[0], v[1], fmt); o.y = pack16x2(v[2], v[3], fmt);
-            o.z = pack16x2(v[4], v[5], fmt); o.w = pack16x2(v[6], v[7], fmt);
         }
-        const int64_t orow = (int64_t)b * hp * wp + pix;
-        *reinterpret_cast<uint4*>(out + orow * C + c) = o;
-        if (raw) *reinterpret_cast<uint4*>(raw + orow * C + c) = r;
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            if (!live[k]) continue;
+            uint4 o = make_uint4(0, 0, 0, 0), r = make_uint4(0, 0, 0, 0);
+            const int c = cch[k];
+            if (inter[k]) {
+                float v[8];
+                if (x16) {
+                    r = u[k];
+                    float2 f;
+                    f = unpack16x2(u[k].x, fmt); v[0] = f.x; v[1] = f.y;
+                    f = unpack16x2(u[k].y, fmt); v[2] = f.x; v[3] = f.y;
+                    f = unpack16x2(u[k].z, fmt); v[4] = f.x; v[5] = f.y;
+                    f = unpack16x2(u[k].w, fmt); v[6] = f.x; v[7] = f.y;
+                } else {
+                    v[0] = f0[k].x; v[1] = f0[k].y; v[2] = f0[k].z; v[3] = f0[k].w;
+                    v[4] = f1[k].x; v[5] = f1[k].y; v[6] = f1[k].z; v[7] = f1[k].w;
+                    if (raw) {
+                        r.x = pack16x2(v[0], v[1], fmt); r.y = pack16x2(v[2], v[3], fmt);
+                        r.z = pack16x2(v[4], v[5], fmt); r.w = pack16x2(v[6], v[7], fmt);
+                    }
+                }
+                const float4 s0 = *reinterpret_cast<const float4*>(scale + c), s1 = *reinterpret_cast<const float4*>(scale + c + 4);
+                const float4 h0 = *reinterpret_cast<const float4*>(shift + c), h1 = *reinterpret_cast<const float4*>(shift + c + 4);
+                v[0] = v[0] * s0.x + h0.x; v[1] = v[1] * s0.y + h0.y; v[2] = v[2] * s0.z + h0.z; v[3] = v[3] * s0.w + h0.w;
+                v[4] = v[4] * s1.x + h1.x; v[5] = v[5] * s1.y + h1.y; v[6] = v[6] * s1.z + h1.z; v[7] = v[7] * s1.w + h1.w;
+                if (do_silu) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = silu(v[i]);
+                }
+                o.x = pack16x2(v[0], v[1], fmt); o.y = pack16x2(v[2], v[3], fmt);
+                o.z = pack16x2(v[4], v[5], fmt); o.w = pack16x2(v[6], v[7], fmt);
+            }
+            const int64_t orow = out_base + opix[k];
+            *reinterpret_cast<uint4*>(out + orow * C + c) = o;
+            if (raw) *reinterpret_cast<uint4*>(raw + orow * C + c) = r;
+        }
     }
 }
 
@@ -693,8 +723,9 @@ extern "C" int smtl_gnapply_run(const smtl_gnapply_args* a, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int hp = a->pad_out ? a->h + 2 : a->h, wp = a->pad_out ? a->w + 2 : a->w;
     const int64_t per_img = (int64_t)hp * wp * (C / 8);
+    SMTL_CHECK_ARG(per_img < ((int64_t)1 << 31), "gnapply: image too large");
     int bpi = (int)((per_img + 256 * 4 - 1) / (256 * 4));
-    const int cap = (148 * 8 + a->batch - 1) / a->batch;
+    const int cap = (148 * 16 + a->batch - 1) / a->batch;
     if (bpi > cap) bpi = cap;
     if (bpi < 1) bpi = 1;
     const size_t smem = (2 * C + 2 * a->groups) * sizeof(float);
