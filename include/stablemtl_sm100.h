@@ -98,6 +98,8 @@ typedef struct smtl_gemm_args {
     float* stats;
     int32_t stats_rows_per_image;
     int32_t stats_images;
+    int32_t cta_group;  /* 0 = auto; 1 = one CTA per 128-row tile; 2 = CTA pair per 256-row tile (tcgen05 cta_group::2) */
+    int32_t pad_;
 } smtl_gemm_args;
 
 typedef struct smtl_gemm_op {
@@ -110,6 +112,8 @@ typedef struct smtl_gemm_op {
     int32_t tiles_m, tiles_n;
     int32_t total_kblocks;
     int32_t smem_bytes;
+    int32_t cta_group;
+    int32_t pad_;
 } smtl_gemm_op;
 
 int smtl_gemm_plan(const smtl_gemm_args* args, smtl_gemm_op* op);

@@ -51,12 +51,15 @@ def gemm_case(name, m, n, k, **kw):
     report(f"gemm {name} m={m} n={n} k={k}", ops.gemm(a, b, out_f32=out, **kw))
 
 
-def conv_case(name, batch, h, w, cin, cout):
+def conv_case(name, batch, h, w, cin, cout, **kw):
+    """the in-pipeline form: 16-bit output + fused GroupNorm statistics"""
     a = rb(batch * (h + 2) * (w + 2), cin)
     wm = rb(cout, 9 * cin)
-    out = torch.empty(batch * h * w, cout, device=DEV)
+    out = torch.empty(batch * h * w, cout, device=DEV, dtype=ops.h16())
     bias = torch.zeros(cout, device=DEV)
-    report(f"conv3x3 {name} b={batch} {h}x{w} {cin}->{cout}", ops.conv3x3(a, wm, batch, h, w, bias=bias, out_f32=out))
+    st = ops.new_stats(batch, cout, DEV)
+    report(f"conv3x3 {name} b={batch} {h}x{w} {cin}->{cout}",
+           ops.conv3x3(a, wm, batch, h, w, bias=bias, out_bf16=out, stats=st, stats_rows_per_image=h * w, **kw))
 
 
 def attn_case(batch, ntok, heads):
@@ -66,8 +69,41 @@ def attn_case(batch, ntok, heads):
     report(f"flash_attn b={batch} ntok={ntok} heads={heads}", ops.flash_attn(qkv, batch, ntok, heads, out, 0, c, 2 * c))
 
 
+def gn_case(batch, h, w, c, pad=True):
+    x = rb(batch * h * w, c)
+    st = ops.new_stats(batch, c, DEV)
+    st[0, :, :, 0] = 0.0
+    st[0, :, :, 1] = float(h * w)
+    g, b = torch.ones(c, device=DEV), torch.zeros(c, device=DEV)
+    rows = batch * (h + 2) * (w + 2) if pad else batch * h * w
+    out = torch.empty(rows, c, device=DEV, dtype=ops.h16())
+    op = ops.gn_apply(x, st, batch, h, w, g, b, out, eps=1e-6, silu=True, pad_out=pad)
+    ms = timeit(op)
+    gb = (x.numel() + out.numel()) * 2 / 1e9
+    print(f"gn_apply b={batch} {h}x{w} c={c:4d}                              {ms:9.3f} ms {gb / ms * 1e3:8.1f} GB/s  "
+          f"{gb / ms * 1e3 / 6552.6 * 100:5.1f}% of measured HBM copy peak", flush=True)
+
+
 if __name__ == "__main__":
     only = sys.argv[1] if len(sys.argv) > 1 else ""
+    if only == "gemm":
+        for cg in (1, 2):
+            print(f"--- cta_group {cg}")
+            gemm_case("square", 8192, 8192, 8192, cta_group=cg)
+            gemm_case("ff1 L0", 112 * 4800, 2560, 320, cta_group=cg)
+            gemm_case("lin L0", 112 * 4800, 320, 320, cta_group=cg)
+            conv_case("unet L0", 16, 60, 80, 320, 320, cta_group=cg)
+            conv_case("unet L2", 16, 15, 20, 1280, 1280, cta_group=cg)
+            conv_case("vae 1/1", 8, 480, 640, 128, 128, cta_group=cg)
+            conv_case("vae 1/2", 8, 240, 320, 256, 256, cta_group=cg)
+            conv_case("vae 1/2 512->256", 8, 240, 320, 512, 256, cta_group=cg)
+            conv_case("vae 1/4", 8, 120, 160, 512, 512, cta_group=cg)
+            conv_case("vae 1/8", 8, 60, 80, 512, 512, cta_group=cg)
+        sys.exit(0)
+    if only == "elem":
+        for args in [(8, 480, 640, 128), (8, 240, 320, 256), (8, 120, 160, 512), (8, 60, 80, 512), (112, 60, 80, 320)]:
+            gn_case(*args)
+        sys.exit(0)
     if only == "attn":
         for args in [(16, 4800, 5), (112, 4800, 5), (112, 1200, 10), (112, 300, 20), (112, 80, 20)]:
             attn_case(*args)

@@ -52,6 +52,7 @@ class GemmArgs(C.Structure):
         ("res_fmt16", i32), ("stats_replicas", i32),
         ("stats", vp),
         ("stats_rows_per_image", i32), ("stats_images", i32),
+        ("cta_group", i32), ("pad_", i32),
     ]
 
 
@@ -60,7 +61,7 @@ class GemmOp(C.Structure):
         ("args", GemmArgs),
         ("tmap_a0", C.c_uint64 * 16), ("tmap_a1", C.c_uint64 * 16), ("tmap_b", C.c_uint64 * 16),
         ("block_n", i32), ("grid", i32), ("tiles_m", i32), ("tiles_n", i32),
-        ("total_kblocks", i32), ("smem_bytes", i32),
+        ("total_kblocks", i32), ("smem_bytes", i32), ("cta_group", i32), ("pad_", i32),
     ]
 
 

@@ -154,11 +154,12 @@ __global__ void gn_apply_kernel(const float* __restrict__ x0, const float* __res
 
 // GroupNorm apply from producer-side per-(image, channel) statistics (smtl_gemm_args.stats): one streaming pass.
 // grid (blocks_per_image, batch), 256 threads; each thread handles 8 channels of one (padded) pixel per step.
-__global__ void __launch_bounds__(256) gn_apply2_kernel(
-    const void* __restrict__ x0, const void* __restrict__ x1, int c0, int c1, int x16, const float* __restrict__ st0,
+template <bool x16>
+__global__ void __launch_bounds__(320, 3) gn_apply2_kernel(
+    const void* __restrict__ x0, const void* __restrict__ x1, int c0, int c1, const float* __restrict__ st0,
     const float* __restrict__ st1, int replicas, int batch, int h, int w, int groups, float eps,
     const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu, int pad_out,
-    uint16_t* __restrict__ out, uint16_t* __restrict__ raw, int fmt) {
+    uint16_t* __restrict__ out, uint16_t* __restrict__ raw, int fmt, FastDiv div_wp) {
     extern __shared__ float sm[];   // scale[C], shift[C], gmean[groups], grstd[groups]
     const int C = c0 + c1;
     float* scale = sm;              // first used as per-channel sum
@@ -203,39 +204,41 @@ __global__ void __launch_bounds__(256) gn_apply2_kernel(
         shift[c] = beta[c] - gmean[g] * sc;
     }
     __syncthreads();
+    // blockDim.x is a multiple of C/8 (host): a thread owns ONE 8-channel vector for the whole kernel, so its
+    // scale/shift live in registers and the only index arithmetic left per pixel is pixel -> (y, x).
     const int cv8 = C >> 3;
     const int hp = pad_out ? h + 2 : h, wp = pad_out ? w + 2 : w;
-    const uint32_t total = (uint32_t)hp * wp * cv8;            // per image; < 2^31 (checked on the host)
+    const uint32_t npix = (uint32_t)hp * wp;                   // per image
+    const int ppb = blockDim.x / cv8;                          // pixels one block covers per step
+    const int cvi = threadIdx.x % cv8;
+    const int pl = threadIdx.x / cv8;
+    const int c = cvi * 8;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sc[i] = scale[c + i]; sh[i] = shift[c + i]; }
+    const void* src;
+    int ld, cc;
+    if (c < c0) { src = x0; ld = c0; cc = c; } else { src = x1; ld = c1; cc = c - c0; }
     constexpr int U = 4;                                       // independent 16-byte loads in flight per thread
-    const uint32_t step = gridDim.x * blockDim.x * U;
     const int64_t in_base = (int64_t)b * hw;
-    const int64_t out_base = (int64_t)b * hp * wp;
-    for (uint32_t base = blockIdx.x * blockDim.x * U + threadIdx.x; base < total; base += step) {
+    const int64_t out_base = (int64_t)b * npix;
+    for (uint32_t p0 = blockIdx.x * U * ppb + pl; p0 < npix; p0 += gridDim.x * U * ppb) {
         uint4 u[U];
         float4 f0[U], f1[U];
-        int cch[U];
-        uint32_t opix[U];
         bool live[U], inter[U];
 #pragma unroll
         for (int k = 0; k < U; ++k) {
-            const uint32_t idx = base + k * blockDim.x;
-            live[k] = idx < total;
-            const uint32_t pix = idx / cv8;
-            const int c = (int)(idx - pix * cv8) * 8;
-            int y = pix / wp, x = pix - y * wp;
+            const uint32_t pix = p0 + k * ppb;
+            live[k] = pix < npix;
+            int y = (int)fastdiv(pix, div_wp), x = (int)pix - y * wp;
             bool interior = live[k];
             if (pad_out) {
                 interior = interior && (y >= 1 && y <= h && x >= 1 && x <= w);
                 y -= 1; x -= 1;
             }
             inter[k] = interior;
-            cch[k] = c;
-            opix[k] = pix;
             u[k] = make_uint4(0, 0, 0, 0);
             if (interior) {
-                const void* src;
-                int ld, cc;
-                if (c < c0) { src = x0; ld = c0; cc = c; } else { src = x1; ld = c1; cc = c - c0; }
                 const int64_t eidx = (in_base + (int64_t)y * w + x) * ld + cc;
                 if (x16) {
                     u[k] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(src) + eidx));
@@ -249,7 +252,6 @@ __global__ void __launch_bounds__(256) gn_apply2_kernel(
         for (int k = 0; k < U; ++k) {
             if (!live[k]) continue;
             uint4 o = make_uint4(0, 0, 0, 0), r = make_uint4(0, 0, 0, 0);
-            const int c = cch[k];
             if (inter[k]) {
                 float v[8];
                 if (x16) {
@@ -267,18 +269,16 @@ __global__ void __launch_bounds__(256) gn_apply2_kernel(
                         r.z = pack16x2(v[4], v[5], fmt); r.w = pack16x2(v[6], v[7], fmt);
                     }
                 }
-                const float4 s0 = *reinterpret_cast<const float4*>(scale + c), s1 = *reinterpret_cast<const float4*>(scale + c + 4);
-                const float4 h0 = *reinterpret_cast<const float4*>(shift + c), h1 = *reinterpret_cast<const float4*>(shift + c + 4);
-                v[0] = v[0] * s0.x + h0.x; v[1] = v[1] * s0.y + h0.y; v[2] = v[2] * s0.z + h0.z; v[3] = v[3] * s0.w + h0.w;
-                v[4] = v[4] * s1.x + h1.x; v[5] = v[5] * s1.y + h1.y; v[6] = v[6] * s1.z + h1.z; v[7] = v[7] * s1.w + h1.w;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], sc[i], sh[i]);
                 if (do_silu) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = silu(v[i]);
+                    for (int i = 0; i < 8; ++i) v[i] = silu_fast(v[i]);
                 }
                 o.x = pack16x2(v[0], v[1], fmt); o.y = pack16x2(v[2], v[3], fmt);
                 o.z = pack16x2(v[4], v[5], fmt); o.w = pack16x2(v[6], v[7], fmt);
             }
-            const int64_t orow = out_base + opix[k];
+            const int64_t orow = out_base + p0 + k * ppb;
             *reinterpret_cast<uint4*>(out + orow * C + c) = o;
             if (raw) *reinterpret_cast<uint4*>(raw + orow * C + c) = r;
         }
@@ -722,17 +722,22 @@ extern "C" int smtl_gnapply_run(const smtl_gnapply_args* a, void* stream) {
     SMTL_CHECK_ARG(a->batch >= 1 && a->h >= 1 && a->w >= 1 && a->stats_replicas >= 1, "gnapply: bad extent");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int hp = a->pad_out ? a->h + 2 : a->h, wp = a->pad_out ? a->w + 2 : a->w;
-    const int64_t per_img = (int64_t)hp * wp * (C / 8);
-    SMTL_CHECK_ARG(per_img < ((int64_t)1 << 31), "gnapply: image too large");
-    int bpi = (int)((per_img + 256 * 4 - 1) / (256 * 4));
+    const int cv8 = C / 8;
+    SMTL_CHECK_ARG(cv8 <= 320, "gnapply: C=%d too wide", C);
+    SMTL_CHECK_ARG((int64_t)hp * wp < ((int64_t)1 << 31), "gnapply: image too large");
+    const int threads = (cv8 > 256) ? cv8 : (256 / cv8) * cv8;        // a multiple of C/8: thread <-> fixed channels
+    const int ppb = threads / cv8;
+    const int64_t steps = ((int64_t)hp * wp + (int64_t)ppb * 4 - 1) / ((int64_t)ppb * 4);
+    int bpi = (int)steps;
     const int cap = (148 * 16 + a->batch - 1) / a->batch;
     if (bpi > cap) bpi = cap;
     if (bpi < 1) bpi = 1;
     const size_t smem = (2 * C + 2 * a->groups) * sizeof(float);
-    gn_apply2_kernel<<<dim3(bpi, a->batch), 256, smem, st>>>(
-        a->x0, a->x1, a->c0, a->c1, a->x_fmt16, a->stats0, a->stats1, a->stats_replicas, a->batch, a->h, a->w,
+    auto kern = a->x_fmt16 ? gn_apply2_kernel<true> : gn_apply2_kernel<false>;
+    kern<<<dim3(bpi, a->batch), threads, smem, st>>>(
+        a->x0, a->x1, a->c0, a->c1, a->stats0, a->stats1, a->stats_replicas, a->batch, a->h, a->w,
         a->groups, a->eps, a->gamma, a->beta, a->silu, a->pad_out, reinterpret_cast<uint16_t*>(a->out_bf16),
-        reinterpret_cast<uint16_t*>(a->raw_bf16), a->fmt16);
+        reinterpret_cast<uint16_t*>(a->raw_bf16), a->fmt16, make_fastdiv((uint32_t)wp));
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;
 }

@@ -12,6 +12,7 @@
 // 1x1 shortcut conv (src/model/resnet.py:172,200).
 #include "smtl_common.cuh"
 #include "smtl_host.h"
+#include <stdlib.h>
 
 namespace {
 
@@ -295,9 +296,13 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t tad
     }
 }
 
-template <int BN>
+// CG = 1: one CTA per 128-row tile.  CG = 2: a CTA PAIR (2-SM cluster) per 256-row tile -- each CTA stages its own
+// 128 A rows and HALF of the B tile, the leader issues tcgen05.mma.cta_group::2 (M = 256) and each CTA's TMEM
+// receives its 128 accumulator rows: half the shared-memory and L2 operand traffic per flop.
+template <int BN, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_constant__ GemmKParams p) {
-    constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
+    constexpr int B_ROWS = BN / CG;                                   // B rows this CTA stages
+    constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
     constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     constexpr int TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
     constexpr int ACC_STRIDE = TMEM_COLS / 2;
@@ -307,14 +312,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stages = p.stages;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * STAGE_BYTES);
-    uint64_t* full_bar = bars;                       // [stages]   TMA -> MMA
-    uint64_t* empty_bar = bars + MAX_STAGES;         // [stages]   MMA -> TMA
-    uint64_t* acc_full = bars + 2 * MAX_STAGES;      // [2]        MMA -> epilogue
-    uint64_t* acc_empty = bars + 2 * MAX_STAGES + 2; // [2]        epilogue -> MMA
+    uint64_t* full_bar = bars;                       // [stages]   TMA (both CTAs) -> MMA (leader)
+    uint64_t* empty_bar = bars + MAX_STAGES;         // [stages]   MMA -> TMA (each CTA its own)
+    uint64_t* acc_full = bars + 2 * MAX_STAGES;      // [2]        MMA -> epilogue (each CTA its own)
+    uint64_t* acc_empty = bars + 2 * MAX_STAGES + 2; // [2]        epilogue (both CTAs) -> MMA (leader)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const bool leader = (rank == 0);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tm_a0);
@@ -326,30 +333,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_empty[s], 4);   // one arrive per epilogue warp
+            mbar_init(&acc_empty[s], 4 * CG);   // one arrive per epilogue warp of every CTA of the pair
         }
         fence_mbar_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_alloc(tmem_slot, TMEM_COLS);       // each CTA allocates its whole accumulator space: same address in both
         tmem_relinquish();
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int num_tiles = p.tiles_m * p.tiles_n;
+    const int num_tiles = p.tiles_m * p.tiles_n;     // tiles_m counts (128 * CG)-row blocks
+    const int tile0 = blockIdx.x / CG;
+    const int tile_step = gridDim.x / CG;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
-                const int64_t m0 = (int64_t)tm * BLOCK_M;
-                const int n0 = tn * BN;
+                const int64_t m0 = ((int64_t)tm * CG + rank) * BLOCK_M;
+                const int n0 = tn * BN + (int)rank * B_ROWS;
                 int kb_global = 0;
                 for (int s = 0; s < p.nseg; ++s) {
                     const smtl_gemm_seg sg = p.seg[s];
@@ -359,43 +368,62 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
                         mbar_wait(&empty_bar[stage], phase ^ 1u);
                         uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
                         uint8_t* sb = sa + A_STAGE_BYTES;
-                        mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-                        tma_load_2d(sa, tma, &full_bar[stage], sg.a_col0 + kb * BLOCK_K, arow);
-                        tma_load_2d(sb, &p.tm_b, &full_bar[stage], kb_global * BLOCK_K, n0);
+                        if (CG == 1) {
+                            mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                            tma_load_2d(sa, tma, &full_bar[stage], sg.a_col0 + kb * BLOCK_K, arow);
+                            tma_load_2d(sb, &p.tm_b, &full_bar[stage], kb_global * BLOCK_K, n0);
+                        } else {
+                            // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of both
+                            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+                            const uint32_t bar = mapa_u32(&full_bar[stage], 0);
+                            tma_load_2d_pair(sa, tma, bar, sg.a_col0 + kb * BLOCK_K, arow);
+                            tma_load_2d_pair(sb, &p.tm_b, bar, kb_global * BLOCK_K, n0);
+                        }
                         if (++stage == stages) { stage = 0; phase ^= 1u; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        const uint32_t IDESC = make_idesc_16(BLOCK_M, BN, 0, 0, p.fmt);
-        int stage = 0;
-        uint32_t phase = 0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
-            mbar_wait(&acc_empty[acc], acc_phase ^ 1u);
-            tc_fence_after();
-            const uint32_t tmem_d = tmem_base + acc * ACC_STRIDE;
-            for (int kb = 0; kb < p.total_kb; ++kb) {
-                mbar_wait(&full_bar[stage], phase);
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (leader) {
+            const uint32_t IDESC = make_idesc_16(BLOCK_M * CG, BN, 0, 0, p.fmt);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&acc_empty[acc], acc_phase ^ 1u);
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-                    const uint64_t da = make_smem_desc_sw128(sa);
-                    const uint64_t db = make_smem_desc_sw128(sa + A_STAGE_BYTES);
+                const uint32_t tmem_d = tmem_base + acc * ACC_STRIDE;
+                for (int kb = 0; kb < p.total_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+                        const uint64_t da = make_smem_desc_sw128(sa);
+                        const uint64_t db = make_smem_desc_sw128(sa + A_STAGE_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / 16; ++k) {
-                        // +32 B per 16-element K step inside the swizzle atom: start-address field += 2
-                        tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
+                        for (int k = 0; k < BLOCK_K / 16; ++k) {
+                            // +32 B per 16-element K step inside the swizzle atom: start-address field += 2
+                            if (CG == 1)
+                                tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
+                            else
+                                tc_mma_f16_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC,
+                                                (kb | k) != 0);
+                        }
+                        if (CG == 1) {
+                            tc_commit(&empty_bar[stage]);                       // smem slot free once these MMAs retire
+                            if (kb == p.total_kb - 1) tc_commit(&acc_full[acc]); // accumulator ready
+                        } else {
+                            tc_commit_pair(&empty_bar[stage]);
+                            if (kb == p.total_kb - 1) tc_commit_pair(&acc_full[acc]);
+                        }
                     }
-                    tc_commit(&empty_bar[stage]);                       // smem slot free once these MMAs retire
-                    if (kb == p.total_kb - 1) tc_commit(&acc_full[acc]); // accumulator ready
+                    __syncwarp();
+                    if (++stage == stages) { stage = 0; phase ^= 1u; }
                 }
-                __syncwarp();
-                if (++stage == stages) { stage = 0; phase ^= 1u; }
             }
         }
     } else {
@@ -403,42 +431,66 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
         const int row_in_tile = quarter * 32 + lane;
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
             EpiRow<BN> er;
-            epilogue_prepare<BN>(p, (int64_t)tm * BLOCK_M + row_in_tile, tn, lane, er);
+            epilogue_prepare<BN>(p, ((int64_t)tm * CG + rank) * BLOCK_M + row_in_tile, tn, lane, er);
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
             epilogue_rows<BN>(p, taddr, tn, lane, er);
-            // release this accumulator stage back to the MMA warp
+            // release this accumulator stage back to the (leader's) MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+            if (lane == 0) {
+                if (CG == 1) mbar_arrive(&acc_empty[acc]);
+                else mbar_arrive_cluster(mapa_u32(&acc_empty[acc], 0));
+            }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
-template <int BN>
+template <int BN, int CG>
 int launch_gemm(const GemmKParams& kp, int grid, int smem_bytes, cudaStream_t stream) {
     static bool attr_set = false;   // per-instantiation; benign race (idempotent)
     if (!attr_set) {
-        SMTL_CHECK_CUDA(cudaFuncSetAttribute(smtl_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        SMTL_CHECK_CUDA(cudaFuncSetAttribute(smtl_gemm_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              SMEM_BUDGET));
         attr_set = true;
     }
-    smtl_gemm_kernel<BN><<<grid, NUM_THREADS, smem_bytes, stream>>>(kp);
+    if (CG == 1) {
+        smtl_gemm_kernel<BN, CG><<<grid, NUM_THREADS, smem_bytes, stream>>>(kp);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid, 1, 1);
+        cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        SMTL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, smtl_gemm_kernel<BN, CG>, kp));
+    }
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;
+}
+
+template <int BN>
+int launch_gemm_cg(const GemmKParams& kp, int cg, int grid, int smem_bytes, cudaStream_t stream) {
+    return cg == 2 ? launch_gemm<BN, 2>(kp, grid, smem_bytes, stream) : launch_gemm<BN, 1>(kp, grid, smem_bytes, stream);
 }
 
 int pick_block_n(int n, int act) {
@@ -505,17 +557,30 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
     }
     SMTL_CHECK_ARG(g.m + 4096 < (int64_t)1 << 31, "gemm_plan: m too large for 32-bit TMA coordinates");
 
+    // CTA pairs (tcgen05 cta_group::2, 256-row tiles) whenever there are enough rows to fill the machine with them
+    int cg = g.cta_group;
+    const int sms = smtl_host::num_sms();
+    if (cg == 0) {
+        const long long tiles256 = ((g.m + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (long long)((g.n + bn - 1) / bn);
+        const char* env = getenv("SMTL_GEMM_CG");
+        // measured on B200 (scripts/bench_kernels.py gemm): pairs win on long plain-K GEMMs (8192^3: 1170 -> 1295
+        // TFLOP/s) and lose on the 9-segment implicit convs and on short-K linears, whose cost is the epilogue
+        cg = env ? atoi(env) : ((tiles256 >= sms / 2 && g.nseg == 1 && g.k >= 2048 && g.n >= 256) ? 2 : 1);
+    }
+    SMTL_CHECK_ARG(cg == 1 || cg == 2, "gemm_plan: cta_group %d", cg);
+    SMTL_CHECK_ARG(cg == 1 || bn % 16 == 0, "gemm_plan: cta_group 2 needs block_n %% 16 == 0");
+    op->cta_group = cg;
     op->block_n = bn;
-    op->tiles_m = (int)((g.m + BLOCK_M - 1) / BLOCK_M);
+    op->tiles_m = (int)((g.m + cg * BLOCK_M - 1) / (cg * BLOCK_M));
     op->tiles_n = (g.n + bn - 1) / bn;
     op->total_kblocks = total_kb;
-    const int stage_bytes = A_STAGE_BYTES + bn * BLOCK_K * 2;
+    const int stage_bytes = A_STAGE_BYTES + (bn / cg) * BLOCK_K * 2;
     int stages = (SMEM_BUDGET - 1024 - 512) / stage_bytes;
     if (stages > 8) stages = 8;
     op->smem_bytes = 1024 + stages * stage_bytes + 512;
     const long long tiles = (long long)op->tiles_m * op->tiles_n;
-    const int sms = smtl_host::num_sms();
-    op->grid = (int)(tiles < sms ? tiles : sms);
+    const int slots = sms / cg;                     // CTAs (cg = 1) or CTA pairs (cg = 2) resident at once
+    op->grid = (int)(tiles < slots ? tiles : slots) * cg;
 
     int rc = smtl_host::encode_tmap_bf16_2d(op->tmap_a0, g.a0, (uint64_t)g.a0_rows, (uint64_t)g.a0_cols,
                                             (uint64_t)g.a0_ld, BLOCK_M);
@@ -527,7 +592,8 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
     } else {
         memcpy(op->tmap_a1, op->tmap_a0, sizeof(op->tmap_a0));
     }
-    rc = smtl_host::encode_tmap_bf16_2d(op->tmap_b, g.b, (uint64_t)g.n, (uint64_t)g.k, (uint64_t)g.ldb, (uint32_t)bn);
+    rc = smtl_host::encode_tmap_bf16_2d(op->tmap_b, g.b, (uint64_t)g.n, (uint64_t)g.k, (uint64_t)g.ldb,
+                                        (uint32_t)(bn / cg));
     return rc;
 }
 
@@ -544,7 +610,8 @@ extern "C" int smtl_gemm_run(const smtl_gemm_op* op, void* stream) {
     kp.tiles_m = op->tiles_m;
     kp.tiles_n = op->tiles_n;
     kp.total_kb = op->total_kblocks;
-    const int stage_bytes = A_STAGE_BYTES + op->block_n * BLOCK_K * 2;
+    const int cg = op->cta_group == 2 ? 2 : 1;
+    const int stage_bytes = A_STAGE_BYTES + (op->block_n / cg) * BLOCK_K * 2;
     kp.stages = (op->smem_bytes - 1024 - 512) / stage_bytes;
     kp.nseg = g.nseg;
     for (int s = 0; s < SMTL_MAX_SEG; ++s) kp.seg[s] = g.seg[s];
@@ -570,13 +637,13 @@ extern "C" int smtl_gemm_run(const smtl_gemm_op* op, void* stream) {
     kp.fmt = g.fmt16;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     switch (op->block_n) {
-        case 32: return launch_gemm<32>(kp, op->grid, op->smem_bytes, st);
-        case 64: return launch_gemm<64>(kp, op->grid, op->smem_bytes, st);
-        case 128: return launch_gemm<128>(kp, op->grid, op->smem_bytes, st);
-        case 160: return launch_gemm<160>(kp, op->grid, op->smem_bytes, st);
-        case 192: return launch_gemm<192>(kp, op->grid, op->smem_bytes, st);
-        case 224: return launch_gemm<224>(kp, op->grid, op->smem_bytes, st);
-        case 256: return launch_gemm<256>(kp, op->grid, op->smem_bytes, st);
+        case 32: return launch_gemm_cg<32>(kp, cg, op->grid, op->smem_bytes, st);
+        case 64: return launch_gemm_cg<64>(kp, cg, op->grid, op->smem_bytes, st);
+        case 128: return launch_gemm_cg<128>(kp, cg, op->grid, op->smem_bytes, st);
+        case 160: return launch_gemm_cg<160>(kp, cg, op->grid, op->smem_bytes, st);
+        case 192: return launch_gemm_cg<192>(kp, cg, op->grid, op->smem_bytes, st);
+        case 224: return launch_gemm_cg<224>(kp, cg, op->grid, op->smem_bytes, st);
+        case 256: return launch_gemm_cg<256>(kp, cg, op->grid, op->smem_bytes, st);
         default: smtl_host::set_error("gemm_run: bad block_n %d", op->block_n); return SMTL_EINVAL;
     }
 }

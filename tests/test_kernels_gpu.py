@@ -430,3 +430,74 @@ def test_upsample_and_im2col_take_16bit_input():
     cols = F.unfold(x.float().permute(0, 3, 1, 2), 3, padding=1, stride=2)
     cols = cols.reshape(b, c, 9, oh * ow).permute(0, 3, 2, 1).reshape(b * oh * ow, 9 * c)
     assert torch.equal(col.float(), cols)
+
+
+# ------------------------------------------------------------------ CTA-pair (tcgen05 cta_group::2) variant
+@pytest.mark.parametrize("m,n,k,bn", [(256, 256, 64, 0), (1000, 640, 1280, 0), (4800, 1280, 320, 0), (130, 4, 576, 0),
+                                      (777, 96, 200, 0), (20000, 320, 2880, 0), (4096, 512, 512, 128), (600, 128, 576, 0),
+                                      (2000, 448, 256, 224), (5000, 384, 384, 192)])
+def test_gemm_cta_pair(m, n, k, bn):
+    ops, L = _ops()
+    kp = (k + 7) // 8 * 8
+    a = rnd(m, kp, seed=1).to(H16())[:, :k]
+    b = rnd(n, kp, scale=k ** -0.5, seed=2).to(H16())[:, :k]
+    bias = rnd(n, seed=3)
+    res = rnd(m, n, seed=4)
+    out = torch.full((m, n), float("nan"), device=DEV)
+    ops.gemm(a, b, bias=bias, res1=res, out_f32=out, block_n=bn, cta_group=2).run()
+    torch.cuda.synchronize()
+    ref = a.float() @ b.float().t() + bias + res
+    err = rel_l2(out, ref)
+    assert err < 2e-5, f"gemm(cta pair) {m}x{n}x{k}: rel-L2 {err}"
+
+
+def test_gemm_cta_pair_geglu_and_stats():
+    ops, L = _ops()
+    from stablemtl_b200.weights import interleave_geglu
+    m, c = 1300, 320
+    a = rnd(m, c, seed=1).to(H16())
+    w = rnd(8 * c, c, scale=c ** -0.5, seed=2).to(H16())
+    bias = rnd(8 * c, seed=3)
+    wi, bi = interleave_geglu(w, bias)
+    out = torch.empty(m, 4 * c, device=DEV, dtype=H16())
+    ops.gemm(a, wi, bias=bi, act=L.ACT_GEGLU, out_bf16=out, cta_group=2).run()
+    h = a.float() @ w.float().t() + bias
+    assert rel_l2(out.float(), h[:, :4 * c] * F.gelu(h[:, 4 * c:])) < 4e-3
+    # statistics + 16-bit residual through the pair kernel
+    n, k, rpi = 640, 320, 325
+    b2 = rnd(n, k, scale=k ** -0.5, seed=5).to(H16())
+    res = rnd(m, n, seed=6).to(H16())
+    stats = ops.new_stats(4, n, DEV)
+    o2 = torch.empty(m, n, device=DEV, dtype=H16())
+    ops.gemm(a, b2, res1=res, out_bf16=o2, stats=stats, stats_rows_per_image=rpi, cta_group=2).run()
+    torch.cuda.synchronize()
+    ref = a.float() @ b2.float().t() + res.float()
+    assert rel_l2(o2.float(), ref) < 4e-3
+    st = stats.sum(0)
+    for img in range(4):
+        blk = ref[img * rpi:(img + 1) * rpi].double()
+        assert rel_l2(st[img, :, 0], blk.sum(0)) < 1e-4 and rel_l2(st[img, :, 1], (blk * blk).sum(0)) < 1e-4
+
+
+@pytest.mark.parametrize("b,h,w,cin,cout,cs", [(2, 8, 10, 64, 64, 0), (3, 15, 20, 320, 640, 0), (2, 30, 40, 640, 320, 960),
+                                               (1, 60, 80, 128, 128, 0)])
+def test_conv3x3_cta_pair(b, h, w, cin, cout, cs):
+    ops, L = _ops()
+    x = rnd(b, h, w, cin, seed=1).to(H16())
+    wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=2).to(H16())
+    bias = rnd(cout, seed=3)
+    res = rnd(b * h * w, cout, seed=4)
+    wmat = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1)
+    xs = None
+    if cs:
+        xs_nhwc = rnd(b, h, w, cs, seed=5).to(H16())
+        ws = rnd(cout, cs, scale=cs ** -0.5, seed=6).to(H16())
+        wmat = torch.cat([wmat, ws], dim=1)
+        ref = ref + F.conv2d(xs_nhwc.float().permute(0, 3, 1, 2), ws.float()[:, :, None, None])
+        xs = _pad_layout(xs_nhwc)
+    ref = ref.permute(0, 2, 3, 1).reshape(b * h * w, cout) + res
+    out = torch.full((b * h * w, cout), float("nan"), device=DEV)
+    ops.conv3x3(_pad_layout(x), wmat.contiguous(), b, h, w, a_short=xs, bias=bias, res1=res, out_f32=out, cta_group=2).run()
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) < 2e-5
