@@ -1,0 +1,54 @@
+"""Runs ONE representative kernel a few times (for `ncu -k ... -s N -c 1`): python scripts/prof_one.py <case>"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from stablemtl_b200 import ops, _lib as L  # noqa: E402
+from stablemtl_b200.weights import interleave_geglu  # noqa: E402
+
+DEV = "cuda"
+case = sys.argv[1]
+rb = lambda *s: (torch.randn(*s, device=DEV) * 0.5).to(ops.h16())
+if case == "ff1":            # GEGLU feed-forward, UNet level 0, 112 images
+    m, c = 112 * 4800, 320
+    a, w, bias = rb(m, c), rb(8 * c, c), torch.randn(8 * c, device=DEV)
+    wi, bi = interleave_geglu(w, bias)
+    out = torch.empty(m, 4 * c, device=DEV, dtype=ops.h16())
+    op = ops.gemm(a, wi, bias=bi, act=L.ACT_GEGLU, out_bf16=out)
+elif case == "lin":          # proj_out-like: K = N = 320, 16-bit residual + stats
+    m, c = 112 * 4800, 320
+    a, w, bias, res = rb(m, c), rb(c, c), torch.randn(c, device=DEV), rb(m, c)
+    out = torch.empty(m, c, device=DEV, dtype=ops.h16())
+    st = ops.new_stats(112, c, DEV)
+    op = ops.gemm(a, w, bias=bias, res1=res, out_bf16=out, stats=st, stats_rows_per_image=4800)
+elif case == "lin0":         # bare K = N = 320 linear, 16-bit out only
+    m, c = 112 * 4800, 320
+    a, w = rb(m, c), rb(c, c)
+    out = torch.empty(m, c, device=DEV, dtype=ops.h16())
+    op = ops.gemm(a, w, out_bf16=out)
+elif case == "conv128":      # VAE full-resolution 128 -> 128 conv, 8 images
+    b, h, wd, c = 8, 480, 640, 128
+    a, w = rb(b * (h + 2) * (wd + 2), c), rb(c, 9 * c)
+    out = torch.empty(b * h * wd, c, device=DEV, dtype=ops.h16())
+    st = ops.new_stats(b, c, DEV)
+    op = ops.conv3x3(a, w, b, h, wd, bias=torch.zeros(c, device=DEV), out_bf16=out, stats=st, stats_rows_per_image=h * wd)
+elif case == "conv512":
+    b, h, wd, c = 8, 120, 160, 512
+    a, w = rb(b * (h + 2) * (wd + 2), c), rb(c, 9 * c)
+    out = torch.empty(b * h * wd, c, device=DEV, dtype=ops.h16())
+    st = ops.new_stats(b, c, DEV)
+    op = ops.conv3x3(a, w, b, h, wd, bias=torch.zeros(c, device=DEV), out_bf16=out, stats=st, stats_rows_per_image=h * wd)
+elif case == "attn":
+    batch, ntok, heads = 16, 4800, 5
+    c = heads * 64
+    qkv = rb(batch * ntok, 3 * c)
+    out = torch.empty(batch * ntok, c, device=DEV, dtype=ops.h16())
+    op = ops.flash_attn(qkv, batch, ntok, heads, out, 0, c, 2 * c)
+else:
+    raise SystemExit("unknown case")
+for _ in range(3):
+    op.run()
+torch.cuda.synchronize()
+print("ok", case)

@@ -21,7 +21,8 @@ using namespace smtl;
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                       // one 128-byte swizzle atom of bf16
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;                   // TMA warp + MMA warp + 8 epilogue warps
+constexpr int EPI_WARPS = 8;
 constexpr int SMEM_BUDGET = 227 * 1024;
 
 struct alignas(64) GemmKParams {
@@ -185,7 +186,7 @@ __device__ __forceinline__ void add_residual(const GemmKParams& p, const void* r
 // Epilogue for one accumulator row per thread: `taddr` = TMEM address of this warp's lane quarter, column 0 of the
 // tile; `tn` = N-tile index.  All tcgen05.ld / shuffles are warp-collective.
 template <int BN>
-__device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t taddr, int tn, int lane,
+__device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t taddr, int tn, int lane, int half,
                                               const EpiRow<BN>& e) {
     const bool geglu = (p.act == SMTL_ACT_GEGLU);
     const int out_bn = geglu ? BN / 2 : BN;
@@ -195,9 +196,13 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t tad
     float bq[BN / 32];          // bias queue: bq[0] is always the current chunk's (rotated once per chunk, so the
 #pragma unroll                  // array is only ever indexed with compile-time constants and stays in registers)
     for (int k = 0; k < BN / 32; ++k) bq[k] = e.bias[k];
+    if (half) {                 // the two warps of a lane quarter take alternate 32-column chunks
+#pragma unroll
+        for (int k = 0; k + 1 < BN / 32; ++k) bq[k] = bq[k + 1];
+    }
 
 #pragma unroll 1
-    for (int c0 = 0; c0 < out_bn; c0 += 32) {
+    for (int c0 = half * 32; c0 < out_bn; c0 += 64) {
         const int ncol_in = n0 + c0;                       // B-row index of the chunk's first column
         if (ncol_in >= p.n) break;                         // warp-uniform
         uint32_t r[32];
@@ -220,12 +225,12 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t tad
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const float g = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, gl, j);
-                v[j] *= gelu_erf(g);
+                v[j] *= gelu_erf_fast(g);
             }
             ocol = tn * (BN / 2) + c0;
         } else if (p.act == SMTL_ACT_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
         } else if (p.act == SMTL_ACT_SILU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
@@ -271,7 +276,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t tad
         }
         __syncwarp();   // reconverge before the next warp-collective instruction
 #pragma unroll
-        for (int k = 0; k + 1 < BN / 32; ++k) bq[k] = bq[k + 1];
+        for (int k = 0; k + 2 < BN / 32; ++k) bq[k] = bq[k + 2];
         if (p.stats && e.img_lo <= e.img_hi) {
             // per-(image, channel) sum / sum of squares of the stored value: lane j ends up owning column ocol + j
             for (int img = e.img_lo; img <= e.img_hi; ++img) {       // warp-uniform; one iteration unless the
@@ -333,7 +338,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_empty[s], 4 * CG);   // one arrive per epilogue warp of every CTA of the pair
+            mbar_init(&acc_empty[s], EPI_WARPS * CG);   // one arrive per epilogue warp of every CTA of the pair
         }
         fence_mbar_init();
     }
@@ -427,8 +432,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        // ------------------------------------------------------------------ epilogue (warps 2..9)
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;             // which of the quarter's two warps: alternate column chunks
         const int row_in_tile = quarter * 32 + lane;
         int it = 0;
         for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
@@ -440,7 +446,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
-            epilogue_rows<BN>(p, taddr, tn, lane, er);
+            epilogue_rows<BN>(p, taddr, tn, lane, half, er);
             // release this accumulator stage back to the (leader's) MMA warp
             tc_fence_before();
             __syncwarp();

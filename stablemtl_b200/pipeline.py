@@ -34,8 +34,9 @@ def _require_cuda(device):
 
 class StableMTLEngine:
     def __init__(self, ucfg: UNetConfig, vcfg: VAEConfig, child_sd, vae_sd, text: Dict[str, torch.Tensor],
-                 main_sd=None, tasks: List[str] = TASKS, device="cuda", max_decode_batch=8):
+                 main_sd=None, tasks: List[str] = TASKS, device="cuda", max_decode_batch=8, use_graph=True):
         self.device = _require_cuda(device)
+        self.use_graph = use_graph
         self.ucfg, self.vcfg, self.tasks = ucfg, vcfg, list(tasks)
         self.multi = main_sd is not None
         self.child_w = UNetWeights(child_sd, ucfg, text, self.tasks, self.device)
@@ -129,21 +130,27 @@ class StableMTLEngine:
         enc.rgb[:B].copy_(rgb, non_blocking=True)                     # H2D (or D2D) copy; dtype cast only if needed
         if rgb_next is not None:
             enc.rgb[B:].copy_(rgb_next, non_blocking=True)
-        enc.run()
-        p["assemble"].run()
-        for u in p["unets"]:
-            u.run()
-        dec, bd, hw = p["dec"], p["bd"], p["hw"]
-        lat = p["lat"]
-        for c0, maps in p["chunks"]:
-            dec.latent.copy_(lat[c0 * hw:(c0 + bd) * hw])
-            dec.run()
-            for m in maps:
-                m.run()
+        # The whole pass (~2000 launches over static buffers) is replayed as ONE CUDA graph: the first call of a plan
+        # runs eagerly (it also sets the kernels' shared-memory attributes), the second captures, later ones replay.
+        if not self.use_graph:
+            self._launch_all(p)
+        elif p.get("graph") is not None:
+            p["graph"].replay()
+        elif not p.get("warm"):
+            self._launch_all(p)
+            p["warm"] = True
+        else:
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                self._launch_all(p)
+            p["graph"] = g
+            g.replay()
         self.last = {t: p["out"][t]["clipped"] for t in self.tasks}
         res = {t: p["out"][t]["post"] for t in self.tasks}
         if return_latents:
             T = len(self.tasks)
+            lat = p["lat"]
             lats = lat.view(T, B, p["h"], p["w"], -1).permute(0, 1, 4, 2, 3)
             return res, {t: lats[i] for i, t in enumerate(self.tasks)}
         return res
@@ -157,6 +164,18 @@ class StableMTLEngine:
             else:
                 out[t] = torch.empty(0, TASK_CH[t], H, W, device=self.device, dtype=F32)
         return out
+
+    def _launch_all(self, p):
+        p["enc"].run()
+        p["assemble"].run()
+        for u in p["unets"]:
+            u.run()
+        dec, bd, hw, lat = p["dec"], p["bd"], p["hw"], p["lat"]
+        for c0, maps in p["chunks"]:
+            dec.latent.copy_(lat[c0 * hw:(c0 + bd) * hw])
+            dec.run()
+            for m in maps:
+                m.run()
 
     def launches_per_step(self, B, H, W, with_next=True):
         return self.plan_for(B, H, W, with_next)["launches"]
