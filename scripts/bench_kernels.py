@@ -86,6 +86,12 @@ def gn_case(batch, h, w, c, pad=True):
 
 if __name__ == "__main__":
     only = sys.argv[1] if len(sys.argv) > 1 else ""
+    if only == "swap":
+        conv_case("vae 1/1 (auto)", 8, 480, 640, 128, 128)
+        conv_case("vae 1/1 256->128 (auto)", 8, 480, 640, 256, 128)
+        conv_case("vae 1/1 (cg1)", 8, 480, 640, 128, 128, cta_group=1)
+        conv_case("vae 1/1 256->128 (cg1)", 8, 480, 640, 256, 128, cta_group=1)
+        sys.exit(0)
     if only == "gemm":
         for cg in (1, 2):
             print(f"--- cta_group {cg}")

@@ -465,6 +465,240 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
     }
 }
 
+// ================================================================================================ swapped form
+// Narrow-output convs / linears (N = Cout = 128: the VAE's full-resolution level).  With the pixels on the MMA's M
+// side a 128 x 128 tile re-reads 8 KB of operands from shared memory per 64 tensor cycles -- the 128 B/clk
+// shared-memory port caps the tensor pipe at ~50 % (measured 750 TFLOP/s).  Here the roles are swapped:
+//     D^T[cout, pixel] = W[cout, K] * X[pixel, K]^T      A := weights (M = 128 = Cout),  B := 256 pixels (N = 256)
+// which has the operand traffic of the wide-N case (12 KB per 128 cycles).  The nine row-shifted K segments of the
+// implicit conv apply to the B operand.  The accumulator comes out channel-major (TMEM lane = output channel,
+// column = pixel), so the epilogue turns each 32 channel x 32 pixel block through a warp-private shared-memory tile
+// into pixel-major 64-byte row pieces (16-bit NHWC); the residual comes in the same way.  GroupNorm statistics are
+// free in this layout: a thread owns ONE channel and just sums its pixels in two registers across all its tiles.
+constexpr int TBN = 256;                            // pixels per tile
+constexpr int T_STAGE_BYTES = A_STAGE_BYTES + TBN * BLOCK_K * 2;   // weights 16 KB + pixels 32 KB
+constexpr int T_STG_WARP = 32 * 80;                 // [32 pixels][32 channels] 16-bit, pitch 64 + 16 bytes
+constexpr int T_STAGING = EPI_WARPS * T_STG_WARP;
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid_constant__ GemmKParams p) {
+    constexpr int TMEM_COLS = 512;
+    constexpr int ACC_STRIDE = 256;
+    constexpr int MAX_STAGES = 12;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stages = p.stages;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * T_STAGE_BYTES);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + MAX_STAGES;
+    uint64_t* acc_full = bars + 2 * MAX_STAGES;
+    uint64_t* acc_empty = bars + 2 * MAX_STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+    uint8_t* staging = smem + (size_t)stages * T_STAGE_BYTES + 512;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tm_a0);
+        tma_prefetch_desc(&p.tm_a1);
+        tma_prefetch_desc(&p.tm_b);
+        for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EPI_WARPS); }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int num_tiles = p.tiles_m;                 // 256-pixel blocks
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int64_t pix0 = (int64_t)tile * TBN;
+                int kb_global = 0;
+                for (int s = 0; s < p.nseg; ++s) {
+                    const smtl_gemm_seg sg = p.seg[s];
+                    const CUtensorMap* tmx = sg.src ? &p.tm_a1 : &p.tm_a0;
+                    const int32_t xrow = (int32_t)(pix0 + sg.row_shift);
+                    for (int kb = 0; kb < sg.kblocks; ++kb, ++kb_global) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1u);
+                        uint8_t* sw = smem + (size_t)stage * T_STAGE_BYTES;     // weights  [128 x 64]
+                        uint8_t* sx = sw + A_STAGE_BYTES;                        // pixels   [256 x 64]
+                        mbar_arrive_expect_tx(&full_bar[stage], T_STAGE_BYTES);
+                        tma_load_2d(sw, &p.tm_b, &full_bar[stage], kb_global * BLOCK_K, 0);
+                        tma_load_2d(sx, tmx, &full_bar[stage], sg.a_col0 + kb * BLOCK_K, xrow);
+                        if (++stage == stages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t IDESC = make_idesc_16(BLOCK_M, TBN, 0, 0, p.fmt);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1u);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * ACC_STRIDE;
+            for (int kb = 0; kb < p.total_kb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sw = smem_u32(smem + (size_t)stage * T_STAGE_BYTES);
+                    const uint64_t da = make_smem_desc_sw128(sw);
+                    const uint64_t db = make_smem_desc_sw128(sw + A_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 16; ++k)
+                        tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
+                    tc_commit(&empty_bar[stage]);
+                    if (kb == p.total_kb - 1) tc_commit(&acc_full[acc]);
+                }
+                __syncwarp();
+                if (++stage == stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: thread = output channel
+        const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int ch = quarter * 32 + lane;                           // this thread's output channel
+        const bool ch_ok = ch < p.n;
+        const float bias_c = (p.bias && ch_ok) ? __ldg(p.bias + ch) : 0.0f;
+        uint8_t* stg = staging + (warp - 2) * T_STG_WARP;
+        const int piece = lane & 3;                                   // 8-channel piece this lane moves (coalesced side)
+        const int cpiece = quarter * 32 + piece * 8;                  // its first channel
+        const bool piece_ok = cpiece + 8 <= p.n;
+        float ssum = 0.f, ssq = 0.f;
+        int cur_img = -1;
+        auto flush = [&]() {
+            if (p.stats && cur_img >= 0 && ch_ok) {
+                float* dst = p.stats + (((int64_t)(blockIdx.x % p.stats_rep) * p.stats_images + cur_img) * p.n + ch) * 2;
+                atomicAdd(dst, ssum);
+                atomicAdd(dst + 1, ssq);
+            }
+            ssum = 0.f;
+            ssq = 0.f;
+        };
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const int64_t pix0 = (int64_t)tile * TBN;
+            mbar_wait(&acc_full[acc], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+            for (int c0 = half * 32; c0 < TBN; c0 += 64) {
+                // pixel (c0 + lane): output row, validity, image
+                const int64_t grow = pix0 + c0 + lane;
+                bool ok = grow < p.m;
+                int64_t orow = grow;
+                if (p.rowmap == SMTL_ROWMAP_CONV_PAD) {
+                    const int wp = p.img_w + 2;
+                    const int plane = (p.img_h + 2) * wp;
+                    const int64_t img = grow / plane;
+                    const int rem = (int)(grow - img * plane);
+                    const int yp = rem / wp, xp = rem - yp * wp;
+                    ok = ok && yp >= 1 && yp <= p.img_h && xp >= 1 && xp <= p.img_w;
+                    orow = (img * p.img_h + (yp - 1)) * p.img_w + (xp - 1);
+                }
+                const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
+                if (okmask == 0 && pix0 + c0 >= p.m) break;             // warp-uniform: past the end
+                const int orow32 = (int)orow;
+                const int img_l = (p.stats && ok) ? (int)(orow / p.stats_rpi) : -1;
+                uint32_t rr[32];
+                float v[32];
+                tmem_ld_32x32(taddr + c0, rr);
+                // rows this lane moves on the coalesced side: pixel 8 i + lane / 4
+                int orow_i[4];
+                uint32_t ok_i = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    orow_i[i] = __shfl_sync(0xffffffffu, orow32, 8 * i + (lane >> 2));
+                    ok_i |= ((okmask >> (8 * i + (lane >> 2))) & 1u) << i;
+                }
+                uint4 rq[4];
+                if (p.res1) {                                            // 16-bit residual, issued before the TMEM wait
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        rq[i] = make_uint4(0, 0, 0, 0);
+                        if (((ok_i >> i) & 1u) && piece_ok)
+                            rq[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.res1) +
+                                                                         (int64_t)orow_i[i] * p.ldres + cpiece));
+                    }
+                }
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]) + bias_c;
+                if (p.res1) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        *reinterpret_cast<uint4*>(stg + (8 * i + (lane >> 2)) * 80 + piece * 16) = rq[i];
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const uint32_t h = *reinterpret_cast<const uint16_t*>(stg + j * 80 + lane * 2);
+                        v[j] += unpack16x2(h, p.fmt).x;
+                    }
+                    __syncwarp();
+                }
+                // channel-major -> pixel-major through the staging tile, then 64-byte row pieces
+#pragma unroll
+                for (int j = 0; j < 32; ++j) *reinterpret_cast<uint16_t*>(stg + j * 80 + lane * 2) = to16(v[j], p.fmt);
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(stg + (8 * i + (lane >> 2)) * 80 + piece * 16);
+                    if (((ok_i >> i) & 1u) && piece_ok)
+                        *reinterpret_cast<uint4*>(p.out_bf16 + (int64_t)orow_i[i] * p.ldc + cpiece) = q;
+                }
+                __syncwarp();
+                if (p.stats && okmask) {
+                    int lo = ok ? img_l : 0x7fffffff, hi = img_l;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+                    }
+                    if (lo == hi) {                                      // the usual case: one image in this chunk
+                        if (lo != cur_img) { flush(); cur_img = lo; }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if ((okmask >> j) & 1u) { ssum += v[j]; ssq += v[j] * v[j]; }
+                    } else {
+                        for (int j = 0; j < 32; ++j) {                   // image boundary inside the chunk (rare)
+                            const int im = __shfl_sync(0xffffffffu, img_l, j);
+                            if ((okmask >> j) & 1u) {
+                                if (im != cur_img) { flush(); cur_img = im; }
+                                ssum += v[j];
+                                ssq += v[j] * v[j];
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        }
+        flush();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
 template <int BN, int CG>
 int launch_gemm(const GemmKParams& kp, int grid, int smem_bytes, cudaStream_t stream) {
     static bool attr_set = false;   // per-instantiation; benign race (idempotent)
@@ -563,9 +797,40 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
     }
     SMTL_CHECK_ARG(g.m + 4096 < (int64_t)1 << 31, "gemm_plan: m too large for 32-bit TMA coordinates");
 
+    const int sms = smtl_host::num_sms();
+    // swapped form (weights on the MMA's M side) for narrow outputs: N <= 128, plain 16-bit output
+    {
+        const char* env = getenv("SMTL_GEMM_SWAP");
+        const bool allow = !(env && env[0] == '0');
+        const bool eligible = g.n <= 128 && g.n >= 64 && g.n % 8 == 0 && g.act == SMTL_ACT_NONE && !g.bias_per_row &&
+                              g.out_bf16 && !g.out_f32 && !g.aux_bf16 && !g.res2 && (!g.res1 || g.res_fmt16 == 1) &&
+                              (g.ldc % 8) == 0 && (!g.res1 || (g.ldres % 8) == 0) && g.block_n == 0 &&
+                              g.cta_group == 0 && g.m >= (int64_t)sms * TBN;
+        if (allow && eligible) {
+            op->cta_group = 3;                      // marks the swapped kernel
+            op->block_n = TBN;
+            op->tiles_m = (int)((g.m + TBN - 1) / TBN);
+            op->tiles_n = 1;
+            op->total_kblocks = total_kb;
+            int stages = (SMEM_BUDGET - 1024 - 512 - T_STAGING) / T_STAGE_BYTES;
+            op->smem_bytes = 1024 + stages * T_STAGE_BYTES + 512 + T_STAGING;
+            op->grid = op->tiles_m < sms ? op->tiles_m : sms;
+            int rc = smtl_host::encode_tmap_bf16_2d(op->tmap_a0, g.a0, (uint64_t)g.a0_rows, (uint64_t)g.a0_cols,
+                                                    (uint64_t)g.a0_ld, TBN);
+            if (rc) return rc;
+            if (g.a1) {
+                rc = smtl_host::encode_tmap_bf16_2d(op->tmap_a1, g.a1, (uint64_t)g.a1_rows, (uint64_t)g.a1_cols,
+                                                    (uint64_t)g.a1_ld, TBN);
+                if (rc) return rc;
+            } else {
+                memcpy(op->tmap_a1, op->tmap_a0, sizeof(op->tmap_a0));
+            }
+            return smtl_host::encode_tmap_bf16_2d(op->tmap_b, g.b, (uint64_t)g.n, (uint64_t)g.k, (uint64_t)g.ldb,
+                                                  BLOCK_M);
+        }
+    }
     // CTA pairs (tcgen05 cta_group::2, 256-row tiles) whenever there are enough rows to fill the machine with them
     int cg = g.cta_group;
-    const int sms = smtl_host::num_sms();
     if (cg == 0) {
         const long long tiles256 = ((g.m + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (long long)((g.n + bn - 1) / bn);
         const char* env = getenv("SMTL_GEMM_CG");
@@ -619,6 +884,7 @@ extern "C" int smtl_gemm_run(const smtl_gemm_op* op, void* stream) {
     const int cg = op->cta_group == 2 ? 2 : 1;
     const int stage_bytes = A_STAGE_BYTES + (op->block_n / cg) * BLOCK_K * 2;
     kp.stages = (op->smem_bytes - 1024 - 512) / stage_bytes;
+    if (op->cta_group == 3) kp.stages = (op->smem_bytes - 1024 - 512 - T_STAGING) / T_STAGE_BYTES;
     kp.nseg = g.nseg;
     for (int s = 0; s < SMTL_MAX_SEG; ++s) kp.seg[s] = g.seg[s];
     kp.bias = g.bias;
@@ -642,6 +908,16 @@ extern "C" int smtl_gemm_run(const smtl_gemm_op* op, void* stream) {
     kp.img_w = g.img_w;
     kp.fmt = g.fmt16;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (op->cta_group == 3) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            SMTL_CHECK_CUDA(cudaFuncSetAttribute(smtl_gemmT_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+            attr_set = true;
+        }
+        smtl_gemmT_kernel<<<op->grid, NUM_THREADS, op->smem_bytes, st>>>(kp);
+        SMTL_CHECK_CUDA(cudaGetLastError());
+        return SMTL_OK;
+    }
     switch (op->block_n) {
         case 32: return launch_gemm_cg<32>(kp, cg, op->grid, op->smem_bytes, st);
         case 64: return launch_gemm_cg<64>(kp, cg, op->grid, op->smem_bytes, st);

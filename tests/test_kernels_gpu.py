@@ -501,3 +501,53 @@ def test_conv3x3_cta_pair(b, h, w, cin, cout, cs):
     ops.conv3x3(_pad_layout(x), wmat.contiguous(), b, h, w, a_short=xs, bias=bias, res1=res, out_f32=out, cta_group=2).run()
     torch.cuda.synchronize()
     assert rel_l2(out, ref) < 2e-5
+
+
+# ------------------------------------------------------------------ swapped form (weights on the MMA M side, N <= 128)
+@pytest.mark.parametrize("b,h,w,cin,cout,cs,with_res", [(1, 200, 200, 128, 128, 0, True), (2, 150, 140, 128, 128, 0, False),
+                                                        (1, 200, 200, 256, 128, 256, False), (1, 210, 190, 64, 96, 0, True)])
+def test_conv3x3_swapped_narrow_output(b, h, w, cin, cout, cs, with_res):
+    """N <= 128 and enough pixels -> the plan picks smtl_gemmT_kernel (channel-major accumulator, transposing
+    epilogue); 16-bit output, optional 16-bit residual, fused 1x1 shortcut segment, per-channel statistics."""
+    ops, L = _ops()
+    x = rnd(b, h, w, cin, seed=1).to(H16())
+    wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=2).to(H16())
+    bias = rnd(cout, seed=3)
+    wmat = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1)
+    xs = None
+    if cs:
+        xs_nhwc = rnd(b, h, w, cs, seed=5).to(H16())
+        ws = rnd(cout, cs, scale=cs ** -0.5, seed=6).to(H16())
+        wmat = torch.cat([wmat, ws], dim=1)
+        ref = ref + F.conv2d(xs_nhwc.float().permute(0, 3, 1, 2), ws.float()[:, :, None, None])
+        xs = _pad_layout(xs_nhwc)
+    ref = ref.permute(0, 2, 3, 1).reshape(b * h * w, cout)
+    res = rnd(b * h * w, cout, seed=4).to(H16()) if with_res else None
+    if with_res:
+        ref = ref + res.float()
+    out = torch.full((b * h * w, cout), float("nan"), device=DEV, dtype=H16())
+    stats = ops.new_stats(b, cout, DEV)
+    op = ops.conv3x3(_pad_layout(x), wmat.contiguous(), b, h, w, a_short=xs, bias=bias, res1=res, out_bf16=out,
+                     stats=stats, stats_rows_per_image=h * w)
+    assert op.struct.cta_group == 3, "expected the swapped kernel"
+    op.run()
+    torch.cuda.synchronize()
+    assert rel_l2(out.float(), ref) < 4e-3
+    st = stats.sum(0)
+    blk = ref.reshape(b, h * w, cout).double()
+    assert rel_l2(st[:, :, 0], blk.sum(1)) < 1e-4
+    assert rel_l2(st[:, :, 1], (blk * blk).sum(1)) < 1e-4
+
+
+def test_gemm_swapped_plain():
+    ops, L = _ops()
+    m, n, k = 50000, 128, 320
+    a, b = rnd(m, k, seed=1).to(H16()), rnd(n, k, scale=k ** -0.5, seed=2).to(H16())
+    bias = rnd(n, seed=3)
+    out = torch.empty(m, n, device=DEV, dtype=H16())
+    op = ops.gemm(a, b, bias=bias, out_bf16=out)
+    assert op.struct.cta_group == 3
+    op.run()
+    torch.cuda.synchronize()
+    assert rel_l2(out.float(), a.float() @ b.float().t() + bias) < 4e-3
