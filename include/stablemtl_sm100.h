@@ -36,7 +36,10 @@ enum {
 };
 
 enum { SMTL_ACT_NONE = 0, SMTL_ACT_GELU = 1, SMTL_ACT_GEGLU = 2, SMTL_ACT_SILU = 3 };
-enum { SMTL_ROWMAP_IDENTITY = 0, SMTL_ROWMAP_CONV_PAD = 1 };
+/* CONV_PAD_UP2: like CONV_PAD, but GEMM row = padded pixel (y, x) of the LOW-resolution map and the output row is
+ * pixel (2y + py, 2x + px) of the 2x nearest-upsampled map (one of the four output parities of "upsample then 3x3
+ * conv", each of which is a 2x2 conv on the low-resolution input; src/model/resnet.py:58-72, diffusers Upsample2D) */
+enum { SMTL_ROWMAP_IDENTITY = 0, SMTL_ROWMAP_CONV_PAD = 1, SMTL_ROWMAP_CONV_PAD_UP2 = 2 };
 /* 16-bit operand format of a call (field `fmt16`): the buffers named *_bf16 hold bf16 (0) or IEEE fp16 (1).
  * Both run at the same tcgen05 kind::f16 rate with fp32 accumulation; fp16 conversions saturate at +-65504. */
 enum { SMTL_FMT_BF16 = 0, SMTL_FMT_F16 = 1 };
@@ -99,7 +102,7 @@ typedef struct smtl_gemm_args {
     int32_t stats_rows_per_image;
     int32_t stats_images;
     int32_t cta_group;  /* 0 = auto; 1 = one CTA per 128-row tile; 2 = CTA pair per 256-row tile (tcgen05 cta_group::2) */
-    int32_t pad_;
+    int32_t up_parity;  /* CONV_PAD_UP2: py * 2 + px */
 } smtl_gemm_args;
 
 typedef struct smtl_gemm_op {

@@ -14,7 +14,7 @@ MAX_SEG = 12
 MAX_TASKS = 8
 
 ACT_NONE, ACT_GELU, ACT_GEGLU, ACT_SILU = 0, 1, 2, 3
-ROWMAP_IDENTITY, ROWMAP_CONV_PAD = 0, 1
+ROWMAP_IDENTITY, ROWMAP_CONV_PAD, ROWMAP_CONV_PAD_UP2 = 0, 1, 2
 FMT_BF16, FMT_F16 = 0, 1
 MAP_MEAN1, MAP_RGB3, MAP_NORMAL, MAP_FLOW2, MAP_FLOW3, MAP_SEMANTIC = range(6)
 (OP_GEMM, OP_FATTN, OP_SOFTMAX, OP_XATTN, OP_TASKATTN, OP_GN, OP_LN, OP_UPSAMPLE, OP_IM2COL, OP_RGBPREP,
@@ -52,7 +52,7 @@ class GemmArgs(C.Structure):
         ("res_fmt16", i32), ("stats_replicas", i32),
         ("stats", vp),
         ("stats_rows_per_image", i32), ("stats_images", i32),
-        ("cta_group", i32), ("pad_", i32),
+        ("cta_group", i32), ("up_parity", i32),
     ]
 
 

@@ -53,6 +53,7 @@ struct alignas(64) GemmKParams {
     int32_t ld_aux;
     int32_t rowmap;
     int32_t img_h, img_w;
+    int32_t up_py, up_px;
     int32_t fmt;
 };
 
@@ -106,14 +107,17 @@ __device__ __forceinline__ void epilogue_prepare(const GemmKParams& p, int64_t g
     const int n0 = tn * BN;
     e.row_ok = grow < p.m;
     e.orow = grow;
-    if (p.rowmap == SMTL_ROWMAP_CONV_PAD) {
+    if (p.rowmap != SMTL_ROWMAP_IDENTITY) {
         const int wp = p.img_w + 2;
         const int plane = (p.img_h + 2) * wp;
         const int64_t img = grow / plane;
         const int rem = (int)(grow - img * plane);
         const int yp = rem / wp, xp = rem - yp * wp;
         e.row_ok = e.row_ok && yp >= 1 && yp <= p.img_h && xp >= 1 && xp <= p.img_w;
-        e.orow = (img * p.img_h + (yp - 1)) * p.img_w + (xp - 1);
+        if (p.rowmap == SMTL_ROWMAP_CONV_PAD)
+            e.orow = (img * p.img_h + (yp - 1)) * p.img_w + (xp - 1);
+        else                                            // CONV_PAD_UP2: output parity (py, px) of the 2x map
+            e.orow = (img * (2 * p.img_h) + 2 * (yp - 1) + p.up_py) * (int64_t)(2 * p.img_w) + 2 * (xp - 1) + p.up_px;
     }
     e.row_bias = (p.bias && p.bias_per_row && grow < p.m) ? __ldg(p.bias + grow) : 0.0f;
 #pragma unroll
@@ -785,8 +789,10 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
         SMTL_CHECK_ARG(!g.bias_per_row, "gemm_plan: GEGLU with per-row bias");
     }
     SMTL_CHECK_ARG(g.fmt16 == SMTL_FMT_BF16 || g.fmt16 == SMTL_FMT_F16, "gemm_plan: bad fmt16 %d", g.fmt16);
-    if (g.rowmap == SMTL_ROWMAP_CONV_PAD)
+    if (g.rowmap != SMTL_ROWMAP_IDENTITY)
         SMTL_CHECK_ARG(g.img_h > 0 && g.img_w > 0, "gemm_plan: conv row map needs img_h/img_w");
+    SMTL_CHECK_ARG(g.rowmap >= SMTL_ROWMAP_IDENTITY && g.rowmap <= SMTL_ROWMAP_CONV_PAD_UP2, "gemm_plan: bad rowmap");
+    SMTL_CHECK_ARG(g.up_parity >= 0 && g.up_parity <= 3, "gemm_plan: bad up_parity");
     SMTL_CHECK_ARG(g.res_fmt16 == 0 || g.res_fmt16 == 1, "gemm_plan: bad res_fmt16 %d", g.res_fmt16);
     if (g.stats) {
         SMTL_CHECK_ARG(g.stats_rows_per_image > 0 && g.stats_images > 0 && g.stats_replicas >= 1 &&
@@ -802,7 +808,7 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
     {
         const char* env = getenv("SMTL_GEMM_SWAP");
         const bool allow = !(env && env[0] == '0');
-        const bool eligible = g.n <= 128 && g.n >= 64 && g.n % 8 == 0 && g.act == SMTL_ACT_NONE && !g.bias_per_row &&
+        const bool eligible = g.rowmap != SMTL_ROWMAP_CONV_PAD_UP2 && g.n <= 128 && g.n >= 64 && g.n % 8 == 0 && g.act == SMTL_ACT_NONE && !g.bias_per_row &&
                               g.out_bf16 && !g.out_f32 && !g.aux_bf16 && !g.res2 && (!g.res1 || g.res_fmt16 == 1) &&
                               (g.ldc % 8) == 0 && (!g.res1 || (g.ldres % 8) == 0) && g.block_n == 0 &&
                               g.cta_group == 0 && g.m >= (int64_t)sms * TBN;
@@ -904,6 +910,8 @@ extern "C" int smtl_gemm_run(const smtl_gemm_op* op, void* stream) {
     kp.ldc = g.ldc;
     kp.ld_aux = g.ld_aux;
     kp.rowmap = g.rowmap;
+    kp.up_py = g.up_parity >> 1;
+    kp.up_px = g.up_parity & 1;
     kp.img_h = g.img_h;
     kp.img_w = g.img_w;
     kp.fmt = g.fmt16;

@@ -551,3 +551,29 @@ def test_gemm_swapped_plain():
     op.run()
     torch.cuda.synchronize()
     assert rel_l2(out.float(), a.float() @ b.float().t() + bias) < 4e-3
+
+
+@pytest.mark.parametrize("b,h,w,cin,cout", [(2, 8, 10, 64, 64), (1, 15, 20, 320, 320), (2, 30, 40, 256, 512)])
+def test_conv_up2x_parity_decomposition(b, h, w, cin, cout):
+    """nearest-2x upsample + 3x3 conv == four 2x2 convs on the low-res map (ops.conv_up2x), incl. statistics"""
+    ops, L = _ops()
+    x = rnd(b, h, w, cin, seed=1).to(H16())
+    wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=2)
+    bias = rnd(cout, seed=3)
+    wmats = [m.to(H16()).contiguous() for m in ops.up2x_weight_matrices(wt)]
+    # reference with the SAME (summed, then rounded) weights the kernel sees would hide a decomposition bug, so the
+    # reference uses the original filter on the upsampled map; tolerance covers the 16-bit rounding of summed taps
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    ref = F.conv2d(up, wt, bias, padding=1).permute(0, 2, 3, 1).reshape(b * 4 * h * w, cout)
+    out = torch.full((b * 4 * h * w, cout), float("nan"), device=DEV, dtype=H16())
+    stats = ops.new_stats(b, cout, DEV)
+    for op in ops.conv_up2x(_pad_layout(x), wmats, b, h, w, bias=bias, out_bf16=out, stats=stats,
+                            stats_rows_per_image=4 * h * w):
+        op.run()
+    torch.cuda.synchronize()
+    assert not torch.isnan(out.float()).any()
+    assert rel_l2(out.float(), ref) < 5e-3
+    st = stats.sum(0)
+    blk = ref.reshape(b, 4 * h * w, cout).double()
+    assert rel_l2(st[:, :, 0], blk.sum(1)) < 2e-3
+    assert rel_l2(st[:, :, 1], (blk * blk).sum(1)) < 2e-3
