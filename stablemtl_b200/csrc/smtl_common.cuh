@@ -292,6 +292,15 @@ __device__ __forceinline__ uint32_t pack16x2(float lo, float hi, int fmt) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
+// same without the +-65504 clamp, for values known to be in range (softmax probabilities)
+__device__ __forceinline__ uint32_t pack16x2_nosat(float lo, float hi, int fmt) {
+    if (fmt == FMT_F16) {
+        __half2 v = __floats2half2_rn(lo, hi);
+        return *reinterpret_cast<uint32_t*>(&v);
+    }
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
 __device__ __forceinline__ float2 unpack16x2(uint32_t u, int fmt) {
     if (fmt == FMT_F16) {
         __half2 v = *reinterpret_cast<__half2*>(&u);
