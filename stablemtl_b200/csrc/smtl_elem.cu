@@ -396,23 +396,33 @@ __global__ void im2col_vec8_kernel(const void* __restrict__ x, int x16, int batc
     }
 }
 // im2col, scalar (tiny Cin stems: 3 or 12 channels), zero-fills k in [9c, kpad)
+// im2col for tiny Cin stems (3 or 12 channels, fp32 in): one thread produces 8 consecutive k (one 16-byte store) of
+// one output pixel; k in [9c, kpad) is zero fill
 __global__ void im2col_scalar_kernel(const float* __restrict__ x, int batch, int h, int w, int c, int stride, int pad_t,
                                      int pad_l, int oh, int ow, int kpad, uint16_t* __restrict__ out, int fmt) {
-    const int64_t total = (int64_t)batch * oh * ow * kpad;
+    const int kv = kpad >> 3;
+    const int64_t total = (int64_t)batch * oh * ow * kv;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
-        const int k = (int)(idx % kpad);
-        const int64_t opix = idx / kpad;
-        float v = 0.f;
-        if (k < 9 * c) {
-            const int tap = k / c, cc = k - tap * c;
-            const int b = (int)(opix / (oh * ow));
-            const int rem = (int)(opix - (int64_t)b * oh * ow);
-            const int oy = rem / ow, ox = rem - oy * ow;
-            const int iy = oy * stride - pad_t + tap / 3, ix = ox * stride - pad_l + tap % 3;
-            if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = __ldg(x + (((int64_t)b * h + iy) * w + ix) * c + cc);
+        const int k0 = (int)(idx % kv) * 8;
+        const int64_t opix = idx / kv;
+        const int b = (int)(opix / (oh * ow));
+        const int rem = (int)(opix - (int64_t)b * oh * ow);
+        const int oy = rem / ow, ox = rem - oy * ow;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int k = k0 + i;
+            v[i] = 0.f;
+            if (k < 9 * c) {
+                const int tap = k / c, cc = k - tap * c;
+                const int iy = oy * stride - pad_t + tap / 3, ix = ox * stride - pad_l + tap % 3;
+                if (iy >= 0 && iy < h && ix >= 0 && ix < w) v[i] = __ldg(x + (((int64_t)b * h + iy) * w + ix) * c + cc);
+            }
         }
-        out[idx] = to16(v, fmt);
+        *reinterpret_cast<uint4*>(out + opix * kpad + k0) =
+            make_uint4(pack16x2(v[0], v[1], fmt), pack16x2(v[2], v[3], fmt), pack16x2(v[4], v[5], fmt),
+                       pack16x2(v[6], v[7], fmt));
     }
 }
 
@@ -791,7 +801,7 @@ extern "C" int smtl_im2col_run(const smtl_im2col_args* a, void* stream) {
                                                                  (uint16_t*)a->out_bf16, a->fmt16);
     } else {
         SMTL_CHECK_ARG(!a->x_fmt16, "im2col: the scalar (tiny Cin) path takes fp32 input");
-        const int64_t total = (int64_t)a->batch * a->oh * a->ow * a->kpad;
+        const int64_t total = (int64_t)a->batch * a->oh * a->ow * (a->kpad / 8);
         im2col_scalar_kernel<<<grid_for(total, 256), 256, 0, st>>>((const float*)a->x, a->batch, a->h, a->w, a->c, a->stride,
                                                                    a->pad_t, a->pad_l, a->oh, a->ow, a->kpad,
                                                                    (uint16_t*)a->out_bf16, a->fmt16);
