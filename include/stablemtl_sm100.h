@@ -103,6 +103,10 @@ typedef struct smtl_gemm_args {
     int32_t stats_images;
     int32_t cta_group;  /* 0 = auto; 1 = one CTA per 128-row tile; 2 = CTA pair per 256-row tile (tcgen05 cta_group::2) */
     int32_t up_parity;  /* CONV_PAD_UP2: py * 2 + px */
+    /* Grouped GEMM (the per-task MLPs of the task attention, src/util/model.py:102-138): rows
+     * [g * group_rows, (g+1) * group_rows) use weight rows [g * n, (g+1) * n) of b (stacked [groups * n, k]) and bias
+     * [g * n, (g+1) * n).  group_rows must be a multiple of 128 (256 for cta_group 2); 0 = off. */
+    int64_t group_rows;
 } smtl_gemm_args;
 
 typedef struct smtl_gemm_op {

@@ -40,6 +40,21 @@ elif case == "conv512":
     out = torch.empty(b * h * wd, c, device=DEV, dtype=ops.h16())
     st = ops.new_stats(b, c, DEV)
     op = ops.conv3x3(a, w, b, h, wd, bias=torch.zeros(c, device=DEV), out_bf16=out, stats=st, stats_rows_per_image=h * wd)
+elif case == "conv512cg2":
+    b, h, wd, c = 8, 120, 160, 512
+    a, w = rb(b * (h + 2) * (wd + 2), c), rb(c, 9 * c)
+    out = torch.empty(b * h * wd, c, device=DEV, dtype=ops.h16())
+    st = ops.new_stats(b, c, DEV)
+    op = ops.conv3x3(a, w, b, h, wd, bias=torch.zeros(c, device=DEV), out_bf16=out, stats=st, stats_rows_per_image=h * wd,
+                     cta_group=2)
+elif case == "sq":
+    a, w = rb(8192, 8192), rb(8192, 8192)
+    out = torch.empty(8192, 8192, device=DEV, dtype=ops.h16())
+    op = ops.gemm(a, w, out_bf16=out, cta_group=1)
+elif case == "sqcg2":
+    a, w = rb(8192, 8192), rb(8192, 8192)
+    out = torch.empty(8192, 8192, device=DEV, dtype=ops.h16())
+    op = ops.gemm(a, w, out_bf16=out, cta_group=2)
 elif case == "attn":
     batch, ntok, heads = 16, 4800, 5
     c = heads * 64

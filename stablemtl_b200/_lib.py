@@ -53,6 +53,7 @@ class GemmArgs(C.Structure):
         ("stats", vp),
         ("stats_rows_per_image", i32), ("stats_images", i32),
         ("cta_group", i32), ("up_parity", i32),
+        ("group_rows", i64),
     ]
 
 

@@ -561,10 +561,13 @@ __global__ void taskattn_kernel(const uint16_t* __restrict__ q, const uint16_t* 
     const int64_t total = (int64_t)n_main * rows_per_group * nheads;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    const int hd = (int)(idx % nheads);
-    const int64_t row = idx / nheads;
-    const int grp = (int)(row / rows_per_group);
-    const int64_t pix = row - (int64_t)grp * rows_per_group;
+    // main task fastest: the n_main threads of one (pixel, head) sit next to each other, so their reads of the same
+    // K/V rows coalesce into one request instead of n_main separate trips to L2/HBM
+    const int grp = (int)(idx % n_main);
+    const int64_t t2 = idx / n_main;
+    const int hd = (int)(t2 % nheads);
+    const int64_t pix = t2 / nheads;
+    const int64_t row = (int64_t)grp * rows_per_group + pix;
     const int dh = c / nheads;
     const int nch = dh >> 3;
     const int my_task = ids.main_task[grp];

@@ -55,6 +55,7 @@ struct alignas(64) GemmKParams {
     int32_t img_h, img_w;
     int32_t up_py, up_px;
     int32_t fmt;
+    int64_t group_rows;   // 0: plain; else rows per weight group
 };
 
 __device__ __forceinline__ void st_global_v4_f32(float* p, float a, float b, float c, float d) {
@@ -123,7 +124,8 @@ __device__ __forceinline__ void epilogue_prepare(const GemmKParams& p, int64_t g
 #pragma unroll
     for (int k = 0; k < BN / 32; ++k) {
         const int c = n0 + 32 * k + lane;
-        e.bias[k] = (p.bias && !p.bias_per_row && c < p.n) ? __ldg(p.bias + c) : 0.0f;
+        const int64_t gofs = p.group_rows ? (grow / p.group_rows) * p.n : 0;       // this tile's weight group
+        e.bias[k] = (p.bias && !p.bias_per_row && c < p.n) ? __ldg(p.bias + gofs + c) : 0.0f;
     }
     // pull this row's residual lines into L2 while the MMAs of the tile run
     if (e.row_ok && (p.res1 || p.res2)) {
@@ -367,7 +369,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
             for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
                 const int64_t m0 = ((int64_t)tm * CG + rank) * BLOCK_M;
-                const int n0 = tn * BN + (int)rank * B_ROWS;
+                const int n0 = tn * BN + (int)rank * B_ROWS +
+                               (p.group_rows ? (int)(((int64_t)tm * CG * BLOCK_M) / p.group_rows) * p.n : 0);
                 int kb_global = 0;
                 for (int s = 0; s < p.nseg; ++s) {
                     const smtl_gemm_seg sg = p.seg[s];
@@ -793,6 +796,12 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
         SMTL_CHECK_ARG(g.img_h > 0 && g.img_w > 0, "gemm_plan: conv row map needs img_h/img_w");
     SMTL_CHECK_ARG(g.rowmap >= SMTL_ROWMAP_IDENTITY && g.rowmap <= SMTL_ROWMAP_CONV_PAD_UP2, "gemm_plan: bad rowmap");
     SMTL_CHECK_ARG(g.up_parity >= 0 && g.up_parity <= 3, "gemm_plan: bad up_parity");
+    if (g.group_rows) {
+        SMTL_CHECK_ARG(g.group_rows > 0 && g.group_rows % BLOCK_M == 0 && g.m % g.group_rows == 0,
+                       "gemm_plan: group_rows %lld must divide m and be a multiple of %d", (long long)g.group_rows, BLOCK_M);
+        SMTL_CHECK_ARG(g.rowmap == SMTL_ROWMAP_IDENTITY && !g.bias_per_row && g.act != SMTL_ACT_GEGLU && !g.stats,
+                       "gemm_plan: grouped GEMM is a plain token linear");
+    }
     SMTL_CHECK_ARG(g.res_fmt16 == 0 || g.res_fmt16 == 1, "gemm_plan: bad res_fmt16 %d", g.res_fmt16);
     if (g.stats) {
         SMTL_CHECK_ARG(g.stats_rows_per_image > 0 && g.stats_images > 0 && g.stats_replicas >= 1 &&
@@ -808,7 +817,7 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
     {
         const char* env = getenv("SMTL_GEMM_SWAP");
         const bool allow = !(env && env[0] == '0');
-        const bool eligible = g.rowmap != SMTL_ROWMAP_CONV_PAD_UP2 && g.n <= 128 && g.n >= 64 && g.n % 8 == 0 && g.act == SMTL_ACT_NONE && !g.bias_per_row &&
+        const bool eligible = g.group_rows == 0 && g.rowmap != SMTL_ROWMAP_CONV_PAD_UP2 && g.n <= 128 && g.n >= 64 && g.n % 8 == 0 && g.act == SMTL_ACT_NONE && !g.bias_per_row &&
                               g.out_bf16 && !g.out_f32 && !g.aux_bf16 && !g.res2 && (!g.res1 || g.res_fmt16 == 1) &&
                               (g.ldc % 8) == 0 && (!g.res1 || (g.ldres % 8) == 0) && g.block_n == 0 &&
                               g.cta_group == 0 && g.m >= (int64_t)sms * TBN;
@@ -843,6 +852,7 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
         // measured on B200 (scripts/bench_kernels.py gemm): pairs win on long plain-K GEMMs (8192^3: 1170 -> 1295
         // TFLOP/s) and lose on the 9-segment implicit convs and on short-K linears, whose cost is the epilogue
         cg = env ? atoi(env) : ((tiles256 >= sms / 2 && g.nseg == 1 && g.k >= 2048 && g.n >= 256) ? 2 : 1);
+        if (g.group_rows) cg = 1;
     }
     SMTL_CHECK_ARG(cg == 1 || cg == 2, "gemm_plan: cta_group %d", cg);
     SMTL_CHECK_ARG(cg == 1 || bn % 16 == 0, "gemm_plan: cta_group 2 needs block_n %% 16 == 0");
@@ -869,8 +879,8 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
     } else {
         memcpy(op->tmap_a1, op->tmap_a0, sizeof(op->tmap_a0));
     }
-    rc = smtl_host::encode_tmap_bf16_2d(op->tmap_b, g.b, (uint64_t)g.n, (uint64_t)g.k, (uint64_t)g.ldb,
-                                        (uint32_t)(bn / cg));
+    const uint64_t b_rows = g.group_rows ? (uint64_t)(g.m / g.group_rows) * (uint64_t)g.n : (uint64_t)g.n;
+    rc = smtl_host::encode_tmap_bf16_2d(op->tmap_b, g.b, b_rows, (uint64_t)g.k, (uint64_t)g.ldb, (uint32_t)(bn / cg));
     return rc;
 }
 
@@ -909,6 +919,7 @@ extern "C" int smtl_gemm_run(const smtl_gemm_op* op, void* stream) {
     kp.aux_bf16 = reinterpret_cast<uint16_t*>(g.aux_bf16);
     kp.ldc = g.ldc;
     kp.ld_aux = g.ld_aux;
+    kp.group_rows = g.group_rows;
     kp.rowmap = g.rowmap;
     kp.up_py = g.up_parity >> 1;
     kp.up_px = g.up_parity & 1;

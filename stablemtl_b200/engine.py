@@ -416,12 +416,28 @@ class UNetPlan(_PlanBase):
             hq = cfg.task_q_hidden
             q1, q2 = P.alloc((M, hq), ops.h16()), P.alloc((M, hq), ops.h16())
             tq = P.alloc((M, C), ops.h16())
-            for gi, t in enumerate(self.group_tasks):
-                r = slice(gi * rpg, (gi + 1) * rpg)
-                add(ops.gemm(qn[r], tw[p + ".tq0.w"][t], bias=tw[p + ".tq0.b"][t], act=L.ACT_GELU, out_bf16=q1[r], name="task_q0"))
-                add(ops.gemm(q1[r], tw[p + ".tq1.w"][t], bias=tw[p + ".tq1.b"][t], act=L.ACT_GELU, out_bf16=q2[r], name="task_q1"))
-                add(ops.gemm(q2[r], tw[p + ".tq2.w"][t], bias=tw[p + ".tq2.b"][t], act=L.ACT_GELU, out_bf16=q1[r], name="task_q2"))
-                add(ops.gemm(q1[r], tw[p + ".tq3.w"][t], bias=tw[p + ".tq3.b"][t], out_bf16=tq[r], name="task_q3"))
+            grouped = rpg % 128 == 0          # one grouped launch for all task streams when tiles cannot straddle groups
+
+            def stacked(key, tasks):
+                """[len(tasks) * out, in] weights / [len(tasks) * out] bias of the per-task module, in row-group order"""
+                wk, bk = tw[p + key + ".w"], tw[p + key + ".b"]
+                idx = torch.tensor(list(tasks), device=wk.device)
+                return (wk.index_select(0, idx).reshape(-1, wk.shape[-1]).contiguous(),
+                        bk.index_select(0, idx).reshape(-1).contiguous(), wk.shape[1])
+
+            def task_linear(key, tasks, src, dst, act, name):
+                if grouped:
+                    wg, bg, nout = stacked(key, tasks)
+                    add(ops.gemm(src, wg, n=nout, bias=bg, act=act, out_bf16=dst, group_rows=rpg, name=name))
+                else:
+                    for gi, t in enumerate(tasks):
+                        r = slice(gi * rpg, (gi + 1) * rpg)
+                        add(ops.gemm(src[r], tw[p + key + ".w"][t], bias=tw[p + key + ".b"][t], act=act, out_bf16=dst[r],
+                                     name=name))
+            task_linear(".tq0", self.group_tasks, qn, q1, L.ACT_GELU, "task_q0")
+            task_linear(".tq1", self.group_tasks, q1, q2, L.ACT_GELU, "task_q1")
+            task_linear(".tq2", self.group_tasks, q2, q1, L.ACT_GELU, "task_q2")
+            task_linear(".tq3", self.group_tasks, q1, tq, L.ACT_NONE, "task_q3")
             P.release(q1, q2)
             # k_t, v_t = MLP_{k,v}[t](LN_{k,v}[t](feat_t)) once per source stream           attention.py:494-495
             F_l = self.feats_in[self.layer]
@@ -436,12 +452,10 @@ class UNetPlan(_PlanBase):
             add(ops.layer_norm(F_l, gk, bk, kn, gamma1=gv, beta1=bv, out1=vn, rows_per_group=rpg))
             hk, hv = P.alloc((Ms, C // 2), ops.h16()), P.alloc((Ms, C // 2), ops.h16())
             K, V = P.alloc((Ms, C), ops.h16()), P.alloc((Ms, C), ops.h16())
-            for si, t in enumerate(self.src_tasks):
-                r = slice(si * rpg, (si + 1) * rpg)
-                add(ops.gemm(kn[r], tw[p + ".tk1.w"][t], bias=tw[p + ".tk1.b"][t], act=L.ACT_GELU, out_bf16=hk[r], name="task_k1"))
-                add(ops.gemm(vn[r], tw[p + ".tv1.w"][t], bias=tw[p + ".tv1.b"][t], act=L.ACT_GELU, out_bf16=hv[r], name="task_v1"))
-                add(ops.gemm(hk[r], tw[p + ".tk2.w"][t], bias=tw[p + ".tk2.b"][t], out_bf16=K[r], name="task_k2"))
-                add(ops.gemm(hv[r], tw[p + ".tv2.w"][t], bias=tw[p + ".tv2.b"][t], out_bf16=V[r], name="task_v2"))
+            task_linear(".tk1", self.src_tasks, kn, hk, L.ACT_GELU, "task_k1")
+            task_linear(".tv1", self.src_tasks, vn, hv, L.ACT_GELU, "task_v1")
+            task_linear(".tk2", self.src_tasks, hk, K, L.ACT_NONE, "task_k2")
+            task_linear(".tv2", self.src_tasks, hv, V, L.ACT_NONE, "task_v2")
             P.release(kn, vn, hk, hv)
             ta = qn
             add(ops.task_attn(tq, K, V, ta, C, cfg.n_attns, self.group_tasks, self.src_tasks, rpg, exclude_self=True))

@@ -126,7 +126,7 @@ def new_stats(images, channels, device):
 
 def gemm(a0, b, *, m=None, k=None, n=None, a1=None, segs=None, bias=None, bias_per_row=False, act=L.ACT_NONE,
          res1=None, res2=None, out_f32=None, out_bf16=None, aux_bf16=None, rowmap=L.ROWMAP_IDENTITY, img_hw=None,
-         block_n=0, name="gemm", stats=None, stats_rows_per_image=0, cta_group=0, up_parity=0):
+         block_n=0, name="gemm", stats=None, stats_rows_per_image=0, cta_group=0, up_parity=0, group_rows=0):
     """D = A @ B^T (+ fused epilogue).  a0/a1: bf16 [rows, cols] (row stride = stride(0)); b: bf16 [n, k].
     segs: list of (row_shift, kblocks, src, a_col0)."""
     assert a0.dtype == BF16 and b.dtype == BF16 and a0.stride(-1) == 1 and b.stride(-1) == 1
@@ -184,8 +184,12 @@ def gemm(a0, b, *, m=None, k=None, n=None, a1=None, segs=None, bias=None, bias_p
     g.block_n = block_n
     g.cta_group = cta_group
     g.up_parity = up_parity
+    g.group_rows = group_rows
     op = L.GemmOp()
     L.check(L.lib.smtl_gemm_plan(C.byref(g), C.byref(op)), "smtl_gemm_plan")
+    if group_rows:
+        assert n is not None and b.shape[0] == (int(g.m) // group_rows) * n, "grouped GEMM: b is [groups * n, k], pass n"
+        assert bias is None or bias.numel() == b.shape[0]
     flops = 2 * int(g.m) * int(g.n) * int(g.k)
     return Op(L.OP_GEMM, op, (a0, a1, b, bias, res1, res2, out_f32, out_bf16, aux_bf16, stats), flops, name)
 

@@ -577,3 +577,17 @@ def test_conv_up2x_parity_decomposition(b, h, w, cin, cout):
     blk = ref.reshape(b, 4 * h * w, cout).double()
     assert rel_l2(st[:, :, 0], blk.sum(1)) < 2e-3
     assert rel_l2(st[:, :, 1], (blk * blk).sum(1)) < 2e-3
+
+
+def test_gemm_grouped_per_task_weights():
+    """rows [g*R, (g+1)*R) use weight / bias group g (the per-task MLPs of the task attention in one launch)"""
+    ops, L = _ops()
+    G, R, n, k = 7, 640, 320, 640
+    a = rnd(G * R, k, seed=1).to(H16())
+    w = rnd(G, n, k, scale=k ** -0.5, seed=2).to(H16())
+    bias = rnd(G, n, seed=3)
+    out = torch.full((G * R, n), float("nan"), device=DEV, dtype=H16())
+    ops.gemm(a, w.reshape(G * n, k), n=n, bias=bias.reshape(-1), act=L.ACT_GELU, out_bf16=out, group_rows=R).run()
+    torch.cuda.synchronize()
+    ref = torch.cat([F.gelu(a[g * R:(g + 1) * R].float() @ w[g].float().t() + bias[g]) for g in range(G)])
+    assert rel_l2(out.float(), ref) < 4e-3
