@@ -35,6 +35,7 @@ def parse():
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--breakdown", default="", help="write a per-kernel-kind time breakdown JSON here")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--decode-batch", type=int, default=0, help="latents per VAE-decode launch group (default: engine's)")
     return ap.parse_args()
 
 
@@ -283,7 +284,8 @@ def main():
     if multi:
         main_sd = dict(synth.make_unet_state_dict(synth.SD2_UNET, 10))
         main_sd.update(synth.make_task_modules_state_dict(synth.SD2_UNET, seed=11))
-    eng = StableMTLEngine(synth.SD2_UNET, synth.SD2_VAE, child, vae, text, main_sd, device=dev)
+    kw = {"max_decode_batch": args.decode_batch} if args.decode_batch else {}
+    eng = StableMTLEngine(synth.SD2_UNET, synth.SD2_VAE, child, vae, text, main_sd, device=dev, **kw)
     del main_sd
 
     g = torch.Generator().manual_seed(100 + rank)

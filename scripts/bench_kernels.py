@@ -86,6 +86,11 @@ def gn_case(batch, h, w, c, pad=True):
 
 if __name__ == "__main__":
     only = sys.argv[1] if len(sys.argv) > 1 else ""
+    if only == "stages":
+        conv_case("vae 1/4 512->512", 8, 120, 160, 512, 512, cta_group=1)
+        conv_case("vae 1/2 256->256", 8, 240, 320, 256, 256, cta_group=1)
+        conv_case("unet L0 320->320", 112, 60, 80, 320, 320, cta_group=1)
+        sys.exit(0)
     if only == "swap":
         conv_case("vae 1/1 (auto)", 8, 480, 640, 128, 128)
         conv_case("vae 1/1 256->128 (auto)", 8, 480, 640, 256, 128)

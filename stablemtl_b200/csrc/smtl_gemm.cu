@@ -864,6 +864,10 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
     const int stage_bytes = A_STAGE_BYTES + (bn / cg) * BLOCK_K * 2;
     int stages = (SMEM_BUDGET - 1024 - 512) / stage_bytes;
     if (stages > 8) stages = 8;
+    if (const char* env = getenv("SMTL_GEMM_MAX_STAGES")) {       // experiment knob: pipeline-depth sensitivity
+        const int cap = atoi(env);
+        if (cap >= 2 && stages > cap) stages = cap;
+    }
     op->smem_bytes = 1024 + stages * stage_bytes + 512;
     const long long tiles = (long long)op->tiles_m * op->tiles_n;
     const int slots = sms / cg;                     // CTAs (cg = 1) or CTA pairs (cg = 2) resident at once

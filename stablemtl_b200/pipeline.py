@@ -34,7 +34,7 @@ def _require_cuda(device):
 
 class StableMTLEngine:
     def __init__(self, ucfg: UNetConfig, vcfg: VAEConfig, child_sd, vae_sd, text: Dict[str, torch.Tensor],
-                 main_sd=None, tasks: List[str] = TASKS, device="cuda", max_decode_batch=8, use_graph=True):
+                 main_sd=None, tasks: List[str] = TASKS, device="cuda", max_decode_batch=16, use_graph=True):
         self.device = _require_cuda(device)
         self.use_graph = use_graph
         self.ucfg, self.vcfg, self.tasks = ucfg, vcfg, list(tasks)
