@@ -1,6 +1,6 @@
 """Checkpoint ingest: the files the reference evaluates from -> the state dicts `StableMTLEngine` takes.
 
-Mirrors the load sequence of the reference (paths relative to /root/reference):
+Mirrors the load sequence of the reference (paths under /root/reference):
   eval_mtl.py:288-300           SD-2 diffusers directory: `<base_ckpt_dir>/stable-diffusion-2/{unet,vae}/diffusion_pytorch_model.*`
   src/util/model.py:196-199     the 4-channel SD-2 `conv_in` is widened to 12 channels: weights tiled x3, scaled 1/3
   src/util/model.py:205-221     `single_stream_unet.pth` -> child UNet (and main unless main_stream_from_scratch)
