@@ -120,7 +120,11 @@ typedef struct smtl_gemm_op {
     int32_t total_kblocks;
     int32_t smem_bytes;
     int32_t cta_group;
-    int32_t pad_;
+    /* shift-grouped mainloop (segments with consecutive row shifts share one activation tile): see smtl_gemm.cu */
+    int32_t grouped;
+    int32_t ngrp, sp, sw;
+    struct { int32_t row_shift, nsub, kblocks, src, a_col0, kb0; } grp[SMTL_MAX_SEG];
+    uint64_t tmap_x8[2][16];
 } smtl_gemm_op;
 
 int smtl_gemm_plan(const smtl_gemm_args* args, smtl_gemm_op* op);

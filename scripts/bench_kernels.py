@@ -86,6 +86,10 @@ def gn_case(batch, h, w, c, pad=True):
 
 if __name__ == "__main__":
     only = sys.argv[1] if len(sys.argv) > 1 else ""
+    if only == "head":
+        a = rb(8 * 482 * 642, 128); wm = rb(3, 9 * 128); out = torch.empty(8 * 480 * 640, 3, device=DEV)
+        report("conv3x3 vae head b=8 480x640 128->3", ops.conv3x3(a, wm, 8, 480, 640, bias=torch.zeros(3, device=DEV), out_f32=out))
+        sys.exit(0)
     if only == "stages":
         conv_case("vae 1/4 512->512", 8, 120, 160, 512, 512, cta_group=1)
         conv_case("vae 1/2 256->256", 8, 240, 320, 256, 256, cta_group=1)

@@ -55,6 +55,9 @@ elif case == "sqcg2":
     a, w = rb(8192, 8192), rb(8192, 8192)
     out = torch.empty(8192, 8192, device=DEV, dtype=ops.h16())
     op = ops.gemm(a, w, out_bf16=out, cta_group=2)
+elif case == "head":
+    a = rb(8 * 482 * 642, 128); w = rb(3, 9 * 128); out = torch.empty(8 * 480 * 640, 3, device=DEV)
+    op = ops.conv3x3(a, w, 8, 480, 640, bias=torch.zeros(3, device=DEV), out_f32=out)
 elif case == "attn":
     batch, ntok, heads = 16, 4800, 5
     c = heads * 64

@@ -62,7 +62,10 @@ class GemmOp(C.Structure):
         ("args", GemmArgs),
         ("tmap_a0", C.c_uint64 * 16), ("tmap_a1", C.c_uint64 * 16), ("tmap_b", C.c_uint64 * 16),
         ("block_n", i32), ("grid", i32), ("tiles_m", i32), ("tiles_n", i32),
-        ("total_kblocks", i32), ("smem_bytes", i32), ("cta_group", i32), ("pad_", i32),
+        ("total_kblocks", i32), ("smem_bytes", i32), ("cta_group", i32), ("grouped", i32),
+        ("ngrp", i32), ("sp", i32), ("sw", i32),
+        ("grp", (i32 * 6) * MAX_SEG),
+        ("tmap_x8", (C.c_uint64 * 16) * 2),
     ]
 
 

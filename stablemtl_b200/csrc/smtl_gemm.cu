@@ -29,6 +29,7 @@ struct alignas(64) GemmKParams {
     CUtensorMap tm_a0;
     CUtensorMap tm_a1;
     CUtensorMap tm_b;
+    CUtensorMap tm_x8[2];  // swapped + grouped: 8-row boxes of a0 / a1 (a TMA box is at most 256 rows)
     int64_t m;
     int32_t n;            // B rows (pre-activation columns)
     int32_t n_out;        // output columns (n, or n/2 for GEGLU)
@@ -56,6 +57,14 @@ struct alignas(64) GemmKParams {
     int32_t up_py, up_px;
     int32_t fmt;
     int64_t group_rows;   // 0: plain; else rows per weight group
+    // "shift-grouped" mainloop: up to three K segments whose row shifts are consecutive (the kx = -1, 0, +1 taps of
+    // one ky of a 3x3 conv) share ONE activation tile loaded with 8 extra rows; the MMA descriptor of tap j simply
+    // starts j rows (j * 128 B) into it -- the 128-byte swizzle is a function of the shared-memory address, so a
+    // row-shifted start reads the shifted rows (verified on B200).  A third of the activation TMA/L2/smem traffic.
+    int32_t grouped;      // 0: one (A, B) ring; 1: activation ring + weight ring
+    int32_t ngrp;
+    int32_t sp, sw;       // stages of the activation / weight rings
+    struct Grp { int32_t row_shift, nsub, kblocks, src, a_col0, kb0; } grp[SMTL_MAX_SEG];
 };
 
 __device__ __forceinline__ void st_global_v4_f32(float* p, float a, float b, float c, float d) {
@@ -319,10 +328,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
     constexpr int ACC_STRIDE = TMEM_COLS / 2;
     constexpr int MAX_STAGES = 12;
 
+    constexpr int PB = (BLOCK_M + 8) * BLOCK_K * 2;                  // grouped mode: activation tile with 8 extra rows
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stages = p.stages;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * STAGE_BYTES);
+    const bool grouped = (CG == 1) && p.grouped;
+    uint8_t* smem_w = smem + (size_t)p.sp * PB;                       // grouped mode: weight ring after the activation ring
+    uint64_t* bars = reinterpret_cast<uint64_t*>(
+        grouped ? smem_w + (size_t)p.sw * B_STAGE_BYTES : smem + (size_t)stages * STAGE_BYTES);
     uint64_t* full_bar = bars;                       // [stages]   TMA (both CTAs) -> MMA (leader)
     uint64_t* empty_bar = bars + MAX_STAGES;         // [stages]   MMA -> TMA (each CTA its own)
     uint64_t* acc_full = bars + 2 * MAX_STAGES;      // [2]        MMA -> epilogue (each CTA its own)
@@ -338,7 +351,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
         tma_prefetch_desc(&p.tm_a0);
         tma_prefetch_desc(&p.tm_a1);
         tma_prefetch_desc(&p.tm_b);
-        for (int s = 0; s < stages; ++s) {
+        for (int s = 0; s < MAX_STAGES; ++s) {     // grouped mode: [0, sp) activation ring, [sp, sp + sw) weight ring
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
@@ -363,7 +376,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        if (lane == 0 && grouped) {
+            int ps = 0, ws = 0;
+            uint32_t pph = 0, wph = 0;
+            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+                const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+                const int64_t m0 = (int64_t)tm * BLOCK_M;
+                const int n0 = tn * BN + (p.group_rows ? (int)(m0 / p.group_rows) * p.n : 0);
+                for (int g = 0; g < p.ngrp; ++g) {
+                    const GemmKParams::Grp gr = p.grp[g];
+                    const CUtensorMap* tma = gr.src ? &p.tm_a1 : &p.tm_a0;
+                    for (int kb = 0; kb < gr.kblocks; ++kb) {
+                        mbar_wait(&empty_bar[ps], pph ^ 1u);
+                        mbar_arrive_expect_tx(&full_bar[ps], PB);
+                        tma_load_2d(smem + (size_t)ps * PB, tma, &full_bar[ps], gr.a_col0 + kb * BLOCK_K,
+                                    (int32_t)(m0 + gr.row_shift));
+                        if (++ps == p.sp) { ps = 0; pph ^= 1u; }
+                        for (int sub = 0; sub < gr.nsub; ++sub) {
+                            const int wb = p.sp + ws;
+                            mbar_wait(&empty_bar[wb], wph ^ 1u);
+                            mbar_arrive_expect_tx(&full_bar[wb], B_STAGE_BYTES);
+                            tma_load_2d(smem_w + (size_t)ws * B_STAGE_BYTES, &p.tm_b, &full_bar[wb],
+                                        (gr.kb0 + sub * gr.kblocks + kb) * BLOCK_K, n0);
+                            if (++ws == p.sw) { ws = 0; wph ^= 1u; }
+                        }
+                    }
+                }
+            }
+        } else if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = tile0; tile < num_tiles; tile += tile_step) {
@@ -398,7 +438,49 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-        if (leader) {
+        if (leader && grouped) {
+            const uint32_t IDESC = make_idesc_16(BLOCK_M, BN, 0, 0, p.fmt);
+            int ps = 0, ws = 0;
+            uint32_t pph = 0, wph = 0;
+            int it = 0;
+            for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * ACC_STRIDE;
+                uint32_t accum = 0;
+                for (int g = 0; g < p.ngrp; ++g) {
+                    const int nsub = p.grp[g].nsub, nkb = p.grp[g].kblocks;
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        mbar_wait(&full_bar[ps], pph);
+                        const uint32_t sa = smem_u32(smem + (size_t)ps * PB);
+                        for (int sub = 0; sub < nsub; ++sub) {
+                            const int wb = p.sp + ws;
+                            mbar_wait(&full_bar[wb], wph);
+                            tc_fence_after();
+                            if (lane == 0) {
+                                const uint64_t da = make_smem_desc_sw128(sa + sub * 128);      // tap `sub`: one row further
+                                const uint64_t db = make_smem_desc_sw128(smem_u32(smem_w + (size_t)ws * B_STAGE_BYTES));
+#pragma unroll
+                                for (int k = 0; k < BLOCK_K / 16; ++k) {
+                                    tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, accum);
+                                    accum = 1;
+                                }
+                                tc_commit(&empty_bar[wb]);
+                            }
+                            accum = 1;
+                            __syncwarp();
+                            if (++ws == p.sw) { ws = 0; wph ^= 1u; }
+                        }
+                        if (lane == 0) tc_commit(&empty_bar[ps]);
+                        __syncwarp();
+                        if (++ps == p.sp) { ps = 0; pph ^= 1u; }
+                    }
+                }
+                if (lane == 0) tc_commit(&acc_full[acc]);
+                __syncwarp();
+            }
+        } else if (leader) {
             const uint32_t IDESC = make_idesc_16(BLOCK_M * CG, BN, 0, 0, p.fmt);
             int stage = 0;
             uint32_t phase = 0;
@@ -484,6 +566,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
 // free in this layout: a thread owns ONE channel and just sums its pixels in two registers across all its tiles.
 constexpr int TBN = 256;                            // pixels per tile
 constexpr int T_STAGE_BYTES = A_STAGE_BYTES + TBN * BLOCK_K * 2;   // weights 16 KB + pixels 32 KB
+constexpr int T_PB = 34 * 1024;                     // grouped mode: 256 + 8 pixel rows x 128 B, rounded up to the 1 KB swizzle repeat
 constexpr int T_STG_WARP = 32 * 80;                 // [32 pixels][32 channels] 16-bit, pitch 64 + 16 bytes
 constexpr int T_STAGING = EPI_WARPS * T_STG_WARP;
 
@@ -494,13 +577,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stages = p.stages;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * T_STAGE_BYTES);
+    const bool grouped = p.grouped != 0;
+    uint8_t* smem_w = smem + (size_t)p.sp * T_PB;                     // grouped: weight ring after the pixel ring
+    uint8_t* ring_end = grouped ? smem_w + (size_t)p.sw * A_STAGE_BYTES : smem + (size_t)stages * T_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring_end);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + MAX_STAGES;
     uint64_t* acc_full = bars + 2 * MAX_STAGES;
     uint64_t* acc_empty = bars + 2 * MAX_STAGES + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
-    uint8_t* staging = smem + (size_t)stages * T_STAGE_BYTES + 512;
+    uint8_t* staging = ring_end + 512;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -508,7 +594,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
         tma_prefetch_desc(&p.tm_a0);
         tma_prefetch_desc(&p.tm_a1);
         tma_prefetch_desc(&p.tm_b);
-        for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EPI_WARPS); }
         fence_mbar_init();
     }
@@ -523,7 +609,35 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
     const int num_tiles = p.tiles_m;                 // 256-pixel blocks
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (lane == 0 && grouped) {
+            int ps = 0, ws = 0;
+            uint32_t pph = 0, wph = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int64_t pix0 = (int64_t)tile * TBN;
+                for (int g = 0; g < p.ngrp; ++g) {
+                    const GemmKParams::Grp gr = p.grp[g];
+                    const CUtensorMap* tmx = gr.src ? &p.tm_a1 : &p.tm_a0;
+                    for (int kb = 0; kb < gr.kblocks; ++kb) {
+                        mbar_wait(&empty_bar[ps], pph ^ 1u);
+                        uint8_t* sx = smem + (size_t)ps * T_PB;
+                        mbar_arrive_expect_tx(&full_bar[ps], (TBN + 8) * BLOCK_K * 2);
+                        const int32_t xrow = (int32_t)(pix0 + gr.row_shift);
+                        tma_load_2d(sx, tmx, &full_bar[ps], gr.a_col0 + kb * BLOCK_K, xrow);                     // 256 rows
+                        tma_load_2d(sx + TBN * BLOCK_K * 2, &p.tm_x8[gr.src ? 1 : 0], &full_bar[ps],
+                                    gr.a_col0 + kb * BLOCK_K, xrow + TBN);                                         // + 8 rows
+                        if (++ps == p.sp) { ps = 0; pph ^= 1u; }
+                        for (int sub = 0; sub < gr.nsub; ++sub) {
+                            const int wb = p.sp + ws;
+                            mbar_wait(&empty_bar[wb], wph ^ 1u);
+                            mbar_arrive_expect_tx(&full_bar[wb], A_STAGE_BYTES);
+                            tma_load_2d(smem_w + (size_t)ws * A_STAGE_BYTES, &p.tm_b, &full_bar[wb],
+                                        (gr.kb0 + sub * gr.kblocks + kb) * BLOCK_K, 0);
+                            if (++ws == p.sw) { ws = 0; wph ^= 1u; }
+                        }
+                    }
+                }
+            }
+        } else if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -544,6 +658,48 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
                     }
                 }
             }
+        }
+    } else if (warp == 1 && grouped) {
+        const uint32_t IDESC = make_idesc_16(BLOCK_M, TBN, 0, 0, p.fmt);
+        int ps = 0, ws = 0;
+        uint32_t pph = 0, wph = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1u);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * ACC_STRIDE;
+            uint32_t accum = 0;
+            for (int g = 0; g < p.ngrp; ++g) {
+                const int nsub = p.grp[g].nsub, nkb = p.grp[g].kblocks;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&full_bar[ps], pph);
+                    const uint32_t sx = smem_u32(smem + (size_t)ps * T_PB);
+                    for (int sub = 0; sub < nsub; ++sub) {
+                        const int wb = p.sp + ws;
+                        mbar_wait(&full_bar[wb], wph);
+                        tc_fence_after();
+                        if (lane == 0) {
+                            const uint64_t da = make_smem_desc_sw128(smem_u32(smem_w + (size_t)ws * A_STAGE_BYTES));
+                            const uint64_t db = make_smem_desc_sw128(sx + sub * 128);            // tap `sub`: one pixel row further
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 16; ++k) {
+                                tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, accum);
+                                accum = 1;
+                            }
+                            tc_commit(&empty_bar[wb]);
+                        }
+                        accum = 1;
+                        __syncwarp();
+                        if (++ws == p.sw) { ws = 0; wph ^= 1u; }
+                    }
+                    if (lane == 0) tc_commit(&empty_bar[ps]);
+                    __syncwarp();
+                    if (++ps == p.sp) { ps = 0; pph ^= 1u; }
+                }
+            }
+            if (lane == 0) tc_commit(&acc_full[acc]);
+            __syncwarp();
         }
     } else if (warp == 1) {
         const uint32_t IDESC = make_idesc_16(BLOCK_M, TBN, 0, 0, p.fmt);
@@ -813,6 +969,32 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
     SMTL_CHECK_ARG(g.m + 4096 < (int64_t)1 << 31, "gemm_plan: m too large for 32-bit TMA coordinates");
 
     const int sms = smtl_host::num_sms();
+    // ---- shift groups: consecutive-row-shift segments (kx = -1, 0, +1 of one ky) share one activation tile
+    {
+        const char* env = getenv("SMTL_GEMM_GROUPED");
+        const bool allow = !(env && env[0] == '0') && g.cta_group != 2;
+        int ng = 0, kb0 = 0;
+        bool any = false;
+        for (int si = 0; si < g.nseg;) {
+            int nsub = 1;
+            while (allow && nsub < 3 && si + nsub < g.nseg &&
+                   g.seg[si + nsub].row_shift == g.seg[si].row_shift + nsub && g.seg[si + nsub].kblocks == g.seg[si].kblocks &&
+                   g.seg[si + nsub].src == g.seg[si].src && g.seg[si + nsub].a_col0 == g.seg[si].a_col0)
+                ++nsub;
+            op->grp[ng].row_shift = g.seg[si].row_shift;
+            op->grp[ng].nsub = nsub;
+            op->grp[ng].kblocks = g.seg[si].kblocks;
+            op->grp[ng].src = g.seg[si].src;
+            op->grp[ng].a_col0 = g.seg[si].a_col0;
+            op->grp[ng].kb0 = kb0;
+            kb0 += nsub * g.seg[si].kblocks;
+            any = any || nsub > 1;
+            si += nsub;
+            ++ng;
+        }
+        op->ngrp = ng;
+        op->grouped = any ? 1 : 0;
+    }
     // swapped form (weights on the MMA's M side) for narrow outputs: N <= 128, plain 16-bit output
     {
         const char* env = getenv("SMTL_GEMM_SWAP");
@@ -829,6 +1011,22 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
             op->total_kblocks = total_kb;
             int stages = (SMEM_BUDGET - 1024 - 512 - T_STAGING) / T_STAGE_BYTES;
             op->smem_bytes = 1024 + stages * T_STAGE_BYTES + 512 + T_STAGING;
+            if (op->grouped) {
+                op->sp = 3;
+                op->sw = (SMEM_BUDGET - 1024 - 512 - T_STAGING - op->sp * T_PB) / A_STAGE_BYTES;
+                if (op->sw > 8) op->sw = 8;
+                op->smem_bytes = 1024 + op->sp * T_PB + op->sw * A_STAGE_BYTES + 512 + T_STAGING;
+                int rc8 = smtl_host::encode_tmap_bf16_2d(op->tmap_x8[0], g.a0, (uint64_t)g.a0_rows, (uint64_t)g.a0_cols,
+                                                         (uint64_t)g.a0_ld, 8);
+                if (rc8) return rc8;
+                if (g.a1) {
+                    rc8 = smtl_host::encode_tmap_bf16_2d(op->tmap_x8[1], g.a1, (uint64_t)g.a1_rows, (uint64_t)g.a1_cols,
+                                                         (uint64_t)g.a1_ld, 8);
+                    if (rc8) return rc8;
+                } else {
+                    memcpy(op->tmap_x8[1], op->tmap_x8[0], sizeof(op->tmap_x8[0]));
+                }
+            }
             op->grid = op->tiles_m < sms ? op->tiles_m : sms;
             int rc = smtl_host::encode_tmap_bf16_2d(op->tmap_a0, g.a0, (uint64_t)g.a0_rows, (uint64_t)g.a0_cols,
                                                     (uint64_t)g.a0_ld, TBN);
@@ -855,6 +1053,7 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
         if (g.group_rows) cg = 1;
     }
     SMTL_CHECK_ARG(cg == 1 || cg == 2, "gemm_plan: cta_group %d", cg);
+    if (cg == 2) op->grouped = 0;                   // the pair kernel keeps the single (A, B) ring
     SMTL_CHECK_ARG(cg == 1 || bn % 16 == 0, "gemm_plan: cta_group 2 needs block_n %% 16 == 0");
     op->cta_group = cg;
     op->block_n = bn;
@@ -869,16 +1068,27 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
         if (cap >= 2 && stages > cap) stages = cap;
     }
     op->smem_bytes = 1024 + stages * stage_bytes + 512;
+    const int a_box_rows = op->grouped ? BLOCK_M + 8 : BLOCK_M;
+    if (op->grouped) {
+        const int pb = (BLOCK_M + 8) * BLOCK_K * 2, wb = bn * BLOCK_K * 2;
+        // narrow tiles are bound by the activation stream: give it the deeper ring (12 barriers in all)
+        op->sp = (SMEM_BUDGET - 1024 - 512 - 6 * wb) / pb;
+        if (op->sp < 3) op->sp = 3;
+        if (op->sp > 6) op->sp = 6;
+        op->sw = (SMEM_BUDGET - 1024 - 512 - op->sp * pb) / wb;
+        if (op->sw > 12 - op->sp) op->sw = 12 - op->sp;
+        op->smem_bytes = 1024 + op->sp * pb + op->sw * wb + 512;
+    }
     const long long tiles = (long long)op->tiles_m * op->tiles_n;
     const int slots = sms / cg;                     // CTAs (cg = 1) or CTA pairs (cg = 2) resident at once
     op->grid = (int)(tiles < slots ? tiles : slots) * cg;
 
     int rc = smtl_host::encode_tmap_bf16_2d(op->tmap_a0, g.a0, (uint64_t)g.a0_rows, (uint64_t)g.a0_cols,
-                                            (uint64_t)g.a0_ld, BLOCK_M);
+                                            (uint64_t)g.a0_ld, a_box_rows);
     if (rc) return rc;
     if (g.a1) {
         rc = smtl_host::encode_tmap_bf16_2d(op->tmap_a1, g.a1, (uint64_t)g.a1_rows, (uint64_t)g.a1_cols,
-                                            (uint64_t)g.a1_ld, BLOCK_M);
+                                            (uint64_t)g.a1_ld, a_box_rows);
         if (rc) return rc;
     } else {
         memcpy(op->tmap_a1, op->tmap_a0, sizeof(op->tmap_a0));
@@ -924,6 +1134,16 @@ extern "C" int smtl_gemm_run(const smtl_gemm_op* op, void* stream) {
     kp.ldc = g.ldc;
     kp.ld_aux = g.ld_aux;
     kp.group_rows = g.group_rows;
+    kp.grouped = op->grouped;
+    kp.ngrp = op->ngrp;
+    kp.sp = op->sp;
+    kp.sw = op->sw;
+    for (int i = 0; i < SMTL_MAX_SEG; ++i) {
+        kp.grp[i].row_shift = op->grp[i].row_shift; kp.grp[i].nsub = op->grp[i].nsub; kp.grp[i].kblocks = op->grp[i].kblocks;
+        kp.grp[i].src = op->grp[i].src; kp.grp[i].a_col0 = op->grp[i].a_col0; kp.grp[i].kb0 = op->grp[i].kb0;
+    }
+    memcpy(&kp.tm_x8[0], op->tmap_x8[0], 128);
+    memcpy(&kp.tm_x8[1], op->tmap_x8[1], 128);
     kp.rowmap = g.rowmap;
     kp.up_py = g.up_parity >> 1;
     kp.up_px = g.up_parity & 1;
