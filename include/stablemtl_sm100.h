@@ -39,7 +39,12 @@ enum { SMTL_ACT_NONE = 0, SMTL_ACT_GELU = 1, SMTL_ACT_GEGLU = 2, SMTL_ACT_SILU =
 /* CONV_PAD_UP2: like CONV_PAD, but GEMM row = padded pixel (y, x) of the LOW-resolution map and the output row is
  * pixel (2y + py, 2x + px) of the 2x nearest-upsampled map (one of the four output parities of "upsample then 3x3
  * conv", each of which is a 2x2 conv on the low-resolution input; src/model/resnet.py:58-72, diffusers Upsample2D) */
-enum { SMTL_ROWMAP_IDENTITY = 0, SMTL_ROWMAP_CONV_PAD = 1, SMTL_ROWMAP_CONV_PAD_UP2 = 2 };
+/* The three *_PAD variants write the OUTPUT (and read the residuals) in the padded layout too, so a chain of convs
+ * never leaves it: PAD_KEEP = padded row -> same padded row, halo rows of the output are written as zeros;
+ * TO_PAD = GEMM rows are compact pixels (token linears, im2col GEMMs), output row = padded index;
+ * UP2_PAD = CONV_PAD_UP2 with a padded (2h+2) x (2w+2) output map.  TO_PAD / UP2_PAD leave the output halo untouched. */
+enum { SMTL_ROWMAP_IDENTITY = 0, SMTL_ROWMAP_CONV_PAD = 1, SMTL_ROWMAP_CONV_PAD_UP2 = 2, SMTL_ROWMAP_PAD_KEEP = 3,
+       SMTL_ROWMAP_TO_PAD = 4, SMTL_ROWMAP_UP2_PAD = 5 };
 /* 16-bit operand format of a call (field `fmt16`): the buffers named *_bf16 hold bf16 (0) or IEEE fp16 (1).
  * Both run at the same tcgen05 kind::f16 rate with fp32 accumulation; fp16 conversions saturate at +-65504. */
 enum { SMTL_FMT_BF16 = 0, SMTL_FMT_F16 = 1 };
@@ -248,6 +253,8 @@ typedef struct smtl_gnapply_args {
     int32_t c0, c1;
     int32_t x_fmt16;        /* 0: x0/x1 are fp32; 1: 16-bit (fmt16) */
     int32_t stats_replicas;
+    int32_t x_padded;       /* 1: x0/x1 are in the padded layout [batch, h+2, w+2, c] (halo ignored) */
+    int32_t pad2_;
     const float* stats0;    /* fp32 [stats_replicas, batch, c0, 2] */
     const float* stats1;    /* fp32 [stats_replicas, batch, c1, 2] or NULL */
     int32_t batch, h, w;

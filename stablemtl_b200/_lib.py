@@ -14,7 +14,8 @@ MAX_SEG = 12
 MAX_TASKS = 8
 
 ACT_NONE, ACT_GELU, ACT_GEGLU, ACT_SILU = 0, 1, 2, 3
-ROWMAP_IDENTITY, ROWMAP_CONV_PAD, ROWMAP_CONV_PAD_UP2 = 0, 1, 2
+(ROWMAP_IDENTITY, ROWMAP_CONV_PAD, ROWMAP_CONV_PAD_UP2, ROWMAP_PAD_KEEP, ROWMAP_TO_PAD,
+ ROWMAP_UP2_PAD) = range(6)
 FMT_BF16, FMT_F16 = 0, 1
 MAP_MEAN1, MAP_RGB3, MAP_NORMAL, MAP_FLOW2, MAP_FLOW3, MAP_SEMANTIC = range(6)
 (OP_GEMM, OP_FATTN, OP_SOFTMAX, OP_XATTN, OP_TASKATTN, OP_GN, OP_LN, OP_UPSAMPLE, OP_IM2COL, OP_RGBPREP,
@@ -120,7 +121,7 @@ class GnArgs(C.Structure):
 class GnApplyArgs(C.Structure):
     _fields_ = [
         ("x0", vp), ("x1", vp), ("c0", i32), ("c1", i32),
-        ("x_fmt16", i32), ("stats_replicas", i32),
+        ("x_fmt16", i32), ("stats_replicas", i32), ("x_padded", i32), ("pad2_", i32),
         ("stats0", vp), ("stats1", vp),
         ("batch", i32), ("h", i32), ("w", i32), ("groups", i32), ("eps", f32), ("silu", i32),
         ("gamma", vp), ("beta", vp),

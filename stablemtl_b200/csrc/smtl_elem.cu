@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(320, 3) gn_apply2_kernel(
     const void* __restrict__ x0, const void* __restrict__ x1, int c0, int c1, const float* __restrict__ st0,
     const float* __restrict__ st1, int replicas, int batch, int h, int w, int groups, float eps,
     const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu, int pad_out,
-    uint16_t* __restrict__ out, uint16_t* __restrict__ raw, int fmt, FastDiv div_wp) {
+    uint16_t* __restrict__ out, uint16_t* __restrict__ raw, int fmt, FastDiv div_wp, int in_pad) {
     extern __shared__ float sm[];   // scale[C], shift[C], gmean[groups], grstd[groups]
     const int C = c0 + c1;
     float* scale = sm;              // first used as per-channel sum
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(320, 3) gn_apply2_kernel(
     int ld, cc;
     if (c < c0) { src = x0; ld = c0; cc = c; } else { src = x1; ld = c1; cc = c - c0; }
     constexpr int U = 4;                                       // independent 16-byte loads in flight per thread
-    const int64_t in_base = (int64_t)b * hw;
+    const int64_t in_base = in_pad ? (int64_t)b * (h + 2) * (w + 2) : (int64_t)b * hw;
     const int64_t out_base = (int64_t)b * npix;
     for (uint32_t p0 = blockIdx.x * U * ppb + pl; p0 < npix; p0 += gridDim.x * U * ppb) {
         uint4 u[U];
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(320, 3) gn_apply2_kernel(
             inter[k] = interior;
             u[k] = make_uint4(0, 0, 0, 0);
             if (interior) {
-                const int64_t eidx = (in_base + (int64_t)y * w + x) * ld + cc;
+                const int64_t eidx = (in_pad ? in_base + (int64_t)(y + 1) * (w + 2) + x + 1 : in_base + (int64_t)y * w + x) * ld + cc;
                 if (x16) {
                     u[k] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(src) + eidx));
                 } else {
@@ -750,7 +750,7 @@ extern "C" int smtl_gnapply_run(const smtl_gnapply_args* a, void* stream) {
     kern<<<dim3(bpi, a->batch), threads, smem, st>>>(
         a->x0, a->x1, a->c0, a->c1, a->stats0, a->stats1, a->stats_replicas, a->batch, a->h, a->w,
         a->groups, a->eps, a->gamma, a->beta, a->silu, a->pad_out, reinterpret_cast<uint16_t*>(a->out_bf16),
-        reinterpret_cast<uint16_t*>(a->raw_bf16), a->fmt16, make_fastdiv((uint32_t)wp));
+        reinterpret_cast<uint16_t*>(a->raw_bf16), a->fmt16, make_fastdiv((uint32_t)wp), a->x_padded);
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;
 }

@@ -98,12 +98,46 @@ __device__ __forceinline__ float warp_transpose_sum(float (&s)[32], int lane) {
     return s[0];
 }
 
+// GEMM row -> output row for every SMTL_ROWMAP_* (see the header).  `halo` = a padded GEMM row that is not an interior
+// pixel (PAD_KEEP stores zeros there; everyone else stores nothing).
+__device__ __forceinline__ void map_row(const GemmKParams& p, int64_t grow, bool& ok, int64_t& orow, bool& halo) {
+    ok = grow < p.m;
+    orow = grow;
+    halo = false;
+    if (p.rowmap == SMTL_ROWMAP_IDENTITY) return;
+    if (p.rowmap == SMTL_ROWMAP_TO_PAD) {                    // compact pixel -> padded index
+        const int hw = p.img_h * p.img_w;
+        const int64_t img = grow / hw;
+        const int rem = (int)(grow - img * hw);
+        const int y = rem / p.img_w, x = rem - y * p.img_w;
+        orow = (img * (p.img_h + 2) + y + 1) * (int64_t)(p.img_w + 2) + x + 1;
+        return;
+    }
+    const int wp = p.img_w + 2;
+    const int plane = (p.img_h + 2) * wp;
+    const int64_t img = grow / plane;
+    const int rem = (int)(grow - img * plane);
+    const int yp = rem / wp, xp = rem - yp * wp;
+    const bool interior = yp >= 1 && yp <= p.img_h && xp >= 1 && xp <= p.img_w;
+    halo = ok && !interior;
+    ok = ok && interior;
+    if (p.rowmap == SMTL_ROWMAP_CONV_PAD)
+        orow = (img * p.img_h + (yp - 1)) * p.img_w + (xp - 1);
+    else if (p.rowmap == SMTL_ROWMAP_CONV_PAD_UP2)           // output parity (py, px) of the compact 2x map
+        orow = (img * (2 * p.img_h) + 2 * (yp - 1) + p.up_py) * (int64_t)(2 * p.img_w) + 2 * (xp - 1) + p.up_px;
+    else if (p.rowmap == SMTL_ROWMAP_UP2_PAD)                // ... of the padded 2x map
+        orow = (img * (2 * p.img_h + 2) + 2 * (yp - 1) + p.up_py + 1) * (int64_t)(2 * p.img_w + 2) + 2 * (xp - 1) +
+               p.up_px + 1;
+    // PAD_KEEP: orow = grow
+}
+
 // Per-thread state of one tile's epilogue, computed BEFORE waiting for the accumulator so that the residual
 // prefetches and the bias loads overlap the tile's MMAs.
 template <int BN>
 struct EpiRow {
     int64_t orow;          // output row of this thread's accumulator row
     bool row_ok;           // false: halo / out-of-range row (nothing stored)
+    bool halo;             // PAD_KEEP: this halo row of the output is zeroed
     int img;               // image of the output row (statistics), -1 if !row_ok
     int img_lo, img_hi;    // warp-wide range of img over valid rows (img_lo > img_hi: no valid row)
     float row_bias;
@@ -115,20 +149,8 @@ __device__ __forceinline__ void epilogue_prepare(const GemmKParams& p, int64_t g
     const bool geglu = (p.act == SMTL_ACT_GEGLU);
     const int out_bn = geglu ? BN / 2 : BN;
     const int n0 = tn * BN;
-    e.row_ok = grow < p.m;
-    e.orow = grow;
-    if (p.rowmap != SMTL_ROWMAP_IDENTITY) {
-        const int wp = p.img_w + 2;
-        const int plane = (p.img_h + 2) * wp;
-        const int64_t img = grow / plane;
-        const int rem = (int)(grow - img * plane);
-        const int yp = rem / wp, xp = rem - yp * wp;
-        e.row_ok = e.row_ok && yp >= 1 && yp <= p.img_h && xp >= 1 && xp <= p.img_w;
-        if (p.rowmap == SMTL_ROWMAP_CONV_PAD)
-            e.orow = (img * p.img_h + (yp - 1)) * p.img_w + (xp - 1);
-        else                                            // CONV_PAD_UP2: output parity (py, px) of the 2x map
-            e.orow = (img * (2 * p.img_h) + 2 * (yp - 1) + p.up_py) * (int64_t)(2 * p.img_w) + 2 * (xp - 1) + p.up_px;
-    }
+    map_row(p, grow, e.row_ok, e.orow, e.halo);
+    e.halo = e.halo && (p.rowmap == SMTL_ROWMAP_PAD_KEEP);
     e.row_bias = (p.bias && p.bias_per_row && grow < p.m) ? __ldg(p.bias + grow) : 0.0f;
 #pragma unroll
     for (int k = 0; k < BN / 32; ++k) {
@@ -287,6 +309,16 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t tad
                     for (int j = 0; j < 32; ++j)
                         if (ocol + j < p.n_out) dst[j] = to16(v[j], p.fmt);
                 }
+            }
+        }
+        if (e.halo && p.out_bf16) {                 // PAD_KEEP: the output keeps a zero halo for its consumers
+            uint16_t* dst = p.out_bf16 + orow * (int64_t)p.ldc + ocol;
+            if (full && (p.ldc & 7) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) st_global_v4_b32(dst + j, 0u, 0u, 0u, 0u);
+            } else {
+                for (int j = 0; j < 32; ++j)
+                    if (ocol + j < p.n_out) dst[j] = 0;
             }
         }
         __syncwarp();   // reconverge before the next warp-collective instruction
@@ -761,19 +793,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
             for (int c0 = half * 32; c0 < TBN; c0 += 64) {
                 // pixel (c0 + lane): output row, validity, image
                 const int64_t grow = pix0 + c0 + lane;
-                bool ok = grow < p.m;
-                int64_t orow = grow;
-                if (p.rowmap == SMTL_ROWMAP_CONV_PAD) {
-                    const int wp = p.img_w + 2;
-                    const int plane = (p.img_h + 2) * wp;
-                    const int64_t img = grow / plane;
-                    const int rem = (int)(grow - img * plane);
-                    const int yp = rem / wp, xp = rem - yp * wp;
-                    ok = ok && yp >= 1 && yp <= p.img_h && xp >= 1 && xp <= p.img_w;
-                    orow = (img * p.img_h + (yp - 1)) * p.img_w + (xp - 1);
-                }
+                bool ok, halo;
+                int64_t orow;
+                map_row(p, grow, ok, orow, halo);
+                halo = halo && (p.rowmap == SMTL_ROWMAP_PAD_KEEP);
                 const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
-                if (okmask == 0 && pix0 + c0 >= p.m) break;             // warp-uniform: past the end
+                const uint32_t halomask = __ballot_sync(0xffffffffu, halo);
+                if ((okmask | halomask) == 0 && pix0 + c0 >= p.m) break;             // warp-uniform: past the end
                 const int orow32 = (int)orow;
                 const int img_l = (p.stats && ok) ? (int)(orow / p.stats_rpi) : -1;
                 uint32_t rr[32];
@@ -781,11 +807,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
                 tmem_ld_32x32(taddr + c0, rr);
                 // rows this lane moves on the coalesced side: pixel 8 i + lane / 4
                 int orow_i[4];
-                uint32_t ok_i = 0;
+                uint32_t ok_i = 0, halo_i = 0;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     orow_i[i] = __shfl_sync(0xffffffffu, orow32, 8 * i + (lane >> 2));
                     ok_i |= ((okmask >> (8 * i + (lane >> 2))) & 1u) << i;
+                    halo_i |= ((halomask >> (8 * i + (lane >> 2))) & 1u) << i;
                 }
                 uint4 rq[4];
                 if (p.res1) {                                            // 16-bit residual, issued before the TMEM wait
@@ -821,6 +848,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
                     const uint4 q = *reinterpret_cast<const uint4*>(stg + (8 * i + (lane >> 2)) * 80 + piece * 16);
                     if (((ok_i >> i) & 1u) && piece_ok)
                         *reinterpret_cast<uint4*>(p.out_bf16 + (int64_t)orow_i[i] * p.ldc + cpiece) = q;
+                    else if (((halo_i >> i) & 1u) && piece_ok)       // PAD_KEEP: zero halo
+                        *reinterpret_cast<uint4*>(p.out_bf16 + (int64_t)orow_i[i] * p.ldc + cpiece) = make_uint4(0, 0, 0, 0);
                 }
                 __syncwarp();
                 if (p.stats && okmask) {
@@ -950,7 +979,7 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
     SMTL_CHECK_ARG(g.fmt16 == SMTL_FMT_BF16 || g.fmt16 == SMTL_FMT_F16, "gemm_plan: bad fmt16 %d", g.fmt16);
     if (g.rowmap != SMTL_ROWMAP_IDENTITY)
         SMTL_CHECK_ARG(g.img_h > 0 && g.img_w > 0, "gemm_plan: conv row map needs img_h/img_w");
-    SMTL_CHECK_ARG(g.rowmap >= SMTL_ROWMAP_IDENTITY && g.rowmap <= SMTL_ROWMAP_CONV_PAD_UP2, "gemm_plan: bad rowmap");
+    SMTL_CHECK_ARG(g.rowmap >= SMTL_ROWMAP_IDENTITY && g.rowmap <= SMTL_ROWMAP_UP2_PAD, "gemm_plan: bad rowmap");
     SMTL_CHECK_ARG(g.up_parity >= 0 && g.up_parity <= 3, "gemm_plan: bad up_parity");
     if (g.group_rows) {
         SMTL_CHECK_ARG(g.group_rows > 0 && g.group_rows % BLOCK_M == 0 && g.m % g.group_rows == 0,
@@ -999,7 +1028,7 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
     {
         const char* env = getenv("SMTL_GEMM_SWAP");
         const bool allow = !(env && env[0] == '0');
-        const bool eligible = g.group_rows == 0 && g.rowmap != SMTL_ROWMAP_CONV_PAD_UP2 && g.n <= 128 && g.n >= 64 && g.n % 8 == 0 && g.act == SMTL_ACT_NONE && !g.bias_per_row &&
+        const bool eligible = g.group_rows == 0 && g.n <= 128 && g.n >= 64 && g.n % 8 == 0 && g.act == SMTL_ACT_NONE && !g.bias_per_row &&
                               g.out_bf16 && !g.out_f32 && !g.aux_bf16 && !g.res2 && (!g.res1 || g.res_fmt16 == 1) &&
                               (g.ldc % 8) == 0 && (!g.res1 || (g.ldres % 8) == 0) && g.block_n == 0 &&
                               g.cta_group == 0 && g.m >= (int64_t)sms * TBN;

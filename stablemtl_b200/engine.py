@@ -559,25 +559,42 @@ class VAEWeights:
 
 
 class _VAEBase(_PlanBase):
+    """`self.padded`: every inter-layer map of the plan stays in the zero-halo padded layout (conv outputs are written
+    there by the epilogue: ROWMAP_PAD_KEEP / TO_PAD / UP2_PAD), so a ResNet's shortcut operand and an up-conv's input
+    are the raw maps themselves -- no padded copies."""
+    padded = False
+
+    def _rows(self, h, w):
+        return self.B * ((h + 2) * (w + 2) if self.padded else h * w)
+
+    def _rpi(self, h, w):
+        return (h + 2) * (w + 2) if self.padded else h * w
+
+    def _new_map(self, h, w, C):
+        return Act(self.pool.alloc((self._rows(h, w), C), ops.h16()), self.arena.new(self.B, C))
+
     def _resnet(self, p, x, h, w, cout):
         W, P, add, B, G = self.W, self.pool, self.plan.add, self.B, self.W.cfg.norm_num_groups
         wt = W.resnet(p)
         cin = x.shape[1]
         short = wt.get(p + ".short", False)
+        pd = self.padded
         a1 = P.alloc((B * (h + 2) * (w + 2), cin), ops.h16())
-        raw = P.alloc((B * (h + 2) * (w + 2), cin), ops.h16()) if short else None
+        raw = P.alloc((B * (h + 2) * (w + 2), cin), ops.h16()) if (short and not pd) else None
         add(ops.gn_apply(x.t, x.stats, B, h, w, wt[p + ".n1g"], wt[p + ".n1b"], a1, eps=1e-6, silu=True, pad_out=True,
-                         raw=raw, groups=G))
-        h1 = self._new_act(B, h * w, cout)
-        add(ops.conv3x3(a1, wt[p + ".w1"], B, h, w, bias=wt[p + ".b1"], name="vae.conv1", **self._into(h1, h * w)))
+                         raw=raw, groups=G, x_padded=pd))
+        h1 = self._new_map(h, w, cout)
+        add(ops.conv3x3(a1, wt[p + ".w1"], B, h, w, bias=wt[p + ".b1"], name="vae.conv1", pad_out=pd,
+                        **self._into(h1, self._rpi(h, w))))
         P.release(a1)
         a2 = P.alloc((B * (h + 2) * (w + 2), cout), ops.h16())
         add(ops.gn_apply(h1.t, h1.stats, B, h, w, wt[p + ".n2g"], wt[p + ".n2b"], a2, eps=1e-6, silu=True, pad_out=True,
-                         groups=G))
+                         groups=G, x_padded=pd))
         P.release(h1)
-        out = self._new_act(B, h * w, cout)
-        add(ops.conv3x3(a2, wt[p + ".w2"], B, h, w, a_short=raw, bias=wt[p + ".b2"], res1=None if short else x.t,
-                        name="vae.conv2", **self._into(out, h * w)))
+        out = self._new_map(h, w, cout)
+        a_short = (x.t if pd else raw) if short else None        # padded mode: the raw input map IS the shortcut operand
+        add(ops.conv3x3(a2, wt[p + ".w2"], B, h, w, a_short=a_short, bias=wt[p + ".b2"], res1=None if short else x.t,
+                        name="vae.conv2", pad_out=pd, **self._into(out, self._rpi(h, w))))
         P.release(a2, raw)
         return out
 
@@ -591,7 +608,7 @@ class _VAEBase(_PlanBase):
         Np = (N + 7) // 8 * 8
         xn = P.alloc((M, C), ops.h16())
         add(ops.gn_apply(x.t, x.stats, B, h, w, wt[p + ".ng"], wt[p + ".nb"], xn, eps=1e-6, silu=False, pad_out=False,
-                         groups=G))
+                         groups=G, x_padded=self.padded))
         qk = P.alloc((M, 2 * C), ops.h16())
         add(ops.gemm(xn, wt[p + ".qk.w"], bias=wt[p + ".qk.b"], out_bf16=qk, name="vae.qk"))
         o = P.alloc((M, C), ops.h16())
@@ -605,8 +622,10 @@ class _VAEBase(_PlanBase):
             add(ops.softmax_rows(S[:, :N], Pm[:, :N], float(C) ** -0.5))
             add(ops.gemm(Pm[:, :N], vT[:, :N], out_bf16=o[r], name="vae.pv"))
         P.release(vT, S, Pm, qk, xn)
-        out = self._new_act(B, N, C)
-        add(ops.gemm(o, wt[p + ".o.w"], bias=wt[p + ".o.b"], res1=x.t, name="vae.attn_out", **self._into(out, N)))
+        out = self._new_map(h, w, C)
+        extra = dict(rowmap=L.ROWMAP_TO_PAD, img_hw=(h, w)) if self.padded else {}
+        add(ops.gemm(o, wt[p + ".o.w"], bias=wt[p + ".o.b"], res1=x.t, name="vae.attn_out",
+                     **self._into(out, self._rpi(h, w)), **extra))
         P.release(o)
         return out
 
@@ -675,6 +694,7 @@ class VAEEncodePlan(_VAEBase):
 
 class VAEDecodePlan(_VAEBase):
     """decode_output (stablemtl_pipeline.py:626-643): latent fp32 [B*h*w, 4] -> decoder output fp32 [B*H*W, 3]."""
+    padded = True
 
     def __init__(self, W: VAEWeights, B, h, w, pool=None, latent=None):
         self.W, self.B = W, B
@@ -693,9 +713,9 @@ class VAEDecodePlan(_VAEBase):
         col = P.alloc((B * h * w, 64), ops.h16())
         add(ops.im2col(z.view(B, h, w, lat), B, h, w, col, stride=1, pad_t=1, pad_l=1, oh=h, ow=w))
         P.release(z)
-        x = self._new_act(B, h * w, c[0])
+        x = self._new_map(h, w, c[0])
         add(ops.gemm(col, W.w["dec.conv_in.w"], bias=W.w["dec.conv_in.b"], name="vae.dec.conv_in",
-                     **self._into(x, h * w)))
+                     rowmap=L.ROWMAP_TO_PAD, img_hw=(h, w), **self._into(x, self._rpi(h, w))))
         P.release(col)
         x = self._mid("decoder.mid_block", x, h, w, c[0])
         for i in range(len(c)):
@@ -705,18 +725,18 @@ class VAEDecodePlan(_VAEBase):
                 x = y
             if i < len(c) - 1:
                 # diffusers Upsample2D (nearest x2, then 3x3 conv) as four per-parity 2x2 convs on the low-res map
+                # the ResNet output is already a zero-halo padded map: it is the up-conv's operand as it stands
                 wmats, bs = W.conv_up(f"decoder.up_blocks.{i}.upsamplers.0.conv")
-                low = P.alloc((B * (h + 2) * (w + 2), c[i]), ops.h16())
-                add(ops.upsample_pad(x.t.view(B, h, w, c[i]), B, h, w, h, w, low))          # zero-halo copy
-                P.release(x)
-                x = self._new_act(B, 4 * h * w, c[i])
-                for o in ops.conv_up2x(low, wmats, B, h, w, bias=bs, name="vae.dec.up", **self._into(x, 4 * h * w)):
+                low = x
+                x = self._new_map(2 * h, 2 * w, c[i])
+                for o in ops.conv_up2x(low.t, wmats, B, h, w, bias=bs, name="vae.dec.up", pad_out=True,
+                                       **self._into(x, self._rpi(2 * h, 2 * w))):
                     add(o)
                 P.release(low)
                 h, w = 2 * h, 2 * w
         a = P.alloc((B * (h + 2) * (w + 2), c[-1]), ops.h16())
         add(ops.gn_apply(x.t, x.stats, B, h, w, W.w["decoder.ng"], W.w["decoder.nb"], a, eps=1e-6, silu=True,
-                         pad_out=True, groups=cfg.norm_num_groups))
+                         pad_out=True, groups=cfg.norm_num_groups, x_padded=True))
         P.release(x)
         self.out = torch.empty(B * h * w, 3, device=dev, dtype=F32)
         add(ops.conv3x3(a, W.w["dec.head.w"], B, h, w, bias=W.w["dec.head.b"], out_f32=self.out, name="vae.dec.head"))

@@ -205,12 +205,13 @@ def conv3x3_segs(cin, w, shortcut_cin=0):
     return segs
 
 
-def conv3x3(a_pad, wmat, batch, h, w, *, a_short=None, name="conv3x3", **epi):
-    """a_pad: bf16 [batch*(h+2)*(w+2), cin] zero-halo layout; wmat: bf16 [cout, 9*cin (+ c_short)]."""
+def conv3x3(a_pad, wmat, batch, h, w, *, a_short=None, name="conv3x3", pad_out=False, **epi):
+    """a_pad: bf16 [batch*(h+2)*(w+2), cin] zero-halo layout; wmat: bf16 [cout, 9*cin (+ c_short)].
+    pad_out: the output (and residuals) are in the padded layout as well (zero halo written)."""
     cin = a_pad.shape[1]
     cs = 0 if a_short is None else a_short.shape[1]
     op = gemm(a_pad, wmat, m=batch * (h + 2) * (w + 2), a1=a_short, segs=conv3x3_segs(cin, w, cs),
-              rowmap=L.ROWMAP_CONV_PAD, img_hw=(h, w), name=name, **epi)
+              rowmap=L.ROWMAP_PAD_KEEP if pad_out else L.ROWMAP_CONV_PAD, img_hw=(h, w), name=name, **epi)
     op.flops = 2 * batch * h * w * wmat.shape[0] * wmat.shape[1]   # algorithmic (halo rows excluded)
     return op
 
@@ -234,7 +235,7 @@ def up2x_weight_matrices(w):
     return mats
 
 
-def conv_up2x(a_pad, wmats, batch, h, w, *, name="up2x_conv", **epi):
+def conv_up2x(a_pad, wmats, batch, h, w, *, name="up2x_conv", pad_out=False, **epi):
     """nearest-2x upsample + 3x3 conv as four 2x2 implicit-GEMM convs over the padded LOW-res map a_pad
     [batch*(h+2)*(w+2), cin]; outputs land in the compact [batch*2h*2w, cout] map.  Returns the four ops."""
     cin = a_pad.shape[1]
@@ -246,7 +247,8 @@ def conv_up2x(a_pad, wmats, batch, h, w, *, name="up2x_conv", **epi):
             ys = (-1, 0) if py == 0 else (0, 1)
             xs = (-1, 0) if px == 0 else (0, 1)
             segs = [(dy * wp + dx, cin // 64, 0, 0) for dy in ys for dx in xs]
-            op = gemm(a_pad, wmats[py * 2 + px], m=batch * (h + 2) * wp, segs=segs, rowmap=L.ROWMAP_CONV_PAD_UP2,
+            op = gemm(a_pad, wmats[py * 2 + px], m=batch * (h + 2) * wp, segs=segs,
+                      rowmap=L.ROWMAP_UP2_PAD if pad_out else L.ROWMAP_CONV_PAD_UP2,
                       img_hw=(h, w), up_parity=py * 2 + px, name=name, **epi)
             op.flops = 2 * batch * h * w * wmats[0].shape[0] * 9 * cin          # algorithmic: 1/4 of the 3x3 conv
             out.append(op)
@@ -330,7 +332,7 @@ def group_norm(x0, batch, h, w, gamma, beta, out, *, x1=None, eps, silu, pad_out
 
 
 def gn_apply(x0, stats0, batch, h, w, gamma, beta, out, *, x1=None, stats1=None, eps, silu, pad_out, raw=None,
-             groups=32):
+             groups=32, x_padded=False):
     """GroupNorm(+SiLU) of the (virtually concatenated) compact map [x0 | x1] using the per-(image, channel) sums the
     producing GEMMs left in stats0 / stats1; writes the 16-bit operand of the next conv (padded) or GEMM (compact)."""
     a = L.GnApplyArgs()
@@ -344,6 +346,8 @@ def gn_apply(x0, stats0, batch, h, w, gamma, beta, out, *, x1=None, stats1=None,
         assert x1.dtype == x0.dtype and x1.is_contiguous() and stats1.shape == (stats0.shape[0], batch, x1.shape[-1], 2)
         a.x1, a.c1, a.stats1 = x1.data_ptr(), x1.shape[-1], stats1.data_ptr()
     a.batch, a.h, a.w, a.groups, a.eps = batch, h, w, groups, eps
+    a.x_padded = int(x_padded)
+    assert x0.shape[0] == batch * ((h + 2) * (w + 2) if x_padded else h * w)
     a.gamma, a.beta = gamma.data_ptr(), beta.data_ptr()
     a.silu, a.pad_out = int(silu), int(pad_out)
     a.out_bf16, a.raw_bf16 = out.data_ptr(), _ptr(raw)

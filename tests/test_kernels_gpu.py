@@ -591,3 +591,88 @@ def test_gemm_grouped_per_task_weights():
     torch.cuda.synchronize()
     ref = torch.cat([F.gelu(a[g * R:(g + 1) * R].float() @ w[g].float().t() + bias[g]) for g in range(G)])
     assert rel_l2(out.float(), ref) < 4e-3
+
+
+# ------------------------------------------------------------------ padded-layout outputs (conv chains that stay padded)
+def _unpad(x_pad, b, h, w):
+    return x_pad.reshape(b, h + 2, w + 2, -1)[:, 1:-1, 1:-1].reshape(b * h * w, -1)
+
+
+@pytest.mark.parametrize("b,h,w,cin,cout,cs", [(2, 8, 10, 64, 64, 0), (2, 30, 40, 128, 256, 128), (1, 200, 200, 128, 128, 0),
+                                               (1, 200, 200, 256, 128, 256)])
+def test_conv3x3_padded_output_zero_halo(b, h, w, cin, cout, cs):
+    """ROWMAP_PAD_KEEP (normal and swapped kernel): output and 16-bit residual in the padded layout, halo rows of the
+    output written as zeros even over a dirty buffer, statistics exclude the halo."""
+    ops, L = _ops()
+    x = rnd(b, h, w, cin, seed=1).to(H16())
+    wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=2).to(H16())
+    bias = rnd(cout, seed=3)
+    wmat = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1)
+    xs = None
+    if cs:
+        xs_nhwc = rnd(b, h, w, cs, seed=5).to(H16())
+        ws = rnd(cout, cs, scale=cs ** -0.5, seed=6).to(H16())
+        wmat = torch.cat([wmat, ws], dim=1)
+        ref = ref + F.conv2d(xs_nhwc.float().permute(0, 3, 1, 2), ws.float()[:, :, None, None])
+        xs = _pad_layout(xs_nhwc)
+        xs[xs == 0] = 7.0                                        # the shortcut source's halo may hold anything
+    res_nhwc = rnd(b, h, w, cout, seed=4).to(H16())
+    ref = ref.permute(0, 2, 3, 1).reshape(b * h * w, cout) + res_nhwc.float().reshape(b * h * w, cout)
+    res = _pad_layout(res_nhwc)
+    out = torch.full((b * (h + 2) * (w + 2), cout), 3.0, device=DEV, dtype=H16())      # dirty
+    stats = ops.new_stats(b, cout, DEV)
+    ops.conv3x3(_pad_layout(x), wmat.contiguous(), b, h, w, a_short=xs, bias=bias, res1=res, out_bf16=out, stats=stats,
+                stats_rows_per_image=(h + 2) * (w + 2), pad_out=True).run()
+    torch.cuda.synchronize()
+    assert rel_l2(_unpad(out, b, h, w).float(), ref) < 4e-3
+    o4 = out.reshape(b, h + 2, w + 2, cout).float()
+    assert o4[:, 0].abs().max() == 0 and o4[:, -1].abs().max() == 0 and o4[:, :, 0].abs().max() == 0 and o4[:, :, -1].abs().max() == 0
+    st = stats.sum(0)
+    blk = ref.reshape(b, h * w, cout).double()
+    assert rel_l2(st[:, :, 0], blk.sum(1)) < 1e-4 and rel_l2(st[:, :, 1], (blk * blk).sum(1)) < 1e-4
+
+
+def test_gemm_to_pad_and_up2x_pad_rowmaps():
+    ops, L = _ops()
+    b, h, w, k, n = 2, 15, 20, 128, 320
+    a = rnd(b * h * w, k, seed=1).to(H16())
+    wt = rnd(n, k, scale=k ** -0.5, seed=2).to(H16())
+    res_nhwc = rnd(b, h, w, n, seed=3).to(H16())
+    out = torch.zeros(b * (h + 2) * (w + 2), n, device=DEV, dtype=H16())
+    stats = ops.new_stats(b, n, DEV)
+    ops.gemm(a, wt, res1=_pad_layout(res_nhwc), out_bf16=out, rowmap=L.ROWMAP_TO_PAD, img_hw=(h, w), stats=stats,
+             stats_rows_per_image=(h + 2) * (w + 2)).run()
+    torch.cuda.synchronize()
+    ref = a.float() @ wt.float().t() + res_nhwc.float().reshape(-1, n)
+    assert rel_l2(_unpad(out, b, h, w).float(), ref) < 4e-3
+    assert rel_l2(stats.sum(0)[:, :, 0], ref.reshape(b, h * w, n).double().sum(1)) < 1e-4
+    # up2x into a padded 2x map
+    cin, cout = 64, 128
+    x = rnd(b, h, w, cin, seed=5).to(H16())
+    w3 = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=6)
+    wm = [m.to(H16()).contiguous() for m in ops.up2x_weight_matrices(w3)]
+    up_ref = F.conv2d(F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest"), w3, padding=1)
+    up_ref = up_ref.permute(0, 2, 3, 1).reshape(b * 4 * h * w, cout)
+    o2 = torch.zeros(b * (2 * h + 2) * (2 * w + 2), cout, device=DEV, dtype=H16())
+    for op in ops.conv_up2x(_pad_layout(x), wm, b, h, w, out_bf16=o2, pad_out=True):
+        op.run()
+    torch.cuda.synchronize()
+    assert rel_l2(_unpad(o2, b, 2 * h, 2 * w).float(), up_ref) < 5e-3
+
+
+def test_gn_apply_reads_padded_input():
+    ops, L = _ops()
+    b, h, w, c = 2, 8, 10, 128
+    x = (rnd(b, h, w, c, seed=1) * 2 + 0.5).to(H16())
+    xp = _pad_layout(x)
+    xp[xp == 0] = 9.0                                            # halo content must be ignored
+    st = ops.new_stats(b, c, DEV)
+    xd = x.double().reshape(b, h * w, c)
+    st[0] = torch.stack([xd.sum(1), (xd * xd).sum(1)], dim=-1).float()
+    gamma, beta = rnd(c, seed=3) + 1, rnd(c, seed=4)
+    out = torch.full((b * (h + 2) * (w + 2), c), float("nan"), device=DEV, dtype=H16())
+    ops.gn_apply(xp, st, b, h, w, gamma, beta, out, eps=1e-6, silu=True, pad_out=True, x_padded=True).run()
+    torch.cuda.synchronize()
+    ref = F.silu(F.group_norm(x.float().permute(0, 3, 1, 2), 32, gamma, beta, eps=1e-6)).permute(0, 2, 3, 1)
+    assert rel_l2(out.float(), _pad_layout(ref)) < 4e-3
