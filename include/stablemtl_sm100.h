@@ -112,6 +112,14 @@ typedef struct smtl_gemm_args {
      * [g * group_rows, (g+1) * group_rows) use weight rows [g * n, (g+1) * n) of b (stacked [groups * n, k]) and bias
      * [g * n, (g+1) * n).  group_rows must be a multiple of 128 (256 for cta_group 2); 0 = off. */
     int64_t group_rows;
+    /* Fused GroupNorm(+SiLU) of the activation operand a0 (3x3 convs over the padded layout only): a0 holds the RAW
+     * map; every tile is normalised in shared memory between TMA and the MMA with
+     *     y = silu?(x * gn_ss[img, c, 0] + gn_ss[img, c, 1])      gn_ss: fp32 [images, a0_cols, 2] (smtl_gnfinalize_run)
+     * and halo / out-of-range rows forced to zero, so no normalised copy of the map is ever written (replaces
+     * GroupNorm + SiLU at src/model/resnet.py:177-178,188,194 and diffusers ResnetBlock2D).  NULL = off. */
+    const float* gn_ss;
+    int32_t gn_silu;
+    int32_t pad3_;
 } smtl_gemm_args;
 
 typedef struct smtl_gemm_op {
@@ -270,6 +278,20 @@ typedef struct smtl_gnapply_args {
 } smtl_gnapply_args;
 int smtl_gnapply_run(const smtl_gnapply_args* a, void* stream);
 
+/* Per-(image, channel) scale / shift of a GroupNorm from the producer-side sums: ss[b, c] = (rstd * gamma, beta -
+ * mean * rstd * gamma) -- the table the fused conv prologue (smtl_gemm_args.gn_ss) applies. */
+typedef struct smtl_gnfinalize_args {
+    const float* stats;     /* fp32 [stats_replicas, batch, c, 2] */
+    int32_t stats_replicas, batch, c, groups;
+    int64_t pixels;         /* interior pixels per image (h * w) */
+    float eps;
+    int32_t pad_;
+    const float* gamma;
+    const float* beta;
+    float* ss;              /* fp32 [batch, c, 2] */
+} smtl_gnfinalize_args;
+int smtl_gnfinalize_run(const smtl_gnfinalize_args* a, void* stream);
+
 /* cudaMemsetAsync on the plan's stream (zeroing the statistics arena before the producers run). */
 typedef struct smtl_memset_args {
     void* ptr;
@@ -389,7 +411,8 @@ int smtl_taskmap_run(const smtl_taskmap_args* a, void* stream);
 enum {
     SMTL_OP_GEMM = 1, SMTL_OP_FATTN = 2, SMTL_OP_SOFTMAX = 3, SMTL_OP_XATTN = 4, SMTL_OP_TASKATTN = 5,
     SMTL_OP_GN = 6, SMTL_OP_LN = 7, SMTL_OP_UPSAMPLE = 8, SMTL_OP_IM2COL = 9, SMTL_OP_RGBPREP = 10,
-    SMTL_OP_UNETIN = 11, SMTL_OP_TASKMAP = 12, SMTL_OP_CHANMIX = 13, SMTL_OP_GNAPPLY = 14, SMTL_OP_MEMSET = 15
+    SMTL_OP_UNETIN = 11, SMTL_OP_TASKMAP = 12, SMTL_OP_CHANMIX = 13, SMTL_OP_GNAPPLY = 14, SMTL_OP_MEMSET = 15,
+    SMTL_OP_GNFINALIZE = 16
 };
 typedef struct smtl_op_ref {
     int32_t kind;

@@ -19,7 +19,7 @@ ACT_NONE, ACT_GELU, ACT_GEGLU, ACT_SILU = 0, 1, 2, 3
 FMT_BF16, FMT_F16 = 0, 1
 MAP_MEAN1, MAP_RGB3, MAP_NORMAL, MAP_FLOW2, MAP_FLOW3, MAP_SEMANTIC = range(6)
 (OP_GEMM, OP_FATTN, OP_SOFTMAX, OP_XATTN, OP_TASKATTN, OP_GN, OP_LN, OP_UPSAMPLE, OP_IM2COL, OP_RGBPREP,
- OP_UNETIN, OP_TASKMAP, OP_CHANMIX, OP_GNAPPLY, OP_MEMSET) = range(1, 16)
+ OP_UNETIN, OP_TASKMAP, OP_CHANMIX, OP_GNAPPLY, OP_MEMSET, OP_GNFINALIZE) = range(1, 17)
 
 vp = C.c_void_p
 i32 = C.c_int32
@@ -55,6 +55,7 @@ class GemmArgs(C.Structure):
         ("stats_rows_per_image", i32), ("stats_images", i32),
         ("cta_group", i32), ("up_parity", i32),
         ("group_rows", i64),
+        ("gn_ss", vp), ("gn_silu", i32), ("pad3_", i32),
     ]
 
 
@@ -130,6 +131,11 @@ class GnApplyArgs(C.Structure):
     ]
 
 
+class GnFinalizeArgs(C.Structure):
+    _fields_ = [("stats", vp), ("stats_replicas", i32), ("batch", i32), ("c", i32), ("groups", i32), ("pixels", i64),
+                ("eps", f32), ("pad_", i32), ("gamma", vp), ("beta", vp), ("ss", vp)]
+
+
 class MemsetArgs(C.Structure):
     _fields_ = [("ptr", vp), ("bytes", i64), ("value", i32), ("pad_", i32)]
 
@@ -177,11 +183,11 @@ class OpRef(C.Structure):
 
 
 STRUCTS_IN_HEADER_ORDER = [GemmSeg, GemmArgs, GemmOp, FattnArgs, FattnOp, SoftmaxArgs, XattnArgs, TaskAttnArgs,
-                           GnArgs, GnApplyArgs, MemsetArgs, LnArgs, UpsampleArgs, Im2colArgs, RgbprepArgs, UnetinArgs, ChanmixArgs, TaskmapArgs, OpRef]
+                           GnArgs, GnApplyArgs, GnFinalizeArgs, MemsetArgs, LnArgs, UpsampleArgs, Im2colArgs, RgbprepArgs, UnetinArgs, ChanmixArgs, TaskmapArgs, OpRef]
 
 EXPORTS = [
     "smtl_gemm_plan", "smtl_gemm_run", "smtl_fattn_plan", "smtl_fattn_run", "smtl_softmax_run", "smtl_xattn_run",
-    "smtl_taskattn_run", "smtl_gn_run", "smtl_gnapply_run", "smtl_memset_run", "smtl_ln_run", "smtl_upsample_run", "smtl_im2col_run", "smtl_rgbprep_run",
+    "smtl_taskattn_run", "smtl_gn_run", "smtl_gnapply_run", "smtl_gnfinalize_run", "smtl_memset_run", "smtl_ln_run", "smtl_upsample_run", "smtl_im2col_run", "smtl_rgbprep_run",
     "smtl_unetin_run", "smtl_chanmix_run", "smtl_taskmap_run", "smtl_run_plan", "smtl_plan_launches", "smtl_abi_version",
     "smtl_last_error", "smtl_struct_sizes",
 ]

@@ -84,7 +84,7 @@ int smtl_struct_sizes(int32_t* out, int32_t cap) {
         (int32_t)sizeof(smtl_gemm_seg),     (int32_t)sizeof(smtl_gemm_args),    (int32_t)sizeof(smtl_gemm_op),
         (int32_t)sizeof(smtl_fattn_args),   (int32_t)sizeof(smtl_fattn_op),     (int32_t)sizeof(smtl_softmax_args),
         (int32_t)sizeof(smtl_xattn_args),   (int32_t)sizeof(smtl_taskattn_args), (int32_t)sizeof(smtl_gn_args),
-        (int32_t)sizeof(smtl_gnapply_args), (int32_t)sizeof(smtl_memset_args),
+        (int32_t)sizeof(smtl_gnapply_args), (int32_t)sizeof(smtl_gnfinalize_args), (int32_t)sizeof(smtl_memset_args),
         (int32_t)sizeof(smtl_ln_args),      (int32_t)sizeof(smtl_upsample_args), (int32_t)sizeof(smtl_im2col_args),
         (int32_t)sizeof(smtl_rgbprep_args), (int32_t)sizeof(smtl_unetin_args),  (int32_t)sizeof(smtl_chanmix_args),
         (int32_t)sizeof(smtl_taskmap_args),
@@ -121,6 +121,7 @@ int smtl_run_plan(const smtl_op_ref* ops, int32_t n_ops, void* stream) {
             case SMTL_OP_CHANMIX: rc = smtl_chanmix_run((const smtl_chanmix_args*)p, stream); break;
             case SMTL_OP_GNAPPLY: rc = smtl_gnapply_run((const smtl_gnapply_args*)p, stream); break;
             case SMTL_OP_MEMSET: rc = smtl_memset_run((const smtl_memset_args*)p, stream); break;
+            case SMTL_OP_GNFINALIZE: rc = smtl_gnfinalize_run((const smtl_gnfinalize_args*)p, stream); break;
             default:
                 smtl_host::set_error("plan op %d: unknown kind %d", i, ops[i].kind);
                 return SMTL_EKIND;

@@ -285,6 +285,45 @@ __global__ void __launch_bounds__(320, 3) gn_apply2_kernel(
     }
 }
 
+// stats -> per-(image, channel) (scale, shift); grid = batch, one thread per channel (blockDim = C rounded up to 32)
+__global__ void gn_finalize_kernel(const float* __restrict__ st, int replicas, int batch, int c, int groups, double n_per_group,
+                                   float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ ss) {
+    extern __shared__ float sm[];   // sum[C], sq[C], mean[groups], rstd[groups]
+    float* csum = sm;
+    float* csq = sm + c;
+    float* gmean = sm + 2 * c;
+    float* grstd = gmean + groups;
+    const int b = blockIdx.x;
+    const int cpg = c / groups;
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+        float s = 0.f, q = 0.f;
+        for (int r = 0; r < replicas; ++r) {
+            const float2 t = __ldg(reinterpret_cast<const float2*>(st + (((int64_t)r * batch + b) * c + ch) * 2));
+            s += t.x;
+            q += t.y;
+        }
+        csum[ch] = s;
+        csq[ch] = q;
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        double s = 0.0, q = 0.0;
+        for (int ch = g * cpg; ch < (g + 1) * cpg; ++ch) { s += (double)csum[ch]; q += (double)csq[ch]; }
+        const double mean = s / n_per_group;
+        double var = q / n_per_group - mean * mean;
+        if (var < 0.0) var = 0.0;
+        gmean[g] = (float)mean;
+        grstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+        const int g = ch / cpg;
+        const float sc = grstd[g] * gamma[ch];
+        reinterpret_cast<float2*>(ss)[(int64_t)b * c + ch] = make_float2(sc, beta[ch] - gmean[g] * sc);
+    }
+}
+
 // ============================================================================================= LayerNorm
 // one warp per row; lane holds up to 10 float4 (C <= 1280).
 template <bool IN_BF16>
@@ -751,6 +790,19 @@ extern "C" int smtl_gnapply_run(const smtl_gnapply_args* a, void* stream) {
         a->x0, a->x1, a->c0, a->c1, a->stats0, a->stats1, a->stats_replicas, a->batch, a->h, a->w,
         a->groups, a->eps, a->gamma, a->beta, a->silu, a->pad_out, reinterpret_cast<uint16_t*>(a->out_bf16),
         reinterpret_cast<uint16_t*>(a->raw_bf16), a->fmt16, make_fastdiv((uint32_t)wp), a->x_padded);
+    SMTL_CHECK_CUDA(cudaGetLastError());
+    return SMTL_OK;
+}
+
+extern "C" int smtl_gnfinalize_run(const smtl_gnfinalize_args* a, void* stream) {
+    SMTL_CHECK_ARG(a && a->stats && a->gamma && a->beta && a->ss, "gnfinalize: NULL argument");
+    SMTL_CHECK_ARG(a->groups > 0 && a->c % a->groups == 0 && a->batch >= 1 && a->stats_replicas >= 1 && a->pixels > 0 &&
+                       a->c <= 8192 && a->groups <= 64, "gnfinalize: bad extent");
+    const size_t smem = (2 * a->c + 2 * a->groups) * sizeof(float);
+    const int threads = a->c < 256 ? ((a->c + 31) / 32) * 32 : 256;
+    gn_finalize_kernel<<<a->batch, threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+        a->stats, a->stats_replicas, a->batch, a->c, a->groups, (double)a->pixels * (a->c / a->groups), a->eps, a->gamma,
+        a->beta, a->ss);
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;
 }
