@@ -91,9 +91,9 @@ if __name__ == "__main__":
         report("conv3x3 vae head b=8 480x640 128->3", ops.conv3x3(a, wm, 8, 480, 640, bias=torch.zeros(3, device=DEV), out_f32=out))
         sys.exit(0)
     if only == "stages":
-        conv_case("vae 1/4 512->512", 8, 120, 160, 512, 512, cta_group=1)
-        conv_case("vae 1/2 256->256", 8, 240, 320, 256, 256, cta_group=1)
-        conv_case("unet L0 320->320", 112, 60, 80, 320, 320, cta_group=1)
+        conv_case("vae 1/4 512->512", 8, 120, 160, 512, 512)
+        conv_case("vae 1/2 256->256", 8, 240, 320, 256, 256)
+        conv_case("unet L2 1280->1280", 112, 15, 20, 1280, 1280)
         sys.exit(0)
     if only == "swap":
         conv_case("vae 1/1 (auto)", 8, 480, 640, 128, 128)

@@ -380,17 +380,21 @@ __global__ void __launch_bounds__(F2_THREADS, 1) smtl_fattn2_kernel(const __grid
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
             tma_load_2d(sQ, &p.tm, q_full, p.q_col0 + hd * HD, row_base + q0);
             tma_load_2d(sQ + TILE_BYTES, &p.tm, q_full, p.q_col0 + hd * HD, row_base + q0 + BQ);
-            for (int j = 0; j < ntiles; ++j) {
-                const int s = j % F2_NS;
-                mbar_wait(&kv_empty[s], ((j / F2_NS) & 1) ^ 1u);
+        }
+        __syncwarp();
+        for (int j = 0; j < ntiles; ++j) {
+            const int s = j % F2_NS;
+            mbar_wait(&kv_empty[s], ((j / F2_NS) & 1) ^ 1u);
+            if (elect_one()) {
                 mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
                 tma_load_2d(sK + s * TILE_BYTES, &p.tm, &kv_full[s], p.k_col0 + hd * HD, row_base + j * BKV);
                 tma_load_2d(sV + s * TILE_BYTES, &p.tm, &kv_full[s], p.v_col0 + hd * HD, row_base + j * BKV);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
         const uint32_t IDESC_S = make_idesc_16(BQ, BKV, 0, 0, p.fmt);   // S[128,128] = Q[128,64] K[128,64]^T
@@ -403,10 +407,12 @@ __global__ void __launch_bounds__(F2_THREADS, 1) smtl_fattn2_kernel(const __grid
             for (int k = 0; k < HD / 16; ++k) tc_mma_f16(tmem_base + w * 128, dq + 2 * k, dk + 2 * k, IDESC_S, k != 0);
             tc_commit(&s_full[w]);
         };
+        // converged warp; elect.sync picks the issuing lane at the instructions (a lane-id branch makes ptxas wrap
+        // every UTCHMMA in a ~165-clk uniform-register waterfall loop, see smtl_gemm.cu)
         mbar_wait(q_full, 0);
         mbar_wait(&kv_full[0], 0);
         tc_fence_after();
-        if (lane == 0)
+        if (elect_one())
             for (int w = 0; w < ntile_q; ++w) issue_s(w, 0);
         __syncwarp();
         for (int j = 0; j < ntiles; ++j) {
@@ -416,11 +422,12 @@ __global__ void __launch_bounds__(F2_THREADS, 1) smtl_fattn2_kernel(const __grid
                 mbar_wait(&p_full[w], j & 1);                 // softmax wrote P_w(j) and rescaled O_w
                 if (w == 0 && j + 1 < ntiles) mbar_wait(&kv_full[sn], ((j + 1) / F2_NS) & 1);
                 tc_fence_after();
-                if (lane == 0) {
+                const uint32_t sv = smem_u32(sV + s * TILE_BYTES);
+                if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < BKV / 16; ++k) {
                         // V rows (kv) 16k .. 16k+16: 16 rows * 128 B = 2048 B per K step; P: 8 TMEM columns per step
-                        const uint64_t dv = make_smem_desc_sw128(smem_u32(sV + s * TILE_BYTES) + k * 16 * 128);
+                        const uint64_t dv = make_smem_desc_sw128(sv + k * 16 * 128);
                         tc_mma_f16_ts(tmem_base + 256 + w * 64, tmem_base + w * 128 + 8 * k, dv, IDESC_O, (j | k) != 0);
                     }
                     if (j + 1 < ntiles) issue_s(w, sn);       // in-order after PV_w(j): may overwrite P_w(j)
@@ -428,7 +435,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) smtl_fattn2_kernel(const __grid
                 }
                 __syncwarp();
             }
-            if (lane == 0) tc_commit(&kv_empty[s]);            // K(j), V(j) consumed by every MMA issued so far
+            if (elect_one()) tc_commit(&kv_empty[s]);          // K(j), V(j) consumed by every MMA issued so far
             __syncwarp();
         }
     } else {

@@ -24,6 +24,7 @@ constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int NUM_THREADS = 320;                   // TMA warp + MMA warp + 8 epilogue warps
 constexpr int EPI_WARPS = 8;
 constexpr int SMEM_BUDGET = 227 * 1024;
+constexpr int GEMM_MAX_STAGES = 24;                // mbarrier slots of smtl_gemm_kernel's rings (activation + weight)
 
 struct alignas(64) GemmKParams {
     CUtensorMap tm_a0;
@@ -358,13 +359,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
     constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     constexpr int TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
     constexpr int ACC_STRIDE = TMEM_COLS / 2;
-    constexpr int MAX_STAGES = 12;
+    constexpr int MAX_STAGES = GEMM_MAX_STAGES;
 
     constexpr int PB = (BLOCK_M + 8) * BLOCK_K * 2;                  // grouped mode: activation tile with 8 extra rows
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stages = p.stages;
-    const bool grouped = (CG == 1) && p.grouped;
+    const bool grouped = p.grouped != 0;
     uint8_t* smem_w = smem + (size_t)p.sp * PB;                       // grouped mode: weight ring after the activation ring
     uint64_t* bars = reinterpret_cast<uint64_t*>(
         grouped ? smem_w + (size_t)p.sw * B_STAGE_BYTES : smem + (size_t)stages * STAGE_BYTES);
@@ -408,34 +409,54 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0 && grouped) {
+        // converged warp, elect.sync at the TMA issue (same reason as for the MMA warp below)
+        if (grouped) {
             int ps = 0, ws = 0;
             uint32_t pph = 0, wph = 0;
             for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
-                const int64_t m0 = (int64_t)tm * BLOCK_M;
-                const int n0 = tn * BN + (p.group_rows ? (int)(m0 / p.group_rows) * p.n : 0);
+                const int64_t m0 = ((int64_t)tm * CG + rank) * BLOCK_M;
+                const int n0 = tn * BN + (int)rank * B_ROWS +
+                               (p.group_rows ? (int)(((int64_t)tm * CG * BLOCK_M) / p.group_rows) * p.n : 0);
                 for (int g = 0; g < p.ngrp; ++g) {
                     const GemmKParams::Grp gr = p.grp[g];
                     const CUtensorMap* tma = gr.src ? &p.tm_a1 : &p.tm_a0;
                     for (int kb = 0; kb < gr.kblocks; ++kb) {
                         mbar_wait(&empty_bar[ps], pph ^ 1u);
-                        mbar_arrive_expect_tx(&full_bar[ps], PB);
-                        tma_load_2d(smem + (size_t)ps * PB, tma, &full_bar[ps], gr.a_col0 + kb * BLOCK_K,
-                                    (int32_t)(m0 + gr.row_shift));
+                        if (elect_one()) {
+                            if (CG == 1) {
+                                mbar_arrive_expect_tx(&full_bar[ps], PB);
+                                tma_load_2d(smem + (size_t)ps * PB, tma, &full_bar[ps], gr.a_col0 + kb * BLOCK_K,
+                                            (int32_t)(m0 + gr.row_shift));
+                            } else {        // both CTAs' tiles complete on the LEADER's barrier
+                                if (leader) mbar_arrive_expect_tx(&full_bar[ps], 2 * PB);
+                                tma_load_2d_pair(smem + (size_t)ps * PB, tma, mapa_u32(&full_bar[ps], 0),
+                                                 gr.a_col0 + kb * BLOCK_K, (int32_t)(m0 + gr.row_shift));
+                            }
+                        }
+                        __syncwarp();
                         if (++ps == p.sp) { ps = 0; pph ^= 1u; }
                         for (int sub = 0; sub < gr.nsub; ++sub) {
                             const int wb = p.sp + ws;
                             mbar_wait(&empty_bar[wb], wph ^ 1u);
-                            mbar_arrive_expect_tx(&full_bar[wb], B_STAGE_BYTES);
-                            tma_load_2d(smem_w + (size_t)ws * B_STAGE_BYTES, &p.tm_b, &full_bar[wb],
-                                        (gr.kb0 + sub * gr.kblocks + kb) * BLOCK_K, n0);
+                            if (elect_one()) {
+                                const int kcol = (gr.kb0 + sub * gr.kblocks + kb) * BLOCK_K;
+                                if (CG == 1) {
+                                    mbar_arrive_expect_tx(&full_bar[wb], B_STAGE_BYTES);
+                                    tma_load_2d(smem_w + (size_t)ws * B_STAGE_BYTES, &p.tm_b, &full_bar[wb], kcol, n0);
+                                } else {
+                                    if (leader) mbar_arrive_expect_tx(&full_bar[wb], 2 * B_STAGE_BYTES);
+                                    tma_load_2d_pair(smem_w + (size_t)ws * B_STAGE_BYTES, &p.tm_b,
+                                                     mapa_u32(&full_bar[wb], 0), kcol, n0);
+                                }
+                            }
+                            __syncwarp();
                             if (++ws == p.sw) { ws = 0; wph ^= 1u; }
                         }
                     }
                 }
             }
-        } else if (lane == 0) {
+        } else {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = tile0; tile < num_tiles; tile += tile_step) {
@@ -452,17 +473,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
                         mbar_wait(&empty_bar[stage], phase ^ 1u);
                         uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
                         uint8_t* sb = sa + A_STAGE_BYTES;
-                        if (CG == 1) {
-                            mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-                            tma_load_2d(sa, tma, &full_bar[stage], sg.a_col0 + kb * BLOCK_K, arow);
-                            tma_load_2d(sb, &p.tm_b, &full_bar[stage], kb_global * BLOCK_K, n0);
-                        } else {
-                            // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of both
-                            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
-                            const uint32_t bar = mapa_u32(&full_bar[stage], 0);
-                            tma_load_2d_pair(sa, tma, bar, sg.a_col0 + kb * BLOCK_K, arow);
-                            tma_load_2d_pair(sb, &p.tm_b, bar, kb_global * BLOCK_K, n0);
+                        if (elect_one()) {
+                            if (CG == 1) {
+                                mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                                tma_load_2d(sa, tma, &full_bar[stage], sg.a_col0 + kb * BLOCK_K, arow);
+                                tma_load_2d(sb, &p.tm_b, &full_bar[stage], kb_global * BLOCK_K, n0);
+                            } else {
+                                // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of both
+                                if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+                                const uint32_t bar = mapa_u32(&full_bar[stage], 0);
+                                tma_load_2d_pair(sa, tma, bar, sg.a_col0 + kb * BLOCK_K, arow);
+                                tma_load_2d_pair(sb, &p.tm_b, bar, kb_global * BLOCK_K, n0);
+                            }
                         }
+                        __syncwarp();
                         if (++stage == stages) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -470,8 +494,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        // The whole warp runs the loop CONVERGED and elect.sync picks the issuing lane right at the instructions (the
+        // CUTLASS idiom).  Under a lane-id branch (`if (lane == 0)`) ptxas cannot prove that the operands of UTCHMMA /
+        // UTCBAR are warp-uniform and wraps every MMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop: ~165 clk
+        // of issue overhead per MMA (ncu source view), a floor above the 16..128 tensor cycles of the MMA itself.
         if (leader && grouped) {
-            const uint32_t IDESC = make_idesc_16(BLOCK_M, BN, 0, 0, p.fmt);
+            const uint32_t IDESC = make_idesc_16(BLOCK_M * CG, BN, 0, 0, p.fmt);
             int ps = 0, ws = 0;
             uint32_t pph = 0, wph = 0;
             int it = 0;
@@ -490,26 +518,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
                             const int wb = p.sp + ws;
                             mbar_wait(&full_bar[wb], wph);
                             tc_fence_after();
-                            if (lane == 0) {
-                                const uint64_t da = make_smem_desc_sw128(sa + sub * 128);      // tap `sub`: one row further
-                                const uint64_t db = make_smem_desc_sw128(smem_u32(smem_w + (size_t)ws * B_STAGE_BYTES));
+                            const uint64_t da = make_smem_desc_sw128(sa + sub * 128);      // tap `sub`: one row further
+                            const uint64_t db = make_smem_desc_sw128(smem_u32(smem_w + (size_t)ws * B_STAGE_BYTES));
+                            if (elect_one()) {
 #pragma unroll
                                 for (int k = 0; k < BLOCK_K / 16; ++k) {
-                                    tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, accum);
-                                    accum = 1;
+                                    if (CG == 1)
+                                        tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, accum | (uint32_t)k);
+                                    else
+                                        tc_mma_f16_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, accum | (uint32_t)k);
                                 }
-                                tc_commit(&empty_bar[wb]);
+                                if (CG == 1) tc_commit(&empty_bar[wb]); else tc_commit_pair(&empty_bar[wb]);
                             }
                             accum = 1;
                             __syncwarp();
                             if (++ws == p.sw) { ws = 0; wph ^= 1u; }
                         }
-                        if (lane == 0) tc_commit(&empty_bar[ps]);
+                        if (elect_one()) { if (CG == 1) tc_commit(&empty_bar[ps]); else tc_commit_pair(&empty_bar[ps]); }
                         __syncwarp();
                         if (++ps == p.sp) { ps = 0; pph ^= 1u; }
                     }
                 }
-                if (lane == 0) tc_commit(&acc_full[acc]);
+                if (elect_one()) { if (CG == 1) tc_commit(&acc_full[acc]); else tc_commit_pair(&acc_full[acc]); }
                 __syncwarp();
             }
         } else if (leader) {
@@ -526,10 +556,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
                 for (int kb = 0; kb < p.total_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    if (lane == 0) {
-                        const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-                        const uint64_t da = make_smem_desc_sw128(sa);
-                        const uint64_t db = make_smem_desc_sw128(sa + A_STAGE_BYTES);
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+                    const uint64_t da = make_smem_desc_sw128(sa);
+                    const uint64_t db = make_smem_desc_sw128(sa + A_STAGE_BYTES);
+                    if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / 16; ++k) {
                             // +32 B per 16-element K step inside the swizzle atom: start-address field += 2
@@ -641,7 +671,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
     const int num_tiles = p.tiles_m;                 // 256-pixel blocks
 
     if (warp == 0) {
-        if (lane == 0 && grouped) {
+        if (grouped) {
             int ps = 0, ws = 0;
             uint32_t pph = 0, wph = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -652,24 +682,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
                     for (int kb = 0; kb < gr.kblocks; ++kb) {
                         mbar_wait(&empty_bar[ps], pph ^ 1u);
                         uint8_t* sx = smem + (size_t)ps * T_PB;
-                        mbar_arrive_expect_tx(&full_bar[ps], (TBN + 8) * BLOCK_K * 2);
                         const int32_t xrow = (int32_t)(pix0 + gr.row_shift);
-                        tma_load_2d(sx, tmx, &full_bar[ps], gr.a_col0 + kb * BLOCK_K, xrow);                     // 256 rows
-                        tma_load_2d(sx + TBN * BLOCK_K * 2, &p.tm_x8[gr.src ? 1 : 0], &full_bar[ps],
-                                    gr.a_col0 + kb * BLOCK_K, xrow + TBN);                                         // + 8 rows
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(&full_bar[ps], (TBN + 8) * BLOCK_K * 2);
+                            tma_load_2d(sx, tmx, &full_bar[ps], gr.a_col0 + kb * BLOCK_K, xrow);                     // 256 rows
+                            tma_load_2d(sx + TBN * BLOCK_K * 2, &p.tm_x8[gr.src ? 1 : 0], &full_bar[ps],
+                                        gr.a_col0 + kb * BLOCK_K, xrow + TBN);                                         // + 8 rows
+                        }
+                        __syncwarp();
                         if (++ps == p.sp) { ps = 0; pph ^= 1u; }
                         for (int sub = 0; sub < gr.nsub; ++sub) {
                             const int wb = p.sp + ws;
                             mbar_wait(&empty_bar[wb], wph ^ 1u);
-                            mbar_arrive_expect_tx(&full_bar[wb], A_STAGE_BYTES);
-                            tma_load_2d(smem_w + (size_t)ws * A_STAGE_BYTES, &p.tm_b, &full_bar[wb],
-                                        (gr.kb0 + sub * gr.kblocks + kb) * BLOCK_K, 0);
+                            if (elect_one()) {
+                                mbar_arrive_expect_tx(&full_bar[wb], A_STAGE_BYTES);
+                                tma_load_2d(smem_w + (size_t)ws * A_STAGE_BYTES, &p.tm_b, &full_bar[wb],
+                                            (gr.kb0 + sub * gr.kblocks + kb) * BLOCK_K, 0);
+                            }
+                            __syncwarp();
                             if (++ws == p.sw) { ws = 0; wph ^= 1u; }
                         }
                     }
                 }
             }
-        } else if (lane == 0) {
+        } else {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -683,81 +719,85 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
                         mbar_wait(&empty_bar[stage], phase ^ 1u);
                         uint8_t* sw = smem + (size_t)stage * T_STAGE_BYTES;     // weights  [128 x 64]
                         uint8_t* sx = sw + A_STAGE_BYTES;                        // pixels   [256 x 64]
-                        mbar_arrive_expect_tx(&full_bar[stage], T_STAGE_BYTES);
-                        tma_load_2d(sw, &p.tm_b, &full_bar[stage], kb_global * BLOCK_K, 0);
-                        tma_load_2d(sx, tmx, &full_bar[stage], sg.a_col0 + kb * BLOCK_K, xrow);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(&full_bar[stage], T_STAGE_BYTES);
+                            tma_load_2d(sw, &p.tm_b, &full_bar[stage], kb_global * BLOCK_K, 0);
+                            tma_load_2d(sx, tmx, &full_bar[stage], sg.a_col0 + kb * BLOCK_K, xrow);
+                        }
+                        __syncwarp();
                         if (++stage == stages) { stage = 0; phase ^= 1u; }
                     }
                 }
             }
         }
-    } else if (warp == 1 && grouped) {
-        const uint32_t IDESC = make_idesc_16(BLOCK_M, TBN, 0, 0, p.fmt);
-        int ps = 0, ws = 0;
-        uint32_t pph = 0, wph = 0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int acc = it & 1;
-            mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1u);
-            tc_fence_after();
-            const uint32_t tmem_d = tmem_base + acc * ACC_STRIDE;
-            uint32_t accum = 0;
-            for (int g = 0; g < p.ngrp; ++g) {
-                const int nsub = p.grp[g].nsub, nkb = p.grp[g].kblocks;
-                for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(&full_bar[ps], pph);
-                    const uint32_t sx = smem_u32(smem + (size_t)ps * T_PB);
-                    for (int sub = 0; sub < nsub; ++sub) {
-                        const int wb = p.sp + ws;
-                        mbar_wait(&full_bar[wb], wph);
-                        tc_fence_after();
-                        if (lane == 0) {
+    } else if (warp == 1) {
+        // converged warp, elect.sync at the issue (see smtl_gemm_kernel)
+        if (grouped) {
+            const uint32_t IDESC = make_idesc_16(BLOCK_M, TBN, 0, 0, p.fmt);
+            int ps = 0, ws = 0;
+            uint32_t pph = 0, wph = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * ACC_STRIDE;
+                uint32_t accum = 0;
+                for (int g = 0; g < p.ngrp; ++g) {
+                    const int nsub = p.grp[g].nsub, nkb = p.grp[g].kblocks;
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        mbar_wait(&full_bar[ps], pph);
+                        const uint32_t sx = smem_u32(smem + (size_t)ps * T_PB);
+                        for (int sub = 0; sub < nsub; ++sub) {
+                            const int wb = p.sp + ws;
+                            mbar_wait(&full_bar[wb], wph);
+                            tc_fence_after();
                             const uint64_t da = make_smem_desc_sw128(smem_u32(smem_w + (size_t)ws * A_STAGE_BYTES));
                             const uint64_t db = make_smem_desc_sw128(sx + sub * 128);            // tap `sub`: one pixel row further
+                            if (elect_one()) {
 #pragma unroll
-                            for (int k = 0; k < BLOCK_K / 16; ++k) {
-                                tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, accum);
-                                accum = 1;
+                                for (int k = 0; k < BLOCK_K / 16; ++k)
+                                    tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, accum | (uint32_t)k);
+                                tc_commit(&empty_bar[wb]);
                             }
-                            tc_commit(&empty_bar[wb]);
+                            accum = 1;
+                            __syncwarp();
+                            if (++ws == p.sw) { ws = 0; wph ^= 1u; }
                         }
-                        accum = 1;
+                        if (elect_one()) tc_commit(&empty_bar[ps]);
                         __syncwarp();
-                        if (++ws == p.sw) { ws = 0; wph ^= 1u; }
+                        if (++ps == p.sp) { ps = 0; pph ^= 1u; }
                     }
-                    if (lane == 0) tc_commit(&empty_bar[ps]);
-                    __syncwarp();
-                    if (++ps == p.sp) { ps = 0; pph ^= 1u; }
                 }
+                if (elect_one()) tc_commit(&acc_full[acc]);
+                __syncwarp();
             }
-            if (lane == 0) tc_commit(&acc_full[acc]);
-            __syncwarp();
-        }
-    } else if (warp == 1) {
-        const uint32_t IDESC = make_idesc_16(BLOCK_M, TBN, 0, 0, p.fmt);
-        int stage = 0;
-        uint32_t phase = 0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int acc = it & 1;
-            mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1u);
-            tc_fence_after();
-            const uint32_t tmem_d = tmem_base + acc * ACC_STRIDE;
-            for (int kb = 0; kb < p.total_kb; ++kb) {
-                mbar_wait(&full_bar[stage], phase);
+        } else {
+            const uint32_t IDESC = make_idesc_16(BLOCK_M, TBN, 0, 0, p.fmt);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1u);
                 tc_fence_after();
-                if (lane == 0) {
+                const uint32_t tmem_d = tmem_base + acc * ACC_STRIDE;
+                for (int kb = 0; kb < p.total_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
                     const uint32_t sw = smem_u32(smem + (size_t)stage * T_STAGE_BYTES);
                     const uint64_t da = make_smem_desc_sw128(sw);
                     const uint64_t db = make_smem_desc_sw128(sw + A_STAGE_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / 16; ++k)
-                        tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
-                    tc_commit(&empty_bar[stage]);
-                    if (kb == p.total_kb - 1) tc_commit(&acc_full[acc]);
+                        for (int k = 0; k < BLOCK_K / 16; ++k)
+                            tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0);
+                        tc_commit(&empty_bar[stage]);
+                        if (kb == p.total_kb - 1) tc_commit(&acc_full[acc]);
+                    }
+                    __syncwarp();
+                    if (++stage == stages) { stage = 0; phase ^= 1u; }
                 }
-                __syncwarp();
-                if (++stage == stages) { stage = 0; phase ^= 1u; }
             }
         }
     } else {
@@ -1001,7 +1041,7 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
     // ---- shift groups: consecutive-row-shift segments (kx = -1, 0, +1 of one ky) share one activation tile
     {
         const char* env = getenv("SMTL_GEMM_GROUPED");
-        const bool allow = !(env && env[0] == '0') && g.cta_group != 2;
+        const bool allow = !(env && env[0] == '0');
         int ng = 0, kb0 = 0;
         bool any = false;
         for (int si = 0; si < g.nseg;) {
@@ -1079,10 +1119,12 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
         // measured on B200 (scripts/bench_kernels.py gemm): pairs win on long plain-K GEMMs (8192^3: 1170 -> 1295
         // TFLOP/s) and lose on the 9-segment implicit convs and on short-K linears, whose cost is the epilogue
         cg = env ? atoi(env) : ((tiles256 >= sms / 2 && g.nseg == 1 && g.k >= 2048 && g.n >= 256) ? 2 : 1);
+        // shift-grouped convs with full-width tiles: pairs halve the weight traffic (L2 -> smem and smem -> MMA)
+        const char* envc = getenv("SMTL_GEMM_CG_CONV");
+        if (!env && op->grouped && bn == 256 && tiles256 >= sms / 2 && !(envc && envc[0] == '0')) cg = 2;
         if (g.group_rows) cg = 1;
     }
     SMTL_CHECK_ARG(cg == 1 || cg == 2, "gemm_plan: cta_group %d", cg);
-    if (cg == 2) op->grouped = 0;                   // the pair kernel keeps the single (A, B) ring
     SMTL_CHECK_ARG(cg == 1 || bn % 16 == 0, "gemm_plan: cta_group 2 needs block_n %% 16 == 0");
     op->cta_group = cg;
     op->block_n = bn;
@@ -1099,13 +1141,18 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
     op->smem_bytes = 1024 + stages * stage_bytes + 512;
     const int a_box_rows = op->grouped ? BLOCK_M + 8 : BLOCK_M;
     if (op->grouped) {
-        const int pb = (BLOCK_M + 8) * BLOCK_K * 2, wb = bn * BLOCK_K * 2;
-        // narrow tiles are bound by the activation stream: give it the deeper ring (12 barriers in all)
+        const int pb = (BLOCK_M + 8) * BLOCK_K * 2, wb = (bn / cg) * BLOCK_K * 2;
+        // narrow tiles are bound by the activation stream: give it the deeper ring.  The producer issues the loads in
+        // program order, so the weight ring must hold the weights of every activation stage in flight (3 taps each)
+        // or it, not the activation ring, sets the prefetch distance: a Cout = 3 conv (BN = 32, 36 clk per MMA) was
+        // load-latency bound with 6 weight stages.
+        const int sp_max = bn <= 64 ? 8 : 6;
         op->sp = (SMEM_BUDGET - 1024 - 512 - 6 * wb) / pb;
         if (op->sp < 3) op->sp = 3;
-        if (op->sp > 6) op->sp = 6;
+        if (op->sp > sp_max) op->sp = sp_max;
         op->sw = (SMEM_BUDGET - 1024 - 512 - op->sp * pb) / wb;
-        if (op->sw > 12 - op->sp) op->sw = 12 - op->sp;
+        if (op->sw > 3 * op->sp) op->sw = 3 * op->sp;
+        if (op->sw > GEMM_MAX_STAGES - op->sp) op->sw = GEMM_MAX_STAGES - op->sp;
         op->smem_bytes = 1024 + op->sp * pb + op->sw * wb + 512;
     }
     const long long tiles = (long long)op->tiles_m * op->tiles_n;
