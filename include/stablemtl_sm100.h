@@ -216,7 +216,7 @@ typedef struct smtl_taskattn_args {
     int32_t n_main, n_src;
     int64_t rows_per_group;                 /* images * tokens */
     int32_t main_task[SMTL_MAX_TASKS];      /* task id of each q row group */
-    int32_t src_task[SMTL_MAX_TASKS];       /* task id of each k/v row group */
+    int32_t src_task[SMTL_MAX_TASKS];       /* task id of each k/v row group; < 0 = empty slot (rows ignored) */
     int32_t exclude_self;                   /* skip src whose task id equals the row's main task (stablemtl_pipeline.py:483-484) */
     float scale;                            /* 1/sqrt(c/nheads) */
     int32_t fmt16;

@@ -616,7 +616,7 @@ __global__ void taskattn_kernel(const uint16_t* __restrict__ q, const uint16_t* 
 #pragma unroll
     for (int s = 0; s < SMTL_MAX_TASKS; ++s) {
         sc[s] = -INFINITY;
-        if (s < n_src && !(exclude_self && ids.src_task[s] == my_task)) {
+        if (s < n_src && ids.src_task[s] >= 0 && !(exclude_self && ids.src_task[s] == my_task)) {   // < 0: empty slot
             const uint4* kp = reinterpret_cast<const uint4*>(k + ((int64_t)s * rows_per_group + pix) * c + hd * dh);
             float d = 0.f;
             for (int i = 0; i < nch; ++i) {

@@ -246,8 +246,28 @@ class UNetPlan(_PlanBase):
     mode "main"  : consumes `feats` (list of 16 bf16 [n_src*images*N_l, C_l], rows grouped by source task)
     """
 
+    @staticmethod
+    def tap_shapes(cfg, h, w):
+        """[(tokens per image, channels)] of the 16 attn1 taps in execution order (child feats_out / main feats)."""
+        c = cfg.block_out_channels
+        nlev = len(c)
+        sizes = [(h, w)]
+        for _ in range(nlev - 1):
+            sizes.append((down_size(sizes[-1][0]), down_size(sizes[-1][1])))
+        out = []
+        for i in range(nlev - 1):
+            out += [(sizes[i][0] * sizes[i][1], c[i])] * cfg.layers_per_block
+        out.append((sizes[-1][0] * sizes[-1][1], c[-1]))
+        for i in range(1, nlev):
+            lev = nlev - 1 - i
+            out += [(sizes[lev][0] * sizes[lev][1], c[lev])] * (cfg.layers_per_block + 1)
+        return out
+
     def __init__(self, W: UNetWeights, images, h, w, group_tasks, mode="single", feats=None, src_tasks=None,
-                 pool=None, x_in=None):
+                 pool=None, x_in=None, feat_bufs=None):
+        """feat_bufs (child mode): caller-owned 16-bit tap buffers, one per layer, at least [G*images*N_l, C_l] -- the
+        send buffers of the task-stream exchange (stablemtl_b200/stream_shard.py).  src_tasks (main mode) may hold -1
+        for an empty exchange slot: its rows are skipped by the task attention."""
         cfg = W.cfg
         self.W, self.cfg, self.mode = W, cfg, mode
         dev = W.device
@@ -268,6 +288,7 @@ class UNetPlan(_PlanBase):
         self.images = images
         self.feats_out = [] if mode == "child" else None
         self.feats_in, self.src_tasks = feats, src_tasks
+        self.feat_bufs = feat_bufs
         self.layer = 0
 
         # ---- stem: [Be, hw, 12] fp32 -> im2col -> GEMM
@@ -399,7 +420,11 @@ class UNetPlan(_PlanBase):
         if self.mode != "main":
             feat = None
             if self.mode == "child":
-                feat = torch.empty(M, C, device=W.device, dtype=ops.h16())      # owned by the plan, read by the main pass
+                if self.feat_bufs is not None:
+                    feat = self.feat_bufs[len(self.feats_out)][:M]
+                    assert feat.shape == (M, C) and feat.dtype == ops.h16() and feat.is_contiguous()
+                else:
+                    feat = torch.empty(M, C, device=W.device, dtype=ops.h16())  # owned by the plan, read by the main pass
                 self.feats_out.append(feat)
             # h += to_out(attn); the pre-residual value is the "afterSelfAttn_residual" tap (attention.py:348-349)
             add(ops.gemm(att, wt[p + ".o.w"], bias=wt[p + ".o.b"], res1=hs, out_f32=hs, aux_bf16=feat, name="attn_out"))
@@ -421,7 +446,7 @@ class UNetPlan(_PlanBase):
             def stacked(key, tasks):
                 """[len(tasks) * out, in] weights / [len(tasks) * out] bias of the per-task module, in row-group order"""
                 wk, bk = tw[p + key + ".w"], tw[p + key + ".b"]
-                idx = torch.tensor(list(tasks), device=wk.device)
+                idx = torch.tensor([max(t, 0) for t in tasks], device=wk.device)   # -1 = empty exchange slot
                 return (wk.index_select(0, idx).reshape(-1, wk.shape[-1]).contiguous(),
                         bk.index_select(0, idx).reshape(-1).contiguous(), wk.shape[1])
 
@@ -431,6 +456,8 @@ class UNetPlan(_PlanBase):
                     add(ops.gemm(src, wg, n=nout, bias=bg, act=act, out_bf16=dst, group_rows=rpg, name=name))
                 else:
                     for gi, t in enumerate(tasks):
+                        if t < 0:
+                            continue
                         r = slice(gi * rpg, (gi + 1) * rpg)
                         add(ops.gemm(src[r], tw[p + key + ".w"][t], bias=tw[p + key + ".b"][t], act=act, out_bf16=dst[r],
                                      name=name))
@@ -445,10 +472,10 @@ class UNetPlan(_PlanBase):
             Ms = S * rpg
             assert F_l.shape == (Ms, C), (F_l.shape, Ms, C)
             kn, vn = P.alloc((Ms, C), ops.h16()), P.alloc((Ms, C), ops.h16())
-            gk = torch.stack([tw[p + ".tnk.g"][t] for t in self.src_tasks]).contiguous()
-            bk = torch.stack([tw[p + ".tnk.b"][t] for t in self.src_tasks]).contiguous()
-            gv = torch.stack([tw[p + ".tnv.g"][t] for t in self.src_tasks]).contiguous()
-            bv = torch.stack([tw[p + ".tnv.b"][t] for t in self.src_tasks]).contiguous()
+            gk = torch.stack([tw[p + ".tnk.g"][max(t, 0)] for t in self.src_tasks]).contiguous()
+            bk = torch.stack([tw[p + ".tnk.b"][max(t, 0)] for t in self.src_tasks]).contiguous()
+            gv = torch.stack([tw[p + ".tnv.g"][max(t, 0)] for t in self.src_tasks]).contiguous()
+            bv = torch.stack([tw[p + ".tnv.b"][max(t, 0)] for t in self.src_tasks]).contiguous()
             add(ops.layer_norm(F_l, gk, bk, kn, gamma1=gv, beta1=bv, out1=vn, rows_per_group=rpg))
             hk, hv = P.alloc((Ms, C // 2), ops.h16()), P.alloc((Ms, C // 2), ops.h16())
             K, V = P.alloc((Ms, C), ops.h16()), P.alloc((Ms, C), ops.h16())

@@ -15,6 +15,7 @@ import torch
 
 from . import _lib as L
 from . import ops
+from . import stream_shard as SS
 from .engine import F32, Pool, UNetPlan, UNetWeights, VAEDecodePlan, VAEEncodePlan, VAEWeights
 from .synth import FLOW_TASKS, TASKS, UNetConfig, VAEConfig
 
@@ -34,11 +35,30 @@ def _require_cuda(device):
 
 class StableMTLEngine:
     def __init__(self, ucfg: UNetConfig, vcfg: VAEConfig, child_sd, vae_sd, text: Dict[str, torch.Tensor],
-                 main_sd=None, tasks: List[str] = TASKS, device="cuda", max_decode_batch=16, use_graph=True):
+                 main_sd=None, tasks: List[str] = TASKS, device="cuda", max_decode_batch=16, use_graph=True,
+                 stream_shard=False, stream_group=None):
+        """stream_shard=True (multi-stream only, torch.distributed initialised): this rank owns a block of the task
+        streams and exchanges the child features with the other ranks between the child and the main pass
+        (stream_shard.py) -- the low-latency sharding for batches smaller than the number of GPUs."""
         self.device = _require_cuda(device)
         self.use_graph = use_graph
         self.ucfg, self.vcfg, self.tasks = ucfg, vcfg, list(tasks)
         self.multi = main_sd is not None
+        self.stream = bool(stream_shard)
+        self.sgroup = stream_group
+        self.my = list(range(len(self.tasks)))                       # task indices this rank computes
+        if self.stream:
+            import torch.distributed as dist
+            if not self.multi:
+                raise ValueError("stream sharding exchanges child features: it needs the multi-stream model")
+            if not (dist.is_available() and dist.is_initialized()):
+                raise RuntimeError("stream_shard=True needs an initialised torch.distributed process group")
+            self.sworld, self.srank = dist.get_world_size(stream_group), dist.get_rank(stream_group)
+            if self.sworld * SS.slots_per_rank(len(self.tasks), self.sworld) > L.MAX_TASKS:
+                raise ValueError(f"{len(self.tasks)} task streams over {self.sworld} ranks need more than "
+                                 f"{L.MAX_TASKS} exchange slots (SMTL_MAX_TASKS)")
+            lo, hi = SS.task_range(len(self.tasks), self.sworld, self.srank)
+            self.my = list(range(lo, hi))
         self.child_w = UNetWeights(child_sd, ucfg, text, self.tasks, self.device)
         self.main_w = UNetWeights(main_sd, ucfg, text, self.tasks, self.device) if self.multi else None
         self.vae_w = VAEWeights(vae_sd, vcfg, self.device)
@@ -51,21 +71,41 @@ class StableMTLEngine:
         dev = self.device
         pool = Pool(dev)
         T = len(self.tasks)
+        mine = self.my
+        Tm = len(mine)
         n_enc = 2 * B if with_next else B
+        xchg = None
+        if self.stream:
+            # exchange buffers of the 16 tap layers: send [n_max * B * N_l, C_l] (my tasks first), receive slot-major
+            h, w = H // 8, W // 8
+            n_max = SS.slots_per_rank(T, self.sworld)
+            shapes = UNetPlan.tap_shapes(self.ucfg, h, w)
+            xchg = dict(send=[torch.zeros(n_max * B * n, c, device=dev, dtype=ops.h16()) for n, c in shapes],
+                        recv=[torch.zeros(self.sworld * n_max * B * n, c, device=dev, dtype=ops.h16()) for n, c in shapes],
+                        slots=SS.task_slots(T, self.sworld))
+            if Tm == 0:                                               # more ranks than tasks: exchange only
+                return dict(enc=None, xchg=xchg, unets=[], chunks=[], out={}, launches=0, flops=0, pool=pool, h=h, w=w,
+                            hw=h * w)
         enc = VAEEncodePlan(self.vae_w, n_enc, H, W, pool=pool, rgb_dtype=rgb_dtype)
         h, w = enc.h, enc.w
         hw = h * w
-        first = torch.arange(B, dtype=torch.int32).repeat(T)
+        first = torch.arange(B, dtype=torch.int32).repeat(Tm)
         second = first.clone()
         if with_next:
-            for gi, t in enumerate(self.tasks):
-                if t in FLOW_TASKS:                                  # stablemtl_pipeline.py:433-434
+            for gi, ti in enumerate(mine):
+                if self.tasks[ti] in FLOW_TASKS:                     # stablemtl_pipeline.py:433-434
                     second[gi * B:(gi + 1) * B] += B
         first, second = first.to(dev), second.to(dev)
-        x_in = torch.empty(T * B * hw, self.ucfg.in_channels, device=dev, dtype=F32)
+        x_in = torch.empty(Tm * B * hw, self.ucfg.in_channels, device=dev, dtype=F32)
         assemble = ops.unet_input(enc.out, first, second, hw, x_in)
-        groups = list(range(T))
-        if self.multi:
+        groups = list(mine)
+        if self.multi and self.stream:
+            child = UNetPlan(self.child_w, B, h, w, groups, mode="child", pool=pool, x_in=x_in, feat_bufs=xchg["send"])
+            main = UNetPlan(self.main_w, B, h, w, groups, mode="main", feats=xchg["recv"], src_tasks=xchg["slots"],
+                            pool=pool, x_in=x_in)
+            unets = [child, main]
+            lat = main.out
+        elif self.multi:
             child = UNetPlan(self.child_w, B, h, w, groups, mode="child", pool=pool, x_in=x_in)
             main = UNetPlan(self.main_w, B, h, w, groups, mode="main", feats=child.feats_out, src_tasks=groups,
                             pool=pool, x_in=x_in)
@@ -75,12 +115,13 @@ class StableMTLEngine:
             single = UNetPlan(self.child_w, B, h, w, groups, mode="single", pool=pool, x_in=x_in)
             unets = [single]
             lat = single.out
-        n_lat = T * B
+        n_lat = Tm * B
         bd = max(d for d in range(1, min(self.max_decode_batch, n_lat) + 1) if n_lat % d == 0)
         dec = VAEDecodePlan(self.vae_w, bd, h, w, pool=pool)
         HW = H * W
         out = {}
-        for t in self.tasks:
+        for ti in mine:
+            t = self.tasks[ti]
             ch = TASK_CH[t]
             out[t] = {"clipped": torch.empty(B, ch, H, W, device=dev, dtype=F32)}
             if t == "semantic":
@@ -94,7 +135,7 @@ class StableMTLEngine:
             while i < c0 + bd:                                       # split the chunk at task boundaries
                 gi, img = divmod(i, B)
                 n = min(B - img, c0 + bd - i)
-                t = self.tasks[gi]
+                t = self.tasks[mine[gi]]
                 x = dec.out[(i - c0) * HW:(i - c0 + n) * HW]
                 o = out[t]
                 if t == "semantic":
@@ -109,7 +150,7 @@ class StableMTLEngine:
             len(chunks) * dec.plan.launches + sum(len(m) for _, m in chunks)
         flops = enc.plan.flops + sum(u.plan.flops for u in unets) + len(chunks) * dec.plan.flops
         return dict(enc=enc, assemble=assemble, unets=unets, lat=lat, dec=dec, bd=bd, chunks=chunks, out=out, hw=hw,
-                    pool=pool, launches=launches, flops=flops, h=h, w=w)
+                    pool=pool, launches=launches, flops=flops, h=h, w=w, xchg=xchg)
 
     def plan_for(self, B, H, W, with_next=True, rgb_dtype=F32):
         key = (B, H, W, with_next, rgb_dtype)
@@ -119,40 +160,56 @@ class StableMTLEngine:
 
     # ------------------------------------------------------------------------------------------ execution
     @torch.no_grad()
-    def predict(self, rgb: torch.Tensor, rgb_next: Optional[torch.Tensor] = None, return_latents=False):
+    def predict(self, rgb: torch.Tensor, rgb_next: Optional[torch.Tensor] = None, return_latents=False, gather=False):
         """rgb / rgb_next: float [B,3,H,W] in [0,255] (host or device).  Returns {task: map} with the reference's
         post-processing (stablemtl_pipeline.py:297-366): depth/shading/albedo in [0,1], unit normals, flows in
-        [-1,1], semantic class ids (int64 [B,H,W]).  `.last` keeps the clipped single_infer() tensors."""
+        [-1,1], semantic class ids (int64 [B,H,W]).  `.last` keeps the clipped single_infer() tensors.
+        With stream sharding the dict holds this rank's tasks, or every task after a broadcast when gather=True."""
         B, _, H, W = rgb.shape
         dt = torch.uint8 if rgb.dtype == torch.uint8 else F32        # uint8 images are converted inside the kernel
         p = self.plan_for(B, H, W, rgb_next is not None, dt)
         enc = p["enc"]
-        enc.rgb[:B].copy_(rgb, non_blocking=True)                     # H2D (or D2D) copy; dtype cast only if needed
-        if rgb_next is not None:
-            enc.rgb[B:].copy_(rgb_next, non_blocking=True)
-        # The whole pass (~2000 launches over static buffers) is replayed as ONE CUDA graph: the first call of a plan
-        # runs eagerly (it also sets the kernels' shared-memory attributes), the second captures, later ones replay.
-        if not self.use_graph:
-            self._launch_all(p)
-        elif p.get("graph") is not None:
-            p["graph"].replay()
-        elif not p.get("warm"):
-            self._launch_all(p)
+        if enc is not None:
+            enc.rgb[:B].copy_(rgb, non_blocking=True)                 # H2D (or D2D) copy; dtype cast only if needed
+            if rgb_next is not None:
+                enc.rgb[B:].copy_(rgb_next, non_blocking=True)
+        # The whole pass (~2000 launches over static buffers) is replayed as CUDA graphs: the first call of a plan runs
+        # eagerly (it also sets the kernels' shared-memory attributes), the second captures, later ones replay.  With
+        # stream sharding there are two graphs, one either side of the feature exchange.
+        stages = self._stages(p)
+        if enc is None:                            # more ranks than task streams: this rank only joins the collectives
+            self._exchange(p)
+        elif not self.use_graph or not p.get("warm"):
+            for i, st in enumerate(stages):
+                if i:
+                    self._exchange(p)
+                st()
             p["warm"] = True
         else:
-            g = torch.cuda.CUDAGraph()
-            torch.cuda.synchronize()
-            with torch.cuda.graph(g):
-                self._launch_all(p)
-            p["graph"] = g
-            g.replay()
-        self.last = {t: p["out"][t]["clipped"] for t in self.tasks}
-        res = {t: p["out"][t]["post"] for t in self.tasks}
+            if p.get("graphs") is None:
+                torch.cuda.synchronize()
+                graphs = []
+                for st in stages:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        st()
+                    graphs.append(g)
+                p["graphs"] = graphs
+            for i, g in enumerate(p["graphs"]):
+                if i:
+                    self._exchange(p)
+                g.replay()
+        self.last = {t: v["clipped"] for t, v in p["out"].items()}
+        res = {t: v["post"] for t, v in p["out"].items()}
+        if self.stream and gather:
+            like = {}
+            for t in self.tasks:
+                like[t] = ((B, H, W), torch.int64) if t == "semantic" else ((B, TASK_CH[t], H, W), F32)
+            res = SS.gather_task_maps(res, self.tasks, like, self.device, self.sgroup)
         if return_latents:
-            T = len(self.tasks)
             lat = p["lat"]
-            lats = lat.view(T, B, p["h"], p["w"], -1).permute(0, 1, 4, 2, 3)
-            return res, {t: lats[i] for i, t in enumerate(self.tasks)}
+            lats = lat.view(len(self.my), B, p["h"], p["w"], -1).permute(0, 1, 4, 2, 3)
+            return res, {self.tasks[ti]: lats[i] for i, ti in enumerate(self.my)}
         return res
 
     def empty_result(self, H, W):
@@ -165,17 +222,46 @@ class StableMTLEngine:
                 out[t] = torch.empty(0, TASK_CH[t], H, W, device=self.device, dtype=F32)
         return out
 
+    def _exchange(self, p):
+        """child features of every stream -> every rank (the one data-path collective, stream_shard.py)"""
+        SS.exchange_taps(p["xchg"]["send"], p["xchg"]["recv"], self.sgroup)
+
+    def _stages(self, p):
+        """launch closures; more than one only when a feature exchange sits between the child and the main pass"""
+        def decode():
+            dec, bd, hw, lat = p["dec"], p["bd"], p["hw"], p["lat"]
+            for c0, maps in p["chunks"]:
+                dec.latent.copy_(lat[c0 * hw:(c0 + bd) * hw])
+                dec.run()
+                for m in maps:
+                    m.run()
+
+        if not self.stream:
+            def whole():
+                p["enc"].run()
+                p["assemble"].run()
+                for u in p["unets"]:
+                    u.run()
+                decode()
+            return [whole]
+        if p["enc"] is None:                                           # no task of mine: nothing to launch
+            return []
+
+        def before():
+            p["enc"].run()
+            p["assemble"].run()
+            p["unets"][0].run()
+
+        def after():
+            p["unets"][1].run()
+            decode()
+        return [before, after]
+
     def _launch_all(self, p):
-        p["enc"].run()
-        p["assemble"].run()
-        for u in p["unets"]:
-            u.run()
-        dec, bd, hw, lat = p["dec"], p["bd"], p["hw"], p["lat"]
-        for c0, maps in p["chunks"]:
-            dec.latent.copy_(lat[c0 * hw:(c0 + bd) * hw])
-            dec.run()
-            for m in maps:
-                m.run()
+        for i, st in enumerate(self._stages(p)):
+            if i:
+                self._exchange(p)
+            st()
 
     def launches_per_step(self, B, H, W, with_next=True):
         return self.plan_for(B, H, W, with_next)["launches"]
