@@ -538,11 +538,58 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, int n, int lds,
     }
 }
 
+// same, 128-bit loads / 64-bit stores: n, lds, ldp multiples of 4 and 16-byte aligned rows; 128 threads per row so
+// that more rows are in flight per SM (the kernel is two block reductions deep: latency, not bandwidth)
+__global__ void __launch_bounds__(128) softmax_rows_vec4_kernel(const float* __restrict__ s, int n, int lds, float scale,
+                                                                uint16_t* __restrict__ p, int ldp, int fmt) {
+    __shared__ float red[4];
+    const int64_t row = blockIdx.x;
+    const float4* src = reinterpret_cast<const float4*>(s + row * lds);
+    const int nv = n >> 2;
+    float4 v[16];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int j = threadIdx.x + i * 128;
+        if (j < nv) {
+            v[i] = __ldg(src + j);
+            v[i].x *= scale; v[i].y *= scale; v[i].z *= scale; v[i].w *= scale;
+            mx = fmaxf(fmaxf(mx, fmaxf(v[i].x, v[i].y)), fmaxf(v[i].z, v[i].w));
+        }
+    }
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    __syncthreads();
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int j = threadIdx.x + i * 128;
+        if (j < nv) {
+            v[i].x = __expf(v[i].x - mx); v[i].y = __expf(v[i].y - mx);
+            v[i].z = __expf(v[i].z - mx); v[i].w = __expf(v[i].w - mx);
+            sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+    sum = warp_sum(sum);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    const float inv = 1.0f / ((red[0] + red[1]) + (red[2] + red[3]));
+    uint2* dst = reinterpret_cast<uint2*>(p + row * ldp);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int j = threadIdx.x + i * 128;
+        if (j < nv) dst[j] = make_uint2(pack16x2(v[i].x * inv, v[i].y * inv, fmt), pack16x2(v[i].z * inv, v[i].w * inv, fmt));
+    }
+}
+
 struct XattnK {
     int ntok[SMTL_MAX_TASKS];
     int task_of_group[SMTL_MAX_TASKS];
 };
-// cross-attention on <= 4 constant keys: one warp per token row, lane owns 2 of the 64 head dims
+// cross-attention on <= 4 constant keys: one warp per token row; a lane owns 8 contiguous channels (one 16-byte
+// load), so 8 lanes make a head, a warp covers 4 heads per pass and a q.k dot product closes with 3 shuffles.
 __global__ void xattn_kernel(const uint16_t* __restrict__ q, int ldq, int64_t rows, int heads,
                              const float* __restrict__ kc, const float* __restrict__ vc, XattnK tk,
                              int64_t rows_per_group, uint16_t* __restrict__ out, int ldo, float scale, int fmt) {
@@ -555,36 +602,54 @@ __global__ void xattn_kernel(const uint16_t* __restrict__ q, int ldq, int64_t ro
     const int C = heads * 64;
     const float* kbase = kc + (int64_t)task * 4 * C;
     const float* vbase = vc + (int64_t)task * 4 * C;
-    for (int hd = 0; hd < heads; ++hd) {
-        const int col = hd * 64 + 2 * lane;
-        const float2 qv = unpack16x2(*reinterpret_cast<const uint32_t*>(q + row * ldq + col), fmt);
+    for (int c0 = 0; c0 < C; c0 += 256) {
+        const int col = c0 + 8 * lane;
+        const bool on = col < C;                       // whole heads: C is a multiple of 64
+        float qf[8];
+        {
+            uint4 u = make_uint4(0, 0, 0, 0);
+            if (on) u = __ldg(reinterpret_cast<const uint4*>(q + row * ldq + col));
+            float2 t;
+            t = unpack16x2(u.x, fmt); qf[0] = t.x; qf[1] = t.y;
+            t = unpack16x2(u.y, fmt); qf[2] = t.x; qf[3] = t.y;
+            t = unpack16x2(u.z, fmt); qf[4] = t.x; qf[5] = t.y;
+            t = unpack16x2(u.w, fmt); qf[6] = t.x; qf[7] = t.y;
+        }
         float sc[4];
         float mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float d = 0.f;
-            if (j < nt) {
-                const float2 kv = __ldg(reinterpret_cast<const float2*>(kbase + j * C + col));
-                d = qv.x * kv.x + qv.y * kv.y;
+            if (j < nt && on) {
+                const float4 k0 = ldg4(kbase + j * C + col), k1 = ldg4(kbase + j * C + col + 4);
+                d = qf[0] * k0.x + qf[1] * k0.y + qf[2] * k0.z + qf[3] * k0.w + qf[4] * k1.x + qf[5] * k1.y +
+                    qf[6] * k1.z + qf[7] * k1.w;
             }
-            d = warp_sum(d) * scale;
-            sc[j] = (j < nt) ? d : -INFINITY;
+            d += __shfl_xor_sync(0xffffffffu, d, 4);
+            d += __shfl_xor_sync(0xffffffffu, d, 2);
+            d += __shfl_xor_sync(0xffffffffu, d, 1);
+            sc[j] = (j < nt) ? d * scale : -INFINITY;
             mx = fmaxf(mx, sc[j]);
         }
         float sum = 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) { sc[j] = (j < nt) ? __expf(sc[j] - mx) : 0.f; sum += sc[j]; }
         const float inv = 1.0f / sum;
-        float o0 = 0.f, o1 = 0.f;
+        float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if (j < nt) {
-                const float2 vv = __ldg(reinterpret_cast<const float2*>(vbase + j * C + col));
-                o0 += sc[j] * vv.x;
-                o1 += sc[j] * vv.y;
+            if (j < nt && on) {
+                const float4 v0 = ldg4(vbase + j * C + col), v1 = ldg4(vbase + j * C + col + 4);
+                o[0] += sc[j] * v0.x; o[1] += sc[j] * v0.y; o[2] += sc[j] * v0.z; o[3] += sc[j] * v0.w;
+                o[4] += sc[j] * v1.x; o[5] += sc[j] * v1.y; o[6] += sc[j] * v1.z; o[7] += sc[j] * v1.w;
             }
         }
-        *reinterpret_cast<uint32_t*>(out + row * ldo + col) = pack16x2(o0 * inv, o1 * inv, fmt);
+        if (on) {
+            uint4 u;
+            u.x = pack16x2(o[0] * inv, o[1] * inv, fmt); u.y = pack16x2(o[2] * inv, o[3] * inv, fmt);
+            u.z = pack16x2(o[4] * inv, o[5] * inv, fmt); u.w = pack16x2(o[6] * inv, o[7] * inv, fmt);
+            *reinterpret_cast<uint4*>(out + row * ldo + col) = u;
+        }
     }
 }
 
@@ -888,8 +953,14 @@ extern "C" int smtl_softmax_run(const smtl_softmax_args* a, void* stream) {
     SMTL_CHECK_ARG(a && a->s && a->p_bf16, "softmax: NULL argument");
     SMTL_CHECK_ARG(a->n > 0 && a->n <= 8192 && a->rows > 0, "softmax: n=%d out of range", a->n);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    softmax_rows_kernel<<<(unsigned)a->rows, 256, 0, st>>>(a->s, a->n, a->lds, a->scale, (uint16_t*)a->p_bf16,
-                                                           a->ldp, a->fmt16);
+    const bool vec = a->n % 4 == 0 && a->lds % 4 == 0 && a->ldp % 4 == 0 && (reinterpret_cast<uintptr_t>(a->s) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(a->p_bf16) & 7) == 0;
+    if (vec)
+        softmax_rows_vec4_kernel<<<(unsigned)a->rows, 128, 0, st>>>(a->s, a->n, a->lds, a->scale, (uint16_t*)a->p_bf16,
+                                                                    a->ldp, a->fmt16);
+    else
+        softmax_rows_kernel<<<(unsigned)a->rows, 256, 0, st>>>(a->s, a->n, a->lds, a->scale, (uint16_t*)a->p_bf16,
+                                                               a->ldp, a->fmt16);
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;
 }
@@ -897,6 +968,7 @@ extern "C" int smtl_softmax_run(const smtl_softmax_args* a, void* stream) {
 extern "C" int smtl_xattn_run(const smtl_xattn_args* a, void* stream) {
     SMTL_CHECK_ARG(a && a->q_bf16 && a->kc && a->vc && a->out_bf16, "xattn: NULL argument");
     SMTL_CHECK_ARG(a->rows > 0 && a->rows_per_group > 0 && a->heads > 0, "xattn: bad extent");
+    SMTL_CHECK_ARG(a->ldq % 8 == 0 && a->ldo % 8 == 0, "xattn: row strides must be multiples of 8 elements");
     SMTL_CHECK_ARG((a->rows + a->rows_per_group - 1) / a->rows_per_group <= SMTL_MAX_TASKS, "xattn: too many groups");
     XattnK tk;
     for (int i = 0; i < SMTL_MAX_TASKS; ++i) {

@@ -286,13 +286,20 @@ def test_task_attention(c):
     assert rel_l2(out.float(), ref) < 4e-3
 
 
-def test_softmax_rows():
+@pytest.mark.parametrize("n", [4800, 8192, 77, 4802])      # 128-bit path (n % 4 == 0) and the scalar one
+def test_softmax_rows(n):
     ops, L = _ops()
-    s = rnd(300, 4800, seed=1) * 5
-    p = torch.empty(300, 4800, device=DEV, dtype=H16())
+    s = rnd(300, n, seed=1) * 5
+    p = torch.empty(300, n, device=DEV, dtype=H16())
     ops.softmax_rows(s, p, 0.25).run()
     torch.cuda.synchronize()
     assert rel_l2(p.float(), torch.softmax(s * 0.25, -1)) < 4e-3
+    # a strided view (the VAE mid-attention's padded score matrix)
+    big = rnd(64, n + 8, seed=2) * 3
+    pb = torch.zeros(64, n + 8, device=DEV, dtype=H16())
+    ops.softmax_rows(big[:, :n], pb[:, :n], 0.5).run()
+    torch.cuda.synchronize()
+    assert rel_l2(pb[:, :n].float(), torch.softmax(big[:, :n] * 0.5, -1)) < 4e-3 and float(pb[:, n:].abs().max()) == 0.0
 
 
 def test_task_map_modes():
