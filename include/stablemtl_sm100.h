@@ -404,6 +404,41 @@ typedef struct smtl_taskmap_args {
 } smtl_taskmap_args;
 int smtl_taskmap_run(const smtl_taskmap_args* a, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ evaluation pre-reductions
+ * the evaluation loop that consumes the path's maps reduces every full-resolution map to a few
+ * numbers on the host (src/trainer/stablemtl_trainer.py:580-1093).  These two kernels do the data-sized part of
+ * that on the device so only the sums cross PCIe.  Both ACCUMULATE into their output: zero it (smtl_memset_run) first. */
+
+/* Sums of the scale/shift least-squares alignment of a predicted map to the ground truth
+ * (align_depth_least_square, src/util/alignment.py:122-169: lstsq([pred, 1], gt) over the valid pixels):
+ *     sums[b] = { n, sum p, sum g, sum p*p, sum p*g }     fp64, per image
+ * scale = (n Spg - Sp Sg) / (n Spp - Sp^2), shift = (Sg - scale Sp) / n on the host. */
+typedef struct smtl_lsqsums_args {
+    const float* pred;      /* fp32 [batch, hw] */
+    const float* gt;        /* fp32 [batch, hw] */
+    const uint8_t* valid;   /* [batch, hw] 0 / non-0; NULL = every pixel */
+    int32_t batch;
+    int32_t pad_;
+    int64_t hw;
+    double* sums;           /* fp64 [batch, 5] */
+} smtl_lsqsums_args;
+int smtl_lsqsums_run(const smtl_lsqsums_args* a, void* stream);
+
+/* Confusion-matrix histogram of predicted against true class ids (SemanticMetrics._fast_hist,
+ * src/util/metric_semantic.py:34-50): hist[t * n_classes + p] += 1 for every valid pixel with 0 <= t < n_classes
+ * (a pixel whose prediction is outside [0, n_classes) is an error: SMTL_EINVAL is NOT raised on the device, the
+ * pixel is skipped and counted in hist[n_classes * n_classes]). */
+typedef struct smtl_confusion_args {
+    const int64_t* label_true;  /* int64 [n] */
+    const int64_t* label_pred;  /* int64 [n] */
+    const uint8_t* valid;       /* [n] or NULL */
+    int64_t n;
+    int32_t n_classes;          /* <= 64 */
+    int32_t pad_;
+    int64_t* hist;              /* int64 [n_classes * n_classes + 1] */
+} smtl_confusion_args;
+int smtl_confusion_run(const smtl_confusion_args* a, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ plans
  * A plan is an array of (kind, pointer-to-op-struct); smtl_run_plan launches them in order on one stream
  * from native code, so a whole UNet/VAE pass costs one call across the ABI (and can be stream-captured
@@ -412,7 +447,7 @@ enum {
     SMTL_OP_GEMM = 1, SMTL_OP_FATTN = 2, SMTL_OP_SOFTMAX = 3, SMTL_OP_XATTN = 4, SMTL_OP_TASKATTN = 5,
     SMTL_OP_GN = 6, SMTL_OP_LN = 7, SMTL_OP_UPSAMPLE = 8, SMTL_OP_IM2COL = 9, SMTL_OP_RGBPREP = 10,
     SMTL_OP_UNETIN = 11, SMTL_OP_TASKMAP = 12, SMTL_OP_CHANMIX = 13, SMTL_OP_GNAPPLY = 14, SMTL_OP_MEMSET = 15,
-    SMTL_OP_GNFINALIZE = 16
+    SMTL_OP_GNFINALIZE = 16, SMTL_OP_LSQSUMS = 17, SMTL_OP_CONFUSION = 18
 };
 typedef struct smtl_op_ref {
     int32_t kind;

@@ -19,7 +19,7 @@ ACT_NONE, ACT_GELU, ACT_GEGLU, ACT_SILU = 0, 1, 2, 3
 FMT_BF16, FMT_F16 = 0, 1
 MAP_MEAN1, MAP_RGB3, MAP_NORMAL, MAP_FLOW2, MAP_FLOW3, MAP_SEMANTIC = range(6)
 (OP_GEMM, OP_FATTN, OP_SOFTMAX, OP_XATTN, OP_TASKATTN, OP_GN, OP_LN, OP_UPSAMPLE, OP_IM2COL, OP_RGBPREP,
- OP_UNETIN, OP_TASKMAP, OP_CHANMIX, OP_GNAPPLY, OP_MEMSET, OP_GNFINALIZE) = range(1, 17)
+ OP_UNETIN, OP_TASKMAP, OP_CHANMIX, OP_GNAPPLY, OP_MEMSET, OP_GNFINALIZE, OP_LSQSUMS, OP_CONFUSION) = range(1, 19)
 
 vp = C.c_void_p
 i32 = C.c_int32
@@ -178,17 +178,26 @@ class TaskmapArgs(C.Structure):
                 ("out_ids", vp), ("palette", vp), ("npalette", i32), ("pad_", i32)]
 
 
+class LsqSumsArgs(C.Structure):
+    _fields_ = [("pred", vp), ("gt", vp), ("valid", vp), ("batch", i32), ("pad_", i32), ("hw", i64), ("sums", vp)]
+
+
+class ConfusionArgs(C.Structure):
+    _fields_ = [("label_true", vp), ("label_pred", vp), ("valid", vp), ("n", i64), ("n_classes", i32), ("pad_", i32),
+                ("hist", vp)]
+
+
 class OpRef(C.Structure):
     _fields_ = [("kind", i32), ("pad_", i32), ("op", vp)]
 
 
 STRUCTS_IN_HEADER_ORDER = [GemmSeg, GemmArgs, GemmOp, FattnArgs, FattnOp, SoftmaxArgs, XattnArgs, TaskAttnArgs,
-                           GnArgs, GnApplyArgs, GnFinalizeArgs, MemsetArgs, LnArgs, UpsampleArgs, Im2colArgs, RgbprepArgs, UnetinArgs, ChanmixArgs, TaskmapArgs, OpRef]
+                           GnArgs, GnApplyArgs, GnFinalizeArgs, MemsetArgs, LnArgs, UpsampleArgs, Im2colArgs, RgbprepArgs, UnetinArgs, ChanmixArgs, TaskmapArgs, LsqSumsArgs, ConfusionArgs, OpRef]
 
 EXPORTS = [
     "smtl_gemm_plan", "smtl_gemm_run", "smtl_fattn_plan", "smtl_fattn_run", "smtl_softmax_run", "smtl_xattn_run",
     "smtl_taskattn_run", "smtl_gn_run", "smtl_gnapply_run", "smtl_gnfinalize_run", "smtl_memset_run", "smtl_ln_run", "smtl_upsample_run", "smtl_im2col_run", "smtl_rgbprep_run",
-    "smtl_unetin_run", "smtl_chanmix_run", "smtl_taskmap_run", "smtl_run_plan", "smtl_plan_launches", "smtl_abi_version",
+    "smtl_unetin_run", "smtl_chanmix_run", "smtl_taskmap_run", "smtl_lsqsums_run", "smtl_confusion_run", "smtl_run_plan", "smtl_plan_launches", "smtl_abi_version",
     "smtl_last_error", "smtl_struct_sizes",
 ]
 

@@ -87,7 +87,7 @@ int smtl_struct_sizes(int32_t* out, int32_t cap) {
         (int32_t)sizeof(smtl_gnapply_args), (int32_t)sizeof(smtl_gnfinalize_args), (int32_t)sizeof(smtl_memset_args),
         (int32_t)sizeof(smtl_ln_args),      (int32_t)sizeof(smtl_upsample_args), (int32_t)sizeof(smtl_im2col_args),
         (int32_t)sizeof(smtl_rgbprep_args), (int32_t)sizeof(smtl_unetin_args),  (int32_t)sizeof(smtl_chanmix_args),
-        (int32_t)sizeof(smtl_taskmap_args),
+        (int32_t)sizeof(smtl_taskmap_args), (int32_t)sizeof(smtl_lsqsums_args), (int32_t)sizeof(smtl_confusion_args),
         (int32_t)sizeof(smtl_op_ref)};
     const int n = (int)(sizeof(sizes) / sizeof(sizes[0]));
     for (int i = 0; i < n && i < cap; ++i) out[i] = sizes[i];
@@ -122,6 +122,8 @@ int smtl_run_plan(const smtl_op_ref* ops, int32_t n_ops, void* stream) {
             case SMTL_OP_GNAPPLY: rc = smtl_gnapply_run((const smtl_gnapply_args*)p, stream); break;
             case SMTL_OP_MEMSET: rc = smtl_memset_run((const smtl_memset_args*)p, stream); break;
             case SMTL_OP_GNFINALIZE: rc = smtl_gnfinalize_run((const smtl_gnfinalize_args*)p, stream); break;
+            case SMTL_OP_LSQSUMS: rc = smtl_lsqsums_run((const smtl_lsqsums_args*)p, stream); break;
+            case SMTL_OP_CONFUSION: rc = smtl_confusion_run((const smtl_confusion_args*)p, stream); break;
             default:
                 smtl_host::set_error("plan op %d: unknown kind %d", i, ops[i].kind);
                 return SMTL_EKIND;

@@ -725,6 +725,55 @@ __global__ void taskattn_kernel(const uint16_t* __restrict__ q, const uint16_t* 
     }
 }
 
+// ============================================================================================= evaluation pre-reductions
+// least-squares alignment sums: grid (blocks per image, batch); fp64 accumulation, one atomicAdd(double) x 5 per warp
+__global__ void __launch_bounds__(256) lsqsums_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                                      const uint8_t* __restrict__ valid, int64_t hw,
+                                                      double* __restrict__ sums) {
+    const int b = blockIdx.y;
+    const float* p = pred + (int64_t)b * hw;
+    const float* g = gt + (int64_t)b * hw;
+    const uint8_t* v = valid ? valid + (int64_t)b * hw : nullptr;
+    double n = 0.0, sp = 0.0, sg = 0.0, spp = 0.0, spg = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (int64_t)gridDim.x * blockDim.x) {
+        if (v && !v[i]) continue;
+        const double x = (double)__ldg(p + i), y = (double)__ldg(g + i);
+        n += 1.0; sp += x; sg += y; spp += x * x; spg += x * y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n += __shfl_xor_sync(0xffffffffu, n, o);
+        sp += __shfl_xor_sync(0xffffffffu, sp, o);
+        sg += __shfl_xor_sync(0xffffffffu, sg, o);
+        spp += __shfl_xor_sync(0xffffffffu, spp, o);
+        spg += __shfl_xor_sync(0xffffffffu, spg, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        double* dst = sums + (int64_t)b * 5;
+        atomicAdd(dst, n); atomicAdd(dst + 1, sp); atomicAdd(dst + 2, sg); atomicAdd(dst + 3, spp); atomicAdd(dst + 4, spg);
+    }
+}
+
+// confusion histogram: per-CTA shared-memory bins (integer atomics: the result is order-independent, bit-exact)
+__global__ void __launch_bounds__(256) confusion_kernel(const int64_t* __restrict__ lt, const int64_t* __restrict__ lp,
+                                                        const uint8_t* __restrict__ valid, int64_t n, int nc,
+                                                        unsigned long long* __restrict__ hist) {
+    extern __shared__ unsigned int bins[];          // nc * nc + 1
+    const int nb = nc * nc + 1;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) bins[i] = 0u;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (valid && !valid[i]) continue;
+        const int64_t t = __ldg(lt + i), p = __ldg(lp + i);
+        if (t < 0 || t >= nc) continue;
+        if (p < 0 || p >= nc) { atomicAdd(&bins[nc * nc], 1u); continue; }
+        atomicAdd(&bins[(int)t * nc + (int)p], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb; i += blockDim.x)
+        if (bins[i]) atomicAdd(hist + i, (unsigned long long)bins[i]);
+}
+
 __global__ void chanmix_kernel(const float* __restrict__ x, int64_t rows, int cin, int cout, const float* __restrict__ w,
                                const float* __restrict__ b, float* __restrict__ y) {
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
@@ -868,6 +917,29 @@ extern "C" int smtl_gnfinalize_run(const smtl_gnfinalize_args* a, void* stream) 
     gn_finalize_kernel<<<a->batch, threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
         a->stats, a->stats_replicas, a->batch, a->c, a->groups, (double)a->pixels * (a->c / a->groups), a->eps, a->gamma,
         a->beta, a->ss);
+    SMTL_CHECK_CUDA(cudaGetLastError());
+    return SMTL_OK;
+}
+
+extern "C" int smtl_lsqsums_run(const smtl_lsqsums_args* a, void* stream) {
+    SMTL_CHECK_ARG(a && a->pred && a->gt && a->sums, "lsqsums: NULL argument");
+    SMTL_CHECK_ARG(a->batch > 0 && a->batch <= 65535 && a->hw > 0, "lsqsums: bad extent");
+    int64_t blocks = (a->hw + 256 * 8 - 1) / (256 * 8);
+    if (blocks > 1184) blocks = 1184;               // 8 CTAs per SM
+    lsqsums_kernel<<<dim3((unsigned)blocks, (unsigned)a->batch), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        a->pred, a->gt, a->valid, a->hw, a->sums);
+    SMTL_CHECK_CUDA(cudaGetLastError());
+    return SMTL_OK;
+}
+
+extern "C" int smtl_confusion_run(const smtl_confusion_args* a, void* stream) {
+    SMTL_CHECK_ARG(a && a->label_true && a->label_pred && a->hist, "confusion: NULL argument");
+    SMTL_CHECK_ARG(a->n > 0 && a->n_classes > 0 && a->n_classes <= 64, "confusion: bad extent (n_classes <= 64)");
+    int64_t blocks = (a->n + 256 * 16 - 1) / (256 * 16);
+    if (blocks > 1184) blocks = 1184;
+    const size_t smem = ((size_t)a->n_classes * a->n_classes + 1) * sizeof(unsigned int);
+    confusion_kernel<<<(unsigned)blocks, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+        a->label_true, a->label_pred, a->valid, a->n, a->n_classes, reinterpret_cast<unsigned long long*>(a->hist));
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;
 }

@@ -60,7 +60,7 @@ _RUNNERS = {
     L.OP_LN: "smtl_ln_run", L.OP_UPSAMPLE: "smtl_upsample_run", L.OP_IM2COL: "smtl_im2col_run",
     L.OP_RGBPREP: "smtl_rgbprep_run", L.OP_UNETIN: "smtl_unetin_run", L.OP_TASKMAP: "smtl_taskmap_run",
     L.OP_CHANMIX: "smtl_chanmix_run", L.OP_GNAPPLY: "smtl_gnapply_run", L.OP_MEMSET: "smtl_memset_run",
-    L.OP_GNFINALIZE: "smtl_gnfinalize_run",
+    L.OP_GNFINALIZE: "smtl_gnfinalize_run", L.OP_LSQSUMS: "smtl_lsqsums_run", L.OP_CONFUSION: "smtl_confusion_run",
 }
 
 
@@ -445,3 +445,27 @@ def task_map(x, batch, hw, mode, *, out_clipped=None, out_post=None, out_ids=Non
         a.palette, a.npalette = palette.data_ptr(), palette.shape[0]
     assert x.dtype == F32
     return Op(L.OP_TASKMAP, a, (x, out_clipped, out_post, out_ids, palette), 0, "task_map")
+
+
+# ------------------------------------------------------------------------------------------------- evaluation pre-reductions
+def lsq_sums(pred, gt, valid, sums):
+    """accumulates fp64 [batch, 5] = (n, sum p, sum g, sum p*p, sum p*g) over the valid pixels of fp32 [batch, hw] maps"""
+    a = L.LsqSumsArgs()
+    batch, hw = pred.shape[0], pred[0].numel()
+    assert pred.dtype == F32 and gt.dtype == F32 and pred.is_contiguous() and gt.is_contiguous() and gt.shape == pred.shape
+    assert sums.dtype == torch.float64 and sums.shape == (batch, 5) and sums.is_contiguous()
+    assert valid is None or (valid.dtype in (torch.uint8, torch.bool) and valid.is_contiguous() and valid.numel() == pred.numel())
+    a.pred, a.gt, a.valid, a.batch, a.hw, a.sums = pred.data_ptr(), gt.data_ptr(), _ptr(valid), batch, hw, sums.data_ptr()
+    return Op(L.OP_LSQSUMS, a, (pred, gt, valid, sums), 0, "lsq_sums")
+
+
+def confusion(label_true, label_pred, valid, hist, n_classes):
+    """accumulates int64 [n_classes^2 + 1]: the confusion matrix (row = true class) + count of out-of-range predictions"""
+    a = L.ConfusionArgs()
+    assert label_true.dtype == torch.int64 and label_pred.dtype == torch.int64 and label_true.shape == label_pred.shape
+    assert label_true.is_contiguous() and label_pred.is_contiguous()
+    assert hist.dtype == torch.int64 and hist.numel() == n_classes * n_classes + 1 and hist.is_contiguous()
+    assert valid is None or (valid.dtype in (torch.uint8, torch.bool) and valid.is_contiguous() and valid.numel() == label_true.numel())
+    a.label_true, a.label_pred, a.valid = label_true.data_ptr(), label_pred.data_ptr(), _ptr(valid)
+    a.n, a.n_classes, a.hist = label_true.numel(), n_classes, hist.data_ptr()
+    return Op(L.OP_CONFUSION, a, (label_true, label_pred, valid, hist), 0, "confusion")

@@ -2,6 +2,8 @@
 (the op-level oracle), called through the C ABI.  bf16 operands are rounded first so the comparison isolates
 the kernel's arithmetic; tolerances are stated per test."""
 import math
+import os
+import sys
 
 import pytest
 import torch
@@ -10,6 +12,7 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 DEV = "cuda"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _ops():
@@ -683,3 +686,71 @@ def test_gn_apply_reads_padded_input():
     torch.cuda.synchronize()
     ref = F.silu(F.group_norm(x.float().permute(0, 3, 1, 2), 32, gamma, beta, eps=1e-6)).permute(0, 2, 3, 1)
     assert rel_l2(out.float(), _pad_layout(ref)) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------- evaluation pre-reductions
+@pytest.mark.parametrize("masked", [True, False])
+def test_lsq_sums_and_scale_shift_vs_oracle(masked):
+    """device sums -> scale/shift against the numpy restatement of align_depth_least_square (alignment.py:122-169)"""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from oracle import metrics_oracle as MO
+    from stablemtl_b200.evaluate import lsq_scale_shift
+    ops, L = _ops()
+    b, h, w = 3, 480, 640
+    g = torch.Generator().manual_seed(7)
+    pred = torch.rand(b, h, w, generator=g)
+    gt = 3.0 * pred + 0.25 + 0.1 * torch.randn(b, h, w, generator=g)
+    valid = (torch.rand(b, h, w, generator=g) > 0.4) if masked else torch.ones(b, h, w, dtype=torch.bool)
+    sums = torch.zeros(b, 5, dtype=torch.float64, device=DEV)
+    ops.lsq_sums(pred.to(DEV).reshape(b, -1), gt.to(DEV).reshape(b, -1),
+                 valid.to(DEV).to(torch.uint8).reshape(b, -1) if masked else None, sums).run()
+    torch.cuda.synchronize()
+    scale, shift = lsq_scale_shift(sums)
+    for i in range(b):
+        assert int(sums[i, 0].item()) == int(valid[i].sum())                 # the count is exact
+        _, s, t = MO.align_least_square(gt[i].numpy(), pred[i].numpy(), valid[i].numpy())
+        assert abs(scale[i] - float(s[0])) <= 1e-4 * abs(float(s[0])) and abs(shift[i] - float(t[0])) <= 1e-4
+    # sums are linear: accumulating the two halves of an image separately gives the whole
+    two = torch.zeros(1, 5, dtype=torch.float64, device=DEV)
+    half = h * w // 2
+    p0, g0 = pred[0].reshape(1, -1).to(DEV), gt[0].reshape(1, -1).to(DEV)
+    ops.lsq_sums(p0[:, :half].contiguous(), g0[:, :half].contiguous(), None, two).run()
+    ops.lsq_sums(p0[:, half:].contiguous(), g0[:, half:].contiguous(), None, two).run()
+    whole = torch.zeros(1, 5, dtype=torch.float64, device=DEV)
+    ops.lsq_sums(p0, g0, None, whole).run()
+    torch.cuda.synchronize()
+    assert torch.allclose(two, whole, rtol=1e-12, atol=0)
+
+
+def test_confusion_histogram_bit_exact_vs_oracle():
+    """integer work: bit-exact against SemanticMetrics.update/_fast_hist (metric_semantic.py:34-50)"""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from oracle import metrics_oracle as MO
+    ops, L = _ops()
+    g = torch.Generator().manual_seed(11)
+    lt = torch.randint(-1, 10, (4, 480, 640), generator=g)                  # -1, 8, 9: ignored labels
+    lp = torch.randint(0, 8, (4, 480, 640), generator=g)
+    vm = torch.rand(4, 480, 640, generator=g) > 0.25
+    hist = torch.zeros(65, dtype=torch.int64, device=DEV)
+    ops.confusion(lt.to(DEV), lp.to(DEV), vm.to(DEV).to(torch.uint8), hist, 8).run()
+    torch.cuda.synchronize()
+    want = MO.confusion(lt.numpy(), lp.numpy(), vm.numpy(), 8)
+    assert np.array_equal(hist[:64].cpu().numpy().reshape(8, 8), want.astype(np.int64)) and int(hist[64]) == 0
+    # accumulation + no mask + an out-of-range prediction is counted aside, not binned
+    lp2 = lp.clone()
+    lp2[0, 0, :5] = 8
+    lt2 = lt.clone()
+    lt2[0, 0, :5] = 3
+    ops.confusion(lt2.to(DEV), lp2.to(DEV), None, hist, 8).run()
+    torch.cuda.synchronize()
+    lt3, lp3 = lt2.numpy().reshape(-1), lp2.numpy().reshape(-1)
+    keep = lp3 < 8
+    want2 = want + MO.fast_hist(lt3[keep], lp3[keep], 8)
+    assert np.array_equal(hist[:64].cpu().numpy().reshape(8, 8), want2.astype(np.int64)) and int(hist[64]) == 5
+    # empty / tiny inputs
+    h1 = torch.zeros(65, dtype=torch.int64, device=DEV)
+    ops.confusion(torch.tensor([2], device=DEV), torch.tensor([2], device=DEV), None, h1, 8).run()
+    torch.cuda.synchronize()
+    assert int(h1.sum()) == 1 and int(h1[2 * 8 + 2]) == 1

@@ -186,3 +186,45 @@ def test_dropin_pipeline_call_surface():
         assert getattr(out, fields[t]) is arr
     with pytest.raises(ValueError):
         pipe(input_image=rgb, exclude_mainstream_output_type=True, processing_res=0, output_type="bogus")
+
+
+def test_batched_evaluator_matches_direct_predict_and_device_metrics():
+    """batches pushed through BatchedEvaluator (one in flight, pinned staging) give the maps of
+    direct predict() calls; the device-side confusion matrix / alignment sums of those maps equal the host oracle's."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from oracle import metrics_oracle as MO
+    from stablemtl_b200 import synth
+    from stablemtl_b200.evaluate import BatchedEvaluator, DeviceMetrics, lsq_scale_shift
+    eng, _ = build_engine(synth.TINY_UNET, synth.TINY_VAE, False)
+    batches = [synth.make_images(2, 64, 96, seed=20 + i) for i in range(3)]
+    direct = []
+    for rgb, nxt in batches:
+        r = eng.predict(rgb.cuda(), nxt.cuda())
+        direct.append({t: v.clone() for t, v in r.items()})
+    got = dict(BatchedEvaluator(eng).run(iter(batches)))
+    assert sorted(got) == [0, 1, 2]
+    for i in range(3):
+        for t in synth.TASKS:
+            a, b = torch.as_tensor(got[i][t]), direct[i][t].cpu()
+            if t == "semantic":
+                assert (a == b).float().mean() > 0.99
+            else:
+                assert rel_l2(a, b) < REL_L2_TOL, (i, t)          # run-to-run bound of the engine (atomics order)
+    # device-side reductions on maps that never leave the GPU
+    dm = DeviceMetrics("cuda", 8)
+    gen = torch.Generator().manual_seed(3)
+    for i, (j, maps) in enumerate(BatchedEvaluator(eng, keep_on_device=True).run(iter(batches))):
+        gt_sem = torch.randint(0, 8, maps["semantic"].shape, generator=gen)
+        valid = torch.rand(maps["semantic"].shape, generator=gen) > 0.2
+        dm.update_semantic(gt_sem.cuda(), maps["semantic"], valid.cuda())
+        if i == 0:
+            want_cm = np.zeros((8, 8))
+        want_cm += MO.confusion(gt_sem.numpy(), maps["semantic"].cpu().numpy(), valid.numpy(), 8)
+        gt_d = 2.0 * maps["depth"].cpu() + 0.3
+        sums = dm.depth_alignment_sums(maps["depth"], gt_d.cuda(), valid.cuda())
+        scale, shift = lsq_scale_shift(sums)
+        for b in range(maps["depth"].shape[0]):
+            _, s, t = MO.align_least_square(gt_d[b].numpy(), maps["depth"][b].cpu().numpy(), valid[b].numpy())
+            assert abs(scale[b] - float(s[0])) < 1e-3 and abs(shift[b] - float(t[0])) < 1e-3
+    assert np.array_equal(dm.confusion_matrix(), want_cm.astype(np.int64))
