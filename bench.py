@@ -379,6 +379,15 @@ def main():
                 fattn_flops += op.flops * reps
     pk = peaks()
     peak = pk["bf16_tflops_sustained"] if pk else 1400.0
+    # DRAM traffic of the dominant kernel: from the committed `ncu --set full` capture (never measured under this run)
+    traffic = traffic_note = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        traffic_note = (f"bytes per launch of {tr['kernel']} on {tr['launch']}: dram read {tr['dram_bytes_read']} + write "
+                        f"{tr['dram_bytes_write']} vs {tr['algorithmic_bytes']} algorithmic ({tr['capture']})")
+    except Exception:
+        pass
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
     alg = algorithmic_flops(H // 8, W // 8, multi)
     if args.breakdown:
@@ -405,7 +414,7 @@ def main():
             "kernel": "smtl_gemm_kernel (tcgen05 implicit-GEMM convs + token linears)", "bound": "tensor",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if pk else "fallback",
-            "traffic": None, "share_of_step": gemm_ms / total_ms,
+            "traffic": traffic, "traffic_note": traffic_note, "share_of_step": gemm_ms / total_ms,
             "whole_step_tflops": alg["total"] * B / (ms_per_step * 1e-3) / 1e12,
             "whole_step_frac": alg["total"] * B / (ms_per_step * 1e-3) / 1e12 / peak,
             "unet_contractions_frac_of_peak": None,
