@@ -72,6 +72,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Long waits (an epilogue warp waiting for a whole tile's MMAs): back off between polls so that idle warps do not
+// compete with the producer / MMA warps for the barrier unit.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(ns);
+        if (++spins > SMTL_SPIN_LIMIT) {
+            printf("smtl: mbarrier watchdog block=(%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y,
+                   threadIdx.x, smem_u32(bar), parity);
+            __trap();
+        }
+    }
+}
+
 // Warp-collective wait: lane 0 polls, the other lanes park at the warp barrier.  An mbarrier wait executed by all 32
 // lanes is 32 serialised barrier-unit operations (~430 clk per warp-wide wait measured on B200, and the spinning lanes
 // of idle warps slow everyone else's barrier traffic); __syncwarp() orders the other lanes after lane 0's observation.

@@ -24,7 +24,15 @@ constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int NUM_THREADS = 320;                   // TMA warp + MMA warp + 8 epilogue warps
 constexpr int EPI_WARPS = 8;
 constexpr int SMEM_BUDGET = 227 * 1024;
-constexpr int GEMM_MAX_STAGES = 24;                // mbarrier slots of smtl_gemm_kernel's rings (activation + weight)
+constexpr int GEMM_MAX_STAGES = 24;
+// The operand tiles are written by TMA and read by tcgen05.mma, both in the async proxy and ordered by the mbarrier's
+// complete_tx; no tcgen05.fence is needed between the full-barrier wait and the MMAs (the fence after the acc_empty
+// wait, which orders the epilogue's tcgen05.ld before the overwriting MMA, stays).
+#ifdef SMTL_MAINLOOP_FENCE
+#define MAINLOOP_FENCE() tc_fence_after()
+#else
+#define MAINLOOP_FENCE() ((void)0)
+#endif                // mbarrier slots of smtl_gemm_kernel's rings (activation + weight)
 
 struct alignas(64) GemmKParams {
     CUtensorMap tm_a0;
@@ -517,7 +525,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
                         for (int sub = 0; sub < nsub; ++sub) {
                             const int wb = p.sp + ws;
                             mbar_wait(&full_bar[wb], wph);
-                            tc_fence_after();
+                            MAINLOOP_FENCE();
                             const uint64_t da = make_smem_desc_sw128(sa + sub * 128);      // tap `sub`: one row further
                             const uint64_t db = make_smem_desc_sw128(smem_u32(smem_w + (size_t)ws * B_STAGE_BYTES));
                             if (elect_one()) {
@@ -555,7 +563,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
                 const uint32_t tmem_d = tmem_base + acc * ACC_STRIDE;
                 for (int kb = 0; kb < p.total_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
+                    MAINLOOP_FENCE();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
                     const uint64_t da = make_smem_desc_sw128(sa);
                     const uint64_t db = make_smem_desc_sw128(sa + A_STAGE_BYTES);
@@ -594,7 +602,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
             const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
             EpiRow<BN> er;
             epilogue_prepare<BN>(p, ((int64_t)tm * CG + rank) * BLOCK_M + row_in_tile, tn, lane, er);
-            mbar_wait(&acc_full[acc], acc_phase);
+            mbar_wait_backoff(&acc_full[acc], acc_phase, 100);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
             epilogue_rows<BN>(p, taddr, tn, lane, half, er);
@@ -751,7 +759,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
                         for (int sub = 0; sub < nsub; ++sub) {
                             const int wb = p.sp + ws;
                             mbar_wait(&full_bar[wb], wph);
-                            tc_fence_after();
+                            MAINLOOP_FENCE();
                             const uint64_t da = make_smem_desc_sw128(smem_u32(smem_w + (size_t)ws * A_STAGE_BYTES));
                             const uint64_t db = make_smem_desc_sw128(sx + sub * 128);            // tap `sub`: one pixel row further
                             if (elect_one()) {
@@ -784,7 +792,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
                 const uint32_t tmem_d = tmem_base + acc * ACC_STRIDE;
                 for (int kb = 0; kb < p.total_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
+                    MAINLOOP_FENCE();
                     const uint32_t sw = smem_u32(smem + (size_t)stage * T_STAGE_BYTES);
                     const uint64_t da = make_smem_desc_sw128(sw);
                     const uint64_t db = make_smem_desc_sw128(sw + A_STAGE_BYTES);
@@ -1121,7 +1129,11 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
         cg = env ? atoi(env) : ((tiles256 >= sms / 2 && g.nseg == 1 && g.k >= 2048 && g.n >= 256) ? 2 : 1);
         // shift-grouped convs with full-width tiles: pairs halve the weight traffic (L2 -> smem and smem -> MMA)
         const char* envc = getenv("SMTL_GEMM_CG_CONV");
-        if (!env && op->grouped && bn == 256 && tiles256 >= sms / 2 && !(envc && envc[0] == '0')) cg = 2;
+        // measured (scripts/exp_pairs.py): +8 % at bn = 256, +2-3 % at bn = 160; SMTL_GEMM_CG_CONV=1 restricts to 256
+        const bool any_bn = !(envc && envc[0] == '1');
+        if (!env && op->grouped && (bn == 256 || (any_bn && bn % 16 == 0 && bn >= 128)) && tiles256 >= sms / 2 &&
+            !(envc && envc[0] == '0'))
+            cg = 2;
         if (g.group_rows) cg = 1;
     }
     SMTL_CHECK_ARG(cg == 1 || cg == 2, "gemm_plan: cta_group %d", cg);
