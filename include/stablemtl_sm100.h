@@ -112,14 +112,6 @@ typedef struct smtl_gemm_args {
      * [g * group_rows, (g+1) * group_rows) use weight rows [g * n, (g+1) * n) of b (stacked [groups * n, k]) and bias
      * [g * n, (g+1) * n).  group_rows must be a multiple of 128 (256 for cta_group 2); 0 = off. */
     int64_t group_rows;
-    /* Fused GroupNorm(+SiLU) of the activation operand a0 (3x3 convs over the padded layout only): a0 holds the RAW
-     * map; every tile is normalised in shared memory between TMA and the MMA with
-     *     y = silu?(x * gn_ss[img, c, 0] + gn_ss[img, c, 1])      gn_ss: fp32 [images, a0_cols, 2] (smtl_gnfinalize_run)
-     * and halo / out-of-range rows forced to zero, so no normalised copy of the map is ever written (replaces
-     * GroupNorm + SiLU at src/model/resnet.py:177-178,188,194 and diffusers ResnetBlock2D).  NULL = off. */
-    const float* gn_ss;
-    int32_t gn_silu;
-    int32_t pad3_;
 } smtl_gemm_args;
 
 typedef struct smtl_gemm_op {
@@ -279,7 +271,7 @@ typedef struct smtl_gnapply_args {
 int smtl_gnapply_run(const smtl_gnapply_args* a, void* stream);
 
 /* Per-(image, channel) scale / shift of a GroupNorm from the producer-side sums: ss[b, c] = (rstd * gamma, beta -
- * mean * rstd * gamma) -- the table the fused conv prologue (smtl_gemm_args.gn_ss) applies. */
+ * mean * rstd * gamma): what GroupNorm reduces to per image once the producer-side sums are known. */
 typedef struct smtl_gnfinalize_args {
     const float* stats;     /* fp32 [stats_replicas, batch, c, 2] */
     int32_t stats_replicas, batch, c, groups;

@@ -55,7 +55,6 @@ class GemmArgs(C.Structure):
         ("stats_rows_per_image", i32), ("stats_images", i32),
         ("cta_group", i32), ("up_parity", i32),
         ("group_rows", i64),
-        ("gn_ss", vp), ("gn_silu", i32), ("pad3_", i32),
     ]
 
 

@@ -127,8 +127,7 @@ def new_stats(images, channels, device):
 
 def gemm(a0, b, *, m=None, k=None, n=None, a1=None, segs=None, bias=None, bias_per_row=False, act=L.ACT_NONE,
          res1=None, res2=None, out_f32=None, out_bf16=None, aux_bf16=None, rowmap=L.ROWMAP_IDENTITY, img_hw=None,
-         block_n=0, name="gemm", stats=None, stats_rows_per_image=0, cta_group=0, up_parity=0, group_rows=0,
-         gn=None, gn_silu=True):
+         block_n=0, name="gemm", stats=None, stats_rows_per_image=0, cta_group=0, up_parity=0, group_rows=0):
     """D = A @ B^T (+ fused epilogue).  a0/a1: bf16 [rows, cols] (row stride = stride(0)); b: bf16 [n, k].
     segs: list of (row_shift, kblocks, src, a_col0)."""
     assert a0.dtype == BF16 and b.dtype == BF16 and a0.stride(-1) == 1 and b.stride(-1) == 1
@@ -187,16 +186,13 @@ def gemm(a0, b, *, m=None, k=None, n=None, a1=None, segs=None, bias=None, bias_p
     g.cta_group = cta_group
     g.up_parity = up_parity
     g.group_rows = group_rows
-    if gn is not None:              # fused GroupNorm(+SiLU) of a0: gn = fp32 [images, a0_cols, 2] (scale, shift)
-        assert gn.dtype == F32 and gn.is_contiguous() and gn.shape[1:] == (a0.shape[1], 2)
-        g.gn_ss, g.gn_silu = gn.data_ptr(), int(gn_silu)
     op = L.GemmOp()
     L.check(L.lib.smtl_gemm_plan(C.byref(g), C.byref(op)), "smtl_gemm_plan")
     if group_rows:
         assert n is not None and b.shape[0] == (int(g.m) // group_rows) * n, "grouped GEMM: b is [groups * n, k], pass n"
         assert bias is None or bias.numel() == b.shape[0]
     flops = 2 * int(g.m) * int(g.n) * int(g.k)
-    return Op(L.OP_GEMM, op, (a0, a1, b, bias, res1, res2, out_f32, out_bf16, aux_bf16, stats, gn), flops, name)
+    return Op(L.OP_GEMM, op, (a0, a1, b, bias, res1, res2, out_f32, out_bf16, aux_bf16, stats), flops, name)
 
 
 def conv3x3_segs(cin, w, shortcut_cin=0):
@@ -361,7 +357,7 @@ def gn_apply(x0, stats0, batch, h, w, gamma, beta, out, *, x1=None, stats1=None,
 
 
 def gn_finalize(stats, batch, pixels, gamma, beta, ss, *, eps, groups=32):
-    """producer-side channel sums -> fp32 [batch, C, 2] (scale, shift) for the fused GroupNorm prologue of a conv"""
+    """producer-side channel sums -> fp32 [batch, C, 2] (scale, shift): GroupNorm as a per-image affine map"""
     a = L.GnFinalizeArgs()
     c = stats.shape[2]
     assert stats.shape[1:] == (batch, c, 2) and ss.shape == (batch, c, 2) and ss.dtype == F32 and ss.is_contiguous()

@@ -754,3 +754,24 @@ def test_confusion_histogram_bit_exact_vs_oracle():
     ops.confusion(torch.tensor([2], device=DEV), torch.tensor([2], device=DEV), None, h1, 8).run()
     torch.cuda.synchronize()
     assert int(h1.sum()) == 1 and int(h1[2 * 8 + 2]) == 1
+
+
+def test_gn_finalize_scale_shift_table():
+    """producer-side sums -> per-(image, channel) (scale, shift): GroupNorm(x)[b, c] == x * scale + shift"""
+    ops, L = _ops()
+    b, hw, c, groups = 3, 500, 320, 32
+    x = rnd(b, hw, c, seed=1) * 2 + 0.7
+    st = ops.new_stats(b, c, DEV)
+    xd = x.double()
+    full = torch.stack([xd.sum(1), (xd * xd).sum(1)], dim=-1).float()
+    if st.shape[0] > 1:
+        st[0], st[1] = full * 0.25, full * 0.75
+    else:
+        st[0] = full
+    gamma, beta = rnd(c, seed=3) + 1, rnd(c, seed=4)
+    ss = torch.zeros(b, c, 2, device=DEV)
+    ops.gn_finalize(st, b, hw, gamma, beta, ss, eps=1e-6, groups=groups).run()
+    torch.cuda.synchronize()
+    ref = F.group_norm(x.permute(0, 2, 1).reshape(b, c, hw, 1), groups, gamma, beta, eps=1e-6).reshape(b, c, hw).permute(0, 2, 1)
+    got = x * ss[:, None, :, 0] + ss[:, None, :, 1]
+    assert rel_l2(got, ref) < 1e-5
