@@ -973,7 +973,7 @@ int launch_gemm_cg(const GemmKParams& kp, int cg, int grid, int smem_bytes, cuda
     return cg == 2 ? launch_gemm<BN, 2>(kp, grid, smem_bytes, stream) : launch_gemm<BN, 1>(kp, grid, smem_bytes, stream);
 }
 
-int pick_block_n(int n, int act) {
+int pick_block_n(int n, int act, int total_kb) {
     if (act == SMTL_ACT_GEGLU) return 256;
     if (n <= 32) return 32;
     if (n <= 64) return 64;
@@ -983,8 +983,15 @@ int pick_block_n(int n, int act) {
     double best_cost = 1e30;
     for (int bn : cands) {
         const int tiles = (n + bn - 1) / bn;
-        // MMA time ~ tiles * max(bn, 160) (narrow tiles are smem-bandwidth bound); small bonus for wide tiles
-        const double cost = (double)tiles * (bn > 160 ? bn : 160) * (1.0 + 16.0 / bn);
+        double cost;
+        if (total_kb >= 16) {
+            // long-K (convs): a k-block costs max(bn / 2 tensor cycles, ~550 clk of barrier hand-offs), so up to ~270
+            // columns are free: fewest tiles wins, then fewest padded columns (N = 640: 3 x 224 beats 4 x 160 by 18 %)
+            cost = (double)tiles * (bn > 275 ? bn : 275) + 1e-3 * tiles * bn;
+        } else {
+            // short-K linears are epilogue / store bound: MMA time ~ tiles * max(bn, 160), small bonus for wide tiles
+            cost = (double)tiles * (bn > 160 ? bn : 160) * (1.0 + 16.0 / bn);
+        }
         if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
     }
     return best;
@@ -1017,7 +1024,7 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
     }
     SMTL_CHECK_ARG(total_kb * BLOCK_K >= g.k && (total_kb - 1) * BLOCK_K < g.k,
                    "gemm_plan: segments cover %d K blocks but k=%d", total_kb, g.k);
-    int bn = g.block_n ? g.block_n : pick_block_n(g.n, g.act);
+    int bn = g.block_n ? g.block_n : pick_block_n(g.n, g.act, total_kb);
     SMTL_CHECK_ARG(bn == 32 || bn == 64 || bn == 128 || bn == 160 || bn == 192 || bn == 224 || bn == 256,
                    "gemm_plan: unsupported block_n %d", bn);
     if (g.act == SMTL_ACT_GEGLU) {
