@@ -355,6 +355,7 @@ def main():
     by_name = {}
     gemm_ms = gemm_flops = 0.0
     fattn_ms = fattn_flops = 0.0
+    hbm = {}                                  # bandwidth-bound kernels with byte accounting: name -> [ms, bytes]
     total_ms = 0.0
     for pname, plan, reps in plans:
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(plan.ops) + 1)]
@@ -377,6 +378,10 @@ def main():
             elif op.kind == L.OP_FATTN:
                 fattn_ms += t
                 fattn_flops += op.flops * reps
+            if getattr(op, "bytes", 0):
+                h = hbm.setdefault(op.name, [0.0, 0.0])
+                h[0] += t
+                h[1] += op.bytes * reps
     pk = peaks()
     peak = pk["bf16_tflops_sustained"] if pk else 1400.0
     # DRAM traffic of the dominant kernel: from the committed `ncu --set full` capture (never measured under this run)
@@ -423,6 +428,11 @@ def main():
             "algorithmic_tflop_per_image": alg["total"] / 1e12,
         },
     }
+    # the HBM-bound residue: algorithmic bytes / CUDA-event time against the measured copy bandwidth
+    hbm_peak = pk["hbm_gbs"] if pk else 6500.0
+    line["roofline"]["hbm_bound_kernels"] = {
+        k: {"GB/s": v[1] / (v[0] * 1e-3) / 1e9, "frac_of_copy_peak": v[1] / (v[0] * 1e-3) / 1e9 / hbm_peak,
+            "share_of_step": v[0] / total_ms} for k, v in hbm.items() if v[0] > 0}
     # UNet-only fraction of peak (north_star "UNet % TC peak"): algorithmic UNet flops / instrumented UNet time
     unet_ms = sum(v[0] for k, v in by_name.items() if k.startswith("unet"))
     if unet_ms > 0:

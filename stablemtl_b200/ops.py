@@ -65,10 +65,11 @@ _RUNNERS = {
 
 
 class Op:
-    __slots__ = ("kind", "struct", "keep", "flops", "name")
+    __slots__ = ("kind", "struct", "keep", "flops", "name", "bytes")
 
-    def __init__(self, kind, struct, keep=(), flops=0, name=""):
+    def __init__(self, kind, struct, keep=(), flops=0, name="", nbytes=0):
         self.kind, self.struct, self.keep, self.flops, self.name = kind, struct, keep, flops, name
+        self.bytes = nbytes          # algorithmic HBM bytes of a bandwidth-bound op (0: not accounted)
 
     def run(self):
         fn = getattr(L.lib, _RUNNERS[self.kind])
@@ -353,7 +354,10 @@ def gn_apply(x0, stats0, batch, h, w, gamma, beta, out, *, x1=None, stats1=None,
     a.silu, a.pad_out = int(silu), int(pad_out)
     a.out_bf16, a.raw_bf16 = out.data_ptr(), _ptr(raw)
     assert out.dtype == BF16
-    return Op(L.OP_GNAPPLY, a, (x0, x1, stats0, stats1, gamma, beta, out, raw), 0, "gn_apply")
+    # algorithmic bytes: every interior element read once, every output element (halo included) written once
+    nb = batch * h * w * (x0.shape[-1] * x0.element_size() + (0 if x1 is None else x1.shape[-1] * x1.element_size()))
+    nb += out.numel() * out.element_size() + (0 if raw is None else raw.numel() * raw.element_size())
+    return Op(L.OP_GNAPPLY, a, (x0, x1, stats0, stats1, gamma, beta, out, raw), 0, "gn_apply", nb)
 
 
 def gn_finalize(stats, batch, pixels, gamma, beta, ss, *, eps, groups=32):
@@ -384,7 +388,8 @@ def layer_norm(x, gamma0, beta0, out0, *, gamma1=None, beta1=None, out1=None, ro
     a.gamma1, a.beta1, a.out1 = _ptr(gamma1), _ptr(beta1), _ptr(out1)
     a.ldo = out0.stride(0)
     assert out0.dtype == BF16 and gamma0.dtype == F32
-    return Op(L.OP_LN, a, (x, gamma0, beta0, out0, gamma1, beta1, out1), 0, "layer_norm")
+    nb = x.numel() * x.element_size() + out0.numel() * out0.element_size() + (0 if out1 is None else out1.numel() * out1.element_size())
+    return Op(L.OP_LN, a, (x, gamma0, beta0, out0, gamma1, beta1, out1), 0, "layer_norm", nb)
 
 
 # ------------------------------------------------------------------------------------------------- data movement
