@@ -25,6 +25,9 @@ constexpr int NUM_THREADS = 320;                   // TMA warp + MMA warp + 8 ep
 constexpr int EPI_WARPS = 8;
 constexpr int SMEM_BUDGET = 227 * 1024;
 constexpr int GEMM_MAX_STAGES = 24;
+// Shift-grouped mainloop: k-blocks per ring stage.  One barrier round trip (wait / expect_tx / TMA issue on one side, wait /
+// MMAs / commit on the other) costs ~550 clk whatever the tile; with two 64-wide k-blocks per stage it is paid per 128 K.
+constexpr int KPB = 2;
 // The operand tiles are written by TMA and read by tcgen05.mma, both in the async proxy and ordered by the mbarrier's
 // complete_tx; no tcgen05.fence is needed between the full-barrier wait and the MMAs (the fence after the acc_empty
 // wait, which orders the epilogue's tcgen05.ld before the overwriting MMA, stays).
@@ -374,9 +377,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stages = p.stages;
     const bool grouped = p.grouped != 0;
-    uint8_t* smem_w = smem + (size_t)p.sp * PB;                       // grouped mode: weight ring after the activation ring
+    constexpr int PB2 = KPB * PB, WB2 = KPB * B_STAGE_BYTES;           // grouped mode: KPB k-blocks per ring stage
+    uint8_t* smem_w = smem + (size_t)p.sp * PB2;                      // grouped mode: weight ring after the activation ring
     uint64_t* bars = reinterpret_cast<uint64_t*>(
-        grouped ? smem_w + (size_t)p.sw * B_STAGE_BYTES : smem + (size_t)stages * STAGE_BYTES);
+        grouped ? smem_w + (size_t)p.sw * WB2 : smem + (size_t)stages * STAGE_BYTES);
     uint64_t* full_bar = bars;                       // [stages]   TMA (both CTAs) -> MMA (leader)
     uint64_t* empty_bar = bars + MAX_STAGES;         // [stages]   MMA -> TMA (each CTA its own)
     uint64_t* acc_full = bars + 2 * MAX_STAGES;      // [2]        MMA -> epilogue (each CTA its own)
@@ -429,17 +433,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
                 for (int g = 0; g < p.ngrp; ++g) {
                     const GemmKParams::Grp gr = p.grp[g];
                     const CUtensorMap* tma = gr.src ? &p.tm_a1 : &p.tm_a0;
-                    for (int kb = 0; kb < gr.kblocks; ++kb) {
+                    for (int kb = 0; kb < gr.kblocks; kb += KPB) {
+                        const int nk = min(KPB, gr.kblocks - kb);          // k-blocks in this stage (the last may be short)
                         mbar_wait(&empty_bar[ps], pph ^ 1u);
                         if (elect_one()) {
+                            uint8_t* sa = smem + (size_t)ps * PB2;
+                            const int32_t arow = (int32_t)(m0 + gr.row_shift);
                             if (CG == 1) {
-                                mbar_arrive_expect_tx(&full_bar[ps], PB);
-                                tma_load_2d(smem + (size_t)ps * PB, tma, &full_bar[ps], gr.a_col0 + kb * BLOCK_K,
-                                            (int32_t)(m0 + gr.row_shift));
+                                mbar_arrive_expect_tx(&full_bar[ps], nk * PB);
+                                for (int j = 0; j < nk; ++j)
+                                    tma_load_2d(sa + j * PB, tma, &full_bar[ps], gr.a_col0 + (kb + j) * BLOCK_K, arow);
                             } else {        // both CTAs' tiles complete on the LEADER's barrier
-                                if (leader) mbar_arrive_expect_tx(&full_bar[ps], 2 * PB);
-                                tma_load_2d_pair(smem + (size_t)ps * PB, tma, mapa_u32(&full_bar[ps], 0),
-                                                 gr.a_col0 + kb * BLOCK_K, (int32_t)(m0 + gr.row_shift));
+                                if (leader) mbar_arrive_expect_tx(&full_bar[ps], 2 * nk * PB);
+                                const uint32_t bar = mapa_u32(&full_bar[ps], 0);
+                                for (int j = 0; j < nk; ++j)
+                                    tma_load_2d_pair(sa + j * PB, tma, bar, gr.a_col0 + (kb + j) * BLOCK_K, arow);
                             }
                         }
                         __syncwarp();
@@ -448,14 +456,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
                             const int wb = p.sp + ws;
                             mbar_wait(&empty_bar[wb], wph ^ 1u);
                             if (elect_one()) {
+                                uint8_t* sb = smem_w + (size_t)ws * WB2;
                                 const int kcol = (gr.kb0 + sub * gr.kblocks + kb) * BLOCK_K;
                                 if (CG == 1) {
-                                    mbar_arrive_expect_tx(&full_bar[wb], B_STAGE_BYTES);
-                                    tma_load_2d(smem_w + (size_t)ws * B_STAGE_BYTES, &p.tm_b, &full_bar[wb], kcol, n0);
+                                    mbar_arrive_expect_tx(&full_bar[wb], nk * B_STAGE_BYTES);
+                                    for (int j = 0; j < nk; ++j)
+                                        tma_load_2d(sb + j * B_STAGE_BYTES, &p.tm_b, &full_bar[wb], kcol + j * BLOCK_K, n0);
                                 } else {
-                                    if (leader) mbar_arrive_expect_tx(&full_bar[wb], 2 * B_STAGE_BYTES);
-                                    tma_load_2d_pair(smem_w + (size_t)ws * B_STAGE_BYTES, &p.tm_b,
-                                                     mapa_u32(&full_bar[wb], 0), kcol, n0);
+                                    if (leader) mbar_arrive_expect_tx(&full_bar[wb], 2 * nk * B_STAGE_BYTES);
+                                    const uint32_t bar = mapa_u32(&full_bar[wb], 0);
+                                    for (int j = 0; j < nk; ++j)
+                                        tma_load_2d_pair(sb + j * B_STAGE_BYTES, &p.tm_b, bar, kcol + j * BLOCK_K, n0);
                                 }
                             }
                             __syncwarp();
@@ -519,22 +530,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
                 uint32_t accum = 0;
                 for (int g = 0; g < p.ngrp; ++g) {
                     const int nsub = p.grp[g].nsub, nkb = p.grp[g].kblocks;
-                    for (int kb = 0; kb < nkb; ++kb) {
+                    for (int kb = 0; kb < nkb; kb += KPB) {
+                        const int nk = min(KPB, nkb - kb);
                         mbar_wait(&full_bar[ps], pph);
-                        const uint32_t sa = smem_u32(smem + (size_t)ps * PB);
+                        const uint32_t sa = smem_u32(smem + (size_t)ps * PB2);
                         for (int sub = 0; sub < nsub; ++sub) {
                             const int wb = p.sp + ws;
                             mbar_wait(&full_bar[wb], wph);
                             MAINLOOP_FENCE();
-                            const uint64_t da = make_smem_desc_sw128(sa + sub * 128);      // tap `sub`: one row further
-                            const uint64_t db = make_smem_desc_sw128(smem_u32(smem_w + (size_t)ws * B_STAGE_BYTES));
+                            const uint32_t sb = smem_u32(smem_w + (size_t)ws * WB2);
                             if (elect_one()) {
+                                for (int j = 0; j < nk; ++j) {
+                                    const uint64_t da = make_smem_desc_sw128(sa + j * PB + sub * 128);  // tap `sub`: one row further
+                                    const uint64_t db = make_smem_desc_sw128(sb + j * B_STAGE_BYTES);
 #pragma unroll
-                                for (int k = 0; k < BLOCK_K / 16; ++k) {
-                                    if (CG == 1)
-                                        tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, accum | (uint32_t)k);
-                                    else
-                                        tc_mma_f16_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, accum | (uint32_t)k);
+                                    for (int k = 0; k < BLOCK_K / 16; ++k) {
+                                        if (CG == 1)
+                                            tc_mma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, accum | (uint32_t)(j | k));
+                                        else
+                                            tc_mma_f16_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, accum | (uint32_t)(j | k));
+                                    }
                                 }
                                 if (CG == 1) tc_commit(&empty_bar[wb]); else tc_commit_pair(&empty_bar[wb]);
                             }
@@ -1160,7 +1175,7 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
     op->smem_bytes = 1024 + stages * stage_bytes + 512;
     const int a_box_rows = op->grouped ? BLOCK_M + 8 : BLOCK_M;
     if (op->grouped) {
-        const int pb = (BLOCK_M + 8) * BLOCK_K * 2, wb = (bn / cg) * BLOCK_K * 2;
+        const int pb = KPB * (BLOCK_M + 8) * BLOCK_K * 2, wb = KPB * (bn / cg) * BLOCK_K * 2;   // KPB k-blocks per stage
         // narrow tiles are bound by the activation stream: give it the deeper ring.  The producer issues the loads in
         // program order, so the weight ring must hold the weights of every activation stage in flight (3 taps each)
         // or it, not the activation ring, sets the prefetch distance: a Cout = 3 conv (BN = 32, 36 clk per MMA) was
@@ -1170,6 +1185,11 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
         if (op->sp < 3) op->sp = 3;
         if (op->sp > sp_max) op->sp = sp_max;
         op->sw = (SMEM_BUDGET - 1024 - 512 - op->sp * pb) / wb;
+        while (op->sw < 2 && op->sp > 2) {          // widest tiles in one CTA: trade an activation stage for a weight stage
+            --op->sp;
+            op->sw = (SMEM_BUDGET - 1024 - 512 - op->sp * pb) / wb;
+        }
+        SMTL_CHECK_ARG(op->sw >= 1, "gemm_plan: no room for a weight stage (block_n %d)", bn);
         if (op->sw > 3 * op->sp) op->sw = 3 * op->sp;
         if (op->sw > GEMM_MAX_STAGES - op->sp) op->sw = GEMM_MAX_STAGES - op->sp;
         op->smem_bytes = 1024 + op->sp * pb + op->sw * wb + 512;
