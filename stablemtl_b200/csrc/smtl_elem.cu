@@ -325,67 +325,101 @@ __global__ void gn_finalize_kernel(const float* __restrict__ st, int replicas, i
 }
 
 // ============================================================================================= LayerNorm
-// one warp per row; lane holds up to 10 float4 (C <= 1280).
-template <bool IN_BF16>
+// A warp normalises R rows at once; a lane holds NV float4 of each (C <= 128 NV).  All R * NV loads are issued before
+// the first reduction: with one row per warp (and registers sized for C = 1280 whatever C was) the kernel sat at 45 % of
+// the copy peak -- too few bytes in flight per SM.
+template <bool IN_BF16, int NV, int R>
 __global__ void ln_kernel(const void* __restrict__ xv, int c, int ldx, int64_t rows, float eps, int64_t rows_per_group,
                           const float* __restrict__ gamma0, const float* __restrict__ beta0,
                           uint16_t* __restrict__ out0, const float* __restrict__ gamma1,
                           const float* __restrict__ beta1, uint16_t* __restrict__ out1, int ldo, int fmt) {
-    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= rows) return;
+    const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
+    if (row0 >= rows) return;
     const int lane = threadIdx.x & 31;
     const int nv = c >> 2;
-    float4 v[10];
-    float s = 0.f;
+    float4 v[R][NV];
+    float s[R];
 #pragma unroll
-    for (int i = 0; i < 10; ++i) {
-        const int j = lane + 32 * i;
-        if (j < nv) {
-            if (IN_BF16) {
-                const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(xv) +
-                                                                     row * ldx + 4 * j));
-                const float2 a = unpack16x2(u.x, fmt), b = unpack16x2(u.y, fmt);
-                v[i] = make_float4(a.x, a.y, b.x, b.y);
-            } else {
-                v[i] = ldg4(reinterpret_cast<const float*>(xv) + row * ldx + 4 * j);
-            }
-            s += v[i].x + v[i].y + v[i].z + v[i].w;
-        }
-    }
-    const float mean = warp_sum(s) / (float)c;
-    float q = 0.f;
+    for (int r = 0; r < R; ++r) {
+        s[r] = 0.f;
+        const int64_t row = row0 + r;
 #pragma unroll
-    for (int i = 0; i < 10; ++i) {
-        const int j = lane + 32 * i;
-        if (j < nv) {
-            const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
-            q += a * a + b * b + cc * cc + d * d;
-        }
-    }
-    const float rstd = rsqrtf(warp_sum(q) / (float)c + eps);
-    const int64_t grp = row / rows_per_group;
-#pragma unroll
-    for (int i = 0; i < 10; ++i) {
-        const int j = lane + 32 * i;
-        if (j < nv) {
-            const float n0 = (v[i].x - mean) * rstd, n1 = (v[i].y - mean) * rstd, n2 = (v[i].z - mean) * rstd,
-                        n3 = (v[i].w - mean) * rstd;
-            {
-                const float4 g = ldg4(gamma0 + grp * c + 4 * j), b = ldg4(beta0 + grp * c + 4 * j);
-                uint2 o;
-                o.x = pack16x2(n0 * g.x + b.x, n1 * g.y + b.y, fmt);
-                o.y = pack16x2(n2 * g.z + b.z, n3 * g.w + b.w, fmt);
-                *reinterpret_cast<uint2*>(out0 + row * ldo + 4 * j) = o;
-            }
-            if (out1) {
-                const float4 g = ldg4(gamma1 + grp * c + 4 * j), b = ldg4(beta1 + grp * c + 4 * j);
-                uint2 o;
-                o.x = pack16x2(n0 * g.x + b.x, n1 * g.y + b.y, fmt);
-                o.y = pack16x2(n2 * g.z + b.z, n3 * g.w + b.w, fmt);
-                *reinterpret_cast<uint2*>(out1 + row * ldo + 4 * j) = o;
+        for (int i = 0; i < NV; ++i) {
+            const int j = lane + 32 * i;
+            v[r][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < nv && row < rows) {
+                if (IN_BF16) {
+                    const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(xv) +
+                                                                         row * ldx + 4 * j));
+                    const float2 a = unpack16x2(u.x, fmt), b = unpack16x2(u.y, fmt);
+                    v[r][i] = make_float4(a.x, a.y, b.x, b.y);
+                } else {
+                    v[r][i] = ldg4(reinterpret_cast<const float*>(xv) + row * ldx + 4 * j);
+                }
             }
         }
     }
+    float mean[R], rstd[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) s[r] += v[r][i].x + v[r][i].y + v[r][i].z + v[r][i].w;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) mean[r] = warp_sum(s[r]) / (float)c;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            if (lane + 32 * i < nv) {
+                const float a = v[r][i].x - mean[r], b = v[r][i].y - mean[r], cc = v[r][i].z - mean[r],
+                            d = v[r][i].w - mean[r];
+                q += a * a + b * b + cc * cc + d * d;
+            }
+        }
+        s[r] = q;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) rstd[r] = rsqrtf(warp_sum(s[r]) / (float)c + eps);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int64_t row = row0 + r;
+        if (row >= rows) break;
+        const int64_t grp = row / rows_per_group;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int j = lane + 32 * i;
+            if (j < nv) {
+                const float n0 = (v[r][i].x - mean[r]) * rstd[r], n1 = (v[r][i].y - mean[r]) * rstd[r],
+                            n2 = (v[r][i].z - mean[r]) * rstd[r], n3 = (v[r][i].w - mean[r]) * rstd[r];
+                {
+                    const float4 g = ldg4(gamma0 + grp * c + 4 * j), b = ldg4(beta0 + grp * c + 4 * j);
+                    uint2 o;
+                    o.x = pack16x2(n0 * g.x + b.x, n1 * g.y + b.y, fmt);
+                    o.y = pack16x2(n2 * g.z + b.z, n3 * g.w + b.w, fmt);
+                    *reinterpret_cast<uint2*>(out0 + row * ldo + 4 * j) = o;
+                }
+                if (out1) {
+                    const float4 g = ldg4(gamma1 + grp * c + 4 * j), b = ldg4(beta1 + grp * c + 4 * j);
+                    uint2 o;
+                    o.x = pack16x2(n0 * g.x + b.x, n1 * g.y + b.y, fmt);
+                    o.y = pack16x2(n2 * g.z + b.z, n3 * g.w + b.w, fmt);
+                    *reinterpret_cast<uint2*>(out1 + row * ldo + 4 * j) = o;
+                }
+            }
+        }
+    }
+}
+
+template <bool IN_BF16, int NV, int R>
+static void launch_ln(const smtl_ln_args* a, cudaStream_t st) {
+    const int wpb = 8;
+    const int64_t rows_per_block = (int64_t)wpb * R;
+    const int64_t grid = (a->rows + rows_per_block - 1) / rows_per_block;
+    ln_kernel<IN_BF16, NV, R><<<(unsigned)grid, wpb * 32, 0, st>>>(a->x, a->c, a->ldx, a->rows, a->eps, a->rows_per_group,
+                                                                 a->gamma0, a->beta0, (uint16_t*)a->out0, a->gamma1,
+                                                                 a->beta1, (uint16_t*)a->out1, a->ldo, a->fmt16);
 }
 
 // ============================================================================================= layout producers
@@ -957,16 +991,15 @@ extern "C" int smtl_ln_run(const smtl_ln_args* a, void* stream) {
     SMTL_CHECK_ARG(a->rows > 0 && a->rows_per_group > 0, "ln: bad rows");
     SMTL_CHECK_ARG(!a->out1 || (a->gamma1 && a->beta1), "ln: out1 without affine");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const int wpb = 8;
-    const int64_t grid = (a->rows + wpb - 1) / wpb;
-    if (a->x_is_bf16)
-        ln_kernel<true><<<(unsigned)grid, wpb * 32, 0, st>>>(a->x, a->c, a->ldx, a->rows, a->eps, a->rows_per_group,
-                                                             a->gamma0, a->beta0, (uint16_t*)a->out0, a->gamma1,
-                                                             a->beta1, (uint16_t*)a->out1, a->ldo, a->fmt16);
-    else
-        ln_kernel<false><<<(unsigned)grid, wpb * 32, 0, st>>>(a->x, a->c, a->ldx, a->rows, a->eps, a->rows_per_group,
-                                                              a->gamma0, a->beta0, (uint16_t*)a->out0, a->gamma1,
-                                                              a->beta1, (uint16_t*)a->out1, a->ldo, a->fmt16);
+    if (a->x_is_bf16) {
+        if (a->c <= 384) launch_ln<true, 3, 4>(a, st);
+        else if (a->c <= 640) launch_ln<true, 5, 2>(a, st);
+        else launch_ln<true, 10, 1>(a, st);
+    } else {
+        if (a->c <= 384) launch_ln<false, 3, 4>(a, st);
+        else if (a->c <= 640) launch_ln<false, 5, 2>(a, st);
+        else launch_ln<false, 10, 1>(a, st);
+    }
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;
 }
