@@ -241,10 +241,10 @@ def run_reference(args):
               f"image time = 2*enc + 7*unet + 7*dec = {per_image:.1f} s (enc {acc['enc']:.2f} s, unet {acc['unet']:.2f} s, "
               f"dec {acc['dec']:.2f} s)")
     line = {
-        "impl": "reference", "metric": "images/sec (all-task dense maps) at 480x640", "value": value, "unit": "images/s",
+        "impl": "reference", "metric": f"images/sec (all-task dense maps) at {H}x{W}", "value": value, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": warm, "ms_per_step": wall / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "StableMTL-S single-stream, all 7 task maps per image, 480x640, random-init SD-2 UNet+VAE, "
+        "config": {"workload": f"StableMTL-S single-stream, all 7 task maps per image, {H}x{W}, random-init SD-2 UNet+VAE, "
                                "CPU fp32 (oracle port of the reference algorithm)"},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -402,7 +402,7 @@ def main():
                                for k, v in sorted(by_name.items(), key=lambda kv: -kv[1][0])}}, f, indent=1)
 
     line = {
-        "metric": "images/sec (all-task dense maps) at 480x640", "value": value, "unit": "images/s",
+        "metric": f"images/sec (all-task dense maps) at {H}x{W}", "value": value, "unit": "images/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": f"{args.precision} operands, fp32 accumulate (tcgen05 kind::f16)", "data": "synthetic",

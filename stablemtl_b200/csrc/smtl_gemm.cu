@@ -77,6 +77,7 @@ struct alignas(64) GemmKParams {
     int32_t ngrp;
     int32_t sp, sw;       // stages of the activation / weight rings
     struct Grp { int32_t row_shift, nsub, kblocks, src, a_col0, kb0; } grp[SMTL_MAX_SEG];
+    FastDiv fd_img, fd_row;   // row maps: rows per image (h*w or (h+2)*(w+2)) and per image row (w or w+2)
 };
 
 __device__ __forceinline__ void st_global_v4_f32(float* p, float a, float b, float c, float d) {
@@ -112,24 +113,30 @@ __device__ __forceinline__ float warp_transpose_sum(float (&s)[32], int lane) {
 
 // GEMM row -> output row for every SMTL_ROWMAP_* (see the header).  `halo` = a padded GEMM row that is not an interior
 // pixel (PAD_KEEP stores zeros there; everyone else stores nothing).
-__device__ __forceinline__ void map_row(const GemmKParams& p, int64_t grow, bool& ok, int64_t& orow, bool& halo) {
+// (rows fit in 31 bits -- checked by the plan -- and the two divisors are per-launch constants: multiply-shift division
+// instead of 64-bit integer division, which was half of the swapped kernel's epilogue instructions)
+__device__ __forceinline__ void map_row(const GemmKParams& p, int64_t grow, bool& ok, int64_t& orow, bool& halo, int& img_out) {
     ok = grow < p.m;
     orow = grow;
     halo = false;
+    img_out = -1;                                            // identity map: the caller divides by stats_rpi itself
     if (p.rowmap == SMTL_ROWMAP_IDENTITY) return;
+    const uint32_t g32 = (uint32_t)grow;
     if (p.rowmap == SMTL_ROWMAP_TO_PAD) {                    // compact pixel -> padded index
-        const int hw = p.img_h * p.img_w;
-        const int64_t img = grow / hw;
-        const int rem = (int)(grow - img * hw);
-        const int y = rem / p.img_w, x = rem - y * p.img_w;
+        const uint32_t hw = (uint32_t)(p.img_h * p.img_w);
+        const int64_t img = fastdiv(g32, p.fd_img);
+        const uint32_t rem = g32 - (uint32_t)img * hw;
+        const int y = (int)fastdiv(rem, p.fd_row), x = (int)rem - y * p.img_w;
         orow = (img * (p.img_h + 2) + y + 1) * (int64_t)(p.img_w + 2) + x + 1;
+        img_out = (int)img;
         return;
     }
     const int wp = p.img_w + 2;
-    const int plane = (p.img_h + 2) * wp;
-    const int64_t img = grow / plane;
-    const int rem = (int)(grow - img * plane);
-    const int yp = rem / wp, xp = rem - yp * wp;
+    const uint32_t plane = (uint32_t)((p.img_h + 2) * wp);
+    const int64_t img = fastdiv(g32, p.fd_img);
+    const uint32_t rem = g32 - (uint32_t)img * plane;
+    const int yp = (int)fastdiv(rem, p.fd_row), xp = (int)rem - yp * wp;
+    img_out = (int)img;
     const bool interior = yp >= 1 && yp <= p.img_h && xp >= 1 && xp <= p.img_w;
     halo = ok && !interior;
     ok = ok && interior;
@@ -161,7 +168,8 @@ __device__ __forceinline__ void epilogue_prepare(const GemmKParams& p, int64_t g
     const bool geglu = (p.act == SMTL_ACT_GEGLU);
     const int out_bn = geglu ? BN / 2 : BN;
     const int n0 = tn * BN;
-    map_row(p, grow, e.row_ok, e.orow, e.halo);
+    int map_img;
+    map_row(p, grow, e.row_ok, e.orow, e.halo, map_img);
     e.halo = e.halo && (p.rowmap == SMTL_ROWMAP_PAD_KEEP);
     e.row_bias = (p.bias && p.bias_per_row && grow < p.m) ? __ldg(p.bias + grow) : 0.0f;
 #pragma unroll
@@ -186,7 +194,7 @@ __device__ __forceinline__ void epilogue_prepare(const GemmKParams& p, int64_t g
     e.img_lo = 1;
     e.img_hi = 0;
     if (p.stats) {
-        e.img = e.row_ok ? (int)(e.orow / p.stats_rpi) : -1;
+        e.img = !e.row_ok ? -1 : (map_img >= 0 ? map_img : (int)(e.orow / p.stats_rpi));
         int lo = e.row_ok ? e.img : 0x7fffffff, hi = e.img;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -858,13 +866,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
                 const int64_t grow = pix0 + c0 + lane;
                 bool ok, halo;
                 int64_t orow;
-                map_row(p, grow, ok, orow, halo);
+                int map_img;
+                map_row(p, grow, ok, orow, halo, map_img);
                 halo = halo && (p.rowmap == SMTL_ROWMAP_PAD_KEEP);
                 const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
                 const uint32_t halomask = __ballot_sync(0xffffffffu, halo);
                 if ((okmask | halomask) == 0 && pix0 + c0 >= p.m) break;             // warp-uniform: past the end
                 const int orow32 = (int)orow;
-                const int img_l = (p.stats && ok) ? (int)(orow / p.stats_rpi) : -1;
+                const int img_l = !(p.stats && ok) ? -1 : (map_img >= 0 ? map_img : (int)(orow / p.stats_rpi));
                 uint32_t rr[32];
                 float v[32];
                 tmem_ld_32x32(taddr + c0, rr);
@@ -1265,6 +1274,15 @@ extern "C" int smtl_gemm_run(const smtl_gemm_op* op, void* stream) {
     kp.img_h = g.img_h;
     kp.img_w = g.img_w;
     kp.fmt = g.fmt16;
+    kp.fd_img = make_fastdiv(1);
+    kp.fd_row = make_fastdiv(1);
+    if (g.rowmap == SMTL_ROWMAP_TO_PAD) {
+        kp.fd_img = make_fastdiv((uint32_t)(g.img_h * g.img_w));
+        kp.fd_row = make_fastdiv((uint32_t)g.img_w);
+    } else if (g.rowmap != SMTL_ROWMAP_IDENTITY) {
+        kp.fd_img = make_fastdiv((uint32_t)((g.img_h + 2) * (g.img_w + 2)));
+        kp.fd_row = make_fastdiv((uint32_t)(g.img_w + 2));
+    }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (op->cta_group == 3) {
         static bool attr_set = false;
