@@ -660,7 +660,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
 constexpr int TBN = 256;                            // pixels per tile
 constexpr int T_STAGE_BYTES = A_STAGE_BYTES + TBN * BLOCK_K * 2;   // weights 16 KB + pixels 32 KB
 constexpr int T_PB = 34 * 1024;                     // grouped mode: 256 + 8 pixel rows x 128 B, rounded up to the 1 KB swizzle repeat
-constexpr int T_STG_WARP = 32 * 80;                 // [32 pixels][32 channels] 16-bit, pitch 64 + 16 bytes
+// [32 pixels][32 channels] 16-bit.  Pitch 64 B, no padding: a 2-byte column write touches one row (64 contiguous bytes)
+// and a quarter-warp of 16-byte accesses covers two consecutive rows = all 32 banks once (a padded pitch of 80 B made
+// those two rows overlap in 4 banks: 20 M conflicts per launch in the profile).
+constexpr int T_STG_PITCH = 64;
+constexpr int T_STG_WARP = 32 * T_STG_PITCH;
 constexpr int T_STAGING = EPI_WARPS * T_STG_WARP;
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid_constant__ GemmKParams p) {
@@ -902,22 +906,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
                 if (p.res1) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        *reinterpret_cast<uint4*>(stg + (8 * i + (lane >> 2)) * 80 + piece * 16) = rq[i];
+                        *reinterpret_cast<uint4*>(stg + (8 * i + (lane >> 2)) * T_STG_PITCH + piece * 16) = rq[i];
                     __syncwarp();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const uint32_t h = *reinterpret_cast<const uint16_t*>(stg + j * 80 + lane * 2);
+                        const uint32_t h = *reinterpret_cast<const uint16_t*>(stg + j * T_STG_PITCH + lane * 2);
                         v[j] += unpack16x2(h, p.fmt).x;
                     }
                     __syncwarp();
                 }
                 // channel-major -> pixel-major through the staging tile, then 64-byte row pieces
 #pragma unroll
-                for (int j = 0; j < 32; ++j) *reinterpret_cast<uint16_t*>(stg + j * 80 + lane * 2) = to16(v[j], p.fmt);
+                for (int j = 0; j < 32; ++j) *reinterpret_cast<uint16_t*>(stg + j * T_STG_PITCH + lane * 2) = to16(v[j], p.fmt);
                 __syncwarp();
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const uint4 q = *reinterpret_cast<const uint4*>(stg + (8 * i + (lane >> 2)) * 80 + piece * 16);
+                    const uint4 q = *reinterpret_cast<const uint4*>(stg + (8 * i + (lane >> 2)) * T_STG_PITCH + piece * 16);
                     if (((ok_i >> i) & 1u) && piece_ok)
                         *reinterpret_cast<uint4*>(p.out_bf16 + (int64_t)orow_i[i] * p.ldc + cpiece) = q;
                     else if (((halo_i >> i) & 1u) && piece_ok)       // PAD_KEEP: zero halo
