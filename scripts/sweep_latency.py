@@ -18,6 +18,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from stablemtl_b200 import synth  # noqa: E402
 from stablemtl_b200.pipeline import StableMTLEngine  # noqa: E402
+from stablemtl_b200.shard import choose_sharding  # noqa: E402
 
 
 def main():
@@ -46,7 +47,7 @@ def main():
         return engines[stream]
 
     for total in [int(b) for b in args.batches.split(",")]:
-        stream = total < world and world > 1
+        stream = choose_sharding(total, world, True) == "streams"
         per_rank = total if stream else max(1, total // world)
         eng = engine(stream)
         g = torch.Generator().manual_seed(100 + (0 if stream else rank))

@@ -67,6 +67,20 @@ def gather_maps(local: Dict[str, torch.Tensor], n_images: int, group=None, dst: 
     return out if (dst is None or dst == rank) else None
 
 
+def choose_sharding(n_images: int, world: int, multi_stream: bool, n_tasks: int = 7, max_slots: int = 8) -> str:
+    """"images" | "streams": how a global batch of n_images is spread over `world` ranks.
+
+    Images whenever every rank gets at least one (no data-path collective); for smaller batches of the multi-stream
+    model the task streams are sharded instead (stream_shard.py: every rank works on all the images, one exchange of
+    the child features per pass) -- measured on 8 GPUs at 384x1248: 1 image 35 ms, 4 images 88 ms sharded by stream
+    against 98 ms for a batch of 8 sharded by image (profiles/r01c_sweep_multi_384x1248_8gpu.jsonl).  Stream sharding
+    needs world * ceil(n_tasks / world) exchange slots <= max_slots (SMTL_MAX_TASKS)."""
+    if world <= 1 or n_images >= world or not multi_stream:
+        return "images"
+    slots = world * ((n_tasks + world - 1) // world)
+    return "streams" if slots <= max_slots else "images"
+
+
 class ShardedEngine:
     """Runs `engine.predict` on this rank's slice of a global batch and (optionally) gathers the maps.
 

@@ -87,3 +87,13 @@ def test_shard_ranges_partition_the_batch(n, world):
     assert cover == list(range(n))
     with pytest.raises(ValueError):
         shard.shard_range(n, world, world)
+
+
+def test_choose_sharding():
+    from stablemtl_b200.shard import choose_sharding
+    assert choose_sharding(64, 8, True) == "images" and choose_sharding(8, 8, True) == "images"
+    assert choose_sharding(1, 8, True) == "streams" and choose_sharding(4, 8, True) == "streams"
+    assert choose_sharding(1, 8, False) == "images"            # single-stream: nothing to exchange
+    assert choose_sharding(1, 1, True) == "images"
+    assert choose_sharding(1, 2, True) == "streams" and choose_sharding(3, 4, True) == "streams"
+    assert choose_sharding(1, 3, True) == "images"             # 3 ranks x 3 slots = 9 > SMTL_MAX_TASKS
