@@ -1197,6 +1197,13 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
         op->sp = (SMEM_BUDGET - 1024 - 512 - 6 * wb) / pb;
         if (op->sp < 3) op->sp = 3;
         if (op->sp > sp_max) op->sp = sp_max;
+        // wide tiles: the weight ring is the critical stream (3 weight stages per activation stage), so it gets the
+        // shared memory -- 2 activation stages + 4 weight stages beat 3 + 3 by 1-2 %, 4 + 2 loses 6 % (bn = 256 pairs)
+        if (bn >= 128) op->sp = 2;
+        if (const char* envsp = getenv("SMTL_GEMM_SP")) {            // experiment knob: activation-ring depth
+            const int v = atoi(envsp);
+            if (v >= 2 && v <= sp_max) op->sp = v;
+        }
         op->sw = (SMEM_BUDGET - 1024 - 512 - op->sp * pb) / wb;
         while (op->sw < 2 && op->sp > 2) {          // widest tiles in one CTA: trade an activation stage for a weight stage
             --op->sp;
