@@ -97,3 +97,17 @@ def test_choose_sharding():
     assert choose_sharding(1, 1, True) == "images"
     assert choose_sharding(1, 2, True) == "streams" and choose_sharding(3, 4, True) == "streams"
     assert choose_sharding(1, 3, True) == "images"             # 3 ranks x 3 slots = 9 > SMTL_MAX_TASKS
+
+
+def test_tap_shapes_follow_the_reference_layer_map():
+    """the 16 attn1 taps in execution order (src/util/model.py:67-84: idx 0-1:320, 2-3:640, 4-5:1280, 6 (mid):1280,
+    7-9:1280, 10-12:640, 13-15:320) with the conv-s2-p1 level sizes of SURVEY 8 (480x640 -> 4800/1200/300/80 tokens)"""
+    from stablemtl_b200 import synth
+    from stablemtl_b200.engine import UNetPlan, down_size
+    shapes = UNetPlan.tap_shapes(synth.SD2_UNET, 60, 80)
+    want = [(4800, 320)] * 2 + [(1200, 640)] * 2 + [(300, 1280)] * 2 + [(80, 1280)] + [(300, 1280)] * 3 + \
+        [(1200, 640)] * 3 + [(4800, 320)] * 3
+    assert shapes == want and len(shapes) == 16
+    # odd sizes: 384x1248 -> 48x156 / 24x78 / 12x39 / 6x20
+    s2 = UNetPlan.tap_shapes(synth.SD2_UNET, 48, 156)
+    assert [n for n, _ in s2[:7]] == [7488, 7488, 1872, 1872, 468, 468, 120] and down_size(39) == 20
