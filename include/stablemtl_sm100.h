@@ -99,11 +99,14 @@ typedef struct smtl_gemm_args {
     int32_t fmt16;      /* SMTL_FMT_* of a0/a1/b/out_bf16/aux_bf16 */
     int32_t res_fmt16;  /* 0: res1/res2 are fp32; 1: they are 16-bit (fmt16), same leading dim ldres */
     /* Fused GroupNorm statistics of the OUTPUT (the input of the next GroupNorm, src/model/resnet.py:177,188):
-     * stats is fp32 [stats_replicas, stats_images, n_out, 2] holding per-(image, channel) sum and sum of squares
-     * of the final value (after residual adds), accumulated with atomic adds -- the caller zeroes it first
-     * (smtl_memset_run).  image = output row / stats_rows_per_image.  NULL = off. */
+     * stats is int64 [stats_replicas, stats_images, n_out, 4]: per-(image, channel) sum and sum of squares of the
+     * final value (after residual adds) as FIXED-POINT cells (sum_lo, sum_hi, sq_lo, sq_hi; value = lo * 2^-35 +
+     * hi * 2^-8), accumulated with integer atomic adds -- exact and order-independent, so the statistics and
+     * everything downstream are bit-reproducible.  The caller zeroes it first (smtl_memset_run).
+     * image = output row / stats_rows_per_image; m must be stats_images whole images (M tiles restart at every
+     * image, which makes an image's statistics independent of its position in the batch).  NULL = off. */
     int32_t stats_replicas;         /* >= 1 copies to spread atomic contention; consumers sum them */
-    float* stats;
+    int64_t* stats;
     int32_t stats_rows_per_image;
     int32_t stats_images;
     int32_t cta_group;  /* 0 = auto; 1 = one CTA per 128-row tile; 2 = CTA pair per 256-row tile (tcgen05 cta_group::2) */
@@ -130,6 +133,9 @@ typedef struct smtl_gemm_op {
     int32_t ngrp, sp, sw;
     struct { int32_t row_shift, nsub, kblocks, src, a_col0, kb0; } grp[SMTL_MAX_SEG];
     uint64_t tmap_x8[2][16];
+    int64_t tile_rpi;       /* image-aligned M tiling: GEMM rows per image (0 = off), M tiles per image */
+    int32_t tiles_per_img;
+    int32_t pad_;
 } smtl_gemm_op;
 
 int smtl_gemm_plan(const smtl_gemm_args* args, smtl_gemm_op* op);
@@ -217,31 +223,10 @@ typedef struct smtl_taskattn_args {
 int smtl_taskattn_run(const smtl_taskattn_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ normalisation
- * GroupNorm statistics + apply (+SiLU) over a (virtually concatenated) fp32 compact map, emitting the bf16
- * operand of the next GEMM/conv.  Replaces torch GroupNorm + F.silu + torch.cat at
+ * GroupNorm (+SiLU) emitting the 16-bit operand of the next GEMM/conv.  Replaces torch GroupNorm + F.silu + torch.cat at
  * src/model/resnet.py:177-178,188,194, src/model/attention.py:183, src/model/unet.py:438-439,
  * src/model/unet_blocks.py:509,597 and the GroupNorms of diffusers' VAE blocks.
  */
-typedef struct smtl_gn_args {
-    const float* x0;
-    const float* x1;        /* second source of a channel concat, or NULL */
-    int32_t c0, c1;
-    int32_t batch, h, w;
-    int32_t groups;
-    float eps;
-    float* partial;         /* scratch fp32 [batch, nchunk, groups, 2] */
-    int32_t nchunk;
-    const float* gamma;
-    const float* beta;
-    int32_t silu;
-    int32_t pad_out;        /* 1: padded layout with zero halo, 0: compact */
-    void* out_bf16;
-    void* raw_bf16;         /* optional un-normalised bf16 copy, same layout (1x1 shortcut operand) */
-    int32_t fmt16;
-    int32_t pad_;
-} smtl_gn_args;
-int smtl_gn_run(const smtl_gn_args* a, void* stream);
-
 /* GroupNorm apply (+SiLU) from PRODUCER-SIDE statistics: the GEMM/conv that wrote x0 (and x1 of a channel
  * concat, src/model/unet_blocks.py:509,597) also accumulated per-(image, channel) sum / sum of squares
  * (smtl_gemm_args.stats), so this is a single streaming pass: 16-bit (or fp32) compact map in, 16-bit operand of
@@ -255,12 +240,12 @@ typedef struct smtl_gnapply_args {
     int32_t stats_replicas;
     int32_t x_padded;       /* 1: x0/x1 are in the padded layout [batch, h+2, w+2, c] (halo ignored) */
     int32_t pad2_;
-    const float* stats0;    /* fp32 [stats_replicas, batch, c0, 2] */
-    const float* stats1;    /* fp32 [stats_replicas, batch, c1, 2] or NULL */
+    const int64_t* stats0;  /* int64 fixed-point cells [stats_replicas, batch, c0, 4] (smtl_gemm_args.stats) */
+    const int64_t* stats1;  /* [stats_replicas, batch, c1, 4] or NULL */
     int32_t batch, h, w;
     int32_t groups;
     float eps;
-    int32_t silu;
+    int32_t silu;           /* 0: none; 1: x*sigmoid(x) with sigmoid from one tanh.approx (rel. 2^-11); 2: ex2+rcp (~2 ulp) */
     const float* gamma;
     const float* beta;
     int32_t pad_out;        /* 1: padded layout with zero halo, 0: compact */
@@ -273,7 +258,7 @@ int smtl_gnapply_run(const smtl_gnapply_args* a, void* stream);
 /* Per-(image, channel) scale / shift of a GroupNorm from the producer-side sums: ss[b, c] = (rstd * gamma, beta -
  * mean * rstd * gamma): what GroupNorm reduces to per image once the producer-side sums are known. */
 typedef struct smtl_gnfinalize_args {
-    const float* stats;     /* fp32 [stats_replicas, batch, c, 2] */
+    const int64_t* stats;   /* int64 fixed-point cells [stats_replicas, batch, c, 4] (smtl_gemm_args.stats) */
     int32_t stats_replicas, batch, c, groups;
     int64_t pixels;         /* interior pixels per image (h * w) */
     float eps;
@@ -437,7 +422,7 @@ int smtl_confusion_run(const smtl_confusion_args* a, void* stream);
  * into a CUDA graph by the caller). */
 enum {
     SMTL_OP_GEMM = 1, SMTL_OP_FATTN = 2, SMTL_OP_SOFTMAX = 3, SMTL_OP_XATTN = 4, SMTL_OP_TASKATTN = 5,
-    SMTL_OP_GN = 6, SMTL_OP_LN = 7, SMTL_OP_UPSAMPLE = 8, SMTL_OP_IM2COL = 9, SMTL_OP_RGBPREP = 10,
+    /* 6 retired (first-generation two-pass GroupNorm) */ SMTL_OP_LN = 7, SMTL_OP_UPSAMPLE = 8, SMTL_OP_IM2COL = 9, SMTL_OP_RGBPREP = 10,
     SMTL_OP_UNETIN = 11, SMTL_OP_TASKMAP = 12, SMTL_OP_CHANMIX = 13, SMTL_OP_GNAPPLY = 14, SMTL_OP_MEMSET = 15,
     SMTL_OP_GNFINALIZE = 16, SMTL_OP_LSQSUMS = 17, SMTL_OP_CONFUSION = 18
 };
@@ -447,7 +432,7 @@ typedef struct smtl_op_ref {
     const void* op;
 } smtl_op_ref;
 int smtl_run_plan(const smtl_op_ref* ops, int32_t n_ops, void* stream);
-/* number of kernel launches smtl_run_plan(ops) performs (a GN op is two kernels) */
+/* number of kernel launches smtl_run_plan(ops) performs (a MEMSET op is a driver memset: 0) */
 int smtl_plan_launches(const smtl_op_ref* ops, int32_t n_ops);
 
 /* ------------------------------------------------------------------------------------------------ misc */

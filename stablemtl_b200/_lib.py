@@ -18,7 +18,7 @@ ACT_NONE, ACT_GELU, ACT_GEGLU, ACT_SILU = 0, 1, 2, 3
  ROWMAP_UP2_PAD) = range(6)
 FMT_BF16, FMT_F16 = 0, 1
 MAP_MEAN1, MAP_RGB3, MAP_NORMAL, MAP_FLOW2, MAP_FLOW3, MAP_SEMANTIC = range(6)
-(OP_GEMM, OP_FATTN, OP_SOFTMAX, OP_XATTN, OP_TASKATTN, OP_GN, OP_LN, OP_UPSAMPLE, OP_IM2COL, OP_RGBPREP,
+(OP_GEMM, OP_FATTN, OP_SOFTMAX, OP_XATTN, OP_TASKATTN, _OP_RETIRED6, OP_LN, OP_UPSAMPLE, OP_IM2COL, OP_RGBPREP,
  OP_UNETIN, OP_TASKMAP, OP_CHANMIX, OP_GNAPPLY, OP_MEMSET, OP_GNFINALIZE, OP_LSQSUMS, OP_CONFUSION) = range(1, 19)
 
 vp = C.c_void_p
@@ -67,6 +67,7 @@ class GemmOp(C.Structure):
         ("ngrp", i32), ("sp", i32), ("sw", i32),
         ("grp", (i32 * 6) * MAX_SEG),
         ("tmap_x8", (C.c_uint64 * 16) * 2),
+        ("tile_rpi", i64), ("tiles_per_img", i32), ("pad_", i32),
     ]
 
 
@@ -104,17 +105,6 @@ class TaskAttnArgs(C.Structure):
         ("rows_per_group", i64),
         ("main_task", i32 * MAX_TASKS), ("src_task", i32 * MAX_TASKS),
         ("exclude_self", i32), ("scale", f32), ("fmt16", i32), ("pad_", i32),
-    ]
-
-
-class GnArgs(C.Structure):
-    _fields_ = [
-        ("x0", vp), ("x1", vp), ("c0", i32), ("c1", i32),
-        ("batch", i32), ("h", i32), ("w", i32), ("groups", i32), ("eps", f32),
-        ("partial", vp), ("nchunk", i32),
-        ("gamma", vp), ("beta", vp),
-        ("silu", i32), ("pad_out", i32),
-        ("out_bf16", vp), ("raw_bf16", vp), ("fmt16", i32), ("pad_", i32),
     ]
 
 
@@ -191,11 +181,11 @@ class OpRef(C.Structure):
 
 
 STRUCTS_IN_HEADER_ORDER = [GemmSeg, GemmArgs, GemmOp, FattnArgs, FattnOp, SoftmaxArgs, XattnArgs, TaskAttnArgs,
-                           GnArgs, GnApplyArgs, GnFinalizeArgs, MemsetArgs, LnArgs, UpsampleArgs, Im2colArgs, RgbprepArgs, UnetinArgs, ChanmixArgs, TaskmapArgs, LsqSumsArgs, ConfusionArgs, OpRef]
+                           GnApplyArgs, GnFinalizeArgs, MemsetArgs, LnArgs, UpsampleArgs, Im2colArgs, RgbprepArgs, UnetinArgs, ChanmixArgs, TaskmapArgs, LsqSumsArgs, ConfusionArgs, OpRef]
 
 EXPORTS = [
     "smtl_gemm_plan", "smtl_gemm_run", "smtl_fattn_plan", "smtl_fattn_run", "smtl_softmax_run", "smtl_xattn_run",
-    "smtl_taskattn_run", "smtl_gn_run", "smtl_gnapply_run", "smtl_gnfinalize_run", "smtl_memset_run", "smtl_ln_run", "smtl_upsample_run", "smtl_im2col_run", "smtl_rgbprep_run",
+    "smtl_taskattn_run", "smtl_gnapply_run", "smtl_gnfinalize_run", "smtl_memset_run", "smtl_ln_run", "smtl_upsample_run", "smtl_im2col_run", "smtl_rgbprep_run",
     "smtl_unetin_run", "smtl_chanmix_run", "smtl_taskmap_run", "smtl_lsqsums_run", "smtl_confusion_run", "smtl_run_plan", "smtl_plan_launches", "smtl_abi_version",
     "smtl_last_error", "smtl_struct_sizes",
 ]

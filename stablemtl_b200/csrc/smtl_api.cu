@@ -83,7 +83,7 @@ int smtl_struct_sizes(int32_t* out, int32_t cap) {
     const int32_t sizes[] = {
         (int32_t)sizeof(smtl_gemm_seg),     (int32_t)sizeof(smtl_gemm_args),    (int32_t)sizeof(smtl_gemm_op),
         (int32_t)sizeof(smtl_fattn_args),   (int32_t)sizeof(smtl_fattn_op),     (int32_t)sizeof(smtl_softmax_args),
-        (int32_t)sizeof(smtl_xattn_args),   (int32_t)sizeof(smtl_taskattn_args), (int32_t)sizeof(smtl_gn_args),
+        (int32_t)sizeof(smtl_xattn_args),   (int32_t)sizeof(smtl_taskattn_args),
         (int32_t)sizeof(smtl_gnapply_args), (int32_t)sizeof(smtl_gnfinalize_args), (int32_t)sizeof(smtl_memset_args),
         (int32_t)sizeof(smtl_ln_args),      (int32_t)sizeof(smtl_upsample_args), (int32_t)sizeof(smtl_im2col_args),
         (int32_t)sizeof(smtl_rgbprep_args), (int32_t)sizeof(smtl_unetin_args),  (int32_t)sizeof(smtl_chanmix_args),
@@ -96,8 +96,8 @@ int smtl_struct_sizes(int32_t* out, int32_t cap) {
 
 int smtl_plan_launches(const smtl_op_ref* ops, int32_t n_ops) {
     int n = 0;
-    for (int i = 0; i < n_ops; ++i)   // GN = stats + apply kernels; MEMSET is a driver memset, not one of ours
-        n += (ops[i].kind == SMTL_OP_GN) ? 2 : (ops[i].kind == SMTL_OP_MEMSET) ? 0 : 1;
+    for (int i = 0; i < n_ops; ++i)   // MEMSET is a driver memset, not one of our kernels
+        n += (ops[i].kind == SMTL_OP_MEMSET) ? 0 : 1;
     return n;
 }
 
@@ -111,7 +111,6 @@ int smtl_run_plan(const smtl_op_ref* ops, int32_t n_ops, void* stream) {
             case SMTL_OP_SOFTMAX: rc = smtl_softmax_run((const smtl_softmax_args*)p, stream); break;
             case SMTL_OP_XATTN: rc = smtl_xattn_run((const smtl_xattn_args*)p, stream); break;
             case SMTL_OP_TASKATTN: rc = smtl_taskattn_run((const smtl_taskattn_args*)p, stream); break;
-            case SMTL_OP_GN: rc = smtl_gn_run((const smtl_gn_args*)p, stream); break;
             case SMTL_OP_LN: rc = smtl_ln_run((const smtl_ln_args*)p, stream); break;
             case SMTL_OP_UPSAMPLE: rc = smtl_upsample_run((const smtl_upsample_args*)p, stream); break;
             case SMTL_OP_IM2COL: rc = smtl_im2col_run((const smtl_im2col_args*)p, stream); break;

@@ -283,6 +283,13 @@ __device__ __forceinline__ float silu_fast(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
     return x * fmaf(t, 0.5f, 0.5f);
 }
+// x * sigmoid(x) to ~2 ulp: ex2.approx + rcp.approx (two SFU ops)
+__device__ __forceinline__ float silu_exact(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return x * r;
+}
 // exact unsigned division by a runtime constant: q = (n * mul) >> 32 >> shr  (n < 2^31, d >= 1)
 struct FastDiv {
     uint32_t mul, shr, d;
@@ -333,6 +340,29 @@ __device__ __forceinline__ float2 unpack16x2(uint32_t u, int fmt) {
 }
 __device__ __forceinline__ uint16_t to16(float x, int fmt) {
     return static_cast<uint16_t>(pack16x2(x, 0.f, fmt) & 0xFFFFu);
+}
+
+// ----------------------------------------------------------------------------- deterministic channel statistics
+// A GroupNorm statistics cell is FOUR int64 fixed-point accumulators (sum_lo, sum_hi, sq_lo, sq_hi): a partial sum p goes,
+// exactly, into the fine accumulator (scale 2^35, |p| < 2^14) or the coarse one (scale 2^8).  Integer addition is
+// associative, so the atomics of the producing GEMM's CTAs give the same bits in whatever order they land (fp32
+// atomicAdd did not: run-to-run differences of ~1e-7 that the network amplified to the parity tolerance).
+constexpr float STATS_LO_LIMIT = 16384.0f;           // 2^14
+constexpr float STATS_LO_SCALE = 34359738368.0f;     // 2^35
+constexpr float STATS_HI_SCALE = 256.0f;             // 2^8
+__device__ __forceinline__ long long stats_fix(float p, bool& hi) {
+    hi = !(fabsf(p) < STATS_LO_LIMIT);
+    return __float2ll_rn(p * (hi ? STATS_HI_SCALE : STATS_LO_SCALE));
+}
+__device__ __forceinline__ void stats_atomic_add(unsigned long long* cell, float s, float q) {
+    bool hi;
+    long long v = stats_fix(s, hi);
+    atomicAdd(cell + (hi ? 1 : 0), (unsigned long long)v);
+    v = stats_fix(q, hi);
+    atomicAdd(cell + (hi ? 3 : 2), (unsigned long long)v);
+}
+__device__ __forceinline__ double stats_value(long long lo, long long hi) {
+    return (double)lo * (1.0 / 34359738368.0) + (double)hi * (1.0 / 256.0);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

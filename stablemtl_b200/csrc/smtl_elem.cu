@@ -34,54 +34,53 @@ __device__ __forceinline__ uint4 load8_as16(const void* base, int64_t idx, int i
 }
 
 // ============================================================================================= GroupNorm
-// stats: grid (nchunk, batch); block = (C/4) * rows_par threads; thread owns 4 fixed channels.
-__global__ void gn_stats_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int c0, int c1, int hw,
-                                int groups, int nchunk, float* __restrict__ partial) {
-    extern __shared__ float sm[];   // [2*groups]
-    const int C = c0 + c1;
-    const int cv = C >> 2;
-    const int rows_par = blockDim.x / cv;
-    const int cvec = threadIdx.x % cv;
-    const int rlane = threadIdx.x / cv;
-    const int b = blockIdx.y, chunk = blockIdx.x;
-    const int per = (hw + nchunk - 1) / nchunk;
-    const int p_begin = chunk * per;
-    const int p_end = min(hw, p_begin + per);
-    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) sm[i] = 0.f;
-    __syncthreads();
-    const int c = cvec * 4;
-    const float* src;
-    int ld, cc;
-    if (c < c0) { src = x0; ld = c0; cc = c; } else { src = x1; ld = c1; cc = c - c0; }
-    float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
-    if (rlane < rows_par) {
-        const float* base = src + ((int64_t)b * hw) * ld + cc;
-        for (int p = p_begin + rlane; p < p_end; p += rows_par) {
-            const float4 v = ldg4(base + (int64_t)p * ld);
-            s[0] += v.x; q[0] += v.x * v.x;
-            s[1] += v.y; q[1] += v.y * v.y;
-            s[2] += v.z; q[2] += v.z * v.z;
-            s[3] += v.w; q[3] += v.w * v.w;
-        }
-        const int cpg = C / groups;
+// Group mean / rstd of image `b` from the producers' int64 fixed-point cells (smtl_common.cuh): a warp per group sums
+// the cells of the group's channels (both sources of a virtual concat, every replica) as INTEGERS -- exact, so the
+// result does not depend on how the producer's atomics were ordered -- and converts once, in double.
+__device__ __forceinline__ void gn_group_stats(const long long* __restrict__ st0, const long long* __restrict__ st1,
+                                               int c0, int c1, int replicas, int batch, int b, int groups, double n,
+                                               float eps, float* gmean, float* grstd) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;   // whole warps only
+    const int cpg = (c0 + c1) / groups;
+    const int ncell = cpg * replicas;
+    if (warp < nwarps) {
+        for (int g = warp; g < groups; g += nwarps) {
+            long long a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+            for (int i = lane; i < ncell; i += 32) {
+                const int r = i / cpg, c = g * cpg + (i - r * cpg);
+                const long long* st = (c < c0) ? st0 + (((int64_t)r * batch + b) * c0 + c) * 4
+                                               : st1 + (((int64_t)r * batch + b) * c1 + (c - c0)) * 4;
+                const longlong2 u = __ldg(reinterpret_cast<const longlong2*>(st));
+                const longlong2 v = __ldg(reinterpret_cast<const longlong2*>(st + 2));
+                a0 += u.x; a1 += u.y; a2 += v.x; a3 += v.y;
+            }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int g = (c + i) / cpg;
-            atomicAdd(&sm[2 * g], s[i]);
-            atomicAdd(&sm[2 * g + 1], q[i]);
+            for (int o = 16; o > 0; o >>= 1) {
+                a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+                a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+                a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+            }
+            if (lane == 0) {
+                const double mean = stats_value(a0, a1) / n;
+                double var = stats_value(a2, a3) / n - mean * mean;
+                if (var < 0.0) var = 0.0;
+                gmean[g] = (float)mean;
+                grstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+            }
         }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x)
-        partial[((int64_t)(b * nchunk + chunk) * groups) * 2 + i] = sm[i];
 }
 
-// apply: grid (blocks_per_image, batch), 256 threads, thread handles 8 channels of one (padded) pixel per step.
-__global__ void gn_apply_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int c0, int c1, int h, int w,
-                                int groups, float eps, const float* __restrict__ partial, int nchunk,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu, int pad_out,
-                                uint16_t* __restrict__ out, uint16_t* __restrict__ raw, int fmt) {
-    extern __shared__ float sm[];   // scale[C], shift[C], mean[groups], rstd[groups]
+// GroupNorm apply from producer-side per-(image, channel) statistics (smtl_gemm_args.stats): one streaming pass.
+// grid (blocks_per_image, batch), 256 threads; each thread handles 8 channels of one (padded) pixel per step.
+template <bool x16>
+__global__ void __launch_bounds__(320, 3) gn_apply2_kernel(
+    const void* __restrict__ x0, const void* __restrict__ x1, int c0, int c1, const long long* __restrict__ st0,
+    const long long* __restrict__ st1, int replicas, int batch, int h, int w, int groups, float eps,
+    const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu, int pad_out,
+    uint16_t* __restrict__ out, uint16_t* __restrict__ raw, int fmt, FastDiv div_wp, int in_pad) {
+    extern __shared__ float sm[];   // scale[C], shift[C], gmean[groups], grstd[groups]
     const int C = c0 + c1;
     float* scale = sm;
     float* shift = sm + C;
@@ -90,112 +89,7 @@ __global__ void gn_apply_kernel(const float* __restrict__ x0, const float* __res
     const int b = blockIdx.y;
     const int hw = h * w;
     const int cpg = C / groups;
-    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-        double s = 0.0, q = 0.0;
-        for (int k = 0; k < nchunk; ++k) {
-            const float* pp = partial + ((int64_t)(b * nchunk + k) * groups + g) * 2;
-            s += (double)pp[0];
-            q += (double)pp[1];
-        }
-        const double n = (double)hw * cpg;
-        const double mean = s / n;
-        double var = q / n - mean * mean;
-        if (var < 0.0) var = 0.0;
-        gmean[g] = (float)mean;
-        grstd[g] = (float)(1.0 / sqrt(var + (double)eps));
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const int g = c / cpg;
-        const float sc = grstd[g] * gamma[c];
-        scale[c] = sc;
-        shift[c] = beta[c] - gmean[g] * sc;
-    }
-    __syncthreads();
-    const int cv8 = C >> 3;
-    const int hp = pad_out ? h + 2 : h, wp = pad_out ? w + 2 : w;
-    const int64_t total = (int64_t)hp * wp * cv8;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const int pix = (int)(idx / cv8);
-        const int c = (int)(idx - (int64_t)pix * cv8) * 8;
-        int y = pix / wp, x = pix - y * wp;
-        uint4 o = make_uint4(0, 0, 0, 0), r = make_uint4(0, 0, 0, 0);
-        bool interior = true;
-        if (pad_out) {
-            interior = (y >= 1 && y <= h && x >= 1 && x <= w);
-            y -= 1; x -= 1;
-        }
-        if (interior) {
-            const float* src;
-            int ld, cc;
-            if (c < c0) { src = x0; ld = c0; cc = c; } else { src = x1; ld = c1; cc = c - c0; }
-            const float* ptr = src + ((int64_t)b * hw + (int64_t)y * w + x) * ld + cc;
-            const float4 a = ldg4(ptr), bb = ldg4(ptr + 4);
-            float v[8] = {a.x, a.y, a.z, a.w, bb.x, bb.y, bb.z, bb.w};
-            if (raw) {
-                r.x = pack16x2(v[0], v[1], fmt); r.y = pack16x2(v[2], v[3], fmt);
-                r.z = pack16x2(v[4], v[5], fmt); r.w = pack16x2(v[6], v[7], fmt);
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float t = v[i] * scale[c + i] + shift[c + i];
-                if (do_silu) t = silu(t);
-                v[i] = t;
-            }
-            o.x = pack16x2(v[0], v[1], fmt); o.y = pack16x2(v[2], v[3], fmt);
-            o.z = pack16x2(v[4], v[5], fmt); o.w = pack16x2(v[6], v[7], fmt);
-        }
-        const int64_t orow = (int64_t)b * hp * wp + pix;
-        *reinterpret_cast<uint4*>(out + orow * C + c) = o;
-        if (raw) *reinterpret_cast<uint4*>(raw + orow * C + c) = r;
-    }
-}
-
-// GroupNorm apply from producer-side per-(image, channel) statistics (smtl_gemm_args.stats): one streaming pass.
-// grid (blocks_per_image, batch), 256 threads; each thread handles 8 channels of one (padded) pixel per step.
-template <bool x16>
-__global__ void __launch_bounds__(320, 3) gn_apply2_kernel(
-    const void* __restrict__ x0, const void* __restrict__ x1, int c0, int c1, const float* __restrict__ st0,
-    const float* __restrict__ st1, int replicas, int batch, int h, int w, int groups, float eps,
-    const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu, int pad_out,
-    uint16_t* __restrict__ out, uint16_t* __restrict__ raw, int fmt, FastDiv div_wp, int in_pad) {
-    extern __shared__ float sm[];   // scale[C], shift[C], gmean[groups], grstd[groups]
-    const int C = c0 + c1;
-    float* scale = sm;              // first used as per-channel sum
-    float* shift = sm + C;          // first used as per-channel sum of squares
-    float* gmean = sm + 2 * C;
-    float* grstd = gmean + groups;
-    const int b = blockIdx.y;
-    const int hw = h * w;
-    const int cpg = C / groups;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const float* st = (c < c0) ? st0 : st1;
-        const int cs = (c < c0) ? c0 : c1;
-        const int cc = (c < c0) ? c : c - c0;
-        float s = 0.f, q = 0.f;
-        for (int r = 0; r < replicas; ++r) {
-            const float2 t = __ldg(reinterpret_cast<const float2*>(st + (((int64_t)r * batch + b) * cs + cc) * 2));
-            s += t.x;
-            q += t.y;
-        }
-        scale[c] = s;
-        shift[c] = q;
-    }
-    __syncthreads();
-    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-        double s = 0.0, q = 0.0;
-        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-            s += (double)scale[c];
-            q += (double)shift[c];
-        }
-        const double n = (double)hw * cpg;
-        const double mean = s / n;
-        double var = q / n - mean * mean;
-        if (var < 0.0) var = 0.0;
-        gmean[g] = (float)mean;
-        grstd[g] = (float)(1.0 / sqrt(var + (double)eps));
-    }
+    gn_group_stats(st0, st1, c0, c1, replicas, batch, b, groups, (double)hw * cpg, eps, gmean, grstd);
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const int g = c / cpg;
@@ -271,9 +165,12 @@ __global__ void __launch_bounds__(320, 3) gn_apply2_kernel(
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], sc[i], sh[i]);
-                if (do_silu) {
+                if (do_silu == 1) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = silu_fast(v[i]);
+                } else if (do_silu == 2) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = silu_exact(v[i]);
                 }
                 o.x = pack16x2(v[0], v[1], fmt); o.y = pack16x2(v[2], v[3], fmt);
                 o.z = pack16x2(v[4], v[5], fmt); o.w = pack16x2(v[6], v[7], fmt);
@@ -286,36 +183,15 @@ __global__ void __launch_bounds__(320, 3) gn_apply2_kernel(
 }
 
 // stats -> per-(image, channel) (scale, shift); grid = batch, one thread per channel (blockDim = C rounded up to 32)
-__global__ void gn_finalize_kernel(const float* __restrict__ st, int replicas, int batch, int c, int groups, double n_per_group,
+__global__ void gn_finalize_kernel(const long long* __restrict__ st, int replicas, int batch, int c, int groups, double n_per_group,
                                    float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ ss) {
-    extern __shared__ float sm[];   // sum[C], sq[C], mean[groups], rstd[groups]
-    float* csum = sm;
-    float* csq = sm + c;
-    float* gmean = sm + 2 * c;
+    extern __shared__ float sm[];   // mean[groups], rstd[groups]
+    float* gmean = sm;
     float* grstd = gmean + groups;
     const int b = blockIdx.x;
     const int cpg = c / groups;
-    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-        float s = 0.f, q = 0.f;
-        for (int r = 0; r < replicas; ++r) {
-            const float2 t = __ldg(reinterpret_cast<const float2*>(st + (((int64_t)r * batch + b) * c + ch) * 2));
-            s += t.x;
-            q += t.y;
-        }
-        csum[ch] = s;
-        csq[ch] = q;
-    }
-    __syncthreads();
-    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-        double s = 0.0, q = 0.0;
-        for (int ch = g * cpg; ch < (g + 1) * cpg; ++ch) { s += (double)csum[ch]; q += (double)csq[ch]; }
-        const double mean = s / n_per_group;
-        double var = q / n_per_group - mean * mean;
-        if (var < 0.0) var = 0.0;
-        gmean[g] = (float)mean;
-        grstd[g] = (float)(1.0 / sqrt(var + (double)eps));
-    }
+    gn_group_stats(st, nullptr, c, 0, replicas, batch, b, groups, n_per_group, eps, gmean, grstd);
     __syncthreads();
     for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
         const int g = ch / cpg;
@@ -882,36 +758,6 @@ inline int grid_for(int64_t total, int block, int max_blocks = 148 * 16) {
 }  // namespace
 
 // ================================================================================================ C ABI
-extern "C" int smtl_gn_run(const smtl_gn_args* a, void* stream) {
-    SMTL_CHECK_ARG(a && a->x0 && a->partial && a->gamma && a->beta && a->out_bf16, "gn: NULL argument");
-    const int C = a->c0 + a->c1;
-    SMTL_CHECK_ARG(a->c1 == 0 || a->x1, "gn: c1 > 0 without x1");
-    SMTL_CHECK_ARG(C % a->groups == 0 && a->c0 % 8 == 0 && a->c1 % 8 == 0, "gn: C=%d+%d groups=%d unsupported", a->c0,
-                   a->c1, a->groups);
-    SMTL_CHECK_ARG(C / 4 <= 1024 && a->groups <= 64, "gn: C=%d too wide", C);
-    SMTL_CHECK_ARG(a->nchunk >= 1 && a->batch >= 1 && a->h >= 1 && a->w >= 1, "gn: bad extent");
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const int cv = C / 4;
-    int rows_par = 256 / cv;
-    if (rows_par < 1) rows_par = 1;
-    const int hw = a->h * a->w;
-    gn_stats_kernel<<<dim3(a->nchunk, a->batch), cv * rows_par, 2 * a->groups * sizeof(float), st>>>(
-        a->x0, a->x1, a->c0, a->c1, hw, a->groups, a->nchunk, a->partial);
-    SMTL_CHECK_CUDA(cudaGetLastError());
-    const int hp = a->pad_out ? a->h + 2 : a->h, wp = a->pad_out ? a->w + 2 : a->w;
-    const int64_t per_img = (int64_t)hp * wp * (C / 8);
-    int bpi = (int)((per_img + 256 * 4 - 1) / (256 * 4));
-    const int cap = (148 * 8 + a->batch - 1) / a->batch;
-    if (bpi > cap) bpi = cap;
-    if (bpi < 1) bpi = 1;
-    const size_t smem = (2 * C + 2 * a->groups) * sizeof(float);
-    gn_apply_kernel<<<dim3(bpi, a->batch), 256, smem, st>>>(
-        a->x0, a->x1, a->c0, a->c1, a->h, a->w, a->groups, a->eps, a->partial, a->nchunk, a->gamma, a->beta, a->silu,
-        a->pad_out, reinterpret_cast<uint16_t*>(a->out_bf16), reinterpret_cast<uint16_t*>(a->raw_bf16), a->fmt16);
-    SMTL_CHECK_CUDA(cudaGetLastError());
-    return SMTL_OK;
-}
-
 extern "C" int smtl_gnapply_run(const smtl_gnapply_args* a, void* stream) {
     SMTL_CHECK_ARG(a && a->x0 && a->stats0 && a->gamma && a->beta && a->out_bf16, "gnapply: NULL argument");
     const int C = a->c0 + a->c1;
@@ -925,7 +771,7 @@ extern "C" int smtl_gnapply_run(const smtl_gnapply_args* a, void* stream) {
     const int cv8 = C / 8;
     SMTL_CHECK_ARG(cv8 <= 320, "gnapply: C=%d too wide", C);
     SMTL_CHECK_ARG((int64_t)hp * wp < ((int64_t)1 << 31), "gnapply: image too large");
-    const int threads = (cv8 > 256) ? cv8 : (256 / cv8) * cv8;        // a multiple of C/8: thread <-> fixed channels
+    const int threads = (cv8 > 256) ? cv8 : (256 / cv8) * cv8;        // a multiple of C/8: thread <-> fixed channels (>= 129)
     const int ppb = threads / cv8;
     const int64_t steps = ((int64_t)hp * wp + (int64_t)ppb * 4 - 1) / ((int64_t)ppb * 4);
     int bpi = (int)steps;
@@ -935,7 +781,8 @@ extern "C" int smtl_gnapply_run(const smtl_gnapply_args* a, void* stream) {
     const size_t smem = (2 * C + 2 * a->groups) * sizeof(float);
     auto kern = a->x_fmt16 ? gn_apply2_kernel<true> : gn_apply2_kernel<false>;
     kern<<<dim3(bpi, a->batch), threads, smem, st>>>(
-        a->x0, a->x1, a->c0, a->c1, a->stats0, a->stats1, a->stats_replicas, a->batch, a->h, a->w,
+        a->x0, a->x1, a->c0, a->c1, reinterpret_cast<const long long*>(a->stats0),
+        reinterpret_cast<const long long*>(a->stats1), a->stats_replicas, a->batch, a->h, a->w,
         a->groups, a->eps, a->gamma, a->beta, a->silu, a->pad_out, reinterpret_cast<uint16_t*>(a->out_bf16),
         reinterpret_cast<uint16_t*>(a->raw_bf16), a->fmt16, make_fastdiv((uint32_t)wp), a->x_padded);
     SMTL_CHECK_CUDA(cudaGetLastError());
@@ -946,10 +793,10 @@ extern "C" int smtl_gnfinalize_run(const smtl_gnfinalize_args* a, void* stream) 
     SMTL_CHECK_ARG(a && a->stats && a->gamma && a->beta && a->ss, "gnfinalize: NULL argument");
     SMTL_CHECK_ARG(a->groups > 0 && a->c % a->groups == 0 && a->batch >= 1 && a->stats_replicas >= 1 && a->pixels > 0 &&
                        a->c <= 8192 && a->groups <= 64, "gnfinalize: bad extent");
-    const size_t smem = (2 * a->c + 2 * a->groups) * sizeof(float);
+    const size_t smem = (2 * a->groups) * sizeof(float);
     const int threads = a->c < 256 ? ((a->c + 31) / 32) * 32 : 256;
     gn_finalize_kernel<<<a->batch, threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-        a->stats, a->stats_replicas, a->batch, a->c, a->groups, (double)a->pixels * (a->c / a->groups), a->eps, a->gamma,
+        reinterpret_cast<const long long*>(a->stats), a->stats_replicas, a->batch, a->c, a->groups, (double)a->pixels * (a->c / a->groups), a->eps, a->gamma,
         a->beta, a->ss);
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;

@@ -57,8 +57,12 @@ struct alignas(64) GemmKParams {
     const void* res2;
     int32_t ldres;
     int32_t res16;
-    float* stats;
+    unsigned long long* stats;   // int64 fixed-point cells [rep, images, n_out, 4] (smtl_common.cuh: stats_atomic_add)
     int32_t stats_rpi, stats_images, stats_rep;
+    // Image-aligned tiling (set whenever stats are produced): M tiles restart at every image's first GEMM row, so the
+    // 32-row partial sums of an image are the same fp32 values wherever the image sits in the batch.
+    int64_t tile_rpi;            // GEMM rows per image; 0 = tiles run over all rows
+    int32_t tiles_per_img;
     float* out_f32;
     uint16_t* out_bf16;
     uint16_t* aux_bf16;
@@ -115,8 +119,8 @@ __device__ __forceinline__ float warp_transpose_sum(float (&s)[32], int lane) {
 // pixel (PAD_KEEP stores zeros there; everyone else stores nothing).
 // (rows fit in 31 bits -- checked by the plan -- and the two divisors are per-launch constants: multiply-shift division
 // instead of 64-bit integer division, which was half of the swapped kernel's epilogue instructions)
-__device__ __forceinline__ void map_row(const GemmKParams& p, int64_t grow, bool& ok, int64_t& orow, bool& halo, int& img_out) {
-    ok = grow < p.m;
+__device__ __forceinline__ void map_row(const GemmKParams& p, int64_t grow, int64_t row_end, bool& ok, int64_t& orow, bool& halo, int& img_out) {
+    ok = grow < row_end;
     orow = grow;
     halo = false;
     img_out = -1;                                            // identity map: the caller divides by stats_rpi itself
@@ -150,6 +154,18 @@ __device__ __forceinline__ void map_row(const GemmKParams& p, int64_t grow, bool
     // PAD_KEEP: orow = grow
 }
 
+// First GEMM row of M tile `tm` (tile_rows = 128, 256 for a CTA pair or the swapped kernel) and the end of its valid rows.
+__device__ __forceinline__ void tile_span(const GemmKParams& p, int tm, int tile_rows, int64_t& row0, int64_t& row_end) {
+    if (p.tile_rpi) {
+        const int img = tm / p.tiles_per_img;
+        row0 = (int64_t)img * p.tile_rpi + (int64_t)(tm - img * p.tiles_per_img) * tile_rows;
+        row_end = (int64_t)(img + 1) * p.tile_rpi;
+    } else {
+        row0 = (int64_t)tm * tile_rows;
+        row_end = p.m;
+    }
+}
+
 // Per-thread state of one tile's epilogue, computed BEFORE waiting for the accumulator so that the residual
 // prefetches and the bias loads overlap the tile's MMAs.
 template <int BN>
@@ -164,12 +180,12 @@ struct EpiRow {
 };
 
 template <int BN>
-__device__ __forceinline__ void epilogue_prepare(const GemmKParams& p, int64_t grow, int tn, int lane, EpiRow<BN>& e) {
+__device__ __forceinline__ void epilogue_prepare(const GemmKParams& p, int64_t grow, int64_t row_end, int tn, int lane, EpiRow<BN>& e) {
     const bool geglu = (p.act == SMTL_ACT_GEGLU);
     const int out_bn = geglu ? BN / 2 : BN;
     const int n0 = tn * BN;
     int map_img;
-    map_row(p, grow, e.row_ok, e.orow, e.halo, map_img);
+    map_row(p, grow, row_end, e.row_ok, e.orow, e.halo, map_img);
     e.halo = e.halo && (p.rowmap == SMTL_ROWMAP_PAD_KEEP);
     e.row_bias = (p.bias && p.bias_per_row && grow < p.m) ? __ldg(p.bias + grow) : 0.0f;
 #pragma unroll
@@ -357,12 +373,9 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t tad
                 }
                 const float cs = warp_transpose_sum(s, lane);
                 const float cq = warp_transpose_sum(q, lane);
-                if (ocol + lane < p.n_out) {
-                    float* dst = p.stats + (((int64_t)(blockIdx.x % p.stats_rep) * p.stats_images + img) * p.n_out +
-                                            ocol + lane) * 2;
-                    atomicAdd(dst, cs);
-                    atomicAdd(dst + 1, cq);
-                }
+                if (ocol + lane < p.n_out)
+                    stats_atomic_add(p.stats + (((int64_t)(blockIdx.x % p.stats_rep) * p.stats_images + img) * p.n_out +
+                                                ocol + lane) * 4, cs, cq);
             }
         }
     }
@@ -435,7 +448,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
             uint32_t pph = 0, wph = 0;
             for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
-                const int64_t m0 = ((int64_t)tm * CG + rank) * BLOCK_M;
+                int64_t row0, row_end;
+                tile_span(p, tm, CG * BLOCK_M, row0, row_end);
+                const int64_t m0 = row0 + (int64_t)rank * BLOCK_M;
                 const int n0 = tn * BN + (int)rank * B_ROWS +
                                (p.group_rows ? (int)(((int64_t)tm * CG * BLOCK_M) / p.group_rows) * p.n : 0);
                 for (int g = 0; g < p.ngrp; ++g) {
@@ -488,7 +503,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
             uint32_t phase = 0;
             for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
-                const int64_t m0 = ((int64_t)tm * CG + rank) * BLOCK_M;
+                int64_t row0, row_end;
+                tile_span(p, tm, CG * BLOCK_M, row0, row_end);
+                const int64_t m0 = row0 + (int64_t)rank * BLOCK_M;
                 const int n0 = tn * BN + (int)rank * B_ROWS +
                                (p.group_rows ? (int)(((int64_t)tm * CG * BLOCK_M) / p.group_rows) * p.n : 0);
                 int kb_global = 0;
@@ -624,7 +641,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
             const uint32_t acc_phase = (it >> 1) & 1;
             const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
             EpiRow<BN> er;
-            epilogue_prepare<BN>(p, ((int64_t)tm * CG + rank) * BLOCK_M + row_in_tile, tn, lane, er);
+            int64_t row0, row_end;
+            tile_span(p, tm, CG * BLOCK_M, row0, row_end);
+            epilogue_prepare<BN>(p, row0 + (int64_t)rank * BLOCK_M + row_in_tile, row_end, tn, lane, er);
             mbar_wait_backoff(&acc_full[acc], acc_phase, 100);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
@@ -710,7 +729,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
             int ps = 0, ws = 0;
             uint32_t pph = 0, wph = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int64_t pix0 = (int64_t)tile * TBN;
+                int64_t pix0, pix_end;
+                tile_span(p, tile, TBN, pix0, pix_end);
                 for (int g = 0; g < p.ngrp; ++g) {
                     const GemmKParams::Grp gr = p.grp[g];
                     const CUtensorMap* tmx = gr.src ? &p.tm_a1 : &p.tm_a0;
@@ -744,7 +764,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int64_t pix0 = (int64_t)tile * TBN;
+                int64_t pix0, pix_end;
+                tile_span(p, tile, TBN, pix0, pix_end);
                 int kb_global = 0;
                 for (int s = 0; s < p.nseg; ++s) {
                     const smtl_gemm_seg sg = p.seg[s];
@@ -846,21 +867,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
         const int piece = lane & 3;                                   // 8-channel piece this lane moves (coalesced side)
         const int cpiece = quarter * 32 + piece * 8;                  // its first channel
         const bool piece_ok = cpiece + 8 <= p.n;
-        float ssum = 0.f, ssq = 0.f;
+        // this thread's channel sums of the current image, exact: every 32-pixel chunk's fp32 partial is added in the
+        // int64 fixed-point form of the statistics cells (smtl_common.cuh), so the order of the chunks does not matter
+        long long acc4[4] = {0, 0, 0, 0};
         int cur_img = -1;
         auto flush = [&]() {
             if (p.stats && cur_img >= 0 && ch_ok) {
-                float* dst = p.stats + (((int64_t)(blockIdx.x % p.stats_rep) * p.stats_images + cur_img) * p.n + ch) * 2;
-                atomicAdd(dst, ssum);
-                atomicAdd(dst + 1, ssq);
+                unsigned long long* dst =
+                    p.stats + (((int64_t)(blockIdx.x % p.stats_rep) * p.stats_images + cur_img) * p.n + ch) * 4;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (acc4[i]) atomicAdd(dst + i, (unsigned long long)acc4[i]);
             }
-            ssum = 0.f;
-            ssq = 0.f;
+            acc4[0] = acc4[1] = acc4[2] = acc4[3] = 0;
+        };
+        auto add_chunk = [&](float s, float q) {
+            bool hi;
+            long long v = stats_fix(s, hi);
+            acc4[hi ? 1 : 0] += v;
+            v = stats_fix(q, hi);
+            acc4[hi ? 3 : 2] += v;
         };
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
-            const int64_t pix0 = (int64_t)tile * TBN;
+            int64_t pix0, pix_end;
+            tile_span(p, tile, TBN, pix0, pix_end);
             mbar_wait(&acc_full[acc], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
@@ -871,11 +903,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
                 bool ok, halo;
                 int64_t orow;
                 int map_img;
-                map_row(p, grow, ok, orow, halo, map_img);
+                map_row(p, grow, pix_end, ok, orow, halo, map_img);
                 halo = halo && (p.rowmap == SMTL_ROWMAP_PAD_KEEP);
                 const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
                 const uint32_t halomask = __ballot_sync(0xffffffffu, halo);
-                if ((okmask | halomask) == 0 && pix0 + c0 >= p.m) break;             // warp-uniform: past the end
+                if ((okmask | halomask) == 0 && pix0 + c0 >= pix_end) break;         // warp-uniform: past the end
                 const int orow32 = (int)orow;
                 const int img_l = !(p.stats && ok) ? -1 : (map_img >= 0 ? map_img : (int)(orow / p.stats_rpi));
                 uint32_t rr[32];
@@ -937,18 +969,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
                     }
                     if (lo == hi) {                                      // the usual case: one image in this chunk
                         if (lo != cur_img) { flush(); cur_img = lo; }
+                        float ssum = 0.f, ssq = 0.f;
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             if ((okmask >> j) & 1u) { ssum += v[j]; ssq += v[j] * v[j]; }
+                        add_chunk(ssum, ssq);
                     } else {
-                        for (int j = 0; j < 32; ++j) {                   // image boundary inside the chunk (rare)
-                            const int im = __shfl_sync(0xffffffffu, img_l, j);
+                        float ssum = 0.f, ssq = 0.f;
+                        for (int j = 0; j < 32; ++j) {                   // image boundary inside the chunk (tiles that are
+                            const int im = __shfl_sync(0xffffffffu, img_l, j);   // not image-aligned only)
                             if ((okmask >> j) & 1u) {
-                                if (im != cur_img) { flush(); cur_img = im; }
+                                if (im != cur_img) { add_chunk(ssum, ssq); ssum = ssq = 0.f; flush(); cur_img = im; }
                                 ssum += v[j];
                                 ssq += v[j] * v[j];
                             }
                         }
+                        add_chunk(ssum, ssq);
                     }
                 }
             }
@@ -1079,6 +1115,21 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
         SMTL_CHECK_ARG(g.act != SMTL_ACT_GEGLU && !g.bias_per_row, "gemm_plan: stats with GEGLU / per-row bias");
     }
     SMTL_CHECK_ARG(g.m + 4096 < (int64_t)1 << 31, "gemm_plan: m too large for 32-bit TMA coordinates");
+    // image-aligned M tiling whenever statistics are produced (see GemmKParams::tile_rpi)
+    int64_t tile_rpi = 0;
+    if (g.stats) {
+        if (g.rowmap == SMTL_ROWMAP_IDENTITY) tile_rpi = g.stats_rows_per_image;
+        else if (g.rowmap == SMTL_ROWMAP_TO_PAD) tile_rpi = (int64_t)g.img_h * g.img_w;
+        else tile_rpi = (int64_t)(g.img_h + 2) * (g.img_w + 2);
+        SMTL_CHECK_ARG(g.m == tile_rpi * g.stats_images, "gemm_plan: stats: m=%lld is not stats_images=%d x %lld rows",
+                       (long long)g.m, g.stats_images, (long long)tile_rpi);
+    }
+    op->tile_rpi = tile_rpi;
+    auto count_tiles_m = [&](int tile_rows) {
+        if (!tile_rpi) { op->tiles_per_img = 0; return (int)((g.m + tile_rows - 1) / tile_rows); }
+        op->tiles_per_img = (int)((tile_rpi + tile_rows - 1) / tile_rows);
+        return op->tiles_per_img * g.stats_images;
+    };
 
     const int sms = smtl_host::num_sms();
     // ---- shift groups: consecutive-row-shift segments (kx = -1, 0, +1 of one ky) share one activation tile
@@ -1118,7 +1169,7 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
         if (allow && eligible) {
             op->cta_group = 3;                      // marks the swapped kernel
             op->block_n = TBN;
-            op->tiles_m = (int)((g.m + TBN - 1) / TBN);
+            op->tiles_m = count_tiles_m(TBN);
             op->tiles_n = 1;
             op->total_kblocks = total_kb;
             int stages = (SMEM_BUDGET - 1024 - 512 - T_STAGING) / T_STAGE_BYTES;
@@ -1157,7 +1208,7 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
     // CTA pairs (tcgen05 cta_group::2, 256-row tiles) whenever there are enough rows to fill the machine with them
     int cg = g.cta_group;
     if (cg == 0) {
-        const long long tiles256 = ((g.m + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (long long)((g.n + bn - 1) / bn);
+        const long long tiles256 = (long long)count_tiles_m(2 * BLOCK_M) * (long long)((g.n + bn - 1) / bn);
         const char* env = getenv("SMTL_GEMM_CG");
         // measured on B200 (scripts/bench_kernels.py gemm): pairs win on long plain-K GEMMs (8192^3: 1170 -> 1295
         // TFLOP/s) and lose on the 9-segment implicit convs and on short-K linears, whose cost is the epilogue
@@ -1175,7 +1226,7 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
     SMTL_CHECK_ARG(cg == 1 || bn % 16 == 0, "gemm_plan: cta_group 2 needs block_n %% 16 == 0");
     op->cta_group = cg;
     op->block_n = bn;
-    op->tiles_m = (int)((g.m + cg * BLOCK_M - 1) / (cg * BLOCK_M));
+    op->tiles_m = count_tiles_m(cg * BLOCK_M);
     op->tiles_n = (g.n + bn - 1) / bn;
     op->total_kblocks = total_kb;
     const int stage_bytes = A_STAGE_BYTES + (bn / cg) * BLOCK_K * 2;
@@ -1259,7 +1310,9 @@ extern "C" int smtl_gemm_run(const smtl_gemm_op* op, void* stream) {
     kp.res2 = g.res2;
     kp.ldres = g.ldres;
     kp.res16 = g.res_fmt16;
-    kp.stats = g.stats;
+    kp.stats = reinterpret_cast<unsigned long long*>(g.stats);
+    kp.tile_rpi = op->tile_rpi;
+    kp.tiles_per_img = op->tiles_per_img;
     kp.stats_rpi = g.stats_rows_per_image;
     kp.stats_images = g.stats_images;
     kp.stats_rep = g.stats_replicas > 0 ? g.stats_replicas : 1;

@@ -88,12 +88,12 @@ class StatsArena:
 
     def new(self, images, channels):
         rep = max(1, min(ops.STATS_REPLICAS, 64 // images))
-        n = rep * images * channels * 2
-        n_al = (n + 63) // 64 * 64
+        n = rep * images * channels * 4
+        n_al = (n + 31) // 32 * 32
         if not self.chunks or self.used[-1] + n_al > self.chunks[-1].numel():
-            self.chunks.append(torch.zeros(max(self.chunk_bytes // 4, n_al), device=self.device, dtype=F32))
+            self.chunks.append(torch.zeros(max(self.chunk_bytes // 8, n_al), device=self.device, dtype=torch.int64))
             self.used.append(0)
-        t = self.chunks[-1][self.used[-1]: self.used[-1] + n].view(rep, images, channels, 2)
+        t = self.chunks[-1][self.used[-1]: self.used[-1] + n].view(rep, images, channels, 4)
         self.used[-1] += n_al
         return t
 

@@ -56,7 +56,7 @@ def _stream():
 
 _RUNNERS = {
     L.OP_GEMM: "smtl_gemm_run", L.OP_FATTN: "smtl_fattn_run", L.OP_SOFTMAX: "smtl_softmax_run",
-    L.OP_XATTN: "smtl_xattn_run", L.OP_TASKATTN: "smtl_taskattn_run", L.OP_GN: "smtl_gn_run",
+    L.OP_XATTN: "smtl_xattn_run", L.OP_TASKATTN: "smtl_taskattn_run",
     L.OP_LN: "smtl_ln_run", L.OP_UPSAMPLE: "smtl_upsample_run", L.OP_IM2COL: "smtl_im2col_run",
     L.OP_RGBPREP: "smtl_rgbprep_run", L.OP_UNETIN: "smtl_unetin_run", L.OP_TASKMAP: "smtl_taskmap_run",
     L.OP_CHANMIX: "smtl_chanmix_run", L.OP_GNAPPLY: "smtl_gnapply_run", L.OP_MEMSET: "smtl_memset_run",
@@ -119,11 +119,28 @@ class Plan:
 
 # ------------------------------------------------------------------------------------------------- GEMM / conv
 STATS_REPLICAS = 8      # copies of a statistics buffer the producing GEMM's CTAs spread their atomics over
+SILU_MODE = 1           # gn_apply(silu=True): 1 = one tanh.approx per element, 2 = ex2 + rcp (~2 ulp)
 
 
-def new_stats(images, channels, device):
-    """fp32 [replicas, images, channels, 2] (sum, sum of squares) filled by a GEMM epilogue; must be zeroed before."""
-    return torch.zeros(STATS_REPLICAS, images, channels, 2, device=device, dtype=F32)
+def new_stats(images, channels, device, replicas=None):
+    """int64 [replicas, images, channels, 4]: fixed-point (sum_lo, sum_hi, sq_lo, sq_hi) cells a GEMM epilogue adds
+    into with integer atomics (exact, order-independent); must be zeroed before the producer runs."""
+    return torch.zeros(replicas or STATS_REPLICAS, images, channels, 4, device=device, dtype=torch.int64)
+
+
+def stats_encode(values):
+    """float64 [..., 2] (sum, sum of squares) -> int64 fixed-point cells [..., 4] the way a producer would add them"""
+    v = values.double()
+    fine = v.abs() < 2.0 ** 14
+    lo = torch.where(fine, torch.round(v * 2.0 ** 35), torch.zeros_like(v)).to(torch.int64)
+    hi = torch.where(fine, torch.zeros_like(v), torch.round(v * 2.0 ** 8)).to(torch.int64)
+    return torch.stack([lo[..., 0], hi[..., 0], lo[..., 1], hi[..., 1]], -1)
+
+
+def stats_values(stats):
+    """float64 [images, channels, 2] (sum, sum of squares) held by a statistics buffer"""
+    s = stats.sum(0).double()
+    return torch.stack([s[..., 0] * 2.0 ** -35 + s[..., 1] * 2.0 ** -8, s[..., 2] * 2.0 ** -35 + s[..., 3] * 2.0 ** -8], -1)
 
 
 def gemm(a0, b, *, m=None, k=None, n=None, a1=None, segs=None, bias=None, bias_per_row=False, act=L.ACT_NONE,
@@ -161,7 +178,7 @@ def gemm(a0, b, *, m=None, k=None, n=None, a1=None, segs=None, bias=None, bias_p
             g.ldres = r.stride(0)
     g.res_fmt16 = int(res_dt is not None and res_dt != F32)
     if stats is not None:
-        assert stats.dtype == F32 and stats.dim() == 4 and stats.shape[3] == 2 and stats.is_contiguous()
+        assert stats.dtype == torch.int64 and stats.dim() == 4 and stats.shape[3] == 4 and stats.is_contiguous()
         assert stats.shape[2] == n_out and stats_rows_per_image > 0
         g.stats, g.stats_replicas, g.stats_images = stats.data_ptr(), stats.shape[0], stats.shape[1]
         g.stats_rows_per_image = stats_rows_per_image
@@ -312,27 +329,6 @@ def task_attn(q, k, v, out, c, nheads, main_tasks, src_tasks, rows_per_group, ex
 
 
 # ------------------------------------------------------------------------------------------------- norms
-def gn_nchunk(hw):
-    return max(1, min(64, hw // 512))
-
-
-def group_norm(x0, batch, h, w, gamma, beta, out, *, x1=None, eps, silu, pad_out, partial, raw=None, groups=32):
-    a = L.GnArgs()
-    a.fmt16 = PREC["fmt"]
-    a.x0, a.c0 = x0.data_ptr(), x0.shape[-1]
-    if x1 is not None:
-        a.x1, a.c1 = x1.data_ptr(), x1.shape[-1]
-    a.batch, a.h, a.w, a.groups, a.eps = batch, h, w, groups, eps
-    a.nchunk = gn_nchunk(h * w)
-    assert partial.dtype == F32 and partial.numel() >= batch * a.nchunk * groups * 2
-    a.partial = partial.data_ptr()
-    a.gamma, a.beta = gamma.data_ptr(), beta.data_ptr()
-    a.silu, a.pad_out = int(silu), int(pad_out)
-    a.out_bf16, a.raw_bf16 = out.data_ptr(), _ptr(raw)
-    assert x0.dtype == F32 and out.dtype == BF16 and x0.is_contiguous()
-    return Op(L.OP_GN, a, (x0, x1, gamma, beta, out, raw, partial), 0, "group_norm")
-
-
 def gn_apply(x0, stats0, batch, h, w, gamma, beta, out, *, x1=None, stats1=None, eps, silu, pad_out, raw=None,
              groups=32, x_padded=False):
     """GroupNorm(+SiLU) of the (virtually concatenated) compact map [x0 | x1] using the per-(image, channel) sums the
@@ -342,16 +338,16 @@ def gn_apply(x0, stats0, batch, h, w, gamma, beta, out, *, x1=None, stats1=None,
     a.x0, a.c0 = x0.data_ptr(), x0.shape[-1]
     a.x_fmt16 = int(x0.dtype != F32)
     assert x0.is_contiguous() and (x0.dtype == F32 or x0.dtype == BF16)
-    assert stats0.shape[1:] == (batch, x0.shape[-1], 2), (stats0.shape, batch, x0.shape)
+    assert stats0.shape[1:] == (batch, x0.shape[-1], 4) and stats0.dtype == torch.int64, (stats0.shape, batch, x0.shape)
     a.stats0, a.stats_replicas = stats0.data_ptr(), stats0.shape[0]
     if x1 is not None:
-        assert x1.dtype == x0.dtype and x1.is_contiguous() and stats1.shape == (stats0.shape[0], batch, x1.shape[-1], 2)
+        assert x1.dtype == x0.dtype and x1.is_contiguous() and stats1.shape == (stats0.shape[0], batch, x1.shape[-1], 4)
         a.x1, a.c1, a.stats1 = x1.data_ptr(), x1.shape[-1], stats1.data_ptr()
     a.batch, a.h, a.w, a.groups, a.eps = batch, h, w, groups, eps
     a.x_padded = int(x_padded)
     assert x0.shape[0] == batch * ((h + 2) * (w + 2) if x_padded else h * w)
     a.gamma, a.beta = gamma.data_ptr(), beta.data_ptr()
-    a.silu, a.pad_out = int(silu), int(pad_out)
+    a.silu, a.pad_out = (SILU_MODE if silu is True else int(silu)), int(pad_out)
     a.out_bf16, a.raw_bf16 = out.data_ptr(), _ptr(raw)
     assert out.dtype == BF16
     # algorithmic bytes: every interior element read once, every output element (halo included) written once
@@ -364,7 +360,7 @@ def gn_finalize(stats, batch, pixels, gamma, beta, ss, *, eps, groups=32):
     """producer-side channel sums -> fp32 [batch, C, 2] (scale, shift): GroupNorm as a per-image affine map"""
     a = L.GnFinalizeArgs()
     c = stats.shape[2]
-    assert stats.shape[1:] == (batch, c, 2) and ss.shape == (batch, c, 2) and ss.dtype == F32 and ss.is_contiguous()
+    assert stats.shape[1:] == (batch, c, 4) and stats.dtype == torch.int64 and ss.shape == (batch, c, 2) and ss.dtype == F32 and ss.is_contiguous()
     a.stats, a.stats_replicas, a.batch, a.c, a.groups = stats.data_ptr(), stats.shape[0], batch, c, groups
     a.pixels, a.eps = pixels, eps
     a.gamma, a.beta, a.ss = gamma.data_ptr(), beta.data_ptr(), ss.data_ptr()

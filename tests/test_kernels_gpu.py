@@ -159,38 +159,6 @@ def test_flash_attention(batch, ntok, heads):
     assert err < 1e-2, f"flash attention rel-L2 {err}"   # P and O are rounded to bf16
 
 
-@pytest.mark.parametrize("b,h,w,c0,c1,silu,pad", [(2, 8, 10, 320, 0, True, True), (1, 15, 20, 1280, 640, True, True),
-                                                  (2, 30, 40, 640, 320, True, True), (2, 6, 20, 320, 0, False, False),
-                                                  (1, 64, 96, 128, 0, True, True)])
-def test_group_norm(b, h, w, c0, c1, silu, pad):
-    ops, L = _ops()
-    x0 = rnd(b, h * w, c0, seed=1) * 2 + 0.5
-    x1 = rnd(b, h * w, c1, seed=2) - 0.3 if c1 else None
-    C = c0 + c1
-    gamma, beta = rnd(C, seed=3) + 1, rnd(C, seed=4)
-    hp, wp = (h + 2, w + 2) if pad else (h, w)
-    out = torch.full((b * hp * wp, C), float("nan"), device=DEV, dtype=H16())
-    raw = torch.full((b * hp * wp, C), float("nan"), device=DEV, dtype=H16())
-    partial = torch.empty(b * 64 * 32 * 2, device=DEV)
-    ops.group_norm(x0, b, h, w, gamma, beta, out, x1=x1, eps=1e-5, silu=silu, pad_out=pad, partial=partial, raw=raw).run()
-    torch.cuda.synchronize()
-    xc = torch.cat([x0, x1], dim=-1) if c1 else x0
-    xn = xc.reshape(b, h, w, C).permute(0, 3, 1, 2)
-    ref = F.group_norm(xn, 32, gamma, beta, eps=1e-5)
-    if silu:
-        ref = F.silu(ref)
-    ref = ref.permute(0, 2, 3, 1)
-    rawref = xc.reshape(b, h, w, C)
-    if pad:
-        ref = _pad_layout(ref)
-        rawref = _pad_layout(rawref)
-    assert rel_l2(out.float(), ref.reshape(-1, C)) < 4e-3
-    assert rel_l2(raw.float(), rawref.reshape(-1, C)) < 4e-3
-    if pad:
-        halo = out.reshape(b, hp, wp, C)
-        assert halo[:, 0].abs().max() == 0 and halo[:, :, 0].abs().max() == 0 and halo[:, -1].abs().max() == 0
-
-
 @pytest.mark.parametrize("rows,c,bf16_in", [(1000, 320, False), (77, 640, False), (300, 1280, True)])
 def test_layer_norm(rows, c, bf16_in):
     ops, L = _ops()
@@ -349,7 +317,7 @@ def test_gemm_16bit_residual_and_channel_stats(m, n, k, rpi):
     torch.cuda.synchronize()
     ref = a.float() @ b.float().t() + bias + res.float()
     assert rel_l2(out.float(), ref) < 4e-3
-    st = stats.sum(0)                                            # replicas
+    st = ops.stats_values(stats)                                 # replicas summed, fixed point -> float64
     for img in range(images):
         blk = ref[img * rpi:(img + 1) * rpi].double()
         assert rel_l2(st[img, :, 0], blk.sum(0)) < 1e-4, img
@@ -373,7 +341,7 @@ def test_conv3x3_16bit_out_with_stats(b, h, w, cin, cout):
                 stats_rows_per_image=h * w).run()
     torch.cuda.synchronize()
     assert rel_l2(out.float(), ref) < 4e-3
-    st = stats.sum(0)
+    st = ops.stats_values(stats)
     blk = ref.reshape(b, h * w, cout).double()
     assert rel_l2(st[:, :, 0], blk.sum(1)) < 1e-4
     assert rel_l2(st[:, :, 1], (blk * blk).sum(1)) < 1e-4
@@ -393,11 +361,11 @@ def test_gn_apply_from_channel_stats(b, h, w, c0, c1, silu, pad, x16):
     def stats_of(x):
         st = ops.new_stats(b, x.shape[-1], DEV)
         xd = x.double()
-        full = torch.stack([xd.sum(1), (xd * xd).sum(1)], dim=-1).float()
+        full = torch.stack([xd.sum(1), (xd * xd).sum(1)], dim=-1)
         if st.shape[0] > 1:                                    # spread over two replicas: the consumer must sum them
-            st[0], st[1] = full * 0.5, full * 0.5
+            st[0], st[1] = ops.stats_encode(full * 0.25), ops.stats_encode(full * 0.75)
         else:
-            st[0] = full
+            st[0] = ops.stats_encode(full)
         return st
     s0 = stats_of(x0)
     s1 = stats_of(x1) if c1 else None
@@ -483,7 +451,7 @@ def test_gemm_cta_pair_geglu_and_stats():
     torch.cuda.synchronize()
     ref = a.float() @ b2.float().t() + res.float()
     assert rel_l2(o2.float(), ref) < 4e-3
-    st = stats.sum(0)
+    st = ops.stats_values(stats)
     for img in range(4):
         blk = ref[img * rpi:(img + 1) * rpi].double()
         assert rel_l2(st[img, :, 0], blk.sum(0)) < 1e-4 and rel_l2(st[img, :, 1], (blk * blk).sum(0)) < 1e-4
@@ -544,7 +512,7 @@ def test_conv3x3_swapped_narrow_output(b, h, w, cin, cout, cs, with_res):
     op.run()
     torch.cuda.synchronize()
     assert rel_l2(out.float(), ref) < 4e-3
-    st = stats.sum(0)
+    st = ops.stats_values(stats)
     blk = ref.reshape(b, h * w, cout).double()
     assert rel_l2(st[:, :, 0], blk.sum(1)) < 1e-4
     assert rel_l2(st[:, :, 1], (blk * blk).sum(1)) < 1e-4
@@ -583,7 +551,7 @@ def test_conv_up2x_parity_decomposition(b, h, w, cin, cout):
     torch.cuda.synchronize()
     assert not torch.isnan(out.float()).any()
     assert rel_l2(out.float(), ref) < 5e-3
-    st = stats.sum(0)
+    st = ops.stats_values(stats)
     blk = ref.reshape(b, 4 * h * w, cout).double()
     assert rel_l2(st[:, :, 0], blk.sum(1)) < 2e-3
     assert rel_l2(st[:, :, 1], (blk * blk).sum(1)) < 2e-3
@@ -638,7 +606,7 @@ def test_conv3x3_padded_output_zero_halo(b, h, w, cin, cout, cs):
     assert rel_l2(_unpad(out, b, h, w).float(), ref) < 4e-3
     o4 = out.reshape(b, h + 2, w + 2, cout).float()
     assert o4[:, 0].abs().max() == 0 and o4[:, -1].abs().max() == 0 and o4[:, :, 0].abs().max() == 0 and o4[:, :, -1].abs().max() == 0
-    st = stats.sum(0)
+    st = ops.stats_values(stats)
     blk = ref.reshape(b, h * w, cout).double()
     assert rel_l2(st[:, :, 0], blk.sum(1)) < 1e-4 and rel_l2(st[:, :, 1], (blk * blk).sum(1)) < 1e-4
 
@@ -656,7 +624,7 @@ def test_gemm_to_pad_and_up2x_pad_rowmaps():
     torch.cuda.synchronize()
     ref = a.float() @ wt.float().t() + res_nhwc.float().reshape(-1, n)
     assert rel_l2(_unpad(out, b, h, w).float(), ref) < 4e-3
-    assert rel_l2(stats.sum(0)[:, :, 0], ref.reshape(b, h * w, n).double().sum(1)) < 1e-4
+    assert rel_l2(ops.stats_values(stats)[:, :, 0], ref.reshape(b, h * w, n).double().sum(1)) < 1e-4
     # up2x into a padded 2x map
     cin, cout = 64, 128
     x = rnd(b, h, w, cin, seed=5).to(H16())
@@ -679,7 +647,7 @@ def test_gn_apply_reads_padded_input():
     xp[xp == 0] = 9.0                                            # halo content must be ignored
     st = ops.new_stats(b, c, DEV)
     xd = x.double().reshape(b, h * w, c)
-    st[0] = torch.stack([xd.sum(1), (xd * xd).sum(1)], dim=-1).float()
+    st[0] = ops.stats_encode(torch.stack([xd.sum(1), (xd * xd).sum(1)], dim=-1))
     gamma, beta = rnd(c, seed=3) + 1, rnd(c, seed=4)
     out = torch.full((b * (h + 2) * (w + 2), c), float("nan"), device=DEV, dtype=H16())
     ops.gn_apply(xp, st, b, h, w, gamma, beta, out, eps=1e-6, silu=True, pad_out=True, x_padded=True).run()
@@ -763,11 +731,11 @@ def test_gn_finalize_scale_shift_table():
     x = rnd(b, hw, c, seed=1) * 2 + 0.7
     st = ops.new_stats(b, c, DEV)
     xd = x.double()
-    full = torch.stack([xd.sum(1), (xd * xd).sum(1)], dim=-1).float()
+    full = torch.stack([xd.sum(1), (xd * xd).sum(1)], dim=-1)
     if st.shape[0] > 1:
-        st[0], st[1] = full * 0.25, full * 0.75
+        st[0], st[1] = ops.stats_encode(full * 0.25), ops.stats_encode(full * 0.75)
     else:
-        st[0] = full
+        st[0] = ops.stats_encode(full)
     gamma, beta = rnd(c, seed=3) + 1, rnd(c, seed=4)
     ss = torch.zeros(b, c, 2, device=DEV)
     ops.gn_finalize(st, b, hw, gamma, beta, ss, eps=1e-6, groups=groups).run()
@@ -775,3 +743,47 @@ def test_gn_finalize_scale_shift_table():
     ref = F.group_norm(x.permute(0, 2, 1).reshape(b, c, hw, 1), groups, gamma, beta, eps=1e-6).reshape(b, c, hw).permute(0, 2, 1)
     got = x * ss[:, None, :, 0] + ss[:, None, :, 1]
     assert rel_l2(got, ref) < 1e-5
+
+
+@pytest.mark.parametrize("kind", ["conv", "conv_pair", "swapped", "token"])
+def test_channel_stats_are_bit_reproducible_and_batch_position_independent(kind):
+    """The GroupNorm statistics are integer fixed-point atomics over image-aligned tiles: two runs give the same BITS,
+    and an image's cells do not depend on where it sits in the batch (the reference evaluation is deterministic)."""
+    ops, L = _ops()
+    if kind == "token":
+        b, rpi, n, k = 5, 300, 320, 640
+        a = rnd(b, rpi, k, seed=1).to(H16())
+        wt = rnd(n, k, scale=k ** -0.5, seed=2).to(H16())
+
+        def run(order):
+            x = a[order].reshape(b * rpi, k).contiguous()
+            st = ops.new_stats(b, n, DEV)
+            out = torch.empty(b * rpi, n, device=DEV, dtype=H16())
+            ops.gemm(x, wt, out_bf16=out, stats=st, stats_rows_per_image=rpi).run()
+            torch.cuda.synchronize()
+            return st.sum(0), out.reshape(b, rpi, n)
+    else:
+        b, h, w, cin, cout = {"conv": (5, 15, 20, 320, 320), "conv_pair": (7, 30, 40, 256, 512),
+                              "swapped": (5, 120, 160, 128, 128)}[kind]
+        x = rnd(b, h, w, cin, seed=1).to(H16())
+        wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=2).to(H16())
+        wmat = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()
+
+        def run(order):
+            st = ops.new_stats(b, cout, DEV)
+            out = torch.empty(b * h * w, cout, device=DEV, dtype=H16())
+            op = ops.conv3x3(_pad_layout(x[order]), wmat, b, h, w, out_bf16=out, stats=st, stats_rows_per_image=h * w)
+            if kind == "swapped":
+                assert op.struct.cta_group == 3
+            if kind == "conv_pair":
+                assert op.struct.cta_group == 2
+            op.run()
+            torch.cuda.synchronize()
+            return st.sum(0), out.reshape(b, h * w, cout)
+    ident = list(range(b))
+    perm = ident[1:] + ident[:1]
+    s0, o0 = run(ident)
+    s1, o1 = run(ident)
+    assert torch.equal(s0, s1) and torch.equal(o0, o1)
+    sp, op_ = run(perm)
+    assert torch.equal(sp, s0[perm]) and torch.equal(op_, o0[perm])

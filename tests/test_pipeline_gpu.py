@@ -140,29 +140,33 @@ def test_other_benchmark_resolutions_vs_gpu_oracle(H, W, multi):
     check_against(eng, rgb, nxt, clipped, maps["semantic"], f"SD-2 {'multi' if multi else 'single'}-stream {H}x{W} vs fp32 oracle on GPU")
 
 
-def test_repeated_calls_and_batch_change_are_consistent():
-    """CUDA-graph replay (third call on) and a second plan for another batch size agree with the eager first call, and
-    an image's maps do not depend on what else is in the batch.  Agreement is NOT bitwise: the GroupNorm sums are
-    accumulated with fp32 atomics whose order varies from run to run (~1e-7), a few 16-bit roundings flip, and the
-    random-init network amplifies that by ~1.5-2x per layer (scripts/debug_repeat2.py) -- the same mechanism that sets
-    the distance to the fp32 oracle.  So the bound here is the parity tolerance itself."""
+def test_repeated_calls_are_bitwise_identical_and_batch_position_independent():
+    """The reference evaluation is deterministic; so is the engine: the eager first call, the captured second and the
+    replayed CUDA-graph calls give the same BITS (GroupNorm statistics are integer fixed-point atomics, everything
+    else has a fixed reduction order), and an image's maps do not depend on where it sits in the batch (image-aligned
+    tiles).  A different batch SIZE may pick other tile shapes: that comparison keeps the parity tolerance."""
     from stablemtl_b200 import synth
     eng, _ = build_engine(synth.TINY_UNET, synth.TINY_VAE, True)
     rgb, nxt = synth.make_images(3, 64, 96, seed=9)
-    first = {t: v.clone() for t, v in eng.predict(rgb.cuda(), nxt.cuda()).items()}
-    for _ in range(3):
-        again = eng.predict(rgb.cuda(), nxt.cuda())
+    runs = []
+    for _ in range(4):                                   # eager, capture, replay, replay
+        r = eng.predict(rgb.cuda(), nxt.cuda())
+        torch.cuda.synchronize()
+        runs.append(({t: v.clone() for t, v in r.items()}, {t: v.clone() for t, v in eng.last.items()}))
+    for post, clipped in runs[1:]:
+        for t in synth.TASKS:
+            assert torch.equal(post[t], runs[0][0][t]), t
+            assert torch.equal(clipped[t], runs[0][1][t]), t
+    perm = [2, 0, 1]
+    r = eng.predict(rgb[perm].cuda(), nxt[perm].cuda())
     torch.cuda.synchronize()
     for t in synth.TASKS:
-        if t == "semantic":
-            assert (again[t] == first[t]).float().mean() > 0.99
-        else:
-            assert rel_l2(again[t], first[t]) < REL_L2_TOL, t
+        assert torch.equal(r[t], runs[0][0][t][perm]), t
     one = eng.predict(rgb[1:2].cuda(), nxt[1:2].cuda())
     torch.cuda.synchronize()
     for t in synth.TASKS:
         if t != "semantic":
-            assert rel_l2(one[t][0], first[t][1]) < REL_L2_TOL, t
+            assert rel_l2(one[t][0], runs[0][0][t][1]) < REL_L2_TOL, t
 
 
 def test_dropin_pipeline_call_surface():
@@ -207,10 +211,7 @@ def test_batched_evaluator_matches_direct_predict_and_device_metrics():
     for i in range(3):
         for t in synth.TASKS:
             a, b = torch.as_tensor(got[i][t]), direct[i][t].cpu()
-            if t == "semantic":
-                assert (a == b).float().mean() > 0.99
-            else:
-                assert rel_l2(a, b) < REL_L2_TOL, (i, t)          # run-to-run bound of the engine (atomics order)
+            assert torch.equal(a, b), (i, t)                      # the engine is bit-reproducible
     # device-side reductions on maps that never leave the GPU
     dm = DeviceMetrics("cuda", 8)
     gen = torch.Generator().manual_seed(3)
