@@ -100,7 +100,7 @@ typedef struct smtl_gemm_args {
     int32_t res_fmt16;  /* 0: res1/res2 are fp32; 1: they are 16-bit (fmt16), same leading dim ldres */
     /* Fused GroupNorm statistics of the OUTPUT (the input of the next GroupNorm, src/model/resnet.py:177,188):
      * stats is int64 [stats_replicas, stats_images, n_out, 4]: per-(image, channel) sum and sum of squares of the
-     * final value (after residual adds) as FIXED-POINT cells (sum_lo, sum_hi, sq_lo, sq_hi; value = lo * 2^-35 +
+     * final value (after residual adds) as FIXED-POINT cells (sum_lo, sum_hi, sq_lo, sq_hi; value = lo * 2^-32 +
      * hi * 2^-8), accumulated with integer atomic adds -- exact and order-independent, so the statistics and
      * everything downstream are bit-reproducible.  The caller zeroes it first (smtl_memset_run).
      * image = output row / stats_rows_per_image; m must be stats_images whole images (M tiles restart at every
@@ -115,6 +115,11 @@ typedef struct smtl_gemm_args {
      * [g * group_rows, (g+1) * group_rows) use weight rows [g * n, (g+1) * n) of b (stacked [groups * n, k]) and bias
      * [g * n, (g+1) * n).  group_rows must be a multiple of 128 (256 for cta_group 2); 0 = off. */
     int64_t group_rows;
+    /* Tile order of the persistent CTAs: 0 = auto; 1 = round robin, column tile fastest; 2 = every CTA a contiguous run of
+     * the column-tile-major order (auto picks 2 for statistics producers: their per-column sums stay on chip for a whole
+     * (image, column tile) run and reach `stats` as one atomic per cell). */
+    int32_t tile_order;
+    int32_t pad_;
 } smtl_gemm_args;
 
 typedef struct smtl_gemm_op {
@@ -330,10 +335,24 @@ int smtl_im2col_run(const smtl_im2col_args* a, void* stream);
 typedef struct smtl_rgbprep_args {
     const void* rgb_nchw;   /* float32 or uint8 [batch, 3, h, w] in [0,255] */
     int32_t batch, h, w;
-    int32_t src_u8;         /* 1: rgb_nchw is uint8 */
+    int32_t src_u8;         /* 0: float32 in [0,255]; 1: uint8; 2: float32 already in [-1,1] (encode_rgb's argument,
+                             * src/stablemtl_pipeline.py:607: layout change only) */
     float* out_nhwc;
 } smtl_rgbprep_args;
 int smtl_rgbprep_run(const smtl_rgbprep_args* a, void* stream);
+
+/* The same normalisation fused with the im2col of the VAE encoder's 3-channel stem conv (diffusers Encoder.conv_in,
+ * reached from src/stablemtl_pipeline.py:619): out is the 16-bit GEMM operand [batch*h*w, 64], k = (ky*3 + kx)*3 + channel
+ * for k < 27 (pad 1, zero outside the image), zero for k >= 27. */
+typedef struct smtl_rgbstem_args {
+    const void* rgb_nchw;   /* [batch, 3, h, w] */
+    int32_t batch, h, w;
+    int32_t src_mode;       /* as smtl_rgbprep_args.src_u8: 0 float32 [0,255], 1 uint8, 2 float32 already in [-1,1] */
+    void* out_bf16;
+    int32_t fmt16;
+    int32_t pad_;
+} smtl_rgbstem_args;
+int smtl_rgbstem_run(const smtl_rgbstem_args* a, void* stream);
 
 /* UNet input assembly (src/stablemtl_pipeline.py:431-450,557-558,582-584): row group g of the output takes its
  * first 4 channels from latent image first_img[g*images + i], the next 4 from second_img[...], last 4 = 0. */
@@ -424,7 +443,7 @@ enum {
     SMTL_OP_GEMM = 1, SMTL_OP_FATTN = 2, SMTL_OP_SOFTMAX = 3, SMTL_OP_XATTN = 4, SMTL_OP_TASKATTN = 5,
     /* 6 retired (first-generation two-pass GroupNorm) */ SMTL_OP_LN = 7, SMTL_OP_UPSAMPLE = 8, SMTL_OP_IM2COL = 9, SMTL_OP_RGBPREP = 10,
     SMTL_OP_UNETIN = 11, SMTL_OP_TASKMAP = 12, SMTL_OP_CHANMIX = 13, SMTL_OP_GNAPPLY = 14, SMTL_OP_MEMSET = 15,
-    SMTL_OP_GNFINALIZE = 16, SMTL_OP_LSQSUMS = 17, SMTL_OP_CONFUSION = 18
+    SMTL_OP_GNFINALIZE = 16, SMTL_OP_LSQSUMS = 17, SMTL_OP_CONFUSION = 18, SMTL_OP_RGBSTEM = 19
 };
 typedef struct smtl_op_ref {
     int32_t kind;

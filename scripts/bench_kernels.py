@@ -51,15 +51,15 @@ def gemm_case(name, m, n, k, **kw):
     report(f"gemm {name} m={m} n={n} k={k}", ops.gemm(a, b, out_f32=out, **kw))
 
 
-def conv_case(name, batch, h, w, cin, cout, **kw):
+def conv_case(name, batch, h, w, cin, cout, stats=True, **kw):
     """the in-pipeline form: 16-bit output + fused GroupNorm statistics"""
     a = rb(batch * (h + 2) * (w + 2), cin)
     wm = rb(cout, 9 * cin)
     out = torch.empty(batch * h * w, cout, device=DEV, dtype=ops.h16())
     bias = torch.zeros(cout, device=DEV)
-    st = ops.new_stats(batch, cout, DEV)
+    skw = dict(stats=ops.new_stats(batch, cout, DEV, replicas=max(1, min(8, 64 // batch))), stats_rows_per_image=h * w) if stats else {}
     report(f"conv3x3 {name} b={batch} {h}x{w} {cin}->{cout}",
-           ops.conv3x3(a, wm, batch, h, w, bias=bias, out_bf16=out, stats=st, stats_rows_per_image=h * w, **kw))
+           ops.conv3x3(a, wm, batch, h, w, bias=bias, out_bf16=out, **skw, **kw))
 
 
 def attn_case(batch, ntok, heads):
@@ -89,6 +89,14 @@ if __name__ == "__main__":
     if only == "head":
         a = rb(8 * 482 * 642, 128); wm = rb(3, 9 * 128); out = torch.empty(8 * 480 * 640, 3, device=DEV)
         report("conv3x3 vae head b=8 480x640 128->3", ops.conv3x3(a, wm, 8, 480, 640, bias=torch.zeros(3, device=DEV), out_f32=out))
+        sys.exit(0)
+    if only == "stats":        # what the fused GroupNorm statistics cost, and the tile order that carries them
+        for args in [("unet L0", 112, 60, 80, 320, 320), ("unet L1", 112, 30, 40, 640, 640), ("unet L2", 112, 15, 20, 1280, 1280),
+                     ("vae 1/2", 16, 240, 320, 256, 256), ("vae 1/4", 16, 120, 160, 512, 512), ("vae 1/1 swapped", 16, 480, 640, 128, 128)]:
+            conv_case(args[0] + " no stats", *args[1:], stats=False)
+            conv_case(args[0] + " no stats contiguous", *args[1:], stats=False, tile_order=2)
+            conv_case(args[0] + " stats round-robin", *args[1:], tile_order=1)
+            conv_case(args[0] + " stats contiguous", *args[1:], tile_order=2)
         sys.exit(0)
     if only == "stages":
         conv_case("vae 1/4 512->512", 8, 120, 160, 512, 512)

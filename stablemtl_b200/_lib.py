@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libstablemtl_sm100.so")
 
 MAX_SEG = 12
 MAX_TASKS = 8
+MAX_XATTN_TOKENS = 4
 
 ACT_NONE, ACT_GELU, ACT_GEGLU, ACT_SILU = 0, 1, 2, 3
 (ROWMAP_IDENTITY, ROWMAP_CONV_PAD, ROWMAP_CONV_PAD_UP2, ROWMAP_PAD_KEEP, ROWMAP_TO_PAD,
@@ -19,7 +20,7 @@ ACT_NONE, ACT_GELU, ACT_GEGLU, ACT_SILU = 0, 1, 2, 3
 FMT_BF16, FMT_F16 = 0, 1
 MAP_MEAN1, MAP_RGB3, MAP_NORMAL, MAP_FLOW2, MAP_FLOW3, MAP_SEMANTIC = range(6)
 (OP_GEMM, OP_FATTN, OP_SOFTMAX, OP_XATTN, OP_TASKATTN, _OP_RETIRED6, OP_LN, OP_UPSAMPLE, OP_IM2COL, OP_RGBPREP,
- OP_UNETIN, OP_TASKMAP, OP_CHANMIX, OP_GNAPPLY, OP_MEMSET, OP_GNFINALIZE, OP_LSQSUMS, OP_CONFUSION) = range(1, 19)
+ OP_UNETIN, OP_TASKMAP, OP_CHANMIX, OP_GNAPPLY, OP_MEMSET, OP_GNFINALIZE, OP_LSQSUMS, OP_CONFUSION, OP_RGBSTEM) = range(1, 20)
 
 vp = C.c_void_p
 i32 = C.c_int32
@@ -55,6 +56,7 @@ class GemmArgs(C.Structure):
         ("stats_rows_per_image", i32), ("stats_images", i32),
         ("cta_group", i32), ("up_parity", i32),
         ("group_rows", i64),
+        ("tile_order", i32), ("pad_", i32),
     ]
 
 
@@ -153,6 +155,11 @@ class RgbprepArgs(C.Structure):
     _fields_ = [("rgb_nchw", vp), ("batch", i32), ("h", i32), ("w", i32), ("src_u8", i32), ("out_nhwc", vp)]
 
 
+class RgbstemArgs(C.Structure):
+    _fields_ = [("rgb_nchw", vp), ("batch", i32), ("h", i32), ("w", i32), ("src_mode", i32), ("out_bf16", vp),
+                ("fmt16", i32), ("pad_", i32)]
+
+
 class UnetinArgs(C.Structure):
     _fields_ = [("latents", vp), ("first_img", vp), ("second_img", vp), ("out_images", i32), ("hw", i32),
                 ("out", vp)]
@@ -181,11 +188,11 @@ class OpRef(C.Structure):
 
 
 STRUCTS_IN_HEADER_ORDER = [GemmSeg, GemmArgs, GemmOp, FattnArgs, FattnOp, SoftmaxArgs, XattnArgs, TaskAttnArgs,
-                           GnApplyArgs, GnFinalizeArgs, MemsetArgs, LnArgs, UpsampleArgs, Im2colArgs, RgbprepArgs, UnetinArgs, ChanmixArgs, TaskmapArgs, LsqSumsArgs, ConfusionArgs, OpRef]
+                           GnApplyArgs, GnFinalizeArgs, MemsetArgs, LnArgs, UpsampleArgs, Im2colArgs, RgbprepArgs, RgbstemArgs, UnetinArgs, ChanmixArgs, TaskmapArgs, LsqSumsArgs, ConfusionArgs, OpRef]
 
 EXPORTS = [
     "smtl_gemm_plan", "smtl_gemm_run", "smtl_fattn_plan", "smtl_fattn_run", "smtl_softmax_run", "smtl_xattn_run",
-    "smtl_taskattn_run", "smtl_gnapply_run", "smtl_gnfinalize_run", "smtl_memset_run", "smtl_ln_run", "smtl_upsample_run", "smtl_im2col_run", "smtl_rgbprep_run",
+    "smtl_taskattn_run", "smtl_gnapply_run", "smtl_gnfinalize_run", "smtl_memset_run", "smtl_ln_run", "smtl_upsample_run", "smtl_im2col_run", "smtl_rgbprep_run", "smtl_rgbstem_run",
     "smtl_unetin_run", "smtl_chanmix_run", "smtl_taskmap_run", "smtl_lsqsums_run", "smtl_confusion_run", "smtl_run_plan", "smtl_plan_launches", "smtl_abi_version",
     "smtl_last_error", "smtl_struct_sizes",
 ]

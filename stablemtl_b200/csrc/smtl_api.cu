@@ -2,6 +2,8 @@
 // dependency, so the library loads on a CPU-only host), struct-size self-check and the native plan runner.
 #include "smtl_host.h"
 
+#include <mutex>
+
 namespace smtl_host {
 
 static thread_local char g_err[512] = "";
@@ -20,15 +22,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 static EncodeTiledFn get_encode_fn() {
     static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static std::once_flag once;
+    std::call_once(once, [] {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult qres;
         cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
         if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
         else (void)cudaGetLastError();
-    }
+    });
     return fn;
 }
 
@@ -63,13 +64,23 @@ int encode_tmap_bf16_2d(uint64_t out[16], const void* base, uint64_t rows, uint6
 }
 
 int num_sms() {
-    static int n = 0;
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    const bool cached = dev >= 0 && dev < 64;
+    int n = cached ? cache[dev].load(std::memory_order_relaxed) : 0;
     if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        if (cached) cache[dev].store(n, std::memory_order_relaxed);
     }
     return n;
+}
+
+bool first_use_on_device(std::atomic<uint64_t>& mask) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;     // unknown: always (re)apply
+    const uint64_t bit = 1ull << dev;
+    return (mask.fetch_or(bit, std::memory_order_acq_rel) & bit) == 0;
 }
 
 }  // namespace smtl_host
@@ -86,7 +97,7 @@ int smtl_struct_sizes(int32_t* out, int32_t cap) {
         (int32_t)sizeof(smtl_xattn_args),   (int32_t)sizeof(smtl_taskattn_args),
         (int32_t)sizeof(smtl_gnapply_args), (int32_t)sizeof(smtl_gnfinalize_args), (int32_t)sizeof(smtl_memset_args),
         (int32_t)sizeof(smtl_ln_args),      (int32_t)sizeof(smtl_upsample_args), (int32_t)sizeof(smtl_im2col_args),
-        (int32_t)sizeof(smtl_rgbprep_args), (int32_t)sizeof(smtl_unetin_args),  (int32_t)sizeof(smtl_chanmix_args),
+        (int32_t)sizeof(smtl_rgbprep_args), (int32_t)sizeof(smtl_rgbstem_args), (int32_t)sizeof(smtl_unetin_args),  (int32_t)sizeof(smtl_chanmix_args),
         (int32_t)sizeof(smtl_taskmap_args), (int32_t)sizeof(smtl_lsqsums_args), (int32_t)sizeof(smtl_confusion_args),
         (int32_t)sizeof(smtl_op_ref)};
     const int n = (int)(sizeof(sizes) / sizeof(sizes[0]));
@@ -123,6 +134,7 @@ int smtl_run_plan(const smtl_op_ref* ops, int32_t n_ops, void* stream) {
             case SMTL_OP_GNFINALIZE: rc = smtl_gnfinalize_run((const smtl_gnfinalize_args*)p, stream); break;
             case SMTL_OP_LSQSUMS: rc = smtl_lsqsums_run((const smtl_lsqsums_args*)p, stream); break;
             case SMTL_OP_CONFUSION: rc = smtl_confusion_run((const smtl_confusion_args*)p, stream); break;
+            case SMTL_OP_RGBSTEM: rc = smtl_rgbstem_run((const smtl_rgbstem_args*)p, stream); break;
             default:
                 smtl_host::set_error("plan op %d: unknown kind %d", i, ops[i].kind);
                 return SMTL_EKIND;

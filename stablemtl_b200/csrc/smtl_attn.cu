@@ -4,7 +4,6 @@
 // The kernel (smtl_fattn2_kernel) is described where it is defined.
 #include "smtl_common.cuh"
 #include "smtl_host.h"
-#include <stdlib.h>
 
 namespace {
 using namespace smtl;
@@ -300,12 +299,10 @@ extern "C" int smtl_fattn_plan(const smtl_fattn_args* a, smtl_fattn_op* op) {
 
 extern "C" int smtl_fattn_run(const smtl_fattn_op* op, void* stream) {
     SMTL_CHECK_ARG(op, "fattn_run: NULL op");
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<uint64_t> attr_devs{0};
+    if (smtl_host::first_use_on_device(attr_devs))
         SMTL_CHECK_CUDA(
             cudaFuncSetAttribute(smtl_fattn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
-        attr_set = true;
-    }
     const smtl_fattn_args& a = op->args;
     FattnKParams kp;
     memcpy(&kp.tm, op->tmap_qkv, 128);

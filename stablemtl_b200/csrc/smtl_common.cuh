@@ -344,11 +344,14 @@ __device__ __forceinline__ uint16_t to16(float x, int fmt) {
 
 // ----------------------------------------------------------------------------- deterministic channel statistics
 // A GroupNorm statistics cell is FOUR int64 fixed-point accumulators (sum_lo, sum_hi, sq_lo, sq_hi): a partial sum p goes,
-// exactly, into the fine accumulator (scale 2^35, |p| < 2^14) or the coarse one (scale 2^8).  Integer addition is
+// exactly, into the fine accumulator (scale 2^32, |p| < 2^12) or the coarse one (scale 2^8).  Integer addition is
 // associative, so the atomics of the producing GEMM's CTAs give the same bits in whatever order they land (fp32
 // atomicAdd did not: run-to-run differences of ~1e-7 that the network amplified to the parity tolerance).
-constexpr float STATS_LO_LIMIT = 16384.0f;           // 2^14
-constexpr float STATS_LO_SCALE = 34359738368.0f;     // 2^35
+// Range: a cell receives at most rows_per_image / 32 partials (9600 at 480x640, full resolution); fine partials are
+// < 2^44 and coarse ones (32 rows of x^2, |x| <= 65504) < 2^45, so a cell stays below 2^63 up to 2^18 partials.
+// Consumers convert each CELL to double before they add cells up (a group's total need not fit an int64).
+constexpr float STATS_LO_LIMIT = 4096.0f;            // 2^12
+constexpr float STATS_LO_SCALE = 4294967296.0f;      // 2^32
 constexpr float STATS_HI_SCALE = 256.0f;             // 2^8
 __device__ __forceinline__ long long stats_fix(float p, bool& hi) {
     hi = !(fabsf(p) < STATS_LO_LIMIT);
@@ -362,7 +365,7 @@ __device__ __forceinline__ void stats_atomic_add(unsigned long long* cell, float
     atomicAdd(cell + (hi ? 3 : 2), (unsigned long long)v);
 }
 __device__ __forceinline__ double stats_value(long long lo, long long hi) {
-    return (double)lo * (1.0 / 34359738368.0) + (double)hi * (1.0 / 256.0);
+    return (double)lo * (1.0 / 4294967296.0) + (double)hi * (1.0 / 256.0);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -34,9 +34,9 @@ __device__ __forceinline__ uint4 load8_as16(const void* base, int64_t idx, int i
 }
 
 // ============================================================================================= GroupNorm
-// Group mean / rstd of image `b` from the producers' int64 fixed-point cells (smtl_common.cuh): a warp per group sums
-// the cells of the group's channels (both sources of a virtual concat, every replica) as INTEGERS -- exact, so the
-// result does not depend on how the producer's atomics were ordered -- and converts once, in double.
+// Group mean / rstd of image `b` from the producers' int64 fixed-point cells (smtl_common.cuh): the cells are exact
+// whatever the order of the producer's atomics was; a warp per group converts each cell to double and adds them up in
+// a FIXED order (lane-strided loop, then the xor tree), so the result is bit-reproducible.
 __device__ __forceinline__ void gn_group_stats(const long long* __restrict__ st0, const long long* __restrict__ st1,
                                                int c0, int c1, int replicas, int batch, int b, int groups, double n,
                                                float eps, float* gmean, float* grstd) {
@@ -45,25 +45,24 @@ __device__ __forceinline__ void gn_group_stats(const long long* __restrict__ st0
     const int ncell = cpg * replicas;
     if (warp < nwarps) {
         for (int g = warp; g < groups; g += nwarps) {
-            long long a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+            double a0 = 0.0, a2 = 0.0;
             for (int i = lane; i < ncell; i += 32) {
                 const int r = i / cpg, c = g * cpg + (i - r * cpg);
                 const long long* st = (c < c0) ? st0 + (((int64_t)r * batch + b) * c0 + c) * 4
                                                : st1 + (((int64_t)r * batch + b) * c1 + (c - c0)) * 4;
                 const longlong2 u = __ldg(reinterpret_cast<const longlong2*>(st));
                 const longlong2 v = __ldg(reinterpret_cast<const longlong2*>(st + 2));
-                a0 += u.x; a1 += u.y; a2 += v.x; a3 += v.y;
+                a0 += stats_value(u.x, u.y);
+                a2 += stats_value(v.x, v.y);
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-                a1 += __shfl_xor_sync(0xffffffffu, a1, o);
                 a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-                a3 += __shfl_xor_sync(0xffffffffu, a3, o);
             }
             if (lane == 0) {
-                const double mean = stats_value(a0, a1) / n;
-                double var = stats_value(a2, a3) / n - mean * mean;
+                const double mean = a0 / n;
+                double var = a2 / n - mean * mean;
                 if (var < 0.0) var = 0.0;
                 gmean[g] = (float)mean;
                 grstd[g] = (float)(1.0 / sqrt(var + (double)eps));
@@ -384,9 +383,51 @@ __global__ void rgbprep_kernel(const void* __restrict__ rgbv, int src_u8, int ba
         const int64_t b = idx / hw, p = idx - b * hw;
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
-            const float v = src_u8 ? (float)__ldg(rgb8 + (b * 3 + ch) * hw + p) : __ldg(rgb + (b * 3 + ch) * hw + p);
-            out[idx * 3 + ch] = v / 255.0f * 2.0f - 1.0f;   // same op order as stablemtl_pipeline.py:263
+            const float v = (src_u8 == 1) ? (float)__ldg(rgb8 + (b * 3 + ch) * hw + p) : __ldg(rgb + (b * 3 + ch) * hw + p);
+            out[idx * 3 + ch] = (src_u8 == 2) ? v : v / 255.0f * 2.0f - 1.0f;   // same op order as stablemtl_pipeline.py:263
         }
+    }
+}
+
+// Stem of the VAE encoder (3 -> C conv, diffusers Encoder.conv_in): [0,255] NCHW rgb -> the 16-bit im2col operand
+// [batch*h*w, 64] (k = tap * 3 + channel for the 27 taps x channels, zero fill to 64) in ONE pass: a thread owns one
+// pixel, reads its 3x3 neighbourhood from the three planes (neighbouring threads share the loads through L1),
+// normalises (stablemtl_pipeline.py:263) and writes 128 contiguous bytes.
+__global__ void __launch_bounds__(256) rgb_stem_kernel(const void* __restrict__ rgbv, int src_mode, int batch, int h, int w,
+                                                       uint16_t* __restrict__ out, int fmt) {
+    const float* rgb = reinterpret_cast<const float*>(rgbv);
+    const uint8_t* rgb8 = reinterpret_cast<const uint8_t*>(rgbv);
+    const int64_t hw = (int64_t)h * w;
+    const int64_t total = (int64_t)batch * hw;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = idx / hw;
+        const int p = (int)(idx - b * hw);
+        const int y = p / w, x = p - y * w;
+        float v[28];
+        v[27] = 0.f;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int iy = y + tap / 3 - 1, ix = x + tap % 3 - 1;
+            const bool in = iy >= 0 && iy < h && ix >= 0 && ix < w;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                float t = 0.f;
+                if (in) {
+                    const int64_t o = (b * 3 + ch) * hw + (int64_t)iy * w + ix;
+                    const float raw = (src_mode == 1) ? (float)__ldg(rgb8 + o) : __ldg(rgb + o);
+                    t = (src_mode == 2) ? raw : raw / 255.0f * 2.0f - 1.0f;
+                }
+                v[tap * 3 + ch] = t;
+            }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(out + idx * 64);
+        dst[0] = make_uint4(pack16x2(v[0], v[1], fmt), pack16x2(v[2], v[3], fmt), pack16x2(v[4], v[5], fmt), pack16x2(v[6], v[7], fmt));
+        dst[1] = make_uint4(pack16x2(v[8], v[9], fmt), pack16x2(v[10], v[11], fmt), pack16x2(v[12], v[13], fmt), pack16x2(v[14], v[15], fmt));
+        dst[2] = make_uint4(pack16x2(v[16], v[17], fmt), pack16x2(v[18], v[19], fmt), pack16x2(v[20], v[21], fmt), pack16x2(v[22], v[23], fmt));
+        dst[3] = make_uint4(pack16x2(v[24], v[25], fmt), pack16x2(v[26], v[27], fmt), 0u, 0u);
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        dst[4] = z; dst[5] = z; dst[6] = z; dst[7] = z;
     }
 }
 
@@ -887,6 +928,16 @@ extern "C" int smtl_rgbprep_run(const smtl_rgbprep_args* a, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int64_t total = (int64_t)a->batch * a->h * a->w;
     rgbprep_kernel<<<grid_for(total, 256), 256, 0, st>>>(a->rgb_nchw, a->src_u8, a->batch, a->h * a->w, a->out_nhwc);
+    SMTL_CHECK_CUDA(cudaGetLastError());
+    return SMTL_OK;
+}
+
+extern "C" int smtl_rgbstem_run(const smtl_rgbstem_args* a, void* stream) {
+    SMTL_CHECK_ARG(a && a->rgb_nchw && a->out_bf16, "rgbstem: NULL argument");
+    SMTL_CHECK_ARG(a->batch > 0 && a->h > 0 && a->w > 0 && a->src_mode >= 0 && a->src_mode <= 2, "rgbstem: bad extent / mode");
+    const int64_t total = (int64_t)a->batch * a->h * a->w;
+    rgb_stem_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        a->rgb_nchw, a->src_mode, a->batch, a->h, a->w, reinterpret_cast<uint16_t*>(a->out_bf16), a->fmt16);
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;
 }

@@ -12,7 +12,6 @@
 // 1x1 shortcut conv (src/model/resnet.py:172,200).
 #include "smtl_common.cuh"
 #include "smtl_host.h"
-#include <stdlib.h>
 
 namespace {
 
@@ -25,6 +24,10 @@ constexpr int NUM_THREADS = 320;                   // TMA warp + MMA warp + 8 ep
 constexpr int EPI_WARPS = 8;
 constexpr int SMEM_BUDGET = 227 * 1024;
 constexpr int GEMM_MAX_STAGES = 24;
+// Statistics producers keep their per-column sums in shared memory across the tiles of one (image, column tile) run:
+// [epilogue warp][32-column chunk of the warp][lane = column] x (sum, sum of squares) as int64 fixed point (fine cells).
+constexpr int STATS_NCH = 4;                                       // chunks per warp: BN <= 256, two warps per lane quarter
+constexpr int STATS_SMEM = EPI_WARPS * STATS_NCH * 32 * 2 * 8;     // 16 KB
 // Shift-grouped mainloop: k-blocks per ring stage.  One barrier round trip (wait / expect_tx / TMA issue on one side, wait /
 // MMAs / commit on the other) costs ~550 clk whatever the tile; with two 64-wide k-blocks per stage it is paid per 128 K.
 constexpr int KPB = 2;
@@ -63,6 +66,11 @@ struct alignas(64) GemmKParams {
     // 32-row partial sums of an image are the same fp32 values wherever the image sits in the batch.
     int64_t tile_rpi;            // GEMM rows per image; 0 = tiles run over all rows
     int32_t tiles_per_img;
+    // Tile order.  0: tile = blockIdx + k * grid, column tile fastest.  1 (statistics producers): every CTA takes a
+    // CONTIGUOUS run of the column-tile-major order, i.e. a long strip of M tiles of one column tile, so the per-column
+    // sums stay in shared memory for a whole (image, column tile) run and reach global memory as one atomic per cell,
+    // not one per 32-row slice.  CTAs c and c + grid / tiles_n walk the same rows at the same time (L2 reuse of A).
+    int32_t tile_order;
     float* out_f32;
     uint16_t* out_bf16;
     uint16_t* aux_bf16;
@@ -260,7 +268,7 @@ __device__ __forceinline__ void add_residual(const GemmKParams& p, const void* r
 // tile; `tn` = N-tile index.  All tcgen05.ld / shuffles are warp-collective.
 template <int BN>
 __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t taddr, int tn, int lane, int half,
-                                              const EpiRow<BN>& e) {
+                                              const EpiRow<BN>& e, long long* stats_acc) {
     const bool geglu = (p.act == SMTL_ACT_GEGLU);
     const int out_bn = geglu ? BN / 2 : BN;
     const int n0 = tn * BN;
@@ -361,21 +369,28 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t tad
 #pragma unroll
         for (int k = 0; k + 2 < BN / 32; ++k) bq[k] = bq[k + 2];
         if (p.stats && e.img_lo <= e.img_hi) {
-            // per-(image, channel) sum / sum of squares of the stored value: lane j ends up owning column ocol + j
-            for (int img = e.img_lo; img <= e.img_hi; ++img) {       // warp-uniform; one iteration unless the
-                float s[32], q[32];                                    // warp's rows straddle an image boundary
-                const bool mine = (e.img == img);
+            // per-(image, channel) sum / sum of squares of the stored value: lane j ends up owning column ocol + j.
+            // Tiles are image-aligned (tile_rpi), so every valid row of the tile belongs to image e.img_lo.
+            float s[32], q[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float x = mine ? v[j] : 0.0f;
-                    s[j] = x;
-                    q[j] = x * x;
-                }
-                const float cs = warp_transpose_sum(s, lane);
-                const float cq = warp_transpose_sum(q, lane);
-                if (ocol + lane < p.n_out)
-                    stats_atomic_add(p.stats + (((int64_t)(blockIdx.x % p.stats_rep) * p.stats_images + img) * p.n_out +
-                                                ocol + lane) * 4, cs, cq);
+            for (int j = 0; j < 32; ++j) {
+                const float x = row_ok ? v[j] : 0.0f;
+                s[j] = x;
+                q[j] = x * x;
+            }
+            const float cs = warp_transpose_sum(s, lane);
+            const float cq = warp_transpose_sum(q, lane);
+            if (ocol + lane < p.n_out) {
+                // fine cells accumulate in this warp's shared-memory slots (flushed once per (image, column tile) run);
+                // a partial too large for the fine scale (|x| >= 2^14: rare) goes straight to its coarse global cell
+                long long* cell = stats_acc + ((c0 >> 6) * 32 + lane) * 2;
+                unsigned long long* gcell = p.stats + (((int64_t)(blockIdx.x % p.stats_rep) * p.stats_images + e.img_lo) *
+                                                           p.n_out + ocol + lane) * 4;
+                bool hi;
+                long long f = stats_fix(cs, hi);
+                if (hi) atomicAdd(gcell + 1, (unsigned long long)f); else cell[0] += f;
+                f = stats_fix(cq, hi);
+                if (hi) atomicAdd(gcell + 3, (unsigned long long)f); else cell[1] += f;
             }
         }
     }
@@ -437,8 +452,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
     const uint32_t tmem_base = *tmem_slot;
 
     const int num_tiles = p.tiles_m * p.tiles_n;     // tiles_m counts (128 * CG)-row blocks
-    const int tile0 = blockIdx.x / CG;
-    const int tile_step = gridDim.x / CG;
+    int tile_begin = blockIdx.x / CG, tile_end = num_tiles, tile_inc = gridDim.x / CG;
+    if (p.tile_order) {                              // contiguous run of the column-tile-major order
+        const int nslots = gridDim.x / CG, slot = blockIdx.x / CG;
+        tile_begin = (int)((int64_t)slot * num_tiles / nslots);
+        tile_end = (int)((int64_t)(slot + 1) * num_tiles / nslots);
+        tile_inc = 1;
+    }
+    auto decode_tile = [&](int tile, int& tm, int& tn) {
+        if (p.tile_order) { tn = tile / p.tiles_m; tm = tile - tn * p.tiles_m; }
+        else { tm = tile / p.tiles_n; tn = tile - tm * p.tiles_n; }
+    };
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -446,8 +470,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
         if (grouped) {
             int ps = 0, ws = 0;
             uint32_t pph = 0, wph = 0;
-            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-                const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+            for (int tile = tile_begin; tile < tile_end; tile += tile_inc) {
+                int tm, tn;
+                decode_tile(tile, tm, tn);
                 int64_t row0, row_end;
                 tile_span(p, tm, CG * BLOCK_M, row0, row_end);
                 const int64_t m0 = row0 + (int64_t)rank * BLOCK_M;
@@ -501,8 +526,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
         } else {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-                const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+            for (int tile = tile_begin; tile < tile_end; tile += tile_inc) {
+                int tm, tn;
+                decode_tile(tile, tm, tn);
                 int64_t row0, row_end;
                 tile_span(p, tm, CG * BLOCK_M, row0, row_end);
                 const int64_t m0 = row0 + (int64_t)rank * BLOCK_M;
@@ -547,7 +573,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
             int ps = 0, ws = 0;
             uint32_t pph = 0, wph = 0;
             int it = 0;
-            for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
+            for (int tile = tile_begin; tile < tile_end; tile += tile_inc, ++it) {
                 const int acc = it & 1;
                 mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1u);
                 tc_fence_after();
@@ -595,7 +621,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
+            for (int tile = tile_begin; tile < tile_end; tile += tile_inc, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(&acc_empty[acc], acc_phase ^ 1u);
@@ -635,19 +661,53 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;             // which of the quarter's two warps: alternate column chunks
         const int row_in_tile = quarter * 32 + lane;
+        // this warp's running column sums (see STATS_SMEM) and the (image, column tile) run they belong to
+        long long* stats_acc = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(bars) + 512) +
+                               (size_t)(warp - 2) * STATS_NCH * 32 * 2;
+        int run_img = -1, run_tn = -1;
+        if (p.stats) {
+#pragma unroll
+            for (int i = 0; i < STATS_NCH * 2; ++i) stats_acc[i * 32 + lane] = 0;
+            __syncwarp();
+        }
+        auto stats_flush = [&](int img, int tn) {
+            if (img < 0) return;
+#pragma unroll
+            for (int i = 0; i < STATS_NCH; ++i) {
+                const int col = tn * BN + half * 32 + 64 * i + lane;
+                long long* cell = stats_acc + (i * 32 + lane) * 2;
+                const long long fs = cell[0], fq = cell[1];
+                if (half * 32 + 64 * i < BN && col < p.n_out && (fs | fq)) {
+                    unsigned long long* g = p.stats + (((int64_t)(blockIdx.x % p.stats_rep) * p.stats_images + img) * p.n_out + col) * 4;
+                    atomicAdd(g, (unsigned long long)fs);
+                    atomicAdd(g + 2, (unsigned long long)fq);
+                }
+                cell[0] = 0;
+                cell[1] = 0;
+            }
+        };
         int it = 0;
-        for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
+        for (int tile = tile_begin; tile < tile_end; tile += tile_inc, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+            int tm, tn;
+            decode_tile(tile, tm, tn);
             EpiRow<BN> er;
             int64_t row0, row_end;
             tile_span(p, tm, CG * BLOCK_M, row0, row_end);
             epilogue_prepare<BN>(p, row0 + (int64_t)rank * BLOCK_M + row_in_tile, row_end, tn, lane, er);
+            if (p.stats) {                             // a new (image, column tile) run: flush the previous one's sums
+                const int img = tm / p.tiles_per_img;
+                if (img != run_img || tn != run_tn) {
+                    stats_flush(run_img, run_tn);
+                    run_img = img;
+                    run_tn = tn;
+                }
+            }
             mbar_wait_backoff(&acc_full[acc], acc_phase, 100);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
-            epilogue_rows<BN>(p, taddr, tn, lane, half, er);
+            epilogue_rows<BN>(p, taddr, tn, lane, half, er, stats_acc);
             // release this accumulator stage back to the (leader's) MMA warp
             tc_fence_before();
             __syncwarp();
@@ -656,6 +716,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
                 else mbar_arrive_cluster(mapa_u32(&acc_empty[acc], 0));
             }
         }
+        if (p.stats) stats_flush(run_img, run_tn);
     }
 
     tc_fence_before();
@@ -869,24 +930,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
         const bool piece_ok = cpiece + 8 <= p.n;
         // this thread's channel sums of the current image, exact: every 32-pixel chunk's fp32 partial is added in the
         // int64 fixed-point form of the statistics cells (smtl_common.cuh), so the order of the chunks does not matter
-        long long acc4[4] = {0, 0, 0, 0};
+        // (the fp32 partial of one TILE -- the same pixels wherever the image sits in the batch -- is what gets fixed)
+        long long acc_sl = 0, acc_sh = 0, acc_ql = 0, acc_qh = 0;
+        float tsum = 0.f, tsq = 0.f;                                  // this tile's running partial
         int cur_img = -1;
+        auto commit = [&]() {                                         // tile partial -> the int64 accumulators
+            bool hi;
+            long long v = stats_fix(tsum, hi);
+            if (hi) acc_sh += v; else acc_sl += v;
+            v = stats_fix(tsq, hi);
+            if (hi) acc_qh += v; else acc_ql += v;
+            tsum = 0.f;
+            tsq = 0.f;
+        };
         auto flush = [&]() {
             if (p.stats && cur_img >= 0 && ch_ok) {
                 unsigned long long* dst =
                     p.stats + (((int64_t)(blockIdx.x % p.stats_rep) * p.stats_images + cur_img) * p.n + ch) * 4;
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (acc4[i]) atomicAdd(dst + i, (unsigned long long)acc4[i]);
+                if (acc_sl) atomicAdd(dst, (unsigned long long)acc_sl);
+                if (acc_sh) atomicAdd(dst + 1, (unsigned long long)acc_sh);
+                if (acc_ql) atomicAdd(dst + 2, (unsigned long long)acc_ql);
+                if (acc_qh) atomicAdd(dst + 3, (unsigned long long)acc_qh);
             }
-            acc4[0] = acc4[1] = acc4[2] = acc4[3] = 0;
-        };
-        auto add_chunk = [&](float s, float q) {
-            bool hi;
-            long long v = stats_fix(s, hi);
-            acc4[hi ? 1 : 0] += v;
-            v = stats_fix(q, hi);
-            acc4[hi ? 3 : 2] += v;
+            acc_sl = acc_sh = acc_ql = acc_qh = 0;
         };
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -968,29 +1034,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
                         hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
                     }
                     if (lo == hi) {                                      // the usual case: one image in this chunk
-                        if (lo != cur_img) { flush(); cur_img = lo; }
-                        float ssum = 0.f, ssq = 0.f;
+                        if (lo != cur_img) { commit(); flush(); cur_img = lo; }
+                        if (okmask == 0xffffffffu) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if ((okmask >> j) & 1u) { ssum += v[j]; ssq += v[j] * v[j]; }
-                        add_chunk(ssum, ssq);
+                            for (int j = 0; j < 32; ++j) { tsum += v[j]; tsq = fmaf(v[j], v[j], tsq); }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if ((okmask >> j) & 1u) { tsum += v[j]; tsq = fmaf(v[j], v[j], tsq); }
+                        }
                     } else {
-                        float ssum = 0.f, ssq = 0.f;
                         for (int j = 0; j < 32; ++j) {                   // image boundary inside the chunk (tiles that are
                             const int im = __shfl_sync(0xffffffffu, img_l, j);   // not image-aligned only)
                             if ((okmask >> j) & 1u) {
-                                if (im != cur_img) { add_chunk(ssum, ssq); ssum = ssq = 0.f; flush(); cur_img = im; }
-                                ssum += v[j];
-                                ssq += v[j] * v[j];
+                                if (im != cur_img) { commit(); flush(); cur_img = im; }
+                                tsum += v[j];
+                                tsq = fmaf(v[j], v[j], tsq);
                             }
                         }
-                        add_chunk(ssum, ssq);
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[acc]);
+            if (p.stats) commit();
         }
         flush();
     }
@@ -1005,12 +1073,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
 
 template <int BN, int CG>
 int launch_gemm(const GemmKParams& kp, int grid, int smem_bytes, cudaStream_t stream) {
-    static bool attr_set = false;   // per-instantiation; benign race (idempotent)
-    if (!attr_set) {
+    static std::atomic<uint64_t> attr_devs{0};   // per instantiation, one bit per device ordinal
+    if (smtl_host::first_use_on_device(attr_devs))
         SMTL_CHECK_CUDA(cudaFuncSetAttribute(smtl_gemm_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              SMEM_BUDGET));
-        attr_set = true;
-    }
     if (CG == 1) {
         smtl_gemm_kernel<BN, CG><<<grid, NUM_THREADS, smem_bytes, stream>>>(kp);
     } else {
@@ -1100,6 +1166,7 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
         SMTL_CHECK_ARG(g.img_h > 0 && g.img_w > 0, "gemm_plan: conv row map needs img_h/img_w");
     SMTL_CHECK_ARG(g.rowmap >= SMTL_ROWMAP_IDENTITY && g.rowmap <= SMTL_ROWMAP_UP2_PAD, "gemm_plan: bad rowmap");
     SMTL_CHECK_ARG(g.up_parity >= 0 && g.up_parity <= 3, "gemm_plan: bad up_parity");
+    SMTL_CHECK_ARG(g.tile_order >= 0 && g.tile_order <= 2, "gemm_plan: bad tile_order");
     if (g.group_rows) {
         SMTL_CHECK_ARG(g.group_rows > 0 && g.group_rows % BLOCK_M == 0 && g.m % g.group_rows == 0,
                        "gemm_plan: group_rows %lld must divide m and be a multiple of %d", (long long)g.group_rows, BLOCK_M);
@@ -1125,6 +1192,7 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
                        (long long)g.m, g.stats_images, (long long)tile_rpi);
     }
     op->tile_rpi = tile_rpi;
+    const int stats_smem = g.stats ? STATS_SMEM : 0;   // running column sums of the epilogue warps (unused by the swapped kernel)
     auto count_tiles_m = [&](int tile_rows) {
         if (!tile_rpi) { op->tiles_per_img = 0; return (int)((g.m + tile_rows - 1) / tile_rows); }
         op->tiles_per_img = (int)((tile_rpi + tile_rows - 1) / tile_rows);
@@ -1134,8 +1202,7 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
     const int sms = smtl_host::num_sms();
     // ---- shift groups: consecutive-row-shift segments (kx = -1, 0, +1 of one ky) share one activation tile
     {
-        const char* env = getenv("SMTL_GEMM_GROUPED");
-        const bool allow = !(env && env[0] == '0');
+        const bool allow = true;
         int ng = 0, kb0 = 0;
         bool any = false;
         for (int si = 0; si < g.nseg;) {
@@ -1160,13 +1227,11 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
     }
     // swapped form (weights on the MMA's M side) for narrow outputs: N <= 128, plain 16-bit output
     {
-        const char* env = getenv("SMTL_GEMM_SWAP");
-        const bool allow = !(env && env[0] == '0');
         const bool eligible = g.group_rows == 0 && g.n <= 128 && g.n >= 64 && g.n % 8 == 0 && g.act == SMTL_ACT_NONE && !g.bias_per_row &&
                               g.out_bf16 && !g.out_f32 && !g.aux_bf16 && !g.res2 && (!g.res1 || g.res_fmt16 == 1) &&
                               (g.ldc % 8) == 0 && (!g.res1 || (g.ldres % 8) == 0) && g.block_n == 0 &&
                               g.cta_group == 0 && g.m >= (int64_t)sms * TBN;
-        if (allow && eligible) {
+        if (eligible) {
             op->cta_group = 3;                      // marks the swapped kernel
             op->block_n = TBN;
             op->tiles_m = count_tiles_m(TBN);
@@ -1209,17 +1274,18 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
     int cg = g.cta_group;
     if (cg == 0) {
         const long long tiles256 = (long long)count_tiles_m(2 * BLOCK_M) * (long long)((g.n + bn - 1) / bn);
-        const char* env = getenv("SMTL_GEMM_CG");
         // measured on B200 (scripts/bench_kernels.py gemm): pairs win on long plain-K GEMMs (8192^3: 1170 -> 1295
-        // TFLOP/s) and lose on the 9-segment implicit convs and on short-K linears, whose cost is the epilogue
-        cg = env ? atoi(env) : ((tiles256 >= sms / 2 && g.nseg == 1 && g.k >= 2048 && g.n >= 256) ? 2 : 1);
-        // shift-grouped convs with full-width tiles: pairs halve the weight traffic (L2 -> smem and smem -> MMA)
-        const char* envc = getenv("SMTL_GEMM_CG_CONV");
-        // measured (scripts/exp_pairs.py): +8 % at bn = 256, +2-3 % at bn = 160; SMTL_GEMM_CG_CONV=1 restricts to 256
-        const bool any_bn = !(envc && envc[0] == '1');
-        if (!env && op->grouped && (bn == 256 || (any_bn && bn % 16 == 0 && bn >= 128)) && tiles256 >= sms / 2 &&
-            !(envc && envc[0] == '0'))
-            cg = 2;
+        // TFLOP/s) and lose on short-K linears, whose cost is the epilogue
+        cg = (tiles256 >= sms / 2 && g.nseg == 1 && g.k >= 2048 && g.n >= 256) ? 2 : 1;
+        // shift-grouped convs: pairs halve the weight traffic (L2 -> smem and smem -> MMA): +8 % at bn = 256, +2-3 % at 160
+        if (op->grouped && bn % 16 == 0 && bn >= 128 && tiles256 >= sms / 2) cg = 2;
+        // image-aligned tiles (statistics producers): 256-row pair tiles pad a small map far more than 128-row tiles do
+        // (15x20: 374 padded rows = 2 x 256 but 3 x 128); the pair is worth ~5 % (measured), so it must not cost more
+        if (cg == 2 && tile_rpi) {
+            const double e2 = (double)tile_rpi / (double)(((tile_rpi + 255) / 256) * 256);
+            const double e1 = (double)tile_rpi / (double)(((tile_rpi + 127) / 128) * 128);
+            if (e2 * 1.05 < e1) cg = 1;
+        }
         if (g.group_rows) cg = 1;
     }
     SMTL_CHECK_ARG(cg == 1 || cg == 2, "gemm_plan: cta_group %d", cg);
@@ -1230,13 +1296,9 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
     op->tiles_n = (g.n + bn - 1) / bn;
     op->total_kblocks = total_kb;
     const int stage_bytes = A_STAGE_BYTES + (bn / cg) * BLOCK_K * 2;
-    int stages = (SMEM_BUDGET - 1024 - 512) / stage_bytes;
+    int stages = (SMEM_BUDGET - 1024 - 512 - stats_smem) / stage_bytes;
     if (stages > 8) stages = 8;
-    if (const char* env = getenv("SMTL_GEMM_MAX_STAGES")) {       // experiment knob: pipeline-depth sensitivity
-        const int cap = atoi(env);
-        if (cap >= 2 && stages > cap) stages = cap;
-    }
-    op->smem_bytes = 1024 + stages * stage_bytes + 512;
+    op->smem_bytes = 1024 + stages * stage_bytes + 512 + stats_smem;
     const int a_box_rows = op->grouped ? BLOCK_M + 8 : BLOCK_M;
     if (op->grouped) {
         const int pb = KPB * (BLOCK_M + 8) * BLOCK_K * 2, wb = KPB * (bn / cg) * BLOCK_K * 2;   // KPB k-blocks per stage
@@ -1245,25 +1307,22 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
         // or it, not the activation ring, sets the prefetch distance: a Cout = 3 conv (BN = 32, 36 clk per MMA) was
         // load-latency bound with 6 weight stages.
         const int sp_max = bn <= 64 ? 8 : 6;
-        op->sp = (SMEM_BUDGET - 1024 - 512 - 6 * wb) / pb;
+        const int budget = SMEM_BUDGET - 1024 - 512 - stats_smem;
+        op->sp = (budget - 6 * wb) / pb;
         if (op->sp < 3) op->sp = 3;
         if (op->sp > sp_max) op->sp = sp_max;
         // wide tiles: the weight ring is the critical stream (3 weight stages per activation stage), so it gets the
         // shared memory -- 2 activation stages + 4 weight stages beat 3 + 3 by 1-2 %, 4 + 2 loses 6 % (bn = 256 pairs)
         if (bn >= 128) op->sp = 2;
-        if (const char* envsp = getenv("SMTL_GEMM_SP")) {            // experiment knob: activation-ring depth
-            const int v = atoi(envsp);
-            if (v >= 2 && v <= sp_max) op->sp = v;
-        }
-        op->sw = (SMEM_BUDGET - 1024 - 512 - op->sp * pb) / wb;
+        op->sw = (budget - op->sp * pb) / wb;
         while (op->sw < 2 && op->sp > 2) {          // widest tiles in one CTA: trade an activation stage for a weight stage
             --op->sp;
-            op->sw = (SMEM_BUDGET - 1024 - 512 - op->sp * pb) / wb;
+            op->sw = (budget - op->sp * pb) / wb;
         }
         SMTL_CHECK_ARG(op->sw >= 1, "gemm_plan: no room for a weight stage (block_n %d)", bn);
         if (op->sw > 3 * op->sp) op->sw = 3 * op->sp;
         if (op->sw > GEMM_MAX_STAGES - op->sp) op->sw = GEMM_MAX_STAGES - op->sp;
-        op->smem_bytes = 1024 + op->sp * pb + op->sw * wb + 512;
+        op->smem_bytes = 1024 + op->sp * pb + op->sw * wb + 512 + stats_smem;
     }
     const long long tiles = (long long)op->tiles_m * op->tiles_n;
     const int slots = sms / cg;                     // CTAs (cg = 1) or CTA pairs (cg = 2) resident at once
@@ -1299,7 +1358,7 @@ extern "C" int smtl_gemm_run(const smtl_gemm_op* op, void* stream) {
     kp.total_kb = op->total_kblocks;
     const int cg = op->cta_group == 2 ? 2 : 1;
     const int stage_bytes = A_STAGE_BYTES + (op->block_n / cg) * BLOCK_K * 2;
-    kp.stages = (op->smem_bytes - 1024 - 512) / stage_bytes;
+    kp.stages = (op->smem_bytes - 1024 - 512 - (g.stats ? STATS_SMEM : 0)) / stage_bytes;
     if (op->cta_group == 3) kp.stages = (op->smem_bytes - 1024 - 512 - T_STAGING) / T_STAGE_BYTES;
     kp.nseg = g.nseg;
     for (int s = 0; s < SMTL_MAX_SEG; ++s) kp.seg[s] = g.seg[s];
@@ -1313,6 +1372,7 @@ extern "C" int smtl_gemm_run(const smtl_gemm_op* op, void* stream) {
     kp.stats = reinterpret_cast<unsigned long long*>(g.stats);
     kp.tile_rpi = op->tile_rpi;
     kp.tiles_per_img = op->tiles_per_img;
+    kp.tile_order = g.tile_order ? (g.tile_order == 2) : ((g.stats && op->cta_group != 3) ? 1 : 0);
     kp.stats_rpi = g.stats_rows_per_image;
     kp.stats_images = g.stats_images;
     kp.stats_rep = g.stats_replicas > 0 ? g.stats_replicas : 1;
@@ -1349,11 +1409,9 @@ extern "C" int smtl_gemm_run(const smtl_gemm_op* op, void* stream) {
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (op->cta_group == 3) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static std::atomic<uint64_t> attr_devs{0};
+        if (smtl_host::first_use_on_device(attr_devs))
             SMTL_CHECK_CUDA(cudaFuncSetAttribute(smtl_gemmT_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
-            attr_set = true;
-        }
         smtl_gemmT_kernel<<<op->grid, NUM_THREADS, op->smem_bytes, st>>>(kp);
         SMTL_CHECK_CUDA(cudaGetLastError());
         return SMTL_OK;

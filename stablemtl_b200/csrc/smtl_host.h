@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -36,6 +37,10 @@ const char* get_error();
 int encode_tmap_bf16_2d(uint64_t out[16], const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                         uint32_t box_rows, uint32_t box_cols = 64);
 
-int num_sms();
+int num_sms();   // of the CURRENT device (cached per device ordinal)
+
+// True the first time it is called for `mask` on the current device (then records the device's bit): per-device,
+// thread-safe guard for cudaFuncSetAttribute, which applies to the current device only.
+bool first_use_on_device(std::atomic<uint64_t>& mask);
 
 }  // namespace smtl_host

@@ -117,8 +117,25 @@ class _PlanBase:
         self.plan.finalize()
 
 
-def _dev(t, device, dtype=F32):
-    return t.to(device=device, dtype=dtype).contiguous()
+class _DevDict(dict):
+    """Packed weights: every tensor is laid out on the HOST (layout changes, 16-bit casts, constant folding) and
+    crosses to the device as one plain copy when it is stored here -- weight ingest launches no kernels at all, so the
+    first kernels a process launches are the path's own (the driver's launch capture sees them, not ATen's)."""
+
+    def __init__(self, device):
+        super().__init__()
+        self.device = device
+
+    def __setitem__(self, k, v):
+        if isinstance(v, torch.Tensor):
+            v = v.contiguous().to(self.device)
+        elif isinstance(v, list):
+            v = [t.contiguous().to(self.device) for t in v]
+        super().__setitem__(k, v)
+
+
+def _host_getter(sd):
+    return lambda k: sd[k].detach().to("cpu", F32)
 
 
 # ================================================================================================== UNet weights
@@ -129,30 +146,33 @@ class UNetWeights:
 
     def __init__(self, sd, cfg: UNetConfig, text, tasks, device, timestep=999):
         self.cfg, self.device, self.tasks = cfg, device, list(tasks)
-        self.w = {}
-        d = device
-        g = lambda k: sd[k].to(d, F32)
+        self.w = _DevDict(device)
+        g = _host_getter(sd)
         c = cfg.block_out_channels
         # --- time embedding (unet.py:347-353; diffusers Timesteps flip_sin_to_cos=True, shift 0)
         half = c[0] // 2
         freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=F32) / half)
         e = torch.tensor([float(timestep)])[:, None] * freqs[None, :]
-        emb = torch.cat([torch.cos(e), torch.sin(e)], dim=-1).to(d)
+        emb = torch.cat([torch.cos(e), torch.sin(e)], dim=-1)
         emb = torch.nn.functional.linear(emb, g("time_embedding.linear_1.weight"), g("time_embedding.linear_1.bias"))
         temb = torch.nn.functional.linear(torch.nn.functional.silu(emb), g("time_embedding.linear_2.weight"),
                                           g("time_embedding.linear_2.bias"))
         self.silu_temb = torch.nn.functional.silu(temb)[0]
         # --- text tokens, padded to 4 per task
         self.ntok = [text[t].shape[0] for t in self.tasks]
-        txt = torch.zeros(len(self.tasks), 4, cfg.cross_attention_dim, device=d)
+        for t, n in zip(self.tasks, self.ntok):
+            if not (1 <= n <= L.MAX_XATTN_TOKENS and text[t].shape[1] == cfg.cross_attention_dim):
+                raise ValueError(f"text embedding of task {t!r} is {tuple(text[t].shape)}: the cross-attention kernel takes "
+                                 f"1..{L.MAX_XATTN_TOKENS} tokens of width {cfg.cross_attention_dim}")
+        txt = torch.zeros(len(self.tasks), L.MAX_XATTN_TOKENS, cfg.cross_attention_dim)
         for i, t in enumerate(self.tasks):
-            txt[i, : self.ntok[i]] = text[t].to(d, F32)
-        self.text = txt
+            txt[i, : self.ntok[i]] = text[t].detach().to("cpu", F32)
+        self.text = txt                                               # host
         # --- stem / head
         w_in = g("conv_in.weight")                                   # [c0, 12, 3, 3]
         kin = 9 * cfg.in_channels
         self.kin_pad = (kin + 63) // 64 * 64
-        wm = torch.zeros(c[0], self.kin_pad, device=d)
+        wm = torch.zeros(c[0], self.kin_pad)
         wm[:, :kin] = conv_weight_matrix(w_in)
         self.w["conv_in.w"] = wm.to(ops.h16())
         self.w["conv_in.b"] = g("conv_in.bias")
@@ -264,7 +284,7 @@ class UNetPlan(_PlanBase):
         return out
 
     def __init__(self, W: UNetWeights, images, h, w, group_tasks, mode="single", feats=None, src_tasks=None,
-                 pool=None, x_in=None, feat_bufs=None):
+                 pool=None, x_in=None, feat_bufs=None, exclude_self=True):
         """feat_bufs (child mode): caller-owned 16-bit tap buffers, one per layer, at least [G*images*N_l, C_l] -- the
         send buffers of the task-stream exchange (stablemtl_b200/stream_shard.py).  src_tasks (main mode) may hold -1
         for an empty exchange slot: its rows are skipped by the task attention."""
@@ -289,6 +309,7 @@ class UNetPlan(_PlanBase):
         self.feats_out = [] if mode == "child" else None
         self.feats_in, self.src_tasks = feats, src_tasks
         self.feat_bufs = feat_bufs
+        self.exclude_self = exclude_self        # stablemtl_pipeline.py:483-484; False: attend to every stream given
         self.layer = 0
 
         # ---- stem: [Be, hw, 12] fp32 -> im2col -> GEMM
@@ -435,8 +456,13 @@ class UNetPlan(_PlanBase):
             add(ops.gemm(att, wt[p + ".o.w"], bias=wt[p + ".o.b"], out_f32=attn_out, name="attn_out"))
             # q = MLPv2_q[main task](LN_q[main task](attn_out))         attention.py:512
             qn = att
-            gq = torch.stack([tw[p + ".tnq.g"][t] for t in self.group_tasks]).contiguous()
-            bq = torch.stack([tw[p + ".tnq.b"][t] for t in self.group_tasks]).contiguous()
+            def rows_of(key, tasks):
+                """[len(tasks), ...] rows of a per-task stack in row-group order (a view when that is every task in order)"""
+                t = tw[p + key]
+                if list(tasks) == list(range(t.shape[0])):
+                    return t
+                return t.index_select(0, torch.tensor([max(x, 0) for x in tasks], device=t.device)).contiguous()
+            gq, bq = rows_of(".tnq.g", self.group_tasks), rows_of(".tnq.b", self.group_tasks)
             add(ops.layer_norm(attn_out, gq, bq, qn, rows_per_group=rpg))
             hq = cfg.task_q_hidden
             q1, q2 = P.alloc((M, hq), ops.h16()), P.alloc((M, hq), ops.h16())
@@ -445,10 +471,8 @@ class UNetPlan(_PlanBase):
 
             def stacked(key, tasks):
                 """[len(tasks) * out, in] weights / [len(tasks) * out] bias of the per-task module, in row-group order"""
-                wk, bk = tw[p + key + ".w"], tw[p + key + ".b"]
-                idx = torch.tensor([max(t, 0) for t in tasks], device=wk.device)   # -1 = empty exchange slot
-                return (wk.index_select(0, idx).reshape(-1, wk.shape[-1]).contiguous(),
-                        bk.index_select(0, idx).reshape(-1).contiguous(), wk.shape[1])
+                wk, bk = rows_of(key + ".w", tasks), rows_of(key + ".b", tasks)      # -1 = empty exchange slot -> task 0
+                return wk.reshape(-1, wk.shape[-1]), bk.reshape(-1), wk.shape[1]
 
             def task_linear(key, tasks, src, dst, act, name):
                 if grouped:
@@ -472,10 +496,8 @@ class UNetPlan(_PlanBase):
             Ms = S * rpg
             assert F_l.shape == (Ms, C), (F_l.shape, Ms, C)
             kn, vn = P.alloc((Ms, C), ops.h16()), P.alloc((Ms, C), ops.h16())
-            gk = torch.stack([tw[p + ".tnk.g"][max(t, 0)] for t in self.src_tasks]).contiguous()
-            bk = torch.stack([tw[p + ".tnk.b"][max(t, 0)] for t in self.src_tasks]).contiguous()
-            gv = torch.stack([tw[p + ".tnv.g"][max(t, 0)] for t in self.src_tasks]).contiguous()
-            bv = torch.stack([tw[p + ".tnv.b"][max(t, 0)] for t in self.src_tasks]).contiguous()
+            gk, bk = rows_of(".tnk.g", self.src_tasks), rows_of(".tnk.b", self.src_tasks)
+            gv, bv = rows_of(".tnv.g", self.src_tasks), rows_of(".tnv.b", self.src_tasks)
             add(ops.layer_norm(F_l, gk, bk, kn, gamma1=gv, beta1=bv, out1=vn, rows_per_group=rpg))
             hk, hv = P.alloc((Ms, C // 2), ops.h16()), P.alloc((Ms, C // 2), ops.h16())
             K, V = P.alloc((Ms, C), ops.h16()), P.alloc((Ms, C), ops.h16())
@@ -485,7 +507,7 @@ class UNetPlan(_PlanBase):
             task_linear(".tv2", self.src_tasks, hv, V, L.ACT_NONE, "task_v2")
             P.release(kn, vn, hk, hv)
             ta = qn
-            add(ops.task_attn(tq, K, V, ta, C, cfg.n_attns, self.group_tasks, self.src_tasks, rpg, exclude_self=True))
+            add(ops.task_attn(tq, K, V, ta, C, cfg.n_attns, self.group_tasks, self.src_tasks, rpg, exclude_self=self.exclude_self))
             P.release(tq, K, V)
             # h += attn_out + to_out_task(task attention)                                   attention.py:598-600, :347
             add(ops.gemm(ta, tw[p + ".tout.w"], bias=tw[p + ".tout.b"], res1=attn_out, res2=hs, out_f32=hs, name="to_out_task"))
@@ -522,11 +544,11 @@ class UNetPlan(_PlanBase):
 class VAEWeights:
     def __init__(self, sd, cfg: VAEConfig, device):
         self.cfg, self.device, self._sd = cfg, device, sd
-        self.w = {}
-        self._g = lambda k: sd[k].to(device, F32)
+        self.w = _DevDict(device)
+        self._g = _host_getter(sd)
         g, w = self._g, self.w
         # encoder stem (3 -> c0), K = 27 padded to 64
-        wm = torch.zeros(cfg.block_out_channels[0], 64, device=device)
+        wm = torch.zeros(cfg.block_out_channels[0], 64)
         wm[:, :27] = conv_weight_matrix(g("encoder.conv_in.weight"))
         w["enc.conv_in.w"], w["enc.conv_in.b"] = wm.to(ops.h16()), g("encoder.conv_in.bias")
         # encoder head: conv_out (3x3, C -> 2L) then quant_conv (1x1) then mean half * 0.18215, folded into one conv C -> L
@@ -539,7 +561,7 @@ class VAEWeights:
         w["dec.pq.w"] = (g("post_quant_conv.weight").reshape(lat, lat) / LATENT_SCALE).contiguous()
         w["dec.pq.b"] = g("post_quant_conv.bias")
         cd = cfg.block_out_channels[-1]
-        wm = torch.zeros(cd, 64, device=device)
+        wm = torch.zeros(cd, 64)
         wm[:, : 9 * lat] = conv_weight_matrix(g("decoder.conv_in.weight"))
         w["dec.conv_in.w"], w["dec.conv_in.b"] = wm.to(ops.h16()), g("decoder.conv_in.bias")
         w["dec.head.w"] = conv_weight_matrix(g("decoder.conv_out.weight")).to(ops.h16())
@@ -673,7 +695,11 @@ class _VAEBase(_PlanBase):
 class VAEEncodePlan(_VAEBase):
     """encode_rgb (stablemtl_pipeline.py:607-624): rgb [B,3,H,W] in [0,255] -> latent mean * 0.18215, fp32 [B*h*w, 4]."""
 
-    def __init__(self, W: VAEWeights, B, H, Wd, pool=None, rgb=None, rgb_dtype=F32):
+    def __init__(self, W: VAEWeights, B, H, Wd, pool=None, rgb=None, rgb_dtype=F32, normalized=False):
+        """normalized: `rgb` holds rgb / 255 * 2 - 1 already (the argument of the reference's encode_rgb)"""
+        if H % 8 or Wd % 8:
+            raise ValueError(f"image size {H}x{Wd}: height and width must be multiples of 8 (the VAE halves the map three "
+                             "times and the task maps are produced at 8x the latent size; resize or pad the input first)")
         self.W, self.B = W, B
         dev = W.device
         self.pool = P = pool or Pool(dev)
@@ -683,11 +709,8 @@ class VAEEncodePlan(_VAEBase):
         cfg = W.cfg
         c = cfg.block_out_channels
         self.rgb = rgb if rgb is not None else torch.zeros(B, 3, H, Wd, device=dev, dtype=rgb_dtype)
-        xin = P.alloc((B * H * Wd, 3), F32)
-        add(ops.rgb_prep(self.rgb, xin))
         col = P.alloc((B * H * Wd, 64), ops.h16())
-        add(ops.im2col(xin.view(B, H, Wd, 3), B, H, Wd, col, stride=1, pad_t=1, pad_l=1, oh=H, ow=Wd))
-        P.release(xin)
+        add(ops.rgb_stem(self.rgb, col, normalized=normalized))      # normalise + im2col of the 3-channel stem, one pass
         x = self._new_act(B, H * Wd, c[0])
         add(ops.gemm(col, W.w["enc.conv_in.w"], bias=W.w["enc.conv_in.b"], name="vae.enc.conv_in",
                      **self._into(x, H * Wd)))

@@ -61,14 +61,16 @@ _RUNNERS = {
     L.OP_RGBPREP: "smtl_rgbprep_run", L.OP_UNETIN: "smtl_unetin_run", L.OP_TASKMAP: "smtl_taskmap_run",
     L.OP_CHANMIX: "smtl_chanmix_run", L.OP_GNAPPLY: "smtl_gnapply_run", L.OP_MEMSET: "smtl_memset_run",
     L.OP_GNFINALIZE: "smtl_gnfinalize_run", L.OP_LSQSUMS: "smtl_lsqsums_run", L.OP_CONFUSION: "smtl_confusion_run",
+    L.OP_RGBSTEM: "smtl_rgbstem_run",
 }
 
 
 class Op:
-    __slots__ = ("kind", "struct", "keep", "flops", "name", "bytes")
+    __slots__ = ("kind", "struct", "keep", "flops", "flops_exec", "name", "bytes")
 
     def __init__(self, kind, struct, keep=(), flops=0, name="", nbytes=0):
         self.kind, self.struct, self.keep, self.flops, self.name = kind, struct, keep, flops, name
+        self.flops_exec = flops      # FLOPs the tensor pipe executes (2*m*n*k of the issued GEMM); `flops` is ALGORITHMIC
         self.bytes = nbytes          # algorithmic HBM bytes of a bandwidth-bound op (0: not accounted)
 
     def run(self):
@@ -131,21 +133,22 @@ def new_stats(images, channels, device, replicas=None):
 def stats_encode(values):
     """float64 [..., 2] (sum, sum of squares) -> int64 fixed-point cells [..., 4] the way a producer would add them"""
     v = values.double()
-    fine = v.abs() < 2.0 ** 14
-    lo = torch.where(fine, torch.round(v * 2.0 ** 35), torch.zeros_like(v)).to(torch.int64)
+    fine = v.abs() < 2.0 ** 12
+    lo = torch.where(fine, torch.round(v * 2.0 ** 32), torch.zeros_like(v)).to(torch.int64)
     hi = torch.where(fine, torch.zeros_like(v), torch.round(v * 2.0 ** 8)).to(torch.int64)
     return torch.stack([lo[..., 0], hi[..., 0], lo[..., 1], hi[..., 1]], -1)
 
 
 def stats_values(stats):
     """float64 [images, channels, 2] (sum, sum of squares) held by a statistics buffer"""
-    s = stats.sum(0).double()
-    return torch.stack([s[..., 0] * 2.0 ** -35 + s[..., 1] * 2.0 ** -8, s[..., 2] * 2.0 ** -35 + s[..., 3] * 2.0 ** -8], -1)
+    s = stats.double()
+    s = torch.stack([s[..., 0] * 2.0 ** -32 + s[..., 1] * 2.0 ** -8, s[..., 2] * 2.0 ** -32 + s[..., 3] * 2.0 ** -8], -1)
+    return s.sum(0)
 
 
 def gemm(a0, b, *, m=None, k=None, n=None, a1=None, segs=None, bias=None, bias_per_row=False, act=L.ACT_NONE,
          res1=None, res2=None, out_f32=None, out_bf16=None, aux_bf16=None, rowmap=L.ROWMAP_IDENTITY, img_hw=None,
-         block_n=0, name="gemm", stats=None, stats_rows_per_image=0, cta_group=0, up_parity=0, group_rows=0):
+         block_n=0, name="gemm", stats=None, stats_rows_per_image=0, cta_group=0, up_parity=0, group_rows=0, tile_order=0):
     """D = A @ B^T (+ fused epilogue).  a0/a1: bf16 [rows, cols] (row stride = stride(0)); b: bf16 [n, k].
     segs: list of (row_shift, kblocks, src, a_col0)."""
     assert a0.dtype == BF16 and b.dtype == BF16 and a0.stride(-1) == 1 and b.stride(-1) == 1
@@ -204,6 +207,7 @@ def gemm(a0, b, *, m=None, k=None, n=None, a1=None, segs=None, bias=None, bias_p
     g.cta_group = cta_group
     g.up_parity = up_parity
     g.group_rows = group_rows
+    g.tile_order = tile_order
     op = L.GemmOp()
     L.check(L.lib.smtl_gemm_plan(C.byref(g), C.byref(op)), "smtl_gemm_plan")
     if group_rows:
@@ -231,7 +235,7 @@ def conv3x3(a_pad, wmat, batch, h, w, *, a_short=None, name="conv3x3", pad_out=F
     cs = 0 if a_short is None else a_short.shape[1]
     op = gemm(a_pad, wmat, m=batch * (h + 2) * (w + 2), a1=a_short, segs=conv3x3_segs(cin, w, cs),
               rowmap=L.ROWMAP_PAD_KEEP if pad_out else L.ROWMAP_CONV_PAD, img_hw=(h, w), name=name, **epi)
-    op.flops = 2 * batch * h * w * wmat.shape[0] * wmat.shape[1]   # algorithmic (halo rows excluded)
+    op.flops = 2 * batch * h * w * wmat.shape[0] * wmat.shape[1]   # algorithmic (halo rows excluded); flops_exec keeps them
     return op
 
 
@@ -269,7 +273,8 @@ def conv_up2x(a_pad, wmats, batch, h, w, *, name="up2x_conv", pad_out=False, **e
             op = gemm(a_pad, wmats[py * 2 + px], m=batch * (h + 2) * wp, segs=segs,
                       rowmap=L.ROWMAP_UP2_PAD if pad_out else L.ROWMAP_CONV_PAD_UP2,
                       img_hw=(h, w), up_parity=py * 2 + px, name=name, **epi)
-            op.flops = 2 * batch * h * w * wmats[0].shape[0] * 9 * cin          # algorithmic: 1/4 of the 3x3 conv
+            # algorithmic: 1/4 of the 3x3 conv on the upsampled map; flops_exec = the 4-tap GEMM that actually runs
+            op.flops = 2 * batch * h * w * wmats[0].shape[0] * 9 * cin
             out.append(op)
     return out
 
@@ -409,13 +414,27 @@ def im2col(x, batch, h, w, out, *, stride, pad_t, pad_l, oh, ow):
     return Op(L.OP_IM2COL, a, (x, out), 0, "im2col")
 
 
-def rgb_prep(rgb_nchw, out_nhwc):
+def rgb_prep(rgb_nchw, out_nhwc, normalized=False):
+    """normalized=True: the input already is rgb / 255 * 2 - 1 (encode_rgb's argument); layout change only"""
     a = L.RgbprepArgs()
     b, _, h, w = rgb_nchw.shape
     a.rgb_nchw, a.batch, a.h, a.w, a.out_nhwc = rgb_nchw.data_ptr(), b, h, w, out_nhwc.data_ptr()
-    a.src_u8 = int(rgb_nchw.dtype == torch.uint8)
+    a.src_u8 = 2 if normalized else int(rgb_nchw.dtype == torch.uint8)
+    assert not (normalized and rgb_nchw.dtype != F32)
     assert rgb_nchw.dtype in (F32, torch.uint8) and rgb_nchw.is_contiguous() and out_nhwc.dtype == F32
     return Op(L.OP_RGBPREP, a, (rgb_nchw, out_nhwc), 0, "rgb_prep")
+
+
+def rgb_stem(rgb_nchw, col, normalized=False):
+    """[0,255] (or already normalised) NCHW rgb -> the 16-bit im2col operand [batch*h*w, 64] of the VAE encoder's stem"""
+    a = L.RgbstemArgs()
+    b, c, h, w = rgb_nchw.shape
+    assert c == 3 and rgb_nchw.is_contiguous() and rgb_nchw.dtype in (F32, torch.uint8) and not (normalized and rgb_nchw.dtype != F32)
+    assert col.dtype == BF16 and col.is_contiguous() and col.shape == (b * h * w, 64)
+    a.rgb_nchw, a.batch, a.h, a.w = rgb_nchw.data_ptr(), b, h, w
+    a.src_mode = 2 if normalized else int(rgb_nchw.dtype == torch.uint8)
+    a.out_bf16, a.fmt16 = col.data_ptr(), PREC["fmt"]
+    return Op(L.OP_RGBSTEM, a, (rgb_nchw, col), 0, "rgb_stem", rgb_nchw.numel() * rgb_nchw.element_size() + col.numel() * 2)
 
 
 def unet_input(latents, first_img, second_img, hw, out):
@@ -437,6 +456,7 @@ def chan_mix(x, w, b, y):
 def task_map(x, batch, hw, mode, *, out_clipped=None, out_post=None, out_ids=None, palette=None):
     a = L.TaskmapArgs()
     a.x, a.batch, a.hw, a.mode = x.data_ptr(), batch, hw, mode
+    assert x.is_contiguous() and x.numel() >= batch * hw * 3, "task_map: the decoder output is smaller than batch * hw pixels"
     a.out_clipped, a.out_post, a.out_ids = _ptr(out_clipped), _ptr(out_post), _ptr(out_ids)
     if palette is not None:
         a.palette, a.npalette = palette.data_ptr(), palette.shape[0]

@@ -2,9 +2,8 @@
 
 `StableMTLEngine` is the batched all-task fast path (deduplicated schedule of SURVEY.md §3.1: 1-2 VAE encodes,
 one batched child pass over the 7 task streams, one batched main pass, 7 decodes).
-`StableMTLPipeline` keeps the reference's call surface (`src/stablemtl_pipeline.py:177-194`, `:519-529`) on top of
-it so `eval_mtl.py` / `StableMTLTrainer.validate_single_dataset` (`src/trainer/stablemtl_trainer.py:697-712`)
-can call it unchanged.  All numerics run in the sm_100a kernels; torch is used for device memory, H2D/D2H copies
+`dropin.StableMTLPipeline` keeps the reference's object surface (`src/stablemtl_pipeline.py:112-658`) on top of
+it so `eval_mtl.py` / `StableMTLTrainer` (`src/trainer/stablemtl_trainer.py:405-437, 697-712`) can use it unchanged.  All numerics run in the sm_100a kernels; torch is used for device memory, H2D/D2H copies
 and the current stream only.  There is no CPU / PyTorch fallback: constructing either class without a CUDA
 device raises.
 """
@@ -62,7 +61,7 @@ class StableMTLEngine:
         self.child_w = UNetWeights(child_sd, ucfg, text, self.tasks, self.device)
         self.main_w = UNetWeights(main_sd, ucfg, text, self.tasks, self.device) if self.multi else None
         self.vae_w = VAEWeights(vae_sd, vcfg, self.device)
-        self.palette = (torch.tensor(PALETTE, dtype=F32, device=self.device) / 255.0 * 2.0 - 1.0).contiguous()
+        self.palette = (torch.tensor(PALETTE, dtype=F32) / 255.0 * 2.0 - 1.0).contiguous().to(self.device)
         self.max_decode_batch = max_decode_batch
         self._plans = {}
 
@@ -263,6 +262,95 @@ class StableMTLEngine:
                 self._exchange(p)
             st()
 
+    # ------------------------------------------------------------------------------------------ stage-level entry points
+    # The reference pipeline's own building blocks (encode_rgb, decode_output, unet(...), create_task_feats), for callers
+    # that drive the stages themselves (stablemtl_trainer.py:262-305); `predict` is the fused all-task schedule.
+    def _stage_plan(self, key, make):
+        if key not in self._plans:
+            self._plans[key] = make()
+        return self._plans[key]
+
+    @torch.no_grad()
+    def encode_rgb(self, rgb_norm: torch.Tensor) -> torch.Tensor:
+        """encode_rgb (stablemtl_pipeline.py:607-624): [B,3,H,W] in [-1,1] -> latent mean * 0.18215, fp32 [B,4,H/8,W/8]"""
+        B, _, H, W = rgb_norm.shape
+        enc = self._stage_plan(("encode_rgb", B, H, W), lambda: VAEEncodePlan(self.vae_w, B, H, W, normalized=True))
+        enc.rgb.copy_(rgb_norm.to(self.device, F32), non_blocking=True)
+        enc.run()
+        return enc.out.view(B, enc.h, enc.w, -1).permute(0, 3, 1, 2).contiguous()
+
+    @torch.no_grad()
+    def decode_latents(self, latent: torch.Tensor) -> torch.Tensor:
+        """the decoder of decode_output (:626-643): task latent [B,4,h,w] -> decoder output fp32 [B,3,8h,8w] (unclipped)"""
+        B, C, h, w = latent.shape
+        bd = min(B, self.max_decode_batch)
+        dec = self._stage_plan(("decode", bd, h, w), lambda: VAEDecodePlan(self.vae_w, bd, h, w))
+        flat = latent.to(self.device, F32).permute(0, 2, 3, 1).reshape(B * h * w, C)
+        H, W = dec.H, dec.Wd
+        out = torch.empty(B, 3, H, W, device=self.device, dtype=F32)
+        for c0 in range(0, B, bd):
+            n = min(bd, B - c0)
+            dec.latent[: n * h * w].copy_(flat[c0 * h * w:(c0 + n) * h * w])
+            dec.run()
+            out[c0:c0 + n].copy_(dec.out[: n * H * W].view(n, H, W, 3).permute(0, 3, 1, 2))
+        return out
+
+    def task_of_text(self, encoder_hidden_states: torch.Tensor) -> int:
+        """index of the task whose (constant) prompt embedding this is: the cross-attention K/V are folded per task at
+        load time (stablemtl_pipeline.py:464-472), so a UNet call is conditioned by naming one of the engine's tasks"""
+        e = encoder_hidden_states.detach().to("cpu", F32)
+        if e.dim() == 2:
+            e = e[None]
+        if not all(torch.equal(e[0], e[i]) for i in range(1, e.shape[0])):
+            raise ValueError("one prompt per UNet call: every batch row must carry the same text embedding")
+        for i, t in enumerate(self.tasks):
+            ref = self.child_w.text[i, : self.child_w.ntok[i]]
+            if e.shape[1] == ref.shape[0] and torch.allclose(e[0], ref, rtol=1e-4, atol=1e-5):
+                return i
+        raise ValueError("encoder_hidden_states is not the embedding of one of the engine's task prompts "
+                         f"({', '.join(self.tasks)}): the accelerated UNet folds the constant prompts at load time")
+
+    @torch.no_grad()
+    def unet_forward(self, which: str, sample: torch.Tensor, task: int, task_feats=None):
+        """UNet3DConditionModel.forward (src/model/unet.py:284-445) at t = 999 for one task prompt.
+        which: "single" | "child" (also returns the 16 attn1 taps) | "main" (consumes task_feats: list[16] of
+        {task name: [B, N_l, C_l]}, attending to every stream given, attention.py:463-600).
+        sample [B,12,1,h,w] -> (sample [B,4,1,h,w] fp32, taps list[16] of fp32 [B, N_l, C_l] or None)."""
+        if sample.dim() != 5 or sample.shape[2] != 1 or sample.shape[1] != self.ucfg.in_channels:
+            raise ValueError(f"sample must be [B, {self.ucfg.in_channels}, 1, h, w], got {tuple(sample.shape)}")
+        B, C, _, h, w = sample.shape
+        W_ = self.main_w if which == "main" else self.child_w
+        if W_ is None:
+            raise ValueError("this engine has no main (multi-stream) UNet")
+        src = None
+        if which == "main":
+            names = [t for t in self.tasks if t in task_feats[0]]
+            if not names or len(task_feats) != len(UNetPlan.tap_shapes(self.ucfg, h, w)):
+                raise ValueError("task_feats must be one {task: features} dict per transformer layer (16 for SD-2)")
+            src = [self.tasks.index(t) for t in names]
+        key = ("unet", which, task, None if src is None else tuple(src), B, h, w)
+
+        def make():
+            feats = None
+            if which == "main":
+                feats = [torch.zeros(len(src) * B * n, c, device=self.device, dtype=ops.h16())
+                         for n, c in UNetPlan.tap_shapes(self.ucfg, h, w)]
+            return UNetPlan(W_, B, h, w, [task], mode=which, feats=feats, src_tasks=src, exclude_self=False)
+        plan = self._stage_plan(key, make)
+        plan.x_in.copy_(sample.to(self.device, F32).squeeze(2).permute(0, 2, 3, 1).reshape(B * h * w, C))
+        if which == "main":
+            for l, buf in enumerate(plan.feats_in):
+                n = buf.shape[0] // len(src)
+                for si, ti in enumerate(src):
+                    f = task_feats[l][self.tasks[ti]]
+                    buf[si * n:(si + 1) * n].copy_(f.to(self.device).reshape(n, -1))
+        plan.run()
+        out = plan.out.view(B, h, w, -1).permute(0, 3, 1, 2).unsqueeze(2).contiguous()
+        taps = None
+        if which == "child":
+            taps = [f.view(B, -1, f.shape[-1]).float() for f in plan.feats_out]
+        return out, taps
+
     def launches_per_step(self, B, H, W, with_next=True):
         return self.plan_for(B, H, W, with_next)["launches"]
 
@@ -270,84 +358,9 @@ class StableMTLEngine:
         return self.plan_for(B, H, W, with_next)["flops"]
 
 
-# ====================================================================================================== drop-in facade
-class _Out(dict):
-    """Attribute/dict output object standing in for diffusers.utils.BaseOutput (stablemtl_pipeline.py:32-109)."""
-    __getattr__ = dict.__getitem__
-
-
-class StableMTLPipeline:
-    """Call-compatible with the reference `StableMTLPipeline.__call__` / `.single_infer`.
-
-    The first call for an image (pair) computes all task maps with the batched engine and caches them; the
-    following calls of the evaluation loop (one per `output_type`, stablemtl_trainer.py:697-712) are served from
-    the cache, which is exactly the deduplication the reference leaves on the table."""
-
-    rgb_latent_scale_factor = 0.18215
-    latent_scale_factor = 0.18215
-
-    def __init__(self, engine: StableMTLEngine, input_noise="deterministic", encode_rgb_model="duplicate"):
-        if input_noise != "deterministic" or encode_rgb_model != "duplicate":
-            raise ValueError("the accelerated path implements input_noise='deterministic', encode_rgb_model='duplicate' "
-                             "(config/train_base_config.yaml:18-24)")
-        self.engine = engine
-        self.device = engine.device
-        self._key = None
-
-    def _all_tasks(self, rgb_norm, rgb_next_norm):
-        key = (rgb_norm.data_ptr(), tuple(rgb_norm.shape), None if rgb_next_norm is None else rgb_next_norm.data_ptr())
-        fresh = self._key is None or self._key[0] != key or not torch.equal(self._key[1], rgb_norm.to(self.device))
-        if fresh:
-            # the engine takes [0,255]; undo (x/255*2-1) of stablemtl_pipeline.py:263 exactly where representable
-            rgb = (rgb_norm.to(self.device, F32) + 1.0) / 2.0 * 255.0
-            nxt = None if rgb_next_norm is None else (rgb_next_norm.to(self.device, F32) + 1.0) / 2.0 * 255.0
-            self.engine.predict(rgb, nxt)
-            self._key = (key, rgb_norm.to(self.device).clone())
-        return self.engine.last
-
-    @torch.no_grad()
-    def single_infer(self, rgb_norm, num_inference_steps, generator, show_pbar, output_type,
-                     exclude_mainstream_output_type, rgb_next_norm=None, task_output_types=[]):
-        if output_type not in self.engine.tasks:
-            raise ValueError(f"Unknown output type: {output_type}")
-        if self.engine.multi and not exclude_mainstream_output_type:
-            raise ValueError("the multi-stream engine is built for exclude_mainstream_output_type=True "
-                             "(config/train_stablemtl.yaml:22)")
-        return self._all_tasks(rgb_norm, rgb_next_norm)[output_type]
-
-    @torch.no_grad()
-    def __call__(self, input_image, exclude_mainstream_output_type, next_input_image=None, denoising_steps=None,
-                 ensemble_size=5, processing_res=None, match_input_res=True, resample_method="bilinear", batch_size=0,
-                 generator=None, color_map="Spectral", show_progress_bar=True, ensemble_kwargs=None,
-                 output_type="depth", task_output_types=[]):
-        if processing_res:
-            raise ValueError("processing_res > 0 (resize) is outside the accelerated path; eval uses processing_res=0 "
-                             "(config/train_base_config.yaml:179-180)")
-        rgb, nxt = input_image, next_input_image
-        assert rgb.min() >= 0 and rgb.max() <= 255, "Input images should be in [0,255] range"
-        rgb_norm = rgb / 255.0 * 2.0 - 1.0
-        nxt_norm = None if nxt is None else nxt / 255.0 * 2.0 - 1.0
-        out = self.single_infer(rgb_norm, denoising_steps, generator, show_progress_bar, output_type,
-                                exclude_mainstream_output_type, nxt_norm, task_output_types)
-        pred = out.squeeze().cpu().numpy()                                       # stablemtl_pipeline.py:294-295
-        if output_type == "albedo":
-            return _Out(albedo_np=(pred + 1.0) / 2.0)
-        if output_type == "shading":
-            return _Out(shading_np=(pred + 1.0) / 2.0)
-        if output_type == "depth":
-            return _Out(depth_np=(pred + 1.0) / 2.0, depth_colored=None)
-        if output_type == "normal":
-            n = np.linalg.norm(pred, axis=0, keepdims=True)
-            n[n == 0] = 1.0
-            return _Out(normal_np=pred / n, normal_colored=None)
-        if output_type == "optical_flow":
-            return _Out(optical_flow_np=pred)
-        if output_type == "scene_flow":
-            return _Out(scene_flow_np=pred)
-        if output_type == "semantic":
-            pal = np.asarray(PALETTE, dtype=np.float32)
-            emb = pal / 255.0 * 2.0 - 1.0
-            flat = pred.transpose(1, 2, 0).reshape(-1, 3)
-            d = np.sqrt(((flat[:, None, :] - emb[None]) ** 2).sum(-1))
-            return _Out(semantic_class_id=d.argmin(1).reshape(pred.shape[1:]), class_color_visualizes=pal)
-        raise ValueError(f"Unknown output type: {output_type}")
+def __getattr__(name):
+    """`from stablemtl_b200.pipeline import StableMTLPipeline` keeps working: the facade lives in dropin.py"""
+    if name == "StableMTLPipeline":
+        from .dropin import StableMTLPipeline
+        return StableMTLPipeline
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

@@ -787,3 +787,30 @@ def test_channel_stats_are_bit_reproducible_and_batch_position_independent(kind)
     assert torch.equal(s0, s1) and torch.equal(o0, o1)
     sp, op_ = run(perm)
     assert torch.equal(sp, s0[perm]) and torch.equal(op_, o0[perm])
+
+
+@pytest.mark.parametrize("cout", [256, 128])
+def test_channel_stats_of_a_large_energetic_map_do_not_overflow(cout):
+    """480x640 full-resolution map with std ~ 8 (what the VAE decoder's last level carries for some task latents): the
+    per-channel sums of squares are ~2e7 and a 32-group GroupNorm adds 4-8 of them -- the fixed-point cells and the
+    consumer's group reduction must hold that (a first version summed a group's cells in int64 and wrapped)."""
+    ops, L = _ops()
+    b, h, w, cin = 1, 480, 640, 64
+    x = rnd(b, h, w, cin, seed=1).to(H16())
+    wt = (rnd(cout, cin, 3, 3, scale=8.0 * (9 * cin) ** -0.5, seed=2)).to(H16())
+    wmat = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()
+    out = torch.empty(b * h * w, cout, device=DEV, dtype=H16())
+    st = ops.new_stats(b, cout, DEV)
+    op = ops.conv3x3(_pad_layout(x), wmat, b, h, w, out_bf16=out, stats=st, stats_rows_per_image=h * w)
+    assert (op.struct.cta_group == 3) == (cout == 128)             # 128 channels: the swapped kernel
+    op.run()
+    gamma, beta = rnd(cout, seed=3) + 1, rnd(cout, seed=4)
+    y = torch.empty(b * h * w, cout, device=DEV, dtype=H16())
+    ops.gn_apply(out, st, b, h, w, gamma, beta, y, eps=1e-6, silu=False, pad_out=False).run()
+    torch.cuda.synchronize()
+    xo = out.float().reshape(b, h * w, cout)
+    assert 6.0 < float(xo.std()) < 11.0
+    vals = ops.stats_values(st)
+    assert rel_l2(vals[:, :, 1], (xo.double() ** 2).sum(1)) < 1e-3
+    ref = F.group_norm(xo.permute(0, 2, 1).reshape(b, cout, h, w), 32, gamma, beta, eps=1e-6)
+    assert rel_l2(y.float().reshape(b, h, w, cout).permute(0, 3, 1, 2), ref) < 4e-3
