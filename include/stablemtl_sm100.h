@@ -51,6 +51,7 @@ enum { SMTL_FMT_BF16 = 0, SMTL_FMT_F16 = 1 };
 
 #define SMTL_MAX_SEG 12
 #define SMTL_MAX_TASKS 8
+#define SMTL_MAX_XATTN_TOKENS 8   /* tokens of a task prompt ("optical flow" = 4 with BOS/EOS; padded count is 4 or 8) */
 
 /* ------------------------------------------------------------------------------------------------ GEMM / conv
  * D[m, n] = sum over K segments of A_src[m + row_shift, a_col0 + kk] * B[n, kbase + kk]
@@ -187,8 +188,8 @@ typedef struct smtl_softmax_args {
 } smtl_softmax_args;
 int smtl_softmax_run(const smtl_softmax_args* a, void* stream);
 
-/* Cross-attention on <= 4 constant text tokens (diffusers Attention as attn2, src/model/attention.py:267-275,360-362).
- * kc/vc are the pre-projected keys/values to_k(text), to_v(text): fp32 [ntask, 4, heads*64]. */
+/* Cross-attention on a few constant text tokens (diffusers Attention as attn2, src/model/attention.py:267-275,360-362).
+ * kc/vc are the pre-projected keys/values to_k(text), to_v(text): fp32 [ntask, ntok_pad, heads*64]. */
 typedef struct smtl_xattn_args {
     const void* q_bf16;
     int32_t ldq;
@@ -203,9 +204,43 @@ typedef struct smtl_xattn_args {
     int32_t ldo;
     float scale;
     int32_t fmt16;
-    int32_t pad_;
+    int32_t ntok_pad;       /* rows per task of kc / vc (<= SMTL_MAX_XATTN_TOKENS) */
 } smtl_xattn_args;
 int smtl_xattn_run(const smtl_xattn_args* a, void* stream);
+
+/* The whole cross-attention step of BasicTransformerBlock (src/model/attention.py:355-373) in one pass over the fp32
+ * residual stream:  hs += attn2(LayerNorm2(hs), text[task]);  out = LayerNorm3(hs)  (the 16-bit operand of the
+ * feed-forward).  The prompt is constant per task, so attn2 is collapsed at load time into 2 * heads * ntok_pad vectors
+ * per task (v = head * ntok_pad + token), LayerNorm2's affine folded in:
+ *     ap  [ntask, V, C] 16-bit   gamma2 * (Wq_head^T k[token, head]) / sqrt(64)
+ *     suma[ntask, V]    fp32     sum over C of the ROUNDED ap row (LayerNorm2's mean term)
+ *     ca  [ntask, V]    fp32     beta2 . (Wq_head^T k[token, head]) / sqrt(64);  -inf for a padding token
+ *     bm  [ntask, V, C] 16-bit   Wo[:, head] v[token, head]
+ *     score = rstd * (hs . ap - mean * suma) + ca;  hs += bo + sum_v softmax_token(score)[v] * bm[v]
+ * heads in {1, 2, 5, 10} (C = 64 * heads <= 640), ntok_pad in {4, 8}: smtl_xattnf_supported(). */
+typedef struct smtl_xattnf_args {
+    float* hs;              /* fp32 [rows, ldh], updated in place */
+    int32_t ldh;
+    int32_t heads;
+    int64_t rows;
+    int64_t rows_per_group; /* row group g = row / rows_per_group uses the vectors of task_of_group[g] */
+    int32_t task_of_group[SMTL_MAX_TASKS];
+    int32_t ntok_pad;
+    int32_t fmt16;
+    const void* ap;
+    const float* suma;
+    const float* ca;
+    const void* bm;
+    const float* bo;        /* fp32 [C] attn2.to_out.0.bias */
+    const float* gamma3;    /* LayerNorm3 affine, fp32 [C] */
+    const float* beta3;
+    void* out_bf16;         /* 16-bit [rows, ldo] */
+    int32_t ldo;
+    float eps2, eps3;
+    int32_t pad_;
+} smtl_xattnf_args;
+int smtl_xattnf_run(const smtl_xattnf_args* a, void* stream);
+int smtl_xattnf_supported(int32_t heads, int32_t ntok_pad);
 
 /* Per-pixel cross-task attention (src/model/attention.py:500-519,553-597): Nq = 1, Nk = number of other task
  * streams, nheads heads of c/nheads channels. q rows are (main task group, image, pixel); k/v rows are
@@ -378,6 +413,21 @@ typedef struct smtl_chanmix_args {
 } smtl_chanmix_args;
 int smtl_chanmix_run(const smtl_chanmix_args* a, void* stream);
 
+/* Second half of a 3x3 / pad-1 conv with cout <= 4 output channels whose three kx taps were folded into the GEMM's N
+ * side (the VAE decoder's conv_out, diffusers Decoder.conv_out reached from src/stablemtl_pipeline.py:643): `partial` is
+ * the fp32 output of a 3-segment (ky) implicit GEMM over the PADDED map,
+ *     partial[row, kx * cout + co] = sum_ky sum_c a_pad[row + (ky - 1) * (w + 2), c] * W[co, c, ky, kx];
+ * this adds the three horizontally shifted entries of every interior pixel and the bias: out[pixel, co], compact fp32. */
+typedef struct smtl_headgather_args {
+    const float* partial;   /* fp32 [batch * (h+2) * (w+2), ldp] */
+    int32_t ldp;
+    int32_t batch, h, w;
+    int32_t cout;           /* 1..4 */
+    const float* bias;      /* fp32 [cout] or NULL */
+    float* out;             /* fp32 [batch * h * w, cout] */
+} smtl_headgather_args;
+int smtl_headgather_run(const smtl_headgather_args* a, void* stream);
+
 /* Task-map epilogue (src/stablemtl_pipeline.py:601,645-654 and the post-processing at :297-366):
  * x is the VAE decoder output fp32 [batch, hw, 3]. */
 enum {
@@ -443,7 +493,7 @@ enum {
     SMTL_OP_GEMM = 1, SMTL_OP_FATTN = 2, SMTL_OP_SOFTMAX = 3, SMTL_OP_XATTN = 4, SMTL_OP_TASKATTN = 5,
     /* 6 retired (first-generation two-pass GroupNorm) */ SMTL_OP_LN = 7, SMTL_OP_UPSAMPLE = 8, SMTL_OP_IM2COL = 9, SMTL_OP_RGBPREP = 10,
     SMTL_OP_UNETIN = 11, SMTL_OP_TASKMAP = 12, SMTL_OP_CHANMIX = 13, SMTL_OP_GNAPPLY = 14, SMTL_OP_MEMSET = 15,
-    SMTL_OP_GNFINALIZE = 16, SMTL_OP_LSQSUMS = 17, SMTL_OP_CONFUSION = 18, SMTL_OP_RGBSTEM = 19
+    SMTL_OP_GNFINALIZE = 16, SMTL_OP_LSQSUMS = 17, SMTL_OP_CONFUSION = 18, SMTL_OP_RGBSTEM = 19, SMTL_OP_HEADGATHER = 20, SMTL_OP_XATTNF = 21
 };
 typedef struct smtl_op_ref {
     int32_t kind;

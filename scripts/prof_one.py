@@ -64,6 +64,24 @@ elif case == "attn":
     qkv = rb(batch * ntok, 3 * c)
     out = torch.empty(batch * ntok, c, device=DEV, dtype=ops.h16())
     op = ops.flash_attn(qkv, batch, ntok, heads, out, 0, c, 2 * c)
+elif case in ("xattnf", "xattnf10"):     # collapsed cross-attention + LN3, UNet level 0 / 1, 112 images
+    heads = 5 if case == "xattnf" else 10
+    rpg, groups, ntp, c = (16 * 4800, 7, 4, 320) if heads == 5 else (16 * 1200, 7, 4, 640)
+    v = heads * ntp
+    hs = torch.randn(groups * rpg, c, device=DEV)
+    ap, bm = rb(7, v, c), rb(7, v, c)
+    ca = torch.randn(7, v, device=DEV)
+    vec = lambda: torch.randn(c, device=DEV)
+    out = torch.empty(groups * rpg, c, device=DEV, dtype=ops.h16())
+    op = ops.xattn_fused(hs, ap, ap.float().sum(-1), ca, bm, vec(), vec(), vec(), list(range(7)), rpg, heads, out)
+elif case == "gnapply":      # GroupNorm + SiLU, VAE decoder half resolution: 16 images, 256 channels, padded in and out
+    b, h, wd, c = 16, 240, 320, 256
+    x = rb(b * (h + 2) * (wd + 2), c)
+    st = ops.new_stats(b, c, DEV, replicas=4)
+    st[0, :, :, 2] = int(h * wd * 0.25 * 2 ** 32)
+    out = torch.empty_like(x)
+    op = ops.gn_apply(x, st, b, h, wd, torch.ones(c, device=DEV), torch.zeros(c, device=DEV), out, eps=1e-6, silu=True,
+                      pad_out=True, x_padded=True)
 else:
     raise SystemExit("unknown case")
 for _ in range(3):

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libstablemtl_sm100.so")
 
 MAX_SEG = 12
 MAX_TASKS = 8
-MAX_XATTN_TOKENS = 4
+MAX_XATTN_TOKENS = 8
 
 ACT_NONE, ACT_GELU, ACT_GEGLU, ACT_SILU = 0, 1, 2, 3
 (ROWMAP_IDENTITY, ROWMAP_CONV_PAD, ROWMAP_CONV_PAD_UP2, ROWMAP_PAD_KEEP, ROWMAP_TO_PAD,
@@ -20,7 +20,7 @@ ACT_NONE, ACT_GELU, ACT_GEGLU, ACT_SILU = 0, 1, 2, 3
 FMT_BF16, FMT_F16 = 0, 1
 MAP_MEAN1, MAP_RGB3, MAP_NORMAL, MAP_FLOW2, MAP_FLOW3, MAP_SEMANTIC = range(6)
 (OP_GEMM, OP_FATTN, OP_SOFTMAX, OP_XATTN, OP_TASKATTN, _OP_RETIRED6, OP_LN, OP_UPSAMPLE, OP_IM2COL, OP_RGBPREP,
- OP_UNETIN, OP_TASKMAP, OP_CHANMIX, OP_GNAPPLY, OP_MEMSET, OP_GNFINALIZE, OP_LSQSUMS, OP_CONFUSION, OP_RGBSTEM) = range(1, 20)
+ OP_UNETIN, OP_TASKMAP, OP_CHANMIX, OP_GNAPPLY, OP_MEMSET, OP_GNFINALIZE, OP_LSQSUMS, OP_CONFUSION, OP_RGBSTEM, OP_HEADGATHER, OP_XATTNF) = range(1, 22)
 
 vp = C.c_void_p
 i32 = C.c_int32
@@ -96,7 +96,16 @@ class XattnArgs(C.Structure):
         ("kc", vp), ("vc", vp),
         ("ntok", i32 * MAX_TASKS), ("task_of_group", i32 * MAX_TASKS),
         ("rows_per_group", i64),
-        ("out_bf16", vp), ("ldo", i32), ("scale", f32), ("fmt16", i32), ("pad_", i32),
+        ("out_bf16", vp), ("ldo", i32), ("scale", f32), ("fmt16", i32), ("ntok_pad", i32),
+    ]
+
+
+class XattnFArgs(C.Structure):
+    _fields_ = [
+        ("hs", vp), ("ldh", i32), ("heads", i32), ("rows", i64), ("rows_per_group", i64),
+        ("task_of_group", i32 * MAX_TASKS), ("ntok_pad", i32), ("fmt16", i32),
+        ("ap", vp), ("suma", vp), ("ca", vp), ("bm", vp), ("bo", vp), ("gamma3", vp), ("beta3", vp),
+        ("out_bf16", vp), ("ldo", i32), ("eps2", f32), ("eps3", f32), ("pad_", i32),
     ]
 
 
@@ -169,6 +178,11 @@ class ChanmixArgs(C.Structure):
     _fields_ = [("x", vp), ("rows", i64), ("cin", i32), ("cout", i32), ("w", vp), ("b", vp), ("y", vp)]
 
 
+class HeadGatherArgs(C.Structure):
+    _fields_ = [("partial", vp), ("ldp", i32), ("batch", i32), ("h", i32), ("w", i32), ("cout", i32), ("bias", vp),
+                ("out", vp)]
+
+
 class TaskmapArgs(C.Structure):
     _fields_ = [("x", vp), ("batch", i32), ("hw", i32), ("mode", i32), ("out_clipped", vp), ("out_post", vp),
                 ("out_ids", vp), ("palette", vp), ("npalette", i32), ("pad_", i32)]
@@ -187,13 +201,13 @@ class OpRef(C.Structure):
     _fields_ = [("kind", i32), ("pad_", i32), ("op", vp)]
 
 
-STRUCTS_IN_HEADER_ORDER = [GemmSeg, GemmArgs, GemmOp, FattnArgs, FattnOp, SoftmaxArgs, XattnArgs, TaskAttnArgs,
-                           GnApplyArgs, GnFinalizeArgs, MemsetArgs, LnArgs, UpsampleArgs, Im2colArgs, RgbprepArgs, RgbstemArgs, UnetinArgs, ChanmixArgs, TaskmapArgs, LsqSumsArgs, ConfusionArgs, OpRef]
+STRUCTS_IN_HEADER_ORDER = [GemmSeg, GemmArgs, GemmOp, FattnArgs, FattnOp, SoftmaxArgs, XattnArgs, XattnFArgs, TaskAttnArgs,
+                           GnApplyArgs, GnFinalizeArgs, MemsetArgs, LnArgs, UpsampleArgs, Im2colArgs, RgbprepArgs, RgbstemArgs, UnetinArgs, ChanmixArgs, HeadGatherArgs, TaskmapArgs, LsqSumsArgs, ConfusionArgs, OpRef]
 
 EXPORTS = [
-    "smtl_gemm_plan", "smtl_gemm_run", "smtl_fattn_plan", "smtl_fattn_run", "smtl_softmax_run", "smtl_xattn_run",
+    "smtl_gemm_plan", "smtl_gemm_run", "smtl_fattn_plan", "smtl_fattn_run", "smtl_softmax_run", "smtl_xattn_run", "smtl_xattnf_run", "smtl_xattnf_supported",
     "smtl_taskattn_run", "smtl_gnapply_run", "smtl_gnfinalize_run", "smtl_memset_run", "smtl_ln_run", "smtl_upsample_run", "smtl_im2col_run", "smtl_rgbprep_run", "smtl_rgbstem_run",
-    "smtl_unetin_run", "smtl_chanmix_run", "smtl_taskmap_run", "smtl_lsqsums_run", "smtl_confusion_run", "smtl_run_plan", "smtl_plan_launches", "smtl_abi_version",
+    "smtl_unetin_run", "smtl_chanmix_run", "smtl_headgather_run", "smtl_taskmap_run", "smtl_lsqsums_run", "smtl_confusion_run", "smtl_run_plan", "smtl_plan_launches", "smtl_abi_version",
     "smtl_last_error", "smtl_struct_sizes",
 ]
 

@@ -94,10 +94,11 @@ int smtl_struct_sizes(int32_t* out, int32_t cap) {
     const int32_t sizes[] = {
         (int32_t)sizeof(smtl_gemm_seg),     (int32_t)sizeof(smtl_gemm_args),    (int32_t)sizeof(smtl_gemm_op),
         (int32_t)sizeof(smtl_fattn_args),   (int32_t)sizeof(smtl_fattn_op),     (int32_t)sizeof(smtl_softmax_args),
-        (int32_t)sizeof(smtl_xattn_args),   (int32_t)sizeof(smtl_taskattn_args),
+        (int32_t)sizeof(smtl_xattn_args),   (int32_t)sizeof(smtl_xattnf_args),  (int32_t)sizeof(smtl_taskattn_args),
         (int32_t)sizeof(smtl_gnapply_args), (int32_t)sizeof(smtl_gnfinalize_args), (int32_t)sizeof(smtl_memset_args),
         (int32_t)sizeof(smtl_ln_args),      (int32_t)sizeof(smtl_upsample_args), (int32_t)sizeof(smtl_im2col_args),
         (int32_t)sizeof(smtl_rgbprep_args), (int32_t)sizeof(smtl_rgbstem_args), (int32_t)sizeof(smtl_unetin_args),  (int32_t)sizeof(smtl_chanmix_args),
+        (int32_t)sizeof(smtl_headgather_args),
         (int32_t)sizeof(smtl_taskmap_args), (int32_t)sizeof(smtl_lsqsums_args), (int32_t)sizeof(smtl_confusion_args),
         (int32_t)sizeof(smtl_op_ref)};
     const int n = (int)(sizeof(sizes) / sizeof(sizes[0]));
@@ -135,6 +136,8 @@ int smtl_run_plan(const smtl_op_ref* ops, int32_t n_ops, void* stream) {
             case SMTL_OP_LSQSUMS: rc = smtl_lsqsums_run((const smtl_lsqsums_args*)p, stream); break;
             case SMTL_OP_CONFUSION: rc = smtl_confusion_run((const smtl_confusion_args*)p, stream); break;
             case SMTL_OP_RGBSTEM: rc = smtl_rgbstem_run((const smtl_rgbstem_args*)p, stream); break;
+            case SMTL_OP_HEADGATHER: rc = smtl_headgather_run((const smtl_headgather_args*)p, stream); break;
+            case SMTL_OP_XATTNF: rc = smtl_xattnf_run((const smtl_xattnf_args*)p, stream); break;
             default:
                 smtl_host::set_error("plan op %d: unknown kind %d", i, ops[i].kind);
                 return SMTL_EKIND;

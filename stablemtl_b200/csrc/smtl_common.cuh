@@ -379,4 +379,19 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// Lane j <- sum over the 32 lanes of s[j] (recursive halving: 31 shuffles instead of 32 x 5).
+__device__ __forceinline__ float warp_transpose_sum(float (&s)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float mine = upper ? s[i + off] : s[i];
+            const float other = upper ? s[i] : s[i + off];
+            s[i] = mine + __shfl_xor_sync(0xffffffffu, other, off);
+        }
+    }
+    return s[0];
+}
+
 }  // namespace smtl

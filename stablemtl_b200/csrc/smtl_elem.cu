@@ -542,7 +542,7 @@ struct XattnK {
 // cross-attention on <= 4 constant keys: one warp per token row; a lane owns 8 contiguous channels (one 16-byte
 // load), so 8 lanes make a head, a warp covers 4 heads per pass and a q.k dot product closes with 3 shuffles.
 __global__ void xattn_kernel(const uint16_t* __restrict__ q, int ldq, int64_t rows, int heads,
-                             const float* __restrict__ kc, const float* __restrict__ vc, XattnK tk,
+                             const float* __restrict__ kc, const float* __restrict__ vc, XattnK tk, int ntp,
                              int64_t rows_per_group, uint16_t* __restrict__ out, int ldo, float scale, int fmt) {
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -551,8 +551,8 @@ __global__ void xattn_kernel(const uint16_t* __restrict__ q, int ldq, int64_t ro
     const int task = tk.task_of_group[grp];
     const int nt = tk.ntok[task];
     const int C = heads * 64;
-    const float* kbase = kc + (int64_t)task * 4 * C;
-    const float* vbase = vc + (int64_t)task * 4 * C;
+    const float* kbase = kc + (int64_t)task * ntp * C;      // [ntask, ntp, C], ntp = padded token count (<= 8)
+    const float* vbase = vc + (int64_t)task * ntp * C;
     for (int c0 = 0; c0 < C; c0 += 256) {
         const int col = c0 + 8 * lane;
         const bool on = col < C;                       // whole heads: C is a multiple of 64
@@ -566,10 +566,10 @@ __global__ void xattn_kernel(const uint16_t* __restrict__ q, int ldq, int64_t ro
             t = unpack16x2(u.z, fmt); qf[4] = t.x; qf[5] = t.y;
             t = unpack16x2(u.w, fmt); qf[6] = t.x; qf[7] = t.y;
         }
-        float sc[4];
+        float sc[SMTL_MAX_XATTN_TOKENS];
         float mx = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < SMTL_MAX_XATTN_TOKENS; ++j) {
             float d = 0.f;
             if (j < nt && on) {
                 const float4 k0 = ldg4(kbase + j * C + col), k1 = ldg4(kbase + j * C + col + 4);
@@ -584,11 +584,11 @@ __global__ void xattn_kernel(const uint16_t* __restrict__ q, int ldq, int64_t ro
         }
         float sum = 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { sc[j] = (j < nt) ? __expf(sc[j] - mx) : 0.f; sum += sc[j]; }
+        for (int j = 0; j < SMTL_MAX_XATTN_TOKENS; ++j) { sc[j] = (j < nt) ? __expf(sc[j] - mx) : 0.f; sum += sc[j]; }
         const float inv = 1.0f / sum;
         float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < SMTL_MAX_XATTN_TOKENS; ++j) {
             if (j < nt && on) {
                 const float4 v0 = ldg4(vbase + j * C + col), v1 = ldg4(vbase + j * C + col + 4);
                 o[0] += sc[j] * v0.x; o[1] += sc[j] * v0.y; o[2] += sc[j] * v0.z; o[3] += sc[j] * v0.w;
@@ -600,6 +600,151 @@ __global__ void xattn_kernel(const uint16_t* __restrict__ q, int ldq, int64_t ro
             u.x = pack16x2(o[0] * inv, o[1] * inv, fmt); u.y = pack16x2(o[2] * inv, o[3] * inv, fmt);
             u.z = pack16x2(o[4] * inv, o[5] * inv, fmt); u.w = pack16x2(o[6] * inv, o[7] * inv, fmt);
             *reinterpret_cast<uint4*>(out + row * ldo + col) = u;
+        }
+    }
+}
+
+// ============================================================================================= fused cross-attention
+// BasicTransformerBlock's  h += attn2(LN2(h), text);  n3 = LN3(h)  (src/model/attention.py:355-373) in ONE pass over the
+// residual stream.  The prompt is one of a few CONSTANT task names (stablemtl_pipeline.py:464-472), so attn2 collapses:
+//     score[head, j] = (LN2(h) Wq_head^T) . k[j, head] / 8 = LN2(h) . (Wq_head^T k[j, head] / 8)         -> vectors A[head, j]
+//     attn2(h)       = sum_head sum_j softmax_j(score)[head, j] * (Wo[:, head] v[j, head]) + bo           -> vectors Bm[head, j]
+// and LN2's affine folds into A:  score = rstd * (h . A' - mean * sum(A')) + beta . A,  A' = gamma * A.
+// That is 2 * C * heads * n_tok multiply-adds per row on the FMA pipe instead of two C x C GEMMs, and the row is read
+// once (fp32), written once (fp32) and emitted once as the 16-bit LN3 operand of the feed-forward: 10 B per element
+// instead of 32 B over five kernels.
+// A warp owns R rows; a lane holds H float2 of each (C = 64 H channels).  Per batch of 32 (row, vector) pairs the lanes
+// accumulate partial dot products, a transposing warp reduction leaves pair k on lane k, the softmax runs on NT adjacent
+// lanes, and the probabilities are broadcast back with shuffles for the output accumulation.
+template <int H, int R, int NT>
+__global__ void __launch_bounds__(256) xattn_fused_kernel(
+    float* __restrict__ hs, int ldh, int64_t rows_per_group, int ngroups, XattnK tk, const uint16_t* __restrict__ ap,
+    const float* __restrict__ suma, const float* __restrict__ ca, const uint16_t* __restrict__ bm,
+    const float* __restrict__ bo, const float* __restrict__ g3, const float* __restrict__ b3,
+    uint16_t* __restrict__ out, int ldo, float eps2, float eps3, int fmt) {
+    constexpr int C = 64 * H, V = H * NT, VB = 32 / R, NB = V / VB;
+    static_assert(V % VB == 0 && VB % NT == 0, "batches must hold whole heads");
+    const int lane = threadIdx.x & 31;
+    const int64_t wpg = (rows_per_group + R - 1) / R;                      // warps per row group
+    const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int grp = (int)(gw / wpg);
+    if (grp >= ngroups) return;
+    const int64_t local0 = (gw - (int64_t)grp * wpg) * R;
+    const int task = tk.task_of_group[grp];
+    const uint16_t* apT = ap + (int64_t)task * V * C;
+    const uint16_t* bmT = bm + (int64_t)task * V * C;
+    const float* saT = suma + task * V;
+    const float* caT = ca + task * V;
+
+    float2 v[R][H];
+    float mean[R], rstd[R];
+    bool live[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        live[r] = local0 + r < rows_per_group;
+        const float* src = hs + ((int64_t)grp * rows_per_group + local0 + r) * ldh;
+#pragma unroll
+        for (int i = 0; i < H; ++i)
+            v[r][i] = live[r] ? __ldg(reinterpret_cast<const float2*>(src) + lane + 32 * i) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < H; ++i) s += v[r][i].x + v[r][i].y;
+        mean[r] = warp_sum(s) * (1.0f / C);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            const float a = v[r][i].x - mean[r], b = v[r][i].y - mean[r];
+            q += a * a + b * b;
+        }
+        rstd[r] = rsqrtf(warp_sum(q) * (1.0f / C) + eps2);
+    }
+    // ---- scores and softmax: lane k of batch b ends up with p of (row k / VB, vector b * VB + k % VB)
+    float prob[NB];
+    const int my_r = lane / VB, my_vb = lane % VB;
+    float my_mean = 0.f, my_rstd = 0.f;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+        if (my_r == r) { my_mean = mean[r]; my_rstd = rstd[r]; }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        float part[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) part[k] = 0.f;
+#pragma unroll
+        for (int vb = 0; vb < VB; ++vb) {
+            const uint32_t* av = reinterpret_cast<const uint32_t*>(apT + (int64_t)(b * VB + vb) * C);
+#pragma unroll
+            for (int i = 0; i < H; ++i) {
+                const float2 a = unpack16x2(__ldg(av + lane + 32 * i), fmt);
+#pragma unroll
+                for (int r = 0; r < R; ++r) part[r * VB + vb] = fmaf(v[r][i].x, a.x, fmaf(v[r][i].y, a.y, part[r * VB + vb]));
+            }
+        }
+        const float d = warp_transpose_sum(part, lane);
+        const int vec = b * VB + my_vb;
+        float sc = my_rstd * (d - my_mean * __ldg(saT + vec)) + __ldg(caT + vec);       // -inf for a padded token
+        float mx = sc;
+#pragma unroll
+        for (int o = 1; o < NT; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const float e = __expf(sc - mx);
+        float sum = e;
+#pragma unroll
+        for (int o = 1; o < NT; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        prob[b] = e / sum;
+    }
+    // ---- h += bo + sum_v p_v Bm_v
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(bo) + lane + 32 * i);
+#pragma unroll
+        for (int r = 0; r < R; ++r) { v[r][i].x += t.x; v[r][i].y += t.y; }
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+#pragma unroll
+        for (int vb = 0; vb < VB; ++vb) {
+            float pr[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) pr[r] = __shfl_sync(0xffffffffu, prob[b], r * VB + vb);
+            const uint32_t* bv = reinterpret_cast<const uint32_t*>(bmT + (int64_t)(b * VB + vb) * C);
+#pragma unroll
+            for (int i = 0; i < H; ++i) {
+                const float2 m = unpack16x2(__ldg(bv + lane + 32 * i), fmt);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    v[r][i].x = fmaf(pr[r], m.x, v[r][i].x);
+                    v[r][i].y = fmaf(pr[r], m.y, v[r][i].y);
+                }
+            }
+        }
+    }
+    // ---- store the residual stream, LayerNorm 3 -> 16-bit operand of the feed-forward
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < H; ++i) s += v[r][i].x + v[r][i].y;
+        const float m3 = warp_sum(s) * (1.0f / C);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            const float a = v[r][i].x - m3, b = v[r][i].y - m3;
+            q += a * a + b * b;
+        }
+        const float r3 = rsqrtf(warp_sum(q) * (1.0f / C) + eps3);
+        if (!live[r]) continue;
+        const int64_t row = (int64_t)grp * rows_per_group + local0 + r;
+        float2* dst = reinterpret_cast<float2*>(hs + row * ldh);
+        uint32_t* o16 = reinterpret_cast<uint32_t*>(out + row * ldo);
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            const int j = lane + 32 * i;
+            dst[j] = v[r][i];
+            const float2 g = __ldg(reinterpret_cast<const float2*>(g3) + j), bb = __ldg(reinterpret_cast<const float2*>(b3) + j);
+            o16[j] = pack16x2((v[r][i].x - m3) * r3 * g.x + bb.x, (v[r][i].y - m3) * r3 * g.y + bb.y, fmt);
         }
     }
 }
@@ -735,6 +880,39 @@ __global__ void chanmix_kernel(const float* __restrict__ x, int64_t rows, int ci
             for (int i = 0; i < cin; ++i) acc += in[i] * w[j * cin + i];
             y[r * cout + j] = acc;
         }
+    }
+}
+
+// ============================================================================================= narrow-output conv head
+// A 3x3 conv with 3-4 output channels (the VAE decoder's conv_out, 128 -> 3) as a 9-tap implicit GEMM reads every
+// activation from shared memory once per tap for a handful of output columns: 26 TFLOP/s.  Instead the three kx taps are
+// folded into the GEMM's N side -- P[row, kx * cout + co] = sum_ky sum_c a[row + (ky - 1) * (w + 2), c] W[co, c, ky, kx],
+// a 3-segment implicit GEMM with N = 3 * cout -- and this kernel adds the three horizontally shifted entries:
+// out[pixel, co] = bias[co] + sum_kx P[pixel + kx - 1, kx * cout + co]  (rows of P are 16 floats: the three reads of a
+// pixel and of its neighbours are contiguous).
+__global__ void __launch_bounds__(256) conv_head_gather_kernel(const float* __restrict__ part, int ldp, int batch, int h, int w,
+                                                               int cout, const float* __restrict__ bias,
+                                                               float* __restrict__ out) {
+    const int wp = w + 2;
+    const int64_t hw = (int64_t)h * w, plane = (int64_t)(h + 2) * wp;
+    const int64_t total = (int64_t)batch * hw;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = idx / hw;
+        const int p = (int)(idx - b * hw);
+        const int y = p / w, x = p - y * w;
+        float acc[4];
+#pragma unroll
+        for (int co = 0; co < 4; ++co) acc[co] = (co < cout && bias) ? __ldg(bias + co) : 0.f;
+        const float* base = part + (b * plane + (int64_t)(y + 1) * wp + x) * ldp;   // padded pixel left of (y, x): kx = 0
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const float* src = base + (int64_t)kx * ldp + kx * cout;
+#pragma unroll
+            for (int co = 0; co < 4; ++co)
+                if (co < cout) acc[co] += __ldg(src + co);
+        }
+        for (int co = 0; co < cout; ++co) out[idx * cout + co] = acc[co];
     }
 }
 
@@ -973,21 +1151,63 @@ extern "C" int smtl_xattn_run(const smtl_xattn_args* a, void* stream) {
     SMTL_CHECK_ARG(a->rows > 0 && a->rows_per_group > 0 && a->heads > 0, "xattn: bad extent");
     SMTL_CHECK_ARG(a->ldq % 8 == 0 && a->ldo % 8 == 0, "xattn: row strides must be multiples of 8 elements");
     SMTL_CHECK_ARG((a->rows + a->rows_per_group - 1) / a->rows_per_group <= SMTL_MAX_TASKS, "xattn: too many groups");
+    SMTL_CHECK_ARG(a->ntok_pad >= 1 && a->ntok_pad <= SMTL_MAX_XATTN_TOKENS, "xattn: ntok_pad %d (1..%d)", a->ntok_pad,
+                   SMTL_MAX_XATTN_TOKENS);
     XattnK tk;
     for (int i = 0; i < SMTL_MAX_TASKS; ++i) {
         tk.ntok[i] = a->ntok[i];
         tk.task_of_group[i] = a->task_of_group[i];
-        SMTL_CHECK_ARG(a->ntok[i] >= 0 && a->ntok[i] <= 4, "xattn: ntok[%d]=%d", i, a->ntok[i]);
+        SMTL_CHECK_ARG(a->ntok[i] >= 0 && a->ntok[i] <= a->ntok_pad, "xattn: ntok[%d]=%d", i, a->ntok[i]);
         SMTL_CHECK_ARG(a->task_of_group[i] >= 0 && a->task_of_group[i] < SMTL_MAX_TASKS, "xattn: bad task id");
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int wpb = 8;
     const int64_t grid = (a->rows + wpb - 1) / wpb;
     xattn_kernel<<<(unsigned)grid, wpb * 32, 0, st>>>((const uint16_t*)a->q_bf16, a->ldq, a->rows, a->heads, a->kc,
-                                                      a->vc, tk, a->rows_per_group, (uint16_t*)a->out_bf16, a->ldo,
+                                                      a->vc, tk, a->ntok_pad, a->rows_per_group, (uint16_t*)a->out_bf16, a->ldo,
                                                       a->scale, a->fmt16);
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;
+}
+
+template <int H, int R, int NT>
+static int launch_xattn_fused(const smtl_xattnf_args* a, const XattnK& tk, int ngroups, cudaStream_t st) {
+    const int64_t wpg = (a->rows_per_group + R - 1) / R;
+    const int64_t warps = wpg * ngroups;
+    xattn_fused_kernel<H, R, NT><<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(
+        a->hs, a->ldh, a->rows_per_group, ngroups, tk, (const uint16_t*)a->ap, a->suma, a->ca, (const uint16_t*)a->bm,
+        a->bo, a->gamma3, a->beta3, (uint16_t*)a->out_bf16, a->ldo, a->eps2, a->eps3, a->fmt16);
+    SMTL_CHECK_CUDA(cudaGetLastError());
+    return SMTL_OK;
+}
+
+extern "C" int smtl_xattnf_supported(int32_t heads, int32_t ntok_pad) {
+    return (heads == 5 || heads == 10 || heads == 1 || heads == 2) && (ntok_pad == 4 || ntok_pad == 8);
+}
+
+extern "C" int smtl_xattnf_run(const smtl_xattnf_args* a, void* stream) {
+    SMTL_CHECK_ARG(a && a->hs && a->ap && a->suma && a->ca && a->bm && a->bo && a->gamma3 && a->beta3 && a->out_bf16,
+                   "xattnf: NULL argument");
+    SMTL_CHECK_ARG(a->rows > 0 && a->rows_per_group > 0 && a->rows % a->rows_per_group == 0, "xattnf: bad rows");
+    const int ngroups = (int)(a->rows / a->rows_per_group);
+    SMTL_CHECK_ARG(ngroups <= SMTL_MAX_TASKS, "xattnf: too many row groups");
+    SMTL_CHECK_ARG(a->ldh % 2 == 0 && a->ldo % 2 == 0, "xattnf: row strides must be even");
+    SMTL_CHECK_ARG(smtl_xattnf_supported(a->heads, a->ntok_pad), "xattnf: heads=%d ntok_pad=%d not instantiated", a->heads,
+                   a->ntok_pad);
+    XattnK tk;
+    for (int i = 0; i < SMTL_MAX_TASKS; ++i) {
+        tk.ntok[i] = 0;
+        tk.task_of_group[i] = a->task_of_group[i];
+        SMTL_CHECK_ARG(a->task_of_group[i] >= 0 && a->task_of_group[i] < SMTL_MAX_TASKS, "xattnf: bad task id");
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool n8 = a->ntok_pad == 8;
+    switch (a->heads) {
+        case 1: return n8 ? launch_xattn_fused<1, 4, 8>(a, tk, ngroups, st) : launch_xattn_fused<1, 8, 4>(a, tk, ngroups, st);
+        case 2: return n8 ? launch_xattn_fused<2, 4, 8>(a, tk, ngroups, st) : launch_xattn_fused<2, 8, 4>(a, tk, ngroups, st);
+        case 5: return n8 ? launch_xattn_fused<5, 4, 8>(a, tk, ngroups, st) : launch_xattn_fused<5, 8, 4>(a, tk, ngroups, st);
+        default: return n8 ? launch_xattn_fused<10, 4, 8>(a, tk, ngroups, st) : launch_xattn_fused<10, 4, 4>(a, tk, ngroups, st);
+    }
 }
 
 extern "C" int smtl_taskattn_run(const smtl_taskattn_args* a, void* stream) {
@@ -1013,6 +1233,17 @@ extern "C" int smtl_chanmix_run(const smtl_chanmix_args* a, void* stream) {
     SMTL_CHECK_ARG(a->cin >= 1 && a->cin <= 16 && a->cout >= 1 && a->cout <= 16 && a->rows > 0, "chanmix: bad shape");
     chanmix_kernel<<<grid_for(a->rows, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a->x, a->rows, a->cin,
                                                                                               a->cout, a->w, a->b, a->y);
+    SMTL_CHECK_CUDA(cudaGetLastError());
+    return SMTL_OK;
+}
+
+extern "C" int smtl_headgather_run(const smtl_headgather_args* a, void* stream) {
+    SMTL_CHECK_ARG(a && a->partial && a->out, "headgather: NULL argument");
+    SMTL_CHECK_ARG(a->batch > 0 && a->h > 0 && a->w > 0 && a->cout >= 1 && a->cout <= 4 && a->ldp >= 3 * a->cout,
+                   "headgather: bad extent (cout <= 4, ldp >= 3 * cout)");
+    const int64_t total = (int64_t)a->batch * a->h * a->w;
+    conv_head_gather_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        a->partial, a->ldp, a->batch, a->h, a->w, a->cout, a->bias, a->out);
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;
 }

@@ -108,21 +108,6 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
     return r;
 }
 
-// Lane j <- sum over the 32 lanes of s[j] (recursive halving: 31 shuffles instead of 32 x 5).
-__device__ __forceinline__ float warp_transpose_sum(float (&s)[32], int lane) {
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        const bool upper = (lane & off) != 0;
-#pragma unroll
-        for (int i = 0; i < off; ++i) {
-            const float mine = upper ? s[i + off] : s[i];
-            const float other = upper ? s[i] : s[i + off];
-            s[i] = mine + __shfl_xor_sync(0xffffffffu, other, off);
-        }
-    }
-    return s[0];
-}
-
 // GEMM row -> output row for every SMTL_ROWMAP_* (see the header).  `halo` = a padded GEMM row that is not an interior
 // pixel (PAD_KEEP stores zeros there; everyone else stores nothing).
 // (rows fit in 31 bits -- checked by the plan -- and the two divisors are per-launch constants: multiply-shift division
@@ -1027,11 +1012,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
                 }
                 __syncwarp();
                 if (p.stats && okmask) {
-                    int lo = ok ? img_l : 0x7fffffff, hi = img_l;
+                    int lo, hi;
+                    if (p.tile_rpi) {                                    // image-aligned tile: its image is known
+                        lo = hi = tile / p.tiles_per_img;
+                    } else {
+                        lo = ok ? img_l : 0x7fffffff;
+                        hi = img_l;
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-                        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+                        for (int o = 16; o > 0; o >>= 1) {
+                            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+                        }
                     }
                     if (lo == hi) {                                      // the usual case: one image in this chunk
                         if (lo != cur_img) { commit(); flush(); cur_img = lo; }
@@ -1280,11 +1271,13 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
         // shift-grouped convs: pairs halve the weight traffic (L2 -> smem and smem -> MMA): +8 % at bn = 256, +2-3 % at 160
         if (op->grouped && bn % 16 == 0 && bn >= 128 && tiles256 >= sms / 2) cg = 2;
         // image-aligned tiles (statistics producers): 256-row pair tiles pad a small map far more than 128-row tiles do
-        // (15x20: 374 padded rows = 2 x 256 but 3 x 128); the pair is worth ~5 % (measured), so it must not cost more
+        // (15x20: 374 padded rows = 2 x 256 but 3 x 128).  Measured (scripts/bench_kernels.py stats): the pair is worth
+        // ~17 % on these convs -- 30x40 maps (6 x 256 vs 11 x 128 rows, 9 % more padding) still run 8 % faster as pairs,
+        // 15x20 maps (33 % more padding) 14 % slower.
         if (cg == 2 && tile_rpi) {
             const double e2 = (double)tile_rpi / (double)(((tile_rpi + 255) / 256) * 256);
             const double e1 = (double)tile_rpi / (double)(((tile_rpi + 127) / 128) * 128);
-            if (e2 * 1.05 < e1) cg = 1;
+            if (e2 * 1.15 < e1) cg = 1;
         }
         if (g.group_rows) cg = 1;
     }
@@ -1372,7 +1365,9 @@ extern "C" int smtl_gemm_run(const smtl_gemm_op* op, void* stream) {
     kp.stats = reinterpret_cast<unsigned long long*>(g.stats);
     kp.tile_rpi = op->tile_rpi;
     kp.tiles_per_img = op->tiles_per_img;
-    kp.tile_order = g.tile_order ? (g.tile_order == 2) : ((g.stats && op->cta_group != 3) ? 1 : 0);
+    // auto: the contiguous order pays when an (image, column tile) run is long (>= 16 tiles: +1.5-2.5 % on the 60x80
+    // and larger maps); with a few tiles per image the round-robin order is 4-13 % faster (measured, same script)
+    kp.tile_order = g.tile_order ? (g.tile_order == 2) : ((g.stats && op->cta_group != 3 && op->tiles_per_img >= 16) ? 1 : 0);
     kp.stats_rpi = g.stats_rows_per_image;
     kp.stats_images = g.stats_images;
     kp.stats_rep = g.stats_replicas > 0 ? g.stats_replicas : 1;

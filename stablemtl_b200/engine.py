@@ -134,6 +134,10 @@ class _DevDict(dict):
         super().__setitem__(k, v)
 
 
+def w_ln2g(g, t):
+    return g(f"{t}.norm2.weight")
+
+
 def _host_getter(sd):
     return lambda k: sd[k].detach().to("cpu", F32)
 
@@ -164,7 +168,8 @@ class UNetWeights:
             if not (1 <= n <= L.MAX_XATTN_TOKENS and text[t].shape[1] == cfg.cross_attention_dim):
                 raise ValueError(f"text embedding of task {t!r} is {tuple(text[t].shape)}: the cross-attention kernel takes "
                                  f"1..{L.MAX_XATTN_TOKENS} tokens of width {cfg.cross_attention_dim}")
-        txt = torch.zeros(len(self.tasks), L.MAX_XATTN_TOKENS, cfg.cross_attention_dim)
+        self.ntp = 4 if max(self.ntok) <= 4 else 8                   # padded token count of the cross-attention tables
+        txt = torch.zeros(len(self.tasks), self.ntp, cfg.cross_attention_dim)
         for i, t in enumerate(self.tasks):
             txt[i, : self.ntok[i]] = text[t].detach().to("cpu", F32)
         self.text = txt                                               # host
@@ -229,11 +234,28 @@ class UNetWeights:
             w[p + ".qkv"] = torch.cat([g(f"{t}.attn1.to_q.weight"), g(f"{t}.attn1.to_k.weight"),
                                        g(f"{t}.attn1.to_v.weight")], dim=0).to(ops.h16()).contiguous()
             w[p + ".o.w"], w[p + ".o.b"] = g(f"{t}.attn1.to_out.0.weight").to(ops.h16()), g(f"{t}.attn1.to_out.0.bias")
-            w[p + ".q2"] = g(f"{t}.attn2.to_q.weight").to(ops.h16())
-            # cross-attention keys/values of the constant task-name tokens: [ntask, 4, C] fp32
-            w[p + ".kc"] = torch.nn.functional.linear(self.text, g(f"{t}.attn2.to_k.weight")).contiguous()
-            w[p + ".vc"] = torch.nn.functional.linear(self.text, g(f"{t}.attn2.to_v.weight")).contiguous()
-            w[p + ".o2.w"], w[p + ".o2.b"] = g(f"{t}.attn2.to_out.0.weight").to(ops.h16()), g(f"{t}.attn2.to_out.0.bias")
+            # cross-attention keys/values of the constant task-name tokens: [ntask, ntp, C] fp32
+            kc = torch.nn.functional.linear(self.text, g(f"{t}.attn2.to_k.weight"))
+            vc = torch.nn.functional.linear(self.text, g(f"{t}.attn2.to_v.weight"))
+            wq, wo = g(f"{t}.attn2.to_q.weight"), g(f"{t}.attn2.to_out.0.weight")
+            w[p + ".o2.b"] = g(f"{t}.attn2.to_out.0.bias")
+            C_ = wq.shape[0]
+            H_ = C_ // 64
+            if ops.xattn_fused_supported(H_, self.ntp):
+                # attn2 collapsed onto the constant prompt (attention.py:355-364; smtl_xattnf_args): 2 * H * ntp vectors
+                T_, n = len(self.tasks), self.ntp
+                a0 = 0.125 * torch.einsum("tjhd,hdc->thjc", kc.view(T_, n, H_, 64), wq.view(H_, 64, C_))     # scale 1/sqrt(64)
+                valid = (torch.arange(n)[None, :] < torch.tensor(self.ntok)[:, None])[:, None, :]           # [T, 1, n]
+                ap = (a0 * w_ln2g(g, t)).masked_fill(~valid[..., None], 0.0).reshape(T_, H_ * n, C_).to(ops.h16())
+                ca = (a0 * g(f"{t}.norm2.bias")).sum(-1).masked_fill(~valid, float("-inf")).reshape(T_, H_ * n)
+                bm = torch.einsum("tjhd,chd->thjc", vc.view(T_, n, H_, 64), wo.view(C_, H_, 64)).reshape(T_, H_ * n, C_)
+                w[p + ".xf.ap"], w[p + ".xf.sa"], w[p + ".xf.ca"] = ap, ap.float().sum(-1), ca
+                w[p + ".xf.bm"] = bm.to(ops.h16())
+                w[p + ".xf"] = True
+            else:
+                w[p + ".q2"] = wq.to(ops.h16())
+                w[p + ".kc"], w[p + ".vc"] = kc.contiguous(), vc.contiguous()
+                w[p + ".o2.w"] = wo.to(ops.h16())
             wi, bi = interleave_geglu(g(f"{t}.ff.net.0.proj.weight"), g(f"{t}.ff.net.0.proj.bias"))
             w[p + ".ff1.w"], w[p + ".ff1.b"] = wi.to(ops.h16()), bi
             w[p + ".ff2.w"], w[p + ".ff2.b"] = g(f"{t}.ff.net.2.weight").to(ops.h16()), g(f"{t}.ff.net.2.bias")
@@ -514,17 +536,22 @@ class UNetPlan(_PlanBase):
             P.release(attn_out)
         self.layer += 1
         # ---- cross-attention on the task-name tokens (attention.py:355-364)
-        n2 = att
-        add(ops.layer_norm(hs, wt[p + ".ln2g"], wt[p + ".ln2b"], n2))
-        q2b = P.alloc((M, C), ops.h16())
-        add(ops.gemm(n2, wt[p + ".q2"], out_bf16=q2b, name="xattn_q"))
-        xa = n2
-        add(ops.xattn(q2b, wt[p + ".kc"], wt[p + ".vc"], W.ntok, self.group_tasks, rpg, heads, xa))
-        P.release(q2b)
-        add(ops.gemm(xa, wt[p + ".o2.w"], bias=wt[p + ".o2.b"], res1=hs, out_f32=hs, name="xattn_out"))
-        # ---- GEGLU feed-forward (attention.py:372-373)
-        n3 = xa
-        add(ops.layer_norm(hs, wt[p + ".ln3g"], wt[p + ".ln3b"], n3))
+        n3 = att
+        if wt.get(p + ".xf", False):
+            # collapsed onto the constant prompt, fused with LayerNorm2, the residual add and LayerNorm3: one pass over hs
+            add(ops.xattn_fused(hs, wt[p + ".xf.ap"], wt[p + ".xf.sa"], wt[p + ".xf.ca"], wt[p + ".xf.bm"], wt[p + ".o2.b"],
+                                wt[p + ".ln3g"], wt[p + ".ln3b"], self.group_tasks, rpg, heads, n3))
+        else:
+            n2 = att
+            add(ops.layer_norm(hs, wt[p + ".ln2g"], wt[p + ".ln2b"], n2))
+            q2b = P.alloc((M, C), ops.h16())
+            add(ops.gemm(n2, wt[p + ".q2"], out_bf16=q2b, name="xattn_q"))
+            xa = n2
+            add(ops.xattn(q2b, wt[p + ".kc"], wt[p + ".vc"], W.ntok, self.group_tasks, rpg, heads, xa))
+            P.release(q2b)
+            add(ops.gemm(xa, wt[p + ".o2.w"], bias=wt[p + ".o2.b"], res1=hs, out_f32=hs, name="xattn_out"))
+            # ---- GEGLU feed-forward (attention.py:372-373)
+            add(ops.layer_norm(hs, wt[p + ".ln3g"], wt[p + ".ln3b"], n3))
         gg = P.alloc((M, 4 * C), ops.h16())
         add(ops.gemm(n3, wt[p + ".ff1.w"], bias=wt[p + ".ff1.b"], act=L.ACT_GEGLU, out_bf16=gg, name="ff1_geglu"))
         hb = n3
@@ -564,7 +591,7 @@ class VAEWeights:
         wm = torch.zeros(cd, 64)
         wm[:, : 9 * lat] = conv_weight_matrix(g("decoder.conv_in.weight"))
         w["dec.conv_in.w"], w["dec.conv_in.b"] = wm.to(ops.h16()), g("decoder.conv_in.bias")
-        w["dec.head.w"] = conv_weight_matrix(g("decoder.conv_out.weight")).to(ops.h16())
+        w["dec.head.w"] = ops.head_weight_matrix(g("decoder.conv_out.weight")).to(ops.h16())   # taps folded into N
         w["dec.head.b"] = g("decoder.conv_out.bias")
         for s in ("encoder", "decoder"):
             w[f"{s}.ng"], w[f"{s}.nb"] = g(f"{s}.conv_norm_out.weight"), g(f"{s}.conv_norm_out.bias")
@@ -789,7 +816,9 @@ class VAEDecodePlan(_VAEBase):
                          pad_out=True, groups=cfg.norm_num_groups, x_padded=True))
         P.release(x)
         self.out = torch.empty(B * h * w, 3, device=dev, dtype=F32)
-        add(ops.conv3x3(a, W.w["dec.head.w"], B, h, w, bias=W.w["dec.head.b"], out_f32=self.out, name="vae.dec.head"))
-        P.release(a)
+        part = P.alloc((B * (h + 2) * (w + 2), W.w["dec.head.w"].shape[0]), F32)
+        for o in ops.conv_head(a, W.w["dec.head.w"], W.w["dec.head.b"], B, h, w, 3, part, self.out, name="vae.dec.head"):
+            add(o)
+        P.release(a, part)
         self.H, self.Wd = h, w
         self._finish()

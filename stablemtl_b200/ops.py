@@ -61,15 +61,16 @@ _RUNNERS = {
     L.OP_RGBPREP: "smtl_rgbprep_run", L.OP_UNETIN: "smtl_unetin_run", L.OP_TASKMAP: "smtl_taskmap_run",
     L.OP_CHANMIX: "smtl_chanmix_run", L.OP_GNAPPLY: "smtl_gnapply_run", L.OP_MEMSET: "smtl_memset_run",
     L.OP_GNFINALIZE: "smtl_gnfinalize_run", L.OP_LSQSUMS: "smtl_lsqsums_run", L.OP_CONFUSION: "smtl_confusion_run",
-    L.OP_RGBSTEM: "smtl_rgbstem_run",
+    L.OP_RGBSTEM: "smtl_rgbstem_run", L.OP_HEADGATHER: "smtl_headgather_run", L.OP_XATTNF: "smtl_xattnf_run",
 }
 
 
 class Op:
-    __slots__ = ("kind", "struct", "keep", "flops", "flops_exec", "name", "bytes")
+    __slots__ = ("kind", "struct", "keep", "flops", "flops_exec", "name", "bytes", "outs16")
 
-    def __init__(self, kind, struct, keep=(), flops=0, name="", nbytes=0):
+    def __init__(self, kind, struct, keep=(), flops=0, name="", nbytes=0, outs16=()):
         self.kind, self.struct, self.keep, self.flops, self.name = kind, struct, keep, flops, name
+        self.outs16 = tuple(t for t in outs16 if t is not None)   # 16-bit outputs (StableMTLEngine.audit_range)
         self.flops_exec = flops      # FLOPs the tensor pipe executes (2*m*n*k of the issued GEMM); `flops` is ALGORITHMIC
         self.bytes = nbytes          # algorithmic HBM bytes of a bandwidth-bound op (0: not accounted)
 
@@ -214,7 +215,8 @@ def gemm(a0, b, *, m=None, k=None, n=None, a1=None, segs=None, bias=None, bias_p
         assert n is not None and b.shape[0] == (int(g.m) // group_rows) * n, "grouped GEMM: b is [groups * n, k], pass n"
         assert bias is None or bias.numel() == b.shape[0]
     flops = 2 * int(g.m) * int(g.n) * int(g.k)
-    return Op(L.OP_GEMM, op, (a0, a1, b, bias, res1, res2, out_f32, out_bf16, aux_bf16, stats), flops, name)
+    return Op(L.OP_GEMM, op, (a0, a1, b, bias, res1, res2, out_f32, out_bf16, aux_bf16, stats), flops, name,
+              outs16=(out_bf16, aux_bf16))
 
 
 def conv3x3_segs(cin, w, shortcut_cin=0):
@@ -290,7 +292,7 @@ def flash_attn(qkv, batch, ntok, heads, out, q_col0, k_col0, v_col0, scale=0.125
     assert qkv.dtype == BF16 and out.dtype == BF16 and qkv.shape[0] == batch * ntok
     op = L.FattnOp()
     L.check(L.lib.smtl_fattn_plan(C.byref(a), C.byref(op)), "smtl_fattn_plan")
-    return Op(L.OP_FATTN, op, (qkv, out), 4 * batch * heads * ntok * ntok * 64, "flash_attn")
+    return Op(L.OP_FATTN, op, (qkv, out), 4 * batch * heads * ntok * ntok * 64, "flash_attn", outs16=(out,))
 
 
 def softmax_rows(s, p, scale):
@@ -299,7 +301,7 @@ def softmax_rows(s, p, scale):
     a.s, a.rows, a.n, a.lds, a.scale = s.data_ptr(), s.shape[0], s.shape[1], s.stride(0), scale
     a.p_bf16, a.ldp = p.data_ptr(), p.stride(0)
     assert s.dtype == F32 and p.dtype == BF16
-    return Op(L.OP_SOFTMAX, a, (s, p), 0, "softmax")
+    return Op(L.OP_SOFTMAX, a, (s, p), 0, "softmax", outs16=(p,))
 
 
 def xattn(q, kc, vc, ntok, task_of_group, rows_per_group, heads, out, scale=0.125):
@@ -307,13 +309,40 @@ def xattn(q, kc, vc, ntok, task_of_group, rows_per_group, heads, out, scale=0.12
     a.fmt16 = PREC["fmt"]
     a.q_bf16, a.ldq, a.rows, a.heads = q.data_ptr(), q.stride(0), q.shape[0], heads
     a.kc, a.vc = kc.data_ptr(), vc.data_ptr()
-    assert kc.dtype == F32 and vc.dtype == F32 and kc.shape[1] == 4 and kc.shape[2] == heads * 64
+    assert kc.dtype == F32 and vc.dtype == F32 and kc.shape[1] <= L.MAX_XATTN_TOKENS and kc.shape[2] == heads * 64
+    a.ntok_pad = kc.shape[1]
     for i in range(L.MAX_TASKS):
         a.ntok[i] = ntok[i] if i < len(ntok) else 0
         a.task_of_group[i] = task_of_group[i] if i < len(task_of_group) else 0
     a.rows_per_group = rows_per_group
     a.out_bf16, a.ldo, a.scale = out.data_ptr(), out.stride(0), scale
-    return Op(L.OP_XATTN, a, (q, kc, vc, out), 0, "xattn")
+    return Op(L.OP_XATTN, a, (q, kc, vc, out), 0, "xattn", outs16=(out,))
+
+
+def xattn_fused_supported(heads, ntok_pad):
+    return bool(L.lib.smtl_xattnf_supported(heads, ntok_pad))
+
+
+def xattn_fused(hs, ap, suma, ca, bm, bo, gamma3, beta3, task_of_group, rows_per_group, heads, out, eps2=1e-5, eps3=1e-5):
+    """hs += attn2(LayerNorm2(hs), text[task]); out = LayerNorm3(hs) -- the collapsed cross-attention (see the header)."""
+    a = L.XattnFArgs()
+    c = heads * 64
+    ntask, v, _ = ap.shape
+    ntp = v // heads
+    assert hs.dtype == F32 and hs.shape[1] == c and hs.stride(1) == 1 and out.dtype == BF16 and out.shape == hs.shape
+    assert ap.dtype == BF16 and bm.dtype == BF16 and ap.shape == bm.shape == (ntask, heads * ntp, c) and ap.is_contiguous() and bm.is_contiguous()
+    assert suma.dtype == F32 and ca.dtype == F32 and suma.shape == ca.shape == (ntask, v) and suma.is_contiguous() and ca.is_contiguous()
+    assert hs.shape[0] % rows_per_group == 0 and len(task_of_group) == hs.shape[0] // rows_per_group
+    a.hs, a.ldh, a.heads, a.rows, a.rows_per_group = hs.data_ptr(), hs.stride(0), heads, hs.shape[0], rows_per_group
+    for i in range(L.MAX_TASKS):
+        a.task_of_group[i] = max(task_of_group[i], 0) if i < len(task_of_group) else 0
+    a.ntok_pad, a.fmt16 = ntp, PREC["fmt"]
+    a.ap, a.suma, a.ca, a.bm, a.bo = ap.data_ptr(), suma.data_ptr(), ca.data_ptr(), bm.data_ptr(), bo.data_ptr()
+    a.gamma3, a.beta3, a.out_bf16, a.ldo, a.eps2, a.eps3 = gamma3.data_ptr(), beta3.data_ptr(), out.data_ptr(), out.stride(0), eps2, eps3
+    op = Op(L.OP_XATTNF, a, (hs, ap, suma, ca, bm, bo, gamma3, beta3, out), 4 * hs.shape[0] * c * c, "xattn_fused",
+            hs.numel() * 8 + out.numel() * 2, outs16=(out,))
+    op.flops_exec = 4 * hs.shape[0] * c * v            # what the FMA pipe runs: 2 * C * V multiply-adds per row
+    return op
 
 
 def task_attn(q, k, v, out, c, nheads, main_tasks, src_tasks, rows_per_group, exclude_self=True):
@@ -330,7 +359,7 @@ def task_attn(q, k, v, out, c, nheads, main_tasks, src_tasks, rows_per_group, ex
     a.scale = float((c // nheads) ** -0.5)
     assert q.dtype == BF16 and k.dtype == BF16 and v.dtype == BF16 and out.dtype == BF16
     assert q.shape == (len(main_tasks) * rows_per_group, c) and k.shape == (len(src_tasks) * rows_per_group, c)
-    return Op(L.OP_TASKATTN, a, (q, k, v, out), 0, "task_attn")
+    return Op(L.OP_TASKATTN, a, (q, k, v, out), 0, "task_attn", outs16=(out,))
 
 
 # ------------------------------------------------------------------------------------------------- norms
@@ -358,7 +387,7 @@ def gn_apply(x0, stats0, batch, h, w, gamma, beta, out, *, x1=None, stats1=None,
     # algorithmic bytes: every interior element read once, every output element (halo included) written once
     nb = batch * h * w * (x0.shape[-1] * x0.element_size() + (0 if x1 is None else x1.shape[-1] * x1.element_size()))
     nb += out.numel() * out.element_size() + (0 if raw is None else raw.numel() * raw.element_size())
-    return Op(L.OP_GNAPPLY, a, (x0, x1, stats0, stats1, gamma, beta, out, raw), 0, "gn_apply", nb)
+    return Op(L.OP_GNAPPLY, a, (x0, x1, stats0, stats1, gamma, beta, out, raw), 0, "gn_apply", nb, outs16=(out, raw))
 
 
 def gn_finalize(stats, batch, pixels, gamma, beta, ss, *, eps, groups=32):
@@ -390,7 +419,7 @@ def layer_norm(x, gamma0, beta0, out0, *, gamma1=None, beta1=None, out1=None, ro
     a.ldo = out0.stride(0)
     assert out0.dtype == BF16 and gamma0.dtype == F32
     nb = x.numel() * x.element_size() + out0.numel() * out0.element_size() + (0 if out1 is None else out1.numel() * out1.element_size())
-    return Op(L.OP_LN, a, (x, gamma0, beta0, out0, gamma1, beta1, out1), 0, "layer_norm", nb)
+    return Op(L.OP_LN, a, (x, gamma0, beta0, out0, gamma1, beta1, out1), 0, "layer_norm", nb, outs16=(out0, out1))
 
 
 # ------------------------------------------------------------------------------------------------- data movement
@@ -400,7 +429,7 @@ def upsample_pad(x, batch, h, w, oh, ow, out):
     a.x, a.batch, a.h, a.w, a.c, a.oh, a.ow, a.out_bf16 = x.data_ptr(), batch, h, w, x.shape[-1], oh, ow, out.data_ptr()
     a.x_fmt16 = int(x.dtype != F32)
     assert (x.dtype == F32 or x.dtype == BF16) and out.dtype == BF16
-    return Op(L.OP_UPSAMPLE, a, (x, out), 0, "upsample")
+    return Op(L.OP_UPSAMPLE, a, (x, out), 0, "upsample", outs16=(out,))
 
 
 def im2col(x, batch, h, w, out, *, stride, pad_t, pad_l, oh, ow):
@@ -411,7 +440,7 @@ def im2col(x, batch, h, w, out, *, stride, pad_t, pad_l, oh, ow):
     a.out_bf16 = out.data_ptr()
     a.x_fmt16 = int(x.dtype != F32)
     assert (x.dtype == F32 or x.dtype == BF16) and out.dtype == BF16 and out.is_contiguous()
-    return Op(L.OP_IM2COL, a, (x, out), 0, "im2col")
+    return Op(L.OP_IM2COL, a, (x, out), 0, "im2col", outs16=(out,))
 
 
 def rgb_prep(rgb_nchw, out_nhwc, normalized=False):
@@ -451,6 +480,33 @@ def chan_mix(x, w, b, y):
     a.w, a.b, a.y = w.data_ptr(), _ptr(b), y.data_ptr()
     assert x.dtype == F32 and w.dtype == F32 and y.dtype == F32
     return Op(L.OP_CHANMIX, a, (x, w, b, y), 0, "chan_mix")
+
+
+def head_weight_matrix(w, npad=16):
+    """[cout <= 4, Cin, 3, 3] filter of a narrow-output conv -> [npad, 3 * Cin]: row kx * cout + co, column ky * Cin + c
+    (the kx taps folded into N, the ky taps stay K segments)"""
+    co, ci, kh, kw = w.shape
+    assert kh == 3 and kw == 3 and 3 * co <= npad
+    m = torch.zeros(npad, 3 * ci, dtype=w.dtype, device=w.device)
+    m[: 3 * co] = w.permute(3, 0, 2, 1).reshape(3 * co, 3 * ci)          # [kx, co, ky, c]
+    return m
+
+
+def conv_head(a_pad, wfold, bias, batch, h, w, cout, partial, out, name="conv_head"):
+    """3x3 / pad-1 conv with cout <= 4 channels: a 3-segment (ky) implicit GEMM over the padded map with the kx taps on
+    the N side (fp32 partials [rows, 16]) followed by the three-tap horizontal gather.  Returns the two ops."""
+    cin = a_pad.shape[1]
+    assert cin % 64 == 0 and wfold.shape[1] == 3 * cin
+    assert partial.dtype == F32 and partial.shape == (a_pad.shape[0], wfold.shape[0]) and out.dtype == F32
+    assert a_pad.shape[0] == batch * (h + 2) * (w + 2) and out.shape == (batch * h * w, cout)
+    segs = [((ky - 1) * (w + 2), cin // 64, 0, 0) for ky in range(3)]
+    g = gemm(a_pad, wfold, segs=segs, out_f32=partial, name=name)
+    g.flops = 2 * batch * h * w * cout * 9 * a_pad.shape[1]                 # algorithmic flops of the conv
+    a = L.HeadGatherArgs()
+    a.partial, a.ldp, a.batch, a.h, a.w, a.cout = partial.data_ptr(), partial.stride(0), batch, h, w, cout
+    a.bias, a.out = _ptr(bias), out.data_ptr()
+    nb = batch * h * w * (3 * cout + cout) * 4
+    return [g, Op(L.OP_HEADGATHER, a, (partial, bias, out), 0, name + ".gather", nb)]
 
 
 def task_map(x, batch, hw, mode, *, out_clipped=None, out_post=None, out_ids=None, palette=None):

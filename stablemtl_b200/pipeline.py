@@ -351,6 +351,50 @@ class StableMTLEngine:
             taps = [f.view(B, -1, f.shape[-1]).float() for f in plan.feats_out]
         return out, taps
 
+    # ------------------------------------------------------------------------------------------ range audit
+    @torch.no_grad()
+    def audit_range(self, rgb: torch.Tensor, rgb_next: Optional[torch.Tensor] = None, headroom: float = 0.5):
+        """IEEE fp16 operands saturate at +-65504 (the kernels clamp instead of producing inf), which would be a SILENT
+        error for a checkpoint whose activations leave that range.  This runs one pass op by op (no CUDA graph) and
+        looks at every 16-bit tensor the kernels write: it returns [(max |x|, plan, op index, op name)] sorted by
+        magnitude and raises OverflowError if any output reaches `headroom` * 65504 -- run it once per checkpoint on
+        representative images; activations depend on the weights far more than on the image.  bf16 operands
+        (ops.set_precision("bf16")) have the fp32 range and nothing to audit."""
+        if self.stream:
+            raise NotImplementedError("audit_range runs the unsharded schedule")
+        B, _, H, W = rgb.shape
+        dt = torch.uint8 if rgb.dtype == torch.uint8 else F32
+        p = self.plan_for(B, H, W, rgb_next is not None, dt)
+        p["enc"].rgb[:B].copy_(rgb)
+        if rgb_next is not None:
+            p["enc"].rgb[B:].copy_(rgb_next)
+        report = []
+
+        def run_plan(pname, plan):
+            for i, op in enumerate(plan.ops):
+                op.run()
+                for t in op.outs16:
+                    if t.dtype == torch.float16:
+                        report.append((float(t.abs().max()), pname, i, op.name))
+        run_plan("vae_encode", p["enc"].plan)
+        p["assemble"].run()
+        for ui, u in enumerate(p["unets"]):
+            run_plan(f"unet{ui}", u.plan)
+        dec, bd, hw, lat = p["dec"], p["bd"], p["hw"], p["lat"]
+        for c0, maps in p["chunks"]:
+            dec.latent.copy_(lat[c0 * hw:(c0 + bd) * hw])
+            run_plan(f"vae_decode[{c0}]", dec.plan)
+            for m in maps:
+                m.run()
+        torch.cuda.synchronize()
+        report.sort(key=lambda r: -r[0])
+        limit = headroom * 65504.0
+        if report and not (report[0][0] < limit):                     # also catches NaN
+            worst = ", ".join(f"{n}#{i} {name}: {m:.0f}" for m, n, i, name in report[:5])
+            raise OverflowError(f"fp16 range: activations reach {report[0][0]:.0f} (limit {limit:.0f} = {headroom} x 65504) -- "
+                                f"{worst}.  Run this checkpoint with ops.set_precision('bf16').")
+        return report
+
     def launches_per_step(self, B, H, W, with_next=True):
         return self.plan_for(B, H, W, with_next)["launches"]
 

@@ -111,3 +111,40 @@ def test_tap_shapes_follow_the_reference_layer_map():
     # odd sizes: 384x1248 -> 48x156 / 24x78 / 12x39 / 6x20
     s2 = UNetPlan.tap_shapes(synth.SD2_UNET, 48, 156)
     assert [n for n, _ in s2[:7]] == [7488, 7488, 1872, 1872, 468, 468, 120] and down_size(39) == 20
+
+
+def test_collapsed_cross_attention_tables_reproduce_attn2():
+    """UNetWeights folds attn2 onto the constant prompts (attention.py:355-364): the tables fed to smtl_xattnf_run must
+    give softmax((LN2(h) Wq^T) k^T / 8) v Wo^T + bo exactly (checked here in fp32 on the host, per task, with the 3- and
+    4-token prompts; the kernel itself is checked on the GPU)."""
+    import torch
+    import torch.nn.functional as F
+    from stablemtl_b200 import ops, synth
+    from stablemtl_b200.engine import UNetWeights
+    ops.set_precision("fp16")
+    u = synth.TINY_UNET
+    sd = synth.make_unet_state_dict(u, 0)
+    text = synth.make_text_embeddings(u.cross_attention_dim)
+    W = UNetWeights(sd, u, text, synth.TASKS, "cpu")
+    p = "down_blocks.1.attentions.0"                    # C = 128, 2 heads
+    w = W.transformer(p)
+    assert w[p + ".xf"] is True
+    t = p + ".transformer_blocks.0"
+    C, H, n = 128, 2, W.ntp
+    torch.manual_seed(0)
+    h = torch.randn(50, C) * 2 + 0.3
+    for ti, task in enumerate(synth.TASKS):
+        n2 = F.layer_norm(h, (C,), sd[t + ".norm2.weight"], sd[t + ".norm2.bias"], 1e-5)
+        q = n2 @ sd[t + ".attn2.to_q.weight"].t()
+        k = text[task] @ sd[t + ".attn2.to_k.weight"].t()
+        v = text[task] @ sd[t + ".attn2.to_v.weight"].t()
+        o = torch.cat([torch.softmax(q[:, hd * 64:(hd + 1) * 64] @ k[:, hd * 64:(hd + 1) * 64].t() / 8.0, -1) @ v[:, hd * 64:(hd + 1) * 64]
+                       for hd in range(H)], dim=1)
+        ref = o @ sd[t + ".attn2.to_out.0.weight"].t() + sd[t + ".attn2.to_out.0.bias"]
+        mean, rstd = h.mean(1, keepdim=True), (h.var(1, unbiased=False, keepdim=True) + 1e-5).rsqrt()
+        ap, sa, ca, bm = w[p + ".xf.ap"][ti].float(), w[p + ".xf.sa"][ti], w[p + ".xf.ca"][ti], w[p + ".xf.bm"][ti].float()
+        score = rstd * (h @ ap.t() - mean * sa) + ca                                     # [rows, H * n]
+        prob = torch.softmax(score.view(-1, H, n), -1).view(-1, H * n)
+        got = prob @ bm + w[p + ".o2.b"]
+        assert float(prob.view(-1, H, n)[:, :, text[task].shape[0]:].abs().max() if text[task].shape[0] < n else 0.0) == 0.0
+        assert ((got - ref).norm() / ref.norm()).item() < 2e-3, task                    # the tables are stored in 16 bits

@@ -763,7 +763,7 @@ def test_channel_stats_are_bit_reproducible_and_batch_position_independent(kind)
             torch.cuda.synchronize()
             return st.sum(0), out.reshape(b, rpi, n)
     else:
-        b, h, w, cin, cout = {"conv": (5, 15, 20, 320, 320), "conv_pair": (7, 30, 40, 256, 512),
+        b, h, w, cin, cout = {"conv": (5, 15, 20, 320, 320), "conv_pair": (3, 60, 80, 256, 512),
                               "swapped": (5, 120, 160, 128, 128)}[kind]
         x = rnd(b, h, w, cin, seed=1).to(H16())
         wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=2).to(H16())
@@ -814,3 +814,82 @@ def test_channel_stats_of_a_large_energetic_map_do_not_overflow(cout):
     assert rel_l2(vals[:, :, 1], (xo.double() ** 2).sum(1)) < 1e-3
     ref = F.group_norm(xo.permute(0, 2, 1).reshape(b, cout, h, w), 32, gamma, beta, eps=1e-6)
     assert rel_l2(y.float().reshape(b, h, w, cout).permute(0, 3, 1, 2), ref) < 4e-3
+
+
+@pytest.mark.parametrize("src", ["uint8", "float255", "normalized"])
+def test_rgb_stem_equals_normalise_then_im2col(src):
+    """the fused stem producer (normalise + 3x3 im2col of the 3 input channels, one pass) gives the BITS of the two-pass
+    form it replaces: rgb_prep (stablemtl_pipeline.py:263) then the scalar im2col"""
+    ops, L = _ops()
+    b, h, w = 2, 24, 40
+    g = torch.Generator().manual_seed(5)
+    u8 = torch.randint(0, 256, (b, 3, h, w), generator=g, dtype=torch.uint8).to(DEV)
+    if src == "uint8":
+        rgb, norm = u8, False
+    elif src == "float255":
+        rgb, norm = u8.float(), False
+    else:
+        rgb, norm = u8.float() / 255.0 * 2.0 - 1.0, True
+    xin = torch.empty(b * h * w, 3, device=DEV)
+    ops.rgb_prep(rgb, xin, normalized=norm).run()
+    ref = torch.full((b * h * w, 64), float("nan"), device=DEV, dtype=H16())
+    ops.im2col(xin.view(b, h, w, 3), b, h, w, ref, stride=1, pad_t=1, pad_l=1, oh=h, ow=w).run()
+    got = torch.full((b * h * w, 64), float("nan"), device=DEV, dtype=H16())
+    ops.rgb_stem(rgb, got, normalized=norm).run()
+    torch.cuda.synchronize()
+    assert torch.equal(got.view(torch.int16), ref.view(torch.int16))
+    want = F.unfold(u8.float() / 255.0 * 2.0 - 1.0, 3, padding=1).view(b, 3, 9, h * w).permute(0, 3, 2, 1).reshape(b * h * w, 27)
+    assert rel_l2(got[:, :27].float(), want) < 2e-3 and float(got[:, 27:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("b,h,w,cin,cout", [(2, 16, 24, 128, 3), (1, 60, 80, 320, 4), (3, 9, 7, 64, 1)])
+def test_conv_head_with_taps_folded_into_n(b, h, w, cin, cout):
+    """narrow-output 3x3 conv = a 3-segment implicit GEMM over the padded map (N = 3 * cout) + the horizontal gather"""
+    ops, L = _ops()
+    x = rnd(b, h, w, cin, seed=1).to(H16())
+    wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=2).to(H16())
+    bias = rnd(cout, seed=3)
+    wfold = ops.head_weight_matrix(wt)
+    a = _pad_layout(x).reshape(-1, cin)
+    part = torch.full((a.shape[0], wfold.shape[0]), float("nan"), device=DEV)
+    out = torch.full((b * h * w, cout), float("nan"), device=DEV)
+    for op in ops.conv_head(a, wfold, bias, b, h, w, cout, part, out):
+        op.run()
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(b * h * w, cout)
+    assert rel_l2(out, ref) < 2e-5
+
+
+@pytest.mark.parametrize("heads,ntp,rpg,groups", [(5, 4, 100, 3), (10, 4, 77, 2), (2, 8, 33, 4), (1, 4, 8, 1), (5, 8, 300, 2)])
+def test_xattn_fused_collapsed_cross_attention(heads, ntp, rpg, groups):
+    """hs += bo + sum_v softmax_token(rstd (hs . ap - mean suma) + ca)[v] bm[v];  out = LayerNorm3(hs)  -- one pass"""
+    ops, L = _ops()
+    c, v, ntask = heads * 64, heads * ntp, 3
+    hs = rnd(groups * rpg, c, seed=1) * 2 + 0.5
+    ap = (rnd(ntask, v, c, seed=2) * 0.05).to(H16())
+    bm = (rnd(ntask, v, c, seed=3) * 0.3).to(H16())
+    ca = rnd(ntask, v, seed=4)
+    ntok = [ntp, ntp - 1, max(1, ntp - 2)]
+    for t in range(ntask):                                         # padding tokens: zero vector, -inf constant
+        pad = torch.arange(v, device=DEV) % ntp >= ntok[t]
+        ap[t, pad] = 0
+        ca[t, pad] = float("-inf")
+    suma = ap.float().sum(-1)
+    bo, g3, b3 = rnd(c, seed=5), rnd(c, seed=6) + 1, rnd(c, seed=7)
+    tasks = [(g * 2) % ntask for g in range(groups)]
+    ref_h, ref_o = [], []
+    for g, t in enumerate(tasks):
+        h = hs[g * rpg:(g + 1) * rpg].double()
+        mean, rstd = h.mean(1, keepdim=True), (h.var(1, unbiased=False, keepdim=True) + 1e-5).rsqrt()
+        score = rstd * (h @ ap[t].double().t() - mean * suma[t].double()) + ca[t].double()
+        prob = torch.softmax(score.view(-1, heads, ntp), -1).view(-1, v)
+        hn = h + bo.double() + prob @ bm[t].double()
+        ref_h.append(hn)
+        ref_o.append(F.layer_norm(hn, (c,), g3.double(), b3.double(), 1e-5))
+    ref_h, ref_o = torch.cat(ref_h), torch.cat(ref_o)
+    out = torch.full((groups * rpg, c), float("nan"), device=DEV, dtype=H16())
+    got_h = hs.clone()
+    ops.xattn_fused(got_h, ap, suma, ca, bm, bo, g3, b3, tasks, rpg, heads, out).run()
+    torch.cuda.synchronize()
+    assert rel_l2(got_h, ref_h) < 1e-5
+    assert rel_l2(out.float(), ref_o) < 4e-3

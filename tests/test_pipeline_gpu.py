@@ -293,6 +293,38 @@ def test_image_sizes_must_be_multiples_of_8():
         eng.predict(rgb.cuda(), nxt.cuda())
 
 
+def test_fp16_range_audit_raises_instead_of_saturating_silently():
+    """fp16 operands clamp at +-65504.  A checkpoint whose activations leave the range must be REPORTED: audit_range
+    passes on the synthetic weights (largest 16-bit activation: a few tens) and raises on a VAE whose decoder convs are
+    scaled up until the residual stream overflows; the same weights run within tolerance with bf16 operands."""
+    sys.path.insert(0, ROOT)
+    from oracle import stablemtl_oracle as O
+    from stablemtl_b200 import ops, synth
+    from stablemtl_b200.pipeline import StableMTLEngine
+    eng, (child, vae, text, _) = build_engine(synth.TINY_UNET, synth.TINY_VAE, False)
+    rgb, nxt = synth.make_images(1, 64, 96, seed=2)
+    report = eng.audit_range(rgb.cuda(), nxt.cuda())
+    assert report and report[0][0] < 1000.0
+    hot = dict(vae)
+    for k in list(hot):
+        if k.startswith("decoder.") and k.endswith(("conv2.weight", "conv2.bias", "conv_in.weight", "conv_in.bias")):
+            hot[k] = hot[k] * 3000.0
+    eng_hot = StableMTLEngine(synth.TINY_UNET, synth.TINY_VAE, child, hot, text)
+    with pytest.raises(OverflowError, match="fp16 range"):
+        eng_hot.audit_range(rgb.cuda(), nxt.cuda())
+    try:
+        ops.set_precision("bf16")
+        eng_bf = StableMTLEngine(synth.TINY_UNET, synth.TINY_VAE, child, hot, text)
+        eng_bf.predict(rgb.cuda(), nxt.cuda())
+        torch.cuda.synchronize()
+        orc = O.Oracle(synth.TINY_UNET, synth.TINY_VAE, child, hot, text)
+        _, clipped, _ = orc.predict_all(rgb, nxt, return_latents=True)
+        for t in synth.TASKS:
+            assert rel_l2(eng_bf.last[t], clipped[t]) < 5e-2, t       # bf16: 8 mantissa bits, full range
+    finally:
+        ops.set_precision("fp16")
+
+
 def test_batched_evaluator_matches_direct_predict_and_device_metrics():
     """batches pushed through BatchedEvaluator (one in flight, pinned staging) give the maps of
     direct predict() calls; the device-side confusion matrix / alignment sums of those maps equal the host oracle's."""
