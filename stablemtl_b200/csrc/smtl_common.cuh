@@ -33,6 +33,33 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ----------------------------------------------------------------------------- explicit shared-space accesses
+// The kernels align their dynamic shared memory by integer arithmetic on the pointer, after which the compiler no longer
+// knows the address space and emits GENERIC loads / stores (LD.E / ST.E through the global pipeline: `lg` stalls in
+// ncu) for plain dereferences.  Staging tiles and on-chip accumulators go through these instead.
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint16_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_v2_s64(uint32_t addr, long long a, long long b) {
+    asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(addr), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void lds_v2_s64(uint32_t addr, long long& a, long long& b) {
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr) : "memory");
+}
+
 // ----------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -310,13 +337,13 @@ __device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv& f) {
     return (t + ((n - t) >> 1)) >> f.shr;
 }
 
-// fp32 -> 16-bit pair.  fp16 conversions saturate at +-65504 instead of overflowing to inf.
+// fp32 -> 16-bit pair.  fp16 conversions saturate at +-65504 instead of overflowing to inf: ONE instruction
+// (F2FP.SATFINITE.F16.F32.PACK_AB) -- the clamp used to be four FMNMX per pair in every epilogue.
 __device__ __forceinline__ uint32_t pack16x2(float lo, float hi, int fmt) {
     if (fmt == FMT_F16) {
-        lo = fminf(fmaxf(lo, -65504.f), 65504.f);
-        hi = fminf(fmaxf(hi, -65504.f), 65504.f);
-        __half2 v = __floats2half2_rn(lo, hi);
-        return *reinterpret_cast<uint32_t*>(&v);
+        uint32_t r;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+        return r;
     }
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);

@@ -253,7 +253,7 @@ __device__ __forceinline__ void add_residual(const GemmKParams& p, const void* r
 // tile; `tn` = N-tile index.  All tcgen05.ld / shuffles are warp-collective.
 template <int BN>
 __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t taddr, int tn, int lane, int half,
-                                              const EpiRow<BN>& e, long long* stats_acc) {
+                                              const EpiRow<BN>& e, uint32_t stats_acc) {
     const bool geglu = (p.act == SMTL_ACT_GEGLU);
     const int out_bn = geglu ? BN / 2 : BN;
     const int n0 = tn * BN;
@@ -368,14 +368,17 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t tad
             if (ocol + lane < p.n_out) {
                 // fine cells accumulate in this warp's shared-memory slots (flushed once per (image, column tile) run);
                 // a partial too large for the fine scale (|x| >= 2^14: rare) goes straight to its coarse global cell
-                long long* cell = stats_acc + ((c0 >> 6) * 32 + lane) * 2;
+                const uint32_t cell = stats_acc + (uint32_t)(((c0 >> 6) * 32 + lane) * 16);
                 unsigned long long* gcell = p.stats + (((int64_t)(blockIdx.x % p.stats_rep) * p.stats_images + e.img_lo) *
                                                            p.n_out + ocol + lane) * 4;
+                long long as, aq;
+                lds_v2_s64(cell, as, aq);
                 bool hi;
                 long long f = stats_fix(cs, hi);
-                if (hi) atomicAdd(gcell + 1, (unsigned long long)f); else cell[0] += f;
+                if (hi) atomicAdd(gcell + 1, (unsigned long long)f); else as += f;
                 f = stats_fix(cq, hi);
-                if (hi) atomicAdd(gcell + 3, (unsigned long long)f); else cell[1] += f;
+                if (hi) atomicAdd(gcell + 3, (unsigned long long)f); else aq += f;
+                sts_v2_s64(cell, as, aq);
             }
         }
     }
@@ -647,12 +650,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
         const int half = (warp - 2) >> 2;             // which of the quarter's two warps: alternate column chunks
         const int row_in_tile = quarter * 32 + lane;
         // this warp's running column sums (see STATS_SMEM) and the (image, column tile) run they belong to
-        long long* stats_acc = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(bars) + 512) +
-                               (size_t)(warp - 2) * STATS_NCH * 32 * 2;
+        const uint32_t stats_acc = smem_u32(reinterpret_cast<uint8_t*>(bars) + 512) +
+                                   (uint32_t)((warp - 2) * STATS_NCH * 32 * 16);        // [chunk][lane] x (sum, sq) int64
         int run_img = -1, run_tn = -1;
         if (p.stats) {
 #pragma unroll
-            for (int i = 0; i < STATS_NCH * 2; ++i) stats_acc[i * 32 + lane] = 0;
+            for (int i = 0; i < STATS_NCH; ++i) sts_v2_s64(stats_acc + (uint32_t)((i * 32 + lane) * 16), 0, 0);
             __syncwarp();
         }
         auto stats_flush = [&](int img, int tn) {
@@ -660,15 +663,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
 #pragma unroll
             for (int i = 0; i < STATS_NCH; ++i) {
                 const int col = tn * BN + half * 32 + 64 * i + lane;
-                long long* cell = stats_acc + (i * 32 + lane) * 2;
-                const long long fs = cell[0], fq = cell[1];
+                const uint32_t cell = stats_acc + (uint32_t)((i * 32 + lane) * 16);
+                long long fs, fq;
+                lds_v2_s64(cell, fs, fq);
                 if (half * 32 + 64 * i < BN && col < p.n_out && (fs | fq)) {
                     unsigned long long* g = p.stats + (((int64_t)(blockIdx.x % p.stats_rep) * p.stats_images + img) * p.n_out + col) * 4;
                     atomicAdd(g, (unsigned long long)fs);
                     atomicAdd(g + 2, (unsigned long long)fq);
                 }
-                cell[0] = 0;
-                cell[1] = 0;
+                sts_v2_s64(cell, 0, 0);
             }
         };
         int it = 0;
@@ -909,7 +912,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
         const int ch = quarter * 32 + lane;                           // this thread's output channel
         const bool ch_ok = ch < p.n;
         const float bias_c = (p.bias && ch_ok) ? __ldg(p.bias + ch) : 0.0f;
-        uint8_t* stg = staging + (warp - 2) * T_STG_WARP;
+        const uint32_t stg = smem_u32(staging + (warp - 2) * T_STG_WARP);      // explicit shared-space accesses below
         const int piece = lane & 3;                                   // 8-channel piece this lane moves (coalesced side)
         const int cpiece = quarter * 32 + piece * 8;                  // its first channel
         const bool piece_ok = cpiece + 8 <= p.n;
@@ -989,22 +992,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
                 if (p.res1) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        *reinterpret_cast<uint4*>(stg + (8 * i + (lane >> 2)) * T_STG_PITCH + piece * 16) = rq[i];
+                        sts_v4(stg + (8 * i + (lane >> 2)) * T_STG_PITCH + piece * 16, rq[i]);
                     __syncwarp();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const uint32_t h = *reinterpret_cast<const uint16_t*>(stg + j * T_STG_PITCH + lane * 2);
-                        v[j] += unpack16x2(h, p.fmt).x;
+                        v[j] += unpack16x2(lds_u16(stg + j * T_STG_PITCH + lane * 2), p.fmt).x;
                     }
                     __syncwarp();
                 }
                 // channel-major -> pixel-major through the staging tile, then 64-byte row pieces
 #pragma unroll
-                for (int j = 0; j < 32; ++j) *reinterpret_cast<uint16_t*>(stg + j * T_STG_PITCH + lane * 2) = to16(v[j], p.fmt);
+                for (int j = 0; j < 32; ++j) sts_u16(stg + j * T_STG_PITCH + lane * 2, to16(v[j], p.fmt));
                 __syncwarp();
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const uint4 q = *reinterpret_cast<const uint4*>(stg + (8 * i + (lane >> 2)) * T_STG_PITCH + piece * 16);
+                    const uint4 q = lds_v4(stg + (8 * i + (lane >> 2)) * T_STG_PITCH + piece * 16);
                     if (((ok_i >> i) & 1u) && piece_ok)
                         *reinterpret_cast<uint4*>(p.out_bf16 + (int64_t)orow_i[i] * p.ldc + cpiece) = q;
                     else if (((halo_i >> i) & 1u) && piece_ok)       // PAD_KEEP: zero halo
