@@ -148,9 +148,11 @@ int smtl_gemm_plan(const smtl_gemm_args* args, smtl_gemm_op* op);
 int smtl_gemm_run(const smtl_gemm_op* op, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ attention
- * Flash-style self-attention, head dim 64, softmax in fp32, tcgen05 for QK^T and PV.
- * Replaces xformers.ops.memory_efficient_attention at src/model/attention.py:391-397,417.
- * q/k/v live in one bf16 matrix [batch*ntok, ld] (the fused QKV projection) at column offsets *_col0 + head*64.
+ * Flash-style self-attention, softmax in fp32, tcgen05 for QK^T and PV, S and P kept in tensor memory.
+ *   head_dim 64, any number of heads: xformers.ops.memory_efficient_attention at src/model/attention.py:391-397,417;
+ *   head_dim 512, one head: the VAE mid-block attention (diffusers Attention(heads=1, dim_head=512) in UNetMidBlock2D,
+ *   reached from src/stablemtl_pipeline.py:619-620,642-643).
+ * q/k/v live in one 16-bit matrix [batch*ntok, ld] (the fused QKV projection) at column offsets *_col0 + head*head_dim.
  */
 typedef struct smtl_fattn_args {
     const void* qkv;
@@ -159,9 +161,9 @@ typedef struct smtl_fattn_args {
     int32_t batch, ntok, heads;
     void* out_bf16;     /* [batch*ntok, ldo], head h at columns h*64 */
     int32_t ldo;
-    float scale;        /* 1/sqrt(64) */
+    float scale;        /* 1/sqrt(head_dim) */
     int32_t fmt16;
-    int32_t pad_;
+    int32_t head_dim;   /* 0 or 64: 64; 512 (heads must be 1) */
 } smtl_fattn_args;
 
 typedef struct smtl_fattn_op {

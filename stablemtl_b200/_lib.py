@@ -77,7 +77,7 @@ class FattnArgs(C.Structure):
     _fields_ = [
         ("qkv", vp), ("ld", i32), ("q_col0", i32), ("k_col0", i32), ("v_col0", i32),
         ("batch", i32), ("ntok", i32), ("heads", i32),
-        ("out_bf16", vp), ("ldo", i32), ("scale", f32), ("fmt16", i32), ("pad_", i32),
+        ("out_bf16", vp), ("ldo", i32), ("scale", f32), ("fmt16", i32), ("head_dim", i32),
     ]
 
 

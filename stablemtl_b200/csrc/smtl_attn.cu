@@ -71,7 +71,8 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
 // 16 x 5 heads x 4800 tokens -- the two tiles already alternate; the gap is the serial ld / max / st / MMA round trip.)
 template <bool MASKED>
 __device__ __forceinline__ void softmax_tile(const FattnKParams& p, uint32_t t_s, int kv_valid, float& m_run,
-                                             float& l_run, uint32_t t_o, bool have_o) {
+                                             float& l_run, uint32_t t_o, bool have_o, int o_chunks = 2,
+                                             uint64_t* pv_bar = nullptr, uint32_t pv_parity = 0) {
     // the whole S row (128 fp32) is pulled into registers with four back-to-back tcgen05.ld and ONE wait
     uint32_t rr[128];
 #pragma unroll
@@ -97,8 +98,12 @@ __device__ __forceinline__ void softmax_tile(const FattnKParams& p, uint32_t t_s
         const float alpha = grow ? ex2_approx(m_run - mx_s) : 1.0f;     // 0 on the first tile (m_run = -inf)
         if (grow) { m_run = mx_s; l_run *= alpha; }
         if (have_o) {
+            if (pv_bar) {                                     // smtl_vattn_kernel issues S(j) BEFORE PV(j-1): O must hold
+                mbar_wait(pv_bar, pv_parity);                 // every earlier tile before it is rescaled
+                tc_fence_after();
+            }
 #pragma unroll 1
-            for (int c = 0; c < 2; ++c) {                     // rare path: keep its register footprint small
+            for (int c = 0; c < o_chunks; ++c) {              // rare path: keep its register footprint small
                 uint32_t oo[32];
                 tmem_ld_32x32(t_o + c * 32, oo);
                 tmem_ld_wait();
@@ -284,6 +289,214 @@ __global__ void __launch_bounds__(F2_THREADS, 1) smtl_fattn2_kernel(const __grid
     }
 }
 
+
+// ================================================================================================ d = 512, one head
+// The VAE mid-block attention (diffusers Attention(heads = 1, dim_head = 512) inside UNetMidBlock2D, reached from
+// src/stablemtl_pipeline.py:619-620,642-643): N = H/8 * W/8 tokens per image, ONE head of 512
+// channels.  Round 1 ran it per image as QK^T -> fp32 S in HBM (92 MB at 480x640) -> row softmax -> PV: four launches
+// per image, 5 % of the step for 1.7 % of its flops.  Here S and P never leave the SM:
+//   one CTA per 128 query rows of one image; Q (128 x 512) stays in shared memory as eight 64-wide slices;
+//   warp 0      : TMA producer -- K and V stream through a ring of [128 x 64] tiles (8 K slices, 4 V slices per KV tile)
+//   warp 1      : MMA issuer   -- S(j) = sum over the 8 slices of Q_s K_s^T into one of TWO S buffers in TMEM, so the
+//                                 tensor pipe works on S(j+1) while the softmax warps work on S(j);
+//                                 O += P(j) V(j) with P read from TMEM (it overwrites the S columns it came from)
+//   warps 2..5  : softmax      -- one query row per thread, as in smtl_fattn2_kernel (lazy running max, ex2.approx)
+// TMEM holds 512 fp32 columns: two S buffers (256) leave room for HALF of O (256 of its 512 columns), so the kernel
+// makes two passes over the keys, one per half of the value channels, recomputing S and the softmax (1.5x the
+// algorithmic flops; the pass is tensor-bound at 3072 clk per KV tile against ~1500 clk of softmax).
+// TMEM columns: S0/P0 [0,128)  S1/P1 [128,256)  O half [256,512).
+constexpr int V5_THREADS = 192;
+constexpr int V5_SLICES = 8;                               // 512 / 64
+constexpr int V5_NS = 6;                                   // ring stages (16 KB each)
+constexpr int V5_SMEM = V5_SLICES * TILE_BYTES + V5_NS * TILE_BYTES + 256;
+
+__global__ void __launch_bounds__(V5_THREADS, 1) smtl_vattn_kernel(const __grid_constant__ FattnKParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sQ = smem;                                    // 8 slices [128 x 64]
+    uint8_t* sR = smem + V5_SLICES * TILE_BYTES;           // K / V ring
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sR + V5_NS * TILE_BYTES);
+    uint64_t* q_full = bars + 0;
+    uint64_t* kv_full = bars + 1;                // [NS]
+    uint64_t* kv_empty = bars + 1 + V5_NS;       // [NS]
+    uint64_t* s_full = bars + 1 + 2 * V5_NS;     // [2]   MMA -> softmax
+    uint64_t* p_full = s_full + 2;               // [2]   softmax -> MMA
+    uint64_t* o_done = p_full + 2;               //       MMA -> epilogue, once per pass
+    uint64_t* o_free = o_done + 1;               //       epilogue -> MMA, once per pass
+    uint64_t* pv_done = o_free + 1;              //       MMA -> softmax: PV(j) retired (needed before O is rescaled)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * BQ;
+    const int row_base = blockIdx.y * p.ntok;
+    const int ntiles = (p.ntok + BKV - 1) / BKV;
+
+    if (threadIdx.x == 0) {
+        if ((smem_u32(smem) & 1023u) != 0) { printf("smtl_vattn: smem base not 1024-aligned\n"); __trap(); }
+        tma_prefetch_desc(&p.tm);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < V5_NS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        for (int w = 0; w < 2; ++w) { mbar_init(&s_full[w], 1); mbar_init(&p_full[w], 4); }
+        mbar_init(o_done, 1);
+        mbar_init(o_free, 4);
+        mbar_init(pv_done, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---------------------------------------------------------------- TMA producer (same order as the MMA warp consumes)
+        if (elect_one()) {
+            mbar_arrive_expect_tx(q_full, V5_SLICES * TILE_BYTES);
+            for (int s = 0; s < V5_SLICES; ++s) tma_load_2d(sQ + s * TILE_BYTES, &p.tm, q_full, p.q_col0 + s * 64, row_base + q0);
+        }
+        __syncwarp();
+        int st = 0;
+        uint32_t ph = 0;
+        auto load = [&](int col, int row) {
+            mbar_wait(&kv_empty[st], ph ^ 1u);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&kv_full[st], TILE_BYTES);
+                tma_load_2d(sR + st * TILE_BYTES, &p.tm, &kv_full[st], col, row);
+            }
+            __syncwarp();
+            if (++st == V5_NS) { st = 0; ph ^= 1u; }
+        };
+        for (int h = 0; h < 2; ++h) {
+            auto load_k = [&](int j) { for (int s = 0; s < V5_SLICES; ++s) load(p.k_col0 + s * 64, row_base + j * BKV); };
+            auto load_v = [&](int j) { for (int s = 0; s < 4; ++s) load(p.v_col0 + h * 256 + s * 64, row_base + j * BKV); };
+            load_k(0);
+            if (ntiles > 1) load_k(1);
+            for (int j = 0; j < ntiles; ++j) {
+                load_v(j);
+                if (j + 2 < ntiles) load_k(j + 2);
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------------------------------------------------------- MMA issuer (converged warp, elect.sync at the issue)
+        const uint32_t IDESC_S = make_idesc_16(BQ, BKV, 0, 0, p.fmt);   // S[128,128] += Q_s[128,64] K_s[128,64]^T
+        const uint32_t IDESC_O = make_idesc_16(BQ, 64, 0, 1, p.fmt);    // O[128,64]  += P[128,128] V_s[128,64]   (V MN-major)
+        int st = 0;
+        uint32_t ph = 0;
+        uint32_t p_uses[2] = {0, 0};
+        auto issue_s = [&](int j) {
+            const int sb = j & 1;
+            for (int s = 0; s < V5_SLICES; ++s) {
+                mbar_wait(&kv_full[st], ph);
+                if (elect_one()) {
+                    const uint64_t dq = make_smem_desc_sw128(smem_u32(sQ + s * TILE_BYTES));
+                    const uint64_t dk = make_smem_desc_sw128(smem_u32(sR + st * TILE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) tc_mma_f16(tmem_base + sb * 128, dq + 2 * k, dk + 2 * k, IDESC_S, (uint32_t)(s | k));
+                    tc_commit(&kv_empty[st]);
+                    if (s == V5_SLICES - 1) tc_commit(&s_full[sb]);
+                }
+                __syncwarp();
+                if (++st == V5_NS) { st = 0; ph ^= 1u; }
+            }
+        };
+        auto issue_pv = [&](int j) {
+            const int sb = j & 1;
+            for (int s = 0; s < 4; ++s) {
+                mbar_wait(&kv_full[st], ph);
+                if (elect_one()) {
+                    const uint32_t sv = smem_u32(sR + st * TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BKV / 16; ++k) {
+                        const uint64_t dv = make_smem_desc_sw128(sv + k * 16 * 128);       // kv rows 16k .. 16k + 16
+                        tc_mma_f16_ts(tmem_base + 256 + s * 64, tmem_base + sb * 128 + 8 * k, dv, IDESC_O, (uint32_t)(j | k));
+                    }
+                    tc_commit(&kv_empty[st]);
+                    if (s == 3) tc_commit(pv_done);
+                }
+                __syncwarp();
+                if (++st == V5_NS) { st = 0; ph ^= 1u; }
+            }
+        };
+        mbar_wait(q_full, 0);
+        for (int h = 0; h < 2; ++h) {
+            issue_s(0);
+            if (ntiles > 1) issue_s(1);
+            for (int j = 0; j < ntiles; ++j) {
+                const int sb = j & 1;
+                mbar_wait(&p_full[sb], p_uses[sb] & 1u);       // softmax wrote P(j) over S(j) and rescaled O
+                ++p_uses[sb];
+                if (j == 0 && h > 0) mbar_wait(o_free, (uint32_t)((h - 1) & 1));   // the epilogue has read the previous half of O
+                tc_fence_after();
+                issue_pv(j);
+                if (j + 2 < ntiles) issue_s(j + 2);           // in order after PV(j): may overwrite P(j)
+            }
+            if (elect_one()) tc_commit(o_done);
+            __syncwarp();
+        }
+    } else {
+        // ---------------------------------------------------------------- softmax + epilogue: one query row per thread
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+        const uint32_t t_o = tmem_base + 256 + lane_off;
+        const int tail = p.ntok - (ntiles - 1) * BKV;
+        const int qrow = q0 + r;
+        const bool row_ok = qrow < p.ntok;
+        uint32_t s_uses[2] = {0, 0};
+        for (int h = 0; h < 2; ++h) {
+            float m_run = -INFINITY, l_run = 0.f;
+            for (int j = 0; j < ntiles; ++j) {
+                const int sb = j & 1;
+                mbar_wait(&s_full[sb], s_uses[sb] & 1u);
+                ++s_uses[sb];
+                tc_fence_after();
+                const uint32_t t_s = tmem_base + sb * 128 + lane_off;
+                const uint32_t pv_par = (uint32_t)((h * ntiles + j - 1) & 1);      // phase in which PV(j-1) completes
+                if (j == ntiles - 1 && tail < BKV) softmax_tile<true>(p, t_s, tail, m_run, l_run, t_o, j > 0, 8, pv_done, pv_par);
+                else softmax_tile<false>(p, t_s, BKV, m_run, l_run, t_o, j > 0, 8, pv_done, pv_par);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[sb]);
+            }
+            mbar_wait(o_done, (uint32_t)(h & 1));
+            tc_fence_after();
+            const float inv = 1.0f / l_run;
+            uint16_t* dst = p.out + (int64_t)(row_base + qrow) * p.ldo + h * 256;
+#pragma unroll 1
+            for (int c = 0; c < 8; ++c) {
+                uint32_t rr[32];
+                tmem_ld_32x32(t_o + c * 32, rr);
+                tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+                        uint4 o;
+                        o.x = pack16x2(__uint_as_float(rr[i]) * inv, __uint_as_float(rr[i + 1]) * inv, p.fmt);
+                        o.y = pack16x2(__uint_as_float(rr[i + 2]) * inv, __uint_as_float(rr[i + 3]) * inv, p.fmt);
+                        o.z = pack16x2(__uint_as_float(rr[i + 4]) * inv, __uint_as_float(rr[i + 5]) * inv, p.fmt);
+                        o.w = pack16x2(__uint_as_float(rr[i + 6]) * inv, __uint_as_float(rr[i + 7]) * inv, p.fmt);
+                        *reinterpret_cast<uint4*>(dst + c * 32 + i) = o;
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(o_free);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 }  // namespace
 
 extern "C" int smtl_fattn_plan(const smtl_fattn_args* a, smtl_fattn_op* op) {
@@ -291,12 +504,20 @@ extern "C" int smtl_fattn_plan(const smtl_fattn_args* a, smtl_fattn_op* op) {
     SMTL_CHECK_ARG(a->batch > 0 && a->ntok > 0 && a->heads > 0, "fattn_plan: empty problem");
     SMTL_CHECK_ARG(a->ld % 8 == 0 && a->ldo % 8 == 0 && a->q_col0 % 8 == 0 && a->k_col0 % 8 == 0 && a->v_col0 % 8 == 0,
                    "fattn_plan: unaligned leading dims / column offsets");
+    SMTL_CHECK_ARG(a->head_dim == 0 || a->head_dim == 64 || (a->head_dim == 512 && a->heads == 1),
+                   "fattn_plan: head_dim %d with %d heads (64 x any, or 512 x 1)", a->head_dim, a->heads);
     memset(op, 0, sizeof(*op));
     op->args = *a;
-    op->grid_x = (a->ntok + 2 * BQ - 1) / (2 * BQ);
-    op->grid_y = a->batch * a->heads;
+    if (a->head_dim == 512) {                       // the VAE mid-block attention: smtl_vattn_kernel
+        op->grid_x = (a->ntok + BQ - 1) / BQ;
+        op->grid_y = a->batch;
+        op->smem_bytes = V5_SMEM;
+    } else {
+        op->grid_x = (a->ntok + 2 * BQ - 1) / (2 * BQ);
+        op->grid_y = a->batch * a->heads;
+        op->smem_bytes = F2_SMEM;
+    }
     SMTL_CHECK_ARG(op->grid_y <= 65535, "fattn_plan: batch*heads=%d exceeds grid.y", op->grid_y);
-    op->smem_bytes = F2_SMEM;
     return smtl_host::encode_tmap_bf16_2d(op->tmap_qkv, a->qkv, (uint64_t)a->batch * a->ntok, (uint64_t)a->ld,
                                           (uint64_t)a->ld, 128);
 }
@@ -319,6 +540,14 @@ extern "C" int smtl_fattn_run(const smtl_fattn_op* op, void* stream) {
     kp.fmt = a.fmt16;
     kp.ldo = a.ldo;
     kp.scale_log2 = a.scale * 1.4426950408889634f;
+    if (a.head_dim == 512) {
+        static std::atomic<uint64_t> attr5{0};
+        if (smtl_host::first_use_on_device(attr5))
+            SMTL_CHECK_CUDA(cudaFuncSetAttribute(smtl_vattn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V5_SMEM));
+        smtl_vattn_kernel<<<dim3(op->grid_x, op->grid_y), V5_THREADS, op->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(kp);
+        SMTL_CHECK_CUDA(cudaGetLastError());
+        return SMTL_OK;
+    }
     smtl_fattn2_kernel<<<dim3(op->grid_x, op->grid_y), F2_THREADS, op->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(kp);
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;

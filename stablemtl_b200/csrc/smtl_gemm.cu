@@ -99,6 +99,35 @@ __device__ __forceinline__ void st_global_v4_b32(void* p, uint32_t a, uint32_t b
     asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// 256-bit global accesses (sm_100: STG.E.ENL2.256 / LDG.E.ENL2.256): a lane writes a whole 32-byte sector per instruction.
+// With 16-byte row pieces every sector of the output was touched by two store instructions -- the SM -> L2 request
+// rate, not DRAM, bound the short-K token linears.  Addresses must be 32-byte aligned.
+__device__ __forceinline__ void st_global_v8_f32(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                 "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void st_global_v8_b32(void* p, const uint32_t* v) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void ldg_nc_v8(const void* p, uint32_t* v) {
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
+}
+// 32 fp32 values -> 16-bit row piece (64 bytes), 256-bit stores when the row pitch allows
+__device__ __forceinline__ void store_row16(uint16_t* dst, const float (&v)[32], int ld, int fmt) {
+    uint32_t w[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) w[j] = pack16x2(v[2 * j], v[2 * j + 1], fmt);
+    if ((ld & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
+        st_global_v8_b32(dst, w);
+        st_global_v8_b32(dst + 16, w + 8);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) st_global_v4_b32(dst + 2 * j, w[j], w[j + 1], w[j + 2], w[j + 3]);
+    }
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -220,7 +249,19 @@ __device__ __forceinline__ void add_residual(const GemmKParams& p, const void* r
                                              float (&v)[32]) {
     if (p.res16) {
         const uint16_t* src = reinterpret_cast<const uint16_t*>(res) + orow * (int64_t)p.ldres + ocol;
-        if (full && (p.ldres & 7) == 0) {
+        if (full && (p.ldres & 15) == 0 && (reinterpret_cast<uintptr_t>(src) & 31) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 16) {
+                uint32_t t[8];
+                ldg_nc_v8(src + j, t);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float2 f = unpack16x2(t[q], p.fmt);
+                    v[j + 2 * q] += f.x;
+                    v[j + 2 * q + 1] += f.y;
+                }
+            }
+        } else if (full && (p.ldres & 7) == 0) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
                 const uint4 t = ldg_nc_v4(src + j);
@@ -236,7 +277,15 @@ __device__ __forceinline__ void add_residual(const GemmKParams& p, const void* r
         }
     } else {
         const float* src = reinterpret_cast<const float*>(res) + orow * (int64_t)p.ldres + ocol;
-        if (full && (p.ldres & 3) == 0) {
+        if (full && (p.ldres & 7) == 0 && (reinterpret_cast<uintptr_t>(src) & 31) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                uint32_t t[8];
+                ldg_nc_v8(src + j, t);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[j + q] += __uint_as_float(t[q]);
+            }
+        } else if (full && (p.ldres & 3) == 0) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
                 const float4 t = __ldg(reinterpret_cast<const float4*>(src + j));
@@ -306,10 +355,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t tad
             if (p.aux_bf16) {
                 uint16_t* dst = p.aux_bf16 + orow * (int64_t)p.ld_aux + ocol;
                 if (full && (p.ld_aux & 7) == 0) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8)
-                        st_global_v4_b32(dst + j, pack16x2(v[j], v[j + 1], p.fmt), pack16x2(v[j + 2], v[j + 3], p.fmt),
-                                         pack16x2(v[j + 4], v[j + 5], p.fmt), pack16x2(v[j + 6], v[j + 7], p.fmt));
+                    store_row16(dst, v, p.ld_aux, p.fmt);
                 } else {
                     for (int j = 0; j < 32; ++j)
                         if (ocol + j < p.n_out) dst[j] = to16(v[j], p.fmt);
@@ -319,7 +365,10 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t tad
             if (p.res2) add_residual(p, p.res2, orow, ocol, full, v);
             if (p.out_f32) {
                 float* dst = p.out_f32 + orow * (int64_t)p.ldc + ocol;
-                if (full && (p.ldc & 3) == 0) {
+                if (full && (p.ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) st_global_v8_f32(dst + j, &v[j]);
+                } else if (full && (p.ldc & 3) == 0) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) st_global_v4_f32(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
                 } else {
@@ -330,10 +379,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t tad
             if (p.out_bf16) {
                 uint16_t* dst = p.out_bf16 + orow * (int64_t)p.ldc + ocol;
                 if (full && (p.ldc & 7) == 0) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8)
-                        st_global_v4_b32(dst + j, pack16x2(v[j], v[j + 1], p.fmt), pack16x2(v[j + 2], v[j + 3], p.fmt),
-                                         pack16x2(v[j + 4], v[j + 5], p.fmt), pack16x2(v[j + 6], v[j + 7], p.fmt));
+                    store_row16(dst, v, p.ldc, p.fmt);
                 } else {
                     for (int j = 0; j < 32; ++j)
                         if (ocol + j < p.n_out) dst[j] = to16(v[j], p.fmt);

@@ -630,6 +630,8 @@ class VAEWeights:
             w[p + ".qk.w"] = torch.cat([g(p + ".to_q.weight"), g(p + ".to_k.weight")]).to(ops.h16()).contiguous()
             w[p + ".qk.b"] = torch.cat([g(p + ".to_q.bias"), g(p + ".to_k.bias")]).contiguous()
             w[p + ".v.w"], w[p + ".v.b"] = g(p + ".to_v.weight").to(ops.h16()), g(p + ".to_v.bias")
+            w[p + ".qkv.w"] = torch.cat([g(p + ".to_q.weight"), g(p + ".to_k.weight"), g(p + ".to_v.weight")]).to(ops.h16())
+            w[p + ".qkv.b"] = torch.cat([g(p + ".to_q.bias"), g(p + ".to_k.bias"), g(p + ".to_v.bias")])
             w[p + ".o.w"], w[p + ".o.b"] = g(p + ".to_out.0.weight").to(ops.h16()), g(p + ".to_out.0.bias")
         return self.w
 
@@ -685,6 +687,16 @@ class _VAEBase(_PlanBase):
         xn = P.alloc((M, C), ops.h16())
         add(ops.gn_apply(x.t, x.stats, B, h, w, wt[p + ".ng"], wt[p + ".nb"], xn, eps=1e-6, silu=False, pad_out=False,
                          groups=G, x_padded=self.padded))
+        if C == 512:
+            # one fused QKV projection, then the d = 512 single-head flash kernel: S and P never leave the SM
+            qkv = P.alloc((M, 3 * C), ops.h16())
+            add(ops.gemm(xn, wt[p + ".qkv.w"], bias=wt[p + ".qkv.b"], out_bf16=qkv, name="vae.qkv"))
+            o = P.alloc((M, C), ops.h16())
+            fa = ops.flash_attn(qkv, B, N, 1, o, 0, C, 2 * C, scale=float(C) ** -0.5, head_dim=C)
+            fa.name = "vae.flash_attn"
+            add(fa)
+            P.release(qkv, xn)
+            return self._mid_attn_out(p, x, o, h, w, C)
         qk = P.alloc((M, 2 * C), ops.h16())
         add(ops.gemm(xn, wt[p + ".qk.w"], bias=wt[p + ".qk.b"], out_bf16=qk, name="vae.qk"))
         o = P.alloc((M, C), ops.h16())
@@ -698,6 +710,12 @@ class _VAEBase(_PlanBase):
             add(ops.softmax_rows(S[:, :N], Pm[:, :N], float(C) ** -0.5))
             add(ops.gemm(Pm[:, :N], vT[:, :N], out_bf16=o[r], name="vae.pv"))
         P.release(vT, S, Pm, qk, xn)
+        return self._mid_attn_out(p, x, o, h, w, C)
+
+    def _mid_attn_out(self, p, x, o, h, w, C):
+        """to_out.0 + the residual connection of the mid-block attention"""
+        W, P, add = self.W, self.pool, self.plan.add
+        wt = W.attn(p)
         out = self._new_map(h, w, C)
         extra = dict(rowmap=L.ROWMAP_TO_PAD, img_hw=(h, w)) if self.padded else {}
         add(ops.gemm(o, wt[p + ".o.w"], bias=wt[p + ".o.b"], res1=x.t, name="vae.attn_out",

@@ -893,3 +893,18 @@ def test_xattn_fused_collapsed_cross_attention(heads, ntp, rpg, groups):
     torch.cuda.synchronize()
     assert rel_l2(got_h, ref_h) < 1e-5
     assert rel_l2(out.float(), ref_o) < 4e-3
+
+
+@pytest.mark.parametrize("batch,ntok", [(2, 4800), (3, 300), (1, 128), (2, 77), (1, 8192)])
+def test_flash_attention_d512_single_head(batch, ntok):
+    """the VAE mid-block attention (one head of 512 channels): S and P stay in tensor memory, two passes over the keys"""
+    ops, L = _ops()
+    c = 512
+    qkv = (rnd(batch * ntok, 3 * c, seed=1) * 1.5).to(H16())
+    out = torch.full((batch * ntok, c), float("nan"), device=DEV, dtype=H16())
+    ops.flash_attn(qkv, batch, ntok, 1, out, 0, c, 2 * c, scale=c ** -0.5, head_dim=c).run()
+    torch.cuda.synchronize()
+    q, k, v = [t.float().reshape(batch, ntok, c) for t in qkv.split(c, dim=1)]
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * c ** -0.5, dim=-1) @ v).reshape(batch * ntok, c)
+    err = rel_l2(out.float(), ref)
+    assert err < 1e-2, f"d=512 flash attention rel-L2 {err}"
