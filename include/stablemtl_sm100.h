@@ -213,12 +213,13 @@ int smtl_xattn_run(const smtl_xattn_args* a, void* stream);
 /* The whole cross-attention step of BasicTransformerBlock (src/model/attention.py:355-373) in one pass over the fp32
  * residual stream:  hs += attn2(LayerNorm2(hs), text[task]);  out = LayerNorm3(hs)  (the 16-bit operand of the
  * feed-forward).  The prompt is constant per task, so attn2 is collapsed at load time into 2 * heads * ntok_pad vectors
- * per task (v = head * ntok_pad + token), LayerNorm2's affine folded in:
- *     ap  [ntask, V, C] 16-bit   gamma2 * (Wq_head^T k[token, head]) / sqrt(64)
- *     suma[ntask, V]    fp32     sum over C of the ROUNDED ap row (LayerNorm2's mean term)
- *     ca  [ntask, V]    fp32     beta2 . (Wq_head^T k[token, head]) / sqrt(64);  -inf for a padding token
- *     bm  [ntask, V, C] 16-bit   Wo[:, head] v[token, head]
- *     score = rstd * (hs . ap - mean * suma) + ca;  hs += bo + sum_v softmax_token(score)[v] * bm[v]
+ * per task (v = head * ntok_pad + token, padded with zero vectors to VP = the next multiple of 16), LayerNorm2's
+ * affine folded in; xn = (hs - mean) * rstd is the normalised row:
+ *     ap  [ntask, VP, C] 16-bit   gamma2 * (Wq_head^T k[token, head]) / sqrt(64)
+ *     ca  [ntask, VP]    fp32     beta2 . (Wq_head^T k[token, head]) / sqrt(64);  -inf for a padding token / vector
+ *     bmt [ntask, C, VP] 16-bit   (Wo[:, head] v[token, head]) transposed
+ *     score = xn . ap + ca;  hs += bo + sum_v softmax_token(score)[v] * bmt[:, v]
+ * Two skinny GEMMs per 16-row block on mma.sync (fp32 accumulate), four passes over the rows (one from HBM).
  * heads in {1, 2, 5, 10} (C = 64 * heads <= 640), ntok_pad in {4, 8}: smtl_xattnf_supported(). */
 typedef struct smtl_xattnf_args {
     float* hs;              /* fp32 [rows, ldh], updated in place */
@@ -230,9 +231,8 @@ typedef struct smtl_xattnf_args {
     int32_t ntok_pad;
     int32_t fmt16;
     const void* ap;
-    const float* suma;
     const float* ca;
-    const void* bm;
+    const void* bmt;
     const float* bo;        /* fp32 [C] attn2.to_out.0.bias */
     const float* gamma3;    /* LayerNorm3 affine, fp32 [C] */
     const float* beta3;
@@ -240,7 +240,7 @@ typedef struct smtl_xattnf_args {
     int32_t ldo;
     float eps2, eps3;
     int32_t pad_;
-} smtl_xattnf_args;
+} smtl_xattnf_args;         /* (no padding: 7 pointers after the two int32 above) */
 int smtl_xattnf_run(const smtl_xattnf_args* a, void* stream);
 int smtl_xattnf_supported(int32_t heads, int32_t ntok_pad);
 

@@ -127,6 +127,20 @@ if __name__ == "__main__":
         for args in [(8, 480, 640, 128), (8, 240, 320, 256), (8, 120, 160, 512), (8, 60, 80, 512), (112, 60, 80, 320)]:
             gn_case(*args)
         sys.exit(0)
+    if only == "xattn":        # collapsed cross-attention + LN2/LN3, UNet level 0 / 1, 112 images
+        for heads, rpg in ((5, 16 * 4800), (10, 16 * 1200)):
+            c, ntp = heads * 64, 4
+            hs = torch.randn(7 * rpg, c, device=DEV)
+            a0, bm = torch.randn(7, heads, ntp, c) * 0.05, torch.randn(7, heads, ntp, c) * 0.3
+            ap, ca, bmt = [t.to(DEV) for t in ops.xattn_tables(a0, torch.ones(c), torch.zeros(c), bm, [3, 3, 3, 4, 4, 3, 3], ntp)]
+            vec = lambda: torch.randn(c, device=DEV)
+            out = torch.empty(7 * rpg, c, device=DEV, dtype=ops.h16())
+            op = ops.xattn_fused(hs, ap, ca, bmt, vec(), vec(), vec(), list(range(7)), rpg, heads, ntp, out)
+            ms = timeit(op)
+            gb = op.bytes / 1e9
+            print(f"xattn_fused heads={heads} rows={7 * rpg}                       {ms:9.3f} ms {gb / ms * 1e3:8.1f} GB/s  "
+                  f"{gb / ms * 1e3 / 6552.6 * 100:5.1f}% of measured HBM copy peak", flush=True)
+        sys.exit(0)
     if only == "attn":
         for args in [(16, 4800, 5), (112, 4800, 5), (112, 1200, 10), (112, 300, 20), (112, 80, 20)]:
             attn_case(*args)

@@ -3,10 +3,12 @@
 # usage (through gpurun): bash scripts/gpu_check.sh <tag>     -> gpurun_out/<tag>_*
 tag=${1:-check}
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_kernels_gpu.py -x -q -k "d512" 2>&1 | tail -15 > gpurun_out/${tag}_d512.log
-if ! grep -q " passed" gpurun_out/${tag}_d512.log || grep -q "failed" gpurun_out/${tag}_d512.log; then
-  tail -n 15 gpurun_out/${tag}_d512.log; echo "d512 kernel test did not pass: stopping"; exit 1
+# the newest kernels first, under a short timeout: a hang must not eat the call
+timeout 300 python -m pytest tests/test_kernels_gpu.py -x -q -k "d512 or xattn_fused" 2>&1 | tail -25 > gpurun_out/${tag}_new.log
+if ! grep -q " passed" gpurun_out/${tag}_new.log || grep -q "failed" gpurun_out/${tag}_new.log; then
+  tail -n 25 gpurun_out/${tag}_new.log; echo "new-kernel tests did not pass: stopping"; exit 1
 fi
+timeout 300 python scripts/bench_kernels.py xattn > gpurun_out/${tag}_xattn.txt 2>&1; cat gpurun_out/${tag}_xattn.txt
 timeout 1500 python -m pytest tests/test_kernels_gpu.py -x -q 2>&1 | tail -25 > gpurun_out/${tag}_kernels.log
 timeout 3000 python -m pytest tests/test_pipeline_gpu.py tests/test_stream_shard_gpu.py -x -q 2>&1 | tail -30 > gpurun_out/${tag}_pipe.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1

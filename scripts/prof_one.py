@@ -67,13 +67,12 @@ elif case == "attn":
 elif case in ("xattnf", "xattnf10"):     # collapsed cross-attention + LN3, UNet level 0 / 1, 112 images
     heads = 5 if case == "xattnf" else 10
     rpg, groups, ntp, c = (16 * 4800, 7, 4, 320) if heads == 5 else (16 * 1200, 7, 4, 640)
-    v = heads * ntp
     hs = torch.randn(groups * rpg, c, device=DEV)
-    ap, bm = rb(7, v, c), rb(7, v, c)
-    ca = torch.randn(7, v, device=DEV)
+    a0, bm = torch.randn(7, heads, ntp, c) * 0.05, torch.randn(7, heads, ntp, c) * 0.3
+    ap, ca, bmt = [t.to(DEV) for t in ops.xattn_tables(a0, torch.ones(c), torch.zeros(c), bm, [3, 3, 3, 4, 4, 3, 3], ntp)]
     vec = lambda: torch.randn(c, device=DEV)
     out = torch.empty(groups * rpg, c, device=DEV, dtype=ops.h16())
-    op = ops.xattn_fused(hs, ap, ap.float().sum(-1), ca, bm, vec(), vec(), vec(), list(range(7)), rpg, heads, out)
+    op = ops.xattn_fused(hs, ap, ca, bmt, vec(), vec(), vec(), list(range(7)), rpg, heads, ntp, out)
 elif case == "gnapply":      # GroupNorm + SiLU, VAE decoder half resolution: 16 images, 256 channels, padded in and out
     b, h, wd, c = 16, 240, 320, 256
     x = rb(b * (h + 2) * (wd + 2), c)

@@ -104,7 +104,7 @@ class XattnFArgs(C.Structure):
     _fields_ = [
         ("hs", vp), ("ldh", i32), ("heads", i32), ("rows", i64), ("rows_per_group", i64),
         ("task_of_group", i32 * MAX_TASKS), ("ntok_pad", i32), ("fmt16", i32),
-        ("ap", vp), ("suma", vp), ("ca", vp), ("bm", vp), ("bo", vp), ("gamma3", vp), ("beta3", vp),
+        ("ap", vp), ("ca", vp), ("bmt", vp), ("bo", vp), ("gamma3", vp), ("beta3", vp),
         ("out_bf16", vp), ("ldo", i32), ("eps2", f32), ("eps3", f32), ("pad_", i32),
     ]
 

@@ -624,146 +624,168 @@ __global__ void xattn_kernel(const uint16_t* __restrict__ q, int ldq, int64_t ro
 }
 
 // ============================================================================================= fused cross-attention
-// BasicTransformerBlock's  h += attn2(LN2(h), text);  n3 = LN3(h)  (src/model/attention.py:355-373) in ONE pass over the
-// residual stream.  The prompt is one of a few CONSTANT task names (stablemtl_pipeline.py:464-472), so attn2 collapses:
-//     score[head, j] = (LN2(h) Wq_head^T) . k[j, head] / 8 = LN2(h) . (Wq_head^T k[j, head] / 8)         -> vectors A[head, j]
-//     attn2(h)       = sum_head sum_j softmax_j(score)[head, j] * (Wo[:, head] v[j, head]) + bo           -> vectors Bm[head, j]
-// and LN2's affine folds into A:  score = rstd * (h . A' - mean * sum(A')) + beta . A,  A' = gamma * A.
-// That is 2 * C * heads * n_tok multiply-adds per row on the FMA pipe instead of two C x C GEMMs, and the row is read
-// once (fp32), written once (fp32) and emitted once as the 16-bit LN3 operand of the feed-forward: 10 B per element
-// instead of 32 B over five kernels.
-// A warp owns R rows; a lane holds H float2 of each (C = 64 H channels).  Per batch of 32 (row, vector) pairs the lanes
-// accumulate partial dot products, a transposing warp reduction leaves pair k on lane k, the softmax runs on NT adjacent
-// lanes, and the probabilities are broadcast back with shuffles for the output accumulation.
-template <int H, int R, int NT>
-__global__ void __launch_bounds__(256) xattn_fused_kernel(
+// BasicTransformerBlock's  h += attn2(LN2(h), text);  n3 = LN3(h)  (src/model/attention.py:355-373) in ONE kernel over
+// the residual stream.  The prompt is one of a few CONSTANT task names (stablemtl_pipeline.py:464-472), so attn2
+// collapses at load time:
+//     score[head, j] = (LN2(h) Wq_head^T) . k[j, head] / 8 = xn . (gamma2 * Wq_head^T k[j, head] / 8) + beta2 . (...)
+//     attn2(h)       = sum_head sum_j softmax_j(score)[head, j] * (Wo[:, head] v[j, head]) + bo
+// i.e. two SKINNY GEMMs per row block -- [16 x C] x [C x V] and [16 x V] x [V x C] with V = heads * n_tok = 20..80
+// vectors -- instead of two C x C GEMMs, with xn = (h - mean) * rstd.  The row is read from HBM once (fp32), written once
+// (fp32) and emitted once as the 16-bit LN3 operand of the feed-forward: 10 B per element instead of 32 B over five
+// kernels.  N = 24..48 is far below a tcgen05 tile, so the contractions run on mma.sync.m16n8k16 (fp32 accumulate)
+// straight from registers: a warp owns 16 rows and makes four passes over them (LN2 statistics; scores; output + LN3
+// statistics; LN3), the re-reads hitting L1 / L2.  (The first version of this kernel did the dot products on the FMA
+// pipe: 7.4 k instructions per 8 rows, 183-206 registers, issue-bound at 3x the HBM floor.)
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, int fmt) {
+    if (fmt == FMT_F16)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    else
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// H = heads (C = 64 H), NT = padded token count (4 or 8).  Vectors v = head * NT + token, padded to VP (multiple of 16).
+template <int H, int NT>
+__global__ void __launch_bounds__(256) xattn_mma_kernel(
     float* __restrict__ hs, int ldh, int64_t rows_per_group, int ngroups, XattnK tk, const uint16_t* __restrict__ ap,
-    const float* __restrict__ suma, const float* __restrict__ ca, const uint16_t* __restrict__ bm,
-    const float* __restrict__ bo, const float* __restrict__ g3, const float* __restrict__ b3,
-    uint16_t* __restrict__ out, int ldo, float eps2, float eps3, int fmt) {
-    constexpr int C = 64 * H, V = H * NT, VB = 32 / R, NB = V / VB;
-    static_assert(V % VB == 0 && VB % NT == 0, "batches must hold whole heads");
+    const float* __restrict__ ca, const uint16_t* __restrict__ bmt, const float* __restrict__ bo,
+    const float* __restrict__ g3, const float* __restrict__ b3, uint16_t* __restrict__ out, int ldo, float eps2,
+    float eps3, int fmt) {
+    constexpr int C = 64 * H, V = H * NT, VP = (V + 15) / 16 * 16, NTILE = VP / 8, KV = VP / 16, KC = C / 16;
     const int lane = threadIdx.x & 31;
-    const int64_t wpg = (rows_per_group + R - 1) / R;                      // warps per row group
+    const int g = lane >> 2, tq = lane & 3;                                // fragment row within 8, column pair
+    const int64_t wpg = (rows_per_group + 15) / 16;                        // warps per row group
     const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int grp = (int)(gw / wpg);
     if (grp >= ngroups) return;
-    const int64_t local0 = (gw - (int64_t)grp * wpg) * R;
+    const int64_t local0 = (gw - (int64_t)grp * wpg) * 16;
     const int task = tk.task_of_group[grp];
-    const uint16_t* apT = ap + (int64_t)task * V * C;
-    const uint16_t* bmT = bm + (int64_t)task * V * C;
-    const float* saT = suma + task * V;
-    const float* caT = ca + task * V;
+    const uint16_t* apT = ap + (int64_t)task * VP * C;                     // [VP][C]
+    const uint16_t* bmT = bmt + (int64_t)task * C * VP;                    // [C][VP]
+    const float* caT = ca + task * VP;
+    // this lane's two rows (clamped: rows past the group's end are computed on the last row and not stored)
+    const bool live_a = local0 + g < rows_per_group, live_b = local0 + g + 8 < rows_per_group;
+    const int64_t last = (int64_t)grp * rows_per_group + rows_per_group - 1;
+    const int64_t row_a = live_a ? (int64_t)grp * rows_per_group + local0 + g : last;
+    const int64_t row_b = live_b ? (int64_t)grp * rows_per_group + local0 + g + 8 : last;
+    float* xa = hs + row_a * ldh + 2 * tq;
+    float* xb = hs + row_b * ldh + 2 * tq;
 
-    float2 v[R][H];
-    float mean[R], rstd[R];
-    bool live[R];
+    // ---- pass 1: LayerNorm 2 statistics.  This is the pass that reads HBM, so the warp sweeps whole rows (512
+    // contiguous bytes per instruction, four rows in flight); the fragment-shaped 8-byte accesses of the later passes
+    // then hit L1 / L2.  (Reading HBM in the fragment pattern -- 32 bytes of a row at a time -- ran at 21 % of the
+    // copy peak.)
+    float mean_a = 0.f, rstd_a = 0.f, mean_b = 0.f, rstd_b = 0.f;
+#pragma unroll 1
+    for (int r0 = 0; r0 < 16; r0 += 4) {
+        float2 v[4][H];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        live[r] = local0 + r < rows_per_group;
-        const float* src = hs + ((int64_t)grp * rows_per_group + local0 + r) * ldh;
+        for (int r = 0; r < 4; ++r) {
+            const int64_t row = (local0 + r0 + r < rows_per_group) ? (int64_t)grp * rows_per_group + local0 + r0 + r : last;
+            const float2* src = reinterpret_cast<const float2*>(hs + row * ldh);
 #pragma unroll
-        for (int i = 0; i < H; ++i)
-            v[r][i] = live[r] ? __ldg(reinterpret_cast<const float2*>(src) + lane + 32 * i) : make_float2(0.f, 0.f);
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < H; ++i) s += v[r][i].x + v[r][i].y;
-        mean[r] = warp_sum(s) * (1.0f / C);
-        float q = 0.f;
-#pragma unroll
-        for (int i = 0; i < H; ++i) {
-            const float a = v[r][i].x - mean[r], b = v[r][i].y - mean[r];
-            q += a * a + b * b;
+            for (int i = 0; i < H; ++i) v[r][i] = __ldg(src + lane + 32 * i);
         }
-        rstd[r] = rsqrtf(warp_sum(q) * (1.0f / C) + eps2);
-    }
-    // ---- scores and softmax: lane k of batch b ends up with p of (row k / VB, vector b * VB + k % VB)
-    float prob[NB];
-    const int my_r = lane / VB, my_vb = lane % VB;
-    float my_mean = 0.f, my_rstd = 0.f;
 #pragma unroll
-    for (int r = 0; r < R; ++r)
-        if (my_r == r) { my_mean = mean[r]; my_rstd = rstd[r]; }
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-        float part[32];
-#pragma unroll
-        for (int k = 0; k < 32; ++k) part[k] = 0.f;
-#pragma unroll
-        for (int vb = 0; vb < VB; ++vb) {
-            const uint32_t* av = reinterpret_cast<const uint32_t*>(apT + (int64_t)(b * VB + vb) * C);
+        for (int r = 0; r < 4; ++r) {
+            float s = 0.f, q = 0.f;
 #pragma unroll
             for (int i = 0; i < H; ++i) {
-                const float2 a = unpack16x2(__ldg(av + lane + 32 * i), fmt);
-#pragma unroll
-                for (int r = 0; r < R; ++r) part[r * VB + vb] = fmaf(v[r][i].x, a.x, fmaf(v[r][i].y, a.y, part[r * VB + vb]));
+                s += v[r][i].x + v[r][i].y;
+                q = fmaf(v[r][i].x, v[r][i].x, fmaf(v[r][i].y, v[r][i].y, q));
             }
-        }
-        const float d = warp_transpose_sum(part, lane);
-        const int vec = b * VB + my_vb;
-        float sc = my_rstd * (d - my_mean * __ldg(saT + vec)) + __ldg(caT + vec);       // -inf for a padded token
-        float mx = sc;
-#pragma unroll
-        for (int o = 1; o < NT; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        const float e = __expf(sc - mx);
-        float sum = e;
-#pragma unroll
-        for (int o = 1; o < NT; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        prob[b] = e / sum;
-    }
-    // ---- h += bo + sum_v p_v Bm_v
-#pragma unroll
-    for (int i = 0; i < H; ++i) {
-        const float2 t = __ldg(reinterpret_cast<const float2*>(bo) + lane + 32 * i);
-#pragma unroll
-        for (int r = 0; r < R; ++r) { v[r][i].x += t.x; v[r][i].y += t.y; }
-    }
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-#pragma unroll
-        for (int vb = 0; vb < VB; ++vb) {
-            float pr[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) pr[r] = __shfl_sync(0xffffffffu, prob[b], r * VB + vb);
-            const uint32_t* bv = reinterpret_cast<const uint32_t*>(bmT + (int64_t)(b * VB + vb) * C);
-#pragma unroll
-            for (int i = 0; i < H; ++i) {
-                const float2 m = unpack16x2(__ldg(bv + lane + 32 * i), fmt);
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    v[r][i].x = fmaf(pr[r], m.x, v[r][i].x);
-                    v[r][i].y = fmaf(pr[r], m.y, v[r][i].y);
-                }
-            }
+            s = warp_sum(s);
+            q = warp_sum(q);
+            const float m = s * (1.0f / C);
+            const float rs = rsqrtf(fmaxf(q * (1.0f / C) - m * m, 0.f) + eps2);
+            if (r0 + r == g) { mean_a = m; rstd_a = rs; }
+            if (r0 + r == g + 8) { mean_b = m; rstd_b = rs; }
         }
     }
-    // ---- store the residual stream, LayerNorm 3 -> 16-bit operand of the feed-forward
+
+    // ---- pass 2: scores[16 x VP] = xn[16 x C] . ap^T
+    float sc[NTILE][4];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        float s = 0.f;
+    for (int t = 0; t < NTILE; ++t) { sc[t][0] = sc[t][1] = sc[t][2] = sc[t][3] = 0.f; }
+#pragma unroll 2
+    for (int kk = 0; kk < KC; ++kk) {
+        const float2 a0 = __ldg(reinterpret_cast<const float2*>(xa + 16 * kk)), a1 = __ldg(reinterpret_cast<const float2*>(xa + 16 * kk + 8));
+        const float2 b0 = __ldg(reinterpret_cast<const float2*>(xb + 16 * kk)), b1 = __ldg(reinterpret_cast<const float2*>(xb + 16 * kk + 8));
+        uint32_t af[4];
+        af[0] = pack16x2((a0.x - mean_a) * rstd_a, (a0.y - mean_a) * rstd_a, fmt);
+        af[1] = pack16x2((b0.x - mean_b) * rstd_b, (b0.y - mean_b) * rstd_b, fmt);
+        af[2] = pack16x2((a1.x - mean_a) * rstd_a, (a1.y - mean_a) * rstd_a, fmt);
+        af[3] = pack16x2((b1.x - mean_b) * rstd_b, (b1.y - mean_b) * rstd_b, fmt);
 #pragma unroll
-        for (int i = 0; i < H; ++i) s += v[r][i].x + v[r][i].y;
-        const float m3 = warp_sum(s) * (1.0f / C);
-        float q = 0.f;
-#pragma unroll
-        for (int i = 0; i < H; ++i) {
-            const float a = v[r][i].x - m3, b = v[r][i].y - m3;
-            q += a * a + b * b;
+        for (int t = 0; t < NTILE; ++t) {
+            const uint32_t* bp = reinterpret_cast<const uint32_t*>(apT + (int64_t)(t * 8 + g) * C + 16 * kk + 2 * tq);
+            mma_16816(sc[t], af, __ldg(bp), __ldg(bp + 4), fmt);
         }
-        const float r3 = rsqrtf(warp_sum(q) * (1.0f / C) + eps3);
-        if (!live[r]) continue;
-        const int64_t row = (int64_t)grp * rows_per_group + local0 + r;
-        float2* dst = reinterpret_cast<float2*>(hs + row * ldh);
-        uint32_t* o16 = reinterpret_cast<uint32_t*>(out + row * ldo);
+    }
+    // ---- softmax over the NT tokens of every head; the probabilities become the A fragments of the second GEMM
+    uint32_t pf[KV][4];
 #pragma unroll
-        for (int i = 0; i < H; ++i) {
-            const int j = lane + 32 * i;
-            dst[j] = v[r][i];
-            const float2 g = __ldg(reinterpret_cast<const float2*>(g3) + j), bb = __ldg(reinterpret_cast<const float2*>(b3) + j);
-            o16[j] = pack16x2((v[r][i].x - m3) * r3 * g.x + bb.x, (v[r][i].y - m3) * r3 * g.y + bb.y, fmt);
+    for (int t = 0; t < NTILE; ++t) {
+        const float2 cc = __ldg(reinterpret_cast<const float2*>(caT + t * 8 + 2 * tq));      // -inf on padding vectors
+        float v0 = sc[t][0] + cc.x, v1 = sc[t][1] + cc.y, v2 = sc[t][2] + cc.x, v3 = sc[t][3] + cc.y;
+        float ma = fmaxf(v0, v1), mb = fmaxf(v2, v3);
+#pragma unroll
+        for (int o = 1; o < NT / 2; o <<= 1) {
+            ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, o));
+            mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+        }
+        ma = (ma == -INFINITY) ? 0.f : ma;                                   // a head made of padding only
+        mb = (mb == -INFINITY) ? 0.f : mb;
+        v0 = __expf(v0 - ma); v1 = __expf(v1 - ma); v2 = __expf(v2 - mb); v3 = __expf(v3 - mb);
+        float la = v0 + v1, lb = v2 + v3;
+#pragma unroll
+        for (int o = 1; o < NT / 2; o <<= 1) {
+            la += __shfl_xor_sync(0xffffffffu, la, o);
+            lb += __shfl_xor_sync(0xffffffffu, lb, o);
+        }
+        const float ia = la > 0.f ? 1.0f / la : 0.f, ib = lb > 0.f ? 1.0f / lb : 0.f;
+        pf[t >> 1][(t & 1) * 2] = pack16x2(v0 * ia, v1 * ia, fmt);
+        pf[t >> 1][(t & 1) * 2 + 1] = pack16x2(v2 * ib, v3 * ib, fmt);
+    }
+    // ---- pass 3: h += bo + P . Bm, one 8-column block at a time; LayerNorm 3 statistics on the way
+    float s3a = 0.f, q3a = 0.f, s3b = 0.f, q3b = 0.f;
+#pragma unroll 2
+    for (int n = 0; n < C / 8; ++n) {
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint32_t* bp = reinterpret_cast<const uint32_t*>(bmT + (int64_t)(n * 8 + g) * VP + 2 * tq);
+#pragma unroll
+        for (int kv = 0; kv < KV; ++kv) mma_16816(d, pf[kv], __ldg(bp + 8 * kv), __ldg(bp + 8 * kv + 4), fmt);
+        const float2 bias = __ldg(reinterpret_cast<const float2*>(bo + 8 * n + 2 * tq));
+        float2 a = *reinterpret_cast<const float2*>(xa + 8 * n), b = *reinterpret_cast<const float2*>(xb + 8 * n);
+        a.x += bias.x + d[0]; a.y += bias.y + d[1];
+        b.x += bias.x + d[2]; b.y += bias.y + d[3];
+        if (live_a) *reinterpret_cast<float2*>(xa + 8 * n) = a;
+        if (live_b) *reinterpret_cast<float2*>(xb + 8 * n) = b;
+        s3a += a.x + a.y; q3a = fmaf(a.x, a.x, fmaf(a.y, a.y, q3a));
+        s3b += b.x + b.y; q3b = fmaf(b.x, b.x, fmaf(b.y, b.y, q3b));
+    }
+#pragma unroll
+    for (int o = 1; o < 4; o <<= 1) {
+        s3a += __shfl_xor_sync(0xffffffffu, s3a, o); q3a += __shfl_xor_sync(0xffffffffu, q3a, o);
+        s3b += __shfl_xor_sync(0xffffffffu, s3b, o); q3b += __shfl_xor_sync(0xffffffffu, q3b, o);
+    }
+    const float m3a = s3a * (1.0f / C), m3b = s3b * (1.0f / C);
+    const float r3a = rsqrtf(fmaxf(q3a * (1.0f / C) - m3a * m3a, 0.f) + eps3);
+    const float r3b = rsqrtf(fmaxf(q3b * (1.0f / C) - m3b * m3b, 0.f) + eps3);
+    // ---- pass 4: LayerNorm 3 of the rows just written (every lane re-reads its OWN stores) -> 16-bit operand
+    uint16_t* oa = out + row_a * ldo + 2 * tq;
+    uint16_t* ob = out + row_b * ldo + 2 * tq;
+#pragma unroll 4
+    for (int n = 0; n < C / 8; ++n) {
+        const float2 gg = __ldg(reinterpret_cast<const float2*>(g3 + 8 * n + 2 * tq)), bb = __ldg(reinterpret_cast<const float2*>(b3 + 8 * n + 2 * tq));
+        if (live_a) {
+            const float2 a = *reinterpret_cast<const float2*>(xa + 8 * n);
+            *reinterpret_cast<uint32_t*>(oa + 8 * n) = pack16x2((a.x - m3a) * r3a * gg.x + bb.x, (a.y - m3a) * r3a * gg.y + bb.y, fmt);
+        }
+        if (live_b) {
+            const float2 b = *reinterpret_cast<const float2*>(xb + 8 * n);
+            *reinterpret_cast<uint32_t*>(ob + 8 * n) = pack16x2((b.x - m3b) * r3b * gg.x + bb.x, (b.y - m3b) * r3b * gg.y + bb.y, fmt);
         }
     }
 }
@@ -1189,13 +1211,13 @@ extern "C" int smtl_xattn_run(const smtl_xattn_args* a, void* stream) {
     return SMTL_OK;
 }
 
-template <int H, int R, int NT>
-static int launch_xattn_fused(const smtl_xattnf_args* a, const XattnK& tk, int ngroups, cudaStream_t st) {
-    const int64_t wpg = (a->rows_per_group + R - 1) / R;
+template <int H, int NT>
+static int launch_xattn_mma(const smtl_xattnf_args* a, const XattnK& tk, int ngroups, cudaStream_t st) {
+    const int64_t wpg = (a->rows_per_group + 15) / 16;
     const int64_t warps = wpg * ngroups;
-    xattn_fused_kernel<H, R, NT><<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(
-        a->hs, a->ldh, a->rows_per_group, ngroups, tk, (const uint16_t*)a->ap, a->suma, a->ca, (const uint16_t*)a->bm,
-        a->bo, a->gamma3, a->beta3, (uint16_t*)a->out_bf16, a->ldo, a->eps2, a->eps3, a->fmt16);
+    xattn_mma_kernel<H, NT><<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(
+        a->hs, a->ldh, a->rows_per_group, ngroups, tk, (const uint16_t*)a->ap, a->ca, (const uint16_t*)a->bmt, a->bo,
+        a->gamma3, a->beta3, (uint16_t*)a->out_bf16, a->ldo, a->eps2, a->eps3, a->fmt16);
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;
 }
@@ -1205,7 +1227,7 @@ extern "C" int smtl_xattnf_supported(int32_t heads, int32_t ntok_pad) {
 }
 
 extern "C" int smtl_xattnf_run(const smtl_xattnf_args* a, void* stream) {
-    SMTL_CHECK_ARG(a && a->hs && a->ap && a->suma && a->ca && a->bm && a->bo && a->gamma3 && a->beta3 && a->out_bf16,
+    SMTL_CHECK_ARG(a && a->hs && a->ap && a->ca && a->bmt && a->bo && a->gamma3 && a->beta3 && a->out_bf16,
                    "xattnf: NULL argument");
     SMTL_CHECK_ARG(a->rows > 0 && a->rows_per_group > 0 && a->rows % a->rows_per_group == 0, "xattnf: bad rows");
     const int ngroups = (int)(a->rows / a->rows_per_group);
@@ -1222,10 +1244,10 @@ extern "C" int smtl_xattnf_run(const smtl_xattnf_args* a, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const bool n8 = a->ntok_pad == 8;
     switch (a->heads) {
-        case 1: return n8 ? launch_xattn_fused<1, 4, 8>(a, tk, ngroups, st) : launch_xattn_fused<1, 8, 4>(a, tk, ngroups, st);
-        case 2: return n8 ? launch_xattn_fused<2, 4, 8>(a, tk, ngroups, st) : launch_xattn_fused<2, 8, 4>(a, tk, ngroups, st);
-        case 5: return n8 ? launch_xattn_fused<5, 4, 8>(a, tk, ngroups, st) : launch_xattn_fused<5, 8, 4>(a, tk, ngroups, st);
-        default: return n8 ? launch_xattn_fused<10, 4, 8>(a, tk, ngroups, st) : launch_xattn_fused<10, 4, 4>(a, tk, ngroups, st);
+        case 1: return n8 ? launch_xattn_mma<1, 8>(a, tk, ngroups, st) : launch_xattn_mma<1, 4>(a, tk, ngroups, st);
+        case 2: return n8 ? launch_xattn_mma<2, 8>(a, tk, ngroups, st) : launch_xattn_mma<2, 4>(a, tk, ngroups, st);
+        case 5: return n8 ? launch_xattn_mma<5, 8>(a, tk, ngroups, st) : launch_xattn_mma<5, 4>(a, tk, ngroups, st);
+        default: return n8 ? launch_xattn_mma<10, 8>(a, tk, ngroups, st) : launch_xattn_mma<10, 4>(a, tk, ngroups, st);
     }
 }
 

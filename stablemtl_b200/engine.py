@@ -245,12 +245,9 @@ class UNetWeights:
                 # attn2 collapsed onto the constant prompt (attention.py:355-364; smtl_xattnf_args): 2 * H * ntp vectors
                 T_, n = len(self.tasks), self.ntp
                 a0 = 0.125 * torch.einsum("tjhd,hdc->thjc", kc.view(T_, n, H_, 64), wq.view(H_, 64, C_))     # scale 1/sqrt(64)
-                valid = (torch.arange(n)[None, :] < torch.tensor(self.ntok)[:, None])[:, None, :]           # [T, 1, n]
-                ap = (a0 * w_ln2g(g, t)).masked_fill(~valid[..., None], 0.0).reshape(T_, H_ * n, C_).to(ops.h16())
-                ca = (a0 * g(f"{t}.norm2.bias")).sum(-1).masked_fill(~valid, float("-inf")).reshape(T_, H_ * n)
-                bm = torch.einsum("tjhd,chd->thjc", vc.view(T_, n, H_, 64), wo.view(C_, H_, 64)).reshape(T_, H_ * n, C_)
-                w[p + ".xf.ap"], w[p + ".xf.sa"], w[p + ".xf.ca"] = ap, ap.float().sum(-1), ca
-                w[p + ".xf.bm"] = bm.to(ops.h16())
+                bm = torch.einsum("tjhd,chd->thjc", vc.view(T_, n, H_, 64), wo.view(C_, H_, 64))
+                w[p + ".xf.ap"], w[p + ".xf.ca"], w[p + ".xf.bmt"] = ops.xattn_tables(
+                    a0, w_ln2g(g, t), g(f"{t}.norm2.bias"), bm, self.ntok, n)
                 w[p + ".xf"] = True
             else:
                 w[p + ".q2"] = wq.to(ops.h16())
@@ -539,8 +536,8 @@ class UNetPlan(_PlanBase):
         n3 = att
         if wt.get(p + ".xf", False):
             # collapsed onto the constant prompt, fused with LayerNorm2, the residual add and LayerNorm3: one pass over hs
-            add(ops.xattn_fused(hs, wt[p + ".xf.ap"], wt[p + ".xf.sa"], wt[p + ".xf.ca"], wt[p + ".xf.bm"], wt[p + ".o2.b"],
-                                wt[p + ".ln3g"], wt[p + ".ln3b"], self.group_tasks, rpg, heads, n3))
+            add(ops.xattn_fused(hs, wt[p + ".xf.ap"], wt[p + ".xf.ca"], wt[p + ".xf.bmt"], wt[p + ".o2.b"],
+                                wt[p + ".ln3g"], wt[p + ".ln3b"], self.group_tasks, rpg, heads, W.ntp, n3))
         else:
             n2 = att
             add(ops.layer_norm(hs, wt[p + ".ln2g"], wt[p + ".ln2b"], n2))

@@ -328,25 +328,45 @@ def xattn_fused_supported(heads, ntok_pad):
     return bool(L.lib.smtl_xattnf_supported(heads, ntok_pad))
 
 
-def xattn_fused(hs, ap, suma, ca, bm, bo, gamma3, beta3, task_of_group, rows_per_group, heads, out, eps2=1e-5, eps3=1e-5):
+def xattn_tables(a0, gamma2, beta2, bm, ntok, ntok_pad):
+    """Host-side packing of the collapsed cross-attention (smtl_xattnf_args): a0 [T, H, ntp, C] = Wq_head^T k / 8 and
+    bm [T, H, ntp, C] = Wo[:, head] v, fp32 -> (ap [T, VP, C] 16-bit, ca [T, VP] fp32, bmt [T, C, VP] 16-bit) with the
+    vectors padded to VP = a multiple of 16 and the padding tokens masked (zero vector, -inf constant)."""
+    T, H, n, C = a0.shape
+    assert n == ntok_pad and bm.shape == a0.shape
+    V = H * n
+    VP = (V + 15) // 16 * 16
+    valid = (torch.arange(n)[None, :] < torch.as_tensor(ntok)[:, None])[:, None, :].expand(T, H, n)          # [T, H, n]
+    ap = torch.zeros(T, VP, C)
+    ap[:, :V] = (a0 * gamma2).masked_fill(~valid[..., None], 0.0).reshape(T, V, C)
+    ca = torch.full((T, VP), float("-inf"))
+    ca[:, :V] = (a0 * beta2).sum(-1).masked_fill(~valid, float("-inf")).reshape(T, V)
+    bmt = torch.zeros(T, C, VP)
+    bmt[:, :, :V] = bm.reshape(T, V, C).transpose(1, 2)
+    return ap.to(h16()).contiguous(), ca.contiguous(), bmt.to(h16()).contiguous()
+
+
+def xattn_fused(hs, ap, ca, bmt, bo, gamma3, beta3, task_of_group, rows_per_group, heads, ntok_pad, out, eps2=1e-5, eps3=1e-5):
     """hs += attn2(LayerNorm2(hs), text[task]); out = LayerNorm3(hs) -- the collapsed cross-attention (see the header)."""
     a = L.XattnFArgs()
     c = heads * 64
-    ntask, v, _ = ap.shape
-    ntp = v // heads
+    ntask, vp, _ = ap.shape
+    ntp = ntok_pad
+    v = heads * ntp
+    assert vp == (v + 15) // 16 * 16
     assert hs.dtype == F32 and hs.shape[1] == c and hs.stride(1) == 1 and out.dtype == BF16 and out.shape == hs.shape
-    assert ap.dtype == BF16 and bm.dtype == BF16 and ap.shape == bm.shape == (ntask, heads * ntp, c) and ap.is_contiguous() and bm.is_contiguous()
-    assert suma.dtype == F32 and ca.dtype == F32 and suma.shape == ca.shape == (ntask, v) and suma.is_contiguous() and ca.is_contiguous()
+    assert ap.dtype == BF16 and bmt.dtype == BF16 and ap.shape == (ntask, vp, c) and bmt.shape == (ntask, c, vp)
+    assert ap.is_contiguous() and bmt.is_contiguous() and ca.dtype == F32 and ca.shape == (ntask, vp) and ca.is_contiguous()
     assert hs.shape[0] % rows_per_group == 0 and len(task_of_group) == hs.shape[0] // rows_per_group
     a.hs, a.ldh, a.heads, a.rows, a.rows_per_group = hs.data_ptr(), hs.stride(0), heads, hs.shape[0], rows_per_group
     for i in range(L.MAX_TASKS):
         a.task_of_group[i] = max(task_of_group[i], 0) if i < len(task_of_group) else 0
     a.ntok_pad, a.fmt16 = ntp, PREC["fmt"]
-    a.ap, a.suma, a.ca, a.bm, a.bo = ap.data_ptr(), suma.data_ptr(), ca.data_ptr(), bm.data_ptr(), bo.data_ptr()
+    a.ap, a.ca, a.bmt, a.bo = ap.data_ptr(), ca.data_ptr(), bmt.data_ptr(), bo.data_ptr()
     a.gamma3, a.beta3, a.out_bf16, a.ldo, a.eps2, a.eps3 = gamma3.data_ptr(), beta3.data_ptr(), out.data_ptr(), out.stride(0), eps2, eps3
-    op = Op(L.OP_XATTNF, a, (hs, ap, suma, ca, bm, bo, gamma3, beta3, out), 4 * hs.shape[0] * c * c, "xattn_fused",
+    op = Op(L.OP_XATTNF, a, (hs, ap, ca, bmt, bo, gamma3, beta3, out), 4 * hs.shape[0] * c * c, "xattn_fused",
             hs.numel() * 8 + out.numel() * 2, outs16=(out,))
-    op.flops_exec = 4 * hs.shape[0] * c * v            # what the FMA pipe runs: 2 * C * V multiply-adds per row
+    op.flops_exec = 4 * hs.shape[0] * c * vp           # what runs: two [rows x C] x [C x VP] skinny GEMMs on mma.sync
     return op
 
 

@@ -142,9 +142,11 @@ def test_collapsed_cross_attention_tables_reproduce_attn2():
                        for hd in range(H)], dim=1)
         ref = o @ sd[t + ".attn2.to_out.0.weight"].t() + sd[t + ".attn2.to_out.0.bias"]
         mean, rstd = h.mean(1, keepdim=True), (h.var(1, unbiased=False, keepdim=True) + 1e-5).rsqrt()
-        ap, sa, ca, bm = w[p + ".xf.ap"][ti].float(), w[p + ".xf.sa"][ti], w[p + ".xf.ca"][ti], w[p + ".xf.bm"][ti].float()
-        score = rstd * (h @ ap.t() - mean * sa) + ca                                     # [rows, H * n]
-        prob = torch.softmax(score.view(-1, H, n), -1).view(-1, H * n)
-        got = prob @ bm + w[p + ".o2.b"]
+        ap, ca, bmt = w[p + ".xf.ap"][ti].float(), w[p + ".xf.ca"][ti], w[p + ".xf.bmt"][ti].float()
+        V, VP = H * n, ap.shape[0]
+        assert VP % 16 == 0 and VP >= V and bmt.shape == (C, VP) and bool(torch.isinf(ca[V:]).all())
+        score = ((h - mean) * rstd) @ ap.t() + ca                                       # [rows, VP]
+        prob = torch.softmax(score[:, :V].view(-1, H, n), -1).view(-1, V)
+        got = prob @ bmt[:, :V].t() + w[p + ".o2.b"]
         assert float(prob.view(-1, H, n)[:, :, text[task].shape[0]:].abs().max() if text[task].shape[0] < n else 0.0) == 0.0
         assert ((got - ref).norm() / ref.norm()).item() < 2e-3, task                    # the tables are stored in 16 bits

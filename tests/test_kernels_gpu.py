@@ -860,38 +860,39 @@ def test_conv_head_with_taps_folded_into_n(b, h, w, cin, cout):
     assert rel_l2(out, ref) < 2e-5
 
 
-@pytest.mark.parametrize("heads,ntp,rpg,groups", [(5, 4, 100, 3), (10, 4, 77, 2), (2, 8, 33, 4), (1, 4, 8, 1), (5, 8, 300, 2)])
+@pytest.mark.parametrize("heads,ntp,rpg,groups", [(5, 4, 100, 3), (10, 4, 77, 2), (2, 8, 33, 4), (1, 4, 8, 1), (5, 8, 300, 2),
+                                                  (10, 8, 16, 1)])
 def test_xattn_fused_collapsed_cross_attention(heads, ntp, rpg, groups):
-    """hs += bo + sum_v softmax_token(rstd (hs . ap - mean suma) + ca)[v] bm[v];  out = LayerNorm3(hs)  -- one pass"""
+    """hs += bo + sum_v softmax_token(LN2-normalised(hs) . ap + ca)[v] bm[v];  out = LayerNorm3(hs)  -- one kernel, two
+    skinny GEMMs on mma.sync; tables packed by ops.xattn_tables (padding tokens / vectors masked)"""
     ops, L = _ops()
-    c, v, ntask = heads * 64, heads * ntp, 3
+    c, ntask = heads * 64, 3
     hs = rnd(groups * rpg, c, seed=1) * 2 + 0.5
-    ap = (rnd(ntask, v, c, seed=2) * 0.05).to(H16())
-    bm = (rnd(ntask, v, c, seed=3) * 0.3).to(H16())
-    ca = rnd(ntask, v, seed=4)
+    a0 = (rnd(ntask, heads, ntp, c, seed=2) * 0.05).cpu()
+    bm = (rnd(ntask, heads, ntp, c, seed=3) * 0.3).cpu()
+    g2, b2 = (rnd(c, seed=8) * 0.1 + 1).cpu(), (rnd(c, seed=9) * 0.1).cpu()
     ntok = [ntp, ntp - 1, max(1, ntp - 2)]
-    for t in range(ntask):                                         # padding tokens: zero vector, -inf constant
-        pad = torch.arange(v, device=DEV) % ntp >= ntok[t]
-        ap[t, pad] = 0
-        ca[t, pad] = float("-inf")
-    suma = ap.float().sum(-1)
+    ap, ca, bmt = [t.to(DEV) for t in ops.xattn_tables(a0, g2, b2, bm, ntok, ntp)]
+    v = heads * ntp
     bo, g3, b3 = rnd(c, seed=5), rnd(c, seed=6) + 1, rnd(c, seed=7)
     tasks = [(g * 2) % ntask for g in range(groups)]
     ref_h, ref_o = [], []
     for g, t in enumerate(tasks):
         h = hs[g * rpg:(g + 1) * rpg].double()
         mean, rstd = h.mean(1, keepdim=True), (h.var(1, unbiased=False, keepdim=True) + 1e-5).rsqrt()
-        score = rstd * (h @ ap[t].double().t() - mean * suma[t].double()) + ca[t].double()
+        score = ((h - mean) * rstd) @ ap[t, :v].double().t() + ca[t, :v].double()
         prob = torch.softmax(score.view(-1, heads, ntp), -1).view(-1, v)
-        hn = h + bo.double() + prob @ bm[t].double()
+        hn = h + bo.double() + prob @ bmt[t, :, :v].double().t()
         ref_h.append(hn)
         ref_o.append(F.layer_norm(hn, (c,), g3.double(), b3.double(), 1e-5))
     ref_h, ref_o = torch.cat(ref_h), torch.cat(ref_o)
     out = torch.full((groups * rpg, c), float("nan"), device=DEV, dtype=H16())
     got_h = hs.clone()
-    ops.xattn_fused(got_h, ap, suma, ca, bm, bo, g3, b3, tasks, rpg, heads, out).run()
+    ops.xattn_fused(got_h, ap, ca, bmt, bo, g3, b3, tasks, rpg, heads, ntp, out).run()
     torch.cuda.synchronize()
-    assert rel_l2(got_h, ref_h) < 1e-5
+    # the normalised row and the probabilities enter the tensor cores in 16 bits: the ADDED term carries ~1e-3 relative
+    assert rel_l2(got_h - hs, ref_h - hs.double()) < 6e-3
+    assert rel_l2(got_h, ref_h) < 1e-3
     assert rel_l2(out.float(), ref_o) < 4e-3
 
 
