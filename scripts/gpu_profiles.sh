@@ -7,9 +7,9 @@ python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-multi-block > gpurun
 timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_launches.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-multi-block > gpurun_out/${tag}_launches_ncu.log 2>&1
 python scripts/summarize_launches.py gpurun_out/${tag}_launches.csv > gpurun_out/${tag}_launches_summary.txt
-for c in conv512 conv128 gnapply attn xattnf; do
+for c in conv512 conv128 gnapply attn vattn xattnf; do
   python scripts/prof_one.py $c > /dev/null 2>&1 || { echo "prof_one $c failed"; continue; }
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:'smtl_|xattn_fused|gn_apply2' -s 2 -c 1 -f \
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:'smtl_|xattn_mma|gn_apply2' -s 2 -c 1 -f \
       -o gpurun_out/${tag}_full_$c python scripts/prof_one.py $c > gpurun_out/${tag}_full_$c.log 2>&1
 done
 head -n 14 gpurun_out/${tag}_launches_summary.txt

@@ -73,6 +73,11 @@ elif case in ("xattnf", "xattnf10"):     # collapsed cross-attention + LN3, UNet
     vec = lambda: torch.randn(c, device=DEV)
     out = torch.empty(groups * rpg, c, device=DEV, dtype=ops.h16())
     op = ops.xattn_fused(hs, ap, ca, bmt, vec(), vec(), vec(), list(range(7)), rpg, heads, ntp, out)
+elif case == "vattn":        # VAE mid-block attention: one head of 512 channels, 16 images of 4800 tokens
+    batch, ntok, c = 16, 4800, 512
+    qkv = rb(batch * ntok, 3 * c)
+    out = torch.empty(batch * ntok, c, device=DEV, dtype=ops.h16())
+    op = ops.flash_attn(qkv, batch, ntok, 1, out, 0, c, 2 * c, scale=c ** -0.5, head_dim=c)
 elif case == "gnapply":      # GroupNorm + SiLU, VAE decoder half resolution: 16 images, 256 channels, padded in and out
     b, h, wd, c = 16, 240, 320, 256
     x = rb(b * (h + 2) * (wd + 2), c)

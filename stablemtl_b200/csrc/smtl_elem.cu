@@ -73,12 +73,16 @@ __device__ __forceinline__ void gn_group_stats(const long long* __restrict__ st0
 
 // GroupNorm apply from producer-side per-(image, channel) statistics (smtl_gemm_args.stats): one streaming pass.
 // grid (blocks_per_image, batch), 256 threads; each thread handles 8 channels of one (padded) pixel per step.
-template <bool x16>
+// Template parameters are everything that would otherwise be a per-vector run-time choice: ptxas turns such choices
+// into predicated instruction pairs, and a predicated-off instruction still takes its issue slot (the run-time format
+// alone doubled the conversions of this kernel).  x16: 16-bit input; FMT: 16-bit format; RAW: also emit the
+// un-normalised copy; SAME: input and output share the pixel grid (both padded or both compact).
+template <bool x16, int FMT, bool RAW, bool SAME>
 __global__ void __launch_bounds__(320, 3) gn_apply2_kernel(
     const void* __restrict__ x0, const void* __restrict__ x1, int c0, int c1, const long long* __restrict__ st0,
     const long long* __restrict__ st1, int replicas, int batch, int h, int w, int groups, float eps,
     const float* __restrict__ gamma, const float* __restrict__ beta, int do_silu, int pad_out,
-    uint16_t* __restrict__ out, uint16_t* __restrict__ raw, int fmt, FastDiv div_wp, int in_pad) {
+    uint16_t* __restrict__ out, uint16_t* __restrict__ raw, FastDiv div_wp, int in_pad) {
     extern __shared__ float sm[];   // scale[C], shift[C], gmean[groups], grstd[groups]
     const int C = c0 + c1;
     float* scale = sm;
@@ -127,15 +131,17 @@ __global__ void __launch_bounds__(320, 3) gn_apply2_kernel(
     uint32_t p = p_begin + pl;
     int y = (int)fastdiv(p, div_wp), x = (int)p - y * wp;      // coordinates on the OUTPUT grid (hp x wp)
     int in_w, in_off;                                          // input pixel = y * in_w + x + in_off
-    if ((pad_out != 0) == (in_pad != 0)) { in_w = wp; in_off = 0; }       // same grid
+    if (SAME) { in_w = wp; in_off = 0; }                                  // same grid: input pixel = output pixel
     else if (pad_out) { in_w = w; in_off = -w - 1; }                      // compact in, padded out
     else { in_w = w + 2; in_off = w + 3; }                                // padded in, compact out
     const char* in_img = reinterpret_cast<const char*>(src) + (in_base * ld + cc) * (x16 ? 2 : 4);
     const int64_t in_pitch = (int64_t)ld * (x16 ? 2 : 4);      // bytes per input pixel
     uint16_t* out_ptr = out + ((int64_t)b * npix + p) * C + c;
-    uint16_t* raw_ptr = raw ? raw + ((int64_t)b * npix + p) * C + c : nullptr;
+    uint16_t* raw_ptr = RAW ? raw + ((int64_t)b * npix + p) * C + c : nullptr;
+    const char* in_ptr = in_img + (int64_t)p * in_pitch;       // SAME: walks with the output pointer
+    const int64_t in_step = (int64_t)ppb * in_pitch;
     const int64_t out_step = (int64_t)ppb * C;                 // elements between this thread's consecutive pixels
-    for (; p < p_end; p += U * ppb, out_ptr += U * out_step) {
+    for (; p < p_end; p += U * ppb, out_ptr += U * out_step, in_ptr += U * in_step) {
         uint4 u[U];
         float4 f0[U], f1[U];
         bool live[U], inter[U];
@@ -145,7 +151,7 @@ __global__ void __launch_bounds__(320, 3) gn_apply2_kernel(
             inter[k] = live[k] && (!pad_out || (y >= 1 && y <= h && x >= 1 && x <= w));
             u[k] = make_uint4(0, 0, 0, 0);
             if (inter[k]) {
-                const char* src_px = in_img + (int64_t)(y * in_w + x + in_off) * in_pitch;
+                const char* src_px = SAME ? in_ptr + k * in_step : in_img + (int64_t)(y * in_w + x + in_off) * in_pitch;
                 if (x16) {
                     u[k] = __ldg(reinterpret_cast<const uint4*>(src_px));
                 } else {
@@ -163,18 +169,18 @@ __global__ void __launch_bounds__(320, 3) gn_apply2_kernel(
             if (inter[k]) {
                 float v[8];
                 if (x16) {
-                    r = u[k];
+                    if (RAW) r = u[k];
                     float2 f;
-                    f = unpack16x2(u[k].x, fmt); v[0] = f.x; v[1] = f.y;
-                    f = unpack16x2(u[k].y, fmt); v[2] = f.x; v[3] = f.y;
-                    f = unpack16x2(u[k].z, fmt); v[4] = f.x; v[5] = f.y;
-                    f = unpack16x2(u[k].w, fmt); v[6] = f.x; v[7] = f.y;
+                    f = unpack16x2(u[k].x, FMT); v[0] = f.x; v[1] = f.y;
+                    f = unpack16x2(u[k].y, FMT); v[2] = f.x; v[3] = f.y;
+                    f = unpack16x2(u[k].z, FMT); v[4] = f.x; v[5] = f.y;
+                    f = unpack16x2(u[k].w, FMT); v[6] = f.x; v[7] = f.y;
                 } else {
                     v[0] = f0[k].x; v[1] = f0[k].y; v[2] = f0[k].z; v[3] = f0[k].w;
                     v[4] = f1[k].x; v[5] = f1[k].y; v[6] = f1[k].z; v[7] = f1[k].w;
-                    if (raw) {
-                        r.x = pack16x2(v[0], v[1], fmt); r.y = pack16x2(v[2], v[3], fmt);
-                        r.z = pack16x2(v[4], v[5], fmt); r.w = pack16x2(v[6], v[7], fmt);
+                    if (RAW) {
+                        r.x = pack16x2(v[0], v[1], FMT); r.y = pack16x2(v[2], v[3], FMT);
+                        r.z = pack16x2(v[4], v[5], FMT); r.w = pack16x2(v[6], v[7], FMT);
                     }
                 }
 #pragma unroll
@@ -190,13 +196,13 @@ __global__ void __launch_bounds__(320, 3) gn_apply2_kernel(
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = silu_exact(v[i]);
                 }
-                o.x = pack16x2(v[0], v[1], fmt); o.y = pack16x2(v[2], v[3], fmt);
-                o.z = pack16x2(v[4], v[5], fmt); o.w = pack16x2(v[6], v[7], fmt);
+                o.x = pack16x2(v[0], v[1], FMT); o.y = pack16x2(v[2], v[3], FMT);
+                o.z = pack16x2(v[4], v[5], FMT); o.w = pack16x2(v[6], v[7], FMT);
             }
             *reinterpret_cast<uint4*>(out_ptr + k * out_step) = o;
-            if (raw) *reinterpret_cast<uint4*>(raw_ptr + k * out_step) = r;
+            if (RAW) *reinterpret_cast<uint4*>(raw_ptr + k * out_step) = r;
         }
-        if (raw) raw_ptr += U * out_step;
+        if (RAW) raw_ptr += U * out_step;
     }
 }
 
@@ -222,11 +228,11 @@ __global__ void gn_finalize_kernel(const long long* __restrict__ st, int replica
 // A warp normalises R rows at once; a lane holds NV float4 of each (C <= 128 NV).  All R * NV loads are issued before
 // the first reduction: with one row per warp (and registers sized for C = 1280 whatever C was) the kernel sat at 45 % of
 // the copy peak -- too few bytes in flight per SM.
-template <bool IN_BF16, int NV, int R>
+template <bool IN_BF16, int NV, int R, int FMT>
 __global__ void ln_kernel(const void* __restrict__ xv, int c, int ldx, int64_t rows, float eps, int64_t rows_per_group,
                           const float* __restrict__ gamma0, const float* __restrict__ beta0,
                           uint16_t* __restrict__ out0, const float* __restrict__ gamma1,
-                          const float* __restrict__ beta1, uint16_t* __restrict__ out1, int ldo, int fmt) {
+                          const float* __restrict__ beta1, uint16_t* __restrict__ out1, int ldo) {
     const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
     if (row0 >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -245,7 +251,7 @@ __global__ void ln_kernel(const void* __restrict__ xv, int c, int ldx, int64_t r
                 if (IN_BF16) {
                     const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(xv) +
                                                                          row * ldx + 4 * j));
-                    const float2 a = unpack16x2(u.x, fmt), b = unpack16x2(u.y, fmt);
+                    const float2 a = unpack16x2(u.x, FMT), b = unpack16x2(u.y, FMT);
                     v[r][i] = make_float4(a.x, a.y, b.x, b.y);
                 } else {
                     v[r][i] = ldg4(reinterpret_cast<const float*>(xv) + row * ldx + 4 * j);
@@ -290,15 +296,15 @@ __global__ void ln_kernel(const void* __restrict__ xv, int c, int ldx, int64_t r
                 {
                     const float4 g = ldg4(gamma0 + grp * c + 4 * j), b = ldg4(beta0 + grp * c + 4 * j);
                     uint2 o;
-                    o.x = pack16x2(n0 * g.x + b.x, n1 * g.y + b.y, fmt);
-                    o.y = pack16x2(n2 * g.z + b.z, n3 * g.w + b.w, fmt);
+                    o.x = pack16x2(n0 * g.x + b.x, n1 * g.y + b.y, FMT);
+                    o.y = pack16x2(n2 * g.z + b.z, n3 * g.w + b.w, FMT);
                     *reinterpret_cast<uint2*>(out0 + row * ldo + 4 * j) = o;
                 }
                 if (out1) {
                     const float4 g = ldg4(gamma1 + grp * c + 4 * j), b = ldg4(beta1 + grp * c + 4 * j);
                     uint2 o;
-                    o.x = pack16x2(n0 * g.x + b.x, n1 * g.y + b.y, fmt);
-                    o.y = pack16x2(n2 * g.z + b.z, n3 * g.w + b.w, fmt);
+                    o.x = pack16x2(n0 * g.x + b.x, n1 * g.y + b.y, FMT);
+                    o.y = pack16x2(n2 * g.z + b.z, n3 * g.w + b.w, FMT);
                     *reinterpret_cast<uint2*>(out1 + row * ldo + 4 * j) = o;
                 }
             }
@@ -311,9 +317,9 @@ static void launch_ln(const smtl_ln_args* a, cudaStream_t st) {
     const int wpb = 8;
     const int64_t rows_per_block = (int64_t)wpb * R;
     const int64_t grid = (a->rows + rows_per_block - 1) / rows_per_block;
-    ln_kernel<IN_BF16, NV, R><<<(unsigned)grid, wpb * 32, 0, st>>>(a->x, a->c, a->ldx, a->rows, a->eps, a->rows_per_group,
-                                                                 a->gamma0, a->beta0, (uint16_t*)a->out0, a->gamma1,
-                                                                 a->beta1, (uint16_t*)a->out1, a->ldo, a->fmt16);
+    auto kern = a->fmt16 == SMTL_FMT_F16 ? ln_kernel<IN_BF16, NV, R, FMT_F16> : ln_kernel<IN_BF16, NV, R, FMT_BF16>;
+    kern<<<(unsigned)grid, wpb * 32, 0, st>>>(a->x, a->c, a->ldx, a->rows, a->eps, a->rows_per_group, a->gamma0, a->beta0,
+                                              (uint16_t*)a->out0, a->gamma1, a->beta1, (uint16_t*)a->out1, a->ldo);
 }
 
 // ============================================================================================= layout producers
@@ -646,12 +652,12 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
 }
 
 // H = heads (C = 64 H), NT = padded token count (4 or 8).  Vectors v = head * NT + token, padded to VP (multiple of 16).
-template <int H, int NT>
+template <int H, int NT, int FMT>
 __global__ void __launch_bounds__(256) xattn_mma_kernel(
     float* __restrict__ hs, int ldh, int64_t rows_per_group, int ngroups, XattnK tk, const uint16_t* __restrict__ ap,
     const float* __restrict__ ca, const uint16_t* __restrict__ bmt, const float* __restrict__ bo,
     const float* __restrict__ g3, const float* __restrict__ b3, uint16_t* __restrict__ out, int ldo, float eps2,
-    float eps3, int fmt) {
+    float eps3) {
     constexpr int C = 64 * H, V = H * NT, VP = (V + 15) / 16 * 16, NTILE = VP / 8, KV = VP / 16, KC = C / 16;
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2, tq = lane & 3;                                // fragment row within 8, column pair
@@ -669,8 +675,12 @@ __global__ void __launch_bounds__(256) xattn_mma_kernel(
     const int64_t last = (int64_t)grp * rows_per_group + rows_per_group - 1;
     const int64_t row_a = live_a ? (int64_t)grp * rows_per_group + local0 + g : last;
     const int64_t row_b = live_b ? (int64_t)grp * rows_per_group + local0 + g + 8 : last;
-    float* xa = hs + row_a * ldh + 2 * tq;
-    float* xb = hs + row_b * ldh + 2 * tq;
+    // The contraction index of an MMA may be permuted freely as long as both operands agree, and so may the columns of
+    // its output: within every 16-wide block, fragment positions (2tq, 2tq+1, 2tq+8, 2tq+9) are mapped to the FOUR
+    // CONSECUTIVE columns 4tq .. 4tq+3, so a lane moves one 16-byte piece per row and block instead of two 8-byte ones
+    // (the first version was bound by L1 request rate: 62 % L1 busy, 17 % issue).
+    float* xa = hs + row_a * ldh + 4 * tq;
+    float* xb = hs + row_b * ldh + 4 * tq;
 
     // ---- pass 1: LayerNorm 2 statistics.  This is the pass that reads HBM, so the warp sweeps whole rows (512
     // contiguous bytes per instruction, four rows in flight); the fragment-shaped 8-byte accesses of the later passes
@@ -710,17 +720,16 @@ __global__ void __launch_bounds__(256) xattn_mma_kernel(
     for (int t = 0; t < NTILE; ++t) { sc[t][0] = sc[t][1] = sc[t][2] = sc[t][3] = 0.f; }
 #pragma unroll 2
     for (int kk = 0; kk < KC; ++kk) {
-        const float2 a0 = __ldg(reinterpret_cast<const float2*>(xa + 16 * kk)), a1 = __ldg(reinterpret_cast<const float2*>(xa + 16 * kk + 8));
-        const float2 b0 = __ldg(reinterpret_cast<const float2*>(xb + 16 * kk)), b1 = __ldg(reinterpret_cast<const float2*>(xb + 16 * kk + 8));
+        const float4 a = __ldg(reinterpret_cast<const float4*>(xa + 16 * kk)), b = __ldg(reinterpret_cast<const float4*>(xb + 16 * kk));
         uint32_t af[4];
-        af[0] = pack16x2((a0.x - mean_a) * rstd_a, (a0.y - mean_a) * rstd_a, fmt);
-        af[1] = pack16x2((b0.x - mean_b) * rstd_b, (b0.y - mean_b) * rstd_b, fmt);
-        af[2] = pack16x2((a1.x - mean_a) * rstd_a, (a1.y - mean_a) * rstd_a, fmt);
-        af[3] = pack16x2((b1.x - mean_b) * rstd_b, (b1.y - mean_b) * rstd_b, fmt);
+        af[0] = pack16x2((a.x - mean_a) * rstd_a, (a.y - mean_a) * rstd_a, FMT);
+        af[1] = pack16x2((b.x - mean_b) * rstd_b, (b.y - mean_b) * rstd_b, FMT);
+        af[2] = pack16x2((a.z - mean_a) * rstd_a, (a.w - mean_a) * rstd_a, FMT);
+        af[3] = pack16x2((b.z - mean_b) * rstd_b, (b.w - mean_b) * rstd_b, FMT);
 #pragma unroll
         for (int t = 0; t < NTILE; ++t) {
-            const uint32_t* bp = reinterpret_cast<const uint32_t*>(apT + (int64_t)(t * 8 + g) * C + 16 * kk + 2 * tq);
-            mma_16816(sc[t], af, __ldg(bp), __ldg(bp + 4), fmt);
+            const uint2 w = __ldg(reinterpret_cast<const uint2*>(apT + (int64_t)(t * 8 + g) * C + 16 * kk + 4 * tq));
+            mma_16816(sc[t], af, w.x, w.y, FMT);
         }
     }
     // ---- softmax over the NT tokens of every head; the probabilities become the A fragments of the second GEMM
@@ -745,25 +754,33 @@ __global__ void __launch_bounds__(256) xattn_mma_kernel(
             lb += __shfl_xor_sync(0xffffffffu, lb, o);
         }
         const float ia = la > 0.f ? 1.0f / la : 0.f, ib = lb > 0.f ? 1.0f / lb : 0.f;
-        pf[t >> 1][(t & 1) * 2] = pack16x2(v0 * ia, v1 * ia, fmt);
-        pf[t >> 1][(t & 1) * 2 + 1] = pack16x2(v2 * ib, v3 * ib, fmt);
+        pf[t >> 1][(t & 1) * 2] = pack16x2(v0 * ia, v1 * ia, FMT);
+        pf[t >> 1][(t & 1) * 2 + 1] = pack16x2(v2 * ib, v3 * ib, FMT);
     }
-    // ---- pass 3: h += bo + P . Bm, one 8-column block at a time; LayerNorm 3 statistics on the way
+    // ---- pass 3: h += bo + P . Bm, one 16-column block (two MMA column tiles) at a time; LayerNorm 3 statistics on the way.
+    // Column tile 0 of a block produces channels 4q, 4q+1 and tile 1 channels 4q+2, 4q+3 of every quad q (see above); the
+    // vector axis of bmt is stored in the matching fragment order by ops.xattn_tables.
     float s3a = 0.f, q3a = 0.f, s3b = 0.f, q3b = 0.f;
+    const int chq = 4 * (g >> 1) + (g & 1);                               // channel (within the block) of B column g, tile 0
 #pragma unroll 2
-    for (int n = 0; n < C / 8; ++n) {
-        float d[4] = {0.f, 0.f, 0.f, 0.f};
-        const uint32_t* bp = reinterpret_cast<const uint32_t*>(bmT + (int64_t)(n * 8 + g) * VP + 2 * tq);
+    for (int nb = 0; nb < C / 16; ++nb) {
+        float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint16_t* bp0 = bmT + (int64_t)(16 * nb + chq) * VP + 4 * tq;
 #pragma unroll
-        for (int kv = 0; kv < KV; ++kv) mma_16816(d, pf[kv], __ldg(bp + 8 * kv), __ldg(bp + 8 * kv + 4), fmt);
-        const float2 bias = __ldg(reinterpret_cast<const float2*>(bo + 8 * n + 2 * tq));
-        float2 a = *reinterpret_cast<const float2*>(xa + 8 * n), b = *reinterpret_cast<const float2*>(xb + 8 * n);
-        a.x += bias.x + d[0]; a.y += bias.y + d[1];
-        b.x += bias.x + d[2]; b.y += bias.y + d[3];
-        if (live_a) *reinterpret_cast<float2*>(xa + 8 * n) = a;
-        if (live_b) *reinterpret_cast<float2*>(xb + 8 * n) = b;
-        s3a += a.x + a.y; q3a = fmaf(a.x, a.x, fmaf(a.y, a.y, q3a));
-        s3b += b.x + b.y; q3b = fmaf(b.x, b.x, fmaf(b.y, b.y, q3b));
+        for (int kv = 0; kv < KV; ++kv) {
+            const uint2 w0 = __ldg(reinterpret_cast<const uint2*>(bp0 + 16 * kv));
+            const uint2 w1 = __ldg(reinterpret_cast<const uint2*>(bp0 + 2 * VP + 16 * kv));
+            mma_16816(d0, pf[kv], w0.x, w0.y, FMT);
+            mma_16816(d1, pf[kv], w1.x, w1.y, FMT);
+        }
+        const float4 bias = __ldg(reinterpret_cast<const float4*>(bo + 16 * nb + 4 * tq));
+        float4 a = *reinterpret_cast<const float4*>(xa + 16 * nb), b = *reinterpret_cast<const float4*>(xb + 16 * nb);
+        a.x += bias.x + d0[0]; a.y += bias.y + d0[1]; a.z += bias.z + d1[0]; a.w += bias.w + d1[1];
+        b.x += bias.x + d0[2]; b.y += bias.y + d0[3]; b.z += bias.z + d1[2]; b.w += bias.w + d1[3];
+        if (live_a) *reinterpret_cast<float4*>(xa + 16 * nb) = a;
+        if (live_b) *reinterpret_cast<float4*>(xb + 16 * nb) = b;
+        s3a += (a.x + a.y) + (a.z + a.w); q3a = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, q3a))));
+        s3b += (b.x + b.y) + (b.z + b.w); q3b = fmaf(b.x, b.x, fmaf(b.y, b.y, fmaf(b.z, b.z, fmaf(b.w, b.w, q3b))));
     }
 #pragma unroll
     for (int o = 1; o < 4; o <<= 1) {
@@ -774,18 +791,22 @@ __global__ void __launch_bounds__(256) xattn_mma_kernel(
     const float r3a = rsqrtf(fmaxf(q3a * (1.0f / C) - m3a * m3a, 0.f) + eps3);
     const float r3b = rsqrtf(fmaxf(q3b * (1.0f / C) - m3b * m3b, 0.f) + eps3);
     // ---- pass 4: LayerNorm 3 of the rows just written (every lane re-reads its OWN stores) -> 16-bit operand
-    uint16_t* oa = out + row_a * ldo + 2 * tq;
-    uint16_t* ob = out + row_b * ldo + 2 * tq;
+    uint16_t* oa = out + row_a * ldo + 4 * tq;
+    uint16_t* ob = out + row_b * ldo + 4 * tq;
 #pragma unroll 4
-    for (int n = 0; n < C / 8; ++n) {
-        const float2 gg = __ldg(reinterpret_cast<const float2*>(g3 + 8 * n + 2 * tq)), bb = __ldg(reinterpret_cast<const float2*>(b3 + 8 * n + 2 * tq));
+    for (int nb = 0; nb < C / 16; ++nb) {
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(g3 + 16 * nb + 4 * tq)), bb = __ldg(reinterpret_cast<const float4*>(b3 + 16 * nb + 4 * tq));
         if (live_a) {
-            const float2 a = *reinterpret_cast<const float2*>(xa + 8 * n);
-            *reinterpret_cast<uint32_t*>(oa + 8 * n) = pack16x2((a.x - m3a) * r3a * gg.x + bb.x, (a.y - m3a) * r3a * gg.y + bb.y, fmt);
+            const float4 a = *reinterpret_cast<const float4*>(xa + 16 * nb);
+            *reinterpret_cast<uint2*>(oa + 16 * nb) =
+                make_uint2(pack16x2((a.x - m3a) * r3a * gg.x + bb.x, (a.y - m3a) * r3a * gg.y + bb.y, FMT),
+                           pack16x2((a.z - m3a) * r3a * gg.z + bb.z, (a.w - m3a) * r3a * gg.w + bb.w, FMT));
         }
         if (live_b) {
-            const float2 b = *reinterpret_cast<const float2*>(xb + 8 * n);
-            *reinterpret_cast<uint32_t*>(ob + 8 * n) = pack16x2((b.x - m3b) * r3b * gg.x + bb.x, (b.y - m3b) * r3b * gg.y + bb.y, fmt);
+            const float4 b = *reinterpret_cast<const float4*>(xb + 16 * nb);
+            *reinterpret_cast<uint2*>(ob + 16 * nb) =
+                make_uint2(pack16x2((b.x - m3b) * r3b * gg.x + bb.x, (b.y - m3b) * r3b * gg.y + bb.y, FMT),
+                           pack16x2((b.z - m3b) * r3b * gg.z + bb.z, (b.w - m3b) * r3b * gg.w + bb.w, FMT));
         }
     }
 }
@@ -1039,12 +1060,24 @@ extern "C" int smtl_gnapply_run(const smtl_gnapply_args* a, void* stream) {
     if (bpi > cap) bpi = cap;
     if (bpi < 1) bpi = 1;
     const size_t smem = (2 * C + 2 * a->groups) * sizeof(float);
-    auto kern = a->x_fmt16 ? gn_apply2_kernel<true> : gn_apply2_kernel<false>;
-    kern<<<dim3(bpi, a->batch), threads, smem, st>>>(
+    const bool same = (a->pad_out != 0) == (a->x_padded != 0);
+    const int variant = (a->x_fmt16 ? 8 : 0) | (a->fmt16 == SMTL_FMT_F16 ? 4 : 0) | (a->raw_bf16 ? 2 : 0) | (same ? 1 : 0);
+    using Kern = void (*)(const void*, const void*, int, int, const long long*, const long long*, int, int, int, int, int,
+                          float, const float*, const float*, int, int, uint16_t*, uint16_t*, FastDiv, int);
+    static const Kern table[16] = {
+        gn_apply2_kernel<false, FMT_BF16, false, false>, gn_apply2_kernel<false, FMT_BF16, false, true>,
+        gn_apply2_kernel<false, FMT_BF16, true, false>,  gn_apply2_kernel<false, FMT_BF16, true, true>,
+        gn_apply2_kernel<false, FMT_F16, false, false>,  gn_apply2_kernel<false, FMT_F16, false, true>,
+        gn_apply2_kernel<false, FMT_F16, true, false>,   gn_apply2_kernel<false, FMT_F16, true, true>,
+        gn_apply2_kernel<true, FMT_BF16, false, false>,  gn_apply2_kernel<true, FMT_BF16, false, true>,
+        gn_apply2_kernel<true, FMT_BF16, true, false>,   gn_apply2_kernel<true, FMT_BF16, true, true>,
+        gn_apply2_kernel<true, FMT_F16, false, false>,   gn_apply2_kernel<true, FMT_F16, false, true>,
+        gn_apply2_kernel<true, FMT_F16, true, false>,    gn_apply2_kernel<true, FMT_F16, true, true>};
+    table[variant]<<<dim3(bpi, a->batch), threads, smem, st>>>(
         a->x0, a->x1, a->c0, a->c1, reinterpret_cast<const long long*>(a->stats0),
         reinterpret_cast<const long long*>(a->stats1), a->stats_replicas, a->batch, a->h, a->w,
         a->groups, a->eps, a->gamma, a->beta, a->silu, a->pad_out, reinterpret_cast<uint16_t*>(a->out_bf16),
-        reinterpret_cast<uint16_t*>(a->raw_bf16), a->fmt16, make_fastdiv((uint32_t)wp), a->x_padded);
+        reinterpret_cast<uint16_t*>(a->raw_bf16), make_fastdiv((uint32_t)wp), a->x_padded);
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;
 }
@@ -1215,9 +1248,10 @@ template <int H, int NT>
 static int launch_xattn_mma(const smtl_xattnf_args* a, const XattnK& tk, int ngroups, cudaStream_t st) {
     const int64_t wpg = (a->rows_per_group + 15) / 16;
     const int64_t warps = wpg * ngroups;
-    xattn_mma_kernel<H, NT><<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(
+    auto kern = a->fmt16 == SMTL_FMT_F16 ? xattn_mma_kernel<H, NT, FMT_F16> : xattn_mma_kernel<H, NT, FMT_BF16>;
+    kern<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(
         a->hs, a->ldh, a->rows_per_group, ngroups, tk, (const uint16_t*)a->ap, a->ca, (const uint16_t*)a->bmt, a->bo,
-        a->gamma3, a->beta3, (uint16_t*)a->out_bf16, a->ldo, a->eps2, a->eps3, a->fmt16);
+        a->gamma3, a->beta3, (uint16_t*)a->out_bf16, a->ldo, a->eps2, a->eps3);
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;
 }
@@ -1232,7 +1266,9 @@ extern "C" int smtl_xattnf_run(const smtl_xattnf_args* a, void* stream) {
     SMTL_CHECK_ARG(a->rows > 0 && a->rows_per_group > 0 && a->rows % a->rows_per_group == 0, "xattnf: bad rows");
     const int ngroups = (int)(a->rows / a->rows_per_group);
     SMTL_CHECK_ARG(ngroups <= SMTL_MAX_TASKS, "xattnf: too many row groups");
-    SMTL_CHECK_ARG(a->ldh % 2 == 0 && a->ldo % 2 == 0, "xattnf: row strides must be even");
+    SMTL_CHECK_ARG(a->ldh % 4 == 0 && a->ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(a->hs) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(a->out_bf16) & 7) == 0,
+                   "xattnf: rows must be 16-byte (hs) / 8-byte (out) aligned");
     SMTL_CHECK_ARG(smtl_xattnf_supported(a->heads, a->ntok_pad), "xattnf: heads=%d ntok_pad=%d not instantiated", a->heads,
                    a->ntok_pad);
     XattnK tk;

@@ -115,7 +115,7 @@ __device__ __forceinline__ void ldg_nc_v8(const void* p, uint32_t* v) {
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
 }
 // 32 fp32 values -> 16-bit row piece (64 bytes), 256-bit stores when the row pitch allows
-__device__ __forceinline__ void store_row16(uint16_t* dst, const float (&v)[32], int ld, int fmt) {
+__device__ __forceinline__ void store_row16(uint16_t* dst, const float (&v)[32], int ld, int fmt) {   // fmt: compile-time at every call
     uint32_t w[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) w[j] = pack16x2(v[2 * j], v[2 * j + 1], fmt);
@@ -244,7 +244,10 @@ __device__ __forceinline__ void epilogue_prepare(const GemmKParams& p, int64_t g
     }
 }
 
-// residual add of one 32-column chunk of this thread's row (fp32 or 16-bit source)
+// residual add of one 32-column chunk of this thread's row (fp32 or 16-bit source).
+// FMT (and with it every conversion below) is a compile-time constant: with a run-time format ptxas emits BOTH
+// conversion sequences under predicates, and a predicated-off instruction still takes its issue slot.
+template <int FMT>
 __device__ __forceinline__ void add_residual(const GemmKParams& p, const void* res, int64_t orow, int ocol, bool full,
                                              float (&v)[32]) {
     if (p.res16) {
@@ -256,7 +259,7 @@ __device__ __forceinline__ void add_residual(const GemmKParams& p, const void* r
                 ldg_nc_v8(src + j, t);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const float2 f = unpack16x2(t[q], p.fmt);
+                    const float2 f = unpack16x2(t[q], FMT);
                     v[j + 2 * q] += f.x;
                     v[j + 2 * q + 1] += f.y;
                 }
@@ -266,14 +269,14 @@ __device__ __forceinline__ void add_residual(const GemmKParams& p, const void* r
             for (int j = 0; j < 32; j += 8) {
                 const uint4 t = ldg_nc_v4(src + j);
                 float2 f;
-                f = unpack16x2(t.x, p.fmt); v[j] += f.x; v[j + 1] += f.y;
-                f = unpack16x2(t.y, p.fmt); v[j + 2] += f.x; v[j + 3] += f.y;
-                f = unpack16x2(t.z, p.fmt); v[j + 4] += f.x; v[j + 5] += f.y;
-                f = unpack16x2(t.w, p.fmt); v[j + 6] += f.x; v[j + 7] += f.y;
+                f = unpack16x2(t.x, FMT); v[j] += f.x; v[j + 1] += f.y;
+                f = unpack16x2(t.y, FMT); v[j + 2] += f.x; v[j + 3] += f.y;
+                f = unpack16x2(t.z, FMT); v[j + 4] += f.x; v[j + 5] += f.y;
+                f = unpack16x2(t.w, FMT); v[j + 6] += f.x; v[j + 7] += f.y;
             }
         } else {
             for (int j = 0; j < 32; ++j)
-                if (ocol + j < p.n_out) v[j] += unpack16x2((uint32_t)src[j], p.fmt).x;
+                if (ocol + j < p.n_out) v[j] += unpack16x2((uint32_t)src[j], FMT).x;
         }
     } else {
         const float* src = reinterpret_cast<const float*>(res) + orow * (int64_t)p.ldres + ocol;
@@ -300,7 +303,7 @@ __device__ __forceinline__ void add_residual(const GemmKParams& p, const void* r
 
 // Epilogue for one accumulator row per thread: `taddr` = TMEM address of this warp's lane quarter, column 0 of the
 // tile; `tn` = N-tile index.  All tcgen05.ld / shuffles are warp-collective.
-template <int BN>
+template <int BN, int FMT>
 __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t taddr, int tn, int lane, int half,
                                               const EpiRow<BN>& e, uint32_t stats_acc) {
     const bool geglu = (p.act == SMTL_ACT_GEGLU);
@@ -355,14 +358,14 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t tad
             if (p.aux_bf16) {
                 uint16_t* dst = p.aux_bf16 + orow * (int64_t)p.ld_aux + ocol;
                 if (full && (p.ld_aux & 7) == 0) {
-                    store_row16(dst, v, p.ld_aux, p.fmt);
+                    store_row16(dst, v, p.ld_aux, FMT);
                 } else {
                     for (int j = 0; j < 32; ++j)
-                        if (ocol + j < p.n_out) dst[j] = to16(v[j], p.fmt);
+                        if (ocol + j < p.n_out) dst[j] = to16(v[j], FMT);
                 }
             }
-            if (p.res1) add_residual(p, p.res1, orow, ocol, full, v);
-            if (p.res2) add_residual(p, p.res2, orow, ocol, full, v);
+            if (p.res1) add_residual<FMT>(p, p.res1, orow, ocol, full, v);
+            if (p.res2) add_residual<FMT>(p, p.res2, orow, ocol, full, v);
             if (p.out_f32) {
                 float* dst = p.out_f32 + orow * (int64_t)p.ldc + ocol;
                 if (full && (p.ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
@@ -379,10 +382,10 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t tad
             if (p.out_bf16) {
                 uint16_t* dst = p.out_bf16 + orow * (int64_t)p.ldc + ocol;
                 if (full && (p.ldc & 7) == 0) {
-                    store_row16(dst, v, p.ldc, p.fmt);
+                    store_row16(dst, v, p.ldc, FMT);
                 } else {
                     for (int j = 0; j < 32; ++j)
-                        if (ocol + j < p.n_out) dst[j] = to16(v[j], p.fmt);
+                        if (ocol + j < p.n_out) dst[j] = to16(v[j], FMT);
                 }
             }
         }
@@ -741,7 +744,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
             mbar_wait_backoff(&acc_full[acc], acc_phase, 100);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
-            epilogue_rows<BN>(p, taddr, tn, lane, half, er, stats_acc);
+            if (p.fmt == FMT_F16) epilogue_rows<BN, FMT_F16>(p, taddr, tn, lane, half, er, stats_acc);
+            else epilogue_rows<BN, FMT_BF16>(p, taddr, tn, lane, half, er, stats_acc);
             // release this accumulator stage back to the (leader's) MMA warp
             tc_fence_before();
             __syncwarp();
@@ -781,6 +785,7 @@ constexpr int T_STG_PITCH = 64;
 constexpr int T_STG_WARP = 32 * T_STG_PITCH;
 constexpr int T_STAGING = EPI_WARPS * T_STG_WARP;
 
+template <int FMT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid_constant__ GemmKParams p) {
     constexpr int TMEM_COLS = 512;
     constexpr int ACC_STRIDE = 256;
@@ -1042,13 +1047,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
                     __syncwarp();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        v[j] += unpack16x2(lds_u16(stg + j * T_STG_PITCH + lane * 2), p.fmt).x;
+                        v[j] += unpack16x2(lds_u16(stg + j * T_STG_PITCH + lane * 2), FMT).x;
                     }
                     __syncwarp();
                 }
                 // channel-major -> pixel-major through the staging tile, then 64-byte row pieces
 #pragma unroll
-                for (int j = 0; j < 32; ++j) sts_u16(stg + j * T_STG_PITCH + lane * 2, to16(v[j], p.fmt));
+                for (int j = 0; j < 32; ++j) sts_u16(stg + j * T_STG_PITCH + lane * 2, to16(v[j], FMT));
                 __syncwarp();
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -1453,9 +1458,12 @@ extern "C" int smtl_gemm_run(const smtl_gemm_op* op, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (op->cta_group == 3) {
         static std::atomic<uint64_t> attr_devs{0};
-        if (smtl_host::first_use_on_device(attr_devs))
-            SMTL_CHECK_CUDA(cudaFuncSetAttribute(smtl_gemmT_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
-        smtl_gemmT_kernel<<<op->grid, NUM_THREADS, op->smem_bytes, st>>>(kp);
+        if (smtl_host::first_use_on_device(attr_devs)) {
+            SMTL_CHECK_CUDA(cudaFuncSetAttribute(smtl_gemmT_kernel<FMT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+            SMTL_CHECK_CUDA(cudaFuncSetAttribute(smtl_gemmT_kernel<FMT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+        }
+        if (kp.fmt == FMT_F16) smtl_gemmT_kernel<FMT_F16><<<op->grid, NUM_THREADS, op->smem_bytes, st>>>(kp);
+        else smtl_gemmT_kernel<FMT_BF16><<<op->grid, NUM_THREADS, op->smem_bytes, st>>>(kp);
         SMTL_CHECK_CUDA(cudaGetLastError());
         return SMTL_OK;
     }

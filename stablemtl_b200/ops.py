@@ -331,7 +331,8 @@ def xattn_fused_supported(heads, ntok_pad):
 def xattn_tables(a0, gamma2, beta2, bm, ntok, ntok_pad):
     """Host-side packing of the collapsed cross-attention (smtl_xattnf_args): a0 [T, H, ntp, C] = Wq_head^T k / 8 and
     bm [T, H, ntp, C] = Wo[:, head] v, fp32 -> (ap [T, VP, C] 16-bit, ca [T, VP] fp32, bmt [T, C, VP] 16-bit) with the
-    vectors padded to VP = a multiple of 16 and the padding tokens masked (zero vector, -inf constant)."""
+    vectors padded to VP = a multiple of 16 and the padding tokens masked (zero vector, -inf constant); bmt's vector axis
+    is stored in the kernel's fragment order (see `xattn_unpermute`)."""
     T, H, n, C = a0.shape
     assert n == ntok_pad and bm.shape == a0.shape
     V = H * n
@@ -343,7 +344,20 @@ def xattn_tables(a0, gamma2, beta2, bm, ntok, ntok_pad):
     ca[:, :V] = (a0 * beta2).sum(-1).masked_fill(~valid, float("-inf")).reshape(T, V)
     bmt = torch.zeros(T, C, VP)
     bmt[:, :, :V] = bm.reshape(T, V, C).transpose(1, 2)
+    # vector axis in MMA fragment order: stored position 16 b + 4 q + e holds vector 16 b + (2q, 2q+1, 2q+8, 2q+9)[e], so
+    # that a lane's four contraction entries of a 16-block are one 8-byte load
+    perm = torch.tensor([16 * b + 2 * q + o for b in range(VP // 16) for q in range(4) for o in (0, 1, 8, 9)])
+    bmt = bmt[:, :, perm]
     return ap.to(h16()).contiguous(), ca.contiguous(), bmt.to(h16()).contiguous()
+
+
+def xattn_unpermute(bmt):
+    """bmt [..., VP] as packed by xattn_tables -> natural vector order (tests / inspection)"""
+    vp = bmt.shape[-1]
+    perm = torch.tensor([16 * b + 2 * q + o for b in range(vp // 16) for q in range(4) for o in (0, 1, 8, 9)], device=bmt.device)
+    out = torch.empty_like(bmt)
+    out[..., perm] = bmt
+    return out
 
 
 def xattn_fused(hs, ap, ca, bmt, bo, gamma3, beta3, task_of_group, rows_per_group, heads, ntok_pad, out, eps2=1e-5, eps3=1e-5):

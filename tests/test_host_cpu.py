@@ -142,7 +142,7 @@ def test_collapsed_cross_attention_tables_reproduce_attn2():
                        for hd in range(H)], dim=1)
         ref = o @ sd[t + ".attn2.to_out.0.weight"].t() + sd[t + ".attn2.to_out.0.bias"]
         mean, rstd = h.mean(1, keepdim=True), (h.var(1, unbiased=False, keepdim=True) + 1e-5).rsqrt()
-        ap, ca, bmt = w[p + ".xf.ap"][ti].float(), w[p + ".xf.ca"][ti], w[p + ".xf.bmt"][ti].float()
+        ap, ca, bmt = w[p + ".xf.ap"][ti].float(), w[p + ".xf.ca"][ti], ops.xattn_unpermute(w[p + ".xf.bmt"][ti]).float()
         V, VP = H * n, ap.shape[0]
         assert VP % 16 == 0 and VP >= V and bmt.shape == (C, VP) and bool(torch.isinf(ca[V:]).all())
         score = ((h - mean) * rstd) @ ap.t() + ca                                       # [rows, VP]

@@ -882,7 +882,7 @@ def test_xattn_fused_collapsed_cross_attention(heads, ntp, rpg, groups):
         mean, rstd = h.mean(1, keepdim=True), (h.var(1, unbiased=False, keepdim=True) + 1e-5).rsqrt()
         score = ((h - mean) * rstd) @ ap[t, :v].double().t() + ca[t, :v].double()
         prob = torch.softmax(score.view(-1, heads, ntp), -1).view(-1, v)
-        hn = h + bo.double() + prob @ bmt[t, :, :v].double().t()
+        hn = h + bo.double() + prob @ ops.xattn_unpermute(bmt[t])[:, :v].double().t()
         ref_h.append(hn)
         ref_o.append(F.layer_norm(hn, (c,), g3.double(), b3.double(), 1e-5))
     ref_h, ref_o = torch.cat(ref_h), torch.cat(ref_o)
