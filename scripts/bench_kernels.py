@@ -62,11 +62,12 @@ def conv_case(name, batch, h, w, cin, cout, stats=True, **kw):
            ops.conv3x3(a, wm, batch, h, w, bias=bias, out_bf16=out, **skw, **kw))
 
 
-def attn_case(batch, ntok, heads):
+def attn_case(batch, ntok, heads, variant=0):
     c = heads * 64
     qkv = rb(batch * ntok, 3 * c)
     out = torch.empty(batch * ntok, c, device=DEV, dtype=ops.h16())
-    report(f"flash_attn b={batch} ntok={ntok} heads={heads}", ops.flash_attn(qkv, batch, ntok, heads, out, 0, c, 2 * c))
+    report(f"flash_attn b={batch} ntok={ntok} heads={heads} variant={variant}",
+           ops.flash_attn(qkv, batch, ntok, heads, out, 0, c, 2 * c, variant=variant))
 
 
 def gn_case(batch, h, w, c, pad=True):
@@ -143,7 +144,8 @@ if __name__ == "__main__":
         sys.exit(0)
     if only == "attn":
         for args in [(16, 4800, 5), (112, 4800, 5), (112, 1200, 10), (112, 300, 20), (112, 80, 20)]:
-            attn_case(*args)
+            for variant in (1, 0):
+                attn_case(*args, variant=variant)
         sys.exit(0)
     gemm_case("square", 8192, 8192, 8192)
     gemm_case("square bn128", 8192, 8192, 8192, block_n=128)

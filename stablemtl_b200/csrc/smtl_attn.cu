@@ -65,6 +65,16 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
         : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
 // (Measured and dropped in round 2: passing an "exp token" over named barriers between the two softmax warps of an SM
 // sub-partition, so that the two tiles' exponential phases run back to back instead of competing for the SFU.  ncu
 // shows the SFU 58 % and the tensor pipe 29 % busy, but the token changed nothing: 0.850 ms before and after on
@@ -286,6 +296,239 @@ __global__ void __launch_bounds__(F2_THREADS, 1) smtl_fattn2_kernel(const __grid
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, F2_TMEM_COLS);
+    }
+}
+
+
+// ================================================================================================ d = 64, four query tiles
+// smtl_fattn4_kernel: the same pipeline with FOUR 128-row query tiles per CTA and 64-key steps (TMEM: S/P 4 x 64 columns,
+// O 4 x 64).  Why: in the two-tile kernel an SM sub-partition hosts two softmax warps that run IN PHASE -- both in their
+// exponential phase (sharing the SFU), then both waiting on the tensor pipe's P·V + next Q·K^T round trip -- so a tile pair
+// costs SFU time PLUS round-trip time (ncu: SFU 58 %, tensor 29 %, issue 41 % busy; 3500 clk per pair of tiles against
+// 2048 SFU clk).  Four independent streams per sub-partition, each with half the work per step, overlap one stream's
+// round trip with the others' exponentials.  K and V are still staged as 128-key boxes (one TMA box per operand and
+// stage); a step consumes half a box.  The softmax arithmetic is packed (FFMA2 / FADD2: two fp32 lanes per issue slot).
+constexpr int F4_NQ = 4;
+constexpr int F4_KS = 64;                                  // keys per step
+constexpr int F4_THREADS = 64 + F4_NQ * 128;               // 576: TMA, MMA, 16 softmax warps
+// Five warps on two of the SM sub-partitions: 96 registers per thread (set with __maxnreg__; __launch_bounds__ would cap the
+// kernel at 88 and spill 130 words of the softmax row).
+constexpr int F4_REGS = 96;
+constexpr int F4_NS = 4;                                   // K/V ring stages (one 128-key box of K and of V: 32 KB)
+constexpr int F4_SMEM = F4_NQ * TILE_BYTES + F4_NS * 2 * TILE_BYTES + 256;
+
+template <bool MASKED, int FMT>
+__device__ __forceinline__ void softmax_step64(const FattnKParams& p, uint32_t t_s, int kv_valid, float& m_run,
+                                               float& l_run, uint32_t t_o, bool have_o) {
+    uint32_t rr[64];
+    tmem_ld_32x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(&rr[0]));
+    tmem_ld_32x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&rr[32]));
+    tmem_ld_wait();
+    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 64; i += 4) {
+        float a = __uint_as_float(rr[i]), b = __uint_as_float(rr[i + 1]), c = __uint_as_float(rr[i + 2]),
+              d = __uint_as_float(rr[i + 3]);
+        if (MASKED) {
+            a = (i < kv_valid) ? a : -INFINITY;
+            b = (i + 1 < kv_valid) ? b : -INFINITY;
+            c = (i + 2 < kv_valid) ? c : -INFINITY;
+            d = (i + 3 < kv_valid) ? d : -INFINITY;
+        }
+        mx0 = fmaxf(mx0, a); mx1 = fmaxf(mx1, b); mx2 = fmaxf(mx2, c); mx3 = fmaxf(mx3, d);
+    }
+    const float mx_s = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+    const bool grow = mx_s > m_run + F2_LAZY;                 // lazy running max, as in softmax_tile
+    if (__any_sync(0xffffffffu, grow)) {
+        const float alpha = grow ? ex2_approx(m_run - mx_s) : 1.0f;
+        if (grow) { m_run = mx_s; l_run *= alpha; }
+        if (have_o) {
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {                     // rare path, 16 columns at a time: the S row stays live
+                uint32_t oo[16];
+                tmem_ld_32x16(t_o + c * 16, oo);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) oo[i] = __float_as_uint(__uint_as_float(oo[i]) * alpha);
+                tmem_st_32x16(t_o + c * 16, oo);
+            }
+        }
+    }
+    const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_run, -m_run);
+    float2 ps = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            const float2 t = ffma2(make_float2(__uint_as_float(rr[c * 32 + i]), __uint_as_float(rr[c * 32 + i + 1])), sc2, nm2);
+            float2 e = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+            if (MASKED) {
+                e.x = (c * 32 + i < kv_valid) ? e.x : 0.f;
+                e.y = (c * 32 + i + 1 < kv_valid) ? e.y : 0.f;
+            }
+            ps = fadd2(ps, e);
+            pk[i >> 1] = pack16x2_nosat(e.x, e.y, FMT);     // p <= 2^8: no fp16 saturation needed
+        }
+        tmem_st_32x16(t_s + c * 16, pk);          // P aliases the S columns (all of S is in registers by now)
+    }
+    l_run += ps.x + ps.y;
+    tmem_st_wait();
+}
+
+template <int FMT>
+__global__ void __maxnreg__(F4_REGS) smtl_fattn4_kernel(const __grid_constant__ FattnKParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sQ = smem;                                    // 4 tiles
+    uint8_t* sK = smem + F4_NQ * TILE_BYTES;               // NS boxes
+    uint8_t* sV = sK + F4_NS * TILE_BYTES;                 // NS boxes
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + F4_NS * TILE_BYTES);
+    uint64_t* q_full = bars + 0;
+    uint64_t* kv_full = bars + 1;                // [NS]
+    uint64_t* kv_empty = bars + 1 + F4_NS;       // [NS]
+    uint64_t* s_full = bars + 1 + 2 * F4_NS;     // [NQ]
+    uint64_t* p_full = s_full + F4_NQ;           // [NQ]
+    uint64_t* o_done = p_full + F4_NQ;           // [NQ]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + F4_NQ);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * F4_NQ * BQ;
+    const int b = blockIdx.y / p.heads;
+    const int hd = blockIdx.y - b * p.heads;
+    const int row_base = b * p.ntok;
+    const int nbox = (p.ntok + BKV - 1) / BKV;             // staged 128-key boxes
+    const int nsub = (p.ntok + F4_KS - 1) / F4_KS;         // 64-key steps
+    const int ntile_q = min(F4_NQ, (p.ntok - q0 + BQ - 1) / BQ);
+
+    if (threadIdx.x == 0) {
+        if ((smem_u32(smem) & 1023u) != 0) { printf("smtl_fattn4: smem base not 1024-aligned\n"); __trap(); }
+        tma_prefetch_desc(&p.tm);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < F4_NS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        for (int w = 0; w < F4_NQ; ++w) { mbar_init(&s_full[w], 1); mbar_init(&p_full[w], 4); mbar_init(&o_done[w], 1); }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_arrive_expect_tx(q_full, ntile_q * TILE_BYTES);
+            for (int w = 0; w < ntile_q; ++w)
+                tma_load_2d(sQ + w * TILE_BYTES, &p.tm, q_full, p.q_col0 + hd * HD, row_base + q0 + w * BQ);
+        }
+        __syncwarp();
+        for (int j = 0; j < nbox; ++j) {
+            const int s = j % F4_NS;
+            mbar_wait(&kv_empty[s], ((j / F4_NS) & 1) ^ 1u);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
+                tma_load_2d(sK + s * TILE_BYTES, &p.tm, &kv_full[s], p.k_col0 + hd * HD, row_base + j * BKV);
+                tma_load_2d(sV + s * TILE_BYTES, &p.tm, &kv_full[s], p.v_col0 + hd * HD, row_base + j * BKV);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        const uint32_t IDESC_S = make_idesc_16(BQ, F4_KS, 0, 0, FMT);  // S[128,64] = Q[128,64] K[64,64]^T
+        const uint32_t IDESC_O = make_idesc_16(BQ, HD, 0, 1, FMT);       // O[128,64] += P[128,64] V[64,64] (V MN-major)
+        auto issue_s = [&](int w, int j) {                               // step j: box j / 2, half j % 2
+            const uint64_t dq = make_smem_desc_sw128(smem_u32(sQ + w * TILE_BYTES));
+            const uint64_t dk = make_smem_desc_sw128(smem_u32(sK + ((j >> 1) % F4_NS) * TILE_BYTES) + (j & 1) * F4_KS * 128);
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k) tc_mma_f16(tmem_base + w * F4_KS, dq + 2 * k, dk + 2 * k, IDESC_S, k != 0);
+            tc_commit(&s_full[w]);
+        };
+        mbar_wait(q_full, 0);
+        mbar_wait(&kv_full[0], 0);
+        tc_fence_after();
+        if (elect_one())
+            for (int w = 0; w < ntile_q; ++w) issue_s(w, 0);
+        __syncwarp();
+        for (int j = 0; j < nsub; ++j) {
+            const int s = (j >> 1) % F4_NS;
+            for (int w = 0; w < ntile_q; ++w) {
+                mbar_wait(&p_full[w], j & 1);                 // softmax wrote P_w(j) and rescaled O_w
+                if (w == 0 && j + 1 < nsub && ((j + 1) & 1) == 0) {      // S(j+1) opens the next box
+                    const int nb = (j + 1) >> 1;
+                    mbar_wait(&kv_full[nb % F4_NS], (nb / F4_NS) & 1);
+                }
+                tc_fence_after();
+                const uint32_t sv = smem_u32(sV + s * TILE_BYTES) + (j & 1) * F4_KS * 128;
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < F4_KS / 16; ++k) {
+                        // V rows (kv) 16k .. 16k+16 of this half box; P: 8 TMEM columns per K step
+                        const uint64_t dv = make_smem_desc_sw128(sv + k * 16 * 128);
+                        tc_mma_f16_ts(tmem_base + 256 + w * HD, tmem_base + w * F4_KS + 8 * k, dv, IDESC_O, (j | k) != 0);
+                    }
+                    if (j + 1 < nsub) issue_s(w, j + 1);      // in-order after PV_w(j): may overwrite P_w(j)
+                    else tc_commit(&o_done[w]);
+                }
+                __syncwarp();
+            }
+            if ((j & 1) || j == nsub - 1) {                   // both halves of the box consumed by every MMA issued so far
+                if (elect_one()) tc_commit(&kv_empty[s]);
+                __syncwarp();
+            }
+        }
+    } else {
+        const int w = (warp - 2) >> 2;                         // which query tile
+        if (w < ntile_q) {
+            const int quarter = warp & 3;                      // TMEM lane quarter this warp may access
+            const int r = quarter * 32 + lane;                 // query row within the tile == TMEM lane
+            const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+            const uint32_t t_s = tmem_base + w * F4_KS + lane_off;
+            const uint32_t t_o = tmem_base + 256 + w * HD + lane_off;
+            float m_run = -INFINITY, l_run = 0.f;
+            const int tail = p.ntok - (nsub - 1) * F4_KS;      // valid kv columns of the last step
+            for (int j = 0; j < nsub; ++j) {
+                mbar_wait(&s_full[w], j & 1);                  // S_w(j) ready; implies PV_w(j-1) retired
+                tc_fence_after();
+                if (j == nsub - 1 && tail < F4_KS) softmax_step64<true, FMT>(p, t_s, tail, m_run, l_run, t_o, j > 0);
+                else softmax_step64<false, FMT>(p, t_s, F4_KS, m_run, l_run, t_o, j > 0);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[w]);
+            }
+            mbar_wait(&o_done[w], 0);
+            tc_fence_after();
+            const float inv = 1.0f / l_run;
+            const int qrow = q0 + w * BQ + r;
+            const bool row_ok = qrow < p.ntok;
+            uint16_t* dst = p.out + (int64_t)(row_base + qrow) * p.ldo + hd * HD;
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                uint32_t rr[32];
+                tmem_ld_32x32(t_o + c * 32, rr);
+                tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+                        uint4 o;
+                        o.x = pack16x2(__uint_as_float(rr[i]) * inv, __uint_as_float(rr[i + 1]) * inv, FMT);
+                        o.y = pack16x2(__uint_as_float(rr[i + 2]) * inv, __uint_as_float(rr[i + 3]) * inv, FMT);
+                        o.z = pack16x2(__uint_as_float(rr[i + 4]) * inv, __uint_as_float(rr[i + 5]) * inv, FMT);
+                        o.w = pack16x2(__uint_as_float(rr[i + 6]) * inv, __uint_as_float(rr[i + 7]) * inv, FMT);
+                        *reinterpret_cast<uint4*>(dst + c * 32 + i) = o;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -513,9 +756,9 @@ extern "C" int smtl_fattn_plan(const smtl_fattn_args* a, smtl_fattn_op* op) {
         op->grid_y = a->batch;
         op->smem_bytes = V5_SMEM;
     } else {
-        op->grid_x = (a->ntok + 2 * BQ - 1) / (2 * BQ);
+        op->grid_x = (a->ntok + F4_NQ * BQ - 1) / (F4_NQ * BQ);
         op->grid_y = a->batch * a->heads;
-        op->smem_bytes = F2_SMEM;
+        op->smem_bytes = F4_SMEM;
     }
     SMTL_CHECK_ARG(op->grid_y <= 65535, "fattn_plan: batch*heads=%d exceeds grid.y", op->grid_y);
     return smtl_host::encode_tmap_bf16_2d(op->tmap_qkv, a->qkv, (uint64_t)a->batch * a->ntok, (uint64_t)a->ld,
@@ -548,7 +791,18 @@ extern "C" int smtl_fattn_run(const smtl_fattn_op* op, void* stream) {
         SMTL_CHECK_CUDA(cudaGetLastError());
         return SMTL_OK;
     }
-    smtl_fattn2_kernel<<<dim3(op->grid_x, op->grid_y), F2_THREADS, op->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(kp);
+    if (op->pad_ == 1) {                            // EXPERIMENT: the two-tile kernel, for the same-run A/B
+        smtl_fattn2_kernel<<<dim3((a.ntok + 2 * BQ - 1) / (2 * BQ), op->grid_y), F2_THREADS, F2_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(kp);
+        SMTL_CHECK_CUDA(cudaGetLastError());
+        return SMTL_OK;
+    }
+    static std::atomic<uint64_t> attr4{0};
+    if (smtl_host::first_use_on_device(attr4)) {
+        SMTL_CHECK_CUDA(cudaFuncSetAttribute(smtl_fattn4_kernel<FMT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM));
+        SMTL_CHECK_CUDA(cudaFuncSetAttribute(smtl_fattn4_kernel<FMT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM));
+    }
+    auto kern = a.fmt16 == SMTL_FMT_F16 ? smtl_fattn4_kernel<FMT_F16> : smtl_fattn4_kernel<FMT_BF16>;
+    kern<<<dim3(op->grid_x, op->grid_y), F4_THREADS, op->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(kp);
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;
 }

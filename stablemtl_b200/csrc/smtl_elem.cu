@@ -183,14 +183,21 @@ __global__ void __launch_bounds__(320, 3) gn_apply2_kernel(
                         r.z = pack16x2(v[4], v[5], FMT); r.w = pack16x2(v[6], v[7], FMT);
                     }
                 }
+                // packed fp32 pairs (FFMA2): half the issue slots of the two FMAs per element, same results
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], sc[i], sh[i]);
+                for (int i = 0; i < 8; i += 2) {
+                    const float2 n = ffma2(make_float2(v[i], v[i + 1]), make_float2(sc[i], sc[i + 1]), make_float2(sh[i], sh[i + 1]));
+                    v[i] = n.x; v[i + 1] = n.y;
+                }
                 if (do_silu == 1) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        float t;
-                        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(v[i]));
-                        v[i] = fmaf(v[i], t, v[i]);
+                    for (int i = 0; i < 8; i += 2) {
+                        float2 t;
+                        asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(v[i]));
+                        asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(v[i + 1]));
+                        const float2 h = make_float2(v[i], v[i + 1]);
+                        const float2 o2 = ffma2(h, t, h);
+                        v[i] = o2.x; v[i + 1] = o2.y;
                     }
                 } else if (do_silu == 2) {
 #pragma unroll
@@ -652,80 +659,110 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
 }
 
 // H = heads (C = 64 H), NT = padded token count (4 or 8).  Vectors v = head * NT + token, padded to VP (multiple of 16).
-template <int H, int NT, int FMT>
-__global__ void __launch_bounds__(256) xattn_mma_kernel(
+// R16: a warp owns 16 rows (both row halves of the MMA tile) or 8 (the upper half of the tile is fed zeros).
+//
+// The warp's rows live in REGISTERS for the whole kernel -- a lane holds, of each of its one or two rows, the four
+// consecutive channels 4tq .. 4tq+3 of every 16-channel block: 160 fp32 for 16 rows of 320 channels or 8 rows of 640 --
+// so HBM is read once (all of a lane's 16-byte loads are issued back to back: 20 KB in flight per warp) and written once.
+// (The first mma.sync version re-read its rows from L1 / L2 in passes 2-4; with 24 warps x 20 KB per SM the re-reads
+// missed L1 and the kernel sat at 19 % of the DRAM peak on load latency: ncu long_scoreboard on every first use.)
+__device__ __forceinline__ float4 ld_stream4(const float* p) {        // read-once data: keep it out of L1 (the tables live there)
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+template <int H, int NT, int FMT, bool R16>
+__global__ void __launch_bounds__(128, 2) xattn_mma_kernel(
     float* __restrict__ hs, int ldh, int64_t rows_per_group, int ngroups, XattnK tk, const uint16_t* __restrict__ ap,
     const float* __restrict__ ca, const uint16_t* __restrict__ bmt, const float* __restrict__ bo,
     const float* __restrict__ g3, const float* __restrict__ b3, uint16_t* __restrict__ out, int ldo, float eps2,
     float eps3) {
     constexpr int C = 64 * H, V = H * NT, VP = (V + 15) / 16 * 16, NTILE = VP / 8, KV = VP / 16, KC = C / 16;
+    constexpr int R = R16 ? 16 : 8;
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2, tq = lane & 3;                                // fragment row within 8, column pair
-    const int64_t wpg = (rows_per_group + 15) / 16;                        // warps per row group
+    const int64_t wpg = (rows_per_group + R - 1) / R;                      // warps per row group
     const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int grp = (int)(gw / wpg);
     if (grp >= ngroups) return;
-    const int64_t local0 = (gw - (int64_t)grp * wpg) * 16;
+    const int64_t local0 = (gw - (int64_t)grp * wpg) * R;
     const int task = tk.task_of_group[grp];
     const uint16_t* apT = ap + (int64_t)task * VP * C;                     // [VP][C]
     const uint16_t* bmT = bmt + (int64_t)task * C * VP;                    // [C][VP]
     const float* caT = ca + task * VP;
-    // this lane's two rows (clamped: rows past the group's end are computed on the last row and not stored)
-    const bool live_a = local0 + g < rows_per_group, live_b = local0 + g + 8 < rows_per_group;
+    // this lane's rows (clamped: rows past the group's end are computed on the last row and not stored)
+    const bool live_a = local0 + g < rows_per_group, live_b = R16 && local0 + g + 8 < rows_per_group;
     const int64_t last = (int64_t)grp * rows_per_group + rows_per_group - 1;
     const int64_t row_a = live_a ? (int64_t)grp * rows_per_group + local0 + g : last;
     const int64_t row_b = live_b ? (int64_t)grp * rows_per_group + local0 + g + 8 : last;
     // The contraction index of an MMA may be permuted freely as long as both operands agree, and so may the columns of
     // its output: within every 16-wide block, fragment positions (2tq, 2tq+1, 2tq+8, 2tq+9) are mapped to the FOUR
-    // CONSECUTIVE columns 4tq .. 4tq+3, so a lane moves one 16-byte piece per row and block instead of two 8-byte ones
-    // (the first version was bound by L1 request rate: 62 % L1 busy, 17 % issue).
+    // CONSECUTIVE columns 4tq .. 4tq+3, so a lane moves one 16-byte piece per row and block.
     float* xa = hs + row_a * ldh + 4 * tq;
     float* xb = hs + row_b * ldh + 4 * tq;
-
-    // ---- pass 1: LayerNorm 2 statistics.  This is the pass that reads HBM, so the warp sweeps whole rows (512
-    // contiguous bytes per instruction, four rows in flight); the fragment-shaped 8-byte accesses of the later passes
-    // then hit L1 / L2.  (Reading HBM in the fragment pattern -- 32 bytes of a row at a time -- ran at 21 % of the
-    // copy peak.)
-    float mean_a = 0.f, rstd_a = 0.f, mean_b = 0.f, rstd_b = 0.f;
-#pragma unroll 1
-    for (int r0 = 0; r0 < 16; r0 += 4) {
-        float2 v[4][H];
+    constexpr int NB = R16 ? KC : 1;                                       // row b only exists for 16-row warps
+    float4 va[KC], vb[NB];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int64_t row = (local0 + r0 + r < rows_per_group) ? (int64_t)grp * rows_per_group + local0 + r0 + r : last;
-            const float2* src = reinterpret_cast<const float2*>(hs + row * ldh);
+    for (int kk = 0; kk < KC; ++kk) va[kk] = ld_stream4(xa + 16 * kk);
+    if (R16) {
 #pragma unroll
-            for (int i = 0; i < H; ++i) v[r][i] = __ldg(src + lane + 32 * i);
-        }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            float s = 0.f, q = 0.f;
-#pragma unroll
-            for (int i = 0; i < H; ++i) {
-                s += v[r][i].x + v[r][i].y;
-                q = fmaf(v[r][i].x, v[r][i].x, fmaf(v[r][i].y, v[r][i].y, q));
-            }
-            s = warp_sum(s);
-            q = warp_sum(q);
-            const float m = s * (1.0f / C);
-            const float rs = rsqrtf(fmaxf(q * (1.0f / C) - m * m, 0.f) + eps2);
-            if (r0 + r == g) { mean_a = m; rstd_a = rs; }
-            if (r0 + r == g + 8) { mean_b = m; rstd_b = rs; }
-        }
+        for (int kk = 0; kk < NB; ++kk) vb[kk] = ld_stream4(xb + 16 * kk);
     }
 
-    // ---- pass 2: scores[16 x VP] = xn[16 x C] . ap^T
+    // ---- LayerNorm 2 statistics: the four lanes of a quad hold one row; mean first, then the centred second moment
+    float mean_a, rstd_a, mean_b = 0.f, rstd_b = 0.f;
+    {
+        float s = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) s += (va[kk].x + va[kk].y) + (va[kk].z + va[kk].w);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        mean_a = s * (1.0f / C);
+        float q = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) {
+            const float d0 = va[kk].x - mean_a, d1 = va[kk].y - mean_a, d2 = va[kk].z - mean_a, d3 = va[kk].w - mean_a;
+            q = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, q))));
+        }
+        q += __shfl_xor_sync(0xffffffffu, q, 1);
+        q += __shfl_xor_sync(0xffffffffu, q, 2);
+        rstd_a = rsqrtf(q * (1.0f / C) + eps2);
+    }
+    if (R16) {
+        float s = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < NB; ++kk) s += (vb[kk].x + vb[kk].y) + (vb[kk].z + vb[kk].w);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        mean_b = s * (1.0f / C);
+        float q = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < NB; ++kk) {
+            const float d0 = vb[kk].x - mean_b, d1 = vb[kk].y - mean_b, d2 = vb[kk].z - mean_b, d3 = vb[kk].w - mean_b;
+            q = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, q))));
+        }
+        q += __shfl_xor_sync(0xffffffffu, q, 1);
+        q += __shfl_xor_sync(0xffffffffu, q, 2);
+        rstd_b = rsqrtf(q * (1.0f / C) + eps2);
+    }
+
+    // ---- scores[R x VP] = xn[R x C] . ap^T
     float sc[NTILE][4];
 #pragma unroll
     for (int t = 0; t < NTILE; ++t) { sc[t][0] = sc[t][1] = sc[t][2] = sc[t][3] = 0.f; }
-#pragma unroll 2
+    const float na = -mean_a * rstd_a, nb_ = -mean_b * rstd_b;
+#pragma unroll
     for (int kk = 0; kk < KC; ++kk) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(xa + 16 * kk)), b = __ldg(reinterpret_cast<const float4*>(xb + 16 * kk));
         uint32_t af[4];
-        af[0] = pack16x2((a.x - mean_a) * rstd_a, (a.y - mean_a) * rstd_a, FMT);
-        af[1] = pack16x2((b.x - mean_b) * rstd_b, (b.y - mean_b) * rstd_b, FMT);
-        af[2] = pack16x2((a.z - mean_a) * rstd_a, (a.w - mean_a) * rstd_a, FMT);
-        af[3] = pack16x2((b.z - mean_b) * rstd_b, (b.w - mean_b) * rstd_b, FMT);
+        af[0] = pack16x2(fmaf(va[kk].x, rstd_a, na), fmaf(va[kk].y, rstd_a, na), FMT);
+        af[2] = pack16x2(fmaf(va[kk].z, rstd_a, na), fmaf(va[kk].w, rstd_a, na), FMT);
+        if (R16) {
+            const float4 b = vb[R16 ? kk : 0];
+            af[1] = pack16x2(fmaf(b.x, rstd_b, nb_), fmaf(b.y, rstd_b, nb_), FMT);
+            af[3] = pack16x2(fmaf(b.z, rstd_b, nb_), fmaf(b.w, rstd_b, nb_), FMT);
+        } else {
+            af[1] = af[3] = 0u;
+        }
 #pragma unroll
         for (int t = 0; t < NTILE; ++t) {
             const uint2 w = __ldg(reinterpret_cast<const uint2*>(apT + (int64_t)(t * 8 + g) * C + 16 * kk + 4 * tq));
@@ -755,15 +792,14 @@ __global__ void __launch_bounds__(256) xattn_mma_kernel(
         }
         const float ia = la > 0.f ? 1.0f / la : 0.f, ib = lb > 0.f ? 1.0f / lb : 0.f;
         pf[t >> 1][(t & 1) * 2] = pack16x2(v0 * ia, v1 * ia, FMT);
-        pf[t >> 1][(t & 1) * 2 + 1] = pack16x2(v2 * ib, v3 * ib, FMT);
+        pf[t >> 1][(t & 1) * 2 + 1] = R16 ? pack16x2(v2 * ib, v3 * ib, FMT) : 0u;
     }
-    // ---- pass 3: h += bo + P . Bm, one 16-column block (two MMA column tiles) at a time; LayerNorm 3 statistics on the way.
+    // ---- h += bo + P . Bm, one 16-column block (two MMA column tiles) at a time, in registers.
     // Column tile 0 of a block produces channels 4q, 4q+1 and tile 1 channels 4q+2, 4q+3 of every quad q (see above); the
     // vector axis of bmt is stored in the matching fragment order by ops.xattn_tables.
-    float s3a = 0.f, q3a = 0.f, s3b = 0.f, q3b = 0.f;
     const int chq = 4 * (g >> 1) + (g & 1);                               // channel (within the block) of B column g, tile 0
-#pragma unroll 2
-    for (int nb = 0; nb < C / 16; ++nb) {
+#pragma unroll
+    for (int nb = 0; nb < KC; ++nb) {
         float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
         const uint16_t* bp0 = bmT + (int64_t)(16 * nb + chq) * VP + 4 * tq;
 #pragma unroll
@@ -774,36 +810,63 @@ __global__ void __launch_bounds__(256) xattn_mma_kernel(
             mma_16816(d1, pf[kv], w1.x, w1.y, FMT);
         }
         const float4 bias = __ldg(reinterpret_cast<const float4*>(bo + 16 * nb + 4 * tq));
-        float4 a = *reinterpret_cast<const float4*>(xa + 16 * nb), b = *reinterpret_cast<const float4*>(xb + 16 * nb);
-        a.x += bias.x + d0[0]; a.y += bias.y + d0[1]; a.z += bias.z + d1[0]; a.w += bias.w + d1[1];
-        b.x += bias.x + d0[2]; b.y += bias.y + d0[3]; b.z += bias.z + d1[2]; b.w += bias.w + d1[3];
-        if (live_a) *reinterpret_cast<float4*>(xa + 16 * nb) = a;
-        if (live_b) *reinterpret_cast<float4*>(xb + 16 * nb) = b;
-        s3a += (a.x + a.y) + (a.z + a.w); q3a = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, q3a))));
-        s3b += (b.x + b.y) + (b.z + b.w); q3b = fmaf(b.x, b.x, fmaf(b.y, b.y, fmaf(b.z, b.z, fmaf(b.w, b.w, q3b))));
+        va[nb].x += bias.x + d0[0]; va[nb].y += bias.y + d0[1]; va[nb].z += bias.z + d1[0]; va[nb].w += bias.w + d1[1];
+        if (live_a) *reinterpret_cast<float4*>(xa + 16 * nb) = va[nb];
+        if (R16) {
+            float4& b = vb[R16 ? nb : 0];
+            b.x += bias.x + d0[2]; b.y += bias.y + d0[3]; b.z += bias.z + d1[2]; b.w += bias.w + d1[3];
+            if (live_b) *reinterpret_cast<float4*>(xb + 16 * nb) = b;
+        }
     }
+    // ---- LayerNorm 3 of the updated rows -> 16-bit operand of the feed-forward
+    float m3a, r3a, m3b = 0.f, r3b = 0.f;
+    {
+        float s = 0.f;
 #pragma unroll
-    for (int o = 1; o < 4; o <<= 1) {
-        s3a += __shfl_xor_sync(0xffffffffu, s3a, o); q3a += __shfl_xor_sync(0xffffffffu, q3a, o);
-        s3b += __shfl_xor_sync(0xffffffffu, s3b, o); q3b += __shfl_xor_sync(0xffffffffu, q3b, o);
+        for (int kk = 0; kk < KC; ++kk) s += (va[kk].x + va[kk].y) + (va[kk].z + va[kk].w);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        m3a = s * (1.0f / C);
+        float q = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) {
+            const float d0 = va[kk].x - m3a, d1 = va[kk].y - m3a, d2 = va[kk].z - m3a, d3 = va[kk].w - m3a;
+            q = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, q))));
+        }
+        q += __shfl_xor_sync(0xffffffffu, q, 1);
+        q += __shfl_xor_sync(0xffffffffu, q, 2);
+        r3a = rsqrtf(q * (1.0f / C) + eps3);
     }
-    const float m3a = s3a * (1.0f / C), m3b = s3b * (1.0f / C);
-    const float r3a = rsqrtf(fmaxf(q3a * (1.0f / C) - m3a * m3a, 0.f) + eps3);
-    const float r3b = rsqrtf(fmaxf(q3b * (1.0f / C) - m3b * m3b, 0.f) + eps3);
-    // ---- pass 4: LayerNorm 3 of the rows just written (every lane re-reads its OWN stores) -> 16-bit operand
+    if (R16) {
+        float s = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < NB; ++kk) s += (vb[kk].x + vb[kk].y) + (vb[kk].z + vb[kk].w);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        m3b = s * (1.0f / C);
+        float q = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < NB; ++kk) {
+            const float d0 = vb[kk].x - m3b, d1 = vb[kk].y - m3b, d2 = vb[kk].z - m3b, d3 = vb[kk].w - m3b;
+            q = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, q))));
+        }
+        q += __shfl_xor_sync(0xffffffffu, q, 1);
+        q += __shfl_xor_sync(0xffffffffu, q, 2);
+        r3b = rsqrtf(q * (1.0f / C) + eps3);
+    }
     uint16_t* oa = out + row_a * ldo + 4 * tq;
     uint16_t* ob = out + row_b * ldo + 4 * tq;
-#pragma unroll 4
-    for (int nb = 0; nb < C / 16; ++nb) {
+#pragma unroll
+    for (int nb = 0; nb < KC; ++nb) {
         const float4 gg = __ldg(reinterpret_cast<const float4*>(g3 + 16 * nb + 4 * tq)), bb = __ldg(reinterpret_cast<const float4*>(b3 + 16 * nb + 4 * tq));
         if (live_a) {
-            const float4 a = *reinterpret_cast<const float4*>(xa + 16 * nb);
+            const float4 a = va[nb];
             *reinterpret_cast<uint2*>(oa + 16 * nb) =
                 make_uint2(pack16x2((a.x - m3a) * r3a * gg.x + bb.x, (a.y - m3a) * r3a * gg.y + bb.y, FMT),
                            pack16x2((a.z - m3a) * r3a * gg.z + bb.z, (a.w - m3a) * r3a * gg.w + bb.w, FMT));
         }
-        if (live_b) {
-            const float4 b = *reinterpret_cast<const float4*>(xb + 16 * nb);
+        if (R16 && live_b) {
+            const float4 b = vb[R16 ? nb : 0];
             *reinterpret_cast<uint2*>(ob + 16 * nb) =
                 make_uint2(pack16x2((b.x - m3b) * r3b * gg.x + bb.x, (b.y - m3b) * r3b * gg.y + bb.y, FMT),
                            pack16x2((b.z - m3b) * r3b * gg.z + bb.z, (b.w - m3b) * r3b * gg.w + bb.w, FMT));
@@ -1246,10 +1309,12 @@ extern "C" int smtl_xattn_run(const smtl_xattn_args* a, void* stream) {
 
 template <int H, int NT>
 static int launch_xattn_mma(const smtl_xattnf_args* a, const XattnK& tk, int ngroups, cudaStream_t st) {
-    const int64_t wpg = (a->rows_per_group + 15) / 16;
+    constexpr bool R16 = H <= 5;                   // 160 fp32 of row data per lane: 16 rows up to 320 channels, 8 rows at 640
+    constexpr int R = R16 ? 16 : 8;
+    const int64_t wpg = (a->rows_per_group + R - 1) / R;
     const int64_t warps = wpg * ngroups;
-    auto kern = a->fmt16 == SMTL_FMT_F16 ? xattn_mma_kernel<H, NT, FMT_F16> : xattn_mma_kernel<H, NT, FMT_BF16>;
-    kern<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(
+    auto kern = a->fmt16 == SMTL_FMT_F16 ? xattn_mma_kernel<H, NT, FMT_F16, R16> : xattn_mma_kernel<H, NT, FMT_BF16, R16>;
+    kern<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(
         a->hs, a->ldh, a->rows_per_group, ngroups, tk, (const uint16_t*)a->ap, a->ca, (const uint16_t*)a->bmt, a->bo,
         a->gamma3, a->beta3, (uint16_t*)a->out_bf16, a->ldo, a->eps2, a->eps3);
     SMTL_CHECK_CUDA(cudaGetLastError());

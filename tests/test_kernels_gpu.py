@@ -144,7 +144,8 @@ def test_conv3x3_implicit_gemm(b, h, w, cin, cout, cs):
     assert err < 2e-5, f"conv rel-L2 {err}"
 
 
-@pytest.mark.parametrize("batch,ntok,heads", [(1, 128, 1), (2, 300, 5), (1, 80, 20), (2, 1200, 10), (1, 4800, 5), (3, 468, 2)])
+@pytest.mark.parametrize("batch,ntok,heads", [(1, 128, 1), (2, 300, 5), (1, 80, 20), (2, 1200, 10), (1, 4800, 5), (3, 468, 2),
+                                              (1, 24, 2), (2, 64, 1), (1, 65, 1), (2, 129, 2), (1, 512, 1), (2, 513, 1), (2, 700, 3)])
 def test_flash_attention(batch, ntok, heads):
     ops, L = _ops()
     c = heads * 64
