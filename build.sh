@@ -3,5 +3,5 @@
 set -e
 cd "$(dirname "$0")"
 SRC="stablemtl_b200/csrc/smtl_api.cu stablemtl_b200/csrc/smtl_gemm.cu stablemtl_b200/csrc/smtl_elem.cu stablemtl_b200/csrc/smtl_attn.cu"
-nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared \
+nvcc --threads 4 -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared \
      -o stablemtl_b200/libstablemtl_sm100.so $SRC "$@"

@@ -142,9 +142,38 @@ if __name__ == "__main__":
             print(f"xattn_fused heads={heads} rows={7 * rpg}                       {ms:9.3f} ms {gb / ms * 1e3:8.1f} GB/s  "
                   f"{gb / ms * 1e3 / 6552.6 * 100:5.1f}% of measured HBM copy peak", flush=True)
         sys.exit(0)
+    if only == "up":           # the VAE decoder's three "nearest 2x + 3x3 conv" layers (four per-parity 2x2 convs each), 16 images
+        for h, w, cin, cout in ((60, 80, 512, 512), (120, 160, 512, 512), (240, 320, 256, 256)):
+            b = 16
+            low = rb(b * (h + 2) * (w + 2), cin)
+            wmats = [m.to(DEV).to(ops.h16()) for m in ops.up2x_weight_matrices(torch.randn(cout, cin, 3, 3) * (9 * cin) ** -0.5)]
+            out = torch.zeros(b * (2 * h + 2) * (2 * w + 2), cout, device=DEV, dtype=ops.h16())
+            st = ops.new_stats(b, cout, DEV, replicas=4)
+            four = ops.conv_up2x(low, wmats, b, h, w, bias=torch.zeros(cout, device=DEV), pad_out=True, out_bf16=out, stats=st,
+                                 stats_rows_per_image=(2 * h + 2) * (2 * w + 2))
+            class Four:
+                flops = sum(o.flops_exec for o in four)
+                def run(self):
+                    for o in four:
+                        o.run()
+            report(f"up2x conv (4 launches, executed flops) b={b} {h}x{w} {cin}->{cout}", Four())
+            conv_case(f"same-shape 3x3 conv at {h}x{w}", b, h, w, cin, cout)
+        sys.exit(0)
+    if only == "act":          # GEMMs whose epilogue carries a GELU: GEGLU feed-forward and the per-task MLPs (UNet level 0 / 1)
+        from stablemtl_b200.weights import interleave_geglu
+        for m, c in ((112 * 4800, 320), (112 * 1200, 640)):
+            a, w, bias = rb(m, c), rb(8 * c, c), torch.randn(8 * c, device=DEV)
+            wi, bi = interleave_geglu(w, bias)
+            out = torch.empty(m, 4 * c, device=DEV, dtype=ops.h16())
+            report(f"ff1 geglu m={m} k={c} n={8 * c}", ops.gemm(a, wi, bias=bi, act=L.ACT_GEGLU, out_bf16=out))
+            w2, b2 = rb(c, c), torch.randn(c, device=DEV)
+            out2 = torch.empty(m, c, device=DEV, dtype=ops.h16())
+            report(f"task mlp gelu m={m} k={c} n={c}", ops.gemm(a, w2, bias=b2, act=L.ACT_GELU, out_bf16=out2))
+            report(f"linear (no act) m={m} k={c} n={c}", ops.gemm(a, w2, bias=b2, out_bf16=out2))
+        sys.exit(0)
     if only == "attn":
         for args in [(16, 4800, 5), (112, 4800, 5), (112, 1200, 10), (112, 300, 20), (112, 80, 20)]:
-            for variant in (1, 0):
+            for variant in (1, 0, 2, 3, 4):
                 attn_case(*args, variant=variant)
         sys.exit(0)
     gemm_case("square", 8192, 8192, 8192)

@@ -58,6 +58,14 @@ elif case == "sqcg2":
 elif case == "head":
     a = rb(8 * 482 * 642, 128); w = rb(3, 9 * 128); out = torch.empty(8 * 480 * 640, 3, device=DEV)
     op = ops.conv3x3(a, w, 8, 480, 640, bias=torch.zeros(3, device=DEV), out_f32=out)
+elif case in ("up2", "up1"):  # one output parity of the VAE decoder's "nearest 2x + 3x3 conv" (2x2 taps), 16 images
+    b, h, wd, c = (16, 240, 320, 256) if case == "up2" else (16, 120, 160, 512)
+    low = rb(b * (h + 2) * (wd + 2), c)
+    wmats = [m.to(DEV).to(ops.h16()) for m in ops.up2x_weight_matrices(torch.randn(c, c, 3, 3) * (9 * c) ** -0.5)]
+    out = torch.zeros(b * (2 * h + 2) * (2 * wd + 2), c, device=DEV, dtype=ops.h16())
+    st = ops.new_stats(b, c, DEV, replicas=4)
+    op = ops.conv_up2x(low, wmats, b, h, wd, bias=torch.zeros(c, device=DEV), pad_out=True, out_bf16=out, stats=st,
+                       stats_rows_per_image=(2 * h + 2) * (2 * wd + 2))[3]
 elif case == "attn":
     batch, ntok, heads = 16, 4800, 5
     c = heads * 64

@@ -317,7 +317,7 @@ constexpr int F4_REGS = 96;
 constexpr int F4_NS = 4;                                   // K/V ring stages (one 128-key box of K and of V: 32 KB)
 constexpr int F4_SMEM = F4_NQ * TILE_BYTES + F4_NS * 2 * TILE_BYTES + 256;
 
-template <bool MASKED, int FMT>
+template <bool MASKED, int FMT, int POLY>
 __device__ __forceinline__ void softmax_step64(const FattnKParams& p, uint32_t t_s, int kv_valid, float& m_run,
                                                float& l_run, uint32_t t_o, bool have_o) {
     uint32_t rr[64];
@@ -362,7 +362,8 @@ __device__ __forceinline__ void softmax_step64(const FattnKParams& p, uint32_t t
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
             const float2 t = ffma2(make_float2(__uint_as_float(rr[c * 32 + i]), __uint_as_float(rr[c * 32 + i + 1])), sc2, nm2);
-            float2 e = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+            // POLY of every 8 pairs take their exponential on the FMA pipe instead of the SFU
+            float2 e = (((i >> 1) & 7) < POLY) ? ex2_poly2(t) : make_float2(ex2_approx(t.x), ex2_approx(t.y));
             if (MASKED) {
                 e.x = (c * 32 + i < kv_valid) ? e.x : 0.f;
                 e.y = (c * 32 + i + 1 < kv_valid) ? e.y : 0.f;
@@ -376,7 +377,7 @@ __device__ __forceinline__ void softmax_step64(const FattnKParams& p, uint32_t t
     tmem_st_wait();
 }
 
-template <int FMT>
+template <int FMT, int POLY>
 __global__ void __maxnreg__(F4_REGS) smtl_fattn4_kernel(const __grid_constant__ FattnKParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sQ = smem;                                    // 4 tiles
@@ -491,8 +492,8 @@ __global__ void __maxnreg__(F4_REGS) smtl_fattn4_kernel(const __grid_constant__ 
             for (int j = 0; j < nsub; ++j) {
                 mbar_wait(&s_full[w], j & 1);                  // S_w(j) ready; implies PV_w(j-1) retired
                 tc_fence_after();
-                if (j == nsub - 1 && tail < F4_KS) softmax_step64<true, FMT>(p, t_s, tail, m_run, l_run, t_o, j > 0);
-                else softmax_step64<false, FMT>(p, t_s, F4_KS, m_run, l_run, t_o, j > 0);
+                if (j == nsub - 1 && tail < F4_KS) softmax_step64<true, FMT, POLY>(p, t_s, tail, m_run, l_run, t_o, j > 0);
+                else softmax_step64<false, FMT, POLY>(p, t_s, F4_KS, m_run, l_run, t_o, j > 0);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p_full[w]);
@@ -796,12 +797,17 @@ extern "C" int smtl_fattn_run(const smtl_fattn_op* op, void* stream) {
         SMTL_CHECK_CUDA(cudaGetLastError());
         return SMTL_OK;
     }
+    using Kern = void (*)(const FattnKParams);
+    static const Kern kerns[2][4] = {
+        {smtl_fattn4_kernel<FMT_BF16, 0>, smtl_fattn4_kernel<FMT_BF16, 1>, smtl_fattn4_kernel<FMT_BF16, 2>, smtl_fattn4_kernel<FMT_BF16, 3>},
+        {smtl_fattn4_kernel<FMT_F16, 0>, smtl_fattn4_kernel<FMT_F16, 1>, smtl_fattn4_kernel<FMT_F16, 2>, smtl_fattn4_kernel<FMT_F16, 3>}};
     static std::atomic<uint64_t> attr4{0};
-    if (smtl_host::first_use_on_device(attr4)) {
-        SMTL_CHECK_CUDA(cudaFuncSetAttribute(smtl_fattn4_kernel<FMT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM));
-        SMTL_CHECK_CUDA(cudaFuncSetAttribute(smtl_fattn4_kernel<FMT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM));
-    }
-    auto kern = a.fmt16 == SMTL_FMT_F16 ? smtl_fattn4_kernel<FMT_F16> : smtl_fattn4_kernel<FMT_BF16>;
+    if (smtl_host::first_use_on_device(attr4))
+        for (int f = 0; f < 2; ++f)
+            for (int q = 0; q < 4; ++q)
+                SMTL_CHECK_CUDA(cudaFuncSetAttribute(kerns[f][q], cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM));
+    const int poly = (op->pad_ >= 2 && op->pad_ <= 4) ? op->pad_ - 1 : 0;        // EXPERIMENT knob
+    Kern kern = kerns[a.fmt16 == SMTL_FMT_F16 ? 1 : 0][poly];
     kern<<<dim3(op->grid_x, op->grid_y), F4_THREADS, op->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(kp);
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;

@@ -151,8 +151,13 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
     return r;
 }
+// Arrive on an mbarrier of another CTA of the cluster.  Default semantics (release at CTA scope) -- NOT `.release.cluster`:
+// that form compiles to MEMBAR.ALL.GPU + ERRBAR in front of the arrive, i.e. the epilogue warp waited for every global
+// store of its tile to be acknowledged before it handed the accumulator back (ncu: 4 % of all samples on the ERRBAR of a
+// K = 1024 conv).  What the peer's MMA warp needs ordered is this warp's TMEM reads, and those are complete at
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load issued by one CTA of a pair whose completion is signalled on an mbarrier that may live in the PEER CTA
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tmap, uint32_t bar_cluster_addr,
@@ -303,6 +308,32 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
         : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
     return d;
 }
+// round-toward-minus-infinity add (FADD2.RM): x + 1.5 * 2^23 leaves floor(x) in the low mantissa bits
+__device__ __forceinline__ float2 fadd2_rm(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "add.rm.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+// 2^x for a pair on the FMA pipe (no SFU): floor by the magic-number add, a cubic for 2^frac on [0, 1) (max relative
+// error 9e-5, below the 16-bit rounding of the probabilities it produces), the integer part added into the exponent
+// field.  x is clamped at -126 (result 2^-126 ~ 0).  10 issue slots per pair against 2 MUFU.EX2 = 16 SFU cycles.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+    x.x = fmaxf(x.x, -126.0f);
+    x.y = fmaxf(x.y, -126.0f);
+    const float2 magic = make_float2(12582912.0f, 12582912.0f);
+    const float2 r = fadd2_rm(x, magic);
+    const float2 back = fadd2(r, make_float2(-12582912.0f, -12582912.0f));
+    const float2 f = fadd2(x, make_float2(-back.x, -back.y));
+    float2 pl = ffma2(f, make_float2(0.077119089663028717f, 0.077119089663028717f), make_float2(0.227564394474029541f, 0.227564394474029541f));
+    pl = ffma2(pl, f, make_float2(0.695146143436431885f, 0.695146143436431885f));
+    pl = ffma2(pl, f, make_float2(1.0f, 1.0f));
+    return make_float2(__uint_as_float(__float_as_uint(pl.x) + (__float_as_uint(r.x) << 23)),
+                       __uint_as_float(__float_as_uint(pl.y) + (__float_as_uint(r.y) << 23)));
+}
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 // erf-GELU with erf from Abramowitz & Stegun 7.1.26 (|abs error| < 1.5e-7, far below the 16-bit rounding of the
 // value it produces): one rcp, one ex2 and 7 FMAs instead of libm erff's ~35 instructions in the GEMM epilogue
@@ -320,6 +351,33 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
     const float erf_abs = fmaf(-pl, e, 1.0f);                 // erf(|x|/sqrt2)
     const float half_x = 0.5f * x;
     return fmaf(fabsf(half_x), erf_abs, half_x);               // 0.5 x (1 + sign(x) erf(|x|/sqrt2))
+}
+// erf-GELU for a PAIR on the FMA pipe alone (no SFU): gelu(x) = x * Phi(x), Phi(x) = 0.5 + xc * R(xc^2) with xc = x
+// clamped to +-4.5 (Phi(-4.5) = 3.4e-6) and R a degree-10 polynomial in t = 2 xc^2 / 4.5^2 - 1 (Chebyshev fit of
+// (Phi(x) - 0.5) / x, converted to the monomial basis in t: well conditioned in fp32).  |error| < 3e-6 for |x| <= 4.5 and
+// < 3e-6 * |x| beyond, far below the 16-bit rounding of the value.  Packed FFMA2: ~9 issue slots per element against
+// 15 + 2 SFU ops for gelu_erf_fast -- the GEGLU / per-task MLP epilogues are issue- and SFU-bound at K = 320.
+__device__ __forceinline__ float2 gelu_poly2(float2 x) {
+    float2 xc;
+    xc.x = fminf(fmaxf(x.x, -4.5f), 4.5f);
+    xc.y = fminf(fmaxf(x.y, -4.5f), 4.5f);
+    const float2 s = ffma2(xc, xc, make_float2(0.f, 0.f));
+    const float k = 2.0f / (4.5f * 4.5f);
+    const float2 t = ffma2(s, make_float2(k, k), make_float2(-1.0f, -1.0f));
+#define SMTL_C2(v) make_float2(v, v)
+    float2 r = ffma2(t, SMTL_C2(0.000789802405051887f), SMTL_C2(-0.002244635485112667f));
+    r = ffma2(r, t, SMTL_C2(0.00314583582803607f));
+    r = ffma2(r, t, SMTL_C2(-0.0054423320107162f));
+    r = ffma2(r, t, SMTL_C2(0.01110508106648922f));
+    r = ffma2(r, t, SMTL_C2(-0.018895722925662994f));
+    r = ffma2(r, t, SMTL_C2(0.028388366103172302f));
+    r = ffma2(r, t, SMTL_C2(-0.040139030665159225f));
+    r = ffma2(r, t, SMTL_C2(0.05468999966979027f));
+    r = ffma2(r, t, SMTL_C2(-0.07719199359416962f));
+    r = ffma2(r, t, SMTL_C2(0.15690511465072632f));
+    const float2 ph = ffma2(xc, r, SMTL_C2(0.5f));
+#undef SMTL_C2
+    return ffma2(x, ph, make_float2(0.f, 0.f));
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 // x * sigmoid(x) with sigmoid(x) = 0.5 tanh(0.5 x) + 0.5: ONE SFU op (tanh.approx, rel. error ~2^-11, below the

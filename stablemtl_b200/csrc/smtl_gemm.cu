@@ -341,14 +341,20 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t tad
             tmem_ld_wait();
             const float gl = bq[BN / 64];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float g = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, gl, j);
-                v[j] *= gelu_erf_fast(g);
+            for (int j = 0; j < 32; j += 2) {
+                const float2 g = gelu_poly2(make_float2(__uint_as_float(r[j]) + __shfl_sync(0xffffffffu, gl, j),
+                                                        __uint_as_float(r[j + 1]) + __shfl_sync(0xffffffffu, gl, j + 1)));
+                v[j] *= g.x;
+                v[j + 1] *= g.y;
             }
             ocol = tn * (BN / 2) + c0;
         } else if (p.act == SMTL_ACT_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+            for (int j = 0; j < 32; j += 2) {
+                const float2 g = gelu_poly2(make_float2(v[j], v[j + 1]));
+                v[j] = g.x;
+                v[j + 1] = g.y;
+            }
         } else if (p.act == SMTL_ACT_SILU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
@@ -436,7 +442,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t tad
 // CG = 1: one CTA per 128-row tile.  CG = 2: a CTA PAIR (2-SM cluster) per 256-row tile -- each CTA stages its own
 // 128 A rows and HALF of the B tile, the leader issues tcgen05.mma.cta_group::2 (M = 256) and each CTA's TMEM
 // receives its 128 accumulator rows: half the shared-memory and L2 operand traffic per flop.
-template <int BN, int CG>
+template <int BN, int CG, int FMT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_constant__ GemmKParams p) {
     constexpr int B_ROWS = BN / CG;                                   // B rows this CTA stages
     constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
@@ -606,7 +612,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
         // UTCBAR are warp-uniform and wraps every MMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop: ~165 clk
         // of issue overhead per MMA (ncu source view), a floor above the 16..128 tensor cycles of the MMA itself.
         if (leader && grouped) {
-            const uint32_t IDESC = make_idesc_16(BLOCK_M * CG, BN, 0, 0, p.fmt);
+            const uint32_t IDESC = make_idesc_16(BLOCK_M * CG, BN, 0, 0, FMT);
             int ps = 0, ws = 0;
             uint32_t pph = 0, wph = 0;
             int it = 0;
@@ -654,7 +660,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
                 __syncwarp();
             }
         } else if (leader) {
-            const uint32_t IDESC = make_idesc_16(BLOCK_M * CG, BN, 0, 0, p.fmt);
+            const uint32_t IDESC = make_idesc_16(BLOCK_M * CG, BN, 0, 0, FMT);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -744,8 +750,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
             mbar_wait_backoff(&acc_full[acc], acc_phase, 100);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
-            if (p.fmt == FMT_F16) epilogue_rows<BN, FMT_F16>(p, taddr, tn, lane, half, er, stats_acc);
-            else epilogue_rows<BN, FMT_BF16>(p, taddr, tn, lane, half, er, stats_acc);
+            // FMT is a template parameter of the KERNEL: with both formats' epilogues inlined the code was 190 KB and
+            // ncu charged 11 % of the samples of a K = 1024 conv to instruction fetch (no_inst)
+            epilogue_rows<BN, FMT>(p, taddr, tn, lane, half, er, stats_acc);
             // release this accumulator stage back to the (leader's) MMA warp
             tc_fence_before();
             __syncwarp();
@@ -1115,14 +1122,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
     }
 }
 
-template <int BN, int CG>
-int launch_gemm(const GemmKParams& kp, int grid, int smem_bytes, cudaStream_t stream) {
+template <int BN, int CG, int FMT>
+int launch_gemm_fmt(const GemmKParams& kp, int grid, int smem_bytes, cudaStream_t stream) {
     static std::atomic<uint64_t> attr_devs{0};   // per instantiation, one bit per device ordinal
     if (smtl_host::first_use_on_device(attr_devs))
-        SMTL_CHECK_CUDA(cudaFuncSetAttribute(smtl_gemm_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        SMTL_CHECK_CUDA(cudaFuncSetAttribute(smtl_gemm_kernel<BN, CG, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              SMEM_BUDGET));
     if (CG == 1) {
-        smtl_gemm_kernel<BN, CG><<<grid, NUM_THREADS, smem_bytes, stream>>>(kp);
+        smtl_gemm_kernel<BN, CG, FMT><<<grid, NUM_THREADS, smem_bytes, stream>>>(kp);
     } else {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid, 1, 1);
@@ -1136,10 +1143,15 @@ int launch_gemm(const GemmKParams& kp, int grid, int smem_bytes, cudaStream_t st
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        SMTL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, smtl_gemm_kernel<BN, CG>, kp));
+        SMTL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, smtl_gemm_kernel<BN, CG, FMT>, kp));
     }
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;
+}
+template <int BN, int CG>
+int launch_gemm(const GemmKParams& kp, int grid, int smem_bytes, cudaStream_t stream) {
+    return kp.fmt == FMT_F16 ? launch_gemm_fmt<BN, CG, FMT_F16>(kp, grid, smem_bytes, stream)
+                             : launch_gemm_fmt<BN, CG, FMT_BF16>(kp, grid, smem_bytes, stream);
 }
 
 template <int BN>
