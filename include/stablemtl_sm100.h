@@ -120,7 +120,11 @@ typedef struct smtl_gemm_args {
      * the column-tile-major order (auto picks 2 for statistics producers: their per-column sums stay on chip for a whole
      * (image, column tile) run and reach `stats` as one atomic per cell). */
     int32_t tile_order;
-    int32_t pad_;
+    /* Statistics granularity: 0 / 1 = one cell per channel.  2, 4 or 8 = the sums of that many ADJACENT channels land in
+     * the cell of the first one and the other cells stay zero -- the same totals for every consumer whose GroupNorm
+     * groups are unions of such aligned blocks (a group's cells are summed), with a fraction of the epilogue's
+     * cross-lane reduction.  n must be a multiple of it. */
+    int32_t stats_group;
 } smtl_gemm_args;
 
 typedef struct smtl_gemm_op {

@@ -98,6 +98,9 @@ if __name__ == "__main__":
             conv_case(args[0] + " no stats contiguous", *args[1:], stats=False, tile_order=2)
             conv_case(args[0] + " stats round-robin", *args[1:], tile_order=1)
             conv_case(args[0] + " stats contiguous", *args[1:], tile_order=2)
+            for g in (2, 8):
+                if (args[-1] // 32) % g == 0:
+                    conv_case(args[0] + f" stats contiguous, {g}-channel cells", *args[1:], tile_order=2, stats_group=g)
         sys.exit(0)
     if only == "stages":
         conv_case("vae 1/4 512->512", 8, 120, 160, 512, 512)
@@ -150,7 +153,7 @@ if __name__ == "__main__":
             out = torch.zeros(b * (2 * h + 2) * (2 * w + 2), cout, device=DEV, dtype=ops.h16())
             st = ops.new_stats(b, cout, DEV, replicas=4)
             four = ops.conv_up2x(low, wmats, b, h, w, bias=torch.zeros(cout, device=DEV), pad_out=True, out_bf16=out, stats=st,
-                                 stats_rows_per_image=(2 * h + 2) * (2 * w + 2))
+                                 stats_rows_per_image=(2 * h + 2) * (2 * w + 2), stats_group=8)
             class Four:
                 flops = sum(o.flops_exec for o in four)
                 def run(self):

@@ -56,7 +56,7 @@ class GemmArgs(C.Structure):
         ("stats_rows_per_image", i32), ("stats_images", i32),
         ("cta_group", i32), ("up_parity", i32),
         ("group_rows", i64),
-        ("tile_order", i32), ("pad_", i32),
+        ("tile_order", i32), ("stats_group", i32),
     ]
 
 

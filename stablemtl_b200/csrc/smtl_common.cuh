@@ -498,4 +498,50 @@ __device__ __forceinline__ float warp_transpose_sum(float (&s)[32], int lane) {
     return s[0];
 }
 
+// N values per lane (N = 1, 2, ... 32, a power of two): lane L <- the warp total of value L / (32 / N).  The first
+// log2(N) stages halve the number of values (splitting on lane bits 4, 3, ...), the rest are a plain butterfly:
+// N - 1 + 5 - log2(N) shuffles.  N = 32 is warp_transpose_sum.
+template <int N>
+__device__ __forceinline__ float warp_transpose_sum_n(float (&s)[N], int lane) {
+    int off = 16;
+#pragma unroll
+    for (int n = N / 2; n >= 1; n >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const float mine = upper ? s[i + n] : s[i];
+            const float other = upper ? s[i] : s[i + n];
+            s[i] = mine + __shfl_xor_sync(0xffffffffu, other, off);
+        }
+        off >>= 1;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        if (off >= 1) s[0] += __shfl_xor_sync(0xffffffffu, s[0], off);
+        off >>= 1;
+    }
+    return s[0];
+}
+// Column statistics of one 32-row x 32-column epilogue chunk (lane = row, v[j] = column j), G adjacent columns summed
+// in the thread first: lane L with L % G == 0 gets the sum / sum of squares of columns L .. L + G - 1 over the 32 rows.
+template <int G>
+__device__ __forceinline__ void chunk_col_stats(const float (&v)[32], bool row_ok, int lane, float& cs, float& cq) {
+    constexpr int N = 32 / G;
+    float s[N], q[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            const float x = row_ok ? v[i * G + k] : 0.0f;
+            a += x;
+            b = fmaf(x, x, b);
+        }
+        s[i] = a;
+        q[i] = b;
+    }
+    cs = warp_transpose_sum_n<N>(s, lane);
+    cq = warp_transpose_sum_n<N>(q, lane);
+}
+
 }  // namespace smtl

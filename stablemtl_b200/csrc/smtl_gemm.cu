@@ -61,7 +61,7 @@ struct alignas(64) GemmKParams {
     int32_t ldres;
     int32_t res16;
     unsigned long long* stats;   // int64 fixed-point cells [rep, images, n_out, 4] (smtl_common.cuh: stats_atomic_add)
-    int32_t stats_rpi, stats_images, stats_rep;
+    int32_t stats_rpi, stats_images, stats_rep, stats_g;
     // Image-aligned tiling (set whenever stats are produced): M tiles restart at every image's first GEMM row, so the
     // 32-row partial sums of an image are the same fp32 values wherever the image sits in the batch.
     int64_t tile_rpi;            // GEMM rows per image; 0 = tiles run over all rows
@@ -80,6 +80,7 @@ struct alignas(64) GemmKParams {
     int32_t img_h, img_w;
     int32_t up_py, up_px;
     int32_t fmt;
+    int32_t lean;         // the launch qualifies for epilogue_rows_lean
     int64_t group_rows;   // 0: plain; else rows per weight group
     // "shift-grouped" mainloop: up to three K segments whose row shifts are consecutive (the kx = -1, 0, +1 taps of
     // one ky of a 3x3 conv) share ONE activation tile loaded with 8 extra rows; the MMA descriptor of tap j simply
@@ -301,11 +302,103 @@ __device__ __forceinline__ void add_residual(const GemmKParams& p, const void* r
     }
 }
 
+// The statistics of one chunk (lane = row, v = the 32 stored columns starting at `ocol`) into this warp's on-chip cells.
+__device__ __forceinline__ void chunk_stats_to_cells(const GemmKParams& p, const float (&v)[32], bool row_ok, int lane, int ocol,
+                                                     int c0, int img, uint32_t stats_acc) {
+    // stats_g adjacent channels share a cell when every consumer's GroupNorm groups are unions of such blocks
+    // (smtl_gemm_args.stats_group): the cross-lane reduction shrinks from 2 x 31 shuffles to 2 x 6 at 8 channels
+    float cs, cq;
+    if (p.stats_g == 8) chunk_col_stats<8>(v, row_ok, lane, cs, cq);
+    else if (p.stats_g == 4) chunk_col_stats<4>(v, row_ok, lane, cs, cq);
+    else if (p.stats_g == 2) chunk_col_stats<2>(v, row_ok, lane, cs, cq);
+    else chunk_col_stats<1>(v, row_ok, lane, cs, cq);
+    if (ocol + lane < p.n_out && (lane & (p.stats_g - 1)) == 0) {
+        // fine cells accumulate in this warp's shared-memory slots (flushed once per (image, column tile) run);
+        // a partial too large for the fine scale (|x| >= 2^14: rare) goes straight to its coarse global cell
+        const uint32_t cell = stats_acc + (uint32_t)(((c0 >> 6) * 32 + lane) * 16);
+        unsigned long long* gcell = p.stats + (((int64_t)(blockIdx.x % p.stats_rep) * p.stats_images + img) *
+                                                   p.n_out + ocol + lane) * 4;
+        long long as, aq;
+        lds_v2_s64(cell, as, aq);
+        bool hi;
+        long long f = stats_fix(cs, hi);
+        if (hi) atomicAdd(gcell + 1, (unsigned long long)f); else as += f;
+        f = stats_fix(cq, hi);
+        if (hi) atomicAdd(gcell + 3, (unsigned long long)f); else aq += f;
+        sts_v2_s64(cell, as, aq);
+    }
+}
+
+// The epilogue of the path's commonest GEMM, with nothing else in the instruction stream: column bias, optional 16-bit
+// residual, 16-bit output (+ zero halo), GroupNorm statistics -- every 3x3 conv of the VAE and the UNet and the plain
+// token linears.  The general epilogue below serves that case with ~830 instructions per 32 x 32 chunk (ncu: 47 branches
+// on per-launch flags, 32 shuffles to broadcast the bias, scalar fallbacks in every store) and two warps per SM
+// sub-partition to issue them: a K = 1024 conv spent 10 us in the epilogue of a tile whose MMAs take 6.4.
+template <int BN, int FMT>
+__device__ __forceinline__ void epilogue_rows_lean(const GemmKParams& p, uint32_t taddr, int tn, int lane, int half,
+                                                   const EpiRow<BN>& e, uint32_t stats_acc) {
+    const int n0 = tn * BN;
+    const bool row_ok = e.row_ok;
+    uint16_t* const out_row = p.out_bf16 + e.orow * (int64_t)p.ldc;
+    const uint16_t* const res_row = reinterpret_cast<const uint16_t*>(p.res1) + e.orow * (int64_t)p.ldres;
+    const bool do_stats = p.stats && e.img_lo <= e.img_hi;
+#pragma unroll 1
+    for (int c0 = half * 32; c0 < BN; c0 += 64) {
+        const int ocol = n0 + c0;
+        if (ocol >= p.n) break;                            // warp-uniform
+        uint32_t r[32];
+        float v[32];
+        tmem_ld_32x32(taddr + c0, r);
+        // the chunk's 32 bias values: every lane reads the SAME 16-byte pieces (one broadcast transaction each, L1-resident)
+        float4 b4[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(p.bias + ocol) + i);
+        uint32_t rs[16];
+        if (p.res1 && row_ok) {
+            ldg_nc_v8(res_row + ocol, rs);
+            ldg_nc_v8(res_row + ocol + 16, rs + 8);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            v[4 * i] = __uint_as_float(r[4 * i]) + b4[i].x;
+            v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b4[i].y;
+            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b4[i].z;
+            v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b4[i].w;
+        }
+        if (p.res1 && row_ok) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const float2 f = unpack16x2(rs[q], FMT);
+                v[2 * q] += f.x;
+                v[2 * q + 1] += f.y;
+            }
+        }
+        if (row_ok) {
+            uint32_t w[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w[j] = pack16x2(v[2 * j], v[2 * j + 1], FMT);
+            st_global_v8_b32(out_row + ocol, w);
+            st_global_v8_b32(out_row + ocol + 16, w + 8);
+        } else if (e.halo) {                               // PAD_KEEP: the output keeps a zero halo for its consumers
+            const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            st_global_v8_b32(out_row + ocol, z);
+            st_global_v8_b32(out_row + ocol + 16, z);
+        }
+        __syncwarp();   // reconverge before the next warp-collective instruction
+        if (do_stats) chunk_stats_to_cells(p, v, row_ok, lane, ocol, c0, e.img_lo, stats_acc);
+    }
+}
+
 // Epilogue for one accumulator row per thread: `taddr` = TMEM address of this warp's lane quarter, column 0 of the
 // tile; `tn` = N-tile index.  All tcgen05.ld / shuffles are warp-collective.
 template <int BN, int FMT>
 __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t taddr, int tn, int lane, int half,
                                               const EpiRow<BN>& e, uint32_t stats_acc) {
+    if (p.lean) {                                          // warp-uniform, fixed per launch (smtl_gemm_run)
+        epilogue_rows_lean<BN, FMT>(p, taddr, tn, lane, half, e, stats_acc);
+        return;
+    }
     const bool geglu = (p.act == SMTL_ACT_GEGLU);
     const int out_bn = geglu ? BN / 2 : BN;
     const int n0 = tn * BN;
@@ -411,30 +504,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t tad
         if (p.stats && e.img_lo <= e.img_hi) {
             // per-(image, channel) sum / sum of squares of the stored value: lane j ends up owning column ocol + j.
             // Tiles are image-aligned (tile_rpi), so every valid row of the tile belongs to image e.img_lo.
-            float s[32], q[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float x = row_ok ? v[j] : 0.0f;
-                s[j] = x;
-                q[j] = x * x;
-            }
-            const float cs = warp_transpose_sum(s, lane);
-            const float cq = warp_transpose_sum(q, lane);
-            if (ocol + lane < p.n_out) {
-                // fine cells accumulate in this warp's shared-memory slots (flushed once per (image, column tile) run);
-                // a partial too large for the fine scale (|x| >= 2^14: rare) goes straight to its coarse global cell
-                const uint32_t cell = stats_acc + (uint32_t)(((c0 >> 6) * 32 + lane) * 16);
-                unsigned long long* gcell = p.stats + (((int64_t)(blockIdx.x % p.stats_rep) * p.stats_images + e.img_lo) *
-                                                           p.n_out + ocol + lane) * 4;
-                long long as, aq;
-                lds_v2_s64(cell, as, aq);
-                bool hi;
-                long long f = stats_fix(cs, hi);
-                if (hi) atomicAdd(gcell + 1, (unsigned long long)f); else as += f;
-                f = stats_fix(cq, hi);
-                if (hi) atomicAdd(gcell + 3, (unsigned long long)f); else aq += f;
-                sts_v2_s64(cell, as, aq);
-            }
+            chunk_stats_to_cells(p, v, row_ok, lane, ocol, c0, e.img_lo, stats_acc);
         }
     }
 }
@@ -1236,6 +1306,10 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
                        "gemm_plan: stats needs rows_per_image/images/replicas (got %d/%d/%d)", g.stats_rows_per_image,
                        g.stats_images, g.stats_replicas);
         SMTL_CHECK_ARG(g.act != SMTL_ACT_GEGLU && !g.bias_per_row, "gemm_plan: stats with GEGLU / per-row bias");
+        SMTL_CHECK_ARG(g.stats_group == 0 || g.stats_group == 1 || g.stats_group == 2 || g.stats_group == 4 || g.stats_group == 8,
+                       "gemm_plan: stats_group=%d (0/1, 2, 4 or 8)", g.stats_group);
+        SMTL_CHECK_ARG(g.stats_group <= 1 || g.n % g.stats_group == 0, "gemm_plan: n=%d is not a multiple of stats_group=%d", g.n,
+                       g.stats_group);
     }
     SMTL_CHECK_ARG(g.m + 4096 < (int64_t)1 << 31, "gemm_plan: m too large for 32-bit TMA coordinates");
     // image-aligned M tiling whenever statistics are produced (see GemmKParams::tile_rpi)
@@ -1436,6 +1510,12 @@ extern "C" int smtl_gemm_run(const smtl_gemm_op* op, void* stream) {
     kp.stats_rpi = g.stats_rows_per_image;
     kp.stats_images = g.stats_images;
     kp.stats_rep = g.stats_replicas > 0 ? g.stats_replicas : 1;
+    kp.stats_g = g.stats_group > 1 ? g.stats_group : 1;
+    // bias + optional 16-bit residual + 16-bit output (+ statistics), whole 32-column chunks, 32-byte aligned rows
+    kp.lean = g.act == SMTL_ACT_NONE && g.bias && !g.bias_per_row && !g.aux_bf16 && !g.res2 && !g.out_f32 && g.out_bf16 &&
+              g.group_rows == 0 && g.n % 32 == 0 && g.ldc % 16 == 0 && (reinterpret_cast<uintptr_t>(g.out_bf16) & 31) == 0 &&
+              (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0 &&
+              (!g.res1 || (g.res_fmt16 && g.ldres % 16 == 0 && (reinterpret_cast<uintptr_t>(g.res1) & 31) == 0));
     kp.out_f32 = g.out_f32;
     kp.out_bf16 = reinterpret_cast<uint16_t*>(g.out_bf16);
     kp.aux_bf16 = reinterpret_cast<uint16_t*>(g.aux_bf16);

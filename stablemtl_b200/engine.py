@@ -107,10 +107,29 @@ class _PlanBase:
     def _new_act(self, images, hw, C):
         return Act(self.pool.alloc((images * hw, C), ops.h16()), self.arena.new(images, C))
 
+    # Statistics granularity of the plan's maps (smtl_gemm_args.stats_group): the largest power of two <= 8 such that every
+    # GroupNorm group that will read a map -- alone or inside a channel concat -- is a union of aligned blocks of that
+    # many channels.  Set by the plan builders from the channel counts and the group count.
+    stats_group = 1
+
     @staticmethod
-    def _into(act, hw):
+    def stats_group_for(channel_counts, groups):
+        """Every group of GroupNorm(groups) over any one map, or over a concat of two maps, of these channel counts starts
+        at a multiple of gcd(c_i / groups) (concat offsets c_i are multiples of it too)."""
+        import math
+        g = 8
+        for c in channel_counts:
+            if c % groups:
+                return 1
+            g = math.gcd(g, c // groups)
+        return g
+
+    def _stats_group_of(self, act):
+        return self.stats_group
+
+    def _into(self, act, hw):
         """epilogue kwargs of the GEMM that produces `act`"""
-        return dict(out_bf16=act.t, stats=act.stats, stats_rows_per_image=hw)
+        return dict(out_bf16=act.t, stats=act.stats, stats_rows_per_image=hw, stats_group=self._stats_group_of(act))
 
     def _finish(self):
         self.plan.ops[0:0] = self.arena.memset_ops()
@@ -314,6 +333,7 @@ class UNetPlan(_PlanBase):
         P = self.pool
         self.arena = StatsArena(dev)
         self.plan = ops.Plan()
+        self.stats_group = self.stats_group_for(cfg.block_out_channels, cfg.norm_num_groups)   # SD-2: gcd(10, 20, 40) -> 2
         add = self.plan.add
         G = len(group_tasks)
         Be = G * images
@@ -647,6 +667,10 @@ class _VAEBase(_PlanBase):
 
     def _new_map(self, h, w, C):
         return Act(self.pool.alloc((self._rows(h, w), C), ops.h16()), self.arena.new(self.B, C))
+
+    def _stats_group_of(self, act):
+        # no channel concats in the VAE: every map is normalised alone, by GroupNorm(norm_num_groups) over its own channels
+        return self.stats_group_for([act.shape[1]], self.W.cfg.norm_num_groups)
 
     def _resnet(self, p, x, h, w, cout):
         W, P, add, B, G = self.W, self.pool, self.plan.add, self.B, self.W.cfg.norm_num_groups

@@ -149,7 +149,8 @@ def stats_values(stats):
 
 def gemm(a0, b, *, m=None, k=None, n=None, a1=None, segs=None, bias=None, bias_per_row=False, act=L.ACT_NONE,
          res1=None, res2=None, out_f32=None, out_bf16=None, aux_bf16=None, rowmap=L.ROWMAP_IDENTITY, img_hw=None,
-         block_n=0, name="gemm", stats=None, stats_rows_per_image=0, cta_group=0, up_parity=0, group_rows=0, tile_order=0):
+         block_n=0, name="gemm", stats=None, stats_rows_per_image=0, cta_group=0, up_parity=0, group_rows=0, tile_order=0,
+         stats_group=0):
     """D = A @ B^T (+ fused epilogue).  a0/a1: bf16 [rows, cols] (row stride = stride(0)); b: bf16 [n, k].
     segs: list of (row_shift, kblocks, src, a_col0)."""
     assert a0.dtype == BF16 and b.dtype == BF16 and a0.stride(-1) == 1 and b.stride(-1) == 1
@@ -186,6 +187,7 @@ def gemm(a0, b, *, m=None, k=None, n=None, a1=None, segs=None, bias=None, bias_p
         assert stats.shape[2] == n_out and stats_rows_per_image > 0
         g.stats, g.stats_replicas, g.stats_images = stats.data_ptr(), stats.shape[0], stats.shape[1]
         g.stats_rows_per_image = stats_rows_per_image
+        g.stats_group = stats_group
     g.res1, g.res2 = _ptr(res1), _ptr(res2)
     outs = [t for t in (out_f32, out_bf16) if t is not None]
     if out_f32 is not None:

@@ -790,6 +790,41 @@ def test_channel_stats_are_bit_reproducible_and_batch_position_independent(kind)
     assert torch.equal(sp, s0[perm]) and torch.equal(op_, o0[perm])
 
 
+@pytest.mark.parametrize("g,cin,cout,h,w", [(2, 320, 320, 15, 20), (4, 128, 256, 24, 40), (8, 256, 512, 60, 80), (8, 64, 96, 9, 7)])
+def test_channel_stats_with_grouped_cells(g, cin, cout, h, w):
+    """stats_group = g: the sums of g adjacent channels land in the first channel's cell, the other cells stay zero, and
+    the block totals equal those of the per-channel run (what a GroupNorm whose groups are unions of such blocks reads)."""
+    ops, L = _ops()
+    b = 3
+    x = rnd(b, h, w, cin, seed=1).to(H16())
+    wmat = rnd(cout, 9 * cin, scale=(9 * cin) ** -0.5, seed=2).to(H16())
+    bias = rnd(cout, seed=3)
+
+    def run(group):
+        st = ops.new_stats(b, cout, DEV)
+        out = torch.empty(b * h * w, cout, device=DEV, dtype=H16())
+        ops.conv3x3(_pad_layout(x), wmat, b, h, w, bias=bias, out_bf16=out, stats=st, stats_rows_per_image=h * w,
+                    stats_group=group).run()
+        torch.cuda.synchronize()
+        v = ops.stats_values(st)                       # [images, channels, 2]
+        return (v[..., 0], v[..., 1]), out
+    (s1, q1), o1 = run(0)
+    (sg, qg), og = run(g)
+    assert torch.equal(o1, og)
+    lead = torch.arange(cout, device=DEV) % g == 0
+    assert (sg[:, ~lead] == 0).all() and (qg[:, ~lead] == 0).all()
+    ref_s = o1.double().reshape(b, h * w, cout // g, g).sum((1, 3))
+    ref_q = (o1.double() ** 2).reshape(b, h * w, cout // g, g).sum((1, 3))
+    # the statistics are those of the fp32 value BEFORE its 16-bit rounding: a block total differs from the stored map's
+    # by the accumulated roundings (~5e-4 relative per element), but agrees with the per-channel run to fp32 summation order
+    n_el = h * w * g
+    eps16 = 2.0 ** -8 if H16() == torch.bfloat16 else 2.0 ** -11
+    assert torch.allclose(sg[:, lead], ref_s, rtol=0, atol=4 * eps16 * n_el ** 0.5), (sg[:, lead] - ref_s).abs().max()
+    assert torch.allclose(qg[:, lead], ref_q, rtol=4 * eps16, atol=1e-2), (qg[:, lead] - ref_q).abs().max()
+    assert torch.allclose(s1.reshape(b, cout // g, g).sum(-1), sg[:, lead], rtol=1e-5, atol=1e-3)
+    assert torch.allclose(q1.reshape(b, cout // g, g).sum(-1), qg[:, lead], rtol=1e-5, atol=1e-3)
+
+
 @pytest.mark.parametrize("cout", [256, 128])
 def test_channel_stats_of_a_large_energetic_map_do_not_overflow(cout):
     """480x640 full-resolution map with std ~ 8 (what the VAE decoder's last level carries for some task latents): the
