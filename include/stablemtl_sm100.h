@@ -172,7 +172,8 @@ typedef struct smtl_fattn_args {
 
 typedef struct smtl_fattn_op {
     smtl_fattn_args args;
-    uint64_t tmap_qkv[16];
+    uint64_t tmap_qkv[16];  /* CUtensorMap image: [128 x 64] boxes */
+    uint64_t tmap_kv[16];   /* head_dim 512: [64 x 64] boxes (each CTA of a pair loads half of every K / V tile) */
     int32_t grid_x, grid_y;
     int32_t smem_bytes;
     int32_t pad_;

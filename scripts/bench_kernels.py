@@ -62,12 +62,11 @@ def conv_case(name, batch, h, w, cin, cout, stats=True, **kw):
            ops.conv3x3(a, wm, batch, h, w, bias=bias, out_bf16=out, **skw, **kw))
 
 
-def attn_case(batch, ntok, heads, variant=0):
+def attn_case(batch, ntok, heads):
     c = heads * 64
     qkv = rb(batch * ntok, 3 * c)
     out = torch.empty(batch * ntok, c, device=DEV, dtype=ops.h16())
-    report(f"flash_attn b={batch} ntok={ntok} heads={heads} variant={variant}",
-           ops.flash_attn(qkv, batch, ntok, heads, out, 0, c, 2 * c, variant=variant))
+    report(f"flash_attn b={batch} ntok={ntok} heads={heads}", ops.flash_attn(qkv, batch, ntok, heads, out, 0, c, 2 * c))
 
 
 def gn_case(batch, h, w, c, pad=True):
@@ -174,10 +173,17 @@ if __name__ == "__main__":
             report(f"task mlp gelu m={m} k={c} n={c}", ops.gemm(a, w2, bias=b2, act=L.ACT_GELU, out_bf16=out2))
             report(f"linear (no act) m={m} k={c} n={c}", ops.gemm(a, w2, bias=b2, out_bf16=out2))
         sys.exit(0)
+    if only == "vattn":        # VAE mid-block attention: one head of 512 channels, 4800 tokens
+        for batch in (16, 7 * 16):
+            c = 512
+            qkv = rb(batch * 4800, 3 * c)
+            out = torch.empty(batch * 4800, c, device=DEV, dtype=ops.h16())
+            report(f"vae attention d=512 b={batch} ntok=4800 (algorithmic flops)",
+                   ops.flash_attn(qkv, batch, 4800, 1, out, 0, c, 2 * c, scale=c ** -0.5, head_dim=c))
+        sys.exit(0)
     if only == "attn":
         for args in [(16, 4800, 5), (112, 4800, 5), (112, 1200, 10), (112, 300, 20), (112, 80, 20)]:
-            for variant in (1, 0, 2, 3, 4):
-                attn_case(*args, variant=variant)
+            attn_case(*args)
         sys.exit(0)
     gemm_case("square", 8192, 8192, 8192)
     gemm_case("square bn128", 8192, 8192, 8192, block_n=128)

@@ -82,7 +82,7 @@ class FattnArgs(C.Structure):
 
 
 class FattnOp(C.Structure):
-    _fields_ = [("args", FattnArgs), ("tmap_qkv", C.c_uint64 * 16), ("grid_x", i32), ("grid_y", i32),
+    _fields_ = [("args", FattnArgs), ("tmap_qkv", C.c_uint64 * 16), ("tmap_kv", C.c_uint64 * 16), ("grid_x", i32), ("grid_y", i32),
                 ("smem_bytes", i32), ("pad_", i32)]
 
 

@@ -1,7 +1,7 @@
 // smtl_attn.cu -- flash-style self-attention for the SD-2 UNet transformer blocks (head dim 64).
 // Replaces xformers.ops.memory_efficient_attention at reference src/model/attention.py:391-397,417.
 //
-// The kernel (smtl_fattn2_kernel) is described where it is defined.
+// The kernels (smtl_fattn4_kernel for the UNet, smtl_vattn_kernel for the VAE mid-block) are described where they are defined.
 #include "smtl_common.cuh"
 #include "smtl_host.h"
 
@@ -13,6 +13,7 @@ constexpr int TILE_BYTES = 128 * 64 * 2;       // 16 KB: a [128 x 64] bf16 tile
 
 struct alignas(64) FattnKParams {
     CUtensorMap tm;
+    CUtensorMap tm_half;                 // same tensor, [64 x 64] box (smtl_vattn_kernel: each CTA of a pair loads half a tile)
     int32_t q_col0, k_col0, v_col0;
     int32_t ntok, heads;
     uint16_t* out;
@@ -21,20 +22,13 @@ struct alignas(64) FattnKParams {
     int32_t fmt;
 };
 
-// ================================================================================================ the kernel
-// One CTA per SM-resident block of 256 query rows (two 128-row tiles that ping-pong on the tensor core):
-//   warp 0      : TMA producer  (Q0, Q1 once; K/V tiles through an NS-stage ring)
-//   warp 1      : MMA issuer    S_w = Q_w K^T, then O_w += P_w V with P_w read straight from TMEM (tcgen05.mma with
-//                               the A operand in tensor memory), alternating w = 0, 1
-//   warps 2..5  : softmax of tile 0; warps 6..9: softmax of tile 1 -- one query row per thread:
-//                 tcgen05.ld S -> running max (lazy: the reference max only moves when it grows by > 2^8) ->
-//                 p = ex2(s*scale - m) -> 16-bit pairs -> tcgen05.st over the S columns just consumed
-// While one tile's softmax runs on the SFU/ALU pipes the other tile's two MMAs run on the tensor pipe.
-// TMEM columns: S0/P0 [0,128)  S1/P1 [128,256)  O0 [256,320)  O1 [320,384).
-constexpr int F2_THREADS = 320;
-constexpr int F2_NS = 4;                                   // K/V ring stages (32 KB each)
-constexpr int F2_SMEM = 2 * TILE_BYTES + F2_NS * 2 * TILE_BYTES + 256;
-constexpr int F2_TMEM_COLS = 512;
+// ================================================================================================ shared pieces
+// Both attention kernels of this file run the same pipeline:
+//   warp 0      : TMA producer  (Q once; K/V tiles through a ring)
+//   warp 1      : MMA issuer    S = Q K^T, then O += P V with P read straight from TMEM (tcgen05.mma with the A operand
+//                               in tensor memory)
+//   softmax     : one query row per thread: tcgen05.ld S -> running max (lazy: the reference max only moves when it
+//                 grows by > 2^8) -> p = ex2(s*scale - m) -> 16-bit pairs -> tcgen05.st over the S columns just consumed
 constexpr float F2_LAZY = 8.0f;                            // log2 units
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -42,8 +36,9 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// (A polynomial ex2 on the FMA pipe for a quarter of the scores -- the FlashAttention-4 trick -- was measured here
-// and LOST 6 %: at head dim 64 this softmax is bound by instruction issue, not by the SFU.)
+// (A polynomial ex2 on the FMA pipe for 1/8 .. 3/8 of the scores -- the FlashAttention-4 trick, on packed FFMA2 / FADD2.RM --
+// was measured in both generations of the d = 64 kernel and lost 3-12 % each time: 10 issue slots per pair against 2
+// MUFU.EX2, and the softmax warps are short of issue slots before they are short of SFU cycles.)
 // D[tmem] (+)= A[tmem] * B[smem]
 __device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
                                               uint32_t accumulate) {
@@ -146,160 +141,6 @@ __device__ __forceinline__ void softmax_tile(const FattnKParams& p, uint32_t t_s
     tmem_st_wait();
 }
 
-__global__ void __launch_bounds__(F2_THREADS, 1) smtl_fattn2_kernel(const __grid_constant__ FattnKParams p) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* sQ = smem;                                    // 2 tiles
-    uint8_t* sK = smem + 2 * TILE_BYTES;                   // NS stages
-    uint8_t* sV = sK + F2_NS * TILE_BYTES;                 // NS stages
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + F2_NS * TILE_BYTES);
-    uint64_t* q_full = bars + 0;
-    uint64_t* kv_full = bars + 1;                // [NS]
-    uint64_t* kv_empty = bars + 1 + F2_NS;       // [NS]
-    uint64_t* s_full = bars + 1 + 2 * F2_NS;     // [2]
-    uint64_t* p_full = s_full + 2;               // [2]
-    uint64_t* o_done = p_full + 2;               // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * 2 * BQ;
-    const int b = blockIdx.y / p.heads;
-    const int hd = blockIdx.y - b * p.heads;
-    const int row_base = b * p.ntok;
-    const int ntiles = (p.ntok + BKV - 1) / BKV;
-    const bool has1 = (q0 + BQ) < p.ntok;
-
-    if (threadIdx.x == 0) {
-        if ((smem_u32(smem) & 1023u) != 0) { printf("smtl_fattn2: smem base not 1024-aligned\n"); __trap(); }
-        tma_prefetch_desc(&p.tm);
-        mbar_init(q_full, 1);
-        for (int s = 0; s < F2_NS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-        for (int w = 0; w < 2; ++w) { mbar_init(&s_full[w], 1); mbar_init(&p_full[w], 4); mbar_init(&o_done[w], 1); }
-        fence_mbar_init();
-    }
-    if (warp == 1) {
-        tmem_alloc(tmem_slot, F2_TMEM_COLS);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (elect_one()) {
-            mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
-            tma_load_2d(sQ, &p.tm, q_full, p.q_col0 + hd * HD, row_base + q0);
-            tma_load_2d(sQ + TILE_BYTES, &p.tm, q_full, p.q_col0 + hd * HD, row_base + q0 + BQ);
-        }
-        __syncwarp();
-        for (int j = 0; j < ntiles; ++j) {
-            const int s = j % F2_NS;
-            mbar_wait(&kv_empty[s], ((j / F2_NS) & 1) ^ 1u);
-            if (elect_one()) {
-                mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
-                tma_load_2d(sK + s * TILE_BYTES, &p.tm, &kv_full[s], p.k_col0 + hd * HD, row_base + j * BKV);
-                tma_load_2d(sV + s * TILE_BYTES, &p.tm, &kv_full[s], p.v_col0 + hd * HD, row_base + j * BKV);
-            }
-            __syncwarp();
-        }
-    } else if (warp == 1) {
-        const uint32_t IDESC_S = make_idesc_16(BQ, BKV, 0, 0, p.fmt);   // S[128,128] = Q[128,64] K[128,64]^T
-        const uint32_t IDESC_O = make_idesc_16(BQ, HD, 0, 1, p.fmt);    // O[128,64] += P[128,128] V[128,64] (V MN-major)
-        const int ntile_q = has1 ? 2 : 1;
-        auto issue_s = [&](int w, int stage) {
-            const uint64_t dq = make_smem_desc_sw128(smem_u32(sQ + w * TILE_BYTES));
-            const uint64_t dk = make_smem_desc_sw128(smem_u32(sK + stage * TILE_BYTES));
-#pragma unroll
-            for (int k = 0; k < HD / 16; ++k) tc_mma_f16(tmem_base + w * 128, dq + 2 * k, dk + 2 * k, IDESC_S, k != 0);
-            tc_commit(&s_full[w]);
-        };
-        // converged warp; elect.sync picks the issuing lane at the instructions (a lane-id branch makes ptxas wrap
-        // every UTCHMMA in a ~165-clk uniform-register waterfall loop, see smtl_gemm.cu)
-        mbar_wait(q_full, 0);
-        mbar_wait(&kv_full[0], 0);
-        tc_fence_after();
-        if (elect_one())
-            for (int w = 0; w < ntile_q; ++w) issue_s(w, 0);
-        __syncwarp();
-        for (int j = 0; j < ntiles; ++j) {
-            const int s = j % F2_NS;
-            const int sn = (j + 1) % F2_NS;
-            for (int w = 0; w < ntile_q; ++w) {
-                mbar_wait(&p_full[w], j & 1);                 // softmax wrote P_w(j) and rescaled O_w
-                if (w == 0 && j + 1 < ntiles) mbar_wait(&kv_full[sn], ((j + 1) / F2_NS) & 1);
-                tc_fence_after();
-                const uint32_t sv = smem_u32(sV + s * TILE_BYTES);
-                if (elect_one()) {
-#pragma unroll
-                    for (int k = 0; k < BKV / 16; ++k) {
-                        // V rows (kv) 16k .. 16k+16: 16 rows * 128 B = 2048 B per K step; P: 8 TMEM columns per step
-                        const uint64_t dv = make_smem_desc_sw128(sv + k * 16 * 128);
-                        tc_mma_f16_ts(tmem_base + 256 + w * 64, tmem_base + w * 128 + 8 * k, dv, IDESC_O, (j | k) != 0);
-                    }
-                    if (j + 1 < ntiles) issue_s(w, sn);       // in-order after PV_w(j): may overwrite P_w(j)
-                    else tc_commit(&o_done[w]);
-                }
-                __syncwarp();
-            }
-            if (elect_one()) tc_commit(&kv_empty[s]);          // K(j), V(j) consumed by every MMA issued so far
-            __syncwarp();
-        }
-    } else {
-        const int w = (warp - 2) >> 2;                         // which query tile
-        if (w == 0 || has1) {
-            const int quarter = warp & 3;                      // TMEM lane quarter this warp may access
-            const int r = quarter * 32 + lane;                 // query row within the tile == TMEM lane
-            const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-            const uint32_t t_s = tmem_base + w * 128 + lane_off;
-            const uint32_t t_o = tmem_base + 256 + w * 64 + lane_off;
-            float m_run = -INFINITY, l_run = 0.f;
-            const int tail = p.ntok - (ntiles - 1) * BKV;      // valid kv columns of the last tile
-            for (int j = 0; j < ntiles; ++j) {
-                mbar_wait(&s_full[w], j & 1);                  // S_w(j) ready; implies PV_w(j-1) retired
-                tc_fence_after();
-                if (j == ntiles - 1 && tail < BKV) softmax_tile<true>(p, t_s, tail, m_run, l_run, t_o, j > 0);
-                else softmax_tile<false>(p, t_s, BKV, m_run, l_run, t_o, j > 0);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&p_full[w]);
-            }
-            mbar_wait(&o_done[w], 0);
-            tc_fence_after();
-            const float inv = 1.0f / l_run;
-            const int qrow = q0 + w * BQ + r;
-            const bool row_ok = qrow < p.ntok;
-            uint16_t* dst = p.out + (int64_t)(row_base + qrow) * p.ldo + hd * HD;
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-                uint32_t rr[32];
-                tmem_ld_32x32(t_o + c * 32, rr);
-                tmem_ld_wait();
-                if (row_ok) {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 8) {
-                        uint4 o;
-                        o.x = pack16x2(__uint_as_float(rr[i]) * inv, __uint_as_float(rr[i + 1]) * inv, p.fmt);
-                        o.y = pack16x2(__uint_as_float(rr[i + 2]) * inv, __uint_as_float(rr[i + 3]) * inv, p.fmt);
-                        o.z = pack16x2(__uint_as_float(rr[i + 4]) * inv, __uint_as_float(rr[i + 5]) * inv, p.fmt);
-                        o.w = pack16x2(__uint_as_float(rr[i + 6]) * inv, __uint_as_float(rr[i + 7]) * inv, p.fmt);
-                        *reinterpret_cast<uint4*>(dst + c * 32 + i) = o;
-                    }
-                }
-                __syncwarp();
-            }
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, F2_TMEM_COLS);
-    }
-}
-
-
 // ================================================================================================ d = 64, four query tiles
 // smtl_fattn4_kernel: the same pipeline with FOUR 128-row query tiles per CTA and 64-key steps (TMEM: S/P 4 x 64 columns,
 // O 4 x 64).  Why: in the two-tile kernel an SM sub-partition hosts two softmax warps that run IN PHASE -- both in their
@@ -317,7 +158,7 @@ constexpr int F4_REGS = 96;
 constexpr int F4_NS = 4;                                   // K/V ring stages (one 128-key box of K and of V: 32 KB)
 constexpr int F4_SMEM = F4_NQ * TILE_BYTES + F4_NS * 2 * TILE_BYTES + 256;
 
-template <bool MASKED, int FMT, int POLY>
+template <bool MASKED, int FMT>
 __device__ __forceinline__ void softmax_step64(const FattnKParams& p, uint32_t t_s, int kv_valid, float& m_run,
                                                float& l_run, uint32_t t_o, bool have_o) {
     uint32_t rr[64];
@@ -362,8 +203,7 @@ __device__ __forceinline__ void softmax_step64(const FattnKParams& p, uint32_t t
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
             const float2 t = ffma2(make_float2(__uint_as_float(rr[c * 32 + i]), __uint_as_float(rr[c * 32 + i + 1])), sc2, nm2);
-            // POLY of every 8 pairs take their exponential on the FMA pipe instead of the SFU
-            float2 e = (((i >> 1) & 7) < POLY) ? ex2_poly2(t) : make_float2(ex2_approx(t.x), ex2_approx(t.y));
+            float2 e = make_float2(ex2_approx(t.x), ex2_approx(t.y));
             if (MASKED) {
                 e.x = (c * 32 + i < kv_valid) ? e.x : 0.f;
                 e.y = (c * 32 + i + 1 < kv_valid) ? e.y : 0.f;
@@ -377,7 +217,7 @@ __device__ __forceinline__ void softmax_step64(const FattnKParams& p, uint32_t t
     tmem_st_wait();
 }
 
-template <int FMT, int POLY>
+template <int FMT>
 __global__ void __maxnreg__(F4_REGS) smtl_fattn4_kernel(const __grid_constant__ FattnKParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sQ = smem;                                    // 4 tiles
@@ -492,8 +332,8 @@ __global__ void __maxnreg__(F4_REGS) smtl_fattn4_kernel(const __grid_constant__ 
             for (int j = 0; j < nsub; ++j) {
                 mbar_wait(&s_full[w], j & 1);                  // S_w(j) ready; implies PV_w(j-1) retired
                 tc_fence_after();
-                if (j == nsub - 1 && tail < F4_KS) softmax_step64<true, FMT, POLY>(p, t_s, tail, m_run, l_run, t_o, j > 0);
-                else softmax_step64<false, FMT, POLY>(p, t_s, F4_KS, m_run, l_run, t_o, j > 0);
+                if (j == nsub - 1 && tail < F4_KS) softmax_step64<true, FMT>(p, t_s, tail, m_run, l_run, t_o, j > 0);
+                else softmax_step64<false, FMT>(p, t_s, F4_KS, m_run, l_run, t_o, j > 0);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p_full[w]);
@@ -544,11 +384,17 @@ __global__ void __maxnreg__(F4_REGS) smtl_fattn4_kernel(const __grid_constant__ 
 //   warp 1      : MMA issuer   -- S(j) = sum over the 8 slices of Q_s K_s^T into one of TWO S buffers in TMEM, so the
 //                                 tensor pipe works on S(j+1) while the softmax warps work on S(j);
 //                                 O += P(j) V(j) with P read from TMEM (it overwrites the S columns it came from)
-//   warps 2..5  : softmax      -- one query row per thread, as in smtl_fattn2_kernel (lazy running max, ex2.approx)
+//   warps 2..5  : softmax      -- one query row per thread (lazy running max, ex2.approx)
 // TMEM holds 512 fp32 columns: two S buffers (256) leave room for HALF of O (256 of its 512 columns), so the kernel
 // makes two passes over the keys, one per half of the value channels, recomputing S and the softmax (1.5x the
 // algorithmic flops; the pass is tensor-bound at 3072 clk per KV tile against ~1500 clk of softmax).
 // TMEM columns: S0/P0 [0,128)  S1/P1 [128,256)  O half [256,512).
+//
+// A CTA consumes 192 KB of K / V per 3072 tensor cycles -- 62 B/clk per SM, 16 TB/s over 148 SMs at full clock, about
+// twice what L2 delivers: the MMA warp spent 42 % of its time waiting for a full ring stage (ncu: tensor pipe 48.6 %
+// active).  So two CTAs on neighbouring query tiles of the same image form a CLUSTER: each loads HALF of every K / V
+// tile (64 of its 128 rows) and the TMA multicasts it into both CTAs' rings -- one L2 read per pair.  A stage is free
+// again when BOTH CTAs' MMAs have retired it: tcgen05.commit multicasts its arrive to both CTAs' empty barriers.
 constexpr int V5_THREADS = 192;
 constexpr int V5_SLICES = 8;                               // 512 / 64
 constexpr int V5_NS = 6;                                   // ring stages (16 KB each)
@@ -571,15 +417,17 @@ __global__ void __launch_bounds__(V5_THREADS, 1) smtl_vattn_kernel(const __grid_
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * BQ;
+    const int q0 = blockIdx.x * BQ;                        // may lie past the image (odd tile count): nothing is stored then
     const int row_base = blockIdx.y * p.ntok;
     const int ntiles = (p.ntok + BKV - 1) / BKV;
+    const uint32_t rank = cluster_ctarank();               // 0 / 1 within the pair (cluster dims 2 x 1 x 1)
 
     if (threadIdx.x == 0) {
         if ((smem_u32(smem) & 1023u) != 0) { printf("smtl_vattn: smem base not 1024-aligned\n"); __trap(); }
         tma_prefetch_desc(&p.tm);
+        tma_prefetch_desc(&p.tm_half);
         mbar_init(q_full, 1);
-        for (int s = 0; s < V5_NS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        for (int s = 0; s < V5_NS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }   // empty: both CTAs' MMAs
         for (int w = 0; w < 2; ++w) { mbar_init(&s_full[w], 1); mbar_init(&p_full[w], 4); }
         mbar_init(o_done, 1);
         mbar_init(o_free, 4);
@@ -591,7 +439,7 @@ __global__ void __launch_bounds__(V5_THREADS, 1) smtl_vattn_kernel(const __grid_
         tmem_relinquish();
     }
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();                                    // both CTAs' barriers are initialised before either signals the other
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -605,10 +453,11 @@ __global__ void __launch_bounds__(V5_THREADS, 1) smtl_vattn_kernel(const __grid_
         int st = 0;
         uint32_t ph = 0;
         auto load = [&](int col, int row) {
-            mbar_wait(&kv_empty[st], ph ^ 1u);
+            mbar_wait(&kv_empty[st], ph ^ 1u);             // both CTAs have retired this stage
             if (elect_one()) {
-                mbar_arrive_expect_tx(&kv_full[st], TILE_BYTES);
-                tma_load_2d(sR + st * TILE_BYTES, &p.tm, &kv_full[st], col, row);
+                mbar_arrive_expect_tx(&kv_full[st], TILE_BYTES);               // my half + the peer's half land here
+                tma_load_2d_mcast(sR + st * TILE_BYTES + rank * (TILE_BYTES / 2), &p.tm_half, &kv_full[st], col,
+                                  row + (int)rank * (BKV / 2), (uint16_t)3);
             }
             __syncwarp();
             if (++st == V5_NS) { st = 0; ph ^= 1u; }
@@ -639,7 +488,7 @@ __global__ void __launch_bounds__(V5_THREADS, 1) smtl_vattn_kernel(const __grid_
                     const uint64_t dk = make_smem_desc_sw128(smem_u32(sR + st * TILE_BYTES));
 #pragma unroll
                     for (int k = 0; k < 4; ++k) tc_mma_f16(tmem_base + sb * 128, dq + 2 * k, dk + 2 * k, IDESC_S, (uint32_t)(s | k));
-                    tc_commit(&kv_empty[st]);
+                    tc_commit_mcast(&kv_empty[st], (uint16_t)3);
                     if (s == V5_SLICES - 1) tc_commit(&s_full[sb]);
                 }
                 __syncwarp();
@@ -657,7 +506,7 @@ __global__ void __launch_bounds__(V5_THREADS, 1) smtl_vattn_kernel(const __grid_
                         const uint64_t dv = make_smem_desc_sw128(sv + k * 16 * 128);       // kv rows 16k .. 16k + 16
                         tc_mma_f16_ts(tmem_base + 256 + s * 64, tmem_base + sb * 128 + 8 * k, dv, IDESC_O, (uint32_t)(j | k));
                     }
-                    tc_commit(&kv_empty[st]);
+                    tc_commit_mcast(&kv_empty[st], (uint16_t)3);
                     if (s == 3) tc_commit(pv_done);
                 }
                 __syncwarp();
@@ -734,7 +583,7 @@ __global__ void __launch_bounds__(V5_THREADS, 1) smtl_vattn_kernel(const __grid_
     }
 
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();                                    // the peer may still be signalling this CTA's barriers
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
@@ -753,9 +602,12 @@ extern "C" int smtl_fattn_plan(const smtl_fattn_args* a, smtl_fattn_op* op) {
     memset(op, 0, sizeof(*op));
     op->args = *a;
     if (a->head_dim == 512) {                       // the VAE mid-block attention: smtl_vattn_kernel
-        op->grid_x = (a->ntok + BQ - 1) / BQ;
+        op->grid_x = ((a->ntok + BQ - 1) / BQ + 1) / 2 * 2;       // CTA pairs (clusters of 2 along x)
         op->grid_y = a->batch;
         op->smem_bytes = V5_SMEM;
+        const int rc = smtl_host::encode_tmap_bf16_2d(op->tmap_kv, a->qkv, (uint64_t)a->batch * a->ntok, (uint64_t)a->ld,
+                                                      (uint64_t)a->ld, 64);
+        if (rc != SMTL_OK) return rc;
     } else {
         op->grid_x = (a->ntok + F4_NQ * BQ - 1) / (F4_NQ * BQ);
         op->grid_y = a->batch * a->heads;
@@ -768,13 +620,10 @@ extern "C" int smtl_fattn_plan(const smtl_fattn_args* a, smtl_fattn_op* op) {
 
 extern "C" int smtl_fattn_run(const smtl_fattn_op* op, void* stream) {
     SMTL_CHECK_ARG(op, "fattn_run: NULL op");
-    static std::atomic<uint64_t> attr_devs{0};
-    if (smtl_host::first_use_on_device(attr_devs))
-        SMTL_CHECK_CUDA(
-            cudaFuncSetAttribute(smtl_fattn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM));
     const smtl_fattn_args& a = op->args;
     FattnKParams kp;
     memcpy(&kp.tm, op->tmap_qkv, 128);
+    memcpy(&kp.tm_half, op->tmap_qkv, 128);
     kp.q_col0 = a.q_col0;
     kp.k_col0 = a.k_col0;
     kp.v_col0 = a.v_col0;
@@ -788,26 +637,29 @@ extern "C" int smtl_fattn_run(const smtl_fattn_op* op, void* stream) {
         static std::atomic<uint64_t> attr5{0};
         if (smtl_host::first_use_on_device(attr5))
             SMTL_CHECK_CUDA(cudaFuncSetAttribute(smtl_vattn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, V5_SMEM));
-        smtl_vattn_kernel<<<dim3(op->grid_x, op->grid_y), V5_THREADS, op->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(kp);
+        memcpy(&kp.tm_half, op->tmap_kv, 128);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(op->grid_x, op->grid_y, 1);
+        cfg.blockDim = dim3(V5_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = op->smem_bytes;
+        cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        SMTL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, smtl_vattn_kernel, kp));
         SMTL_CHECK_CUDA(cudaGetLastError());
         return SMTL_OK;
     }
-    if (op->pad_ == 1) {                            // EXPERIMENT: the two-tile kernel, for the same-run A/B
-        smtl_fattn2_kernel<<<dim3((a.ntok + 2 * BQ - 1) / (2 * BQ), op->grid_y), F2_THREADS, F2_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(kp);
-        SMTL_CHECK_CUDA(cudaGetLastError());
-        return SMTL_OK;
-    }
-    using Kern = void (*)(const FattnKParams);
-    static const Kern kerns[2][4] = {
-        {smtl_fattn4_kernel<FMT_BF16, 0>, smtl_fattn4_kernel<FMT_BF16, 1>, smtl_fattn4_kernel<FMT_BF16, 2>, smtl_fattn4_kernel<FMT_BF16, 3>},
-        {smtl_fattn4_kernel<FMT_F16, 0>, smtl_fattn4_kernel<FMT_F16, 1>, smtl_fattn4_kernel<FMT_F16, 2>, smtl_fattn4_kernel<FMT_F16, 3>}};
     static std::atomic<uint64_t> attr4{0};
-    if (smtl_host::first_use_on_device(attr4))
-        for (int f = 0; f < 2; ++f)
-            for (int q = 0; q < 4; ++q)
-                SMTL_CHECK_CUDA(cudaFuncSetAttribute(kerns[f][q], cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM));
-    const int poly = (op->pad_ >= 2 && op->pad_ <= 4) ? op->pad_ - 1 : 0;        // EXPERIMENT knob
-    Kern kern = kerns[a.fmt16 == SMTL_FMT_F16 ? 1 : 0][poly];
+    if (smtl_host::first_use_on_device(attr4)) {
+        SMTL_CHECK_CUDA(cudaFuncSetAttribute(smtl_fattn4_kernel<FMT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM));
+        SMTL_CHECK_CUDA(cudaFuncSetAttribute(smtl_fattn4_kernel<FMT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM));
+    }
+    auto kern = a.fmt16 == SMTL_FMT_F16 ? smtl_fattn4_kernel<FMT_F16> : smtl_fattn4_kernel<FMT_BF16>;
     kern<<<dim3(op->grid_x, op->grid_y), F4_THREADS, op->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(kp);
     SMTL_CHECK_CUDA(cudaGetLastError());
     return SMTL_OK;

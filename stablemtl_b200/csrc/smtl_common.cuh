@@ -159,6 +159,23 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// TMA load MULTICAST to the CTAs of `cta_mask`: the box lands at the same shared-memory offset in each of them and
+// complete_tx is signalled on the mbarrier at the same offset in each of them (one L2 read feeds the whole cluster).
+__device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int32_t c0, int32_t c1,
+                                                  uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
+}
+// commit all prior tcgen05.mma of this thread (cta_group::1); arrive(1) on the mbarrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void tc_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
 // TMA load issued by one CTA of a pair whose completion is signalled on an mbarrier that may live in the PEER CTA
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tmap, uint32_t bar_cluster_addr,
                                                  int32_t c0, int32_t c1) {
@@ -307,32 +324,6 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
         "mov.b64 {%0, %1}, rd;\n\t}"
         : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
     return d;
-}
-// round-toward-minus-infinity add (FADD2.RM): x + 1.5 * 2^23 leaves floor(x) in the low mantissa bits
-__device__ __forceinline__ float2 fadd2_rm(float2 a, float2 b) {
-    float2 d;
-    asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
-        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
-        "add.rm.f32x2 rd, ra, rb;\n\t"
-        "mov.b64 {%0, %1}, rd;\n\t}"
-        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-    return d;
-}
-// 2^x for a pair on the FMA pipe (no SFU): floor by the magic-number add, a cubic for 2^frac on [0, 1) (max relative
-// error 9e-5, below the 16-bit rounding of the probabilities it produces), the integer part added into the exponent
-// field.  x is clamped at -126 (result 2^-126 ~ 0).  10 issue slots per pair against 2 MUFU.EX2 = 16 SFU cycles.
-__device__ __forceinline__ float2 ex2_poly2(float2 x) {
-    x.x = fmaxf(x.x, -126.0f);
-    x.y = fmaxf(x.y, -126.0f);
-    const float2 magic = make_float2(12582912.0f, 12582912.0f);
-    const float2 r = fadd2_rm(x, magic);
-    const float2 back = fadd2(r, make_float2(-12582912.0f, -12582912.0f));
-    const float2 f = fadd2(x, make_float2(-back.x, -back.y));
-    float2 pl = ffma2(f, make_float2(0.077119089663028717f, 0.077119089663028717f), make_float2(0.227564394474029541f, 0.227564394474029541f));
-    pl = ffma2(pl, f, make_float2(0.695146143436431885f, 0.695146143436431885f));
-    pl = ffma2(pl, f, make_float2(1.0f, 1.0f));
-    return make_float2(__uint_as_float(__float_as_uint(pl.x) + (__float_as_uint(r.x) << 23)),
-                       __uint_as_float(__float_as_uint(pl.y) + (__float_as_uint(r.y) << 23)));
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 // erf-GELU with erf from Abramowitz & Stegun 7.1.26 (|abs error| < 1.5e-7, far below the 16-bit rounding of the

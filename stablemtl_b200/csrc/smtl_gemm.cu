@@ -199,6 +199,7 @@ struct EpiRow {
     int img;               // image of the output row (statistics), -1 if !row_ok
     int img_lo, img_hi;    // warp-wide range of img over valid rows (img_lo > img_hi: no valid row)
     float row_bias;
+    int64_t bias_ofs;      // grouped GEMM: first bias element of this row's weight group (0 otherwise)
     float bias[BN / 32];   // lane-distributed: bias[k] = bias_vec[n0 + 32 k + lane]
 };
 
@@ -211,6 +212,7 @@ __device__ __forceinline__ void epilogue_prepare(const GemmKParams& p, int64_t g
     map_row(p, grow, row_end, e.row_ok, e.orow, e.halo, map_img);
     e.halo = e.halo && (p.rowmap == SMTL_ROWMAP_PAD_KEEP);
     e.row_bias = (p.bias && p.bias_per_row && grow < p.m) ? __ldg(p.bias + grow) : 0.0f;
+    e.bias_ofs = p.group_rows ? (grow / p.group_rows) * p.n : 0;
 #pragma unroll
     for (int k = 0; k < BN / 32; ++k) {
         const int c = n0 + 32 * k + lane;
@@ -334,27 +336,31 @@ __device__ __forceinline__ void chunk_stats_to_cells(const GemmKParams& p, const
 // token linears.  The general epilogue below serves that case with ~830 instructions per 32 x 32 chunk (ncu: 47 branches
 // on per-launch flags, 32 shuffles to broadcast the bias, scalar fallbacks in every store) and two warps per SM
 // sub-partition to issue them: a K = 1024 conv spent 10 us in the epilogue of a tile whose MMAs take 6.4.
-template <int BN, int FMT>
+template <int BN, int FMT, int ACT>
 __device__ __forceinline__ void epilogue_rows_lean(const GemmKParams& p, uint32_t taddr, int tn, int lane, int half,
                                                    const EpiRow<BN>& e, uint32_t stats_acc) {
+    constexpr bool GEGLU = ACT == SMTL_ACT_GEGLU;
+    constexpr int OUT_BN = GEGLU ? BN / 2 : BN;            // GEGLU: [value 128 | gate 128] per tile -> 128 output columns
     const int n0 = tn * BN;
     const bool row_ok = e.row_ok;
     uint16_t* const out_row = p.out_bf16 + e.orow * (int64_t)p.ldc;
     const uint16_t* const res_row = reinterpret_cast<const uint16_t*>(p.res1) + e.orow * (int64_t)p.ldres;
-    const bool do_stats = p.stats && e.img_lo <= e.img_hi;
+    const float* const bias = p.bias + e.bias_ofs;
+    const bool do_stats = ACT == SMTL_ACT_NONE && p.stats && e.img_lo <= e.img_hi;
 #pragma unroll 1
-    for (int c0 = half * 32; c0 < BN; c0 += 64) {
-        const int ocol = n0 + c0;
-        if (ocol >= p.n) break;                            // warp-uniform
+    for (int c0 = half * 32; c0 < OUT_BN; c0 += 64) {
+        const int ncol_in = n0 + c0;                       // B-row index of the chunk's first column
+        if (ncol_in >= p.n) break;                         // warp-uniform
+        const int ocol = GEGLU ? tn * OUT_BN + c0 : ncol_in;
         uint32_t r[32];
         float v[32];
         tmem_ld_32x32(taddr + c0, r);
         // the chunk's 32 bias values: every lane reads the SAME 16-byte pieces (one broadcast transaction each, L1-resident)
         float4 b4[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(p.bias + ocol) + i);
+        for (int i = 0; i < 8; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(bias + ncol_in) + i);
         uint32_t rs[16];
-        if (p.res1 && row_ok) {
+        if (ACT == SMTL_ACT_NONE && p.res1 && row_ok) {
             ldg_nc_v8(res_row + ocol, rs);
             ldg_nc_v8(res_row + ocol + 16, rs + 8);
         }
@@ -366,7 +372,26 @@ __device__ __forceinline__ void epilogue_rows_lean(const GemmKParams& p, uint32_
             v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b4[i].z;
             v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b4[i].w;
         }
-        if (p.res1 && row_ok) {
+        if (GEGLU) {                                       // v = value * gelu(gate)
+            tmem_ld_32x32(taddr + OUT_BN + c0, r);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(bias + ncol_in + OUT_BN) + i);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float2 g0 = gelu_poly2(make_float2(__uint_as_float(r[4 * i]) + b4[i].x, __uint_as_float(r[4 * i + 1]) + b4[i].y));
+                const float2 g1 = gelu_poly2(make_float2(__uint_as_float(r[4 * i + 2]) + b4[i].z, __uint_as_float(r[4 * i + 3]) + b4[i].w));
+                v[4 * i] *= g0.x; v[4 * i + 1] *= g0.y; v[4 * i + 2] *= g1.x; v[4 * i + 3] *= g1.y;
+            }
+        } else if (ACT == SMTL_ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                const float2 g = gelu_poly2(make_float2(v[j], v[j + 1]));
+                v[j] = g.x;
+                v[j + 1] = g.y;
+            }
+        }
+        if (ACT == SMTL_ACT_NONE && p.res1 && row_ok) {
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
                 const float2 f = unpack16x2(rs[q], FMT);
@@ -396,7 +421,9 @@ template <int BN, int FMT>
 __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t taddr, int tn, int lane, int half,
                                               const EpiRow<BN>& e, uint32_t stats_acc) {
     if (p.lean) {                                          // warp-uniform, fixed per launch (smtl_gemm_run)
-        epilogue_rows_lean<BN, FMT>(p, taddr, tn, lane, half, e, stats_acc);
+        if (p.act == SMTL_ACT_GEGLU) epilogue_rows_lean<BN, FMT, SMTL_ACT_GEGLU>(p, taddr, tn, lane, half, e, stats_acc);
+        else if (p.act == SMTL_ACT_GELU) epilogue_rows_lean<BN, FMT, SMTL_ACT_GELU>(p, taddr, tn, lane, half, e, stats_acc);
+        else epilogue_rows_lean<BN, FMT, SMTL_ACT_NONE>(p, taddr, tn, lane, half, e, stats_acc);
         return;
     }
     const bool geglu = (p.act == SMTL_ACT_GEGLU);
@@ -1511,11 +1538,15 @@ extern "C" int smtl_gemm_run(const smtl_gemm_op* op, void* stream) {
     kp.stats_images = g.stats_images;
     kp.stats_rep = g.stats_replicas > 0 ? g.stats_replicas : 1;
     kp.stats_g = g.stats_group > 1 ? g.stats_group : 1;
-    // bias + optional 16-bit residual + 16-bit output (+ statistics), whole 32-column chunks, 32-byte aligned rows
-    kp.lean = g.act == SMTL_ACT_NONE && g.bias && !g.bias_per_row && !g.aux_bf16 && !g.res2 && !g.out_f32 && g.out_bf16 &&
-              g.group_rows == 0 && g.n % 32 == 0 && g.ldc % 16 == 0 && (reinterpret_cast<uintptr_t>(g.out_bf16) & 31) == 0 &&
-              (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0 &&
-              (!g.res1 || (g.res_fmt16 && g.ldres % 16 == 0 && (reinterpret_cast<uintptr_t>(g.res1) & 31) == 0));
+    // column bias + {nothing | GELU | GEGLU} + 16-bit output, whole 32-column chunks, 32-byte aligned rows; without an
+    // activation also a 16-bit residual and the statistics
+    const bool plain = g.act == SMTL_ACT_NONE;
+    const int n_out = g.act == SMTL_ACT_GEGLU ? g.n / 2 : g.n;
+    kp.lean = (plain || g.act == SMTL_ACT_GELU || g.act == SMTL_ACT_GEGLU) && g.bias && !g.bias_per_row && !g.aux_bf16 &&
+              !g.res2 && !g.out_f32 && g.out_bf16 && n_out % 32 == 0 && g.n % 32 == 0 && g.ldc % 16 == 0 &&
+              (reinterpret_cast<uintptr_t>(g.out_bf16) & 31) == 0 && (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0 &&
+              (plain ? (!g.res1 || (g.res_fmt16 && g.ldres % 16 == 0 && (reinterpret_cast<uintptr_t>(g.res1) & 31) == 0))
+                     : (!g.res1 && !g.stats));
     kp.out_f32 = g.out_f32;
     kp.out_bf16 = reinterpret_cast<uint16_t*>(g.out_bf16);
     kp.aux_bf16 = reinterpret_cast<uint16_t*>(g.aux_bf16);

@@ -284,7 +284,7 @@ def conv_up2x(a_pad, wmats, batch, h, w, *, name="up2x_conv", pad_out=False, **e
 
 
 # ------------------------------------------------------------------------------------------------- attention
-def flash_attn(qkv, batch, ntok, heads, out, q_col0, k_col0, v_col0, scale=0.125, head_dim=64, variant=0):
+def flash_attn(qkv, batch, ntok, heads, out, q_col0, k_col0, v_col0, scale=0.125, head_dim=64):
     """head_dim 64 (UNet self-attention) or 512 with one head (VAE mid-block attention)"""
     a = L.FattnArgs()
     a.head_dim = head_dim
@@ -296,7 +296,6 @@ def flash_attn(qkv, batch, ntok, heads, out, q_col0, k_col0, v_col0, scale=0.125
     assert qkv.dtype == BF16 and out.dtype == BF16 and qkv.shape[0] == batch * ntok
     op = L.FattnOp()
     L.check(L.lib.smtl_fattn_plan(C.byref(a), C.byref(op)), "smtl_fattn_plan")
-    op.pad_ = variant
     o = Op(L.OP_FATTN, op, (qkv, out), 4 * batch * heads * ntok * ntok * head_dim, "flash_attn", outs16=(out,))
     if head_dim == 512:
         o.flops_exec = o.flops * 3 // 2          # two passes over the keys: QK^T runs twice

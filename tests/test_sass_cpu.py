@@ -36,8 +36,8 @@ def _count(lines, mnemonic):
 
 def test_tensor_kernels_are_tcgen05_and_tma(sass):
     gemm = {k: v for k, v in sass.items() if "smtl_gemm_kernel" in k or "smtl_gemmT_kernel" in k}
-    attn = {k: v for k, v in sass.items() if "smtl_fattn2_kernel" in k}
-    assert len(gemm) >= 15 and len(attn) == 1
+    attn = {k: v for k, v in sass.items() if "smtl_fattn4_kernel" in k or "smtl_vattn_kernel" in k}
+    assert len(gemm) >= 15 and len(attn) >= 3                 # two formats of the d = 64 kernel + the d = 512 one
     for name, lines in list(gemm.items()) + list(attn.items()):
         assert _count(lines, "UTCHMMA") >= 4, name            # tcgen05.mma
         assert _count(lines, "UTMALDG") >= 2, name            # cp.async.bulk.tensor
@@ -50,5 +50,5 @@ def test_tensor_kernels_are_tcgen05_and_tma(sass):
 
 def test_no_uniform_register_waterfall_on_the_issue_path(sass):
     for name, lines in sass.items():
-        if "smtl_gemm_kernel" in name or "smtl_gemmT_kernel" in name or "smtl_fattn2_kernel" in name:
+        if "smtl_gemm_kernel" in name or "smtl_gemmT_kernel" in name or "smtl_fattn4_kernel" in name or "smtl_vattn_kernel" in name:
             assert _count(lines, "BRA.U.ANY") == 0, f"{name}: waterfall loop around a uniform-datapath instruction"
