@@ -343,9 +343,7 @@ __device__ __forceinline__ void epilogue_rows_lean(const GemmKParams& p, uint32_
     constexpr int OUT_BN = GEGLU ? BN / 2 : BN;            // GEGLU: [value 128 | gate 128] per tile -> 128 output columns
     const int n0 = tn * BN;
     const bool row_ok = e.row_ok;
-    uint16_t* const out_row = p.out_bf16 + e.orow * (int64_t)p.ldc;
-    const uint16_t* const res_row = reinterpret_cast<const uint16_t*>(p.res1) + e.orow * (int64_t)p.ldres;
-    const float* const bias = p.bias + e.bias_ofs;
+    const float* const bias = p.bias ? p.bias + e.bias_ofs : nullptr;
     const bool do_stats = ACT == SMTL_ACT_NONE && p.stats && e.img_lo <= e.img_hi;
 #pragma unroll 1
     for (int c0 = half * 32; c0 < OUT_BN; c0 += 64) {
@@ -357,12 +355,19 @@ __device__ __forceinline__ void epilogue_rows_lean(const GemmKParams& p, uint32_
         tmem_ld_32x32(taddr + c0, r);
         // the chunk's 32 bias values: every lane reads the SAME 16-byte pieces (one broadcast transaction each, L1-resident)
         float4 b4[8];
+        if (bias) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(bias + ncol_in) + i);
-        uint32_t rs[16];
-        if (ACT == SMTL_ACT_NONE && p.res1 && row_ok) {
-            ldg_nc_v8(res_row + ocol, rs);
-            ldg_nc_v8(res_row + ocol + 16, rs + 8);
+            for (int i = 0; i < 8; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(bias + ncol_in) + i);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) b4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        uint32_t rs[16];                                   // 16-bit residual, issued before the TMEM wait
+        const bool res16 = ACT == SMTL_ACT_NONE && p.res1 && p.res16 && row_ok;
+        if (res16) {
+            const uint16_t* src = reinterpret_cast<const uint16_t*>(p.res1) + e.orow * (int64_t)p.ldres + ocol;
+            ldg_nc_v8(src, rs);
+            ldg_nc_v8(src + 16, rs + 8);
         }
         tmem_ld_wait();
 #pragma unroll
@@ -374,8 +379,10 @@ __device__ __forceinline__ void epilogue_rows_lean(const GemmKParams& p, uint32_
         }
         if (GEGLU) {                                       // v = value * gelu(gate)
             tmem_ld_32x32(taddr + OUT_BN + c0, r);
+            if (bias) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(bias + ncol_in + OUT_BN) + i);
+                for (int i = 0; i < 8; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(bias + ncol_in + OUT_BN) + i);
+            }
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -391,24 +398,55 @@ __device__ __forceinline__ void epilogue_rows_lean(const GemmKParams& p, uint32_
                 v[j + 1] = g.y;
             }
         }
-        if (ACT == SMTL_ACT_NONE && p.res1 && row_ok) {
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const float2 f = unpack16x2(rs[q], FMT);
-                v[2 * q] += f.x;
-                v[2 * q + 1] += f.y;
-            }
-        }
         if (row_ok) {
-            uint32_t w[16];
+            if (p.aux_bf16) {                              // the value before the residual add (child-stream feature tap)
+                uint32_t w[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) w[j] = pack16x2(v[2 * j], v[2 * j + 1], FMT);
-            st_global_v8_b32(out_row + ocol, w);
-            st_global_v8_b32(out_row + ocol + 16, w + 8);
-        } else if (e.halo) {                               // PAD_KEEP: the output keeps a zero halo for its consumers
+                for (int j = 0; j < 16; ++j) w[j] = pack16x2(v[2 * j], v[2 * j + 1], FMT);
+                uint16_t* dst = p.aux_bf16 + e.orow * (int64_t)p.ld_aux + ocol;
+                st_global_v8_b32(dst, w);
+                st_global_v8_b32(dst + 16, w + 8);
+            }
+            if (res16) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const float2 f = unpack16x2(rs[q], FMT);
+                    v[2 * q] += f.x;
+                    v[2 * q + 1] += f.y;
+                }
+            } else if (p.res1) {                           // fp32 residual stream(s) of the transformer
+#pragma unroll 1
+                for (int k = 0; k < 2; ++k) {
+                    const float* res = reinterpret_cast<const float*>(k == 0 ? p.res1 : p.res2);
+                    if (!res) break;
+                    const float* src = res + e.orow * (int64_t)p.ldres + ocol;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint32_t t[8];
+                        ldg_nc_v8(src + j, t);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[j + q] += __uint_as_float(t[q]);
+                    }
+                }
+            }
+            if (p.out_f32) {
+                float* dst = p.out_f32 + e.orow * (int64_t)p.ldc + ocol;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) st_global_v8_f32(dst + j, &v[j]);
+            }
+            if (p.out_bf16) {
+                uint32_t w[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) w[j] = pack16x2(v[2 * j], v[2 * j + 1], FMT);
+                uint16_t* dst = p.out_bf16 + e.orow * (int64_t)p.ldc + ocol;
+                st_global_v8_b32(dst, w);
+                st_global_v8_b32(dst + 16, w + 8);
+            }
+        } else if (e.halo && p.out_bf16) {                 // PAD_KEEP: the output keeps a zero halo for its consumers
             const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-            st_global_v8_b32(out_row + ocol, z);
-            st_global_v8_b32(out_row + ocol + 16, z);
+            uint16_t* dst = p.out_bf16 + e.orow * (int64_t)p.ldc + ocol;
+            st_global_v8_b32(dst, z);
+            st_global_v8_b32(dst + 16, z);
         }
         __syncwarp();   // reconverge before the next warp-collective instruction
         if (do_stats) chunk_stats_to_cells(p, v, row_ok, lane, ocol, c0, e.img_lo, stats_acc);
@@ -1538,15 +1576,20 @@ extern "C" int smtl_gemm_run(const smtl_gemm_op* op, void* stream) {
     kp.stats_images = g.stats_images;
     kp.stats_rep = g.stats_replicas > 0 ? g.stats_replicas : 1;
     kp.stats_g = g.stats_group > 1 ? g.stats_group : 1;
-    // column bias + {nothing | GELU | GEGLU} + 16-bit output, whole 32-column chunks, 32-byte aligned rows; without an
-    // activation also a 16-bit residual and the statistics
-    const bool plain = g.act == SMTL_ACT_NONE;
-    const int n_out = g.act == SMTL_ACT_GEGLU ? g.n / 2 : g.n;
-    kp.lean = (plain || g.act == SMTL_ACT_GELU || g.act == SMTL_ACT_GEGLU) && g.bias && !g.bias_per_row && !g.aux_bf16 &&
-              !g.res2 && !g.out_f32 && g.out_bf16 && n_out % 32 == 0 && g.n % 32 == 0 && g.ldc % 16 == 0 &&
-              (reinterpret_cast<uintptr_t>(g.out_bf16) & 31) == 0 && (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0 &&
-              (plain ? (!g.res1 || (g.res_fmt16 && g.ldres % 16 == 0 && (reinterpret_cast<uintptr_t>(g.res1) & 31) == 0))
-                     : (!g.res1 && !g.stats));
+    // whole 32-column chunks and 32-byte aligned rows everywhere: the lean epilogue has no scalar fallbacks
+    {
+        auto al = [](const void* q, uintptr_t a) { return (reinterpret_cast<uintptr_t>(q) & (a - 1)) == 0; };
+        const bool plain = g.act == SMTL_ACT_NONE;
+        const int n_out = g.act == SMTL_ACT_GEGLU ? g.n / 2 : g.n;
+        const int res_ld = g.res_fmt16 ? 16 : 8;
+        bool ok = (plain || g.act == SMTL_ACT_GELU || g.act == SMTL_ACT_GEGLU) && !g.bias_per_row && n_out % 32 == 0 &&
+                  g.n % 32 == 0 && (g.out_bf16 || g.out_f32) && (!g.bias || al(g.bias, 16));
+        ok = ok && (!g.out_bf16 || (g.ldc % 16 == 0 && al(g.out_bf16, 32))) && (!g.out_f32 || (g.ldc % 8 == 0 && al(g.out_f32, 32)));
+        ok = ok && (!g.aux_bf16 || (g.ld_aux % 16 == 0 && al(g.aux_bf16, 32)));
+        ok = ok && (!g.res1 || (g.ldres % res_ld == 0 && al(g.res1, 32))) && (!g.res2 || (g.res1 && !g.res_fmt16 && al(g.res2, 32)));
+        ok = ok && (plain || (!g.res1 && !g.res2 && !g.stats));
+        kp.lean = ok ? 1 : 0;
+    }
     kp.out_f32 = g.out_f32;
     kp.out_bf16 = reinterpret_cast<uint16_t*>(g.out_bf16);
     kp.aux_bf16 = reinterpret_cast<uint16_t*>(g.aux_bf16);
