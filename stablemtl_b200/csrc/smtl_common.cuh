@@ -289,6 +289,29 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// TMEM -> registers in the MMA-fragment shape: 16 lanes x (4 x 256 bits = 32 fp32 columns).  Thread t = (g = t / 4, q = t % 4)
+// gets r[4k + 2j + e] = (lane lane0 + g + 8j, column col0 + 8k + 2q + e) -- lanes g and g + 8, column pairs, like the
+// accumulator fragment of mma.m16n8.  A packed pair {r[4k+2j], r[4k+2j+1]} is then one stmatrix / ldmatrix fragment.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+// Four 8x8 16-bit matrices, registers <-> shared memory, TRANSPOSED on the way: thread 8i + r supplies the address of the
+// 16-byte row r of matrix i; a thread's register of matrix i holds elements (2q, g) and (2q + 1, g) of the stored rows x
+// columns, i.e. with fragments indexed [g][2q + e] the stored matrix is the transpose.
+__device__ __forceinline__ void stmatrix_x4_trans(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("stmatrix.sync.aligned.x4.trans.m8n8.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c),
+                 "r"(d) : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d)
+                 : "r"(addr) : "memory");
+}
 
 // registers -> TMEM, same shape
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {

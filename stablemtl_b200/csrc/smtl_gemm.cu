@@ -920,10 +920,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
 constexpr int TBN = 256;                            // pixels per tile
 constexpr int T_STAGE_BYTES = A_STAGE_BYTES + TBN * BLOCK_K * 2;   // weights 16 KB + pixels 32 KB
 constexpr int T_PB = 34 * 1024;                     // grouped mode: 256 + 8 pixel rows x 128 B, rounded up to the 1 KB swizzle repeat
-// [32 pixels][32 channels] 16-bit.  Pitch 64 B, no padding: a 2-byte column write touches one row (64 contiguous bytes)
-// and a quarter-warp of 16-byte accesses covers two consecutive rows = all 32 banks once (a padded pitch of 80 B made
-// those two rows overlap in 4 banks: 20 M conflicts per launch in the profile).
-constexpr int T_STG_PITCH = 64;
+// [32 pixels][32 channels] 16-bit, pitch 80 B: the eight 16-byte rows of an stmatrix / ldmatrix 8x8 block (pixels r .. r + 7,
+// one 8-channel piece) and the eight rows a quarter-warp moves on the coalesced side (same piece of eight pixels) fall
+// in eight different 16-byte bank groups (5 r mod 8).
+constexpr int T_STG_PITCH = 80;
 constexpr int T_STG_WARP = 32 * T_STG_PITCH;
 constexpr int T_STAGING = EPI_WARPS * T_STG_WARP;
 
@@ -1099,30 +1099,59 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue: thread = output channel
+        // ------------------------------------------------------------------ epilogue
+        // The accumulator is channel-major (TMEM lane = output channel, column = pixel); the output is pixel-major.
+        // tcgen05.ld.16x256b hands a thread the MMA-fragment shape (channels g, g + 8 of a 16-lane half x pixel PAIRS), so
+        // a packed pair is one stmatrix fragment and stmatrix.trans writes [pixel][8 channels] rows: 4 transposing
+        // stores per 32 x 32 block instead of 32 two-byte ones, half the 16-bit conversions, and the residual comes back
+        // the same way through ldmatrix.trans.  (The first version -- one channel per thread, 32 st.shared.u16 + 32
+        // ld.shared.u16 per block -- shared the 128 B/clk shared-memory port with the MMAs' 96 B/clk of operand reads:
+        // tensor pipe 73 % active, 15 M bank conflicts per launch.)
         const int quarter = warp & 3;
         const int half = (warp - 2) >> 2;
-        const int ch = quarter * 32 + lane;                           // this thread's output channel
+        const int g = lane >> 2, tq = lane & 3;
+        // statistics: after the quad reduction lane (g, tq) owns channel 32 quarter + 8 tq + g
+        const int ch = quarter * 32 + 8 * tq + g;
         const bool ch_ok = ch < p.n;
-        const float bias_c = (p.bias && ch_ok) ? __ldg(p.bias + ch) : 0.0f;
+        float bias_c[4];                                              // channels 32 quarter + 8 m + g, m = 2 h + j
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const int c = quarter * 32 + 8 * m + g;
+            bias_c[m] = (p.bias && c < p.n) ? __ldg(p.bias + c) : 0.0f;
+        }
         const uint32_t stg = smem_u32(staging + (warp - 2) * T_STG_WARP);      // explicit shared-space accesses below
-        const int piece = lane & 3;                                   // 8-channel piece this lane moves (coalesced side)
+        // coalesced side: in step i a lane moves the 8-channel piece (lane >> 3) of pixel 8 i + (lane & 7)
+        const int piece = lane >> 3;
+        const int prow = lane & 7;
         const int cpiece = quarter * 32 + piece * 8;                  // its first channel
         const bool piece_ok = cpiece + 8 <= p.n;
-        // this thread's channel sums of the current image, exact: every 32-pixel chunk's fp32 partial is added in the
-        // int64 fixed-point form of the statistics cells (smtl_common.cuh), so the order of the chunks does not matter
+        // matrix side: thread 8 i + r addresses row r (= pixel) of matrix i of an x4 group; group (h, kk) holds the
+        // matrices (pixel block 2 kk + (i >> 1), channel block 2 h + (i & 1))
+        const uint32_t mat_off = (uint32_t)((8 * (lane >> 4) + (lane & 7)) * T_STG_PITCH + 16 * ((lane >> 3) & 1));
+        // this lane's channel sums of the current image, exact: every tile's fp32 partial is added in the int64
+        // fixed-point form of the statistics cells (smtl_common.cuh), so the order of the tiles does not matter
         // (the fp32 partial of one TILE -- the same pixels wherever the image sits in the batch -- is what gets fixed)
         long long acc_sl = 0, acc_sh = 0, acc_ql = 0, acc_qh = 0;
-        float tsum = 0.f, tsq = 0.f;                                  // this tile's running partial
+        float2 tsum[4], tsq[4];                                       // this tile's running partials of channel m (even, odd pixels)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) { tsum[m] = make_float2(0.f, 0.f); tsq[m] = make_float2(0.f, 0.f); }
         int cur_img = -1;
-        auto commit = [&]() {                                         // tile partial -> the int64 accumulators
+        auto commit = [&]() {                                         // tile partials -> the int64 accumulators
+            float s_mine = 0.f, q_mine = 0.f;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {                             // the four lanes of a quad hold the same channels
+                float a = tsum[m].x + tsum[m].y, b = tsq[m].x + tsq[m].y;
+                a += __shfl_xor_sync(0xffffffffu, a, 1); a += __shfl_xor_sync(0xffffffffu, a, 2);
+                b += __shfl_xor_sync(0xffffffffu, b, 1); b += __shfl_xor_sync(0xffffffffu, b, 2);
+                if (m == tq) { s_mine = a; q_mine = b; }
+                tsum[m] = make_float2(0.f, 0.f);
+                tsq[m] = make_float2(0.f, 0.f);
+            }
             bool hi;
-            long long v = stats_fix(tsum, hi);
+            long long v = stats_fix(s_mine, hi);
             if (hi) acc_sh += v; else acc_sl += v;
-            v = stats_fix(tsq, hi);
+            v = stats_fix(q_mine, hi);
             if (hi) acc_qh += v; else acc_ql += v;
-            tsum = 0.f;
-            tsq = 0.f;
         };
         auto flush = [&]() {
             if (p.stats && cur_img >= 0 && ch_ok) {
@@ -1140,12 +1169,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
             const int acc = it & 1;
             int64_t pix0, pix_end;
             tile_span(p, tile, TBN, pix0, pix_end);
+            if (p.stats) {                                            // tiles are image-aligned whenever statistics are produced
+                const int img = tile / p.tiles_per_img;
+                if (img != cur_img) { flush(); cur_img = img; }
+            }
             mbar_wait(&acc_full[acc], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
             for (int c0 = half * 32; c0 < TBN; c0 += 64) {
-                // pixel (c0 + lane): output row, validity, image
+                // pixel (c0 + lane): output row, validity
                 const int64_t grow = pix0 + c0 + lane;
                 bool ok, halo;
                 int64_t orow;
@@ -1156,90 +1189,83 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemmT_kernel(const __grid
                 const uint32_t halomask = __ballot_sync(0xffffffffu, halo);
                 if ((okmask | halomask) == 0 && pix0 + c0 >= pix_end) break;         // warp-uniform: past the end
                 const int orow32 = (int)orow;
-                const int img_l = !(p.stats && ok) ? -1 : (map_img >= 0 ? map_img : (int)(orow / p.stats_rpi));
-                uint32_t rr[32];
-                float v[32];
-                tmem_ld_32x32(taddr + c0, rr);
-                // rows this lane moves on the coalesced side: pixel 8 i + lane / 4
+                uint32_t rr[2][16];
+                tmem_ld_16x256b_x4(taddr + c0, rr[0]);                               // channels quarter * 32 + 0 .. 15
+                tmem_ld_16x256b_x4(taddr + (16u << 16) + c0, rr[1]);                 //                     + 16 .. 31
+                // rows this lane moves on the coalesced side: pixel 8 i + prow
                 int orow_i[4];
                 uint32_t ok_i = 0, halo_i = 0;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    orow_i[i] = __shfl_sync(0xffffffffu, orow32, 8 * i + (lane >> 2));
-                    ok_i |= ((okmask >> (8 * i + (lane >> 2))) & 1u) << i;
-                    halo_i |= ((halomask >> (8 * i + (lane >> 2))) & 1u) << i;
+                    orow_i[i] = __shfl_sync(0xffffffffu, orow32, 8 * i + prow);
+                    ok_i |= ((okmask >> (8 * i + prow)) & 1u) << i;
+                    halo_i |= ((halomask >> (8 * i + prow)) & 1u) << i;
                 }
-                uint4 rq[4];
-                if (p.res1) {                                            // 16-bit residual, issued before the TMEM wait
+                uint32_t rp[2][8];                                       // the residual as fragments (pixel pairs)
+                if (p.res1) {                                            // 16-bit residual: global -> staging tile -> ldmatrix.trans
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        rq[i] = make_uint4(0, 0, 0, 0);
+                        uint4 q = make_uint4(0, 0, 0, 0);
                         if (((ok_i >> i) & 1u) && piece_ok)
-                            rq[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.res1) +
-                                                                         (int64_t)orow_i[i] * p.ldres + cpiece));
+                            q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.res1) +
+                                                                     (int64_t)orow_i[i] * p.ldres + cpiece));
+                        sts_v4(stg + (8 * i + prow) * T_STG_PITCH + piece * 16, q);
                     }
+                    __syncwarp();
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk)
+                            ldmatrix_x4_trans(stg + mat_off + (uint32_t)(16 * kk * T_STG_PITCH + 32 * h), rp[h][4 * kk],
+                                              rp[h][4 * kk + 1], rp[h][4 * kk + 2], rp[h][4 * kk + 3]);
+                    __syncwarp();
                 }
                 tmem_ld_wait();
+                uint32_t w[2][8];                                        // w[h][2 k + j]: pixels 8 k + 2 tq + {0, 1}, channel 16 h + 8 j + g
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]) + bias_c;
-                if (p.res1) {
+                for (int h = 0; h < 2; ++h) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        sts_v4(stg + (8 * i + (lane >> 2)) * T_STG_PITCH + piece * 16, rq[i]);
-                    __syncwarp();
+                    for (int k = 0; k < 4; ++k) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        v[j] += unpack16x2(lds_u16(stg + j * T_STG_PITCH + lane * 2), FMT).x;
+                        for (int j = 0; j < 2; ++j) {
+                            const int m = 2 * h + j;
+                            float v0 = __uint_as_float(rr[h][4 * k + 2 * j]) + bias_c[m];
+                            float v1 = __uint_as_float(rr[h][4 * k + 2 * j + 1]) + bias_c[m];
+                            if (p.res1) {
+                                const float2 f = unpack16x2(rp[h][2 * k + j], FMT);
+                                v0 += f.x;
+                                v1 += f.y;
+                            }
+                            w[h][2 * k + j] = pack16x2(v0, v1, FMT);
+                            if (p.stats) {                               // packed: one FADD2 + one FFMA2 per pixel pair
+                                if (okmask != 0xffffffffu) {                 // warp-uniform; halo / out-of-range pixels count as 0
+                                    const int px = 8 * k + 2 * tq;
+                                    v0 = ((okmask >> px) & 1u) ? v0 : 0.f;
+                                    v1 = ((okmask >> (px + 1)) & 1u) ? v1 : 0.f;
+                                }
+                                tsum[m] = fadd2(tsum[m], make_float2(v0, v1));
+                                tsq[m] = ffma2(make_float2(v0, v1), make_float2(v0, v1), tsq[m]);
+                            }
+                        }
                     }
-                    __syncwarp();
                 }
-                // channel-major -> pixel-major through the staging tile, then 64-byte row pieces
+                // channel-major -> pixel-major: four transposing 8x8 stores per 16-channel half, then 64-byte row pieces
 #pragma unroll
-                for (int j = 0; j < 32; ++j) sts_u16(stg + j * T_STG_PITCH + lane * 2, to16(v[j], FMT));
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk)
+                        stmatrix_x4_trans(stg + mat_off + (uint32_t)(16 * kk * T_STG_PITCH + 32 * h), w[h][4 * kk], w[h][4 * kk + 1],
+                                          w[h][4 * kk + 2], w[h][4 * kk + 3]);
                 __syncwarp();
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const uint4 q = lds_v4(stg + (8 * i + (lane >> 2)) * T_STG_PITCH + piece * 16);
+                    const uint4 q = lds_v4(stg + (8 * i + prow) * T_STG_PITCH + piece * 16);
                     if (((ok_i >> i) & 1u) && piece_ok)
                         *reinterpret_cast<uint4*>(p.out_bf16 + (int64_t)orow_i[i] * p.ldc + cpiece) = q;
                     else if (((halo_i >> i) & 1u) && piece_ok)       // PAD_KEEP: zero halo
                         *reinterpret_cast<uint4*>(p.out_bf16 + (int64_t)orow_i[i] * p.ldc + cpiece) = make_uint4(0, 0, 0, 0);
                 }
                 __syncwarp();
-                if (p.stats && okmask) {
-                    int lo, hi;
-                    if (p.tile_rpi) {                                    // image-aligned tile: its image is known
-                        lo = hi = tile / p.tiles_per_img;
-                    } else {
-                        lo = ok ? img_l : 0x7fffffff;
-                        hi = img_l;
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-                            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-                        }
-                    }
-                    if (lo == hi) {                                      // the usual case: one image in this chunk
-                        if (lo != cur_img) { commit(); flush(); cur_img = lo; }
-                        if (okmask == 0xffffffffu) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) { tsum += v[j]; tsq = fmaf(v[j], v[j], tsq); }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if ((okmask >> j) & 1u) { tsum += v[j]; tsq = fmaf(v[j], v[j], tsq); }
-                        }
-                    } else {
-                        for (int j = 0; j < 32; ++j) {                   // image boundary inside the chunk (tiles that are
-                            const int im = __shfl_sync(0xffffffffu, img_l, j);   // not image-aligned only)
-                            if ((okmask >> j) & 1u) {
-                                if (im != cur_img) { commit(); flush(); cur_img = im; }
-                                tsum += v[j];
-                                tsq = fmaf(v[j], v[j], tsq);
-                            }
-                        }
-                    }
-                }
             }
             tc_fence_before();
             __syncwarp();
