@@ -108,6 +108,17 @@ def main():
     out["semantic_margin_cdf"] = {str(m): (margin < m).float().mean().item() for m in (1e-3, 2e-3, 5e-3, 1e-2, 2e-2, 5e-2)}
     out["semantic_map_abs_err_rms"] = (clipped_e["semantic"].double() - clipped["semantic"].double()).pow(2).mean().sqrt().item()
     out["semantic_map_rms"] = clipped["semantic"].double().pow(2).mean().sqrt().item()
+    # The same checker against ITSELF at the precision the reference runs at on a GPU with PyTorch's defaults
+    # (torch.backends.cudnn.allow_tf32 = True: every cuDNN conv takes TF32 operands; matmuls stay fp32) and with TF32
+    # matmuls too: how far a GPU run of the unmodified reference is from its own strict-fp32 result.
+    for name, conv_tf32, mm_tf32 in (("reference_tf32_convs_pytorch_default", True, False), ("reference_tf32_convs_and_matmuls", True, True)):
+        torch.backends.cudnn.allow_tf32 = conv_tf32
+        torch.backends.cuda.matmul.allow_tf32 = mm_tf32
+        maps_t, clipped_t, _ = orc.predict_all(rgb.cuda(), nxt.cuda(), return_latents=True)
+        out[name] = {"map_rel_l2": {t: rel_l2(clipped_t[t], clipped[t]) for t in synth.TASKS},
+                     "semantic_agreement": (maps_t["semantic"] == maps["semantic"]).float().mean().item()}
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     print(json.dumps(out))
 
 
