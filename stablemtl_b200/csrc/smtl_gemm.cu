@@ -350,24 +350,26 @@ __device__ __forceinline__ void epilogue_rows_lean(const GemmKParams& p, uint32_
         const int ncol_in = n0 + c0;                       // B-row index of the chunk's first column
         if (ncol_in >= p.n) break;                         // warp-uniform
         const int ocol = GEGLU ? tn * OUT_BN + c0 : ncol_in;
+        const bool whole = GEGLU || ocol + 32 <= p.n_out;  // else the last chunk of a launch with n % 32 == 16: 16 columns
         uint32_t r[32];
         float v[32];
         tmem_ld_32x32(taddr + c0, r);
         // the chunk's 32 bias values: every lane reads the SAME 16-byte pieces (one broadcast transaction each, L1-resident)
         float4 b4[8];
-        if (bias) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(bias + ncol_in) + i);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) b4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int i = 0; i < 8; ++i)
+            b4[i] = (bias && (whole || i < 4)) ? __ldg(reinterpret_cast<const float4*>(bias + ncol_in) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         uint32_t rs[16];                                   // 16-bit residual, issued before the TMEM wait
         const bool res16 = ACT == SMTL_ACT_NONE && p.res1 && p.res16 && row_ok;
         if (res16) {
             const uint16_t* src = reinterpret_cast<const uint16_t*>(p.res1) + e.orow * (int64_t)p.ldres + ocol;
             ldg_nc_v8(src, rs);
-            ldg_nc_v8(src + 16, rs + 8);
+            if (whole) {
+                ldg_nc_v8(src + 16, rs + 8);
+            } else {
+#pragma unroll
+                for (int q = 8; q < 16; ++q) rs[q] = 0u;
+            }
         }
         tmem_ld_wait();
 #pragma unroll
@@ -405,7 +407,7 @@ __device__ __forceinline__ void epilogue_rows_lean(const GemmKParams& p, uint32_
                 for (int j = 0; j < 16; ++j) w[j] = pack16x2(v[2 * j], v[2 * j + 1], FMT);
                 uint16_t* dst = p.aux_bf16 + e.orow * (int64_t)p.ld_aux + ocol;
                 st_global_v8_b32(dst, w);
-                st_global_v8_b32(dst + 16, w + 8);
+                if (whole) st_global_v8_b32(dst + 16, w + 8);
             }
             if (res16) {
 #pragma unroll
@@ -422,6 +424,7 @@ __device__ __forceinline__ void epilogue_rows_lean(const GemmKParams& p, uint32_
                     const float* src = res + e.orow * (int64_t)p.ldres + ocol;
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
+                        if (!whole && j >= 16) break;
                         uint32_t t[8];
                         ldg_nc_v8(src + j, t);
 #pragma unroll
@@ -432,7 +435,8 @@ __device__ __forceinline__ void epilogue_rows_lean(const GemmKParams& p, uint32_
             if (p.out_f32) {
                 float* dst = p.out_f32 + e.orow * (int64_t)p.ldc + ocol;
 #pragma unroll
-                for (int j = 0; j < 32; j += 8) st_global_v8_f32(dst + j, &v[j]);
+                for (int j = 0; j < 32; j += 8)
+                    if (whole || j < 16) st_global_v8_f32(dst + j, &v[j]);
             }
             if (p.out_bf16) {
                 uint32_t w[16];
@@ -440,13 +444,13 @@ __device__ __forceinline__ void epilogue_rows_lean(const GemmKParams& p, uint32_
                 for (int j = 0; j < 16; ++j) w[j] = pack16x2(v[2 * j], v[2 * j + 1], FMT);
                 uint16_t* dst = p.out_bf16 + e.orow * (int64_t)p.ldc + ocol;
                 st_global_v8_b32(dst, w);
-                st_global_v8_b32(dst + 16, w + 8);
+                if (whole) st_global_v8_b32(dst + 16, w + 8);
             }
         } else if (e.halo && p.out_bf16) {                 // PAD_KEEP: the output keeps a zero halo for its consumers
             const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
             uint16_t* dst = p.out_bf16 + e.orow * (int64_t)p.ldc + ocol;
             st_global_v8_b32(dst, z);
-            st_global_v8_b32(dst + 16, z);
+            if (whole) st_global_v8_b32(dst + 16, z);
         }
         __syncwarp();   // reconverge before the next warp-collective instruction
         if (do_stats) chunk_stats_to_cells(p, v, row_ok, lane, ocol, c0, e.img_lo, stats_acc);
@@ -1608,8 +1612,9 @@ extern "C" int smtl_gemm_run(const smtl_gemm_op* op, void* stream) {
         const bool plain = g.act == SMTL_ACT_NONE;
         const int n_out = g.act == SMTL_ACT_GEGLU ? g.n / 2 : g.n;
         const int res_ld = g.res_fmt16 ? 16 : 8;
-        bool ok = (plain || g.act == SMTL_ACT_GELU || g.act == SMTL_ACT_GEGLU) && !g.bias_per_row && n_out % 32 == 0 &&
-                  g.n % 32 == 0 && (g.out_bf16 || g.out_f32) && (!g.bias || al(g.bias, 16));
+        bool ok = (plain || g.act == SMTL_ACT_GELU || g.act == SMTL_ACT_GEGLU) && !g.bias_per_row &&
+                  (g.act == SMTL_ACT_GEGLU ? (n_out % 32 == 0 && g.n % 32 == 0) : g.n % 16 == 0) && (g.out_bf16 || g.out_f32) &&
+                  (!g.bias || al(g.bias, 16));
         ok = ok && (!g.out_bf16 || (g.ldc % 16 == 0 && al(g.out_bf16, 32))) && (!g.out_f32 || (g.ldc % 8 == 0 && al(g.out_f32, 32)));
         ok = ok && (!g.aux_bf16 || (g.ld_aux % 16 == 0 && al(g.aux_bf16, 32)));
         ok = ok && (!g.res1 || (g.ldres % res_ld == 0 && al(g.res1, 32))) && (!g.res2 || (g.res1 && !g.res_fmt16 && al(g.res2, 32)));
