@@ -659,7 +659,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
                 tile_span(p, tm, CG * BLOCK_M, row0, row_end);
                 const int64_t m0 = row0 + (int64_t)rank * BLOCK_M;
                 const int n0 = tn * BN + (int)rank * B_ROWS +
-                               (p.group_rows ? (int)(((int64_t)tm * CG * BLOCK_M) / p.group_rows) * p.n : 0);
+                               (p.group_rows ? (int)(row0 / p.group_rows) * p.n : 0);
                 for (int g = 0; g < p.ngrp; ++g) {
                     const GemmKParams::Grp gr = p.grp[g];
                     const CUtensorMap* tma = gr.src ? &p.tm_a1 : &p.tm_a0;
@@ -715,7 +715,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
                 tile_span(p, tm, CG * BLOCK_M, row0, row_end);
                 const int64_t m0 = row0 + (int64_t)rank * BLOCK_M;
                 const int n0 = tn * BN + (int)rank * B_ROWS +
-                               (p.group_rows ? (int)(((int64_t)tm * CG * BLOCK_M) / p.group_rows) * p.n : 0);
+                               (p.group_rows ? (int)(row0 / p.group_rows) * p.n : 0);
                 int kb_global = 0;
                 for (int s = 0; s < p.nseg; ++s) {
                     const smtl_gemm_seg sg = p.seg[s];
@@ -1389,8 +1389,8 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
     SMTL_CHECK_ARG(g.up_parity >= 0 && g.up_parity <= 3, "gemm_plan: bad up_parity");
     SMTL_CHECK_ARG(g.tile_order >= 0 && g.tile_order <= 2, "gemm_plan: bad tile_order");
     if (g.group_rows) {
-        SMTL_CHECK_ARG(g.group_rows > 0 && g.group_rows % BLOCK_M == 0 && g.m % g.group_rows == 0,
-                       "gemm_plan: group_rows %lld must divide m and be a multiple of %d", (long long)g.group_rows, BLOCK_M);
+        SMTL_CHECK_ARG(g.group_rows > 0 && g.m % g.group_rows == 0, "gemm_plan: group_rows %lld must divide m",
+                       (long long)g.group_rows);
         SMTL_CHECK_ARG(g.rowmap == SMTL_ROWMAP_IDENTITY && !g.bias_per_row && g.act != SMTL_ACT_GEGLU && !g.stats,
                        "gemm_plan: grouped GEMM is a plain token linear");
     }
@@ -1416,12 +1416,16 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
         SMTL_CHECK_ARG(g.m == tile_rpi * g.stats_images, "gemm_plan: stats: m=%lld is not stats_images=%d x %lld rows",
                        (long long)g.m, g.stats_images, (long long)tile_rpi);
     }
+    // grouped GEMM whose groups are not whole tiles: M tiles restart at every group as well (rows of the last tile of a
+    // group that belong to the next one are computed with the wrong weights and masked by the tile's row_end)
+    if (g.group_rows && g.group_rows % BLOCK_M != 0) tile_rpi = g.group_rows;
     op->tile_rpi = tile_rpi;
+    const int tile_units = tile_rpi ? (int)(g.m / tile_rpi) : 0;      // images / weight groups the M tiles restart at
     const int stats_smem = g.stats ? STATS_SMEM : 0;   // running column sums of the epilogue warps (unused by the swapped kernel)
     auto count_tiles_m = [&](int tile_rows) {
         if (!tile_rpi) { op->tiles_per_img = 0; return (int)((g.m + tile_rows - 1) / tile_rows); }
         op->tiles_per_img = (int)((tile_rpi + tile_rows - 1) / tile_rows);
-        return op->tiles_per_img * g.stats_images;
+        return op->tiles_per_img * tile_units;
     };
 
     const int sms = smtl_host::num_sms();

@@ -506,7 +506,7 @@ class UNetPlan(_PlanBase):
             hq = cfg.task_q_hidden
             q1, q2 = P.alloc((M, hq), ops.h16()), P.alloc((M, hq), ops.h16())
             tq = P.alloc((M, C), ops.h16())
-            grouped = rpg % 128 == 0          # one grouped launch for all task streams when tiles cannot straddle groups
+            grouped = True                    # one grouped launch for all task streams (M tiles restart at every group)
 
             def stacked(key, tasks):
                 """[len(tasks) * out, in] weights / [len(tasks) * out] bias of the per-task module, in row-group order"""

@@ -558,10 +558,11 @@ def test_conv_up2x_parity_decomposition(b, h, w, cin, cout):
     assert rel_l2(st[:, :, 1], (blk * blk).sum(1)) < 2e-3
 
 
-def test_gemm_grouped_per_task_weights():
-    """rows [g*R, (g+1)*R) use weight / bias group g (the per-task MLPs of the task attention in one launch)"""
+@pytest.mark.parametrize("G,R,n,k", [(7, 640, 320, 640), (7, 2400, 1280, 640), (3, 300, 320, 320), (5, 72, 64, 128)])
+def test_gemm_grouped_per_task_weights(G, R, n, k):
+    """rows [g*R, (g+1)*R) use weight / bias group g (the per-task MLPs of the task attention in one launch); R need not
+    be a multiple of the 128-row tile: M tiles restart at every group"""
     ops, L = _ops()
-    G, R, n, k = 7, 640, 320, 640
     a = rnd(G * R, k, seed=1).to(H16())
     w = rnd(G, n, k, scale=k ** -0.5, seed=2).to(H16())
     bias = rnd(G, n, seed=3)
