@@ -146,7 +146,7 @@ typedef struct smtl_gemm_op {
     uint64_t tmap_x8[2][16];
     int64_t tile_rpi;       /* image-aligned M tiling: GEMM rows per image (0 = off), M tiles per image */
     int32_t tiles_per_img;
-    int32_t pad_;
+    int32_t pair_split;     /* cta_group 2 over image-aligned tiles of small maps: the pair takes two consecutive 128-row tiles */
 } smtl_gemm_op;
 
 int smtl_gemm_plan(const smtl_gemm_args* args, smtl_gemm_op* op);

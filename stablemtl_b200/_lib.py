@@ -69,7 +69,7 @@ class GemmOp(C.Structure):
         ("ngrp", i32), ("sp", i32), ("sw", i32),
         ("grp", (i32 * 6) * MAX_SEG),
         ("tmap_x8", (C.c_uint64 * 16) * 2),
-        ("tile_rpi", i64), ("tiles_per_img", i32), ("pad_", i32),
+        ("tile_rpi", i64), ("tiles_per_img", i32), ("pair_split", i32),
     ]
 
 

@@ -66,6 +66,11 @@ struct alignas(64) GemmKParams {
     // 32-row partial sums of an image are the same fp32 values wherever the image sits in the batch.
     int64_t tile_rpi;            // GEMM rows per image; 0 = tiles run over all rows
     int32_t tiles_per_img;
+    // CTA pairs over image-aligned tiles of SMALL maps: the two CTAs of a pair take two CONSECUTIVE 128-row tiles of the
+    // image-aligned 128-row tiling (tiles_per_img then counts 128-row tiles) instead of the halves of one 256-row tile
+    // -- nothing in cta_group::2 needs the two halves of A to be adjacent rows.  A 15x20 map (374 padded rows) is 3 x 128
+    // rows either way instead of 2 x 256 = 37 % padding, and keeps the pair's halved weight traffic (+17 % on these convs).
+    int32_t pair_split;
     // Tile order.  0: tile = blockIdx + k * grid, column tile fastest.  1 (statistics producers): every CTA takes a
     // CONTIGUOUS run of the column-tile-major order, i.e. a long strip of M tiles of one column tile, so the per-column
     // sums stay in shared memory for a whole (image, column tile) run and reach global memory as one atomic per cell,
@@ -183,9 +188,21 @@ __device__ __forceinline__ void tile_span(const GemmKParams& p, int tm, int tile
         const int img = tm / p.tiles_per_img;
         row0 = (int64_t)img * p.tile_rpi + (int64_t)(tm - img * p.tiles_per_img) * tile_rows;
         row_end = (int64_t)(img + 1) * p.tile_rpi;
+        if (row_end > p.m) row_end = p.m;                  // the odd tile out of a split pair: no valid row
     } else {
         row0 = (int64_t)tm * tile_rows;
         row_end = p.m;
+    }
+}
+
+// First GEMM row of the 128 rows CTA `rank` of a pair (or the only CTA) works on in M tile `tm`, and the end of its valid rows.
+template <int CG>
+__device__ __forceinline__ void cta_span(const GemmKParams& p, int tm, uint32_t rank, int64_t& row0, int64_t& row_end) {
+    if (CG == 2 && p.pair_split) {
+        tile_span(p, 2 * tm + (int)rank, BLOCK_M, row0, row_end);
+    } else {
+        tile_span(p, tm, CG * BLOCK_M, row0, row_end);
+        row0 += (int64_t)rank * BLOCK_M;
     }
 }
 
@@ -655,11 +672,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
             for (int tile = tile_begin; tile < tile_end; tile += tile_inc) {
                 int tm, tn;
                 decode_tile(tile, tm, tn);
-                int64_t row0, row_end;
-                tile_span(p, tm, CG * BLOCK_M, row0, row_end);
-                const int64_t m0 = row0 + (int64_t)rank * BLOCK_M;
+                int64_t m0, row_end;
+                cta_span<CG>(p, tm, rank, m0, row_end);
                 const int n0 = tn * BN + (int)rank * B_ROWS +
-                               (p.group_rows ? (int)(row0 / p.group_rows) * p.n : 0);
+                               (p.group_rows ? (int)(m0 / p.group_rows) * p.n : 0);       // grouped GEMMs are single-CTA
                 for (int g = 0; g < p.ngrp; ++g) {
                     const GemmKParams::Grp gr = p.grp[g];
                     const CUtensorMap* tma = gr.src ? &p.tm_a1 : &p.tm_a0;
@@ -711,11 +727,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
             for (int tile = tile_begin; tile < tile_end; tile += tile_inc) {
                 int tm, tn;
                 decode_tile(tile, tm, tn);
-                int64_t row0, row_end;
-                tile_span(p, tm, CG * BLOCK_M, row0, row_end);
-                const int64_t m0 = row0 + (int64_t)rank * BLOCK_M;
+                int64_t m0, row_end;
+                cta_span<CG>(p, tm, rank, m0, row_end);
                 const int n0 = tn * BN + (int)rank * B_ROWS +
-                               (p.group_rows ? (int)(row0 / p.group_rows) * p.n : 0);
+                               (p.group_rows ? (int)(m0 / p.group_rows) * p.n : 0);       // grouped GEMMs are single-CTA
                 int kb_global = 0;
                 for (int s = 0; s < p.nseg; ++s) {
                     const smtl_gemm_seg sg = p.seg[s];
@@ -876,10 +891,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) smtl_gemm_kernel(const __grid_
             decode_tile(tile, tm, tn);
             EpiRow<BN> er;
             int64_t row0, row_end;
-            tile_span(p, tm, CG * BLOCK_M, row0, row_end);
-            epilogue_prepare<BN>(p, row0 + (int64_t)rank * BLOCK_M + row_in_tile, row_end, tn, lane, er);
+            cta_span<CG>(p, tm, rank, row0, row_end);
+            epilogue_prepare<BN>(p, row0 + row_in_tile, row_end, tn, lane, er);
             if (p.stats) {                             // a new (image, column tile) run: flush the previous one's sums
-                const int img = tm / p.tiles_per_img;
+                const int img = (int)(row0 / p.tile_rpi);
                 if (img != run_img || tn != run_tn) {
                     stats_flush(run_img, run_tn);
                     run_img = img;
@@ -1512,18 +1527,27 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
         // (15x20: 374 padded rows = 2 x 256 but 3 x 128).  Measured (scripts/bench_kernels.py stats): the pair is worth
         // ~17 % on these convs -- 30x40 maps (6 x 256 vs 11 x 128 rows, 9 % more padding) still run 8 % faster as pairs,
         // 15x20 maps (33 % more padding) 14 % slower.
-        if (cg == 2 && tile_rpi) {
-            const double e2 = (double)tile_rpi / (double)(((tile_rpi + 255) / 256) * 256);
-            const double e1 = (double)tile_rpi / (double)(((tile_rpi + 127) / 128) * 128);
-            if (e2 * 1.15 < e1) cg = 1;
-        }
         if (g.group_rows) cg = 1;
     }
     SMTL_CHECK_ARG(cg == 1 || cg == 2, "gemm_plan: cta_group %d", cg);
     SMTL_CHECK_ARG(cg == 1 || bn % 16 == 0, "gemm_plan: cta_group 2 needs block_n %% 16 == 0");
+    // Image-aligned tiles of SMALL maps under a pair: 256-row tiles pad them badly, so the two CTAs take two consecutive
+    // 128-row tiles of the 128-row tiling instead (GemmKParams::pair_split) -- the padding of single CTAs with the weight
+    // traffic of pairs.  (Before: such convs fell back to single CTAs, measured 14 % slower than an unpadded pair.)
+    op->pair_split = 0;
+    if (cg == 2 && tile_rpi) {
+        const double e2 = (double)tile_rpi / (double)(((tile_rpi + 255) / 256) * 256);
+        const double e1 = (double)tile_rpi / (double)(((tile_rpi + 127) / 128) * 128);
+        if (e2 * 1.04 < e1) op->pair_split = 1;
+    }
     op->cta_group = cg;
     op->block_n = bn;
-    op->tiles_m = count_tiles_m(cg * BLOCK_M);
+    if (op->pair_split) {
+        const int t128 = count_tiles_m(BLOCK_M);          // also sets tiles_per_img in 128-row units
+        op->tiles_m = (t128 + 1) / 2;
+    } else {
+        op->tiles_m = count_tiles_m(cg * BLOCK_M);
+    }
     op->tiles_n = (g.n + bn - 1) / bn;
     op->total_kblocks = total_kb;
     const int stage_bytes = A_STAGE_BYTES + (bn / cg) * BLOCK_K * 2;
@@ -1602,6 +1626,7 @@ extern "C" int smtl_gemm_run(const smtl_gemm_op* op, void* stream) {
     kp.res16 = g.res_fmt16;
     kp.stats = reinterpret_cast<unsigned long long*>(g.stats);
     kp.tile_rpi = op->tile_rpi;
+    kp.pair_split = op->pair_split;
     kp.tiles_per_img = op->tiles_per_img;
     // auto: the contiguous order pays when an (image, column tile) run is long (>= 16 tiles: +1.5-2.5 % on the 60x80
     // and larger maps); with a few tiles per image the round-robin order is 4-13 % faster (measured, same script)

@@ -747,7 +747,7 @@ def test_gn_finalize_scale_shift_table():
     assert rel_l2(got, ref) < 1e-5
 
 
-@pytest.mark.parametrize("kind", ["conv", "conv_pair", "swapped", "token"])
+@pytest.mark.parametrize("kind", ["conv", "conv_pair", "conv_pair_split", "swapped", "token"])
 def test_channel_stats_are_bit_reproducible_and_batch_position_independent(kind):
     """The GroupNorm statistics are integer fixed-point atomics over image-aligned tiles: two runs give the same BITS,
     and an image's cells do not depend on where it sits in the batch (the reference evaluation is deterministic)."""
@@ -766,7 +766,8 @@ def test_channel_stats_are_bit_reproducible_and_batch_position_independent(kind)
             return st.sum(0), out.reshape(b, rpi, n)
     else:
         b, h, w, cin, cout = {"conv": (5, 15, 20, 320, 320), "conv_pair": (3, 60, 80, 256, 512),
-                              "swapped": (5, 120, 160, 128, 128)}[kind]
+                              "conv_pair_split": (5, 15, 20, 320, 320), "swapped": (5, 120, 160, 128, 128)}[kind]
+        force = dict(cta_group=2) if kind == "conv_pair_split" else {}
         x = rnd(b, h, w, cin, seed=1).to(H16())
         wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=2).to(H16())
         wmat = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()
@@ -774,7 +775,9 @@ def test_channel_stats_are_bit_reproducible_and_batch_position_independent(kind)
         def run(order):
             st = ops.new_stats(b, cout, DEV)
             out = torch.empty(b * h * w, cout, device=DEV, dtype=H16())
-            op = ops.conv3x3(_pad_layout(x[order]), wmat, b, h, w, out_bf16=out, stats=st, stats_rows_per_image=h * w)
+            op = ops.conv3x3(_pad_layout(x[order]), wmat, b, h, w, out_bf16=out, stats=st, stats_rows_per_image=h * w, **force)
+            if kind == "conv_pair_split" and force:  # 374 padded rows per image: the pair takes two consecutive 128-row tiles
+                assert op.struct.cta_group == 2 and op.struct.pair_split == 1 and op.struct.tiles_m == 8
             if kind == "swapped":
                 assert op.struct.cta_group == 3
             if kind == "conv_pair":
@@ -789,6 +792,11 @@ def test_channel_stats_are_bit_reproducible_and_batch_position_independent(kind)
     assert torch.equal(s0, s1) and torch.equal(o0, o1)
     sp, op_ = run(perm)
     assert torch.equal(sp, s0[perm]) and torch.equal(op_, o0[perm])
+    if kind == "conv_pair_split":                # same maps and statistics as the single-CTA tiling of the same conv
+        force.clear()
+        s1, o1 = run(ident)
+        assert rel_l2(o0.float(), o1.float()) < 1e-6
+        assert ((s0 - s1).double().abs() <= 1e-5 * s0.double().abs() + 2.0 ** 20).all()      # cells are 2^-32 fixed point
 
 
 @pytest.mark.parametrize("g,cin,cout,h,w", [(2, 320, 320, 15, 20), (4, 128, 256, 24, 40), (8, 256, 512, 60, 80), (8, 64, 96, 9, 7)])
