@@ -144,6 +144,20 @@ if __name__ == "__main__":
             print(f"xattn_fused heads={heads} rows={7 * rpg}                       {ms:9.3f} ms {gb / ms * 1e3:8.1f} GB/s  "
                   f"{gb / ms * 1e3 / 6552.6 * 100:5.1f}% of measured HBM copy peak", flush=True)
         sys.exit(0)
+    if only == "res":          # decoder ResNet convs as they run in the plan: padded in, padded out, statistics; conv2 adds the 16-bit residual
+        for name, b, h, w, cin, cout in (("vae 1/1", 16, 480, 640, 128, 128), ("vae 1/2", 16, 240, 320, 256, 256),
+                                         ("vae 1/4", 16, 120, 160, 512, 512), ("vae 1/8", 16, 60, 80, 512, 512)):
+            a = rb(b * (h + 2) * (w + 2), cin)
+            wm = rb(cout, 9 * cin)
+            res = rb(b * (h + 2) * (w + 2), cout)
+            out = torch.empty(b * (h + 2) * (w + 2), cout, device=DEV, dtype=ops.h16())
+            bias = torch.zeros(cout, device=DEV)
+            for tag, kw in (("conv1 (no residual)", {}), ("conv2 (+ 16-bit residual)", dict(res1=res))):
+                st = ops.new_stats(b, cout, DEV, replicas=4)
+                report(f"{name} {cin}->{cout} padded out, {tag}",
+                       ops.conv3x3(a, wm, b, h, w, bias=bias, out_bf16=out, pad_out=True, stats=st,
+                                   stats_rows_per_image=(h + 2) * (w + 2), stats_group=min(8, cout // 32), **kw))
+        sys.exit(0)
     if only == "up":           # the VAE decoder's three "nearest 2x + 3x3 conv" layers (four per-parity 2x2 convs each), 16 images
         for h, w, cin, cout in ((60, 80, 512, 512), (120, 160, 512, 512), (240, 320, 256, 256)):
             b = 16
