@@ -229,11 +229,15 @@ __device__ __forceinline__ void epilogue_prepare(const GemmKParams& p, int64_t g
     map_row(p, grow, row_end, e.row_ok, e.orow, e.halo, map_img);
     e.halo = e.halo && (p.rowmap == SMTL_ROWMAP_PAD_KEEP);
     e.row_bias = (p.bias && p.bias_per_row && grow < p.m) ? __ldg(p.bias + grow) : 0.0f;
-    e.bias_ofs = p.group_rows ? (grow / p.group_rows) * p.n : 0;
+    // this tile's weight group.  Rows past the end of the tile's valid rows (the tail of a group that is not a whole
+    // number of tiles -- past the end of the MATRIX for the last group) take the group of the last valid row: their
+    // results are never stored, but the bias they index must exist.
+    const int64_t grow_c = grow < row_end ? grow : row_end - 1;
+    e.bias_ofs = p.group_rows ? (grow_c / p.group_rows) * p.n : 0;
 #pragma unroll
     for (int k = 0; k < BN / 32; ++k) {
         const int c = n0 + 32 * k + lane;
-        const int64_t gofs = p.group_rows ? (grow / p.group_rows) * p.n : 0;       // this tile's weight group
+        const int64_t gofs = e.bias_ofs;
         e.bias[k] = (p.bias && !p.bias_per_row && c < p.n) ? __ldg(p.bias + gofs + c) : 0.0f;
     }
     // pull this row's residual lines into L2 while the MMAs of the tile run
