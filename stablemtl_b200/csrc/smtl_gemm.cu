@@ -13,6 +13,12 @@
 #include "smtl_common.cuh"
 #include "smtl_host.h"
 
+// The kernels are compiled in TWO translation units from this one file (build.sh / __graft_entry__.build()): the
+// default one holds the host code and the fp16 instantiations, -DSMTL_GEMM_BF16_PART the bf16 instantiations behind
+// this function -- 28 instantiations of the GEMM kernel in one ptxas run were three minutes of a four-file build.
+// cg: 1 / 2 = smtl_gemm_kernel<block_n, cg, BF16>, 3 = smtl_gemmT_kernel<BF16>; kp: GemmKParams of the launch.
+int smtl_detail_gemm_launch_bf16(int block_n, int cg, const void* kp, int grid, int smem_bytes, cudaStream_t stream);
+
 namespace {
 
 using namespace smtl;
@@ -1334,8 +1340,12 @@ int launch_gemm_fmt(const GemmKParams& kp, int grid, int smem_bytes, cudaStream_
 }
 template <int BN, int CG>
 int launch_gemm(const GemmKParams& kp, int grid, int smem_bytes, cudaStream_t stream) {
+#ifdef SMTL_GEMM_BF16_PART
+    return launch_gemm_fmt<BN, CG, FMT_BF16>(kp, grid, smem_bytes, stream);
+#else
     return kp.fmt == FMT_F16 ? launch_gemm_fmt<BN, CG, FMT_F16>(kp, grid, smem_bytes, stream)
-                             : launch_gemm_fmt<BN, CG, FMT_BF16>(kp, grid, smem_bytes, stream);
+                             : smtl_detail_gemm_launch_bf16(BN, CG, &kp, grid, smem_bytes, stream);
+#endif
 }
 
 template <int BN>
@@ -1369,6 +1379,29 @@ int pick_block_n(int n, int act, int total_kb) {
 
 }  // namespace
 
+#ifdef SMTL_GEMM_BF16_PART
+int smtl_detail_gemm_launch_bf16(int block_n, int cg, const void* kpv, int grid, int smem_bytes, cudaStream_t st) {
+    const GemmKParams& kp = *reinterpret_cast<const GemmKParams*>(kpv);
+    if (cg == 3) {
+        static std::atomic<uint64_t> attr_devs{0};
+        if (smtl_host::first_use_on_device(attr_devs))
+            SMTL_CHECK_CUDA(cudaFuncSetAttribute(smtl_gemmT_kernel<FMT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+        smtl_gemmT_kernel<FMT_BF16><<<grid, NUM_THREADS, smem_bytes, st>>>(kp);
+        SMTL_CHECK_CUDA(cudaGetLastError());
+        return SMTL_OK;
+    }
+    switch (block_n) {
+        case 32: return launch_gemm_cg<32>(kp, cg, grid, smem_bytes, st);
+        case 64: return launch_gemm_cg<64>(kp, cg, grid, smem_bytes, st);
+        case 128: return launch_gemm_cg<128>(kp, cg, grid, smem_bytes, st);
+        case 160: return launch_gemm_cg<160>(kp, cg, grid, smem_bytes, st);
+        case 192: return launch_gemm_cg<192>(kp, cg, grid, smem_bytes, st);
+        case 224: return launch_gemm_cg<224>(kp, cg, grid, smem_bytes, st);
+        case 256: return launch_gemm_cg<256>(kp, cg, grid, smem_bytes, st);
+        default: smtl_host::set_error("gemm_run: bad block_n %d", block_n); return SMTL_EINVAL;
+    }
+}
+#else
 extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
     SMTL_CHECK_ARG(a && op, "gemm_plan: NULL argument");
     SMTL_CHECK_ARG(a->a0 && a->b, "gemm_plan: NULL operand");
@@ -1687,13 +1720,11 @@ extern "C" int smtl_gemm_run(const smtl_gemm_op* op, void* stream) {
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (op->cta_group == 3) {
+        if (kp.fmt != FMT_F16) return smtl_detail_gemm_launch_bf16(0, 3, &kp, op->grid, op->smem_bytes, st);
         static std::atomic<uint64_t> attr_devs{0};
-        if (smtl_host::first_use_on_device(attr_devs)) {
+        if (smtl_host::first_use_on_device(attr_devs))
             SMTL_CHECK_CUDA(cudaFuncSetAttribute(smtl_gemmT_kernel<FMT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
-            SMTL_CHECK_CUDA(cudaFuncSetAttribute(smtl_gemmT_kernel<FMT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
-        }
-        if (kp.fmt == FMT_F16) smtl_gemmT_kernel<FMT_F16><<<op->grid, NUM_THREADS, op->smem_bytes, st>>>(kp);
-        else smtl_gemmT_kernel<FMT_BF16><<<op->grid, NUM_THREADS, op->smem_bytes, st>>>(kp);
+        smtl_gemmT_kernel<FMT_F16><<<op->grid, NUM_THREADS, op->smem_bytes, st>>>(kp);
         SMTL_CHECK_CUDA(cudaGetLastError());
         return SMTL_OK;
     }
@@ -1708,3 +1739,4 @@ extern "C" int smtl_gemm_run(const smtl_gemm_op* op, void* stream) {
         default: smtl_host::set_error("gemm_run: bad block_n %d", op->block_n); return SMTL_EINVAL;
     }
 }
+#endif  // SMTL_GEMM_BF16_PART
