@@ -150,3 +150,26 @@ def test_collapsed_cross_attention_tables_reproduce_attn2():
         got = prob @ bmt[:, :V].t() + w[p + ".o2.b"]
         assert float(prob.view(-1, H, n)[:, :, text[task].shape[0]:].abs().max() if text[task].shape[0] < n else 0.0) == 0.0
         assert ((got - ref).norm() / ref.norm()).item() < 2e-3, task                    # the tables are stored in 16 bits
+
+
+def test_stats_group_divides_every_groupnorm_group_that_reads_a_map():
+    """smtl_gemm_args.stats_group: the block size of shared statistics cells must divide the channels-per-group of every
+    GroupNorm over a map alone or over a concat of two maps of the plan's channel counts, and every concat offset."""
+    from stablemtl_b200.engine import _PlanBase
+    for cfg in (synth.SD2_UNET, synth.TINY_UNET):
+        c, G = cfg.block_out_channels, cfg.norm_num_groups
+        g = _PlanBase.stats_group_for(c, G)
+        assert g in (1, 2, 4, 8)
+        for a in c:
+            assert (a // G) % g == 0 and a % g == 0
+            for b in c:
+                assert ((a + b) // G) % g == 0                       # GroupNorm over cat([a, b]): group size and ...
+                for k in range(1, G):                                # ... every group boundary, as seen from either map
+                    edge = k * ((a + b) // G)
+                    assert edge % g == 0 and (edge - a) % g == 0
+    assert _PlanBase.stats_group_for(synth.SD2_UNET.block_out_channels, 32) == 2          # gcd(10, 20, 40, 40) -> 2
+    for cfg in (synth.SD2_VAE, synth.TINY_VAE):                      # the VAE has no concats: per map
+        for a in cfg.block_out_channels:
+            g = _PlanBase.stats_group_for([a], cfg.norm_num_groups)
+            assert g == min(8, a // cfg.norm_num_groups) and (a // cfg.norm_num_groups) % g == 0
+    assert _PlanBase.stats_group_for([100], 32) == 1                 # channels not divisible by the group count: per channel
