@@ -70,10 +70,9 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
         : "memory");
 }
 
-// (Measured and dropped in round 2: passing an "exp token" over named barriers between the two softmax warps of an SM
-// sub-partition, so that the two tiles' exponential phases run back to back instead of competing for the SFU.  ncu
-// shows the SFU 58 % and the tensor pipe 29 % busy, but the token changed nothing: 0.850 ms before and after on
-// 16 x 5 heads x 4800 tokens -- the two tiles already alternate; the gap is the serial ld / max / st / MMA round trip.)
+// (Measured and dropped in round 2, on the first d = 64 kernel -- two query tiles per CTA, one softmax warp of each per SM
+// sub-partition: passing an "exp token" over named barriers between those two warps so that their exponential phases run
+// back to back.  0.850 ms before and after; what fixed that kernel's lock-step was more, shorter streams: smtl_fattn4_kernel.)
 template <bool MASKED>
 __device__ __forceinline__ void softmax_tile(const FattnKParams& p, uint32_t t_s, int kv_valid, float& m_run,
                                              float& l_run, uint32_t t_o, bool have_o, int o_chunks = 2,

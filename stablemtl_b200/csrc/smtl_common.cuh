@@ -348,29 +348,12 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
         : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
     return d;
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
-// erf-GELU with erf from Abramowitz & Stegun 7.1.26 (|abs error| < 1.5e-7, far below the 16-bit rounding of the
-// value it produces): one rcp, one ex2 and 7 FMAs instead of libm erff's ~35 instructions in the GEMM epilogue
-__device__ __forceinline__ float gelu_erf_fast(float x) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    float t;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-    float pl = fmaf(t, 1.061405429f, -1.453152027f);
-    pl = fmaf(pl, t, 1.421413741f);
-    pl = fmaf(pl, t, -0.284496736f);
-    pl = fmaf(pl, t, 0.254829592f);
-    pl *= t;
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
-    const float erf_abs = fmaf(-pl, e, 1.0f);                 // erf(|x|/sqrt2)
-    const float half_x = 0.5f * x;
-    return fmaf(fabsf(half_x), erf_abs, half_x);               // 0.5 x (1 + sign(x) erf(|x|/sqrt2))
-}
 // erf-GELU for a PAIR on the FMA pipe alone (no SFU): gelu(x) = x * Phi(x), Phi(x) = 0.5 + xc * R(xc^2) with xc = x
 // clamped to +-4.5 (Phi(-4.5) = 3.4e-6) and R a degree-10 polynomial in t = 2 xc^2 / 4.5^2 - 1 (Chebyshev fit of
 // (Phi(x) - 0.5) / x, converted to the monomial basis in t: well conditioned in fp32).  |error| < 3e-6 for |x| <= 4.5 and
 // < 3e-6 * |x| beyond, far below the 16-bit rounding of the value.  Packed FFMA2: ~9 issue slots per element against
-// 15 + 2 SFU ops for gelu_erf_fast -- the GEGLU / per-task MLP epilogues are issue- and SFU-bound at K = 320.
+// 15 + 2 SFU ops (rcp, ex2) for the Abramowitz-Stegun erf it replaced -- the GEGLU / per-task MLP epilogues are
+// issue- and SFU-bound at K = 320.
 __device__ __forceinline__ float2 gelu_poly2(float2 x) {
     float2 xc;
     xc.x = fminf(fmaxf(x.x, -4.5f), 4.5f);
