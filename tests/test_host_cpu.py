@@ -173,3 +173,28 @@ def test_stats_group_divides_every_groupnorm_group_that_reads_a_map():
             g = _PlanBase.stats_group_for([a], cfg.norm_num_groups)
             assert g == min(8, a // cfg.norm_num_groups) and (a // cfg.norm_num_groups) % g == 0
     assert _PlanBase.stats_group_for([100], 32) == 1                 # channels not divisible by the group count: per channel
+
+
+def test_polynomial_gelu_coefficients_in_the_kernel_source():
+    """gelu_poly2 (csrc/smtl_common.cuh): the coefficients compiled into the GEMM epilogues, evaluated here in fp32 exactly
+    as the kernel does (clamp, t = 2 x^2 / 4.5^2 - 1, Horner, 0.5 + x_c R, x Phi), against erf-GELU in fp64."""
+    import re
+    import numpy as np
+    src = open(os.path.join(ROOT, "stablemtl_b200", "csrc", "smtl_common.cuh")).read()
+    body = src[src.index("float2 gelu_poly2(float2 x)"):]
+    body = body[:body.index("#undef SMTL_C2")]
+    coef = [np.float32(c) for c in re.findall(r"SMTL_C2\((-?[0-9.eE+-]+)f\)", body)]
+    assert len(coef) == 12 and coef[-1] == np.float32(0.5)          # 11 polynomial coefficients (degree 10) + the 0.5 of Phi
+    x = np.linspace(-12, 12, 480001).astype(np.float32)
+    xc = np.clip(x, np.float32(-4.5), np.float32(4.5))
+    t = (xc * xc * np.float32(2.0 / (4.5 * 4.5)) - np.float32(1.0)).astype(np.float32)
+    r = (t * coef[0] + coef[1]).astype(np.float32)
+    for c in coef[2:11]:
+        r = (r * t + c).astype(np.float32)
+    g = (x * (xc * r + np.float32(0.5)).astype(np.float32)).astype(np.float32)
+    xd = x.astype(np.float64)
+    ref = xd * 0.5 * (1.0 + np.vectorize(__import__("math").erf)(xd / np.sqrt(2.0)))
+    err = np.abs(g - ref)
+    inside = np.abs(xd) <= 4.5
+    assert err[inside].max() < 5e-6, err[inside].max()
+    assert (err[~inside] < 5e-6 * np.abs(xd[~inside])).all()
