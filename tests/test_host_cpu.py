@@ -198,3 +198,30 @@ def test_polynomial_gelu_coefficients_in_the_kernel_source():
     inside = np.abs(xd) <= 4.5
     assert err[inside].max() < 5e-6, err[inside].max()
     assert (err[~inside] < 5e-6 * np.abs(xd[~inside])).all()
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 8, 16, 32])
+def test_transposing_warp_reduction_index_map(n):
+    """warp_transpose_sum_n (csrc/smtl_common.cuh), restated lane by lane: after log2(n) halving stages on lane bits
+    4, 3, ... and a butterfly over the rest, lane L holds the warp total of value L // (32 // n) -- the rule the GEMM
+    epilogue relies on when it lets lane L (L % G == 0) update the statistics cell of column ocol + L."""
+    import numpy as np
+    rng = np.random.default_rng(n)
+    s = rng.standard_normal((32, n))
+    ref = s.sum(0)
+    lanes = np.arange(32)
+    off, cnt = 16, n // 2
+    cur = s.copy()
+    while cnt >= 1:
+        upper = (lanes & off) != 0
+        nxt = cur.copy()
+        for i in range(cnt):
+            mine = np.where(upper, cur[:, i + cnt], cur[:, i])
+            other = np.where(upper, cur[:, i], cur[:, i + cnt])
+            nxt[:, i] = mine + other[lanes ^ off]                    # __shfl_xor_sync(other, off)
+        cur, off, cnt = nxt, off >> 1, cnt >> 1
+    while off >= 1:
+        cur[:, 0] = cur[:, 0] + cur[lanes ^ off, 0]
+        off >>= 1
+    got = cur[:, 0]
+    assert np.allclose(got, ref[lanes // (32 // n)])
