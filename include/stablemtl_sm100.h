@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SMTL_ABI_VERSION 2
+#define SMTL_ABI_VERSION 3
 
 enum {
     SMTL_OK = 0,
