@@ -115,7 +115,8 @@ typedef struct smtl_gemm_args {
     /* Grouped GEMM (the per-task MLPs of the task attention, src/util/model.py:102-138): rows
      * [g * group_rows, (g+1) * group_rows) use weight rows [g * n, (g+1) * n) of b (stacked [groups * n, k]) and bias
      * [g * n, (g+1) * n).  group_rows must divide m; when it is not a multiple of the 128-row tile the M tiles restart at
-     * every group (like the image-aligned tiles of the statistics producers).  0 = off. */
+     * every group (like the image-aligned tiles of the statistics producers).  Single CTAs only (cta_group 0 / 1).
+     * 0 = off. */
     int64_t group_rows;
     /* Tile order of the persistent CTAs: 0 = auto; 1 = round robin, column tile fastest; 2 = every CTA a contiguous run of
      * the column-tile-major order (auto picks 2 for statistics producers: their per-column sums stay on chip for a whole

@@ -1567,6 +1567,7 @@ extern "C" int smtl_gemm_plan(const smtl_gemm_args* a, smtl_gemm_op* op) {
         if (g.group_rows) cg = 1;
     }
     SMTL_CHECK_ARG(cg == 1 || cg == 2, "gemm_plan: cta_group %d", cg);
+    SMTL_CHECK_ARG(!(g.group_rows && cg == 2), "gemm_plan: a grouped GEMM runs on single CTAs (cta_group 0 or 1)");
     SMTL_CHECK_ARG(cg == 1 || bn % 16 == 0, "gemm_plan: cta_group 2 needs block_n %% 16 == 0");
     // Image-aligned tiles of SMALL maps under a pair: 256-row tiles pad them badly, so the two CTAs take two consecutive
     // 128-row tiles of the 128-row tiling instead (GemmKParams::pair_split) -- the padding of single CTAs with the weight
